@@ -1,0 +1,127 @@
+/* cwg.h - C ABI of the B200 (sm_100a) WaveGlow inverse pass.
+ *
+ * This is the drop-in boundary for the reference's mel->wave hot path
+ *   CookieTTS/_4_mtw/waveglow/glow.py:314-350   WaveGlow.infer(spect, speaker_id, sigma)
+ * and the functions it calls (WN.forward :188-222, Invertible1x1Conv.forward(reverse=True)
+ * :85-99, fused_add_tanh_sigmoid_multiply :34-41).  The reference has no FFI of its own
+ * (pure Python on torch); the binding a maintainer adds is the ctypes stub in
+ * INTEGRATION.md, which is what cookietts_b200/_cabi.py does.
+ *
+ * Conventions
+ *  - Every pointer in cwg_weights / cwg_infer is a DEVICE pointer owned by the caller.
+ *    The library allocates nothing, keeps no mutable global state except the last error
+ *    string (thread local), never synchronises the host, and enqueues all work on the
+ *    stream it is given.
+ *  - Return value: 0 on success, non-zero on error; cwg_last_error() describes it.
+ *  - Layouts: mel [B, n_mel, T_mel] fp32 (the reference layout); z and audio [B, T] fp32 with
+ *    T = T_mel*hop; latent channel c of group-step s is z[b, s*n_group + c], channels ordered
+ *    as the reference stacks them at the end of infer (early outputs of the lowest flow
+ *    first, the main latent last; glow.py:326,342-347).
+ *  - Packed weights are produced by cookietts_b200/packing.py (weight-norm folded, the
+ *    linear cond chain folded with the transposed-conv upsampler, `end` folded into the
+ *    skip half of res_skip; see DESIGN.md "Packed weights").
+ */
+#ifndef CWG_H
+#define CWG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CWG_ABI_VERSION 1
+
+/* Arithmetic modes of the WN contractions. */
+#define CWG_MODE_FFMA   0   /* fp32 weights/activations, CUDA-core FFMA (exact fp32 semantics)        */
+#define CWG_MODE_BF16X3 1   /* tcgen05 bf16 MMA, operands split hi+lo, 3 products, fp32 accumulate   */
+#define CWG_MODE_BF16   2   /* tcgen05 bf16 MMA, single product, fp32 accumulate + hi/lo residual    */
+
+#define CWG_EO_PAD 16       /* padded width of the folded `end` output (2*n_half <= 16)              */
+#define CWG_MAX_GROUP 16    /* n_group <= 16                                                         */
+
+/* Mirrors the constructor arguments of the reference WaveGlow (glow.py:226-227) and
+ * WN_config (glow.py:116-117) that the inverse pass depends on. */
+typedef struct cwg_config {
+  int32_t n_mel;          /* n_mel_channels                                   */
+  int32_t n_flows;
+  int32_t n_group;
+  int32_t n_early_every;
+  int32_t n_early_size;
+  int32_t win_length;     /* ConvTranspose1d kernel                           */
+  int32_t hop_length;     /* ConvTranspose1d stride                           */
+  int32_t n_layers;       /* WN layers L                                      */
+  int32_t n_channels;     /* WN channels C                                    */
+  int32_t kernel_size;    /* WN dilated conv taps (odd)                       */
+  int32_t cond_hidden;    /* H: width of the folded cond chain output (256)   */
+} cwg_config;
+
+/* Device pointers to the packed weights.  F = n_flows, L = n_layers, C = n_channels,
+ * H = cond_hidden, P = hop/n_group, J = ceil(win/hop), M = n_mel, K1 = kernel_size*C + H,
+ * N2 = C + CWG_EO_PAD.  fp32 arrays are used by CWG_MODE_FFMA, the bf16 hi/lo planes by the
+ * tensor-core modes (lo = bf16(w - float(hi))); unused ones may be NULL. */
+typedef struct cwg_weights {
+  const float*    cond_w_f32;   /* [F][P*H][J*M]   row p*H+h, col j*M+ci               */
+  const uint16_t* cond_w_hi;    /* same, bf16                                          */
+  const uint16_t* cond_w_lo;
+  const float*    w1_f32;       /* [F][L][2C][K1]  col tap*C+c | kernel_size*C+h        */
+  const uint16_t* w1_hi;
+  const uint16_t* w1_lo;
+  const float*    b1;           /* [F][L][2C]      in_layer bias + cond_layers.2 bias   */
+  const float*    w2_f32;       /* [F][L][N2][C]   rows <C: res, rows >=C: end*skip     */
+  const uint16_t* w2_hi;
+  const uint16_t* w2_lo;
+  const float*    b2;           /* [F][L][C]       res bias (0 for the last layer)      */
+  const float*    eo_b;         /* [F][CWG_EO_PAD] end bias + end*(sum of skip biases)  */
+  const float*    start_w;      /* [F][C][CWG_MAX_GROUP/2]                              */
+  const float*    start_b;      /* [F][C]                                               */
+  const float*    winv;         /* [F][CWG_MAX_GROUP][CWG_MAX_GROUP]  W^-1, row major   */
+} cwg_weights;
+
+int         cwg_abi_version(void);
+const char* cwg_last_error(void);
+
+/* Bytes of device workspace cwg_infer needs for (batch, t_mel) in `mode`. 0 on error. */
+size_t cwg_workspace_bytes(const cwg_config* cfg, int mode, int batch, int t_mel);
+
+/* WaveGlow.infer with explicit latent (glow.py:314-350).
+ *   mel        [batch][n_mel][t_mel] fp32
+ *   cond_bias  [batch][F][H] fp32: folded cond-chain bias per utterance (carries the speaker
+ *              embedding branch glow.py:193-196 when speaker_embed_dim > 0)
+ *   z          [batch][t_mel*hop] fp32 standard normal
+ *   audio      [batch][t_mel*hop] fp32 out
+ * All work is enqueued on `cuda_stream` (a cudaStream_t). */
+int cwg_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
+              const float* mel, const float* cond_bias, const float* z, float sigma,
+              float* audio, void* workspace, size_t workspace_bytes,
+              int batch, int t_mel, void* cuda_stream);
+
+/* Number of kernels cwg_infer launches for this configuration (bench.py's gpu_launches). */
+int cwg_launch_count(const cwg_config* cfg, int mode);
+
+/* ---- stage-level entry points (tests bisect the pipeline with these) ---------------- */
+
+/* Folded cond chain for one flow: H2 [batch][T'][H] (fp32 in FFMA mode; bf16 hi/lo planes,
+ * hi first then lo, each [batch][T'][H], in the tensor-core modes). */
+int cwg_cond(const cwg_config* cfg, const cwg_weights* w, int mode, int flow,
+             const float* mel, const float* cond_bias, void* h2_out,
+             void* workspace, size_t workspace_bytes, int batch, int t_mel, void* cuda_stream);
+
+/* One WN layer: x_in -> x_out (fp32 [batch][T'][C] in FFMA mode; hi/lo bf16 planes otherwise),
+ * eo [batch][T'][CWG_EO_PAD] fp32 accumulated (written when layer == 0). */
+int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow, int layer,
+                 const void* x_in, void* x_out, const void* h2, float* eo,
+                 void* workspace, size_t workspace_bytes, int batch, int t_mel, void* cuda_stream);
+
+/* Flow boundary: optional init (audio = sigma*z), optional coupling + W^-1 of flow `flow_done`
+ * (glow.py:329-340) and optional `start` conv of flow `flow_next` (glow.py:189). -1 disables. */
+int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,
+                      int flow_done, int flow_next, const float* z, float sigma,
+                      float* audio, const float* eo, void* x_out,
+                      int batch, int t_mel, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWG_H */

@@ -1,0 +1,83 @@
+"""numpy evaluation of the PACKED weight form (tests only).
+
+Executable statement of what the CUDA kernels compute from `cwg_weights`
+(cookietts_b200/packing.py): channels-last activations, folded cond chain, folded `end`,
+audio state updated in place inside the [B, T] output buffer.  Used to prove on CPU that
+the packing algebra reproduces the reference (via the golden vectors) before any kernel runs,
+and with `emulate='bf16'/'bf16x3'` to predict the tensor-core modes' error.
+"""
+import numpy as np
+
+from cookietts_b200.packing import PackConfig, bf16_bits_to_f32, f32_to_bf16_bits, EO_PAD
+
+
+def _round_bf16(x):
+    return bf16_bits_to_f32(f32_to_bf16_bits(x.astype(np.float32))).astype(np.float64)
+
+
+def _split(x):
+    hi = _round_bf16(x)
+    lo = _round_bf16(x - hi)
+    return hi, lo
+
+
+def _mm(a, w, emulate):
+    """a [rows, K] @ w[N, K]^T with the operand rounding of the chosen mode.
+    w is (w_full, w_hi, w_lo)."""
+    w_full, w_hi, w_lo = w
+    if emulate is None:
+        return a @ w_full.T
+    a_hi, a_lo = _split(a)
+    if emulate == "bf16":
+        return a_hi @ w_hi.T
+    return a_hi @ w_hi.T + a_lo @ w_hi.T + a_hi @ w_lo.T     # bf16x3
+
+
+def packed_infer(pk, cfg: PackConfig, mel, z, sigma, emulate=None, cond_bias=None):
+    B, M, Tm = mel.shape
+    G, C, L, H, P, J, ks = cfg.n_group, cfg.n_channels, cfg.n_layers, cfg.cond_hidden, cfg.phases, cfg.taps, cfg.kernel_size
+    Tp = Tm * P
+    mel = mel.astype(np.float64)
+
+    def W(name, *idx):
+        if emulate is None:
+            full = pk[name + "_f32"][idx].astype(np.float64)
+            return (full, None, None)
+        hi = bf16_bits_to_f32(pk[name + "_hi"][idx]).astype(np.float64)
+        lo = bf16_bits_to_f32(pk[name + "_lo"][idx]).astype(np.float64)
+        return (None, hi, lo)
+
+    # mel4[b, f, j*M + ci] = mel[b, ci, f - j]
+    mel4 = np.zeros((B, Tm, J * M))
+    for j in range(J):
+        mel4[:, j:, j * M:(j + 1) * M] = mel.transpose(0, 2, 1)[:, :Tm - j]
+    audio = (np.float64(sigma) * z.astype(np.float64)).reshape(B, Tp, G).copy()   # state == output buffer
+    if cond_bias is None:
+        cond_bias = np.broadcast_to(pk["cond_b_base"].astype(np.float64)[None], (B, cfg.n_flows, H))
+    fc = cfg.flow_channels()
+    for k in reversed(range(cfg.n_flows)):
+        n_rem, n_half = fc[k]
+        off = G - n_rem
+        # cond GEMM: H2[b, f*P + p, h]
+        h2 = _mm(mel4.reshape(B * Tm, J * M), W("cond_w", k), emulate).reshape(B, Tm, P, H)
+        h2 = h2.reshape(B, Tp, H) + cond_bias[:, k][:, None, :]
+        # start
+        a0 = audio[:, :, off:off + n_half]
+        x = a0 @ pk["start_w"][k][:, :n_half].astype(np.float64).T + pk["start_b"][k].astype(np.float64)
+        eo = np.tile(pk["eo_b"][k].astype(np.float64), (B, Tp, 1))
+        for i in range(L):
+            d = 2 ** i
+            xp = np.zeros((B, Tp + 2 * d * (ks // 2), C))
+            xp[:, d * (ks // 2):d * (ks // 2) + Tp] = x
+            a = np.concatenate([xp[:, tap * d:tap * d + Tp] for tap in range(ks)] + [h2], axis=2)  # [B,T',K1]
+            pre = _mm(a.reshape(B * Tp, -1), W("w1", k, i), emulate) + pk["b1"][k, i].astype(np.float64)
+            acts = np.tanh(pre[:, :C]) / (1.0 + np.exp(-pre[:, C:]))
+            rs = _mm(acts, W("w2", k, i), emulate).reshape(B, Tp, C + EO_PAD)
+            if i < L - 1:
+                x = x + rs[:, :, :C] + pk["b2"][k, i].astype(np.float64)
+            eo = eo + rs[:, :, C:]
+        b, s = eo[:, :, :n_half], eo[:, :, n_half:2 * n_half]
+        a1 = (audio[:, :, off + n_half:] - b) * np.exp(-s)
+        v = np.concatenate([a0, a1], axis=2)
+        audio[:, :, off:] = v @ pk["winv"][k][:n_rem, :n_rem].astype(np.float64).T
+    return audio.reshape(B, Tp * G)
