@@ -1,0 +1,96 @@
+"""ctypes binding of libcwg.so (include/cwg.h).
+
+The product path has NO fallback: if the shared library is missing or a symbol is absent,
+importing the binding raises.  Build it with `python __graft_entry__.py` (or
+`make -C cookietts_b200/csrc`)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcwg.so")
+
+MODE_FFMA, MODE_BF16X3, MODE_BF16 = 0, 1, 2
+MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+EO_PAD = 16
+MAX_GROUP = 16
+ABI_VERSION = 1
+
+
+class CwgConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_mel", "n_flows", "n_group", "n_early_every", "n_early_size", "win_length",
+        "hop_length", "n_layers", "n_channels", "kernel_size", "cond_hidden")]
+
+
+WEIGHT_FIELDS = ("cond_w_f32", "cond_w_hi", "cond_w_lo", "w1_f32", "w1_hi", "w1_lo", "b1",
+                 "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv")
+
+
+class CwgWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
+           "cwg_infer", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary")
+
+
+class CwgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libcwg.so once; raises if it is missing (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CwgError(f"{LIB_PATH} not found - build the CUDA extension first "
+                       f"(python -c 'import __graft_entry__ as g; g.build()')")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise CwgError(f"libcwg.so does not export {name}")
+    lib.cwg_abi_version.restype = C.c_int
+    lib.cwg_last_error.restype = C.c_char_p
+    lib.cwg_workspace_bytes.restype = C.c_size_t
+    lib.cwg_workspace_bytes.argtypes = [C.POINTER(CwgConfig), C.c_int, C.c_int, C.c_int]
+    lib.cwg_launch_count.restype = C.c_int
+    lib.cwg_launch_count.argtypes = [C.POINTER(CwgConfig), C.c_int]
+    lib.cwg_infer.restype = C.c_int
+    lib.cwg_infer.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_cond.restype = C.c_int
+    lib.cwg_cond.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int, C.c_int,
+                             C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_wn_layer.restype = C.c_int
+    lib.cwg_wn_layer.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_flow_boundary.restype = C.c_int
+    lib.cwg_flow_boundary.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p]
+    if lib.cwg_abi_version() != ABI_VERSION:
+        raise CwgError(f"libcwg.so ABI {lib.cwg_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise CwgError(f"libcwg error {rc}: {load().cwg_last_error().decode()}")
+
+
+def make_config(pc) -> CwgConfig:
+    return CwgConfig(n_mel=pc.n_mel, n_flows=pc.n_flows, n_group=pc.n_group,
+                     n_early_every=pc.n_early_every, n_early_size=pc.n_early_size,
+                     win_length=pc.win_length, hop_length=pc.hop_length, n_layers=pc.n_layers,
+                     n_channels=pc.n_channels, kernel_size=pc.kernel_size, cond_hidden=pc.cond_hidden)

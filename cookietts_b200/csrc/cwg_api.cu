@@ -1,0 +1,205 @@
+// extern "C" entry points of libcwg (see include/cwg.h): argument checks, workspace carving and
+// the launch sequence of WaveGlow.infer (glow.py:314-350).  No allocation, no host sync.
+#include "cwg_common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace cwg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct Workspace {
+  // FFMA mode
+  float *x[2], *h2, *pre, *acts;
+  // tensor-core modes (each: hi plane then lo plane)
+  __nv_bfloat16 *xb[2], *h2b, *mel4;
+  float* eo;
+  size_t bytes;
+};
+
+int check_config(const cwg_config* c) {
+  CWG_REQUIRE(c != nullptr, "cfg is NULL");
+  CWG_REQUIRE(c->n_group % 2 == 0 && c->n_group >= 2 && c->n_group <= CWG_MAX_GROUP,
+              "n_group must be even and <= %d", CWG_MAX_GROUP);
+  CWG_REQUIRE(c->hop_length > 0 && c->hop_length % c->n_group == 0, "hop_length must be a multiple of n_group");
+  CWG_REQUIRE(c->win_length >= c->hop_length, "win_length < hop_length");
+  CWG_REQUIRE(c->kernel_size % 2 == 1, "kernel_size must be odd");
+  CWG_REQUIRE(c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_flows / n_layers");
+  CWG_REQUIRE(c->n_channels >= 2 && c->n_mel >= 1 && c->cond_hidden >= 1, "bad channel counts");
+  CWG_REQUIRE(c->n_early_every >= 1 && c->n_early_size % 2 == 0, "bad early-output settings");
+  int n_rem, n_half;
+  flow_channels(c, c->n_flows - 1, &n_rem, &n_half);
+  CWG_REQUIRE(n_half >= 1, "too many early outputs for n_group");
+  return 0;
+}
+
+int check_mode(const cwg_config* c, int mode) {
+  CWG_REQUIRE(mode == CWG_MODE_FFMA || mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16, "unknown mode %d", mode);
+  if (mode != CWG_MODE_FFMA) {
+    CWG_REQUIRE(c->n_channels == 256 && c->cond_hidden == 256 && c->kernel_size == 3,
+                "tensor-core modes are built for n_channels=256, cond_hidden=256, kernel_size=3 "
+                "(got %d, %d, %d); use CWG_MODE_FFMA", c->n_channels, c->cond_hidden, c->kernel_size);
+    CWG_REQUIRE((c->n_mel * ((c->win_length + c->hop_length - 1) / c->hop_length)) % 64 == 0,
+                "tensor-core modes need n_mel * ceil(win/hop) to be a multiple of 64");
+  }
+  return 0;
+}
+
+void carve(const Dims& d, int mode, void* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return (char*)base + o; };
+  memset(ws, 0, sizeof(*ws));
+  ws->eo = (float*)take((size_t)d.BT * CWG_EO_PAD * sizeof(float));
+  if (mode == CWG_MODE_FFMA) {
+    ws->x[0] = (float*)take((size_t)d.BT * d.C * 4);
+    ws->x[1] = (float*)take((size_t)d.BT * d.C * 4);
+    ws->h2 = (float*)take((size_t)d.BT * d.H * 4);
+    ws->pre = (float*)take((size_t)d.BT * 2 * d.C * 4);
+    ws->acts = (float*)take((size_t)d.BT * d.C * 4);
+  } else {
+    ws->xb[0] = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
+    ws->xb[1] = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
+    ws->h2b = (__nv_bfloat16*)take((size_t)d.BT * d.H * 2 * 2);
+    ws->mel4 = (__nv_bfloat16*)take((size_t)d.B * d.Tm * d.KC * 2 * 2);
+  }
+  ws->bytes = off;
+}
+
+int check_run(const cwg_config* cfg, const cwg_weights* w, int mode, int batch, int t_mel) {
+  if (int r = check_config(cfg)) return r;
+  if (int r = check_mode(cfg, mode)) return r;
+  CWG_REQUIRE(w != nullptr, "weights is NULL");
+  CWG_REQUIRE(batch >= 1 && t_mel >= 1, "batch and t_mel must be >= 1");
+  CWG_REQUIRE((long long)batch * t_mel * (cfg->hop_length / cfg->n_group) < (1ll << 31) / 4,
+              "batch * T' too large for one call; split the batch");
+  CWG_REQUIRE(w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b && w->winv, "missing weight arrays");
+  if (mode == CWG_MODE_FFMA) CWG_REQUIRE(w->cond_w_f32 && w->w1_f32 && w->w2_f32, "fp32 weight planes missing");
+  else CWG_REQUIRE(w->cond_w_hi && w->w1_hi && w->w2_hi && w->cond_w_lo && w->w1_lo && w->w2_lo,
+                   "bf16 hi/lo weight planes missing");
+  return 0;
+}
+
+}  // namespace
+}  // namespace cwg
+
+using namespace cwg;
+
+extern "C" {
+
+int cwg_abi_version(void) { return CWG_ABI_VERSION; }
+
+const char* cwg_last_error(void) { return cwg::g_err; }
+
+size_t cwg_workspace_bytes(const cwg_config* cfg, int mode, int batch, int t_mel) {
+  if (check_config(cfg) || check_mode(cfg, mode) || batch < 1 || t_mel < 1) return 0;
+  Dims d = make_dims(cfg, batch, t_mel);
+  Workspace ws;
+  carve(d, mode, nullptr, &ws);
+  return ws.bytes + 1024;
+}
+
+int cwg_launch_count(const cwg_config* cfg, int mode) {
+  if (check_config(cfg) || check_mode(cfg, mode)) return -1;
+  // per flow: cond (+ mel4 build in tensor modes), L layers, one boundary; plus the initial boundary
+  int per_layer = mode == CWG_MODE_FFMA ? 3 : 1;
+  int cond = mode == CWG_MODE_FFMA ? 1 : 1;
+  int once = mode == CWG_MODE_FFMA ? 1 : 2;   // init boundary (+ mel4 im2col)
+  return once + cfg->n_flows * (cond + per_layer * cfg->n_layers + 1);
+}
+
+int cwg_cond(const cwg_config* cfg, const cwg_weights* w, int mode, int flow,
+             const float* mel, const float* cond_bias, void* h2_out,
+             void* workspace, size_t workspace_bytes, int batch, int t_mel, void* cuda_stream) {
+  if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
+  CWG_REQUIRE(flow >= 0 && flow < cfg->n_flows, "flow out of range");
+  Dims d = make_dims(cfg, batch, t_mel);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (mode == CWG_MODE_FFMA) return launch_cond_ffma(d, w, flow, mel, cond_bias, (float*)h2_out, s);
+  Workspace ws;
+  CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
+  carve(d, mode, workspace, &ws);
+  CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+  return launch_cond_tc(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, mel, cond_bias,
+                        (__nv_bfloat16*)h2_out, ws.mel4, s);
+}
+
+int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow, int layer,
+                 const void* x_in, void* x_out, const void* h2, float* eo,
+                 void* workspace, size_t workspace_bytes, int batch, int t_mel, void* cuda_stream) {
+  if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
+  CWG_REQUIRE(flow >= 0 && flow < cfg->n_flows && layer >= 0 && layer < cfg->n_layers, "flow/layer out of range");
+  Dims d = make_dims(cfg, batch, t_mel);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (mode == CWG_MODE_FFMA) {
+    Workspace ws;
+    CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
+    carve(d, mode, workspace, &ws);
+    CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+    return launch_layer_ffma(d, w, flow, layer, (const float*)x_in, (float*)x_out, (const float*)h2, eo,
+                             ws.pre, ws.acts, s);
+  }
+  return launch_layer_tc(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, layer, (const __nv_bfloat16*)x_in,
+                         (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, eo, s);
+}
+
+int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,
+                      int flow_done, int flow_next, const float* z, float sigma,
+                      float* audio, const float* eo, void* x_out,
+                      int batch, int t_mel, void* cuda_stream) {
+  if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
+  CWG_REQUIRE(flow_done < cfg->n_flows && flow_next < cfg->n_flows, "flow out of range");
+  Dims d = make_dims(cfg, batch, t_mel);
+  return launch_flow_boundary(cfg, d, w, mode == CWG_MODE_FFMA ? 0 : 1, flow_done, flow_next, z, sigma,
+                              audio, eo, x_out, (cudaStream_t)cuda_stream);
+}
+
+int cwg_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
+              const float* mel, const float* cond_bias, const float* z, float sigma,
+              float* audio, void* workspace, size_t workspace_bytes,
+              int batch, int t_mel, void* cuda_stream) {
+  if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
+  CWG_REQUIRE(mel && cond_bias && z && audio, "NULL tensor argument");
+  CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
+  Dims d = make_dims(cfg, batch, t_mel);
+  Workspace ws;
+  carve(d, mode, workspace, &ws);
+  CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool tc = mode != CWG_MODE_FFMA;
+  const int npass = mode == CWG_MODE_BF16X3 ? 3 : 1;
+  const int xfmt = tc ? 1 : 0;
+  const int F = cfg->n_flows, L = cfg->n_layers;
+
+  // audio = sigma * z (glow.py:326; early z already sits in its final columns), x = start_{F-1}(audio_0)
+  void* x0 = tc ? (void*)ws.xb[0] : (void*)ws.x[0];
+  if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s)) return r;
+  for (int k = F - 1; k >= 0; --k) {                       // glow.py:328
+    if (tc) {
+      if (int r = launch_cond_tc(d, w, npass, k, k == F - 1 ? mel : nullptr, cond_bias, ws.h2b, ws.mel4, s)) return r;
+    } else {
+      if (int r = launch_cond_ffma(d, w, k, mel, cond_bias, ws.h2, s)) return r;
+    }
+    for (int i = 0; i < L; ++i) {                          // glow.py:201-220
+      if (tc) {
+        if (int r = launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s)) return r;
+      } else {
+        if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
+      }
+    }
+    // coupling inverse + W^-1 of flow k, then start conv of flow k-1 (glow.py:329-347, :189)
+    if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s)) return r;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Shared declarations for the cwg (CookieTTS WaveGlow, B200) kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cwg.h"
+
+namespace cwg {
+
+// Derived problem dimensions (all in elements).
+struct Dims {
+  int B, Tm, Tp;        // batch, mel frames, group-steps T' = Tm * P
+  int F, L, C, H;       // flows, WN layers, WN channels, cond hidden
+  int G, M, P, J, ks;   // n_group, n_mel, phases hop/G, upsampler taps, WN kernel size
+  int K1, N2, KC;       // ks*C + H, C + CWG_EO_PAD, J*M
+  long long BT;         // B * Tp
+};
+
+inline Dims make_dims(const cwg_config* c, int batch, int t_mel) {
+  Dims d;
+  d.B = batch; d.Tm = t_mel;
+  d.F = c->n_flows; d.L = c->n_layers; d.C = c->n_channels; d.H = c->cond_hidden;
+  d.G = c->n_group; d.M = c->n_mel; d.P = c->hop_length / c->n_group;
+  d.J = (c->win_length + c->hop_length - 1) / c->hop_length; d.ks = c->kernel_size;
+  d.Tp = t_mel * d.P;
+  d.K1 = d.ks * d.C + d.H; d.N2 = d.C + CWG_EO_PAD; d.KC = d.J * d.M;
+  d.BT = (long long)batch * d.Tp;
+  return d;
+}
+
+// (n_remaining_channels, n_half) of flow k; glow.py:251-264.
+inline void flow_channels(const cwg_config* c, int k, int* n_rem, int* n_half) {
+  int nh = c->n_group / 2, nr = c->n_group;
+  for (int j = 1; j <= k; ++j)
+    if (j % c->n_early_every == 0) { nh -= c->n_early_size / 2; nr -= c->n_early_size; }
+  *n_rem = nr; *n_half = nh;
+}
+
+void set_error(const char* fmt, ...);
+
+#define CWG_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      cwg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+#define CWG_REQUIRE(cond, ...)                  \
+  do {                                          \
+    if (!(cond)) { cwg::set_error(__VA_ARGS__); return 2; } \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- launchers implemented in cwg_simple.cu (CUDA-core fp32 path + shared boundary kernels) ----
+int launch_cond_ffma(const Dims& d, const cwg_weights* w, int flow, const float* mel,
+                     const float* cond_bias, float* h2, cudaStream_t s);
+int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, const float* x_in,
+                      float* x_out, const float* h2, float* eo, float* pre, float* acts, cudaStream_t s);
+// xfmt: 0 = fp32 [BT][C]; 1 = bf16 hi plane followed by lo plane (each [BT][C])
+int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
+                         int flow_done, int flow_next, const float* z, float sigma, float* audio,
+                         const float* eo, void* x_out, cudaStream_t s);
+
+// ---- launchers implemented in cwg_tc.cu (tcgen05 / TMA path) ----
+int tc_workspace_extra(const Dims& d, size_t* bytes);
+int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, const float* mel,
+                   const float* cond_bias, __nv_bfloat16* h2_planes, __nv_bfloat16* mel4_planes,
+                   cudaStream_t s);
+int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
+                    const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
+                    float* eo, cudaStream_t s);
+
+}  // namespace cwg

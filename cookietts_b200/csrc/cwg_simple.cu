@@ -1,0 +1,264 @@
+// CUDA-core (fp32 FFMA) kernels of the WaveGlow inverse pass, plus the flow-boundary kernel
+// that both arithmetic modes share.  This path keeps exact fp32 semantics (CWG_MODE_FFMA) and
+// doubles as the on-device cross-check for the tcgen05 path in cwg_tc.cu.
+//
+// Reference lines implemented (CookieTTS/_4_mtw/waveglow/glow.py):
+//   cond GEMM        : upsample + squeeze + cond_layers[0..1]  :318-324, :198-199 (folded, see packing.py)
+//   layer GEMM1+gate : in_layers[i] + cond_layers[2] slice + fused_add_tanh_sigmoid_multiply :201-209, :34-41
+//   layer GEMM2      : res_skip_layers[i], residual/skip update, `end` (folded) :211-222
+//   flow boundary    : affine coupling inverse, W^-1, early-z concat, start conv :329-347, :189
+#include "cwg_common.cuh"
+
+namespace cwg {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+struct GemmP {
+  int M, N, K;
+  const float* W; int ldw;          // [N][ldw]
+  const float* a0; const float* a1; // A sources
+  int Tm, Tp, nmel, C, ks, dil, H;
+  float* o0; float* o1;
+  const float* bias; const float* bias2; const float* xin;
+  int bias_bstride;                 // cond: batch stride of the per-utterance bias
+  int has_res, first;
+};
+
+// A(m, kk) for the three GEMMs.
+template <int AMODE>
+__device__ __forceinline__ float load_a(const GemmP& p, int m, int kk) {
+  if (m >= p.M || kk >= p.K) return 0.f;
+  if (AMODE == 0) {             // mel4[b, f, j*nmel + ci] = mel[b, ci, f - j]
+    int b = m / p.Tm, f = m - b * p.Tm;
+    int j = kk / p.nmel, ci = kk - j * p.nmel;
+    int ff = f - j;
+    return ff >= 0 ? __ldg(p.a0 + ((size_t)b * p.nmel + ci) * p.Tm + ff) : 0.f;
+  } else if (AMODE == 1) {      // [x taps | h2]
+    int kx = p.ks * p.C;
+    if (kk < kx) {
+      int b = m / p.Tp, t = m - b * p.Tp;
+      int tap = kk / p.C, c = kk - tap * p.C;
+      int tt = t + (tap - p.ks / 2) * p.dil;
+      return (tt >= 0 && tt < p.Tp) ? __ldg(p.a0 + ((size_t)b * p.Tp + tt) * p.C + c) : 0.f;
+    }
+    return __ldg(p.a1 + (size_t)m * p.H + (kk - kx));
+  } else {
+    return __ldg(p.a0 + (size_t)m * p.K + kk);
+  }
+}
+
+template <int EMODE>
+__device__ __forceinline__ void store_c(const GemmP& p, int m, int n, float acc) {
+  if (m >= p.M || n >= p.N) return;
+  if (EMODE == 0) {             // H2[m][n] (+ per-utterance cond bias of channel n % H)
+    int b = m / p.Tm;
+    p.o0[(size_t)m * p.N + n] = acc + __ldg(p.bias + (size_t)b * p.bias_bstride + (n % p.H));
+  } else if (EMODE == 1) {      // pre-activation
+    p.o0[(size_t)m * p.N + n] = acc + __ldg(p.bias + n);
+  } else {                      // res / folded end
+    if (n < p.C) {
+      if (p.has_res) p.o0[(size_t)m * p.C + n] = __ldg(p.xin + (size_t)m * p.C + n) + acc + __ldg(p.bias + n);
+    } else {
+      int j = n - p.C;
+      float* e = p.o1 + (size_t)m * CWG_EO_PAD + j;
+      *e = (p.first ? __ldg(p.bias2 + j) : *e) + acc;
+    }
+  }
+}
+
+template <int AMODE, int EMODE>
+__global__ void __launch_bounds__(256) k_sgemm(GemmP p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  float acc[TM][TN] = {};
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / 256; ++r) {
+      int idx = tid + r * 256;
+      int row, kk;
+      if (AMODE == 0) { kk = idx / BM; row = idx % BM; } else { row = idx / BK; kk = idx % BK; }
+      As[kk][row] = load_a<AMODE>(p, m0 + row, k0 + kk);
+    }
+#pragma unroll
+    for (int r = 0; r < (BN * BK) / 256; ++r) {
+      int idx = tid + r * 256;
+      int n = idx / BK, kk = idx % BK;
+      Bs[kk][n] = (n0 + n < p.N && k0 + kk < p.K) ? __ldg(p.W + (size_t)(n0 + n) * p.ldw + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) store_c<EMODE>(p, m0 + ty * TM + i, n0 + tx * TN + j, acc[i][j]);
+}
+
+// acts[m][c] = tanh(pre[m][c]) * sigmoid(pre[m][C + c])   (glow.py:34-41)
+__global__ void k_gate(const float* __restrict__ pre, float* __restrict__ acts, long long n, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long m = i / C; int c = (int)(i - m * C);
+  float a = pre[m * 2 * C + c], b = pre[m * 2 * C + C + c];
+  acts[i] = tanhf(a) * (1.f / (1.f + expf(-b)));
+}
+
+constexpr int TB = 32;   // group-steps per block in the boundary kernel
+
+struct BoundaryP {
+  long long BT; int G, C;
+  int init, do_flow, do_start;
+  int n_rem, n_half;          // of flow_done
+  int n_rem2, n_half2;        // of flow_next
+  const float* z; float sigma;
+  float* audio; const float* eo;
+  const float* winv;          // [MAX_GROUP][MAX_GROUP] of flow_done
+  const float* start_w;       // [C][MAX_GROUP/2] of flow_next
+  const float* start_b;       // [C]
+  void* x_out;
+};
+
+// One block handles TB consecutive group-steps (rows of the [B*T'][G] audio state, which IS
+// the [B, T] output buffer: latent channel c of step s lives at audio[b, s*G + c], so the
+// early-z concat (glow.py:342-347) and the final un-squeeze (:349) are no-ops by layout).
+template <int XFMT>
+__global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
+  __shared__ float a_s[TB][CWG_MAX_GROUP];
+  const long long m0 = (long long)blockIdx.x * TB;
+  const int tid = threadIdx.x;
+  if (tid < TB) {
+    long long m = m0 + tid;
+    if (m < p.BT) {
+      float a[CWG_MAX_GROUP];
+      for (int g = 0; g < p.G; ++g)
+        a[g] = p.init ? p.sigma * p.z[m * p.G + g] : p.audio[m * p.G + g];
+      if (p.do_flow) {
+        const int off = p.G - p.n_rem;
+        const float* e = p.eo + m * CWG_EO_PAD;
+        float v[CWG_MAX_GROUP];
+        for (int j = 0; j < p.n_half; ++j) v[j] = a[off + j];
+        for (int j = 0; j < p.n_rem - p.n_half; ++j) {
+          // audio_1 = (audio_1 - b) / exp(s), glow.py:337
+          float b = e[j], s = e[p.n_half + j];
+          v[p.n_half + j] = (a[off + p.n_half + j] - b) * expf(-s);
+        }
+        for (int r = 0; r < p.n_rem; ++r) {           // z = conv1d(z, W^-1), glow.py:98
+          float acc = 0.f;
+          for (int c = 0; c < p.n_rem; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
+          a[off + r] = acc;
+        }
+      }
+      if (p.init || p.do_flow)
+        for (int g = 0; g < p.G; ++g) p.audio[m * p.G + g] = a[g];
+      for (int g = 0; g < p.G; ++g) a_s[tid][g] = a[g];
+    }
+  }
+  if (!p.do_start) return;
+  __syncthreads();
+  const int off2 = p.G - p.n_rem2;
+  const int nrow = (int)min((long long)TB, p.BT - m0);
+  for (int c = tid; c < p.C; c += blockDim.x) {     // audio = start(audio_0), glow.py:189
+    float w[CWG_MAX_GROUP / 2];
+    for (int j = 0; j < p.n_half2; ++j) w[j] = __ldg(p.start_w + c * (CWG_MAX_GROUP / 2) + j);
+    const float bias = __ldg(p.start_b + c);
+    for (int r = 0; r < nrow; ++r) {
+      float x = bias;
+      for (int j = 0; j < p.n_half2; ++j) x = fmaf(w[j], a_s[r][off2 + j], x);
+      size_t idx = (size_t)(m0 + r) * p.C + c;
+      if (XFMT == 0) {
+        reinterpret_cast<float*>(p.x_out)[idx] = x;
+      } else {
+        __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(p.x_out);
+        __nv_bfloat16* lo = hi + (size_t)p.BT * p.C;
+        __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi[idx] = h;
+        lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_cond_ffma(const Dims& d, const cwg_weights* w, int flow, const float* mel,
+                     const float* cond_bias, float* h2, cudaStream_t s) {
+  GemmP p{};
+  p.M = d.B * d.Tm; p.N = d.P * d.H; p.K = d.KC;
+  p.W = w->cond_w_f32 + (size_t)flow * p.N * p.K; p.ldw = p.K;
+  p.a0 = mel; p.Tm = d.Tm; p.nmel = d.M; p.H = d.H;
+  p.o0 = h2; p.bias = cond_bias + (size_t)flow * d.H; p.bias_bstride = d.F * d.H;
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+  k_sgemm<0, 0><<<grid, 256, 0, s>>>(p);
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, const float* x_in,
+                      float* x_out, const float* h2, float* eo, float* pre, float* acts, cudaStream_t s) {
+  const size_t fl = (size_t)flow * d.L + layer;
+  GemmP p{};
+  p.M = (int)d.BT; p.N = 2 * d.C; p.K = d.K1;
+  p.W = w->w1_f32 + fl * (size_t)(2 * d.C) * d.K1; p.ldw = d.K1;
+  p.a0 = x_in; p.a1 = h2; p.Tp = d.Tp; p.C = d.C; p.ks = d.ks; p.dil = 1 << layer; p.H = d.H;
+  p.o0 = pre; p.bias = w->b1 + fl * (size_t)(2 * d.C);
+  dim3 g1((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+  k_sgemm<1, 1><<<g1, 256, 0, s>>>(p);
+  CWG_CHECK_CUDA(cudaGetLastError());
+
+  long long n = d.BT * d.C;
+  k_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pre, acts, n, d.C);
+  CWG_CHECK_CUDA(cudaGetLastError());
+
+  GemmP q{};
+  q.M = (int)d.BT; q.N = d.N2; q.K = d.C;
+  q.W = w->w2_f32 + fl * (size_t)d.N2 * d.C; q.ldw = d.C;
+  q.a0 = acts; q.C = d.C;
+  q.o0 = x_out; q.o1 = eo; q.xin = x_in;
+  q.bias = w->b2 + fl * (size_t)d.C; q.bias2 = w->eo_b + (size_t)flow * CWG_EO_PAD;
+  q.has_res = layer < d.L - 1; q.first = layer == 0;
+  dim3 g2((q.M + BM - 1) / BM, (q.N + BN - 1) / BN);
+  k_sgemm<2, 2><<<g2, 256, 0, s>>>(q);
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
+                         int flow_done, int flow_next, const float* z, float sigma, float* audio,
+                         const float* eo, void* x_out, cudaStream_t s) {
+  BoundaryP p{};
+  p.BT = d.BT; p.G = d.G; p.C = d.C;
+  p.init = z != nullptr; p.do_flow = flow_done >= 0; p.do_start = flow_next >= 0;
+  p.z = z; p.sigma = sigma; p.audio = audio; p.eo = eo; p.x_out = x_out;
+  if (p.do_flow) {
+    flow_channels(cfg, flow_done, &p.n_rem, &p.n_half);
+    p.winv = w->winv + (size_t)flow_done * CWG_MAX_GROUP * CWG_MAX_GROUP;
+  }
+  if (p.do_start) {
+    flow_channels(cfg, flow_next, &p.n_rem2, &p.n_half2);
+    p.start_w = w->start_w + (size_t)flow_next * d.C * (CWG_MAX_GROUP / 2);
+    p.start_b = w->start_b + (size_t)flow_next * d.C;
+  }
+  unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
+  if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
+  else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cwg

@@ -1,0 +1,237 @@
+"""Drop-in `WaveGlow` module whose `infer` runs on hand-written sm_100a kernels.
+
+Mirrors the interface of the reference class `CookieTTS/_4_mtw/waveglow/glow.py:225-350`:
+same constructor kwargs (`WaveGlow(**waveglow_config)`, glow.py:226-227 and `WN_config`
+:116-117), same parameter names/shapes (so `load_state_dict(checkpoint['model'])` of a
+reference checkpoint works unchanged), same
+`infer(spect, speaker_id=None, sigma=1.0)` call.  Only the inverse pass is implemented
+(north_star scope): `forward` (the training direction) raises.
+
+There is no CPU or PyTorch fallback: `infer` needs a CUDA device and the in-tree
+`libcwg.so`; otherwise it raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .packing import PackConfig, pack_state_dict
+
+
+class Invertible1x1Conv(nn.Module):
+    """Parameter holder for glow.py:65-107 (key `convinv.{k}.conv.weight`).  `W_inverse`
+    may be set/deleted by callers as in the reference (train.py:332-334); it is not used -
+    the inverse is recomputed from `conv.weight` whenever the weights change."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv1d(c, c, kernel_size=1, stride=1, padding=0, bias=False)
+        w = torch.linalg.qr(torch.randn(c, c))[0]
+        if torch.det(w) < 0:
+            w[:, 0] = -w[:, 0]
+        self.conv.weight.data = w.view(c, c, 1).contiguous()
+
+
+class WN(nn.Module):
+    """Parameter holder with the layout of glow.py:110-186."""
+
+    def __init__(self, n_in_channels, n_mel_channels, n_layers, n_channels, kernel_size,
+                 speaker_embed_dim=0, rezero=False):
+        super().__init__()
+        assert kernel_size % 2 == 1 and n_channels % 2 == 0
+        wn = nn.utils.weight_norm          # legacy API on purpose: yields weight_g / weight_v keys
+        self.n_layers, self.n_channels, self.speaker_embed_dim = n_layers, n_channels, speaker_embed_dim
+        self.in_layers = nn.ModuleList()
+        self.res_skip_layers = nn.ModuleList()
+        if rezero:
+            self.alpha_i = nn.ParameterList()
+        if speaker_embed_dim:
+            self.speaker_embed = nn.Embedding(512, speaker_embed_dim)
+            self.speaker_embed.weight.data.mul_(0.05)
+        self.start = wn(nn.Conv1d(n_in_channels, n_channels, 1), name="weight")
+        self.end = nn.Conv1d(n_channels, 2 * n_in_channels, 1)
+        self.end.weight.data.zero_()
+        self.end.bias.data.zero_()
+        hidden = 256                        # literal in the reference, glow.py:153
+        self.cond_layers = nn.ModuleList([
+            wn(nn.Conv1d(n_mel_channels + speaker_embed_dim, hidden, 1), name="weight"),
+            wn(nn.Conv1d(hidden, hidden, 1), name="weight"),
+            wn(nn.Conv1d(hidden, 2 * n_channels * n_layers, 1), name="weight")])
+        for i in range(n_layers):
+            d = 2 ** i
+            self.in_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels, kernel_size, dilation=d,
+                                               padding=(kernel_size * d - d) // 2), name="weight"))
+            rs = 2 * n_channels if i < n_layers - 1 else n_channels
+            self.res_skip_layers.append(wn(nn.Conv1d(n_channels, rs, 1), name="weight"))
+            if rezero:
+                self.alpha_i.append(nn.Parameter(torch.rand(1) * 0.02 + 0.09))
+
+
+class WaveGlow(nn.Module):
+    def __init__(self, yoyo=False, yoyo_WN=False, n_mel_channels=80, n_flows=12, n_group=8,
+                 n_early_every=4, n_early_size=2, memory_efficient=False, spect_scaling=False,
+                 upsample_mode="normal", WN_config=None, win_length=1024, hop_length=256,
+                 precision: str = "bf16x3"):
+        super().__init__()
+        if yoyo or yoyo_WN:
+            raise ValueError("yoyo models select a different reference class (efficient_model*), not glow.WaveGlow")
+        if memory_efficient:
+            raise ValueError("memory_efficient=True builds no layers in the reference (glow.py:263-264)")
+        if spect_scaling:
+            raise ValueError("spect_scaling=True is unusable in the reference (glow.py:232-235,315-316)")
+        if upsample_mode != "normal":
+            raise ValueError("only upsample_mode='normal' is supported")
+        WN_config = dict(WN_config or dict(n_layers=8, n_channels=256, kernel_size=3, speaker_embed_dim=0, rezero=False))
+        WN_config.setdefault("speaker_embed_dim", 0)
+        WN_config.setdefault("rezero", False)
+        assert n_group % 2 == 0
+        self.spect_scaling = False
+        self.multispeaker = WN_config["speaker_embed_dim"] > 0
+        self.n_flows, self.n_group = n_flows, n_group
+        self.n_early_every, self.n_early_size = n_early_every, n_early_size
+        self.precision = precision
+        self.upsample = nn.ConvTranspose1d(n_mel_channels, n_mel_channels, win_length, stride=hop_length)
+        self.WN = nn.ModuleList()
+        self.convinv = nn.ModuleList()
+        self.pack_config = PackConfig(
+            n_mel=n_mel_channels, n_flows=n_flows, n_group=n_group, n_early_every=n_early_every,
+            n_early_size=n_early_size, win_length=win_length, hop_length=hop_length,
+            n_layers=WN_config["n_layers"], n_channels=WN_config["n_channels"],
+            kernel_size=WN_config["kernel_size"], cond_hidden=256,
+            speaker_embed_dim=WN_config["speaker_embed_dim"], rezero=bool(WN_config["rezero"]))
+        self.pack_config.validate()
+        for n_rem, n_half in self.pack_config.flow_channels():
+            self.convinv.append(Invertible1x1Conv(n_rem))
+            self.WN.append(WN(n_half, n_mel_channels * n_group, **WN_config))
+        self.n_remaining_channels = self.pack_config.flow_channels()[-1][0]
+        self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self._packed_key = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------ checkpoint compatibility
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts the weight-normed layout (weight_g/weight_v) and the plain `weight` layout
+        (after `remove_weight_norm`): a plain weight w becomes v = w, g = ||w||."""
+        own = set(self.state_dict().keys())
+        sd = {}
+        for k, v in state_dict.items():
+            if k.endswith(".weight") and k not in own and k[:-7] + ".weight_v" in own:
+                norm = v.float().pow(2).sum(dim=tuple(range(1, v.dim())), keepdim=True).sqrt()
+                sd[k[:-7] + ".weight_v"] = v
+                sd[k[:-7] + ".weight_g"] = norm.to(v.dtype)
+            else:
+                sd[k] = v
+        self._packed = None
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    @staticmethod
+    def remove_weightnorm(model):
+        """The reference version is broken (glow.py:352-360); weight-norm is folded at pack
+        time here, so this is a no-op kept for call-site compatibility."""
+        return model
+
+    def forward(self, *a, **kw):
+        raise NotImplementedError("only the inverse pass (infer) is in scope of this implementation")
+
+    # ------------------------------------------------------------------ packing cache
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision,)
+
+    def _device(self) -> torch.device:
+        return self.upsample.weight.device
+
+    def _ensure_packed(self):
+        key = self._weights_key()
+        if self._packed is not None and self._packed_key == key:
+            return
+        dev = self._device()
+        planes = ("f32",) if self.precision == "ffma" else ("hi", "lo")
+        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
+        pk = pack_state_dict(sd, self.pack_config, planes=planes)
+        dev_pk = {}
+        for name, arr in pk.items():
+            if arr.dtype == np.uint16:
+                arr = arr.view(np.int16)
+            dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        w = _cabi.CwgWeights()
+        for f in _cabi.WEIGHT_FIELDS:
+            setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
+        self._packed, self._packed_key, self._cw = dev_pk, key, w
+        self._ccfg = _cabi.make_config(self.pack_config)
+        if self.multispeaker:
+            self._spk_tables = torch.stack([wn.speaker_embed.weight.detach().float() for wn in self.WN]).to(dev)
+
+    def _cond_bias(self, batch: int, speaker_ids) -> torch.Tensor:
+        base = self._packed["cond_b_base"]                           # [F, H]
+        bias = base.unsqueeze(0).expand(batch, -1, -1)
+        if self.multispeaker and speaker_ids is not None:            # glow.py:193-196
+            emb = self._spk_tables[:, speaker_ids.to(base.device).long()]          # [F, B, E]
+            bias = bias + torch.einsum("fhe,fbe->bfh", self._packed["cond_w_spk"], emb)
+        return bias.contiguous()
+
+    def draw_z(self, batch: int, t_mel: int, generator=None) -> torch.Tensor:
+        """Standard-normal latent [B, T] drawn in the order of the reference's draws
+        (main latent, then the early outputs at descending k; glow.py:326,342-347)."""
+        pc, dev = self.pack_config, self._device()
+        tp = t_mel * pc.phases
+        z = torch.empty(batch, tp, pc.n_group, device=dev)
+        n_rem_last = self.n_remaining_channels
+        z[:, :, pc.n_group - n_rem_last:] = torch.randn(batch, n_rem_last, tp, device=dev, generator=generator).transpose(1, 2)
+        early = [k for k in range(pc.n_flows) if k % pc.n_early_every == 0 and k > 0]
+        off = pc.n_group - n_rem_last
+        for _ in sorted(early, reverse=True):
+            off -= pc.n_early_size
+            z[:, :, off:off + pc.n_early_size] = torch.randn(batch, pc.n_early_size, tp, device=dev, generator=generator).transpose(1, 2)
+        return z.view(batch, tp * pc.n_group)
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def infer(self, spect, speaker_id=None, sigma=1.0, *, speaker_ids=None, z=None):
+        """mel [B, n_mel, T_mel] -> audio [B, T_mel*hop] (fp32, on the module's device).
+
+        `speaker_id` is the reference keyword (glow.py:314); `speaker_ids` is what
+        `Denoiser`/notebooks pass (denoiser.py:39).  `z` ([B, T], standard normal) injects the
+        latent the reference draws internally; None draws it here."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("cookietts_b200.WaveGlow.infer needs the module on a CUDA device (no CPU fallback)")
+        lib = _cabi.load()
+        if self.precision not in _cabi.MODES:
+            raise ValueError(f"precision must be one of {list(_cabi.MODES)}")
+        mode = _cabi.MODES[self.precision]
+        if speaker_id is None:
+            speaker_id = speaker_ids
+        pc = self.pack_config
+        if spect.dim() != 3 or spect.shape[1] != pc.n_mel:
+            raise ValueError(f"spect must be [B, {pc.n_mel}, T_mel], got {tuple(spect.shape)}")
+        mel = spect.to(device=dev, dtype=torch.float32).contiguous()
+        batch, _, t_mel = mel.shape
+        if t_mel == 0 or batch == 0:
+            return torch.zeros(batch, t_mel * pc.hop_length, device=dev)
+        with torch.cuda.device(dev):
+            self._ensure_packed()
+            T = t_mel * pc.hop_length
+            if z is None:
+                z = self.draw_z(batch, t_mel)
+            z = z.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(z.shape) != (batch, T):
+                raise ValueError(f"z must be [B, T_mel*hop] = {(batch, T)}, got {tuple(z.shape)}")
+            cond_bias = self._cond_bias(batch, speaker_id)
+            nbytes = lib.cwg_workspace_bytes(self._ccfg, mode, batch, t_mel)
+            if nbytes == 0:
+                raise _cabi.CwgError(lib.cwg_last_error().decode())
+            if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+            audio = torch.empty(batch, T, device=dev, dtype=torch.float32)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _cabi.check(lib.cwg_infer(self._ccfg, self._cw, mode, mel.data_ptr(), cond_bias.data_ptr(),
+                                      z.data_ptr(), float(sigma), audio.data_ptr(), ws_ptr,
+                                      self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
+                                      batch, t_mel, stream))
+        return audio

@@ -1,0 +1,97 @@
+"""CPU checks of the drop-in boundary: libcwg.so loads, exports every symbol include/cwg.h
+declares, validates arguments (no compute calls without a GPU), and the Python module keeps
+the reference's state_dict layout."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from cookietts_b200 import WaveGlow, _cabi
+from cookietts_b200.packing import PackConfig
+from tests.helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def module_kwargs(cfg):
+    return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
+                n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size,
+                WN_config=dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size,
+                               speaker_embed_dim=cfg.speaker_embed_dim, rezero=cfg.rezero),
+                win_length=cfg.win_length, hop_length=cfg.hop_length)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "cwg.h")).read()
+    declared = set(re.findall(r"\b(cwg_[a-z_]+)\s*\(", header))
+    assert declared == set(_cabi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cwg_abi_version() == 1
+
+
+def test_workspace_and_argument_validation():
+    lib = _cabi.load()
+    cfg = _cabi.make_config(PackConfig())
+    n_ffma = lib.cwg_workspace_bytes(cfg, _cabi.MODE_FFMA, 2, 10)
+    n_tc = lib.cwg_workspace_bytes(cfg, _cabi.MODE_BF16X3, 2, 10)
+    assert n_ffma > 0 and n_tc > 0 and n_tc < n_ffma
+    assert lib.cwg_workspace_bytes(cfg, 7, 2, 10) == 0
+    assert b"mode" in lib.cwg_last_error()
+    bad = _cabi.make_config(PackConfig(n_group=8, hop_length=252))
+    assert lib.cwg_workspace_bytes(bad, _cabi.MODE_FFMA, 1, 1) == 0
+    # tensor-core modes are specialised for 256 channels: other widths are refused loudly
+    c512 = _cabi.make_config(PackConfig(n_channels=512))
+    assert lib.cwg_workspace_bytes(c512, _cabi.MODE_FFMA, 1, 4) > 0
+    assert lib.cwg_launch_count(cfg, _cabi.MODE_FFMA) == 1 + 12 * (1 + 3 * 8 + 1)
+    # NULL weights -> error code, not a crash
+    rc = lib.cwg_infer(cfg, None, _cabi.MODE_FFMA, None, None, None, 1.0, None, None, 0, 1, 1, None)
+    assert rc != 0 and b"NULL" in lib.cwg_last_error()
+
+
+@pytest.mark.parametrize("name", ["tiny", "rezero"])
+def test_state_dict_layout_matches_reference(name):
+    cfg, sd, _ = load_golden(name)
+    model = WaveGlow(**module_kwargs(cfg))
+    own = model.state_dict()
+    assert set(own.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+
+
+def test_plain_weight_checkpoint_is_accepted():
+    cfg, sd, _ = load_golden("tiny")
+    from oracle.waveglow_oracle import weight_norm_effective
+    plain = {}
+    for k, v in sd.items():
+        if k.endswith(".weight_g"):
+            plain[k[:-9] + ".weight"] = weight_norm_effective(v, sd[k[:-9] + ".weight_v"])
+        elif not k.endswith(".weight_v"):
+            plain[k] = v
+    model = WaveGlow(**module_kwargs(cfg))
+    model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in plain.items()}, strict=True)
+    from cookietts_b200.packing import pack_state_dict
+    a = pack_state_dict({k: v.detach().numpy() for k, v in model.state_dict().items()}, model.pack_config, planes=("f32",))
+    b = pack_state_dict(sd, model.pack_config, planes=("f32",))
+    for key in ("w1_f32", "w2_f32", "cond_w_f32", "start_w"):
+        assert np.allclose(a[key], b[key], atol=1e-6), key
+
+
+def test_unsupported_constructor_values_raise():
+    with pytest.raises(ValueError):
+        WaveGlow(spect_scaling=True)
+    with pytest.raises(ValueError):
+        WaveGlow(memory_efficient=True)
+    with pytest.raises(ValueError):
+        WaveGlow(upsample_mode="simple")
+
+
+def test_infer_refuses_cpu():
+    cfg, sd, g = load_golden("tiny")
+    model = WaveGlow(**module_kwargs(cfg))
+    with pytest.raises(RuntimeError):
+        model.infer(torch.from_numpy(g["mel"]))
