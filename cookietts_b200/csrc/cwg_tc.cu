@@ -1,10 +1,614 @@
-// placeholder: tcgen05 path (being written)
+// Tensor-core path of the WaveGlow inverse pass for sm_100a: TMA-fed tcgen05.mma kernels with
+// TMEM accumulators.
+//
+//   k_cond_tc   : folded upsample+squeeze+cond_layers[0..1] GEMM (glow.py:318-324,198-199)
+//                 H2[b, f*P+p, :] = mel4[b, f, :] @ cond_w[p*H:(p+1)*H, :]^T + bias
+//   k_layer_tc  : one WN layer (glow.py:201-220): dilated conv + cond_layers[2] slice as ONE
+//                 implicit GEMM (K = 3C + H), tanh*sigmoid gate in the TMEM epilogue, res_skip
+//                 GEMM from shared memory, residual update (TMA store) and folded-`end` skip sum.
+//
+// Operand precision: every fp32 quantity q that feeds an MMA is stored as two bf16 planes,
+// q ~= hi + lo.  NPASS = 1 issues hi*hi only (CWG_MODE_BF16); NPASS = 3 issues
+// hi*hi + lo*hi + hi*lo (CWG_MODE_BF16X3, ~2^-17 relative operand error).  Accumulation is fp32 in
+// TMEM; the residual stream always keeps both planes.
 #include "cwg_common.cuh"
+#include "cwg_sm100.cuh"
+
 namespace cwg {
-int launch_cond_tc(const Dims&, const cwg_weights*, int, int, const float*, const float*, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t) {
-  set_error("tensor-core path not built"); return 3;
+
+using namespace sm100;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// host: tensor maps (driver entry point resolved at run time; no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_encodeTiled)p;
+  return fn;
 }
-int launch_layer_tc(const Dims&, const cwg_weights*, int, int, int, const __nv_bfloat16*, __nv_bfloat16*, const __nv_bfloat16*, float*, cudaStream_t) {
-  set_error("tensor-core path not built"); return 3;
+
+// bf16 tensor, innermost dim contiguous, 128B swizzle, zero OOB fill. strides_bytes has rank-1 entries.
+int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  CWG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CWG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
 }
+
+int map_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows}; uint64_t st[1] = {cols * 2}; uint32_t box[2] = {64, box_rows};
+  return make_map(m, ptr, 2, dims, st, box);
 }
+
+// activations [B][T'][C] bf16 as (C, T', B); box = 64 channels x 128 steps of one utterance.
+// Out-of-range steps (negative or >= T') are zero-filled: the conv's zero padding, per utterance.
+int map_act(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uint64_t B) {
+  uint64_t dims[3] = {C, Tp, B}; uint64_t st[2] = {C * 2, Tp * C * 2}; uint32_t box[3] = {64, 128, 1};
+  return make_map(m, ptr, 3, dims, st, box);
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_A = 128 * 128;      // [128 rows][64 bf16] = 16 KB
+constexpr uint32_t IDESC_N256 = umma_idesc_bf16(128, 256);
+constexpr uint32_t IDESC_N128 = umma_idesc_bf16(128, 128);
+constexpr uint32_t IDESC_N16 = umma_idesc_bf16(128, 16);
+
+__device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
+  uint32_t a = smem_u32(p);
+  return p + ((1024u - (a & 1023u)) & 1023u);
+}
+
+// One 64-deep k-block = 4 UMMA K-steps of 16 bf16 (32 bytes along the swizzled row).
+__device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t b_addr, uint32_t tmem_d, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(tmem_d, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, (first && k == 0) ? 0u : 1u);
+}
+
+// two 16-column TMEM loads + wait in ONE asm block so no consumer can be scheduled before the wait
+__device__ __forceinline__ void tmem_ld16x2_sync(uint32_t ta, uint32_t tb, float* a, float* b) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
+}
+__device__ __forceinline__ void tmem_ld16_sync(uint32_t ta, float* a) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
+}
+
+// 16 fp32 values of one row -> bf16 hi (and lo) planes, written as 2 x 16-byte chunks into
+// 128B-swizzled tiles (chunks `chunk0`, `chunk0 + 1` of `row`).
+template <bool WITH_LO>
+__device__ __forceinline__ void store_split16(const float* v, uint8_t* tile_hi, uint8_t* tile_lo, int row, int chunk0) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    if (WITH_LO) {
+      float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
+      lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+    }
+  }
+  *reinterpret_cast<uint4*>(tile_hi + sw128_offset(row, chunk0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(tile_hi + sw128_offset(row, chunk0 + 1)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (WITH_LO) {
+    *reinterpret_cast<uint4*>(tile_lo + sw128_offset(row, chunk0)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(tile_lo + sw128_offset(row, chunk0 + 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
+// tanh(a) * sigmoid(b), glow.py:34-41
+template <int NPASS>
+__device__ __forceinline__ float gate(float a, float b) {
+  if (NPASS == 3) {
+    // (1-u)/((1+u)(1+v)), u = e^-2a, v = e^-b : 2 ex2 + 1 rcp, ~1e-6 relative
+    a = fmaxf(a, -15.f);
+    float u = __expf(-2.f * a), v = __expf(-b);
+    return __fdividef(1.f - u, (1.f + u) * (1.f + v));
+  } else {
+    float t, s;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(a));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(s) : "f"(0.5f * b));
+    return t * fmaf(s, 0.5f, 0.5f);
+  }
+}
+
+__device__ __forceinline__ void ring_advance(int& slot, uint32_t& phase, int n) {
+  if (++slot == n) { slot = 0; phase ^= 1u; }
+}
+
+// ------------------------------------------------------------------------------------------
+// mel4 im2col: mel4[b*Tm + f][j*M + ci] = mel[b][ci][f - j] (0 for f < j), bf16 hi / lo planes
+// ------------------------------------------------------------------------------------------
+__global__ void k_im2col_mel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                             int B, int M, int Tm, int J) {
+  long long n = (long long)B * Tm * J * M;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int KC = J * M;
+  long long row = i / KC; int kk = (int)(i - row * KC);
+  int b = (int)(row / Tm), f = (int)(row - (long long)b * Tm);
+  int j = kk / M, ci = kk - j * M;
+  float v = f >= j ? mel[((size_t)b * M + ci) * Tm + (f - j)] : 0.f;
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// ------------------------------------------------------------------------------------------
+// cond GEMM: tile 128 rows (b,f) x 256 columns (one phase p, all H=256 hidden channels)
+// ------------------------------------------------------------------------------------------
+struct CondArgs {
+  const float* bias;      // cond_bias + flow*H ; [B] stride bias_bstride
+  int bias_bstride;
+  int M, Tm, B;
+  int w_row0;             // flow * P * H
+  int nkb;                // KC / 64
+};
+
+template <int NPASS>
+struct CondCfg {
+  static constexpr int PL = NPASS == 3 ? 2 : 1;
+  static constexpr int STAGE = (TILE_A + 2 * TILE_A) * PL;     // A 16 KB + B 32 KB per plane
+  static constexpr int NST = NPASS == 3 ? 2 : 4;
+  static constexpr int SMEM = NST * STAGE + 256 + 1024;
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(192, 1)
+k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+          const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+          const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo, CondArgs a) {
+  using Cfg = CondCfg<NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::NST * Cfg::STAGE);
+  uint64_t* empty = full + Cfg::NST;
+  uint64_t* acc_full = empty + Cfg::NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x, m0 = blockIdx.y * 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* st = smem + s * Cfg::STAGE;
+      mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+      tma_load_2d(st, &tm_a_hi, &full[s], kb * 64, m0);
+      tma_load_2d(st + TILE_A, &tm_b_hi, &full[s], kb * 64, a.w_row0 + p * 256);
+      if (NPASS == 3) {
+        tma_load_2d(st + 3 * TILE_A, &tm_a_lo, &full[s], kb * 64, m0);
+        tma_load_2d(st + 4 * TILE_A, &tm_b_lo, &full[s], kb * 64, a.w_row0 + p * 256);
+      }
+      ring_advance(s, ph, Cfg::NST);
+    }
+  } else if (warp == 1 && lane == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after_sync();
+      uint32_t st = smem_u32(smem + s * Cfg::STAGE);
+      issue_kblock(st, st + TILE_A, tmem, IDESC_N256, kb == 0);
+      if (NPASS == 3) {
+        issue_kblock(st + 3 * TILE_A, st + TILE_A, tmem, IDESC_N256, false);   // lo * hi
+        issue_kblock(st, st + 4 * TILE_A, tmem, IDESC_N256, false);            // hi * lo
+      }
+      umma_commit(&empty[s]);
+      ring_advance(s, ph, Cfg::NST);
+    }
+    umma_commit(acc_full);
+  } else if (warp >= 2) {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    int m = m0 + row;
+    int b = min(m / a.Tm, a.B - 1);
+    const float4* bias4 = reinterpret_cast<const float4*>(a.bias + (size_t)b * a.bias_bstride);
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    // staging aliases the (now idle) pipeline stages: hi boxes at 0..64 KB, lo boxes at 64..128 KB
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) {
+      float v[16];
+      tmem_ld16_sync(trow + c * 16, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 bb = __ldg(bias4 + c * 4 + q);
+        v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+      }
+      uint8_t* thi = smem + (c >> 2) * TILE_A;
+      store_split16<NPASS == 3>(v, thi, thi + 4 * TILE_A, row, (c & 3) * 2);
+    }
+    tc_fence_before_sync();
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      for (int j = 0; j < 4; ++j) {
+        tma_store_2d(&tm_c_hi, smem + j * TILE_A, p * 256 + j * 64, m0);
+        if (NPASS == 3) tma_store_2d(&tm_c_lo, smem + (4 + j) * TILE_A, p * 256 + j * 64, m0);
+      }
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 256); }
+}
+
+// ------------------------------------------------------------------------------------------
+// WN layer
+// ------------------------------------------------------------------------------------------
+struct LayerArgs {
+  const float* b1;        // [2C]
+  const float* b2;        // [C]
+  const float* eo_b;      // [16]
+  float* eo;              // [B*T'][16]
+  const __nv_bfloat16* x_hi;   // x_in planes (residual read)
+  const __nv_bfloat16* x_lo;
+  int Tp, dil;
+  int w1_row0, w2_row0;
+  int has_res, first;
+};
+
+constexpr int L_NA = 8, L_NB = 5;
+constexpr int L_OFF_B = L_NA * TILE_A;                 // 131072
+constexpr int L_OFF_WSE = L_OFF_B + L_NB * TILE_A;     // 212992
+constexpr int L_OFF_BAR = L_OFF_WSE + 16384;           // 229376
+constexpr int L_SMEM = L_OFF_BAR + 256 + 1024;         // 230656
+
+template <int NPASS>
+__global__ void __launch_bounds__(224, 1)
+k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+           const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
+           const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+           const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+           const __grid_constant__ CUtensorMap tm_wse_hi, const __grid_constant__ CUtensorMap tm_wse_lo,
+           const __grid_constant__ CUtensorMap tm_xo_hi, const __grid_constant__ CUtensorMap tm_xo_lo, LayerArgs a) {
+  constexpr int PL = NPASS == 3 ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L_OFF_BAR);
+  uint64_t* a_empty = a_full + L_NA;
+  uint64_t* b_full = a_empty + L_NA;
+  uint64_t* b_empty = b_full + L_NB;
+  uint64_t* wse_full = b_empty + L_NB;
+  uint64_t* acc1_full = wse_full + 1;
+  uint64_t* acts_ready = acc1_full + 1;
+  uint64_t* acc2_full = acts_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * 128, b = blockIdx.y;
+  auto slot_a = [&](int i) { return smem + i * TILE_A; };
+  auto slot_b = [&](int i) { return smem + L_OFF_B + i * TILE_A; };
+  auto wse = [&](int plane, int kb) { return smem + L_OFF_WSE + plane * 8192 + kb * 2048; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < L_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < L_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, 128); mbar_init(acc2_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- producer A: activation tiles (3 dilated taps of x, then the cond hidden H2)
+    tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_h_hi);
+    mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL);
+    for (int kb = 0; kb < 4; ++kb) {
+      tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
+      if (NPASS == 3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
+    }
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < 16; ++kb) {
+      for (int pl = 0; pl < PL; ++pl) {
+        mbar_wait(&a_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&a_full[s], TILE_A);
+        if (kb < 12) {
+          int tap = kb >> 2, cb = kb & 3;
+          tma_load_3d(slot_a(s), pl ? &tm_x_lo : &tm_x_hi, &a_full[s], cb * 64, t0 + (tap - 1) * a.dil, b);
+        } else {
+          tma_load_3d(slot_a(s), pl ? &tm_h_lo : &tm_h_hi, &a_full[s], (kb - 12) * 64, t0, b);
+        }
+        ring_advance(s, ph, L_NA);
+      }
+    }
+  } else if (warp == 6 && lane == 0) {
+    // ---------------- producer B: weight tiles [128 rows x 64 k]
+    tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w2_hi);
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < 16; ++kb)
+      for (int q = 0; q < 4; ++q)
+        for (int pl = 0; pl < PL; ++pl) {
+          mbar_wait(&b_empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&b_full[s], TILE_A);
+          tma_load_2d(slot_b(s), pl ? &tm_w1_lo : &tm_w1_hi, &b_full[s], kb * 64, a.w1_row0 + q * 128);
+          ring_advance(s, ph, L_NB);
+        }
+    if (a.has_res)
+      for (int kb = 0; kb < 4; ++kb)
+        for (int h = 0; h < 2; ++h)
+          for (int pl = 0; pl < PL; ++pl) {
+            mbar_wait(&b_empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&b_full[s], TILE_A);
+            tma_load_2d(slot_b(s), pl ? &tm_w2_lo : &tm_w2_hi, &b_full[s], kb * 64, a.w2_row0 + h * 128);
+            ring_advance(s, ph, L_NB);
+          }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    // GEMM1: pre[128 x 512] = [x taps | H2] (K = 1024) x W1^T, accumulators in TMEM columns 0..511
+    for (int kb = 0; kb < 16; ++kb) {
+      uint32_t a_hi, a_lo = 0; int sa_hi = sa, sa_lo = 0;
+      mbar_wait(&a_full[sa], pa); a_hi = smem_u32(slot_a(sa)); ring_advance(sa, pa, L_NA);
+      if (NPASS == 3) { sa_lo = sa; mbar_wait(&a_full[sa], pa); a_lo = smem_u32(slot_a(sa)); ring_advance(sa, pa, L_NA); }
+      for (int q = 0; q < 4; ++q) {
+        uint32_t b_hi, b_lo = 0; int sb_hi = sb, sb_lo = 0;
+        mbar_wait(&b_full[sb], pb); b_hi = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB);
+        if (NPASS == 3) { sb_lo = sb; mbar_wait(&b_full[sb], pb); b_lo = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB); }
+        tc_fence_after_sync();
+        const uint32_t d = tmem + q * 128;
+        issue_kblock(a_hi, b_hi, d, IDESC_N128, kb == 0);
+        if (NPASS == 3) {
+          issue_kblock(a_lo, b_hi, d, IDESC_N128, false);
+          issue_kblock(a_hi, b_lo, d, IDESC_N128, false);
+        }
+        umma_commit(&b_empty[sb_hi]);
+        if (NPASS == 3) umma_commit(&b_empty[sb_lo]);
+      }
+      umma_commit(&a_empty[sa_hi]);
+      if (NPASS == 3) umma_commit(&a_empty[sa_lo]);
+    }
+    umma_commit(acc1_full);
+    // GEMM2: [res | folded end] = acts (smem, A slots 0..3 hi / 4..7 lo) x W2^T
+    mbar_wait(acts_ready, 0);
+    tc_fence_after_sync();
+    mbar_wait(wse_full, 0);
+    for (int kb = 0; kb < 4; ++kb) {
+      const uint32_t a_hi = smem_u32(slot_a(kb)), a_lo = smem_u32(slot_a(4 + kb));
+      if (a.has_res) {
+        for (int h = 0; h < 2; ++h) {
+          uint32_t b_hi, b_lo = 0; int sb_hi = sb, sb_lo = 0;
+          mbar_wait(&b_full[sb], pb); b_hi = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB);
+          if (NPASS == 3) { sb_lo = sb; mbar_wait(&b_full[sb], pb); b_lo = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB); }
+          tc_fence_after_sync();
+          const uint32_t d = tmem + h * 128;
+          issue_kblock(a_hi, b_hi, d, IDESC_N128, kb == 0);
+          if (NPASS == 3) {
+            issue_kblock(a_lo, b_hi, d, IDESC_N128, false);
+            issue_kblock(a_hi, b_lo, d, IDESC_N128, false);
+          }
+          umma_commit(&b_empty[sb_hi]);
+          if (NPASS == 3) umma_commit(&b_empty[sb_lo]);
+        }
+      }
+      const uint32_t d = tmem + 256;
+      issue_kblock(a_hi, smem_u32(wse(0, kb)), d, IDESC_N16, kb == 0);
+      if (NPASS == 3) {
+        issue_kblock(a_lo, smem_u32(wse(0, kb)), d, IDESC_N16, false);
+        issue_kblock(a_hi, smem_u32(wse(1, kb)), d, IDESC_N16, false);
+      }
+    }
+    umma_commit(acc2_full);
+  } else if (warp >= 2 && warp <= 5) {
+    // ---------------- epilogue warps: TMEM lane quarter = warp % 4, one row (group-step) per thread
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    const bool valid = t0 + row < a.Tp;
+    const size_t m = (size_t)b * a.Tp + (size_t)min(t0 + row, a.Tp - 1);
+    const float4* b1t = reinterpret_cast<const float4*>(a.b1);
+    const float4* b1s = reinterpret_cast<const float4*>(a.b1 + 256);
+
+    // gate: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) -> bf16 planes in A slots (GEMM2's A operand)
+    mbar_wait(acc1_full, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) {
+      float ta[16], sg[16], act[16];
+      tmem_ld16x2_sync(trow + c * 16, trow + 256 + c * 16, ta, sg);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 bt = __ldg(b1t + c * 4 + q), bs = __ldg(b1s + c * 4 + q);
+        act[4 * q + 0] = gate<NPASS>(ta[4 * q + 0] + bt.x, sg[4 * q + 0] + bs.x);
+        act[4 * q + 1] = gate<NPASS>(ta[4 * q + 1] + bt.y, sg[4 * q + 1] + bs.y);
+        act[4 * q + 2] = gate<NPASS>(ta[4 * q + 2] + bt.z, sg[4 * q + 2] + bs.z);
+        act[4 * q + 3] = gate<NPASS>(ta[4 * q + 3] + bt.w, sg[4 * q + 3] + bs.w);
+      }
+      store_split16<NPASS == 3>(act, slot_a(c >> 2), slot_a(4 + (c >> 2)), row, (c & 3) * 2);
+    }
+    tc_fence_before_sync();
+    fence_proxy_async_smem();
+    mbar_arrive(acts_ready);
+
+    // res / skip
+    mbar_wait(acc2_full, 0);
+    tc_fence_after_sync();
+    {
+      float sk[16];
+      tmem_ld16_sync(trow + 256, sk);
+      if (valid) {
+        float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
+        const float4* eb = reinterpret_cast<const float4*>(a.eo_b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 v = a.first ? __ldg(eb + q) : e[q];
+          v.x += sk[4 * q]; v.y += sk[4 * q + 1]; v.z += sk[4 * q + 2]; v.w += sk[4 * q + 3];
+          e[q] = v;
+        }
+      }
+    }
+    if (a.has_res) {
+      const uint4* xh = reinterpret_cast<const uint4*>(a.x_hi + m * 256);
+      const uint4* xl = reinterpret_cast<const uint4*>(a.x_lo + m * 256);
+      const float4* b2 = reinterpret_cast<const float4*>(a.b2);
+#pragma unroll 1
+      for (int c = 0; c < 16; ++c) {
+        uint4 h0 = __ldg(xh + 2 * c), h1 = __ldg(xh + 2 * c + 1), l0 = __ldg(xl + 2 * c), l1 = __ldg(xl + 2 * c + 1);
+        float r[16];
+        tmem_ld16_sync(trow + c * 16, r);
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 bb = __ldg(b2 + c * 4 + q);
+          r[4 * q] += bb.x; r[4 * q + 1] += bb.y; r[4 * q + 2] += bb.z; r[4 * q + 3] += bb.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {   // x_new = x_old(hi + lo) + res, glow.py:217
+          r[2 * i] += __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+          r[2 * i + 1] += __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+        }
+        store_split16<true>(r, slot_a(c >> 2), slot_a(4 + (c >> 2)), row, (c & 3) * 2);
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        for (int kb = 0; kb < 4; ++kb) {
+          tma_store_3d(&tm_xo_hi, slot_a(kb), kb * 64, t0, b);
+          tma_store_3d(&tm_xo_lo, slot_a(4 + kb), kb * 64, t0, b);
+        }
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 512); }
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  CWG_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+}  // namespace
+
+int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, const float* mel,
+                   const float* cond_bias, __nv_bfloat16* h2_planes, __nv_bfloat16* mel4_planes,
+                   cudaStream_t s) {
+  const size_t n4 = (size_t)d.B * d.Tm * d.KC;
+  __nv_bfloat16* m4_hi = mel4_planes; __nv_bfloat16* m4_lo = mel4_planes + n4;
+  if (mel != nullptr) {
+    k_im2col_mel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(mel, m4_hi, m4_lo, d.B, d.M, d.Tm, d.J);
+    CWG_CHECK_CUDA(cudaGetLastError());
+  }
+  const uint64_t rows = (uint64_t)d.B * d.Tm, ncol = (uint64_t)d.P * d.H;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo;
+  if (int r = map_2d(&ta_hi, m4_hi, d.KC, rows, 128)) return r;
+  if (int r = map_2d(&ta_lo, m4_lo, d.KC, rows, 128)) return r;
+  if (int r = map_2d(&tb_hi, w->cond_w_hi, d.KC, (uint64_t)d.F * ncol, 256)) return r;
+  if (int r = map_2d(&tb_lo, w->cond_w_lo, d.KC, (uint64_t)d.F * ncol, 256)) return r;
+  if (int r = map_2d(&tc_hi, h2_planes, ncol, rows, 128)) return r;
+  if (int r = map_2d(&tc_lo, h2_planes + (size_t)d.BT * d.H, ncol, rows, 128)) return r;
+  CondArgs a{};
+  a.bias = cond_bias + (size_t)flow * d.H; a.bias_bstride = d.F * d.H;
+  a.M = (int)rows; a.Tm = d.Tm; a.B = d.B; a.w_row0 = flow * (int)ncol; a.nkb = d.KC / 64;
+  dim3 grid(d.P, (unsigned)((rows + 127) / 128));
+  if (npass == 3) {
+    if (int r = set_smem(k_cond_tc<3>, CondCfg<3>::SMEM)) return r;
+    k_cond_tc<3><<<grid, 192, CondCfg<3>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, a);
+  } else {
+    if (int r = set_smem(k_cond_tc<1>, CondCfg<1>::SMEM)) return r;
+    k_cond_tc<1><<<grid, 192, CondCfg<1>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, a);
+  }
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
+                    const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
+                    float* eo, cudaStream_t s) {
+  const size_t plane = (size_t)d.BT * d.C, hplane = (size_t)d.BT * d.H;
+  const uint64_t fl = (uint64_t)d.F * d.L;
+  CUtensorMap tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo;
+  if (int r = map_act(&tx_hi, x_in, d.C, d.Tp, d.B)) return r;
+  if (int r = map_act(&tx_lo, x_in + plane, d.C, d.Tp, d.B)) return r;
+  if (int r = map_act(&th_hi, h2, d.H, d.Tp, d.B)) return r;
+  if (int r = map_act(&th_lo, h2 + hplane, d.H, d.Tp, d.B)) return r;
+  if (int r = map_2d(&tw1_hi, w->w1_hi, d.K1, fl * 2 * d.C, 128)) return r;
+  if (int r = map_2d(&tw1_lo, w->w1_lo, d.K1, fl * 2 * d.C, 128)) return r;
+  if (int r = map_2d(&tw2_hi, w->w2_hi, d.C, fl * d.N2, 128)) return r;
+  if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 128)) return r;
+  if (int r = map_2d(&tse_hi, w->w2_hi, d.C, fl * d.N2, 16)) return r;
+  if (int r = map_2d(&tse_lo, w->w2_lo, d.C, fl * d.N2, 16)) return r;
+  if (int r = map_act(&to_hi, x_out, d.C, d.Tp, d.B)) return r;
+  if (int r = map_act(&to_lo, x_out + plane, d.C, d.Tp, d.B)) return r;
+  const size_t idx = (size_t)flow * d.L + layer;
+  LayerArgs a{};
+  a.b1 = w->b1 + idx * 2 * d.C; a.b2 = w->b2 + idx * d.C; a.eo_b = w->eo_b + (size_t)flow * CWG_EO_PAD;
+  a.eo = eo; a.x_hi = x_in; a.x_lo = x_in + plane;
+  a.Tp = d.Tp; a.dil = 1 << layer;
+  a.w1_row0 = (int)(idx * 2 * d.C); a.w2_row0 = (int)(idx * d.N2);
+  a.has_res = layer < d.L - 1; a.first = layer == 0;
+  dim3 grid((unsigned)((d.Tp + 127) / 128), d.B);
+  if (npass == 3) {
+    if (int r = set_smem(k_layer_tc<3>, L_SMEM)) return r;
+    k_layer_tc<3><<<grid, 224, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
+  } else {
+    if (int r = set_smem(k_layer_tc<1>, L_SMEM)) return r;
+    k_layer_tc<1><<<grid, 224, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
+  }
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cwg

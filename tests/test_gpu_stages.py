@@ -1,0 +1,129 @@
+"""GPU stage-level checks through the C ABI: each tensor-core stage (cond GEMM, WN layer) is
+compared with the fp32 CUDA-core stage on the same inputs, and the CUDA-core stages with a
+torch fp64 evaluation of the packed form.  These bisect the pipeline when end-to-end parity fails."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cookietts_b200 import WaveGlow, _cabi
+from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict
+from tests.test_cabi_cpu import module_kwargs
+
+pytestmark = pytest.mark.gpu
+
+CFG = OracleConfig()          # 12 flows, 8 x 256
+B, TM = 2, 9                  # T' = 288: two full 128-step tiles and a ragged one
+
+
+def make(precision):
+    sd = synthetic_state_dict(CFG, 1234)
+    m = WaveGlow(precision=precision, **module_kwargs(CFG))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.cuda().eval()
+    m._ensure_packed()
+    return m
+
+
+@pytest.fixture(scope="module")
+def models():
+    return {p: make(p) for p in ("ffma", "bf16x3", "bf16")}
+
+
+def workspace(model, mode):
+    lib = _cabi.load()
+    n = lib.cwg_workspace_bytes(model._ccfg, mode, B, TM)
+    ws = torch.zeros(n + 1024, dtype=torch.uint8, device="cuda")
+    ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+    return ws, ptr, n
+
+
+def split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()       # [2, ...]: hi plane then lo plane
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+def run_cond(model, mode, flow, mel, out):
+    lib = _cabi.load()
+    bias = model._cond_bias(B, None)
+    ws, ptr, n = workspace(model, mode)
+    _cabi.check(lib.cwg_cond(model._ccfg, model._cw, mode, flow, mel.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                             ptr, n, B, TM, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("flow", [0, 11])
+def test_cond_stage(models, flow):
+    pc = models["ffma"].pack_config
+    tp, H = TM * pc.phases, pc.cond_hidden
+    torch.manual_seed(0)
+    mel = (torch.randn(B, 80, TM, device="cuda") * 2 - 5).clamp(-11.5, 2.0)
+    h_f = torch.zeros(B, tp, H, device="cuda")
+    run_cond(models["ffma"], _cabi.MODE_FFMA, flow, mel, h_f)
+    # fp64 evaluation of the packed form
+    pk = models["ffma"]._packed
+    mel4 = torch.zeros(B, TM, pc.taps * 80, device="cuda", dtype=torch.float64)
+    for j in range(pc.taps):
+        mel4[:, j:, j * 80:(j + 1) * 80] = mel.double().transpose(1, 2)[:, :TM - j]
+    ref = (mel4.reshape(B * TM, -1) @ pk["cond_w_f32"][flow].double().T).reshape(B, tp, H) + pk["cond_b_base"][flow].double()
+    assert rel_err(h_f, ref) < 1e-5
+    for prec, mode, tol in (("bf16x3", _cabi.MODE_BF16X3, 2e-5), ("bf16", _cabi.MODE_BF16, 2e-2)):
+        h_t = torch.zeros(2, B, tp, H, device="cuda", dtype=torch.bfloat16)
+        run_cond(models[prec], mode, flow, mel, h_t)
+        got = h_t[0].float() + (h_t[1].float() if prec == "bf16x3" else 0)
+        assert torch.isfinite(got).all()
+        assert rel_err(got, ref) < tol, prec
+
+
+@pytest.mark.parametrize("layer", [0, 3, 6, 7])
+def test_layer_stage(models, layer):
+    lib = _cabi.load()
+    pc = models["ffma"].pack_config
+    tp, H, Cc = TM * pc.phases, pc.cond_hidden, pc.n_channels
+    flow = 5
+    torch.manual_seed(1 + layer)
+    x = torch.randn(B, tp, Cc, device="cuda")
+    h2 = torch.randn(B, tp, H, device="cuda")
+    eo0 = torch.randn(B, tp, 16, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    # fp32 CUDA-core stage
+    mf = models["ffma"]
+    ws, ptr, n = workspace(mf, _cabi.MODE_FFMA)
+    xo_f, eo_f = torch.zeros_like(x), eo0.clone()
+    _cabi.check(lib.cwg_wn_layer(mf._ccfg, mf._cw, _cabi.MODE_FFMA, flow, layer, x.data_ptr(), xo_f.data_ptr(),
+                                 h2.data_ptr(), eo_f.data_ptr(), ptr, n, B, TM, stream))
+    torch.cuda.synchronize()
+    # fp64 evaluation of the packed form
+    pk = mf._packed
+    d = 2 ** layer
+    xp = torch.zeros(B, tp + 2 * d, Cc, device="cuda", dtype=torch.float64)
+    xp[:, d:d + tp] = x.double()
+    a = torch.cat([xp[:, 0:tp], xp[:, d:d + tp], xp[:, 2 * d:2 * d + tp], h2.double()], dim=2)
+    pre = a @ pk["w1_f32"][flow, layer].double().T + pk["b1"][flow, layer].double()
+    acts = torch.tanh(pre[..., :Cc]) * torch.sigmoid(pre[..., Cc:])
+    rs = acts @ pk["w2_f32"][flow, layer].double().T
+    x_ref = x.double() + rs[..., :Cc] + pk["b2"][flow, layer].double()
+    eo_ref = (pk["eo_b"][flow].double() if layer == 0 else eo0.double()) + rs[..., Cc:]
+    assert rel_err(eo_f, eo_ref) < 1e-5
+    if layer < pc.n_layers - 1:
+        assert rel_err(xo_f, x_ref) < 1e-5
+    for prec, mode, tol in (("bf16x3", _cabi.MODE_BF16X3, 5e-5), ("bf16", _cabi.MODE_BF16, 3e-2)):
+        mt = models[prec]
+        xin = split(x)
+        h2p = split(h2)
+        xo_t = torch.zeros_like(xin)
+        eo_t = eo0.clone()
+        _cabi.check(lib.cwg_wn_layer(mt._ccfg, mt._cw, mode, flow, layer, xin.data_ptr(), xo_t.data_ptr(),
+                                     h2p.data_ptr(), eo_t.data_ptr(), 0, 0, B, TM, stream))
+        torch.cuda.synchronize()
+        assert torch.isfinite(eo_t).all()
+        assert rel_err(eo_t, eo_ref) < tol, (prec, "eo")
+        if layer < pc.n_layers - 1:
+            got = xo_t[0].float() + xo_t[1].float()
+            assert rel_err(got, x_ref) < tol, (prec, "x")
