@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py - WaveGlow inverse pass (mel -> wave) throughput on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one `WaveGlow.infer` over one batch of synthetic 80-bin mels with injected z.
+At N=1 the workload is BASELINE.json configs[1]: 12-flow / 256-channel WaveGlow, batch 16 x 10 s
+(T_mel = 861), sigma 0.666, the fp32-accurate path (bf16x3 split operands, fp32 accumulate).
+For N>1 every rank processes its own batch of the same shape (weak scaling, the path shards by
+utterance) and rank 0 gathers the waveforms over NCCL inside the timed region.
+
+One JSON line is printed by rank 0.  `value` = audio samples / s with inputs resident in HBM;
+`e2e` = the same through host buffers (pinned H2D of mel+z, D2H of the waveform) per step;
+`roofline` = the WN layer kernel's algorithmic FLOP/s (timed with CUDA events around every
+layer launch inside the timed steps) against the measured bf16 peak; `cpu_baseline` = the
+torch-op CPU port of the reference on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 22050
+MODEL_KW = dict(n_mel_channels=80, n_flows=12, n_group=8, n_early_every=4, n_early_size=2,
+                WN_config=dict(n_layers=8, n_channels=256, kernel_size=3, speaker_embed_dim=0, rezero=False),
+                win_length=1024, hop_length=256)
+METRIC = "waveglow_infer_audio_samples_per_sec"
+
+
+def algorithmic_macs(C=256, L=8, H=256, n_mel=80, G=8, J=4, flows=((8, 4),) * 4 + ((6, 3),) * 4 + ((4, 2),) * 4):
+    """the reference's dense MACs per audio sample, and the part one WN layer
+    launch covers per group-step (in_layer + cond_layers[2] slice + res_skip)."""
+    per_step = 0
+    for n_rem, n_half in flows:
+        per_step += n_half * C + (n_mel * G * H + H * H + H * 2 * C * L) + L * 3 * C * 2 * C \
+            + ((L - 1) * 2 * C * C + C * C) + C * 2 * n_half + n_rem * n_rem
+    per_sample = per_step / G + J * n_mel * n_mel
+    layer_step = [3 * C * 2 * C + H * 2 * C + (2 * C * C if i < L - 1 else C * C) for i in range(L)]
+    return per_sample, layer_step
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(batch, t_mel, repeats, warmup):
+    """The reference's CPU implementation of the path (torch-op port in oracle/, pinned to golden
+    vectors of the real reference) on all host threads; returns (samples/s, seconds per run, threads)."""
+    import torch
+    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict, synthetic_inputs
+    from oracle.waveglow_torch_port import TorchPort
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = OracleConfig()
+    sd = synthetic_state_dict(cfg, 1234)
+    mel, z = synthetic_inputs(cfg, batch, t_mel, 0)
+    port = TorchPort(sd, cfg, torch.float32)
+    times = []
+    for i in range(warmup + repeats):
+        t = time.perf_counter()
+        out = port.infer(mel, z, 0.666)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    sec = float(np.median(times))
+    return out.size / sec, sec, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the workload: 1 utterance x 2 s of the batch-16 x 10-s job per step
+    b, tm = 1, 172
+    value, sec, threads = cpu_reference_run(b, tm, max(args.steps, 1), max(min(args.warmup, 1), 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "WaveGlow 12-flow/256-ch inverse pass, batch 16 x 10 s mels (T_mel 861), sigma 0.666, injected z",
+                   "sample": f"{b} utterance x {tm} mel frames per step"},
+        "xrt": value / SR,
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{b} x {tm} mel frames ({b * tm * 256} samples) per step, torch-op CPU port of glow.py::WaveGlow.infer, fp32"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "ffma"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--t-mel", type=int, default=861)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cookietts_b200 import WaveGlow
+    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    B, Tm = args.batch, args.t_mel
+    T = Tm * 256
+
+    # model: reference layout, random init (seed 1234) with non-zero `end`
+    sd = synthetic_state_dict(OracleConfig(), 1234)
+    model = WaveGlow(precision=args.precision, **MODEL_KW)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.to(dev).eval()
+
+    # synthetic inputs in pinned host memory (per rank: different seed)
+    g = torch.Generator().manual_seed(1000 + rank)
+    mel_h = (torch.randn(B, 80, Tm, generator=g) * 2.0 - 5.0).clamp_(-11.5129, 2.0).pin_memory()
+    z_h = torch.randn(B, T, generator=g).pin_memory()
+    out_h = torch.empty(B, T).pin_memory()
+    mel_d, z_d = mel_h.to(dev), z_h.to(dev)
+    gather_buf = [torch.empty(B, T, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(audio):
+        if world > 1:     # final waveform gather: the only collective of the path
+            dist.gather(audio, gather_buf, dst=0)
+
+    def step_resident(events=None):
+        audio = model.infer(mel_d, sigma=0.666, z=z_d, layer_events=events)
+        gather(audio)
+        return audio
+
+    def step_e2e():
+        m = mel_h.to(dev, non_blocking=True)
+        zz = z_h.to(dev, non_blocking=True)
+        audio = model.infer(m, sigma=0.666, z=zz)
+        gather(audio)
+        out_h.copy_(audio, non_blocking=True)
+        return audio
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_layers_total = 12 * 8
+    ev_b = [[torch.cuda.Event(enable_timing=True) for _ in range(n_layers_total)] for _ in range(args.steps)]
+    ev_e = [[torch.cuda.Event(enable_timing=True) for _ in range(n_layers_total)] for _ in range(args.steps)]
+
+    for _ in range(warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: inputs resident in HBM -------------------------------------------
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        step_resident((ev_b[i], ev_e[i]))
+    t1.record()
+    barrier()
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
+    clocks = sampler.stop() if rank == 0 else None
+    layer_ms = np.array([[ev_b[i][j].elapsed_time(ev_e[i][j]) for j in range(n_layers_total)] for i in range(args.steps)])
+
+    # ---- timed region 2: end to end through host buffers ----------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    finite = bool(torch.isfinite(out_h).all())
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    samples_per_step = world * B * T
+    value = samples_per_step * args.steps / (ms_total * 1e-3)
+    e2e = samples_per_step * args.steps / (ms_e2e * 1e-3)
+    per_sample_macs, layer_step_macs = algorithmic_macs()
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    # dominant kernel: k_layer_tc (one launch per WN layer); algorithmic FLOPs per launch / avg duration
+    steps_per_launch = B * Tm * 32
+    flops_per_launch = np.array([2.0 * m * steps_per_launch for m in layer_step_macs] * 12)
+    layer_avg_ms = layer_ms.mean(axis=0)
+    achieved = float(flops_per_launch.sum() / (layer_avg_ms.sum() * 1e-3) / 1e12)
+    passes = {"bf16x3": 3, "bf16": 1, "ffma": 1}[args.precision]
+    roofline = {
+        "bound": "tensor", "kernel": "k_layer_tc" if args.precision != "ffma" else "k_sgemm",
+        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        "peak_source": peak_src, "traffic": None,
+        "launches_timed": int(layer_ms.size), "avg_launch_ms": float(layer_avg_ms.mean()),
+        "layer_share_of_step": float(layer_avg_ms.sum() / (ms_total / args.steps)),
+        "mma_passes": passes, "issued_mma_tflops": achieved * passes,
+        "note": "achieved = reference's dense FLOPs per layer launch (SURVEY 8d) / CUDA-event duration; "
+                "bf16x3 issues 3 bf16 MMAs per algorithmic MAC, so frac <= 1/3 by construction in that mode",
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16x3": "bf16x3 (hi+lo split bf16 operands, 3 MMAs, fp32 accumulate)",
+                  "bf16": "bf16 (fp32 accumulate, hi+lo residual)", "ffma": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"WaveGlow 12-flow/256-ch inverse pass, batch {B} x {Tm} mel frames ({T / SR:.1f} s) per GPU, "
+                               f"sigma 0.666, injected z, random-init weights (seed 1234, end ~ N(0,0.02))",
+                   "precision": args.precision, "batch_per_gpu": B, "t_mel": Tm, "samples_per_step": samples_per_step,
+                   "parallelism": f"dp{world} by utterance", "l2": "working set (1.4 GB workspace per step) >> 126 MB L2, no flush needed"},
+        "xrt": value / SR,
+        "algorithmic_tflops": value * per_sample_macs * 2 / 1e12,
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(mel_h.numel() * 4 + z_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
+                "xrt": e2e / SR},
+        "gpu_launches": int(model.launch_count() * args.steps),
+        "roofline": roofline,
+        "output_finite": finite,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        b, tm = 1, 172
+        v, sec, threads = cpu_reference_run(b, tm, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "xrt": v / SR,
+                                "sample": f"{b} x {tm} mel frames ({b * tm * 256} samples), median of 3 after 1 warm-up, "
+                                          f"torch-op CPU port of glow.py::WaveGlow.infer, fp32"}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

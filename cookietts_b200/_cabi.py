@@ -33,7 +33,7 @@ class CwgWeights(C.Structure):
 
 
 EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
-           "cwg_infer", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary")
+           "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary")
 
 
 class CwgError(RuntimeError):
@@ -65,6 +65,8 @@ def load():
     lib.cwg_infer.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_infer_profiled.restype = C.c_int
+    lib.cwg_infer_profiled.argtypes = lib.cwg_infer.argtypes + [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
     lib.cwg_cond.restype = C.c_int
     lib.cwg_cond.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p,

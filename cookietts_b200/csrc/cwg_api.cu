@@ -167,7 +167,17 @@ int cwg_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
               const float* mel, const float* cond_bias, const float* z, float sigma,
               float* audio, void* workspace, size_t workspace_bytes,
               int batch, int t_mel, void* cuda_stream) {
+  return cwg_infer_profiled(cfg, w, mode, mel, cond_bias, z, sigma, audio, workspace, workspace_bytes,
+                            batch, t_mel, cuda_stream, nullptr, nullptr, 0);
+}
+
+int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
+                       const float* mel, const float* cond_bias, const float* z, float sigma,
+                       float* audio, void* workspace, size_t workspace_bytes,
+                       int batch, int t_mel, void* cuda_stream,
+                       void** layer_ev_begin, void** layer_ev_end, int n_events) {
   if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
+  CWG_REQUIRE(n_events == 0 || (layer_ev_begin && layer_ev_end), "event arrays are NULL");
   CWG_REQUIRE(mel && cond_bias && z && audio, "NULL tensor argument");
   CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
   Dims d = make_dims(cfg, batch, t_mel);
@@ -190,11 +200,14 @@ int cwg_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
       if (int r = launch_cond_ffma(d, w, k, mel, cond_bias, ws.h2, s)) return r;
     }
     for (int i = 0; i < L; ++i) {                          // glow.py:201-220
+      const int ev = (F - 1 - k) * L + i;
+      if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_begin[ev], s));
       if (tc) {
         if (int r = launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s)) return r;
       } else {
         if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
       }
+      if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_end[ev], s));
     }
     // coupling inverse + W^-1 of flow k, then start conv of flow k-1 (glow.py:329-347, :189)
     if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s)) return r;

@@ -190,12 +190,13 @@ class WaveGlow(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
-    def infer(self, spect, speaker_id=None, sigma=1.0, *, speaker_ids=None, z=None):
+    def infer(self, spect, speaker_id=None, sigma=1.0, *, speaker_ids=None, z=None, layer_events=None):
         """mel [B, n_mel, T_mel] -> audio [B, T_mel*hop] (fp32, on the module's device).
 
         `speaker_id` is the reference keyword (glow.py:314); `speaker_ids` is what
         `Denoiser`/notebooks pass (denoiser.py:39).  `z` ([B, T], standard normal) injects the
-        latent the reference draws internally; None draws it here."""
+        latent the reference draws internally; None draws it here.  `layer_events` (optional,
+        (begin, end) lists of torch.cuda.Event) are recorded around each WN-layer launch."""
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("cookietts_b200.WaveGlow.infer needs the module on a CUDA device (no CPU fallback)")
@@ -230,8 +231,25 @@ class WaveGlow(nn.Module):
             ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
             audio = torch.empty(batch, T, device=dev, dtype=torch.float32)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _cabi.check(lib.cwg_infer(self._ccfg, self._cw, mode, mel.data_ptr(), cond_bias.data_ptr(),
-                                      z.data_ptr(), float(sigma), audio.data_ptr(), ws_ptr,
-                                      self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
-                                      batch, t_mel, stream))
+            ws_bytes = self._workspace.numel() - (ws_ptr - self._workspace.data_ptr())
+            if layer_events is None:
+                _cabi.check(lib.cwg_infer(self._ccfg, self._cw, mode, mel.data_ptr(), cond_bias.data_ptr(),
+                                          z.data_ptr(), float(sigma), audio.data_ptr(), ws_ptr, ws_bytes,
+                                          batch, t_mel, stream))
+            else:
+                import ctypes
+                begin, end = layer_events
+                for e in list(begin) + list(end):          # torch creates the handle lazily
+                    if not e.cuda_event:
+                        e.record(torch.cuda.current_stream(dev))
+                arr_b = (ctypes.c_void_p * len(begin))(*[e.cuda_event for e in begin])
+                arr_e = (ctypes.c_void_p * len(end))(*[e.cuda_event for e in end])
+                _cabi.check(lib.cwg_infer_profiled(self._ccfg, self._cw, mode, mel.data_ptr(), cond_bias.data_ptr(),
+                                                   z.data_ptr(), float(sigma), audio.data_ptr(), ws_ptr, ws_bytes,
+                                                   batch, t_mel, stream, arr_b, arr_e, len(begin)))
         return audio
+
+    def launch_count(self) -> int:
+        """Kernels launched by one `infer` call in the current precision mode."""
+        lib = _cabi.load()
+        return int(lib.cwg_launch_count(_cabi.make_config(self.pack_config), _cabi.MODES[self.precision]))

@@ -97,6 +97,16 @@ int cwg_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
               float* audio, void* workspace, size_t workspace_bytes,
               int batch, int t_mel, void* cuda_stream);
 
+/* Same as cwg_infer; additionally records the CUDA events layer_ev_begin[e] / layer_ev_end[e]
+ * (cudaEvent_t handles owned by the caller) on `cuda_stream` around the e-th WN-layer launch,
+ * e = (n_flows-1-flow)*n_layers + layer, for e < n_events.  bench.py uses it to time the dominant
+ * kernel inside the real step. */
+int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
+                       const float* mel, const float* cond_bias, const float* z, float sigma,
+                       float* audio, void* workspace, size_t workspace_bytes,
+                       int batch, int t_mel, void* cuda_stream,
+                       void** layer_ev_begin, void** layer_ev_end, int n_events);
+
 /* Number of kernels cwg_infer launches for this configuration (bench.py's gpu_launches). */
 int cwg_launch_count(const cwg_config* cfg, int mode);
 

@@ -50,3 +50,14 @@ def test_wn_is_not_vacuous():
     a = infer_with_z(sd, cfg, g["mel"], g["z"], float(g["sigma"]), np.float64)
     b = infer_with_z(sd0, cfg, g["mel"], g["z"], float(g["sigma"]), np.float64)
     assert max_abs(a, b) > 1e-2
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "rezero", "config1"])
+def test_torch_port_matches_reference(name):
+    """The torch-op CPU port used as bench.py's CPU baseline is pinned to the same vectors."""
+    import torch
+    from oracle.waveglow_torch_port import TorchPort
+    cfg, sd, g = load_golden(name)
+    out = TorchPort(sd, cfg, torch.float32).infer(g["mel"], g["z"], float(g["sigma"]))
+    assert max_abs(out, g["audio_ref_fp32"]) < 2e-5
+    assert snr_db(g["audio_ref_fp64"], out) > 100.0
