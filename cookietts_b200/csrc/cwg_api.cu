@@ -98,6 +98,9 @@ extern "C" {
 
 int cwg_abi_version(void) { return CWG_ABI_VERSION; }
 
+// Debug only (not in cwg.h): the WN layer kernel writes 16 clock64 stamps per CTA into `buf`.
+void cwg_debug_set_timing(void* buf) { cwg::debug_set_timing((long long*)buf); }
+
 const char* cwg_last_error(void) { return cwg::g_err; }
 
 size_t cwg_workspace_bytes(const cwg_config* cfg, int mode, int batch, int t_mel) {

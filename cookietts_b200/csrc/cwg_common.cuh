@@ -68,7 +68,7 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
                          const float* eo, void* x_out, cudaStream_t s);
 
 // ---- launchers implemented in cwg_tc.cu (tcgen05 / TMA path) ----
-int tc_workspace_extra(const Dims& d, size_t* bytes);
+void debug_set_timing(long long* buf);
 int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, const float* mel,
                    const float* cond_bias, __nv_bfloat16* h2_planes, __nv_bfloat16* mel4_planes,
                    cudaStream_t s);

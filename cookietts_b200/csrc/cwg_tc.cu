@@ -301,16 +301,65 @@ struct LayerArgs {
   int Tp, dil;
   int w1_row0, w2_row0;
   int has_res, first;
+  long long* dbg;         // optional per-CTA clock64 stamps (cwg_debug_set_timing), 16 per CTA
 };
 
-constexpr int L_NA = 8, L_NB = 5;
-constexpr int L_OFF_B = L_NA * TILE_A;                 // 131072
-constexpr int L_OFF_WSE = L_OFF_B + L_NB * TILE_A;     // 212992
-constexpr int L_OFF_BAR = L_OFF_WSE + 16384;           // 229376
-constexpr int L_SMEM = L_OFF_BAR + 256 + 1024;         // 230656
+long long* g_dbg_timing = nullptr;
+
+// Shared memory: one pool of 12 16-KB tile slots.
+//   GEMM1: activation (A) tiles cycle through slots 0..3, weight (B) tiles through slots 4..11.
+//   gate : acts hi -> slots 0..3, acts lo -> slots 4..7 (GEMM1 is complete by then).
+//   GEMM2: W2 tiles cycle through slots 8..11; epilogue-2 stages x_new hi/lo in slots 0..7.
+// Every slot has its own full/empty mbarrier pair and its own phase bit (kept in a bit mask by
+// the producer and by the consumer), so the slot sequences above need no common ring modulus.
+constexpr int L_NS = 12, L_NA = 4;
+constexpr int L_OFF_WSE = L_NS * TILE_A;               // 196608
+constexpr int L_OFF_B1 = L_OFF_WSE + 16384;            // 212992
+constexpr int L_OFF_B2 = L_OFF_B1 + 2048;              // 215040
+constexpr int L_OFF_BAR = L_OFF_B2 + 1024;             // 216064
+constexpr int L_SMEM = L_OFF_BAR + 256 + 1024;         // 217344
+constexpr int L_THREADS = 384;                         // 12 warps: TMA-A, MMA, TMA-B, spare, 8 epilogue
+constexpr int L_EPI_THREADS = 256;
+
+// 2 x 16 TMEM columns, issued without waiting; pair with tmem_wait32.
+__device__ __forceinline__ void tmem_issue16x2(uint32_t ta, uint32_t tb, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta), "r"(tb)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_issue16(uint32_t ta, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta)
+      : "memory");
+}
+// tcgen05.wait::ld with the destination registers threaded through the asm ("+r"), so that no
+// use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_wait32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
 
 template <int NPASS>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(L_THREADS, 1)
 k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
            const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
            const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
@@ -320,11 +369,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   constexpr int PL = NPASS == 3 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L_OFF_BAR);
-  uint64_t* a_empty = a_full + L_NA;
-  uint64_t* b_full = a_empty + L_NA;
-  uint64_t* b_empty = b_full + L_NB;
-  uint64_t* wse_full = b_empty + L_NB;
+  float* b1s = reinterpret_cast<float*>(smem + L_OFF_B1);
+  float* b2s = reinterpret_cast<float*>(smem + L_OFF_B2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L_OFF_BAR);
+  uint64_t* empty = full + L_NS;
+  uint64_t* wse_full = empty + L_NS;
   uint64_t* acc1_full = wse_full + 1;
   uint64_t* acts_ready = acc1_full + 1;
   uint64_t* acc2_full = acts_ready + 1;
@@ -332,21 +381,25 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * 128, b = blockIdx.y;
-  auto slot_a = [&](int i) { return smem + i * TILE_A; };
-  auto slot_b = [&](int i) { return smem + L_OFF_B + i * TILE_A; };
+  auto slot = [&](int i) { return smem + i * TILE_A; };
   auto wse = [&](int plane, int kb) { return smem + L_OFF_WSE + plane * 8192 + kb * 2048; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < L_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < L_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, 128); mbar_init(acc2_full, 1);
+    for (int i = 0; i < L_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, L_EPI_THREADS); mbar_init(acc2_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 4) {   // biases -> smem (read as broadcast float4 in the epilogues)
+    const int e = threadIdx.x - 128;
+    b1s[e] = __ldg(a.b1 + e); b1s[256 + e] = __ldg(a.b1 + 256 + e); b2s[e] = __ldg(a.b2 + e);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  long long* dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define CWG_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
     // ---------------- producer A: activation tiles (3 dilated taps of x, then the cond hidden H2)
@@ -356,87 +409,100 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
       if (NPASS == 3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
     }
-    int s = 0; uint32_t ph = 0;
+    int s = 0; uint32_t pm = 0;
     for (int kb = 0; kb < 16; ++kb) {
       for (int pl = 0; pl < PL; ++pl) {
-        mbar_wait(&a_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&a_full[s], TILE_A);
+        mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
+        pm ^= 1u << s;
+        mbar_arrive_expect_tx(&full[s], TILE_A);
         if (kb < 12) {
           int tap = kb >> 2, cb = kb & 3;
-          tma_load_3d(slot_a(s), pl ? &tm_x_lo : &tm_x_hi, &a_full[s], cb * 64, t0 + (tap - 1) * a.dil, b);
+          tma_load_3d(slot(s), pl ? &tm_x_lo : &tm_x_hi, &full[s], cb * 64, t0 + (tap - 1) * a.dil, b);
         } else {
-          tma_load_3d(slot_a(s), pl ? &tm_h_lo : &tm_h_hi, &a_full[s], (kb - 12) * 64, t0, b);
+          tma_load_3d(slot(s), pl ? &tm_h_lo : &tm_h_hi, &full[s], (kb - 12) * 64, t0, b);
         }
-        ring_advance(s, ph, L_NA);
+        s = (s + 1 == L_NA) ? 0 : s + 1;
       }
     }
-  } else if (warp == 6 && lane == 0) {
+  } else if (warp == 2 && lane == 0) {
     // ---------------- producer B: weight tiles [128 rows x 64 k]
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w2_hi);
-    int s = 0; uint32_t ph = 0;
+    int s = L_NA; uint32_t pm = 0;
     for (int kb = 0; kb < 16; ++kb)
       for (int q = 0; q < 4; ++q)
         for (int pl = 0; pl < PL; ++pl) {
-          mbar_wait(&b_empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&b_full[s], TILE_A);
-          tma_load_2d(slot_b(s), pl ? &tm_w1_lo : &tm_w1_hi, &b_full[s], kb * 64, a.w1_row0 + q * 128);
-          ring_advance(s, ph, L_NB);
+          mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
+          pm ^= 1u << s;
+          mbar_arrive_expect_tx(&full[s], TILE_A);
+          tma_load_2d(slot(s), pl ? &tm_w1_lo : &tm_w1_hi, &full[s], kb * 64, a.w1_row0 + q * 128);
+          s = (s + 1 == L_NS) ? L_NA : s + 1;
         }
-    if (a.has_res)
+    if (a.has_res) {
+      s = 8;
       for (int kb = 0; kb < 4; ++kb)
         for (int h = 0; h < 2; ++h)
           for (int pl = 0; pl < PL; ++pl) {
-            mbar_wait(&b_empty[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&b_full[s], TILE_A);
-            tma_load_2d(slot_b(s), pl ? &tm_w2_lo : &tm_w2_hi, &b_full[s], kb * 64, a.w2_row0 + h * 128);
-            ring_advance(s, ph, L_NB);
+            mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
+            pm ^= 1u << s;
+            mbar_arrive_expect_tx(&full[s], TILE_A);
+            tma_load_2d(slot(s), pl ? &tm_w2_lo : &tm_w2_hi, &full[s], kb * 64, a.w2_row0 + h * 128);
+            s = (s + 1 == L_NS) ? 8 : s + 1;
           }
+    }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer
-    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    int sa = 0, sb = L_NA; uint32_t cm = 0;
+    auto take = [&](int& s, int lo, int hi) {     // wait for the tile in slot s, return (address, slot), advance
+      mbar_wait(&full[s], (cm >> s) & 1u);
+      cm ^= 1u << s;
+      int cur = s;
+      s = (s + 1 == hi) ? lo : s + 1;
+      return cur;
+    };
     // GEMM1: pre[128 x 512] = [x taps | H2] (K = 1024) x W1^T, accumulators in TMEM columns 0..511
     for (int kb = 0; kb < 16; ++kb) {
-      uint32_t a_hi, a_lo = 0; int sa_hi = sa, sa_lo = 0;
-      mbar_wait(&a_full[sa], pa); a_hi = smem_u32(slot_a(sa)); ring_advance(sa, pa, L_NA);
-      if (NPASS == 3) { sa_lo = sa; mbar_wait(&a_full[sa], pa); a_lo = smem_u32(slot_a(sa)); ring_advance(sa, pa, L_NA); }
+      const int sa_hi = take(sa, 0, L_NA);
+      const int sa_lo = NPASS == 3 ? take(sa, 0, L_NA) : 0;
+      if (kb == 0) CWG_STAMP(5);
       for (int q = 0; q < 4; ++q) {
-        uint32_t b_hi, b_lo = 0; int sb_hi = sb, sb_lo = 0;
-        mbar_wait(&b_full[sb], pb); b_hi = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB);
-        if (NPASS == 3) { sb_lo = sb; mbar_wait(&b_full[sb], pb); b_lo = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB); }
+        const int sb_hi = take(sb, L_NA, L_NS);
+        const int sb_lo = NPASS == 3 ? take(sb, L_NA, L_NS) : 0;
         tc_fence_after_sync();
         const uint32_t d = tmem + q * 128;
-        issue_kblock(a_hi, b_hi, d, IDESC_N128, kb == 0);
+        issue_kblock(smem_u32(slot(sa_hi)), smem_u32(slot(sb_hi)), d, IDESC_N128, kb == 0);
         if (NPASS == 3) {
-          issue_kblock(a_lo, b_hi, d, IDESC_N128, false);
-          issue_kblock(a_hi, b_lo, d, IDESC_N128, false);
+          issue_kblock(smem_u32(slot(sa_lo)), smem_u32(slot(sb_hi)), d, IDESC_N128, false);
+          issue_kblock(smem_u32(slot(sa_hi)), smem_u32(slot(sb_lo)), d, IDESC_N128, false);
         }
-        umma_commit(&b_empty[sb_hi]);
-        if (NPASS == 3) umma_commit(&b_empty[sb_lo]);
+        umma_commit(&empty[sb_hi]);
+        if (NPASS == 3) umma_commit(&empty[sb_lo]);
       }
-      umma_commit(&a_empty[sa_hi]);
-      if (NPASS == 3) umma_commit(&a_empty[sa_lo]);
+      umma_commit(&empty[sa_hi]);
+      if (NPASS == 3) umma_commit(&empty[sa_lo]);
     }
     umma_commit(acc1_full);
-    // GEMM2: [res | folded end] = acts (smem, A slots 0..3 hi / 4..7 lo) x W2^T
+    CWG_STAMP(6);
+    // GEMM2: [res | folded end] = acts (smem slots 0..3 hi / 4..7 lo) x W2^T
     mbar_wait(acts_ready, 0);
     tc_fence_after_sync();
     mbar_wait(wse_full, 0);
+    CWG_STAMP(7);
+    sb = 8;
     for (int kb = 0; kb < 4; ++kb) {
-      const uint32_t a_hi = smem_u32(slot_a(kb)), a_lo = smem_u32(slot_a(4 + kb));
+      const uint32_t a_hi = smem_u32(slot(kb)), a_lo = smem_u32(slot(4 + kb));
       if (a.has_res) {
         for (int h = 0; h < 2; ++h) {
-          uint32_t b_hi, b_lo = 0; int sb_hi = sb, sb_lo = 0;
-          mbar_wait(&b_full[sb], pb); b_hi = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB);
-          if (NPASS == 3) { sb_lo = sb; mbar_wait(&b_full[sb], pb); b_lo = smem_u32(slot_b(sb)); ring_advance(sb, pb, L_NB); }
+          const int sb_hi = take(sb, 8, L_NS);
+          const int sb_lo = NPASS == 3 ? take(sb, 8, L_NS) : 0;
           tc_fence_after_sync();
           const uint32_t d = tmem + h * 128;
-          issue_kblock(a_hi, b_hi, d, IDESC_N128, kb == 0);
+          issue_kblock(a_hi, smem_u32(slot(sb_hi)), d, IDESC_N128, kb == 0);
           if (NPASS == 3) {
-            issue_kblock(a_lo, b_hi, d, IDESC_N128, false);
-            issue_kblock(a_hi, b_lo, d, IDESC_N128, false);
+            issue_kblock(a_lo, smem_u32(slot(sb_hi)), d, IDESC_N128, false);
+            issue_kblock(a_hi, smem_u32(slot(sb_lo)), d, IDESC_N128, false);
           }
-          umma_commit(&b_empty[sb_hi]);
-          if (NPASS == 3) umma_commit(&b_empty[sb_lo]);
+          umma_commit(&empty[sb_hi]);
+          if (NPASS == 3) umma_commit(&empty[sb_lo]);
         }
       }
       const uint32_t d = tmem + 256;
@@ -447,88 +513,121 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       }
     }
     umma_commit(acc2_full);
-  } else if (warp >= 2 && warp <= 5) {
-    // ---------------- epilogue warps: TMEM lane quarter = warp % 4, one row (group-step) per thread
-    const int quarter = warp & 3, row = quarter * 32 + lane;
+    CWG_STAMP(8);
+  } else if (warp >= 4) {
+    // ---------------- 8 epilogue warps: TMEM lane quarter = warp % 4 (one group-step per lane),
+    // column half = (warp - 4) / 4 (channels [128*half, 128*half + 128)).
+    const int quarter = warp & 3, half = (warp - 4) >> 2, row = quarter * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool valid = t0 + row < a.Tp;
     const size_t m = (size_t)b * a.Tp + (size_t)min(t0 + row, a.Tp - 1);
-    const float4* b1t = reinterpret_cast<const float4*>(a.b1);
-    const float4* b1s = reinterpret_cast<const float4*>(a.b1 + 256);
+    const bool stamp = dbg && warp == 4 && lane == 0;
+    const float4* b1t = reinterpret_cast<const float4*>(b1s);
+    const float4* b1g = reinterpret_cast<const float4*>(b1s + 256);
 
-    // gate: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) -> bf16 planes in A slots (GEMM2's A operand)
+    // gate: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) -> bf16 planes in slots 0..7 (GEMM2's A operand)
+    if (stamp) dbg[0] = clock64();
     mbar_wait(acc1_full, 0);
     tc_fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < 16; ++c) {
-      float ta[16], sg[16], act[16];
-      tmem_ld16x2_sync(trow + c * 16, trow + 256 + c * 16, ta, sg);
+    if (stamp) dbg[1] = clock64();
+    {
+      uint32_t buf[2][32];
+      const int c0 = half * 8;
+      tmem_issue16x2(trow + c0 * 16, trow + 256 + c0 * 16, buf[0]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 bt = __ldg(b1t + c * 4 + q), bs = __ldg(b1s + c * 4 + q);
-        act[4 * q + 0] = gate<NPASS>(ta[4 * q + 0] + bt.x, sg[4 * q + 0] + bs.x);
-        act[4 * q + 1] = gate<NPASS>(ta[4 * q + 1] + bt.y, sg[4 * q + 1] + bs.y);
-        act[4 * q + 2] = gate<NPASS>(ta[4 * q + 2] + bt.z, sg[4 * q + 2] + bs.z);
-        act[4 * q + 3] = gate<NPASS>(ta[4 * q + 3] + bt.w, sg[4 * q + 3] + bs.w);
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        uint32_t* cur = buf[i & 1];
+        tmem_wait32(cur);
+        if (i + 1 < 8) tmem_issue16x2(trow + (c + 1) * 16, trow + 256 + (c + 1) * 16, buf[(i + 1) & 1]);
+        float act[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bt = b1t[c * 4 + q], bs = b1g[c * 4 + q];
+          act[4 * q + 0] = gate<NPASS>(__uint_as_float(cur[4 * q + 0]) + bt.x, __uint_as_float(cur[16 + 4 * q + 0]) + bs.x);
+          act[4 * q + 1] = gate<NPASS>(__uint_as_float(cur[4 * q + 1]) + bt.y, __uint_as_float(cur[16 + 4 * q + 1]) + bs.y);
+          act[4 * q + 2] = gate<NPASS>(__uint_as_float(cur[4 * q + 2]) + bt.z, __uint_as_float(cur[16 + 4 * q + 2]) + bs.z);
+          act[4 * q + 3] = gate<NPASS>(__uint_as_float(cur[4 * q + 3]) + bt.w, __uint_as_float(cur[16 + 4 * q + 3]) + bs.w);
+        }
+        store_split16<NPASS == 3>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
       }
-      store_split16<NPASS == 3>(act, slot_a(c >> 2), slot_a(4 + (c >> 2)), row, (c & 3) * 2);
     }
     tc_fence_before_sync();
     fence_proxy_async_smem();
     mbar_arrive(acts_ready);
+    if (stamp) dbg[2] = clock64();
+
+    // prefetch the first residual chunk while GEMM2 runs
+    const uint4* xh = reinterpret_cast<const uint4*>(a.x_hi + m * 256) + half * 16;
+    const uint4* xl = reinterpret_cast<const uint4*>(a.x_lo + m * 256) + half * 16;
+    uint4 xo[2][4];
+    if (a.has_res) { xo[0][0] = __ldg(xh); xo[0][1] = __ldg(xh + 1); xo[0][2] = __ldg(xl); xo[0][3] = __ldg(xl + 1); }
 
     // res / skip
     mbar_wait(acc2_full, 0);
     tc_fence_after_sync();
-    {
-      float sk[16];
-      tmem_ld16_sync(trow + 256, sk);
+    if (stamp) dbg[3] = clock64();
+    if (half == 0) {
+      uint32_t sk[16];
+      tmem_issue16(trow + 256, sk);
+      tmem_wait16(sk);
       if (valid) {
         float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
         const float4* eb = reinterpret_cast<const float4*>(a.eo_b);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 v = a.first ? __ldg(eb + q) : e[q];
-          v.x += sk[4 * q]; v.y += sk[4 * q + 1]; v.z += sk[4 * q + 2]; v.w += sk[4 * q + 3];
+          v.x += __uint_as_float(sk[4 * q]); v.y += __uint_as_float(sk[4 * q + 1]);
+          v.z += __uint_as_float(sk[4 * q + 2]); v.w += __uint_as_float(sk[4 * q + 3]);
           e[q] = v;
         }
       }
     }
     if (a.has_res) {
-      const uint4* xh = reinterpret_cast<const uint4*>(a.x_hi + m * 256);
-      const uint4* xl = reinterpret_cast<const uint4*>(a.x_lo + m * 256);
-      const float4* b2 = reinterpret_cast<const float4*>(a.b2);
-#pragma unroll 1
-      for (int c = 0; c < 16; ++c) {
-        uint4 h0 = __ldg(xh + 2 * c), h1 = __ldg(xh + 2 * c + 1), l0 = __ldg(xl + 2 * c), l1 = __ldg(xl + 2 * c + 1);
-        float r[16];
-        tmem_ld16_sync(trow + c * 16, r);
+      const float4* b2v = reinterpret_cast<const float4*>(b2s);
+      uint32_t buf[2][16];
+      const int c0 = half * 8;
+      tmem_issue16(trow + c0 * 16, buf[0]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        uint32_t* cur = buf[i & 1];
+        tmem_wait16(cur);
+        if (i + 1 < 8) {
+          tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
+          xo[(i + 1) & 1][0] = __ldg(xh + 2 * (i + 1)); xo[(i + 1) & 1][1] = __ldg(xh + 2 * (i + 1) + 1);
+          xo[(i + 1) & 1][2] = __ldg(xl + 2 * (i + 1)); xo[(i + 1) & 1][3] = __ldg(xl + 2 * (i + 1) + 1);
+        }
+        const uint4 h0 = xo[i & 1][0], h1 = xo[i & 1][1], l0 = xo[i & 1][2], l1 = xo[i & 1][3];
         const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        float r[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 bb = __ldg(b2 + c * 4 + q);
-          r[4 * q] += bb.x; r[4 * q + 1] += bb.y; r[4 * q + 2] += bb.z; r[4 * q + 3] += bb.w;
+          const float4 bb = b2v[c * 4 + q];
+          r[4 * q] = __uint_as_float(cur[4 * q]) + bb.x; r[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + bb.y;
+          r[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + bb.z; r[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + bb.w;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {   // x_new = x_old(hi + lo) + res, glow.py:217
-          r[2 * i] += __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-          r[2 * i + 1] += __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+        for (int j = 0; j < 8; ++j) {   // x_new = x_old(hi + lo) + res, glow.py:217
+          r[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+          r[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
         }
-        store_split16<true>(r, slot_a(c >> 2), slot_a(4 + (c >> 2)), row, (c & 3) * 2);
+        store_split16<true>(r, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 4 && lane == 0) {
         for (int kb = 0; kb < 4; ++kb) {
-          tma_store_3d(&tm_xo_hi, slot_a(kb), kb * 64, t0, b);
-          tma_store_3d(&tm_xo_lo, slot_a(4 + kb), kb * 64, t0, b);
+          tma_store_3d(&tm_xo_hi, slot(kb), kb * 64, t0, b);
+          tma_store_3d(&tm_xo_lo, slot(4 + kb), kb * 64, t0, b);
         }
         tma_store_commit();
         tma_store_wait_all();
       }
     }
     tc_fence_before_sync();
+    if (stamp) dbg[4] = clock64();
   }
   __syncthreads();
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 512); }
@@ -541,6 +640,8 @@ int set_smem(K kernel, int bytes) {
 }
 
 }  // namespace
+
+void debug_set_timing(long long* buf) { g_dbg_timing = buf; }
 
 int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, const float* mel,
                    const float* cond_bias, __nv_bfloat16* h2_planes, __nv_bfloat16* mel4_planes,
@@ -599,13 +700,14 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.Tp = d.Tp; a.dil = 1 << layer;
   a.w1_row0 = (int)(idx * 2 * d.C); a.w2_row0 = (int)(idx * d.N2);
   a.has_res = layer < d.L - 1; a.first = layer == 0;
+  a.dbg = g_dbg_timing;
   dim3 grid((unsigned)((d.Tp + 127) / 128), d.B);
   if (npass == 3) {
     if (int r = set_smem(k_layer_tc<3>, L_SMEM)) return r;
-    k_layer_tc<3><<<grid, 224, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
+    k_layer_tc<3><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
   } else {
     if (int r = set_smem(k_layer_tc<1>, L_SMEM)) return r;
-    k_layer_tc<1><<<grid, 224, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
+    k_layer_tc<1><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
   }
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
