@@ -306,13 +306,16 @@ struct LayerArgs {
 
 long long* g_dbg_timing = nullptr;
 
-// Shared memory: one pool of 12 16-KB tile slots.
-//   GEMM1: activation (A) tiles cycle through slots 0..3, weight (B) tiles through slots 4..11.
-//   gate : acts hi -> slots 0..3, acts lo -> slots 4..7 (GEMM1 is complete by then).
-//   GEMM2: W2 tiles cycle through slots 8..11; epilogue-2 stages x_new hi/lo in slots 0..7.
-// Every slot has its own full/empty mbarrier pair and its own phase bit (kept in a bit mask by
-// the producer and by the consumer), so the slot sequences above need no common ring modulus.
-constexpr int L_NS = 12, L_NA = 4;
+// Shared memory: a pool of twelve 16-KB units.
+//   GEMM1: activation (A) tiles [128 x 64] cycle through units 0..3; weight (B) tiles
+//          [256 rows x 64] = 32 KB cycle through the four unit pairs 4..11 (one N=256 MMA group each).
+//   gate : acts hi -> units 0..3, acts lo -> units 4..7 (GEMM1 is complete by then).
+//   GEMM2: W2 res tiles [256 x 64] cycle through unit pairs (8,9) and (10,11); epilogue-2 stages
+//          x_new hi/lo in units 0..7.
+// Every tile slot has its own full/empty mbarrier pair and its own phase bit (kept in a bit mask
+// by the producer and by the consumer), so the slot sequences above need no common ring modulus.
+// Barrier index: A slot i -> i (0..3); B slot j -> 4 + j (j = 0..3, units 4+2j, 5+2j).
+constexpr int L_NS = 12, L_NA = 4, L_NBAR = 8;
 constexpr int L_OFF_WSE = L_NS * TILE_A;               // 196608
 constexpr int L_OFF_B1 = L_OFF_WSE + 16384;            // 212992
 constexpr int L_OFF_B2 = L_OFF_B1 + 2048;              // 215040
@@ -320,6 +323,17 @@ constexpr int L_OFF_BAR = L_OFF_B2 + 1024;             // 216064
 constexpr int L_SMEM = L_OFF_BAR + 256 + 1024;         // 217344
 constexpr int L_THREADS = 384;                         // 12 warps: TMA-A, MMA, TMA-B, spare, 8 epilogue
 constexpr int L_EPI_THREADS = 256;
+
+// UMMA descriptor with the address-independent bits precomputed; k-steps add 32 bytes (>>4 = 2).
+constexpr uint64_t DESC_SW128_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+__device__ __forceinline__ void issue_kblock_fast(uint32_t a_addr, uint32_t b_addr, uint32_t tmem_d, uint32_t idesc, bool first) {
+  const uint64_t da = DESC_SW128_HI | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+  const uint64_t db = DESC_SW128_HI | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+  umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+  umma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+  umma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
+  umma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+}
 
 // 2 x 16 TMEM columns, issued without waiting; pair with tmem_wait32.
 __device__ __forceinline__ void tmem_issue16x2(uint32_t ta, uint32_t tb, uint32_t* r) {
@@ -372,8 +386,8 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   float* b1s = reinterpret_cast<float*>(smem + L_OFF_B1);
   float* b2s = reinterpret_cast<float*>(smem + L_OFF_B2);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L_OFF_BAR);
-  uint64_t* empty = full + L_NS;
-  uint64_t* wse_full = empty + L_NS;
+  uint64_t* empty = full + L_NBAR;
+  uint64_t* wse_full = empty + L_NBAR;
   uint64_t* acc1_full = wse_full + 1;
   uint64_t* acts_ready = acc1_full + 1;
   uint64_t* acc2_full = acts_ready + 1;
@@ -381,11 +395,12 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * 128, b = blockIdx.y;
-  auto slot = [&](int i) { return smem + i * TILE_A; };
+  auto slot = [&](int i) { return smem + i * TILE_A; };                 // 16-KB unit i
+  auto bslot = [&](int j) { return smem + (L_NA + 2 * j) * TILE_A; };   // 32-KB weight slot j (barrier 4 + j)
   auto wse = [&](int plane, int kb) { return smem + L_OFF_WSE + plane * 8192 + kb * 2048; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < L_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < L_NBAR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, L_EPI_THREADS); mbar_init(acc2_full, 1);
     fence_barrier_init();
   }
@@ -425,91 +440,87 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       }
     }
   } else if (warp == 2 && lane == 0) {
-    // ---------------- producer B: weight tiles [128 rows x 64 k]
+    // ---------------- producer B: weight tiles [256 rows x 64 k]
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w2_hi);
-    int s = L_NA; uint32_t pm = 0;
+    int j = 0; uint32_t pm = 0;
     for (int kb = 0; kb < 16; ++kb)
-      for (int q = 0; q < 4; ++q)
+      for (int g = 0; g < 2; ++g)
         for (int pl = 0; pl < PL; ++pl) {
-          mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
-          pm ^= 1u << s;
-          mbar_arrive_expect_tx(&full[s], TILE_A);
-          tma_load_2d(slot(s), pl ? &tm_w1_lo : &tm_w1_hi, &full[s], kb * 64, a.w1_row0 + q * 128);
-          s = (s + 1 == L_NS) ? L_NA : s + 1;
+          mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
+          pm ^= 1u << j;
+          mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
+          tma_load_2d(bslot(j), pl ? &tm_w1_lo : &tm_w1_hi, &full[4 + j], kb * 64, a.w1_row0 + g * 256);
+          j = (j + 1) & 3;
         }
     if (a.has_res) {
-      s = 8;
+      j = 2;
       for (int kb = 0; kb < 4; ++kb)
-        for (int h = 0; h < 2; ++h)
-          for (int pl = 0; pl < PL; ++pl) {
-            mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
-            pm ^= 1u << s;
-            mbar_arrive_expect_tx(&full[s], TILE_A);
-            tma_load_2d(slot(s), pl ? &tm_w2_lo : &tm_w2_hi, &full[s], kb * 64, a.w2_row0 + h * 128);
-            s = (s + 1 == L_NS) ? 8 : s + 1;
-          }
+        for (int pl = 0; pl < PL; ++pl) {
+          mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
+          pm ^= 1u << j;
+          mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
+          tma_load_2d(bslot(j), pl ? &tm_w2_lo : &tm_w2_hi, &full[4 + j], kb * 64, a.w2_row0);
+          j = j == 2 ? 3 : 2;
+        }
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer
-    int sa = 0, sb = L_NA; uint32_t cm = 0;
-    auto take = [&](int& s, int lo, int hi) {     // wait for the tile in slot s, return (address, slot), advance
-      mbar_wait(&full[s], (cm >> s) & 1u);
-      cm ^= 1u << s;
-      int cur = s;
-      s = (s + 1 == hi) ? lo : s + 1;
-      return cur;
+    int sa = 0, jb = 0; uint32_t cm = 0;
+    auto wait_full = [&](int bar) {               // bar: barrier index (A slot i -> i, B slot j -> 4 + j)
+      mbar_wait(&full[bar], (cm >> bar) & 1u);
+      cm ^= 1u << bar;
     };
     // GEMM1: pre[128 x 512] = [x taps | H2] (K = 1024) x W1^T, accumulators in TMEM columns 0..511
     for (int kb = 0; kb < 16; ++kb) {
-      const int sa_hi = take(sa, 0, L_NA);
-      const int sa_lo = NPASS == 3 ? take(sa, 0, L_NA) : 0;
+      const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
+      int sa_lo = 0;
+      if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
       if (kb == 0) CWG_STAMP(5);
-      for (int q = 0; q < 4; ++q) {
-        const int sb_hi = take(sb, L_NA, L_NS);
-        const int sb_lo = NPASS == 3 ? take(sb, L_NA, L_NS) : 0;
+      for (int g = 0; g < 2; ++g) {
+        const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+        int jb_lo = 0;
+        if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
         tc_fence_after_sync();
-        const uint32_t d = tmem + q * 128;
-        issue_kblock(smem_u32(slot(sa_hi)), smem_u32(slot(sb_hi)), d, IDESC_N128, kb == 0);
+        const uint32_t d = tmem + g * 256;
+        issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), d, IDESC_N256, kb == 0);
         if (NPASS == 3) {
-          issue_kblock(smem_u32(slot(sa_lo)), smem_u32(slot(sb_hi)), d, IDESC_N128, false);
-          issue_kblock(smem_u32(slot(sa_hi)), smem_u32(slot(sb_lo)), d, IDESC_N128, false);
+          issue_kblock_fast(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), d, IDESC_N256, false);
+          issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), d, IDESC_N256, false);
         }
-        umma_commit(&empty[sb_hi]);
-        if (NPASS == 3) umma_commit(&empty[sb_lo]);
+        umma_commit(&empty[4 + jb_hi]);
+        if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
       }
       umma_commit(&empty[sa_hi]);
       if (NPASS == 3) umma_commit(&empty[sa_lo]);
     }
     umma_commit(acc1_full);
     CWG_STAMP(6);
-    // GEMM2: [res | folded end] = acts (smem slots 0..3 hi / 4..7 lo) x W2^T
+    // GEMM2: [res | folded end] = acts (smem units 0..3 hi / 4..7 lo) x W2^T
     mbar_wait(acts_ready, 0);
     tc_fence_after_sync();
     mbar_wait(wse_full, 0);
     CWG_STAMP(7);
-    sb = 8;
+    jb = 2;
     for (int kb = 0; kb < 4; ++kb) {
       const uint32_t a_hi = smem_u32(slot(kb)), a_lo = smem_u32(slot(4 + kb));
       if (a.has_res) {
-        for (int h = 0; h < 2; ++h) {
-          const int sb_hi = take(sb, 8, L_NS);
-          const int sb_lo = NPASS == 3 ? take(sb, 8, L_NS) : 0;
-          tc_fence_after_sync();
-          const uint32_t d = tmem + h * 128;
-          issue_kblock(a_hi, smem_u32(slot(sb_hi)), d, IDESC_N128, kb == 0);
-          if (NPASS == 3) {
-            issue_kblock(a_lo, smem_u32(slot(sb_hi)), d, IDESC_N128, false);
-            issue_kblock(a_hi, smem_u32(slot(sb_lo)), d, IDESC_N128, false);
-          }
-          umma_commit(&empty[sb_hi]);
-          if (NPASS == 3) umma_commit(&empty[sb_lo]);
+        const int jb_hi = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2;
+        int jb_lo = 0;
+        if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2; }
+        tc_fence_after_sync();
+        issue_kblock_fast(a_hi, smem_u32(bslot(jb_hi)), tmem, IDESC_N256, kb == 0);
+        if (NPASS == 3) {
+          issue_kblock_fast(a_lo, smem_u32(bslot(jb_hi)), tmem, IDESC_N256, false);
+          issue_kblock_fast(a_hi, smem_u32(bslot(jb_lo)), tmem, IDESC_N256, false);
         }
+        umma_commit(&empty[4 + jb_hi]);
+        if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
       }
       const uint32_t d = tmem + 256;
-      issue_kblock(a_hi, smem_u32(wse(0, kb)), d, IDESC_N16, kb == 0);
+      issue_kblock_fast(a_hi, smem_u32(wse(0, kb)), d, IDESC_N16, kb == 0);
       if (NPASS == 3) {
-        issue_kblock(a_lo, smem_u32(wse(0, kb)), d, IDESC_N16, false);
-        issue_kblock(a_hi, smem_u32(wse(1, kb)), d, IDESC_N16, false);
+        issue_kblock_fast(a_lo, smem_u32(wse(0, kb)), d, IDESC_N16, false);
+        issue_kblock_fast(a_hi, smem_u32(wse(1, kb)), d, IDESC_N16, false);
       }
     }
     umma_commit(acc2_full);
@@ -557,11 +568,14 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     mbar_arrive(acts_ready);
     if (stamp) dbg[2] = clock64();
 
-    // prefetch the first residual chunk while GEMM2 runs
+    // prefetch the first two residual chunks while GEMM2 runs
     const uint4* xh = reinterpret_cast<const uint4*>(a.x_hi + m * 256) + half * 16;
     const uint4* xl = reinterpret_cast<const uint4*>(a.x_lo + m * 256) + half * 16;
-    uint4 xo[2][4];
-    if (a.has_res) { xo[0][0] = __ldg(xh); xo[0][1] = __ldg(xh + 1); xo[0][2] = __ldg(xl); xo[0][3] = __ldg(xl + 1); }
+    uint4 xo[3][4];
+    auto load_x = [&](int i, uint4* dst) {
+      dst[0] = __ldg(xh + 2 * i); dst[1] = __ldg(xh + 2 * i + 1); dst[2] = __ldg(xl + 2 * i); dst[3] = __ldg(xl + 2 * i + 1);
+    };
+    if (a.has_res) { load_x(0, xo[0]); load_x(1, xo[1]); }
 
     // res / skip
     mbar_wait(acc2_full, 0);
@@ -583,6 +597,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         }
       }
     }
+    if (stamp) dbg[9] = clock64();
     if (a.has_res) {
       const float4* b2v = reinterpret_cast<const float4*>(b2s);
       uint32_t buf[2][16];
@@ -593,12 +608,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
         tmem_wait16(cur);
-        if (i + 1 < 8) {
-          tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
-          xo[(i + 1) & 1][0] = __ldg(xh + 2 * (i + 1)); xo[(i + 1) & 1][1] = __ldg(xh + 2 * (i + 1) + 1);
-          xo[(i + 1) & 1][2] = __ldg(xl + 2 * (i + 1)); xo[(i + 1) & 1][3] = __ldg(xl + 2 * (i + 1) + 1);
-        }
-        const uint4 h0 = xo[i & 1][0], h1 = xo[i & 1][1], l0 = xo[i & 1][2], l1 = xo[i & 1][3];
+        if (i + 1 < 8) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
+        if (i + 2 < 8) load_x(i + 2, xo[(i + 2) % 3]);
+        const uint4 h0 = xo[i % 3][0], h1 = xo[i % 3][1], l0 = xo[i % 3][2], l1 = xo[i % 3][3];
         const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         float r[16];
@@ -614,17 +626,20 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           r[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
         }
         store_split16<true>(r, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 4 && lane == 0) {
-        for (int kb = 0; kb < 4; ++kb) {
-          tma_store_3d(&tm_xo_hi, slot(kb), kb * 64, t0, b);
-          tma_store_3d(&tm_xo_lo, slot(4 + kb), kb * 64, t0, b);
+        if ((i & 3) == 3) {
+          // one 64-channel tile (hi + lo) of this column half is staged: store it while the rest computes
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          if (quarter == 0 && lane == 0) {
+            const int kb = c >> 2;
+            tma_store_3d(&tm_xo_hi, slot(kb), kb * 64, t0, b);
+            tma_store_3d(&tm_xo_lo, slot(4 + kb), kb * 64, t0, b);
+            tma_store_commit();
+          }
         }
-        tma_store_commit();
-        tma_store_wait_all();
       }
+      if (stamp) dbg[10] = clock64();
+      if (quarter == 0 && lane == 0) tma_store_wait_all();
     }
     tc_fence_before_sync();
     if (stamp) dbg[4] = clock64();
@@ -685,10 +700,10 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
   if (int r = map_act(&tx_lo, x_in + plane, d.C, d.Tp, d.B)) return r;
   if (int r = map_act(&th_hi, h2, d.H, d.Tp, d.B)) return r;
   if (int r = map_act(&th_lo, h2 + hplane, d.H, d.Tp, d.B)) return r;
-  if (int r = map_2d(&tw1_hi, w->w1_hi, d.K1, fl * 2 * d.C, 128)) return r;
-  if (int r = map_2d(&tw1_lo, w->w1_lo, d.K1, fl * 2 * d.C, 128)) return r;
-  if (int r = map_2d(&tw2_hi, w->w2_hi, d.C, fl * d.N2, 128)) return r;
-  if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 128)) return r;
+  if (int r = map_2d(&tw1_hi, w->w1_hi, d.K1, fl * 2 * d.C, 256)) return r;
+  if (int r = map_2d(&tw1_lo, w->w1_lo, d.K1, fl * 2 * d.C, 256)) return r;
+  if (int r = map_2d(&tw2_hi, w->w2_hi, d.C, fl * d.N2, 256)) return r;
+  if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 256)) return r;
   if (int r = map_2d(&tse_hi, w->w2_hi, d.C, fl * d.N2, 16)) return r;
   if (int r = map_2d(&tse_lo, w->w2_lo, d.C, fl * d.N2, 16)) return r;
   if (int r = map_act(&to_hi, x_out, d.C, d.Tp, d.B)) return r;

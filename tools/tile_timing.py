@@ -31,7 +31,7 @@ e0.record(); run(); e1.record(); torch.cuda.synchronize()
 lib.cwg_debug_set_timing(None)
 d = dbg.cpu().numpy().reshape(-1, 16).astype(np.float64)
 names = {"first TMA landed (5-0)": (0, 5), "GEMM1 issue done (6-5)": (5, 6), "GEMM1 complete seen by epi (1-0)": (0, 1),
-         "gate (2-1)": (1, 2), "acts_ready->GEMM2 issued (8-7)": (7, 8), "GEMM2 wait in epi (3-2)": (2, 3), "epi2+store (4-3)": (3, 4), "total (4-0)": (0, 4)}
+         "gate (2-1)": (1, 2), "acts_ready->GEMM2 issued (8-7)": (7, 8), "GEMM2 wait in epi (3-2)": (2, 3), "epi2 skip/eo (9-3)": (3, 9), "epi2 res loop (10-9)": (9, 10), "store wait (4-10)": (10, 4), "epi2+store (4-3)": (3, 4), "total (4-0)": (0, 4)}
 print(f"{prec} layer {layer}: kernel {e0.elapsed_time(e1):.3f} ms, {d.shape[0]} CTAs")
 for k, (a, b) in names.items():
     v = d[:, b] - d[:, a]
