@@ -391,7 +391,8 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   uint64_t* acc1_full = wse_full + 1;
   uint64_t* acts_ready = acc1_full + 1;
   uint64_t* acc2_full = acts_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
+  uint64_t* xold_full = acc2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xold_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * 128, b = blockIdx.y;
@@ -402,6 +403,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L_NBAR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, L_EPI_THREADS); mbar_init(acc2_full, 1);
+    mbar_init(xold_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -503,28 +505,49 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     jb = 2;
     for (int kb = 0; kb < 4; ++kb) {
       const uint32_t a_hi = smem_u32(slot(kb)), a_lo = smem_u32(slot(4 + kb));
+      const uint32_t w_hi = smem_u32(wse(0, kb)), w_lo = smem_u32(wse(1, kb));
+      const uint32_t d16 = tmem + 256;
       if (a.has_res) {
         const int jb_hi = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2;
         int jb_lo = 0;
         if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2; }
         tc_fence_after_sync();
-        issue_kblock_fast(a_hi, smem_u32(bslot(jb_hi)), tmem, IDESC_N256, kb == 0);
-        if (NPASS == 3) {
-          issue_kblock_fast(a_lo, smem_u32(bslot(jb_hi)), tmem, IDESC_N256, false);
-          issue_kblock_fast(a_hi, smem_u32(bslot(jb_lo)), tmem, IDESC_N256, false);
+        // The N=16 folded-`end` MMAs form a dependent chain on 16 columns; interleaving them with
+        // the N=256 res MMAs hides their issue-to-issue latency.
+        const uint32_t r_hi = smem_u32(bslot(jb_hi)), r_lo = smem_u32(bslot(jb_lo));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t o = 32 * k;
+          umma_bf16(tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(r_hi + o), IDESC_N256, (kb | k) ? 1u : 0u);
+          umma_bf16(d16, umma_desc_sw128(a_hi + o), umma_desc_sw128(w_hi + o), IDESC_N16, (kb | k) ? 1u : 0u);
+          if (NPASS == 3) {
+            umma_bf16(tmem, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), IDESC_N256, 1u);
+            umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), IDESC_N16, 1u);
+            umma_bf16(tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(r_lo + o), IDESC_N256, 1u);
+            umma_bf16(d16, umma_desc_sw128(a_hi + o), umma_desc_sw128(w_lo + o), IDESC_N16, 1u);
+          }
         }
         umma_commit(&empty[4 + jb_hi]);
         if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
-      }
-      const uint32_t d = tmem + 256;
-      issue_kblock_fast(a_hi, smem_u32(wse(0, kb)), d, IDESC_N16, kb == 0);
-      if (NPASS == 3) {
-        issue_kblock_fast(a_lo, smem_u32(wse(0, kb)), d, IDESC_N16, false);
-        issue_kblock_fast(a_hi, smem_u32(wse(1, kb)), d, IDESC_N16, false);
+      } else {
+        issue_kblock_fast(a_hi, w_hi, d16, IDESC_N16, kb == 0);
+        if (NPASS == 3) {
+          issue_kblock_fast(a_lo, w_hi, d16, IDESC_N16, false);
+          issue_kblock_fast(a_hi, w_lo, d16, IDESC_N16, false);
+        }
       }
     }
     umma_commit(acc2_full);
     CWG_STAMP(8);
+    if (a.has_res) {
+      // x_old (centre tap) tiles -> units 0..7 for the residual add, once GEMM2 no longer reads acts
+      mbar_wait(acc2_full, 0);
+      mbar_arrive_expect_tx(xold_full, 8 * TILE_A);
+      for (int kb = 0; kb < 4; ++kb) {
+        tma_load_3d(slot(kb), &tm_x_hi, xold_full, kb * 64, t0, b);
+        tma_load_3d(slot(4 + kb), &tm_x_lo, xold_full, kb * 64, t0, b);
+      }
+    }
   } else if (warp >= 4) {
     // ---------------- 8 epilogue warps: TMEM lane quarter = warp % 4 (one group-step per lane),
     // column half = (warp - 4) / 4 (channels [128*half, 128*half + 128)).
@@ -568,14 +591,13 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     mbar_arrive(acts_ready);
     if (stamp) dbg[2] = clock64();
 
-    // prefetch the first two residual chunks while GEMM2 runs
-    const uint4* xh = reinterpret_cast<const uint4*>(a.x_hi + m * 256) + half * 16;
-    const uint4* xl = reinterpret_cast<const uint4*>(a.x_lo + m * 256) + half * 16;
-    uint4 xo[3][4];
-    auto load_x = [&](int i, uint4* dst) {
-      dst[0] = __ldg(xh + 2 * i); dst[1] = __ldg(xh + 2 * i + 1); dst[2] = __ldg(xl + 2 * i); dst[3] = __ldg(xl + 2 * i + 1);
-    };
-    if (a.has_res) { load_x(0, xo[0]); load_x(1, xo[1]); }
+    // prefetch this row's folded-`end` accumulator while GEMM2 runs
+    float4 eold[4];
+    if (half == 0) {
+      const float4* e = reinterpret_cast<const float4*>(a.first ? a.eo_b : a.eo + m * CWG_EO_PAD);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) eold[q] = __ldg(e + q);
+    }
 
     // res / skip
     mbar_wait(acc2_full, 0);
@@ -587,10 +609,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       tmem_wait16(sk);
       if (valid) {
         float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
-        const float4* eb = reinterpret_cast<const float4*>(a.eo_b);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 v = a.first ? __ldg(eb + q) : e[q];
+          float4 v = eold[q];
           v.x += __uint_as_float(sk[4 * q]); v.y += __uint_as_float(sk[4 * q + 1]);
           v.z += __uint_as_float(sk[4 * q + 2]); v.w += __uint_as_float(sk[4 * q + 3]);
           e[q] = v;
@@ -603,14 +624,18 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       uint32_t buf[2][16];
       const int c0 = half * 8;
       tmem_issue16(trow + c0 * 16, buf[0]);
+      mbar_wait(xold_full, 0);          // x_old tiles (hi: units 0..3, lo: units 4..7) have landed
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
         tmem_wait16(cur);
         if (i + 1 < 8) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
-        if (i + 2 < 8) load_x(i + 2, xo[(i + 2) % 3]);
-        const uint4 h0 = xo[i % 3][0], h1 = xo[i % 3][1], l0 = xo[i % 3][2], l1 = xo[i % 3][3];
+        uint8_t* thi = slot(c >> 2);
+        uint8_t* tlo = slot(4 + (c >> 2));
+        const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);
+        const uint4 h0 = *reinterpret_cast<const uint4*>(thi + o0), h1 = *reinterpret_cast<const uint4*>(thi + o1);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(tlo + o0), l1 = *reinterpret_cast<const uint4*>(tlo + o1);
         const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         float r[16];
@@ -625,9 +650,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           r[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
           r[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
         }
-        store_split16<true>(r, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        store_split16<true>(r, thi, tlo, row, (c & 3) * 2);     // in place: same thread, same addresses
         if ((i & 3) == 3) {
-          // one 64-channel tile (hi + lo) of this column half is staged: store it while the rest computes
+          // one 64-channel tile (hi + lo) of this column half is final: store it while the rest computes
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
           if (quarter == 0 && lane == 0) {
