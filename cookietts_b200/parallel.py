@@ -1,0 +1,131 @@
+"""Sharding of the WaveGlow inverse pass: by utterance across GPUs and by halo-overlapped
+chunks along time (long-form audio).
+
+The reference `infer` is single-process and processes a whole utterance in one tensor
+(SURVEY 2.2, 5 "long-context").  The path shards naturally (glow.py:314-350 has no reduction
+over the batch, and every output sample depends on a bounded window of mel frames and latent),
+so this layer is net-new host logic:
+
+* utterance sharding: rank r takes utterances r, r+world, ...; weights are replicated; the only
+  collective is the final gather of waveforms (never inside a flow step);
+* time chunking: a chunk `[c0, c1)` of mel frames is computed from frames
+  `[c0 - halo - (J-1), c1 + halo)` with the latent sliced by position, and only the core is kept.
+  `halo = ceil(n_flows * (2^L - 1) * (k-1)/2 / P)` frames covers the receptive field of the
+  dilated convs of all flows (glow.py:167-171), `J-1` more frames on the left feed the
+  ConvTranspose1d taps (glow.py:238-241).  With that halo the chunked result equals the
+  un-chunked function on every core sample (tests/test_chunking.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from .packing import PackConfig
+
+
+def shard_indices(n_items: int, world: int, rank: int) -> List[int]:
+    """Utterance indices owned by `rank` (round-robin, like the reference's per-GPU process
+    layout in distributed.py:146-171)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return list(range(rank, n_items, world))
+
+
+def unshard_order(n_items: int, world: int) -> List[int]:
+    """Position in the rank-major concatenation of every utterance index: gathered[j] is
+    utterance order[j]."""
+    order = []
+    for r in range(world):
+        order.extend(shard_indices(n_items, world, r))
+    return order
+
+
+def halo_frames(pc: PackConfig) -> int:
+    steps = pc.n_flows * (2 ** pc.n_layers - 1) * (pc.kernel_size - 1) // 2
+    return -(-steps // pc.phases)
+
+
+@dataclass(frozen=True)
+class Chunk:
+    core0: int      # first mel frame of the core
+    core1: int      # one past the last core frame
+    lo: int         # first frame actually computed (core0 - halo - (J-1), clamped)
+    hi: int         # one past the last frame computed (core1 + halo, clamped)
+
+
+def plan_chunks(t_mel: int, n_chunks: int, pc: PackConfig) -> List[Chunk]:
+    """Split `t_mel` frames into `n_chunks` contiguous cores (sizes differ by at most 1)."""
+    if n_chunks < 1 or t_mel < 1:
+        raise ValueError("need t_mel >= 1 and n_chunks >= 1")
+    n_chunks = min(n_chunks, t_mel)
+    h, warm = halo_frames(pc), pc.taps - 1
+    base, rem = divmod(t_mel, n_chunks)
+    chunks, c0 = [], 0
+    for i in range(n_chunks):
+        c1 = c0 + base + (1 if i < rem else 0)
+        chunks.append(Chunk(c0, c1, max(0, c0 - h - warm), min(t_mel, c1 + h)))
+        c0 = c1
+    return chunks
+
+
+def infer_chunk(model, spect: torch.Tensor, z: torch.Tensor, sigma: float, ch: Chunk, **kw) -> torch.Tensor:
+    """Audio of the core of one chunk: [B, (core1-core0)*hop]."""
+    hop = model.pack_config.hop_length
+    out = model.infer(spect[:, :, ch.lo:ch.hi], sigma=sigma, z=z[:, ch.lo * hop:ch.hi * hop], **kw)
+    return out[:, (ch.core0 - ch.lo) * hop:(ch.core1 - ch.lo) * hop]
+
+
+def infer_long(model, spect: torch.Tensor, sigma: float = 1.0, z: Optional[torch.Tensor] = None,
+               n_chunks: int = 8, chunks: Optional[Sequence[Chunk]] = None, **kw) -> torch.Tensor:
+    """Long-form inference by halo-overlapped chunks on ONE device (the multi-GPU variant hands
+    `plan_chunks(...)[rank::world]` to each rank and gathers)."""
+    pc = model.pack_config
+    B, _, t_mel = spect.shape
+    if z is None:
+        z = model.draw_z(B, t_mel)
+    plan = list(chunks) if chunks is not None else plan_chunks(t_mel, n_chunks, pc)
+    parts = [infer_chunk(model, spect, z, sigma, ch, **kw) for ch in plan]
+    return torch.cat(parts, dim=1)
+
+
+def gather_waveforms(audio_local: torch.Tensor, n_items: int, dst: int = 0) -> Optional[torch.Tensor]:
+    """Final collective of the sharded path: gathers every rank's `[B_local, T]` waveforms to
+    `dst` and restores utterance order.  Ranks may own different counts (round-robin shards differ
+    by at most one), so shards are padded to the largest count for the fixed-size gather.
+    Returns the `[n_items, T]` tensor on `dst`, None elsewhere.  Works on NCCL (GPU) and gloo (CPU)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    T = audio_local.shape[1]
+    max_local = -(-n_items // world)
+    padded = audio_local.new_zeros(max_local, T)
+    padded[:audio_local.shape[0]] = audio_local
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = audio_local.new_empty(n_items, T)
+    for r in range(world):
+        idx = shard_indices(n_items, world, r)
+        if idx:
+            out[idx] = bufs[r][:len(idx)]
+    return out
+
+
+def infer_sharded(model, spect: torch.Tensor, sigma: float = 1.0, z: Optional[torch.Tensor] = None,
+                  dst: int = 0, **kw) -> Optional[torch.Tensor]:
+    """Data-parallel `infer` over the utterances of `spect` ([N, n_mel, T_mel], same on every
+    rank): each rank computes its round-robin shard on its own GPU, rank `dst` receives all
+    waveforms in utterance order.  Needs an initialised process group."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = spect.shape[0]
+    idx = shard_indices(n, world, rank)
+    hop = model.pack_config.hop_length
+    if idx:
+        z_local = z[idx] if z is not None else None
+        audio = model.infer(spect[idx], sigma=sigma, z=z_local, **kw)
+    else:
+        audio = torch.zeros(0, spect.shape[2] * hop, device=next(model.parameters()).device)
+    return gather_waveforms(audio, n, dst)

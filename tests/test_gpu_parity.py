@@ -47,3 +47,103 @@ def test_tensor_core_modes_match_reference(precision):
     assert np.isfinite(out).all()
     assert max_abs(out, ref) <= TOL[precision]["max_abs"]
     assert snr_db(ref, out) >= TOL[precision]["snr"]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size checks through size-independent properties (the CPU oracle is too slow there)
+# ---------------------------------------------------------------------------------------------
+
+def _model(precision, sd_seed=1234):
+    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict
+    cfg = OracleConfig()
+    sd = synthetic_state_dict(cfg, sd_seed)
+    m = WaveGlow(precision=precision, **module_kwargs(cfg))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m.cuda().eval()
+
+
+def _inputs(batch, t_mel, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    mel = (torch.randn(batch, 80, t_mel, generator=g) * 2 - 5).clamp_(-11.5129, 2.0).cuda()
+    z = torch.randn(batch, t_mel * 256, generator=g).cuda()
+    return mel, z
+
+
+def _snr(ref, out):
+    ref, out = ref.double(), out.double()
+    return float(10 * torch.log10(ref.pow(2).sum() / (out - ref).pow(2).sum().clamp_min(1e-300)))
+
+
+def test_full_length_tensor_modes_vs_fp32_cuda_cores():
+    """10-s utterances (T_mel = 861, BASELINE config 2 length): the tensor-core modes against the
+    exact-fp32 CUDA-core mode, which tests above pin to the reference."""
+    mel, z = _inputs(2, 861)
+    ref = _model("ffma").infer(mel, sigma=0.666, z=z)
+    for precision in ("bf16x3", "bf16"):
+        out = _model(precision).infer(mel, sigma=0.666, z=z)
+        assert torch.isfinite(out).all()
+        assert float((out - ref).abs().max()) <= TOL[precision]["max_abs"], precision
+        assert _snr(ref, out) >= TOL[precision]["snr"], precision
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "ffma"])
+def test_chunked_long_form_equals_unchunked(precision):
+    """Halo-chunked inference (cookietts_b200.parallel) reproduces the un-chunked waveform."""
+    from cookietts_b200.parallel import infer_long
+    m = _model(precision)
+    mel, z = _inputs(1, 700, seed=5)
+    full = m.infer(mel, sigma=0.666, z=z)
+    got = infer_long(m, mel, sigma=0.666, z=z, n_chunks=3)
+    assert got.shape == full.shape
+    assert float((got - full).abs().max()) <= 1e-4
+
+
+def test_batch_items_are_independent():
+    """No state crosses utterances (glow.py:314-350 has no batch reduction): permuting the batch
+    permutes the output, and an utterance gives the same waveform alone or inside a batch."""
+    m = _model("bf16x3")
+    mel, z = _inputs(3, 120, seed=9)
+    out = m.infer(mel, sigma=0.666, z=z)
+    perm = torch.tensor([2, 0, 1], device="cuda")
+    out_p = m.infer(mel[perm], sigma=0.666, z=z[perm])
+    assert torch.equal(out_p, out[perm])
+    alone = m.infer(mel[1:2], sigma=0.666, z=z[1:2])
+    assert torch.equal(alone, out[1:2])
+
+
+def test_ragged_and_minimal_lengths():
+    """T_mel = 1 (32 group-steps, far below one 128-step tile) and lengths that leave ragged tiles."""
+    ref_m, m = _model("ffma"), _model("bf16x3")
+    for t_mel in (1, 3, 5, 37):
+        mel, z = _inputs(2, t_mel, seed=t_mel)
+        ref = ref_m.infer(mel, sigma=1.0, z=z)
+        out = m.infer(mel, sigma=1.0, z=z)
+        assert out.shape == (2, t_mel * 256)
+        assert float((out - ref).abs().max()) <= 1e-3
+    assert m.infer(torch.zeros(2, 80, 0, device="cuda")).shape == (2, 0)
+
+
+def test_internal_z_draw_and_sigma_zero():
+    m = _model("bf16x3")
+    mel, z = _inputs(1, 20, seed=2)
+    a = m.infer(mel, sigma=0.7)              # z drawn internally
+    assert a.shape == (1, 20 * 256) and torch.isfinite(a).all()
+    # sigma = 0: the latent is irrelevant
+    b0 = m.infer(mel, sigma=0.0, z=z)
+    b1 = m.infer(mel, sigma=0.0, z=torch.randn_like(z))
+    assert torch.equal(b0, b1)
+
+
+def test_weight_update_invalidates_packed_cache():
+    m = _model("bf16x3")
+    mel, z = _inputs(1, 16, seed=3)
+    a = m.infer(mel, sigma=0.666, z=z)
+    with torch.no_grad():
+        m.WN[3].end.bias.add_(0.05)
+    b = m.infer(mel, sigma=0.666, z=z)
+    assert float((a - b).abs().max()) > 1e-3
+    for conv in m.convinv:                   # train.py:332-334 does this after validation
+        if hasattr(conv, "W_inverse"):
+            delattr(conv, "W_inverse")
+    c = m.infer(mel, sigma=0.666, z=z)
+    assert torch.equal(b, c)

@@ -3,9 +3,9 @@
 # the dominant kernel per precision mode.  Outputs land in gpurun_out/.
 set -x
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 366 -c 122 --csv \
-    --log-file gpurun_out/launches_bf16x3.csv python bench.py --precision bf16x3 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 for p in bf16x3 bf16; do
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 366 -c 122 --csv \
+      --log-file gpurun_out/launches_$p.csv python bench.py --precision $p --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_$p.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:k_layer_tc -s 20 -c 2 \
       -o gpurun_out/prof_layer_$p -f python bench.py --precision $p --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$p.log 2>&1
 done
