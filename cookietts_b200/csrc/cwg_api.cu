@@ -35,7 +35,7 @@ int check_config(const cwg_config* c) {
   CWG_REQUIRE(c->win_length >= c->hop_length, "win_length < hop_length");
   CWG_REQUIRE(c->kernel_size % 2 == 1, "kernel_size must be odd");
   CWG_REQUIRE(c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_flows / n_layers");
-  CWG_REQUIRE(c->n_channels >= 2 && c->n_mel >= 1 && c->cond_hidden >= 1, "bad channel counts");
+  CWG_REQUIRE(c->n_channels >= 2 && c->n_channels % 2 == 0 && c->n_mel >= 1 && c->cond_hidden >= 1, "bad channel counts");
   CWG_REQUIRE(c->n_early_every >= 1 && c->n_early_size % 2 == 0, "bad early-output settings");
   int n_rem, n_half;
   flow_channels(c, c->n_flows - 1, &n_rem, &n_half);

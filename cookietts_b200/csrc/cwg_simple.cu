@@ -119,6 +119,8 @@ __global__ void k_gate(const float* __restrict__ pre, float* __restrict__ acts, 
   acts[i] = tanhf(a) * (1.f / (1.f + expf(-b)));
 }
 
+constexpr int TB = 32;   // group-steps per block in the boundary kernel
+
 struct BoundaryP {
   long long BT; int G, C;
   int init, do_flow, do_start;
@@ -132,112 +134,71 @@ struct BoundaryP {
   void* x_out;
 };
 
-// One warp per group-step (a row of the [B*T'][G] audio state, which IS the [B, T] output buffer:
-// latent channel c of step s lives at audio[b, s*G + c], so the early-z concat (glow.py:342-347)
-// and the final un-squeeze (:349) are no-ops by layout).  Every lane redundantly evaluates the
-// tiny coupling + W^-1 of its warp's row (broadcast loads), then the warp writes the next flow's
-// `start` conv output: lane l owns channels [8l, 8l+8) of each 256-channel block, so a row of the
-// bf16 planes is one coalesced 512-byte store per plane.
+// One block handles TB consecutive group-steps (rows of the [B*T'][G] audio state, which IS
+// the [B, T] output buffer: latent channel c of step s lives at audio[b, s*G + c], so the
+// early-z concat (glow.py:342-347) and the final un-squeeze (:349) are no-ops by layout).
 template <int XFMT>
 __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-  const int off2 = p.G - p.n_rem2;
-  for (long long m = warp_global; m < p.BT; m += n_warps) {
-    float a[CWG_MAX_GROUP];
-#pragma unroll
-    for (int g = 0; g < CWG_MAX_GROUP; ++g)
-      a[g] = g < p.G ? (p.init ? p.sigma * __ldg(p.z + m * p.G + g) : p.audio[m * p.G + g]) : 0.f;
-    if (p.do_flow) {
-      const int off = p.G - p.n_rem;
-      const float* e = p.eo + m * CWG_EO_PAD;
-      float v[CWG_MAX_GROUP];
-#pragma unroll
-      for (int j = 0; j < CWG_MAX_GROUP; ++j) {
-        float x = 0.f;
-        if (j < p.n_rem) {
-          x = a[off + j];
-          if (j >= p.n_half) {     // audio_1 = (audio_1 - b) / exp(s), glow.py:337
-            const float bb = __ldg(e + (j - p.n_half)), ss = __ldg(e + j);
-            x = (x - bb) * expf(-ss);
-          }
+  __shared__ float a_s[TB][CWG_MAX_GROUP];
+  const long long m0 = (long long)blockIdx.x * TB;
+  const int tid = threadIdx.x;
+  if (tid < TB) {
+    long long m = m0 + tid;
+    if (m < p.BT) {
+      float a[CWG_MAX_GROUP];
+      for (int g = 0; g < p.G; ++g)
+        a[g] = p.init ? p.sigma * p.z[m * p.G + g] : p.audio[m * p.G + g];
+      if (p.do_flow) {
+        const int off = p.G - p.n_rem;
+        const float* e = p.eo + m * CWG_EO_PAD;
+        float v[CWG_MAX_GROUP];
+        for (int j = 0; j < p.n_half; ++j) v[j] = a[off + j];
+        for (int j = 0; j < p.n_rem - p.n_half; ++j) {
+          // audio_1 = (audio_1 - b) / exp(s), glow.py:337
+          float b = e[j], s = e[p.n_half + j];
+          v[p.n_half + j] = (a[off + p.n_half + j] - b) * expf(-s);
         }
-        v[j] = x;
-      }
-#pragma unroll
-      for (int r = 0; r < CWG_MAX_GROUP; ++r) {       // z = conv1d(z, W^-1), glow.py:98
-        if (r < p.n_rem) {
+        for (int r = 0; r < p.n_rem; ++r) {           // z = conv1d(z, W^-1), glow.py:98
           float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < CWG_MAX_GROUP; ++c)
-            if (c < p.n_rem) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
+          for (int c = 0; c < p.n_rem; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
           a[off + r] = acc;
         }
       }
+      if (p.init || p.do_flow)
+        for (int g = 0; g < p.G; ++g) p.audio[m * p.G + g] = a[g];
+      for (int g = 0; g < p.G; ++g) a_s[tid][g] = a[g];
     }
-    __syncwarp();               // every lane has read the row before any lane rewrites it
-    if ((p.init || p.do_flow) && lane < p.G) {
-      float mine = 0.f;
-#pragma unroll
-      for (int g = 0; g < CWG_MAX_GROUP; ++g) if (g == lane) mine = a[g];
-      p.audio[m * p.G + lane] = mine;
+  }
+  if (!p.do_start) return;
+  __syncthreads();
+  const int off2 = p.G - p.n_rem2;
+  const int nrow = (int)min((long long)TB, p.BT - m0);
+  // audio = start(audio_0), glow.py:189.  Thread -> channel pair (4-byte bf16x2 / 8-byte fp32 stores,
+  // 128 B per warp store); the two halves of the block take alternate rows.
+  const int npair = p.C >> 1, rpar = tid >> 7;
+  for (int cp = tid & 127; cp < npair; cp += 128) {
+    const int c = 2 * cp;
+    float w0[CWG_MAX_GROUP / 2], w1[CWG_MAX_GROUP / 2];
+    for (int j = 0; j < p.n_half2; ++j) {
+      w0[j] = __ldg(p.start_w + c * (CWG_MAX_GROUP / 2) + j);
+      w1[j] = __ldg(p.start_w + (c + 1) * (CWG_MAX_GROUP / 2) + j);
     }
-    if (!p.do_start) continue;
-    float a0[CWG_MAX_GROUP / 2];
-#pragma unroll
-    for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) {
-      float x = 0.f;
-#pragma unroll
-      for (int g = 0; g < CWG_MAX_GROUP; ++g) if (g == off2 + j && j < p.n_half2) x = a[g];
-      a0[j] = x;
-    }
-    for (int c0 = lane * 8; c0 < p.C; c0 += 256) {      // audio = start(audio_0), glow.py:189
-      float x[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        float acc = 0.f;
-        if (c < p.C) {
-          acc = __ldg(p.start_b + c);
-          const float* w = p.start_w + (size_t)c * (CWG_MAX_GROUP / 2);
-#pragma unroll
-          for (int j = 0; j < CWG_MAX_GROUP / 2; ++j)
-            if (j < p.n_half2) acc = fmaf(__ldg(w + j), a0[j], acc);
-        }
-        x[i] = acc;
+    const float bias0 = __ldg(p.start_b + c), bias1 = __ldg(p.start_b + c + 1);
+    for (int r = rpar; r < nrow; r += 2) {
+      float x0 = bias0, x1 = bias1;
+      for (int j = 0; j < p.n_half2; ++j) {
+        const float av = a_s[r][off2 + j];
+        x0 = fmaf(w0[j], av, x0); x1 = fmaf(w1[j], av, x1);
       }
-      const size_t idx = (size_t)m * p.C + c0;
+      const size_t idx = (size_t)(m0 + r) * p.C + c;
       if (XFMT == 0) {
-        float* o = reinterpret_cast<float*>(p.x_out) + idx;
-        if (c0 + 8 <= p.C && (p.C & 3) == 0) {
-          *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-        } else {
-          for (int i = 0; i < 8; ++i) if (c0 + i < p.C) o[i] = x[i];
-        }
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.x_out) + idx) = make_float2(x0, x1);
       } else {
-        __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(p.x_out) + idx;
+        __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(p.x_out);
         __nv_bfloat16* lo = hi + (size_t)p.BT * p.C;
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-          __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - __low2float(hh), x[2 * i + 1] - __high2float(hh));
-          h[i] = *reinterpret_cast<uint32_t*>(&hh);
-          l[i] = *reinterpret_cast<uint32_t*>(&ll);
-        }
-        if (c0 + 8 <= p.C && (p.C & 7) == 0) {
-          *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
-        } else {
-          for (int i = 0; i < 8; ++i)
-            if (c0 + i < p.C) {
-              __nv_bfloat16 hv = __float2bfloat16_rn(x[i]);
-              hi[i] = hv;
-              lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hv));
-            }
-        }
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+        *reinterpret_cast<__nv_bfloat162*>(hi + idx) = h;
+        *reinterpret_cast<__nv_bfloat162*>(lo + idx) = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
       }
     }
   }
@@ -303,9 +264,7 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
     p.start_w = w->start_w + (size_t)flow_next * d.C * (CWG_MAX_GROUP / 2);
     p.start_b = w->start_b + (size_t)flow_next * d.C;
   }
-  // 8 warps per block, one group-step per warp per iteration; enough blocks for ~16 rows per warp
-  long long want = (d.BT + 8 * 16 - 1) / (8 * 16);
-  unsigned grid = (unsigned)(want < 148 ? 148 : (want > 148 * 64 ? 148 * 64 : want));
+  unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
   if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
   else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);
   CWG_CHECK_CUDA(cudaGetLastError());
