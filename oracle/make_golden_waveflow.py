@@ -1,0 +1,106 @@
+"""Golden vectors for the WaveFlow path from the UNMODIFIED reference ax model
+(`CookieTTS/_4_mtw/waveglow/efficient_model_ax.py::WaveGlow`, waveflow=True).
+
+    python oracle/make_golden_waveflow.py          (build container only; needs /root/reference)
+
+The reference module is imported in place.  Its import chain shells out to `git clone` / pip for
+`CookieTTS.utils.audio.iso226` (iso226.py:3-9; no network here), so a stub module with an unused
+`ISO_226` class is pre-inserted into sys.modules - nothing on the inverse path touches it
+(iso226_empthasis=False).  Per case: build the model, `load_state_dict(strict=True)` the seeded
+synthetic checkpoint (pins the key layout), call the reference's own `inverse(z, cond)` with an
+explicit latent in fp32 and fp64, and its `infer(spect, sigma=...)` with `Tensor.normal_` patched to
+return the pre-drawn z.  Outputs go to tests/golden/waveflow_*.npz (weights are regenerated from
+the seed by oracle.waveflow_oracle.synthetic_state_dict).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict  # noqa: E402
+from oracle.make_golden import InjectedNormal  # noqa: E402
+
+
+def load_reference_ax():
+    stub = types.ModuleType("CookieTTS.utils.audio.iso226")
+
+    class ISO_226:  # never constructed on this path
+        def __init__(self, *a, **k):
+            raise RuntimeError("stub")
+
+    stub.ISO_226 = ISO_226
+    sys.modules["CookieTTS.utils.audio.iso226"] = stub
+    sys.path.insert(0, "/root/reference")
+    from CookieTTS._4_mtw.waveglow.efficient_model_ax import WaveGlow
+    return WaveGlow
+
+
+def reference_kwargs(cfg: WaveFlowConfig) -> dict:
+    wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size_w=cfg.kernel_size_w,
+              kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=None, n_layers_dilations_h=1,
+              speaker_embed_dim=0, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
+              cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=False,
+              res_skip=True, merge_res_skip=False, upsample_mode=cfg.upsample_mode)
+    return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
+                n_early_every=cfg.n_flows * 2, n_early_size=2, memory_efficient=0.0, spect_scaling=False,
+                upsample_mode="normal", upsample_first=True, speaker_embed=0, cond_layers=0,
+                cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
+                cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
+                sampling_rate=22050, channel_mixing="permuteheight", mix_first=True, waveflow=True)
+
+
+CASES = {
+    # name: (cfg kwargs, batch, frames, sigma, weight seed, input seed)
+    "waveflow_tiny": (dict(n_mel_channels=8, n_flows=4, n_group=8, n_layers=3, n_channels=16,
+                           win_length=64, hop_length=16), 2, 7, 0.8, 21, 1),
+    "waveflow_nearest": (dict(n_mel_channels=10, n_flows=2, n_group=4, n_layers=2, n_channels=8,
+                              win_length=32, hop_length=8, upsample_mode="nearest"), 1, 9, 1.0, 22, 2),
+    "waveflow_small": (dict(n_mel_channels=80, n_flows=8, n_group=16, n_layers=4, n_channels=32), 1, 3, 0.666, 23, 3),
+    # BASELINE config 5 model (8 flows, h=16, 8 x 128, 3x3) on a short clip
+    "waveflow_config5": (dict(), 1, 12, 0.666, 1234, 0),
+}
+
+
+def main():
+    WaveGlowAx = load_reference_ax()
+    outdir = os.path.join(ROOT, "tests", "golden")
+    for name, (kw, batch, frames, sigma, wseed, iseed) in CASES.items():
+        cfg = WaveFlowConfig(**kw)
+        sd = synthetic_state_dict(cfg, wseed)
+        rs = np.random.RandomState(iseed)
+        mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
+        z = rs.standard_normal((batch, frames * cfg.hop_length)).astype(np.float32)
+        outs = {}
+        for dt, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
+            model = WaveGlowAx(**reference_kwargs(cfg))
+            model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
+            model = model.eval().to(dt)
+            with torch.no_grad():
+                # (1) explicit-z API: inverse(z, cond) on the un-padded mel
+                zz = torch.from_numpy(z).to(dt) * sigma
+                inv, _ = model.inverse(zz, torch.from_numpy(mel).to(dt))
+                outs["inverse_" + tag] = inv.numpy()
+                # (2) infer(): pads one zero frame, draws z [B, frames*hop] with std=sigma, trims hop
+                with InjectedNormal([torch.from_numpy(z)]):
+                    aud = model.infer(torch.from_numpy(mel).to(dt), sigma=sigma)
+                outs["infer_" + tag] = aud.numpy()
+        e1 = np.abs(outs["inverse_fp32"] - outs["inverse_fp64"]).max()
+        print(f"{name}: inverse {outs['inverse_fp64'].shape} infer {outs['infer_fp64'].shape} "
+              f"rms {np.sqrt((outs['inverse_fp64'] ** 2).mean()):.3f} fp32-vs-fp64 {e1:.2e}")
+        np.savez_compressed(os.path.join(outdir, f"{name}.npz"), config=json.dumps(kw), batch=batch, frames=frames,
+                            sigma=sigma, weight_seed=wseed, input_seed=iseed, mel=mel, z=z,
+                            inverse_ref_fp32=outs["inverse_fp32"], inverse_ref_fp64=outs["inverse_fp64"],
+                            infer_ref_fp32=outs["infer_fp32"], infer_ref_fp64=outs["infer_fp64"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+"""CPU oracle for the WaveFlow inverse pass of the reference's "ax" model (BASELINE config 5).
+
+TEST INFRASTRUCTURE ONLY (same rules as waveglow_oracle.py).  numpy restatement of, in
+/root/reference/CookieTTS/_4_mtw/waveglow/:
+  efficient_model_ax.py:279-357  WaveGlow.inverse (explicit z)           -> `inverse`
+  efficient_model_ax.py:359-388  WaveGlow.infer (zero-frame pad, trim)   -> `infer_with_z`
+  efficient_model_ax.py:171-182  _upsample_mels (F.interpolate)          -> `upsample_cond`
+  efficient_modules.py:42-65     WaveFlowCoupling.inverse (AR over height)-> `coupling_inverse`
+  glow_ax.py:556-635             WN_2d.forward with conv queues          -> `wn2d_step`
+  efficient_modules.py:360-403   PermuteHeight.inverse                   -> `permute_height`
+for the configuration subset the B200 build supports (and config 5 pins):
+waveflow=True, channel_mixing='permuteheight', mix_first=True, upsample_first=True, no model-level
+cond layers / upsample net / speaker embedding, WN_2d with one 1x1 cond layer, full (non-separable)
+kernel (kh, kw), dilation_h = 1, dilation_w = 2^i, GTU gate, res_skip without merge.
+
+Parity status: PINNED - `oracle/make_golden_waveflow.py` runs the unmodified reference model
+(`inverse` with explicit z and `infer` with the RNG draw replaced) and stores
+tests/golden/waveflow_*.npz; tests/test_waveflow_oracle.py checks this file against them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict
+
+import numpy as np
+
+from .waveglow_oracle import weight_norm_effective
+
+
+@dataclass
+class WaveFlowConfig:
+    n_mel_channels: int = 80
+    n_flows: int = 8
+    n_group: int = 16            # squeeze height h
+    n_layers: int = 8
+    n_channels: int = 128
+    kernel_size_w: int = 3
+    kernel_size_h: int = 3
+    win_length: int = 1024
+    hop_length: int = 256
+    upsample_mode: str = "linear"   # WN_config['upsample_mode'] used by the model-level interpolate
+
+
+def _w(sd, prefix, dtype):
+    if prefix + ".weight_g" in sd:
+        return weight_norm_effective(np.asarray(sd[prefix + ".weight_g"], np.float64),
+                                     np.asarray(sd[prefix + ".weight_v"], np.float64)).astype(dtype)
+    return np.asarray(sd[prefix + ".weight"], dtype)
+
+
+def upsample_cond(cond: np.ndarray, size: int, mode: str) -> np.ndarray:
+    """F.interpolate(cond [B,C,Tm], size, mode, align_corners=True if linear)
+    (efficient_model_ax.py:174-175)."""
+    B, C, Tm = cond.shape
+    if mode == "linear":
+        src = np.arange(size, dtype=np.float64) * ((Tm - 1) / (size - 1) if size > 1 else 0.0)
+        i0 = np.minimum(np.floor(src).astype(np.int64), Tm - 1)
+        i1 = np.minimum(i0 + 1, Tm - 1)
+        w = (src - i0).astype(cond.dtype)
+        return cond[:, :, i0] * (1 - w) + cond[:, :, i1] * w
+    if mode == "nearest":
+        idx = np.minimum(np.floor(np.arange(size) * (Tm / size)).astype(np.int64), Tm - 1)
+        return cond[:, :, idx]
+    raise NotImplementedError(mode)
+
+
+def permute_height(x: np.ndarray, k: int) -> np.ndarray:
+    """PermuteHeight(k).inverse == forward (an involution): full reverse, or for k % 4 in (2,3)
+    reverse each half (efficient_modules.py:341-353,377-383,400-403)."""
+    h = x.shape[1]
+    idx = list(range(h))
+    if k % 4 in (2, 3):
+        half = h // 2
+        idx = idx[:half][::-1] + idx[half:][::-1]
+    else:
+        idx = idx[::-1]
+    return x[:, idx]
+
+
+def wn2d_step(sd, k, cfg: WaveFlowConfig, row: np.ndarray, spec_all: np.ndarray, queues, dtype):
+    """One autoregressive step of WN_2d (glow_ax.py:556-635) with conv queues.
+    row [B, T'] is the newest height row; spec_all [B, 2CL, T'] the cond-layer output;
+    queues[i] holds the last (kh-1) input rows of layer i, [B, C, kh-1, T'] (zeros at start).
+    Returns (log_s, t) each [B, T']."""
+    p = f"WN.{k}.WN."
+    C, L, kh, kw = cfg.n_channels, cfg.n_layers, cfg.kernel_size_h, cfg.kernel_size_w
+    B, T = row.shape
+    w_s = _w(sd, p + "start", dtype).reshape(C)
+    audio = w_s[None, :, None] * row[:, None, :] + np.asarray(sd[p + "start.bias"], dtype)[None, :, None]   # :558
+    output = np.zeros_like(audio)
+    for i in range(L):
+        d = 2 ** i
+        if queues[i] is None:                                            # :597-599
+            queues[i] = np.zeros((B, C, kh - 1, T), dtype)
+        stack = np.concatenate([queues[i], audio[:, :, None, :]], axis=2)   # [B, C, kh, T']  :602
+        queues[i] = stack[:, :, 1:]
+        w_in = _w(sd, p + f"in_layers.{i}", dtype)                       # [2C, C, kh, kw]
+        pad = ((kw - 1) * d) // 2
+        sp = np.zeros((B, C, kh, T + 2 * pad), dtype)
+        sp[:, :, :, pad:pad + T] = stack
+        acts = np.zeros((B, 2 * C, T), dtype)
+        for a in range(kh):
+            for b in range(kw):
+                acts += np.einsum("oc,bct->bot", w_in[:, :, a, b], sp[:, :, a, b * d:b * d + T], optimize=True)
+        acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None]
+        acts += spec_all[:, 2 * C * i:2 * C * (i + 1)]                   # :585-608 (GTU: add, tanh*sigmoid)
+        g = np.tanh(acts[:, :C]) * (1.0 / (1.0 + np.exp(-acts[:, C:])))
+        w_rs = _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0, 0]
+        rs = np.einsum("oc,bct->bot", w_rs, g, optimize=True) + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
+        if i < L - 1:                                                    # :613-626
+            audio = audio + rs[:, :C]
+            output = output + rs[:, C:]
+        else:
+            output = output + rs
+    w_e = np.asarray(sd[p + "end.weight"], dtype)[:, :, 0, 0]            # [2, C]
+    out = np.einsum("oc,bct->bot", w_e, output, optimize=True) + np.asarray(sd[p + "end.bias"], dtype)[None, :, None]
+    return out[:, 0], out[:, 1]                                          # log_s, t  (:628, efficient_modules.py:62)
+
+
+def coupling_inverse(sd, k, cfg, audio_out: np.ndarray, spec_all: np.ndarray, dtype) -> np.ndarray:
+    """WaveFlowCoupling.inverse (efficient_modules.py:42-65): audio_out [B, h, T'] -> z."""
+    h = audio_out.shape[1]
+    z = [audio_out[:, 0]]
+    queues = [None] * cfg.n_layers
+    for i in range(h - 1):
+        log_s, t = wn2d_step(sd, k, cfg, z[-1], spec_all, queues, dtype)
+        z.append((audio_out[:, i + 1] - t) / np.exp(log_s))
+    return np.stack(z, axis=1)
+
+
+def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """WaveGlow.inverse(z, cond) (efficient_model_ax.py:279-357): z [B, T] (already scaled by
+    sigma), cond [B, n_mel, frames] -> audio [B, T]."""
+    z = np.asarray(z, dtype)
+    cond = np.asarray(cond, dtype)
+    B = z.shape[0]
+    zz = z.reshape(B, -1, cfg.n_group).transpose(0, 2, 1)               # :310
+    Tp = zz.shape[2]
+    cond_up = upsample_cond(cond, Tp, cfg.upsample_mode)                 # :313-314
+    C, L = cfg.n_channels, cfg.n_layers
+    for k in reversed(range(cfg.n_flows)):                               # :325
+        p = f"WN.{k}.WN.cond_layers.0"
+        w_c = _w(sd, p, dtype)[:, :, 0]                                  # [2CL, n_mel]
+        spec_all = np.einsum("oc,bct->bot", w_c, cond_up, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
+        zz = coupling_inverse(sd, k, cfg, zz, spec_all, dtype)           # :331
+        zz = permute_height(zz, k)                                       # :336-337 (mix_first)
+    return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)    # :346
+
+
+def infer_with_z(sd, cfg: WaveFlowConfig, spect: np.ndarray, z: np.ndarray, sigma: float,
+                 artifact_trimming: int = 1, dtype=np.float32) -> np.ndarray:
+    """WaveGlow.infer (efficient_model_ax.py:359-388) with the latent passed in: z is standard
+    normal [B, frames*hop]; returns [B, (frames*hop) - artifact_trimming*hop... ] exactly as the
+    reference: pad `artifact_trimming` zero frames, run inverse on (steps-1)*hop samples, trim."""
+    spect = np.asarray(spect, dtype)
+    if artifact_trimming > 0:
+        spect = np.concatenate([spect, np.zeros(spect.shape[:2] + (artifact_trimming,), dtype)], axis=2)   # :370-371
+    steps = spect.shape[2]
+    samples = (steps - 1) * cfg.hop_length
+    samples -= samples % cfg.n_group
+    assert z.shape[1] == samples, (z.shape, samples)
+    audio = inverse(sd, cfg, np.asarray(z, dtype) * dtype(sigma), spect, dtype)
+    if artifact_trimming > 0:
+        audio = audio[:, :-artifact_trimming * cfg.hop_length]           # :381-383
+    return audio
+
+
+def synthetic_state_dict(cfg: WaveFlowConfig, seed: int = 1234) -> Dict[str, np.ndarray]:
+    """Seeded checkpoint with the reference ax/WaveFlow key layout (probe-printed: WN.{k}.WN.*,
+    4-D conv weights, no convinv parameters for permuteheight); `end` non-zero."""
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+    C, L, kh, kw = cfg.n_channels, cfg.n_layers, cfg.kernel_size_h, cfg.kernel_size_w
+
+    def wn(prefix, shape, fan_in):
+        bound = 1.0 / np.sqrt(fan_in)
+        v = rs.uniform(-bound, bound, size=shape).astype(np.float32)
+        norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=tuple(range(1, v.ndim)), keepdims=True))
+        sd[prefix + ".bias"] = rs.uniform(-bound, bound, size=(shape[0],)).astype(np.float32)
+        sd[prefix + ".weight_g"] = (norm * rs.uniform(0.8, 1.2, size=norm.shape)).astype(np.float32)
+        sd[prefix + ".weight_v"] = v
+
+    for k in range(cfg.n_flows):
+        p = f"WN.{k}.WN."
+        for i in range(L):
+            wn(p + f"in_layers.{i}", (2 * C, C, kh, kw), C * kh * kw)
+            wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1, 1), C)
+        wn(p + "start", (C, 1, 1, 1), 1)
+        sd[p + "end.weight"] = (rs.standard_normal((2, C, 1, 1)) * 0.02).astype(np.float32)
+        sd[p + "end.bias"] = (rs.standard_normal((2,)) * 0.02).astype(np.float32)
+        wn(p + "cond_layers.0", (2 * C * L, cfg.n_mel_channels, 1), cfg.n_mel_channels)
+    return sd

@@ -1,0 +1,45 @@
+"""The WaveFlow oracle is pinned against the unmodified reference ax model
+(tests/golden/waveflow_*.npz, made by oracle/make_golden_waveflow.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict, inverse, infer_with_z, permute_height
+from oracle.waveglow_oracle import snr_db
+from tests.helpers import GOLDEN_DIR, max_abs
+
+CASES = ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config5"]
+
+
+def load(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+    return cfg, synthetic_state_dict(cfg, int(g["weight_seed"])), g
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_inverse_fp64(name):
+    cfg, sd, g = load(name)
+    out = inverse(sd, cfg, g["z"].astype(np.float64) * float(g["sigma"]), g["mel"], np.float64)
+    assert max_abs(out, g["inverse_ref_fp64"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", CASES[:3])
+def test_infer_fp64_and_fp32(name):
+    cfg, sd, g = load(name)
+    out = infer_with_z(sd, cfg, g["mel"], g["z"], float(g["sigma"]), 1, np.float64)
+    assert out.shape == g["infer_ref_fp64"].shape
+    assert max_abs(out, g["infer_ref_fp64"]) < 1e-9
+    out32 = infer_with_z(sd, cfg, g["mel"], g["z"], float(g["sigma"]), 1, np.float32)
+    assert max_abs(out32, g["infer_ref_fp32"]) < 2e-5
+    assert snr_db(g["infer_ref_fp64"], out32) > 100.0
+
+
+def test_permute_height_is_an_involution():
+    x = np.arange(2 * 16 * 3).reshape(2, 16, 3)
+    for k in range(8):
+        assert np.array_equal(permute_height(permute_height(x, k), k), x)
+    assert list(permute_height(x, 0)[0, :, 0] // 3) == list(range(15, -1, -1))
+    assert list(permute_height(x, 2)[0, :, 0] // 3) == [7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8]
