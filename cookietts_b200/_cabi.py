@@ -33,7 +33,8 @@ class CwgWeights(C.Structure):
 
 
 EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
-           "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary")
+           "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
+           "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer")
 
 
 class CwgError(RuntimeError):

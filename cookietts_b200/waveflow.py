@@ -1,0 +1,289 @@
+"""Drop-in for the reference's "ax" model `CookieTTS/_4_mtw/waveglow/efficient_model_ax.py::WaveGlow`
+in its WaveFlow configuration (`waveflow=True`, `WN_2d`, `PermuteHeight`; BASELINE config 5),
+inverse pass only, on sm_100a tensor-core kernels (csrc/cwg_wf.cu).
+
+Interface mirrored: the ax constructor keywords (efficient_model_ax.py:19-20), the state_dict layout
+(`WN.{k}.WN.{start,end,cond_layers.0,in_layers.i,res_skip_layers.i}`; probe-printed, pinned by
+oracle/make_golden_waveflow.py loading the same dict into the real reference with strict=True),
+`inverse(z, cond)` (:279) and `infer(spect, speaker_ids=None, artifact_trimming=1, sigma=1.,
+t_scaler=1.0, return_CPU=True)` (:359-388).  Everything outside the supported subset raises at
+construction (see `_check_supported`); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .packing import split_hi_lo, effective_weight, _np, EO_PAD
+
+COND_PAD = 128
+
+
+@dataclass(frozen=True)
+class WaveFlowPackConfig:
+    n_mel: int = 80
+    n_flows: int = 8
+    n_group: int = 16
+    n_layers: int = 8
+    n_channels: int = 128
+    kernel_h: int = 3
+    kernel_w: int = 3
+    hop_length: int = 256
+    upsample_linear: bool = True
+
+    @property
+    def k1(self) -> int:
+        return self.kernel_h * self.kernel_w * self.n_channels + COND_PAD
+
+
+def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig) -> Dict[str, np.ndarray]:
+    """fp64 folding of weight-norm, the WN_2d cond layer (extra K columns on the interpolated mel)
+    and `end` (into the skip half), to the arrays of `cwg_wf_weights` (include/cwg.h)."""
+    F, L, Cc, kh, kw, M = cfg.n_flows, cfg.n_layers, cfg.n_channels, cfg.kernel_h, cfg.kernel_w, cfg.n_mel
+    K1, N2 = cfg.k1, Cc + EO_PAD
+    w1 = np.zeros((F, L, 2 * Cc, K1)); b1 = np.zeros((F, L, 2 * Cc))
+    w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, EO_PAD))
+    start_w = np.zeros((F, Cc)); start_b = np.zeros((F, Cc))
+    for k in range(F):
+        p = f"WN.{k}.WN."
+        w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]           # [2CL, M]
+        b_c = _np(sd[p + "cond_layers.0.bias"])
+        w_end = _np(sd[p + "end.weight"])[:, :, 0, 0]                      # [2, C]  (log_s, t)
+        eo_bias = _np(sd[p + "end.bias"]).copy()
+        for i in range(L):
+            w_in = effective_weight(sd, p + f"in_layers.{i}")              # [2C, C, kh, kw]
+            w1[k, i, :, :kh * kw * Cc] = w_in.transpose(0, 2, 3, 1).reshape(2 * Cc, kh * kw * Cc)   # col (a*kw+b)*C + c
+            w1[k, i, :, kh * kw * Cc:kh * kw * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
+            b1[k, i] = _np(sd[p + f"in_layers.{i}.bias"]) + b_c[2 * Cc * i:2 * Cc * (i + 1)]
+            w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0, 0]
+            b_rs = _np(sd[p + f"res_skip_layers.{i}.bias"])
+            if i < L - 1:
+                w2[k, i, :Cc] = w_rs[:Cc]; b2[k, i] = b_rs[:Cc]
+                w_skip, b_skip = w_rs[Cc:], b_rs[Cc:]
+            else:
+                w_skip, b_skip = w_rs, b_rs
+            w2[k, i, Cc:Cc + 2] = w_end @ w_skip
+            eo_bias += w_end @ b_skip
+        eo_b[k, :2] = eo_bias
+        start_w[k] = effective_weight(sd, p + "start").reshape(Cc)
+        start_b[k] = _np(sd[p + "start.bias"])
+    out = {"b1": b1.astype(np.float32), "b2": b2.astype(np.float32), "eo_b": eo_b.astype(np.float32),
+           "start_w": start_w.astype(np.float32), "start_b": start_b.astype(np.float32),
+           "w1_f64": w1, "w2_f64": w2}
+    out["w1_hi"], out["w1_lo"] = split_hi_lo(w1)
+    out["w2_hi"], out["w2_lo"] = split_hi_lo(w2)
+    return out
+
+
+class CwgWfConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mel", "n_flows", "n_group", "n_layers", "n_channels",
+                                          "kernel_h", "kernel_w", "hop_length", "upsample_linear")]
+
+
+WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b")
+
+
+class CwgWfWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS]
+
+
+def _bind(lib):
+    if getattr(lib, "_wf_bound", False):
+        return
+    lib.cwg_wf_workspace_bytes.restype = C.c_size_t
+    lib.cwg_wf_workspace_bytes.argtypes = [C.POINTER(CwgWfConfig), C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.cwg_wf_launch_count.restype = C.c_int
+    lib.cwg_wf_launch_count.argtypes = [C.POINTER(CwgWfConfig)]
+    lib.cwg_wf_infer.restype = C.c_int
+    lib.cwg_wf_infer.argtypes = [C.POINTER(CwgWfConfig), C.POINTER(CwgWfWeights), C.c_int,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_wf_layer.restype = C.c_int
+    lib.cwg_wf_layer.argtypes = [C.POINTER(CwgWfConfig), C.POINTER(CwgWfWeights), C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib._wf_bound = True
+
+
+class _WN2d(nn.Module):
+    """Parameter holder with the layout of glow_ax.py:421-553 (supported subset)."""
+
+    def __init__(self, n_layers, n_channels, kernel_h, kernel_w, cond_in_channels):
+        super().__init__()
+        wn = nn.utils.weight_norm
+        self.in_layers = nn.ModuleList()
+        self.res_skip_layers = nn.ModuleList()
+        for i in range(n_layers):
+            d = 2 ** i
+            self.in_layers.append(wn(nn.Conv2d(n_channels, 2 * n_channels, (kernel_h, kernel_w), dilation=(1, d),
+                                               padding=(0, ((kernel_w - 1) * d) // 2)), name="weight"))
+            rs = 2 * n_channels if i < n_layers - 1 else n_channels
+            self.res_skip_layers.append(wn(nn.Conv2d(n_channels, rs, (1, 1)), name="weight"))
+        self.start = wn(nn.Conv2d(1, n_channels, (1, 1)), name="weight")
+        self.end = nn.Conv2d(n_channels, 2, (1, 1))
+        self.end.weight.data.zero_(); self.end.bias.data.zero_()
+        self.cond_layers = nn.ModuleList([wn(nn.Conv1d(cond_in_channels, 2 * n_channels * n_layers, 1), name="weight")])
+
+
+class _Coupling(nn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        self.WN = _WN2d(**kw)
+
+
+class WaveFlow(nn.Module):
+    """`efficient_model_ax.WaveGlow(..., waveflow=True)` - inverse pass on B200."""
+
+    def __init__(self, n_mel_channels, n_flows, n_group, n_early_every, n_early_size, memory_efficient,
+                 spect_scaling, upsample_mode, upsample_first, speaker_embed, cond_layers, cond_hidden_channels,
+                 cond_output_channels, cond_kernel_size, cond_residual, cond_padding_mode, WN_config, win_length,
+                 hop_length, sampling_rate=48000, cond_res_rezero=False, cond_activation_func="none",
+                 negative_slope=None, channel_mixing="1x1conv", mix_first=True, preceived_vol_scaling=False,
+                 waveflow=True, yoyo="depreciated", yoyo_WN="depreciated", shift_spect=0., scale_spect=1.,
+                 preempthasis=None, use_logvar_channels=False, load_hidden_from_disk=False,
+                 transposed_conv_hidden_dim=256, transposed_conv_kernel_size=4, transposed_conv_scales=None,
+                 transposed_conv_output_dim=256, transposed_conv_residual=False, transposed_conv_residual_linear=False,
+                 transposed_conv_res_rezero=False, group_conv_output_dim=None, group_conv_groupped=True,
+                 iso226_empthasis=False, precision: str = "bf16x3"):
+        super().__init__()
+        wn = dict(WN_config)
+        self._check_supported(locals(), wn)
+        self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
+        self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
+        self.shift_spect, self.scale_spect = shift_spect, scale_spect
+        self.precision = precision
+        self.pack_config = WaveFlowPackConfig(
+            n_mel=n_mel_channels, n_flows=n_flows, n_group=n_group, n_layers=wn["n_layers"],
+            n_channels=wn["n_channels"], kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
+            hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear")
+        self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
+                                           kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
+                                           cond_in_channels=n_mel_channels) for _ in range(n_flows)])
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+
+    @staticmethod
+    def _check_supported(a, wn):
+        def need(cond, msg):
+            if not cond:
+                raise NotImplementedError("cookietts_b200.WaveFlow: " + msg)
+        need(a["waveflow"], "only waveflow=True (WN_2d) is built; use cookietts_b200.WaveGlow for the classic model")
+        need(str(a["channel_mixing"]).lower() in "waveflowpermuteheightpermutechannelpermute", "channel_mixing must be 'permuteheight'")
+        need(a["mix_first"], "mix_first=False is not supported")
+        need(a["upsample_first"] is True, "upsample_first must be True")
+        need(a["n_flows"] % 2 == 0, "PermuteHeight requires an even n_flows (efficient_modules.py:370)")
+        need(a["n_early_every"] >= a["n_flows"], "early outputs are not supported with waveflow (set n_early_every >= n_flows)")
+        need(not a["speaker_embed"] and not wn.get("speaker_embed_dim", 0), "speaker embeddings are not supported")
+        need(not a["cond_layers"], "model-level cond_layers must be 0")
+        need(not a["transposed_conv_scales"] and not wn.get("transposed_conv_scales"), "TransposedUpsampleNet is not supported")
+        need(not a["group_conv_output_dim"], "n_flow_group_conv is not supported")
+        need(not a["preempthasis"] and not a["preceived_vol_scaling"] and not a["iso226_empthasis"], "pre-emphasis / volume scaling / ISO-226 are not supported")
+        need(not a["use_logvar_channels"] and not a["load_hidden_from_disk"] and not a["spect_scaling"], "logvar / hidden / spect_scaling inputs are not supported")
+        need(not a["memory_efficient"], "memory_efficient is a training feature")
+        need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1, "WN cond_layers must be one 1x1 conv")
+        need(wn.get("cond_activation_func", "none") == "none", "WN cond activation is not supported")
+        need(not wn.get("seperable_conv") and not wn.get("merge_res_skip") and wn.get("res_skip", True), "separable / merged res_skip variants are not supported")
+        need(wn.get("gated_unit", "GTU") == "GTU", "only the GTU gate is supported")
+        need(wn.get("n_layers_dilations_w") is None and wn.get("n_layers_dilations_h", 1) == 1, "custom dilations are not supported")
+        need(wn["n_channels"] == 128 and wn["kernel_size_h"] == 3 and wn["kernel_size_w"] == 3, "kernels are built for n_channels=128, kernel 3x3")
+        need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
+        need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 16 and a["n_mel_channels"] <= COND_PAD, "n_group <= 16, n_mel <= 128")
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def remove_weightnorm(self):
+        return self
+
+    def forward(self, *a, **kw):
+        raise NotImplementedError("only the inverse pass is in scope of this implementation")
+
+    def _device(self):
+        return self.WN[0].WN.end.weight.device
+
+    def _ensure_packed(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is not None and self._packed_key == key:
+            return
+        dev = self._device()
+        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
+        pk = pack_waveflow_state_dict(sd, self.pack_config)
+        dev_pk = {}
+        for name in WF_WEIGHT_FIELDS:
+            arr = pk[name]
+            if arr.dtype == np.uint16:
+                arr = arr.view(np.int16)
+            dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        w = CwgWfWeights()
+        for f in WF_WEIGHT_FIELDS:
+            setattr(w, f, dev_pk[f].data_ptr())
+        pc = self.pack_config
+        self._ccfg = CwgWfConfig(pc.n_mel, pc.n_flows, pc.n_group, pc.n_layers, pc.n_channels, pc.kernel_h, pc.kernel_w,
+                                 pc.hop_length, int(pc.upsample_linear))
+        self._packed, self._packed_key, self._cw = dev_pk, key, w
+
+    @torch.no_grad()
+    def inverse(self, z, cond, speaker_ids=None, return_CPU=True, *, _pad_frames: int = 0):
+        """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("cookietts_b200.WaveFlow needs the module on a CUDA device (no CPU fallback)")
+        lib = _cabi.load()
+        _bind(lib)
+        mode = _cabi.MODES[self.precision]
+        cond = cond.to(device=dev, dtype=torch.float32)
+        if self.shift_spect != 0.:
+            cond = cond + self.shift_spect
+        if self.scale_spect != 1.:
+            cond = cond * self.scale_spect
+        cond = cond.contiguous()
+        z = z.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, frames = cond.shape
+        T = z.shape[1]
+        with torch.cuda.device(dev):
+            self._ensure_packed()
+            nbytes = lib.cwg_wf_workspace_bytes(self._ccfg, mode, B, frames, T)
+            if nbytes == 0:
+                raise _cabi.CwgError(lib.cwg_last_error().decode())
+            if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+            audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+            _cabi.check(lib.cwg_wf_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, _pad_frames,
+                                         z.data_ptr(), 1.0, audio.data_ptr(), ws_ptr,
+                                         self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
+                                         B, T, torch.cuda.current_stream(dev).cuda_stream))
+        return (audio.cpu() if return_CPU else audio), None
+
+    @torch.no_grad()
+    def infer(self, spect, speaker_ids=None, artifact_trimming=1, sigma=1., t_scaler=1.0, return_CPU=True, *, z=None):
+        """efficient_model_ax.py:359-388.  `z` ([B, samples], standard normal) injects the latent."""
+        if spect.dim() == 2:
+            spect = spect[None]
+        in_dtype = spect.dtype
+        dev = self._device()
+        B, _, frames = spect.shape
+        steps = frames + max(artifact_trimming, 0)
+        samples = int((steps - 1) * self.hop_length * t_scaler)
+        samples -= samples % self.n_group
+        if z is None:
+            z = torch.randn(B, samples, device=dev)
+        zz = z.to(dev).float() * float(sigma) if sigma > 0 else torch.zeros(B, samples, device=dev)
+        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU, _pad_frames=max(artifact_trimming, 0))
+        if artifact_trimming > 0:
+            audio = audio[:, :-artifact_trimming * self.hop_length]
+        return audio.to(in_dtype)
+
+    def launch_count(self) -> int:
+        lib = _cabi.load()
+        _bind(lib)
+        self._ensure_packed()
+        return int(lib.cwg_wf_launch_count(self._ccfg))

@@ -131,6 +131,59 @@ int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,
                       float* audio, const float* eo, void* x_out,
                       int batch, int t_mel, void* cuda_stream);
 
+/* =====================================================================================
+ * WaveFlow (BASELINE config 5): the reference's "ax" model with waveflow=True
+ *   efficient_model_ax.py:279-357  WaveGlow.inverse      efficient_modules.py:42-65  WaveFlowCoupling.inverse
+ *   glow_ax.py:556-635             WN_2d.forward          efficient_modules.py:360-403 PermuteHeight
+ * Supported subset: channel_mixing='permuteheight', mix_first, upsample_first (model-level
+ * F.interpolate of the mel), WN_2d with one 1x1 cond layer, kernel (3,3), dilation_h 1,
+ * dilation_w 2^i, n_channels 128, GTU gate, res_skip without merge.  Tensor-core modes only.
+ * ===================================================================================== */
+#define CWG_WF_COND_PAD 128  /* mel channels padded to two 64-wide k-blocks */
+
+typedef struct cwg_wf_config {
+  int32_t n_mel;
+  int32_t n_flows;
+  int32_t n_group;        /* squeeze height h (<= CWG_MAX_GROUP) */
+  int32_t n_layers;
+  int32_t n_channels;     /* 128 */
+  int32_t kernel_h, kernel_w;   /* 3, 3 */
+  int32_t hop_length;
+  int32_t upsample_linear;      /* 1: F.interpolate(mode='linear', align_corners=True); 0: 'nearest' */
+} cwg_wf_config;
+
+/* K1 = kernel_h*kernel_w*C + CWG_WF_COND_PAD, N2 = C + CWG_EO_PAD */
+typedef struct cwg_wf_weights {
+  const uint16_t* w1_hi;   /* [F][L][2C][K1]  col (kh*kw_n + kw)*C + c | 9C + mel channel   */
+  const uint16_t* w1_lo;
+  const float*    b1;      /* [F][L][2C]      in_layer bias + cond layer bias slice          */
+  const uint16_t* w2_hi;   /* [F][L][N2][C]   rows <C res (0 for last layer), C: log_s, C+1: t (end folded) */
+  const uint16_t* w2_lo;
+  const float*    b2;      /* [F][L][C]                                                      */
+  const float*    eo_b;    /* [F][CWG_EO_PAD]                                                */
+  const float*    start_w; /* [F][C]   Conv2d(1, C, 1x1)                                     */
+  const float*    start_b; /* [F][C]                                                         */
+} cwg_wf_weights;
+
+size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples);
+
+/* WaveGlow.inverse of the ax model (explicit latent): mel [batch][n_mel][frames] fp32, zero-extended
+ * to frames + pad_frames (infer's artifact_trimming pad, efficient_model_ax.py:370-371) and
+ * interpolated to T' = t_samples / n_group steps; z [batch][t_samples] standard normal (scaled by
+ * sigma inside); audio [batch][t_samples] out.  mode: CWG_MODE_BF16X3 or CWG_MODE_BF16. */
+int cwg_wf_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
+                 const float* mel, int frames, int pad_frames, const float* z, float sigma,
+                 float* audio, void* workspace, size_t workspace_bytes,
+                 int batch, int t_samples, void* cuda_stream);
+
+int cwg_wf_launch_count(const cwg_wf_config* cfg);
+
+/* Stage entry point (tests): one WN_2d layer of one autoregressive row step.
+ * x_rings: bf16 planes (hi then lo), each [L][3][batch][T'][C]; mel_up planes [batch][T'][128];
+ * reads ring slots of rows row, row-1, row-2 of layer `layer`, writes slot row%3 of layer+1. */
+int cwg_wf_layer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode, int flow, int layer, int row,
+                 void* x_rings, const void* mel_up, float* eo, int batch, int t_samples, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

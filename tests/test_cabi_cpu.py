@@ -95,3 +95,55 @@ def test_infer_refuses_cpu():
     model = WaveGlow(**module_kwargs(cfg))
     with pytest.raises(RuntimeError):
         model.infer(torch.from_numpy(g["mel"]))
+
+
+def test_waveflow_state_dict_layout_and_packing_cpu():
+    """Host logic of the WaveFlow path: reference key layout; packed form reproduces the oracle's
+    WN_2d step (fp64) on CPU."""
+    from cookietts_b200 import WaveFlow
+    from cookietts_b200.waveflow import pack_waveflow_state_dict
+    from oracle.make_golden_waveflow import reference_kwargs
+    from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict, wn2d_step
+    cfg = WaveFlowConfig(n_flows=2, n_layers=2)
+    sd = synthetic_state_dict(cfg, 5)
+    m = WaveFlow(**reference_kwargs(cfg))
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    pk = pack_waveflow_state_dict(sd, m.pack_config)
+    # evaluate one AR step (row 2: full 3-row queue) of flow 1 from the packed arrays
+    rs = np.random.RandomState(0)
+    B, T, Cc, L = 1, 40, cfg.n_channels, cfg.n_layers
+    rows = rs.standard_normal((3, B, T))
+    cond_up = rs.standard_normal((B, cfg.n_mel_channels, T))
+    k = 1
+    from oracle.waveflow_oracle import _w
+    w_c = _w(sd, f"WN.{k}.WN.cond_layers.0", np.float64)[:, :, 0]
+    spec_all = np.einsum("oc,bct->bot", w_c, cond_up) + np.asarray(sd[f"WN.{k}.WN.cond_layers.0.bias"], np.float64)[None, :, None]
+    queues = [None] * L
+    for r in range(3):
+        log_s, t = wn2d_step(sd, k, cfg, rows[r], spec_all, queues, np.float64)
+    # packed evaluation: x rings per layer hold rows 0..2
+    x = [pk["start_w"][k].astype(np.float64)[None, None, :] * rows[r][:, :, None] + pk["start_b"][k].astype(np.float64) for r in range(3)]
+    eo = np.tile(pk["eo_b"][k].astype(np.float64), (B, T, 1))
+    hist = [list(x)]            # hist[l][r] = layer-l input at row r
+    for l in range(L):
+        d = 2 ** l
+        nxt = []
+        for r in range(3):
+            cols = []
+            for a in range(3):
+                rr = r - 2 + a
+                src = hist[l][rr] if rr >= 0 else np.zeros((B, T, Cc))
+                xp = np.zeros((B, T + 2 * d, Cc)); xp[:, d:d + T] = src
+                cols += [xp[:, b * d:b * d + T] for b in range(3)]
+            mel_pad = np.zeros((B, T, 128)); mel_pad[:, :, :cfg.n_mel_channels] = cond_up.transpose(0, 2, 1)
+            a_mat = np.concatenate(cols + [mel_pad], axis=2)
+            pre = a_mat @ pk["w1_f64"][k, l].T + pk["b1"][k, l].astype(np.float64)
+            acts = np.tanh(pre[..., :Cc]) / (1 + np.exp(-pre[..., Cc:]))
+            rsk = acts @ pk["w2_f64"][k, l].T
+            nxt.append(hist[l][r] + rsk[..., :Cc] + pk["b2"][k, l].astype(np.float64))
+            if r == 2:
+                eo = eo + rsk[..., Cc:]
+        hist.append(nxt)
+    assert np.abs(eo[..., 0] - log_s).max() < 1e-6
+    assert np.abs(eo[..., 1] - t).max() < 1e-6

@@ -1,0 +1,71 @@
+"""GPU parity of the WaveFlow path (BASELINE config 5 model) against golden vectors of the
+unmodified reference ax model and against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cookietts_b200 import WaveFlow
+from oracle.make_golden_waveflow import reference_kwargs
+from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict, inverse as oracle_inverse
+from oracle.waveglow_oracle import snr_db
+from tests.helpers import GOLDEN_DIR, max_abs
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16x3": dict(max_abs=1e-3, snr=60.0), "bf16": dict(max_abs=5e-2, snr=40.0)}
+
+
+def build(cfg, sd, precision):
+    m = WaveFlow(precision=precision, **reference_kwargs(cfg))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_config5_model_matches_reference(precision):
+    g = np.load(os.path.join(GOLDEN_DIR, "waveflow_config5.npz"))
+    cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+    sd = synthetic_state_dict(cfg, int(g["weight_seed"]))
+    m = build(cfg, sd, precision)
+    sigma = float(g["sigma"])
+    z = torch.from_numpy(g["z"]).cuda()
+    mel = torch.from_numpy(g["mel"]).cuda()
+    out, _ = m.inverse(z * sigma, mel, return_CPU=True)
+    ref = g["inverse_ref_fp64"]
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert max_abs(out.numpy(), ref) <= TOL[precision]["max_abs"]
+    assert snr_db(ref, out.numpy()) >= TOL[precision]["snr"]
+    # infer(): zero-frame pad, explicit z, hop trim
+    aud = m.infer(mel, sigma=sigma, z=z)
+    ref2 = g["infer_ref_fp64"]
+    assert aud.shape == ref2.shape and aud.device.type == "cpu"
+    assert max_abs(aud.numpy(), ref2) <= TOL[precision]["max_abs"]
+    assert snr_db(ref2, aud.numpy()) >= TOL[precision]["snr"]
+
+
+def test_ragged_batch_against_oracle():
+    """Batch 2, T' = 5*256/16 = 80 (one ragged tile), nearest-neighbour upsampling."""
+    cfg = WaveFlowConfig(upsample_mode="nearest")
+    sd = synthetic_state_dict(cfg, 99)
+    rs = np.random.RandomState(4)
+    mel = np.clip(rs.standard_normal((2, 80, 5)) * 2 - 5, -11.5, 2.0).astype(np.float32)
+    z = (rs.standard_normal((2, 5 * 256)) * 0.7).astype(np.float32)
+    ref = oracle_inverse(sd, cfg, z, mel, np.float64)
+    m = build(cfg, sd, "bf16x3")
+    out, _ = m.inverse(torch.from_numpy(z), torch.from_numpy(mel), return_CPU=True)
+    assert max_abs(out.numpy(), ref) <= 1e-3
+    assert snr_db(ref, out.numpy()) >= 60.0
+
+
+def test_unsupported_options_raise():
+    cfg = WaveFlowConfig()
+    kw = reference_kwargs(cfg)
+    bad = dict(kw, waveflow=False)
+    with pytest.raises(NotImplementedError):
+        WaveFlow(**bad)
+    bad = dict(kw, WN_config=dict(kw["WN_config"], n_channels=64))
+    with pytest.raises(NotImplementedError):
+        WaveFlow(**bad)
