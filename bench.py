@@ -148,6 +148,74 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_waveflow(args):
+    """BASELINE config 5: WaveFlow (h=16, 8 flows, WN_2d 8 x 128, 3x3), batch 64 x 10 s, one GPU per rank."""
+    import torch
+    import torch.distributed as dist
+    from cookietts_b200 import WaveFlow
+    from oracle.make_golden_waveflow import reference_kwargs
+    from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch if args.batch != 16 else 64
+    Tm = args.t_mel
+    cfg = WaveFlowConfig()
+    model = WaveFlow(precision=args.precision, **reference_kwargs(cfg))
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic_state_dict(cfg, 1234).items()})
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(2000 + rank)
+    mel = (torch.randn(B, 80, Tm, generator=g) * 2.0 - 5.0).clamp_(-11.5129, 2.0).to(dev)
+    z = torch.randn(B, Tm * 256, generator=g).to(dev)
+    warmup = max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        out = model.infer(mel, sigma=0.666, z=z, return_CPU=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); t0.record()
+    for _ in range(args.steps):
+        out = model.infer(mel, sigma=0.666, z=z, return_CPU=False)
+    t1.record(); barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        dist.destroy_process_group()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    C, L, G, M = 128, 8, 16, 80
+    macs_step = L * (9 * C * 2 * C + M * 2 * C) + ((L - 1) * 2 * C * C + C * C) + C + 2 * C     # per AR row step
+    macs_sample = 8 * 15 * macs_step / G
+    samples = world * B * Tm * 256
+    value = samples * args.steps / (ms * 1e-3)
+    peak_tf, _, peak_src = measured_peaks()
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"WaveFlow (ax model, h=16, 8 flows, WN_2d 8 x 128, 3x3) inverse pass, batch {B} x {Tm} mel frames per GPU, sigma 0.666, injected z",
+                       "precision": args.precision, "parallelism": f"dp{world} by utterance"},
+            "xrt": value / SR, "algorithmic_tflops": value * macs_sample * 2 / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "k_wf_layer_tc", "achieved": value * macs_sample * 2 / 1e12 / world,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": value * macs_sample * 2 / 1e12 / world / peak_tf,
+                         "peak_source": peak_src, "traffic": None,
+                         "note": "whole-step algorithmic FLOP/s (all kernels), not a per-kernel event timing"},
+            "clocks": clocks, "gpu_launches": int(model.launch_count() * args.steps),
+            "output_finite": bool(torch.isfinite(out).all())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,9 +226,13 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--t-mel", type=int, default=861)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="waveglow", choices=["waveglow", "waveflow"],
+                    help="waveglow = BASELINE config 2 (default, the driver's line); waveflow = config 5 (B=64 x 10 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "waveflow":
+        return run_waveflow(args)
 
     import torch
     import torch.distributed as dist
