@@ -5,3 +5,4 @@ inverse pass only) and the C ABI in `include/cwg.h` (`cookietts_b200/libcwg.so`)
 from .waveglow import WaveGlow  # noqa: F401
 from .packing import PackConfig, pack_state_dict  # noqa: F401
 from .waveflow import WaveFlow  # noqa: F401
+from .waveglow_ax import WaveGlowAx  # noqa: F401

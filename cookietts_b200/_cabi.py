@@ -34,6 +34,7 @@ class CwgWeights(C.Structure):
 
 EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
            "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
+           "cwg_ax_workspace_bytes", "cwg_ax_infer",
            "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer")
 
 

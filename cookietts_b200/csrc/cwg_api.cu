@@ -43,14 +43,15 @@ int check_config(const cwg_config* c) {
   return 0;
 }
 
-int check_mode(const cwg_config* c, int mode) {
+int check_mode(const cwg_config* c, int mode, bool cond_gemm = true) {
   CWG_REQUIRE(mode == CWG_MODE_FFMA || mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16, "unknown mode %d", mode);
   if (mode != CWG_MODE_FFMA) {
     CWG_REQUIRE(c->n_channels == 256 && c->cond_hidden == 256 && c->kernel_size == 3,
                 "tensor-core modes are built for n_channels=256, cond_hidden=256, kernel_size=3 "
                 "(got %d, %d, %d); use CWG_MODE_FFMA", c->n_channels, c->cond_hidden, c->kernel_size);
-    CWG_REQUIRE((c->n_mel * ((c->win_length + c->hop_length - 1) / c->hop_length)) % 64 == 0,
-                "tensor-core modes need n_mel * ceil(win/hop) to be a multiple of 64");
+    if (cond_gemm)
+      CWG_REQUIRE((c->n_mel * ((c->win_length + c->hop_length - 1) / c->hop_length)) % 64 == 0,
+                  "tensor-core modes need n_mel * ceil(win/hop) to be a multiple of 64");
   }
   return 0;
 }
@@ -214,6 +215,79 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
     }
     // coupling inverse + W^-1 of flow k, then start conv of flow k-1 (glow.py:329-347, :189)
     if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s)) return r;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ax WaveGlow (waveflow=False): efficient_model_ax.py:279-357 with AffineCouplingBlock.inverse
+// (efficient_modules.py:94-105), glow_ax.WN.forward (:375-418), InvertibleConv1x1.inverse (:269-286)
+// or PermuteHeight as the channel mixing (packed as a permutation matrix in `winv`).
+// Same layer / boundary kernels as the classic model; the cond vector is the interpolated mel
+// (channels padded to cfg->cond_hidden) and the WN's single 1x1 cond layer rides in w1's K columns.
+// ---------------------------------------------------------------------------------------------
+namespace {
+Dims ax_dims(const cwg_config* cfg, int batch, int frames, int t_samples) {
+  Dims d = make_dims(cfg, batch, frames);
+  d.Tp = t_samples / cfg->n_group;
+  d.BT = (long long)batch * d.Tp;
+  return d;
+}
+int ax_check(const cwg_config* cfg, int mode, int batch, int frames, int t_samples) {
+  if (int r = check_config(cfg)) return r;
+  if (int r = check_mode(cfg, mode, false)) return r;
+  CWG_REQUIRE(batch >= 1 && frames >= 1 && t_samples >= cfg->n_group && t_samples % cfg->n_group == 0,
+              "t_samples must be a positive multiple of n_group");
+  CWG_REQUIRE(cfg->n_mel <= cfg->cond_hidden, "n_mel must be <= cond_hidden (the padded cond width)");
+  return 0;
+}
+}  // namespace
+
+size_t cwg_ax_workspace_bytes(const cwg_config* cfg, int mode, int batch, int frames, int t_samples) {
+  if (ax_check(cfg, mode, batch, frames, t_samples)) return 0;
+  Dims d = ax_dims(cfg, batch, frames, t_samples);
+  Workspace ws;
+  carve(d, mode, nullptr, &ws);
+  return ws.bytes + 1024;
+}
+
+int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
+                 const float* mel, int frames, int pad_frames, int upsample_linear, int mix_first,
+                 const float* z, float sigma, float* audio, void* workspace, size_t workspace_bytes,
+                 int batch, int t_samples, void* cuda_stream) {
+  if (int r = ax_check(cfg, mode, batch, frames, t_samples)) return r;
+  CWG_REQUIRE(w && w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b && w->winv, "missing weight arrays");
+  if (mode == CWG_MODE_FFMA) CWG_REQUIRE(w->w1_f32 && w->w2_f32, "fp32 weight planes missing");
+  else CWG_REQUIRE(w->w1_hi && w->w2_hi && w->w1_lo && w->w2_lo, "bf16 hi/lo weight planes missing");
+  CWG_REQUIRE(mel && z && audio && pad_frames >= 0, "bad tensor arguments");
+  CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
+  Dims d = ax_dims(cfg, batch, frames, t_samples);
+  Workspace ws;
+  carve(d, mode, workspace, &ws);
+  CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool tc = mode != CWG_MODE_FFMA;
+  const int npass = mode == CWG_MODE_BF16X3 ? 3 : 1;
+  const int xfmt = tc ? 1 : 0;
+  const int F = cfg->n_flows, L = cfg->n_layers;
+  void* x0 = tc ? (void*)ws.xb[0] : (void*)ws.x[0];
+  void* h2 = tc ? (void*)ws.h2b : (void*)ws.h2;
+  // cond = interpolate(mel) once for all flows (upsample_first), efficient_model_ax.py:313-314
+  if (int r = launch_mel_up(xfmt, mel, h2, d.B, d.M, frames, frames + pad_frames, d.Tp, d.H, upsample_linear, s)) return r;
+  // z -> audio state; mix_first=False applies the channel mixing of flow F-1 before its coupling
+  if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s, mix_first ? -1 : F - 1)) return r;
+  for (int k = F - 1; k >= 0; --k) {                       // efficient_model_ax.py:325
+    for (int i = 0; i < L; ++i) {
+      if (tc) {
+        if (int r = launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s)) return r;
+      } else {
+        if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
+      }
+    }
+    // coupling inverse of flow k, then (mix_first) mixing of flow k or (else) mixing of flow k-1
+    // after the early-z concat, then the start conv of flow k-1
+    if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s,
+                                     mix_first ? k : k - 1)) return r;
   }
   return 0;
 }

@@ -65,7 +65,10 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
 // xfmt: 0 = fp32 [BT][C]; 1 = bf16 hi plane followed by lo plane (each [BT][C])
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
-                         const float* eo, void* x_out, cudaStream_t s);
+                         const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2);
+
+int launch_mel_up(int xfmt, const float* mel, void* out, int B, int M, int frames, int frames_padded, int Tp, int H,
+                  int linear, cudaStream_t s);
 
 // ---- launchers implemented in cwg_tc.cu (tcgen05 / TMA path) ----
 void debug_set_timing(long long* buf);

@@ -123,12 +123,13 @@ constexpr int TB = 32;   // group-steps per block in the boundary kernel
 
 struct BoundaryP {
   long long BT; int G, C;
-  int init, do_flow, do_start;
-  int n_rem, n_half;          // of flow_done
+  int init, do_flow, do_mix, do_start;
+  int n_rem, n_half;          // of flow_done (coupling)
+  int n_rem_mix;              // channels of the inverse 1x1 conv applied after the coupling
   int n_rem2, n_half2;        // of flow_next
   const float* z; float sigma;
   float* audio; const float* eo;
-  const float* winv;          // [MAX_GROUP][MAX_GROUP] of flow_done
+  const float* winv;          // [MAX_GROUP][MAX_GROUP] of the mixing flow
   const float* start_w;       // [C][MAX_GROUP/2] of flow_next
   const float* start_b;       // [C]
   void* x_out;
@@ -151,20 +152,23 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
       if (p.do_flow) {
         const int off = p.G - p.n_rem;
         const float* e = p.eo + m * CWG_EO_PAD;
-        float v[CWG_MAX_GROUP];
-        for (int j = 0; j < p.n_half; ++j) v[j] = a[off + j];
         for (int j = 0; j < p.n_rem - p.n_half; ++j) {
           // audio_1 = (audio_1 - b) / exp(s), glow.py:337
           float b = e[j], s = e[p.n_half + j];
-          v[p.n_half + j] = (a[off + p.n_half + j] - b) * expf(-s);
+          a[off + p.n_half + j] = (a[off + p.n_half + j] - b) * expf(-s);
         }
-        for (int r = 0; r < p.n_rem; ++r) {           // z = conv1d(z, W^-1), glow.py:98
+      }
+      if (p.do_mix) {                                 // z = conv1d(z, W^-1), glow.py:98
+        const int off = p.G - p.n_rem_mix;
+        float v[CWG_MAX_GROUP];
+        for (int c = 0; c < p.n_rem_mix; ++c) v[c] = a[off + c];
+        for (int r = 0; r < p.n_rem_mix; ++r) {
           float acc = 0.f;
-          for (int c = 0; c < p.n_rem; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
+          for (int c = 0; c < p.n_rem_mix; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
           a[off + r] = acc;
         }
       }
-      if (p.init || p.do_flow)
+      if (p.init || p.do_flow || p.do_mix)
         for (int g = 0; g < p.G; ++g) p.audio[m * p.G + g] = a[g];
       for (int g = 0; g < p.G; ++g) a_s[tid][g] = a[g];
     }
@@ -204,7 +208,54 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
   }
 }
 
+// mel [B][M][frames] -> cond [B][T'][H] (channels >= M are zero): zero-extended by pad frames and
+// interpolated to T' steps like F.interpolate(mode='linear', align_corners=True) / 'nearest'
+// (efficient_model_ax.py:171-182).  XFMT 0: fp32; 1: bf16 hi plane then lo plane.
+template <int XFMT>
+__global__ void k_mel_up(const float* __restrict__ mel, void* __restrict__ out, int B, int M, int frames,
+                         int frames_padded, int Tp, int H, int linear) {
+  long long n = (long long)B * Tp * H;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % H);
+  long long m = i / H;
+  int t = (int)(m % Tp), b = (int)(m / Tp);
+  float v = 0.f;
+  if (c < M) {
+    const float* row = mel + ((size_t)b * M + c) * frames;
+    if (linear) {
+      double src = Tp > 1 ? (double)t * (double)(frames_padded - 1) / (double)(Tp - 1) : 0.0;
+      int i0 = min((int)floor(src), frames_padded - 1);
+      int i1 = min(i0 + 1, frames_padded - 1);
+      float w = (float)(src - (double)i0);
+      float v0 = i0 < frames ? row[i0] : 0.f, v1 = i1 < frames ? row[i1] : 0.f;
+      v = v0 * (1.f - w) + v1 * w;
+    } else {
+      int i0 = min((int)floor((double)t * ((double)frames_padded / (double)Tp)), frames_padded - 1);
+      v = i0 < frames ? row[i0] : 0.f;
+    }
+  }
+  if (XFMT == 0) {
+    reinterpret_cast<float*>(out)[i] = v;
+  } else {
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out);
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    hi[n + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace
+
+int launch_mel_up(int xfmt, const float* mel, void* out, int B, int M, int frames, int frames_padded, int Tp, int H,
+                  int linear, cudaStream_t s) {
+  long long n = (long long)B * Tp * H;
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (xfmt == 0) k_mel_up<0><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
+  else           k_mel_up<1><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launch_cond_ffma(const Dims& d, const cwg_weights* w, int flow, const float* mel,
                      const float* cond_bias, float* h2, cudaStream_t s) {
@@ -250,14 +301,18 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
 
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
-                         const float* eo, void* x_out, cudaStream_t s) {
+                         const float* eo, void* x_out, cudaStream_t s, int mix_flow) {
+  // mix_flow: flow whose inverse 1x1 conv follows the coupling; -2 = the classic order (flow_done)
+  if (mix_flow == -2) mix_flow = flow_done;
   BoundaryP p{};
   p.BT = d.BT; p.G = d.G; p.C = d.C;
-  p.init = z != nullptr; p.do_flow = flow_done >= 0; p.do_start = flow_next >= 0;
+  p.init = z != nullptr; p.do_flow = flow_done >= 0; p.do_start = flow_next >= 0; p.do_mix = mix_flow >= 0;
   p.z = z; p.sigma = sigma; p.audio = audio; p.eo = eo; p.x_out = x_out;
-  if (p.do_flow) {
-    flow_channels(cfg, flow_done, &p.n_rem, &p.n_half);
-    p.winv = w->winv + (size_t)flow_done * CWG_MAX_GROUP * CWG_MAX_GROUP;
+  if (p.do_flow) flow_channels(cfg, flow_done, &p.n_rem, &p.n_half);
+  if (p.do_mix) {
+    int nh;
+    flow_channels(cfg, mix_flow, &p.n_rem_mix, &nh);
+    p.winv = w->winv + (size_t)mix_flow * CWG_MAX_GROUP * CWG_MAX_GROUP;
   }
   if (p.do_start) {
     flow_channels(cfg, flow_next, &p.n_rem2, &p.n_half2);

@@ -1,0 +1,275 @@
+"""Drop-in for the reference's "ax" model `efficient_model_ax.py::WaveGlow` with `waveflow=False`
+(1-D WN + affine coupling + invertible 1x1 conv / PermuteHeight), inverse pass only.
+
+It runs on the SAME sm_100a layer / boundary kernels as the classic model (csrc/cwg_tc.cu,
+cwg_simple.cu): the cond vector is the F.interpolate'd mel (efficient_model_ax.py:171-182, computed
+once because `upsample_first=True`), zero-padded to the kernels' cond width, and the WN's single 1x1
+cond layer (glow_ax.py:297-312) rides as extra K columns of each in_layer GEMM; PermuteHeight is
+packed as a permutation matrix in the W^-1 slot.  Interface mirrored: constructor keywords
+(efficient_model_ax.py:19-20), state_dict layout (`convinv.{k}.weight`, `WN.{k}.WN.*`), `inverse(z,
+cond)` (:279) and `infer(...)` (:359-388).  Unsupported options raise at construction.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .packing import PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
+
+
+def permute_height_index(k: int, h: int):
+    """PermuteHeight index list of flow k (efficient_modules.py:341-353,377-383)."""
+    idx = list(range(h))
+    if k % 4 in (2, 3):
+        half = h // 2
+        return idx[:half][::-1] + idx[half:][::-1]
+    return idx[::-1]
+
+
+def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "lo")) -> Dict[str, np.ndarray]:
+    """Arrays of `cwg_weights` for the ax 1-D model.  `pc.cond_hidden` is the padded cond width H
+    (>= n_mel); eo rows are ordered [t | log_s] so the shared boundary kernel's (b, s) convention holds
+    (AffineCouplingBlock.inverse: `log_s, t = WN(...)`, efficient_modules.py:102-103)."""
+    F, L, Cc, H, ks, M = pc.n_flows, pc.n_layers, pc.n_channels, pc.cond_hidden, pc.kernel_size, pc.n_mel
+    K1, N2 = ks * Cc + H, Cc + EO_PAD
+    w1 = np.zeros((F, L, 2 * Cc, K1)); b1 = np.zeros((F, L, 2 * Cc))
+    w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, EO_PAD))
+    start_w = np.zeros((F, Cc, MAX_GROUP // 2)); start_b = np.zeros((F, Cc))
+    winv = np.zeros((F, MAX_GROUP, MAX_GROUP))
+    for k, (n_rem, n_half) in enumerate(pc.flow_channels()):
+        p = f"WN.{k}.WN."
+        w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]
+        b_c = _np(sd[p + "cond_layers.0.bias"])
+        w_end = _np(sd[p + "end.weight"])[:, :, 0]
+        b_end = _np(sd[p + "end.bias"])
+        swap = np.r_[n_half:2 * n_half, 0:n_half]            # [t | log_s]
+        w_end, eo_bias = w_end[swap], b_end[swap].copy()
+        for i in range(L):
+            w_in = effective_weight(sd, p + f"in_layers.{i}")
+            w1[k, i, :, :ks * Cc] = w_in.transpose(0, 2, 1).reshape(2 * Cc, ks * Cc)
+            w1[k, i, :, ks * Cc:ks * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
+            b1[k, i] = _np(sd[p + f"in_layers.{i}.bias"]) + b_c[2 * Cc * i:2 * Cc * (i + 1)]
+            w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0]
+            b_rs = _np(sd[p + f"res_skip_layers.{i}.bias"])
+            if i < L - 1:
+                w2[k, i, :Cc] = w_rs[:Cc]; b2[k, i] = b_rs[:Cc]
+                w_skip, b_skip = w_rs[Cc:], b_rs[Cc:]
+            else:
+                w_skip, b_skip = w_rs, b_rs
+            w2[k, i, Cc:Cc + 2 * n_half] = w_end @ w_skip
+            eo_bias += w_end @ b_skip
+        eo_b[k, :2 * n_half] = eo_bias
+        start_w[k, :, :n_half] = effective_weight(sd, p + "start")[:, :, 0]
+        start_b[k] = _np(sd[p + "start.bias"])
+        if channel_mixing == "permuteheight":
+            for c, src in enumerate(permute_height_index(k, n_rem)):
+                winv[k, c, src] = 1.0
+        else:
+            winv[k, :n_rem, :n_rem] = np.linalg.inv(_np(sd[f"convinv.{k}.weight"]).reshape(n_rem, n_rem))
+    out = {"b1": b1.astype(np.float32), "b2": b2.astype(np.float32), "eo_b": eo_b.astype(np.float32),
+           "start_w": start_w.astype(np.float32), "start_b": start_b.astype(np.float32), "winv": winv.astype(np.float32)}
+    for name, arr in (("w1", w1), ("w2", w2)):
+        if "f32" in planes:
+            out[name + "_f32"] = arr.astype(np.float32)
+        if "hi" in planes:
+            out[name + "_hi"], out[name + "_lo"] = split_hi_lo(arr)
+    return out
+
+
+class _WN1d(nn.Module):
+    """Parameter holder with the layout of glow_ax.py:245-373 (supported subset)."""
+
+    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels):
+        super().__init__()
+        wn = nn.utils.weight_norm
+        self.in_layers = nn.ModuleList()
+        self.res_skip_layers = nn.ModuleList()
+        for i in range(n_layers):
+            d = 2 ** i
+            self.in_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels, kernel_size, dilation=d,
+                                               padding=(kernel_size * d - d) // 2), name="weight"))
+            self.res_skip_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels if i < n_layers - 1 else n_channels, 1), name="weight"))
+        self.start = wn(nn.Conv1d(n_in, n_channels, 1), name="weight")
+        self.end = nn.Conv1d(n_channels, 2 * n_in, 1)
+        self.end.weight.data.zero_(); self.end.bias.data.zero_()
+        self.cond_layers = nn.ModuleList([wn(nn.Conv1d(cond_in_channels, 2 * n_channels * n_layers, 1), name="weight")])
+
+
+class _Coupling(nn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        self.WN = _WN1d(**kw)
+
+
+class _InvConv(nn.Conv1d):
+    """`InvertibleConv1x1` parameter holder (efficient_modules.py:236-251): key `convinv.{k}.weight`."""
+
+    def __init__(self, c):
+        super().__init__(c, c, 1, bias=False)
+        w = torch.linalg.qr(torch.randn(c, c))[0]
+        if torch.det(w) < 0:
+            w[:, 0] = -w[:, 0]
+        self.weight.data = w.view(c, c, 1).contiguous()
+
+
+class WaveGlowAx(nn.Module):
+    """`efficient_model_ax.WaveGlow(..., waveflow=False)` - inverse pass on B200."""
+
+    def __init__(self, n_mel_channels, n_flows, n_group, n_early_every, n_early_size, memory_efficient,
+                 spect_scaling, upsample_mode, upsample_first, speaker_embed, cond_layers, cond_hidden_channels,
+                 cond_output_channels, cond_kernel_size, cond_residual, cond_padding_mode, WN_config, win_length,
+                 hop_length, sampling_rate=48000, cond_res_rezero=False, cond_activation_func="none",
+                 negative_slope=None, channel_mixing="1x1conv", mix_first=True, preceived_vol_scaling=False,
+                 waveflow=True, yoyo="depreciated", yoyo_WN="depreciated", shift_spect=0., scale_spect=1.,
+                 preempthasis=None, use_logvar_channels=False, load_hidden_from_disk=False,
+                 transposed_conv_hidden_dim=256, transposed_conv_kernel_size=4, transposed_conv_scales=None,
+                 transposed_conv_output_dim=256, transposed_conv_residual=False, transposed_conv_residual_linear=False,
+                 transposed_conv_res_rezero=False, group_conv_output_dim=None, group_conv_groupped=True,
+                 iso226_empthasis=False, precision: str = "bf16x3"):
+        super().__init__()
+        wn = dict(WN_config)
+        a = locals()
+
+        def need(cond, msg):
+            if not cond:
+                raise NotImplementedError("cookietts_b200.WaveGlowAx: " + msg)
+        need(not waveflow, "waveflow=True is served by cookietts_b200.WaveFlow")
+        mixing = str(channel_mixing).lower()
+        self.channel_mixing = "1x1conv" if mixing in "1x1convinvertibleconv1x1invconv" else (
+            "permuteheight" if mixing in "waveflowpermuteheightpermutechannelpermute" else None)
+        need(self.channel_mixing is not None, "channel_mixing must be '1x1conv' or 'permuteheight'")
+        need(self.channel_mixing == "1x1conv" or n_flows % 2 == 0, "PermuteHeight requires an even n_flows")
+        need(upsample_first is True, "upsample_first must be True")
+        need(not speaker_embed and not wn.get("speaker_embed_dim", 0), "speaker embeddings are not supported")
+        need(not cond_layers, "model-level cond_layers must be 0")
+        need(not transposed_conv_scales and not wn.get("transposed_conv_scales"), "TransposedUpsampleNet is not supported")
+        need(not group_conv_output_dim, "n_flow_group_conv is not supported")
+        need(not preempthasis and not preceived_vol_scaling and not iso226_empthasis, "pre-emphasis / volume scaling / ISO-226 are not supported")
+        need(not use_logvar_channels and not load_hidden_from_disk and not spect_scaling and not memory_efficient, "unsupported input/training options")
+        need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1 and wn.get("cond_activation_func", "none") == "none",
+             "WN cond_layers must be one linear 1x1 conv")
+        need(not wn.get("seperable_conv") and not wn.get("merge_res_skip") and wn.get("res_skip", True), "separable / merged res_skip variants are not supported")
+        need(wn.get("gated_unit", "GTU") == "GTU" and wn.get("n_layers_dilations_w") is None, "only the GTU gate with 2^i dilations is supported")
+        need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
+        ks = wn.get("kernel_size_w") or wn.get("kernel_size")
+        need(hop_length % n_group == 0 and n_group <= MAX_GROUP, "hop_length % n_group == 0 and n_group <= 16")
+        self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
+        self.shift_spect, self.scale_spect = shift_spect, scale_spect
+        self.mix_first, self.upsample_linear = bool(mix_first), wn.get("upsample_mode", "linear") == "linear"
+        self.precision = precision
+        self._base = dict(n_mel=n_mel_channels, n_flows=n_flows, n_group=n_group, n_early_every=n_early_every,
+                          n_early_size=n_early_size, win_length=hop_length, hop_length=hop_length,
+                          n_layers=wn["n_layers"], n_channels=wn["n_channels"], kernel_size=ks)
+        pc = PackConfig(cond_hidden=n_mel_channels, **self._base)
+        pc.validate()
+        self.WN = nn.ModuleList()
+        self.convinv = nn.ModuleList() if self.channel_mixing == "1x1conv" else []
+        for n_rem, n_half in pc.flow_channels():
+            if self.channel_mixing == "1x1conv":
+                self.convinv.append(_InvConv(n_rem))
+            self.WN.append(_Coupling(n_in=n_half, n_layers=wn["n_layers"], n_channels=wn["n_channels"],
+                                     kernel_size=ks, cond_in_channels=n_mel_channels))
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def remove_weightnorm(self):
+        return self
+
+    def forward(self, *a, **kw):
+        raise NotImplementedError("only the inverse pass is in scope of this implementation")
+
+    def _device(self):
+        return self.WN[0].WN.end.weight.device
+
+    def _ensure_packed(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision,)
+        if self._packed is not None and self._packed_key == key:
+            return
+        dev = self._device()
+        tensor = self.precision != "ffma"
+        # tensor-core kernels are built for a 256-wide cond operand; the fp32 path takes it unpadded
+        pc = PackConfig(cond_hidden=256 if tensor else self._base["n_mel"], **self._base)
+        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
+        pk = pack_ax_state_dict(sd, pc, self.channel_mixing, planes=("hi", "lo") if tensor else ("f32",))
+        dev_pk = {}
+        for name, arr in pk.items():
+            if arr.dtype == np.uint16:
+                arr = arr.view(np.int16)
+            dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        w = _cabi.CwgWeights()
+        for f in _cabi.WEIGHT_FIELDS:
+            setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
+        self.pack_config = pc
+        self._ccfg = _cabi.make_config(pc)
+        self._packed, self._packed_key, self._cw = dev_pk, key, w
+
+    @torch.no_grad()
+    def inverse(self, z, cond, speaker_ids=None, return_CPU=True, *, _pad_frames: int = 0):
+        """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("cookietts_b200.WaveGlowAx needs the module on a CUDA device (no CPU fallback)")
+        lib = _cabi.load()
+        if not getattr(lib, "_ax_bound", False):
+            lib.cwg_ax_workspace_bytes.restype = C.c_size_t
+            lib.cwg_ax_workspace_bytes.argtypes = [C.POINTER(_cabi.CwgConfig), C.c_int, C.c_int, C.c_int, C.c_int]
+            lib.cwg_ax_infer.restype = C.c_int
+            lib.cwg_ax_infer.argtypes = [C.POINTER(_cabi.CwgConfig), C.POINTER(_cabi.CwgWeights), C.c_int,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+            lib._ax_bound = True
+        mode = _cabi.MODES[self.precision]
+        cond = cond.to(device=dev, dtype=torch.float32)
+        if self.shift_spect != 0.:
+            cond = cond + self.shift_spect
+        if self.scale_spect != 1.:
+            cond = cond * self.scale_spect
+        cond = cond.contiguous()
+        z = z.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, frames = cond.shape
+        T = z.shape[1]
+        with torch.cuda.device(dev):
+            self._ensure_packed()
+            nbytes = lib.cwg_ax_workspace_bytes(self._ccfg, mode, B, frames, T)
+            if nbytes == 0:
+                raise _cabi.CwgError(lib.cwg_last_error().decode())
+            if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+            audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+            _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, _pad_frames,
+                                         int(self.upsample_linear), int(self.mix_first), z.data_ptr(), 1.0,
+                                         audio.data_ptr(), ws_ptr,
+                                         self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
+                                         B, T, torch.cuda.current_stream(dev).cuda_stream))
+        return (audio.cpu() if return_CPU else audio), None
+
+    @torch.no_grad()
+    def infer(self, spect, speaker_ids=None, artifact_trimming=1, sigma=1., t_scaler=1.0, return_CPU=True, *, z=None):
+        """efficient_model_ax.py:359-388.  `z` ([B, samples], standard normal) injects the latent."""
+        if spect.dim() == 2:
+            spect = spect[None]
+        in_dtype = spect.dtype
+        dev = self._device()
+        B, _, frames = spect.shape
+        steps = frames + max(artifact_trimming, 0)
+        samples = int((steps - 1) * self.hop_length * t_scaler)
+        samples -= samples % self.n_group
+        if z is None:
+            z = torch.randn(B, samples, device=dev)
+        zz = z.to(dev).float() * float(sigma) if sigma > 0 else torch.zeros(B, samples, device=dev)
+        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU, _pad_frames=max(artifact_trimming, 0))
+        if artifact_trimming > 0:
+            audio = audio[:, :-artifact_trimming * self.hop_length]
+        return audio.to(in_dtype)

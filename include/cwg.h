@@ -131,6 +131,19 @@ int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,
                       float* audio, const float* eo, void* x_out,
                       int batch, int t_mel, void* cuda_stream);
 
+/* ax WaveGlow with waveflow=False (efficient_model_ax.py:279-357; AffineCouplingBlock.inverse
+ * efficient_modules.py:94-105; glow_ax.WN.forward :375-418; InvertibleConv1x1.inverse :269-286 or
+ * PermuteHeight, packed as a permutation matrix in `winv`).  Uses cwg_config / cwg_weights:
+ * cond_hidden = padded width of the interpolated mel (256 in the tensor-core modes), w1's last
+ * cond_hidden columns hold the WN's 1x1 cond layer, cond_w_* are unused, eo rows are ordered
+ * [t | log_s].  mel [batch][n_mel][frames] is zero-extended by pad_frames and interpolated to
+ * T' = t_samples / n_group steps.  mix_first selects coupling-then-mixing (1) or mixing-then-coupling (0). */
+size_t cwg_ax_workspace_bytes(const cwg_config* cfg, int mode, int batch, int frames, int t_samples);
+int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
+                 const float* mel, int frames, int pad_frames, int upsample_linear, int mix_first,
+                 const float* z, float sigma, float* audio, void* workspace, size_t workspace_bytes,
+                 int batch, int t_samples, void* cuda_stream);
+
 /* =====================================================================================
  * WaveFlow (BASELINE config 5): the reference's "ax" model with waveflow=True
  *   efficient_model_ax.py:279-357  WaveGlow.inverse      efficient_modules.py:42-65  WaveFlowCoupling.inverse

@@ -70,9 +70,69 @@ CASES = {
 }
 
 
+def reference_kwargs_ax1d(cfg) -> dict:
+    """Constructor kwargs of the ax model with waveflow=False for an oracle.waveglow_ax_oracle.AxConfig."""
+    wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, kernel_size_w=None,
+              n_layers_dilations_w=None, n_layers_dilations_h=1, speaker_embed_dim=0, rezero=False, cond_layers=1,
+              cond_activation_func="none", negative_slope=None, cond_hidden_channels=256, cond_kernel_size=1,
+              cond_padding_mode="zeros", seperable_conv=False, res_skip=True, merge_res_skip=False,
+              upsample_mode=cfg.upsample_mode)
+    return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
+                n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size, memory_efficient=0.0,
+                spect_scaling=False, upsample_mode="normal", upsample_first=True, speaker_embed=0, cond_layers=0,
+                cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
+                cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
+                sampling_rate=22050, channel_mixing=cfg.channel_mixing, mix_first=cfg.mix_first, waveflow=False)
+
+
+AX_CASES = {
+    "waveglow_ax_tiny": (dict(n_mel_channels=8, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, n_layers=3,
+                              n_channels=16, win_length=64, hop_length=16), 2, 7, 0.8, 31, 1),
+    "waveglow_ax_permute": (dict(n_mel_channels=10, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, n_layers=2,
+                                 n_channels=8, win_length=64, hop_length=16, channel_mixing="permuteheight",
+                                 mix_first=False, upsample_mode="nearest"), 1, 9, 1.0, 32, 2),
+    "waveglow_ax_mixlast": (dict(n_mel_channels=12, n_flows=6, n_group=8, n_early_every=2, n_early_size=2, n_layers=2,
+                                 n_channels=8, win_length=64, hop_length=16, mix_first=False), 1, 6, 0.9, 33, 3),
+    # the classic-sized model (12 flows, 8 x 256) in its ax form, short clip
+    "waveglow_ax_256": (dict(), 1, 10, 0.666, 1234, 0),
+}
+
+
+def main_ax(WaveGlowAx, outdir):
+    from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd
+    for name, (kw, batch, frames, sigma, wseed, iseed) in AX_CASES.items():
+        cfg = AxConfig(**kw)
+        sd = ax_sd(cfg, wseed)
+        rs = np.random.RandomState(iseed)
+        mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
+        z = rs.standard_normal((batch, frames * cfg.hop_length)).astype(np.float32)
+        outs = {}
+        for dt, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
+            model = WaveGlowAx(**reference_kwargs_ax1d(cfg))
+            model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
+            model = model.eval().to(dt)
+            if dt == torch.float64 and cfg.channel_mixing == "1x1conv":
+                for conv in model.convinv:        # W_inverse is always created fp32 (efficient_modules.py:271-275)
+                    conv.W_inverse = conv.weight.squeeze().double().inverse().unsqueeze(-1)
+            with torch.no_grad():
+                inv, _ = model.inverse(torch.from_numpy(z).to(dt) * sigma, torch.from_numpy(mel).to(dt))
+                outs["inverse_" + tag] = inv.numpy()
+                with InjectedNormal([torch.from_numpy(z)]):
+                    aud = model.infer(torch.from_numpy(mel).to(dt), sigma=sigma)
+                outs["infer_" + tag] = aud.numpy()
+        e1 = np.abs(outs["inverse_fp32"] - outs["inverse_fp64"]).max()
+        print(f"{name}: inverse {outs['inverse_fp64'].shape} infer {outs['infer_fp64'].shape} "
+              f"rms {np.sqrt((outs['inverse_fp64'] ** 2).mean()):.3f} fp32-vs-fp64 {e1:.2e}")
+        np.savez_compressed(os.path.join(outdir, f"{name}.npz"), config=json.dumps(kw), batch=batch, frames=frames,
+                            sigma=sigma, weight_seed=wseed, input_seed=iseed, mel=mel, z=z,
+                            inverse_ref_fp32=outs["inverse_fp32"], inverse_ref_fp64=outs["inverse_fp64"],
+                            infer_ref_fp32=outs["infer_fp32"], infer_ref_fp64=outs["infer_fp64"])
+
+
 def main():
     WaveGlowAx = load_reference_ax()
     outdir = os.path.join(ROOT, "tests", "golden")
+    main_ax(WaveGlowAx, outdir)
     for name, (kw, batch, frames, sigma, wseed, iseed) in CASES.items():
         cfg = WaveFlowConfig(**kw)
         sd = synthetic_state_dict(cfg, wseed)

@@ -1,0 +1,159 @@
+"""CPU oracle for the 1-D ("WaveGlow", waveflow=False) configuration of the reference's ax model.
+
+TEST INFRASTRUCTURE ONLY (same rules as waveglow_oracle.py).  numpy restatement of, in
+/root/reference/CookieTTS/_4_mtw/waveglow/:
+  efficient_model_ax.py:279-357  WaveGlow.inverse (explicit z; early-z split :319-340)
+  efficient_model_ax.py:359-388  WaveGlow.infer (zero-frame pad, hop trim)
+  efficient_modules.py:94-105    AffineCouplingBlock.inverse (non-memory-efficient branch)
+  glow_ax.py:375-418             WN.forward (1-D, one 1x1 cond layer, GTU gate)
+  efficient_modules.py:269-286   InvertibleConv1x1.inverse   |  :360-403 PermuteHeight.inverse
+for the subset the B200 build supports: upsample_first=True with model-level F.interpolate, no
+model-level cond layers / upsample net / speaker embedding, channel_mixing '1x1conv' or
+'permuteheight', mix_first True or False, early outputs.
+
+Parity status: PINNED by oracle/make_golden_waveflow.py (cases `waveglow_ax_*`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List
+
+import numpy as np
+
+from .waveflow_oracle import _w, upsample_cond, permute_height
+
+
+@dataclass
+class AxConfig:
+    n_mel_channels: int = 80
+    n_flows: int = 12
+    n_group: int = 8
+    n_early_every: int = 4
+    n_early_size: int = 2
+    n_layers: int = 8
+    n_channels: int = 256
+    kernel_size: int = 3
+    win_length: int = 1024
+    hop_length: int = 256
+    upsample_mode: str = "linear"
+    channel_mixing: str = "1x1conv"      # or "permuteheight"
+    mix_first: bool = True
+
+    def flow_channels(self) -> List[int]:
+        out, n_rem = [], self.n_group
+        for k in range(self.n_flows):
+            if k % self.n_early_every == 0 and k > 0:
+                n_rem -= self.n_early_size
+            out.append(n_rem)
+        return out
+
+
+def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype):
+    """glow_ax.WN.forward (:375-418): returns (log_s, t)."""
+    p = f"WN.{k}.WN."
+    C, L = cfg.n_channels, cfg.n_layers
+    audio = np.einsum("oc,bct->bot", _w(sd, p + "start", dtype)[:, :, 0], audio0, optimize=True) \
+        + np.asarray(sd[p + "start.bias"], dtype)[None, :, None]
+    spect = np.einsum("oc,bct->bot", _w(sd, p + "cond_layers.0", dtype)[:, :, 0], cond_up, optimize=True) \
+        + np.asarray(sd[p + "cond_layers.0.bias"], dtype)[None, :, None]
+    B, _, T = audio.shape
+    output = None
+    for i in range(L):
+        d = 2 ** i
+        w_in = _w(sd, p + f"in_layers.{i}", dtype)
+        ks = w_in.shape[2]
+        pad = (ks * d - d) // 2
+        xp = np.zeros((B, C, T + 2 * pad), dtype); xp[:, :, pad:pad + T] = audio
+        acts = np.zeros((B, 2 * C, T), dtype)
+        for j in range(ks):
+            acts += np.einsum("oc,bct->bot", w_in[:, :, j], xp[:, :, j * d:j * d + T], optimize=True)
+        acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None] + spect[:, 2 * C * i:2 * C * (i + 1)]
+        g = np.tanh(acts[:, :C]) * (1.0 / (1.0 + np.exp(-acts[:, C:])))
+        rs = np.einsum("oc,bct->bot", _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0], g, optimize=True) \
+            + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
+        if i < L - 1:
+            audio = audio + rs[:, :C]
+            skip = rs[:, C:]
+        else:
+            skip = rs
+        output = skip if output is None else output + skip
+    end = np.einsum("oc,bct->bot", np.asarray(sd[p + "end.weight"], dtype)[:, :, 0], output, optimize=True) \
+        + np.asarray(sd[p + "end.bias"], dtype)[None, :, None]
+    n = end.shape[1] // 2
+    return end[:, :n], end[:, n:]                                        # chunk(2, 1): (log_s, t)
+
+
+def mix_inverse(sd, k, cfg: AxConfig, z, dtype):
+    if cfg.channel_mixing == "permuteheight":
+        return permute_height(z, k)
+    W = np.asarray(sd[f"convinv.{k}.weight"], dtype)[:, :, 0]
+    W_inv = np.linalg.inv(W.astype(np.float64)).astype(dtype) if dtype == np.float64 else np.linalg.inv(W.astype(np.float32))
+    return np.einsum("oc,bct->bot", W_inv, z, optimize=True)
+
+
+def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32):
+    z = np.asarray(z, dtype); cond = np.asarray(cond, dtype)
+    B = z.shape[0]
+    zz = z.reshape(B, -1, cfg.n_group).transpose(0, 2, 1)               # :310
+    cond_up = upsample_cond(cond, zz.shape[2], cfg.upsample_mode)        # :313-314
+    n_early = sum(1 for k in range(cfg.n_flows) if k % cfg.n_early_every == 0 and k > 0)
+    sizes = [cfg.n_early_size] * n_early + [cfg.n_group - cfg.n_early_size * n_early]
+    parts, off = [], 0
+    for s in sizes:                                                      # :319-322
+        parts.append(zz[:, off:off + s]); off += s
+    *remained, zz = parts
+    for k in reversed(range(cfg.n_flows)):                               # :325
+        if not cfg.mix_first:
+            zz = mix_inverse(sd, k, cfg, zz, dtype)
+        n_half = zz.shape[1] // 2
+        a0, a1 = zz[:, :n_half], zz[:, n_half:]
+        log_s, t = wn_forward(sd, k, cfg, a0, cond_up, dtype)            # efficient_modules.py:99-105
+        zz = np.concatenate([a0, (a1 - t) / np.exp(log_s)], axis=1)
+        if cfg.mix_first:
+            zz = mix_inverse(sd, k, cfg, zz, dtype)
+        if k % cfg.n_early_every == 0 and k:
+            zz = np.concatenate([remained.pop(), zz], axis=1)            # :339-340
+    return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)
+
+
+def infer_with_z(sd, cfg: AxConfig, spect, z, sigma, artifact_trimming=1, dtype=np.float32):
+    spect = np.asarray(spect, dtype)
+    if artifact_trimming > 0:
+        spect = np.concatenate([spect, np.zeros(spect.shape[:2] + (artifact_trimming,), dtype)], axis=2)
+    samples = (spect.shape[2] - 1) * cfg.hop_length
+    samples -= samples % cfg.n_group
+    assert z.shape[1] == samples
+    audio = inverse(sd, cfg, np.asarray(z, dtype) * dtype(sigma), spect, dtype)
+    return audio[:, :-artifact_trimming * cfg.hop_length] if artifact_trimming > 0 else audio
+
+
+def synthetic_state_dict(cfg: AxConfig, seed: int = 1234) -> Dict[str, np.ndarray]:
+    """Reference ax key layout for waveflow=False (probe-printed): `convinv.{k}.weight` (1x1conv mixing
+    only), `WN.{k}.WN.{in_layers,res_skip_layers,start,end,cond_layers.0}` with 3-D conv weights."""
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+    C, L, ks = cfg.n_channels, cfg.n_layers, cfg.kernel_size
+
+    def wn(prefix, shape, fan_in):
+        bound = 1.0 / np.sqrt(fan_in)
+        v = rs.uniform(-bound, bound, size=shape).astype(np.float32)
+        norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=tuple(range(1, v.ndim)), keepdims=True))
+        sd[prefix + ".bias"] = rs.uniform(-bound, bound, size=(shape[0],)).astype(np.float32)
+        sd[prefix + ".weight_g"] = (norm * rs.uniform(0.8, 1.2, size=norm.shape)).astype(np.float32)
+        sd[prefix + ".weight_v"] = v
+
+    for k, n_rem in enumerate(cfg.flow_channels()):
+        n_half = n_rem // 2
+        if cfg.channel_mixing == "1x1conv":
+            q1, _ = np.linalg.qr(rs.standard_normal((n_rem, n_rem)))
+            q2, _ = np.linalg.qr(rs.standard_normal((n_rem, n_rem)))
+            sd[f"convinv.{k}.weight"] = (q1 @ np.diag(rs.uniform(0.7, 1.4, size=n_rem)) @ q2).astype(np.float32)[:, :, None]
+        p = f"WN.{k}.WN."
+        for i in range(L):
+            wn(p + f"in_layers.{i}", (2 * C, C, ks), C * ks)
+            wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1), C)
+        wn(p + "start", (C, n_half, 1), n_half)
+        sd[p + "end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
+        sd[p + "end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
+        wn(p + "cond_layers.0", (2 * C * L, cfg.n_mel_channels, 1), cfg.n_mel_channels)
+    return sd

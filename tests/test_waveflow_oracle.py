@@ -43,3 +43,21 @@ def test_permute_height_is_an_involution():
         assert np.array_equal(permute_height(permute_height(x, k), k), x)
     assert list(permute_height(x, 0)[0, :, 0] // 3) == list(range(15, -1, -1))
     assert list(permute_height(x, 2)[0, :, 0] // 3) == [7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8]
+
+
+AX_CASES = ["waveglow_ax_tiny", "waveglow_ax_permute", "waveglow_ax_mixlast", "waveglow_ax_256"]
+
+
+@pytest.mark.parametrize("name", AX_CASES)
+def test_ax_1d_oracle_matches_reference(name):
+    """oracle/waveglow_ax_oracle.py (ax model, waveflow=False) against the unmodified reference."""
+    from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd, inverse as ax_inverse, infer_with_z as ax_infer
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = AxConfig(**json.loads(str(g["config"])))
+    sd = ax_sd(cfg, int(g["weight_seed"]))
+    out = ax_inverse(sd, cfg, g["z"].astype(np.float64) * float(g["sigma"]), g["mel"], np.float64)
+    assert max_abs(out, g["inverse_ref_fp64"]) < 1e-9
+    if name != "waveglow_ax_256":
+        out2 = ax_infer(sd, cfg, g["mel"], g["z"], float(g["sigma"]), 1, np.float64)
+        assert out2.shape == g["infer_ref_fp64"].shape
+        assert max_abs(out2, g["infer_ref_fp64"]) < 1e-9
