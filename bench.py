@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--t-mel", type=int, default=861)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels", type=int, default=256, help="WN channels (512 = BASELINE config 4 model)")
     ap.add_argument("--workload", default="waveglow", choices=["waveglow", "waveflow"],
                     help="waveglow = BASELINE config 2 (default, the driver's line); waveflow = config 5 (B=64 x 10 s)")
     args = ap.parse_args()
@@ -251,8 +252,9 @@ def main():
     T = Tm * 256
 
     # model: reference layout, random init (seed 1234) with non-zero `end`
-    sd = synthetic_state_dict(OracleConfig(), 1234)
-    model = WaveGlow(precision=args.precision, **MODEL_KW)
+    sd = synthetic_state_dict(OracleConfig(n_channels=args.channels), 1234)
+    kw = dict(MODEL_KW, WN_config=dict(MODEL_KW["WN_config"], n_channels=args.channels))
+    model = WaveGlow(precision=args.precision, **kw)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     model = model.to(dev).eval()
 
@@ -335,7 +337,7 @@ def main():
     samples_per_step = world * B * T
     value = samples_per_step * args.steps / (ms_total * 1e-3)
     e2e = samples_per_step * args.steps / (ms_e2e * 1e-3)
-    per_sample_macs, layer_step_macs = algorithmic_macs()
+    per_sample_macs, layer_step_macs = algorithmic_macs(C=args.channels)
     peak_tf, peak_hbm, peak_src = measured_peaks()
     # dominant kernel: k_layer_tc (one launch per WN layer); algorithmic FLOPs per launch / avg duration
     steps_per_launch = B * Tm * 32
@@ -344,7 +346,7 @@ def main():
     achieved = float(flops_per_launch.sum() / (layer_avg_ms.sum() * 1e-3) / 1e12)
     passes = {"bf16x3": 3, "bf16": 1, "ffma": 1}[args.precision]
     roofline = {
-        "bound": "tensor", "kernel": "k_layer_tc" if args.precision != "ffma" else "k_sgemm",
+        "bound": "tensor", "kernel": ("k_layer_tc" if args.channels == 256 else "k_gate512_tc+k_res512_tc") if args.precision != "ffma" else "k_sgemm",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
         "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
@@ -365,7 +367,7 @@ def main():
         "dtype": {"bf16x3": "bf16x3 (hi+lo split bf16 operands, 3 MMAs, fp32 accumulate)",
                   "bf16": "bf16 (fp32 accumulate, hi+lo residual)", "ffma": "f32"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"WaveGlow 12-flow/256-ch inverse pass, batch {B} x {Tm} mel frames ({T / SR:.1f} s) per GPU, "
+        "config": {"workload": f"WaveGlow 12-flow/{args.channels}-ch inverse pass, batch {B} x {Tm} mel frames ({T / SR:.1f} s) per GPU, "
                                f"sigma 0.666, injected z, random-init weights (seed 1234, end ~ N(0,0.02))",
                    "precision": args.precision, "batch_per_gpu": B, "t_mel": Tm, "samples_per_step": samples_per_step,
                    "parallelism": f"dp{world} by utterance", "l2": "working set (1.4 GB workspace per step) >> 126 MB L2, no flush needed"},

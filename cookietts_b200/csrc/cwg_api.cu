@@ -22,7 +22,7 @@ struct Workspace {
   // FFMA mode
   float *x[2], *h2, *pre, *acts;
   // tensor-core modes (each: hi plane then lo plane)
-  __nv_bfloat16 *xb[2], *h2b, *mel4;
+  __nv_bfloat16 *xb[2], *h2b, *mel4, *actsb;
   float* eo;
   size_t bytes;
 };
@@ -46,8 +46,8 @@ int check_config(const cwg_config* c) {
 int check_mode(const cwg_config* c, int mode, bool cond_gemm = true) {
   CWG_REQUIRE(mode == CWG_MODE_FFMA || mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16, "unknown mode %d", mode);
   if (mode != CWG_MODE_FFMA) {
-    CWG_REQUIRE(c->n_channels == 256 && c->cond_hidden == 256 && c->kernel_size == 3,
-                "tensor-core modes are built for n_channels=256, cond_hidden=256, kernel_size=3 "
+    CWG_REQUIRE((c->n_channels == 256 || c->n_channels == 512) && c->cond_hidden == 256 && c->kernel_size == 3,
+                "tensor-core modes are built for n_channels in {256, 512}, cond_hidden=256, kernel_size=3 "
                 "(got %d, %d, %d); use CWG_MODE_FFMA", c->n_channels, c->cond_hidden, c->kernel_size);
     if (cond_gemm)
       CWG_REQUIRE((c->n_mel * ((c->win_length + c->hop_length - 1) / c->hop_length)) % 64 == 0,
@@ -72,8 +72,15 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
     ws->xb[1] = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
     ws->h2b = (__nv_bfloat16*)take((size_t)d.BT * d.H * 2 * 2);
     ws->mel4 = (__nv_bfloat16*)take((size_t)d.B * d.Tm * d.KC * 2 * 2);
+    if (d.C == 512) ws->actsb = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
   }
   ws->bytes = off;
+}
+
+int layer_tc(const Dims& d, const cwg_weights* w, int npass, int k, int i, const Workspace& ws, cudaStream_t s) {
+  if (d.C == 512)
+    return launch_layer_tc512(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.actsb, ws.eo, s);
+  return launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s);
 }
 
 int check_run(const cwg_config* cfg, const cwg_weights* w, int mode, int batch, int t_mel) {
@@ -115,7 +122,7 @@ size_t cwg_workspace_bytes(const cwg_config* cfg, int mode, int batch, int t_mel
 int cwg_launch_count(const cwg_config* cfg, int mode) {
   if (check_config(cfg) || check_mode(cfg, mode)) return -1;
   // per flow: cond (+ mel4 build in tensor modes), L layers, one boundary; plus the initial boundary
-  int per_layer = mode == CWG_MODE_FFMA ? 3 : 1;
+  int per_layer = mode == CWG_MODE_FFMA ? 3 : (cfg->n_channels == 512 ? 2 : 1);
   int cond = mode == CWG_MODE_FFMA ? 1 : 1;
   int once = mode == CWG_MODE_FFMA ? 1 : 2;   // init boundary (+ mel4 im2col)
   return once + cfg->n_flows * (cond + per_layer * cfg->n_layers + 1);
@@ -151,6 +158,14 @@ int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow
     CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
     return launch_layer_ffma(d, w, flow, layer, (const float*)x_in, (float*)x_out, (const float*)h2, eo,
                              ws.pre, ws.acts, s);
+  }
+  if (d.C == 512) {
+    Workspace ws;
+    CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
+    carve(d, mode, workspace, &ws);
+    CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+    return launch_layer_tc512(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, layer, (const __nv_bfloat16*)x_in,
+                              (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, ws.actsb, eo, s);
   }
   return launch_layer_tc(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, layer, (const __nv_bfloat16*)x_in,
                          (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, eo, s);
@@ -207,7 +222,7 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
       const int ev = (F - 1 - k) * L + i;
       if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_begin[ev], s));
       if (tc) {
-        if (int r = launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s)) return r;
+        if (int r = layer_tc(d, w, npass, k, i, ws, s)) return r;
       } else {
         if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
       }
@@ -279,7 +294,7 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   for (int k = F - 1; k >= 0; --k) {                       // efficient_model_ax.py:325
     for (int i = 0; i < L; ++i) {
       if (tc) {
-        if (int r = launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s)) return r;
+        if (int r = layer_tc(d, w, npass, k, i, ws, s)) return r;
       } else {
         if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
       }

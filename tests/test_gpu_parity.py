@@ -40,9 +40,11 @@ def test_ffma_matches_reference(name):
     assert max_abs(out, g["audio_ref_fp32"]) <= TOL["ffma"]["max_abs"]
 
 
+@pytest.mark.parametrize("name", ["config1", "c512"])
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-def test_tensor_core_modes_match_reference(precision):
-    out, g = run("config1", precision)
+def test_tensor_core_modes_match_reference(precision, name):
+    """config1: the fused 256-channel layer kernel; c512: the two-kernel 512-channel layer."""
+    out, g = run(name, precision)
     ref = g["audio_ref_fp64"]
     assert np.isfinite(out).all()
     assert max_abs(out, ref) <= TOL[precision]["max_abs"]
