@@ -90,6 +90,36 @@ def infer_long(model, spect: torch.Tensor, sigma: float = 1.0, z: Optional[torch
     return torch.cat(parts, dim=1)
 
 
+def infer_long_sharded(model, spect: torch.Tensor, sigma: float = 1.0, z: Optional[torch.Tensor] = None,
+                       n_chunks: Optional[int] = None, dst: int = 0, **kw) -> Optional[torch.Tensor]:
+    """Long-form inference of the SAME utterance(s) across ranks (BASELINE config 4): the mel is cut
+    into `n_chunks` (default: world size) halo-overlapped chunks, rank r computes chunks r, r+world, ...
+    on its own GPU with the latent sliced by position, and rank `dst` receives the stitched waveform
+    `[B, T_mel*hop]` (None elsewhere).  `spect` and `z` must be identical on every rank (pass an
+    explicit z; ranks cannot draw the same latent independently).  Needs an initialised process group."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    pc = model.pack_config
+    B, _, t_mel = spect.shape
+    if z is None:
+        raise ValueError("infer_long_sharded needs an explicit latent z shared by all ranks")
+    plan = plan_chunks(t_mel, n_chunks or world, pc)
+    hop = pc.hop_length
+    dev = next(model.parameters()).device
+    # every rank sends a fixed-size buffer: its chunks' cores laid out at their final positions
+    mine = torch.zeros(B, t_mel * hop, device=dev)
+    for ch in plan[rank::world]:
+        mine[:, ch.core0 * hop:ch.core1 * hop] = infer_chunk(model, spect, z, sigma, ch, **kw)
+    bufs = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.empty_like(mine)
+    for i, ch in enumerate(plan):
+        out[:, ch.core0 * hop:ch.core1 * hop] = bufs[i % world][:, ch.core0 * hop:ch.core1 * hop]
+    return out
+
+
 def gather_waveforms(audio_local: torch.Tensor, n_items: int, dst: int = 0) -> Optional[torch.Tensor]:
     """Final collective of the sharded path: gathers every rank's `[B_local, T]` waveforms to
     `dst` and restores utterance order.  Ranks may own different counts (round-robin shards differ
