@@ -61,7 +61,6 @@ inline int map_act(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uin
 // ------------------------------------------------------------------------------------------
 constexpr int TILE_A = 128 * 128;      // [128 rows][64 bf16] = 16 KB
 constexpr uint32_t IDESC_N256 = umma_idesc_bf16(128, 256);
-constexpr uint32_t IDESC_N128 = umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_N16 = umma_idesc_bf16(128, 16);
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
@@ -76,22 +75,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t b_addr, u
     umma_bf16(tmem_d, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, (first && k == 0) ? 0u : 1u);
 }
 
-// two 16-column TMEM loads + wait in ONE asm block so no consumer can be scheduled before the wait
-__device__ __forceinline__ void tmem_ld16x2_sync(uint32_t ta, uint32_t tb, float* a, float* b) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(ta), "r"(tb)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
-}
+// 16-column TMEM load + wait in ONE asm block so no consumer can be scheduled before the wait
 __device__ __forceinline__ void tmem_ld16_sync(uint32_t ta, float* a) {
   uint32_t r[16];
   asm volatile(
