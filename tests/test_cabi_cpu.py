@@ -147,3 +147,24 @@ def test_waveflow_state_dict_layout_and_packing_cpu():
         hist.append(nxt)
     assert np.abs(eo[..., 0] - log_s).max() < 1e-6
     assert np.abs(eo[..., 1] - t).max() < 1e-6
+
+
+def test_compat_import_paths():
+    """`compat.install()` serves the reference import paths (run in a subprocess: it edits sys.modules)."""
+    import subprocess, sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import cookietts_b200.compat as c; c.install()\n"
+        "from CookieTTS._4_mtw.waveglow.glow import WaveGlow\n"
+        "from CookieTTS._4_mtw.waveglow.efficient_model_ax import WaveGlow as Ax\n"
+        "import cookietts_b200 as p\n"
+        "assert WaveGlow is p.WaveGlow\n"
+        "from oracle.make_golden_waveflow import reference_kwargs, reference_kwargs_ax1d\n"
+        "from oracle.waveflow_oracle import WaveFlowConfig\n"
+        "from oracle.waveglow_ax_oracle import AxConfig\n"
+        "assert isinstance(Ax(**reference_kwargs(WaveFlowConfig(n_flows=2, n_layers=1))), p.WaveFlow)\n"
+        "assert isinstance(Ax(**reference_kwargs_ax1d(AxConfig(n_flows=2, n_layers=1, n_channels=8))), p.WaveGlowAx)\n"
+        "assert c.is_ax({'upsample_first': True}) and not c.is_ax({'n_flows': 12})\n"
+        "print('ok')\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
