@@ -125,17 +125,20 @@ struct WfLayerArgs {
   int has_res, first;
 };
 
-// smem pool: A units 0..3 (16 KB), weight slots [256 x 64] = unit pairs 4..11 (barriers 4..7).
-// acts hi -> units 0,1; lo -> units 2,3.  x_old tiles / x_new staging reuse units 0..3.
-constexpr int W_NS = 12, W_NA = 4, W_NBAR = 8;
-constexpr int W_OFF_B1 = W_NS * TILE_A;                // 196608
+// Two CTAs per SM (each: 6 smem units = 96 KB, 256 TMEM columns), so one CTA's epilogues overlap
+// the other's MMAs.  Pool: A units 0,1 (barriers 0,1); weight slots [256 x 64] = unit pairs (2,3) and
+// (4,5) (barriers 2,3).  After GEMM1: acts hi -> units 0,1, lo -> units 2,3; W2 tiles use slot 1
+// only when acts lo occupies slot 0 (NPASS = 3).  x_old tiles / x_new staging reuse units 0..3.
+// TMEM: pre-activation in columns 0..255; [res | folded end] reuses columns 0..143 after the gate.
+constexpr int W_NS = 6, W_NA = 2, W_NBAR = 4;
+constexpr int W_OFF_B1 = W_NS * TILE_A;                // 98304
 constexpr int W_OFF_B2 = W_OFF_B1 + 1024;
 constexpr int W_OFF_BAR = W_OFF_B2 + 512;
 constexpr int W_SMEM = W_OFF_BAR + 256 + 1024;
 constexpr int W_THREADS = 384, W_EPI_THREADS = 256;
 
 template <int NPASS>
-__global__ void __launch_bounds__(W_THREADS, 1)
+__global__ void __launch_bounds__(W_THREADS, 2)
 k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
               const __grid_constant__ CUtensorMap tm_m_hi, const __grid_constant__ CUtensorMap tm_m_lo,
               const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
@@ -165,7 +168,7 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
     mbar_init(acc1_full, 1); mbar_init(acts_ready, W_EPI_THREADS); mbar_init(acc2_full, 1); mbar_init(xold_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   if (warp >= 4) {
     const int e = threadIdx.x - 128;
     b1s[e] = __ldg(a.b1 + e);
@@ -204,12 +207,13 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
   } else if (warp == 2 && lane == 0) {
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w2_hi);
     int j = 0; uint32_t pm = 0;
-    auto put = [&](const CUtensorMap* m, int c0, int r0, uint32_t bytes) {
-      mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
+    auto put = [&](const CUtensorMap* m, int c0, int r0, uint32_t bytes, bool only1) {
+      if (only1) j = 1;
+      mbar_wait(&empty[W_NA + j], ((pm >> j) & 1u) ^ 1u);
       pm ^= 1u << j;
-      mbar_arrive_expect_tx(&full[4 + j], bytes);
-      tma_load_2d(bslot(j), m, &full[4 + j], c0, r0);
-      j = (j + 1) & 3;
+      mbar_arrive_expect_tx(&full[W_NA + j], bytes);
+      tma_load_2d(bslot(j), m, &full[W_NA + j], c0, r0);
+      j ^= 1;
     };
     for (int kb = 0; kb < nkb; ++kb) {
       int col;
@@ -219,46 +223,51 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
       } else {
         col = WF_KH * WF_KW * WF_C + (kb - nkb_x) * 64;
       }
-      for (int pl = 0; pl < PL; ++pl) put(pl ? &tm_w1_lo : &tm_w1_hi, col, a.w1_row0, 2 * TILE_A);
+      for (int pl = 0; pl < PL; ++pl) put(pl ? &tm_w1_lo : &tm_w1_hi, col, a.w1_row0, 2 * TILE_A, false);
     }
     for (int kb = 0; kb < 2; ++kb)
-      for (int pl = 0; pl < PL; ++pl) put(pl ? &tm_w2_lo : &tm_w2_hi, kb * 64, a.w2_row0, WF_N2 * 128);
+      for (int pl = 0; pl < PL; ++pl) put(pl ? &tm_w2_lo : &tm_w2_hi, kb * 64, a.w2_row0, WF_N2 * 128, NPASS == 3);
   } else if (warp == 1 && lane == 0) {
     int sa = 0, jb = 0; uint32_t cm = 0;
     auto wait_full = [&](int bar) { mbar_wait(&full[bar], (cm >> bar) & 1u); cm ^= 1u << bar; };
     // GEMM1: pre[128 x 256] (tanh | sigmoid halves) in TMEM columns 0..255
     for (int kb = 0; kb < nkb; ++kb) {
-      const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
+      const int sa_hi = sa; wait_full(sa); sa ^= 1;
       int sa_lo = 0;
-      if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
-      const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+      if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa ^= 1; }
+      const int jb_hi = jb; wait_full(W_NA + jb); jb ^= 1;
       int jb_lo = 0;
-      if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
+      if (NPASS == 3) { jb_lo = jb; wait_full(W_NA + jb); jb ^= 1; }
       tc_fence_after_sync();
       issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), tmem, IDESC_N256, kb == 0);
       if (NPASS == 3) {
         issue_kblock_fast(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), tmem, IDESC_N256, false);
         issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), tmem, IDESC_N256, false);
       }
-      umma_commit(&empty[4 + jb_hi]);
-      if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
+      umma_commit(&empty[W_NA + jb_hi]);
+      if (NPASS == 3) umma_commit(&empty[W_NA + jb_lo]);
       umma_commit(&empty[sa_hi]);
       if (NPASS == 3) umma_commit(&empty[sa_lo]);
     }
     umma_commit(acc1_full);
-    // GEMM2: [res (128) | folded end (16)] = acts x W2^T in TMEM columns 256..399
+    // GEMM2: [res (128) | folded end (16)] = acts x W2^T, reusing TMEM columns 0..143
     mbar_wait(acts_ready, 0);
     tc_fence_after_sync();
     for (int kb = 0; kb < 2; ++kb) {
       const uint32_t a_hi = smem_u32(slot(kb)), a_lo = smem_u32(slot(2 + kb));
-      const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
-      int jb_lo = 0;
-      if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
+      if (NPASS == 3) jb = 1;
+      const int jb_hi = jb; wait_full(W_NA + jb); jb ^= 1;
       tc_fence_after_sync();
-      issue_kblock_fast(a_hi, smem_u32(bslot(jb_hi)), tmem + 256, IDESC_N144, kb == 0);
+      issue_kblock_fast(a_hi, smem_u32(bslot(jb_hi)), tmem, IDESC_N144, kb == 0);
       if (NPASS == 3) {
-        issue_kblock_fast(a_lo, smem_u32(bslot(jb_hi)), tmem + 256, IDESC_N144, false);
-        issue_kblock_fast(a_hi, smem_u32(bslot(jb_lo)), tmem + 256, IDESC_N144, false);
+        issue_kblock_fast(a_lo, smem_u32(bslot(jb_hi)), tmem, IDESC_N144, false);
+        umma_commit(&empty[W_NA + jb_hi]);
+        wait_full(W_NA + 1);                 // W2 lo tile arrives in the same (only) slot
+        tc_fence_after_sync();
+        issue_kblock_fast(a_hi, smem_u32(bslot(1)), tmem, IDESC_N144, false);
+        umma_commit(&empty[W_NA + 1]);
+      } else {
+        umma_commit(&empty[W_NA + jb_hi]);
       }
     }
     umma_commit(acc2_full);
@@ -320,7 +329,7 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
     tc_fence_after_sync();
     if (half == 0) {
       uint32_t sk[16];
-      tmem_issue16(trow + 256 + WF_C, sk);
+      tmem_issue16(trow + WF_C, sk);
       tmem_wait16(sk);
       if (valid) {
         float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
@@ -337,14 +346,14 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
       const float4* b2v = reinterpret_cast<const float4*>(b2s);
       uint32_t buf[2][16];
       const int c0 = half * 4;
-      tmem_issue16(trow + 256 + c0 * 16, buf[0]);
+      tmem_issue16(trow + c0 * 16, buf[0]);
       mbar_wait(xold_full, 0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
         tmem_wait16(cur);
-        if (i + 1 < 4) tmem_issue16(trow + 256 + (c + 1) * 16, buf[(i + 1) & 1]);
+        if (i + 1 < 4) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
         uint8_t* thi = slot(c >> 2);
         uint8_t* tlo = slot(2 + (c >> 2));
         const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);
@@ -382,7 +391,7 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
     tc_fence_before_sync();
   }
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 512); }
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 256); }
 }
 
 struct WfWorkspace {
