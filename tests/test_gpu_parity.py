@@ -149,3 +149,28 @@ def test_weight_update_invalidates_packed_cache():
             delattr(conv, "W_inverse")
     c = m.infer(mel, sigma=0.666, z=z)
     assert torch.equal(b, c)
+
+
+def test_infer_is_cuda_graph_capturable():
+    """The C ABI never allocates or synchronises and passes tensor maps by value, so a whole infer
+    (122 launches) can be captured into a CUDA graph and replayed on new inputs in the same buffers."""
+    m = _model("bf16x3")
+    mel, z = _inputs(1, 40, seed=11)
+    ref = m.infer(mel, sigma=0.666, z=z)                      # warm-up: packs weights, sizes the workspace
+    static_mel, static_z = mel.clone(), z.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        m.infer(static_mel, sigma=0.666, z=static_z)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = m.infer(static_mel, sigma=0.666, z=static_z)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, ref)
+    mel2, z2 = _inputs(1, 40, seed=12)
+    static_mel.copy_(mel2); static_z.copy_(z2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, m.infer(mel2, sigma=0.666, z=z2))
