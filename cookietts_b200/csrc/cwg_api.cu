@@ -72,7 +72,7 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
     ws->xb[1] = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
     ws->h2b = (__nv_bfloat16*)take((size_t)d.BT * d.H * 2 * 2);
     ws->mel4 = (__nv_bfloat16*)take((size_t)d.B * d.Tm * d.KC * 2 * 2);
-    if (d.C == 512) ws->actsb = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
+    if (d.C == 512) ws->actsb = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);   // gated activations (two-kernel layer)
   }
   ws->bytes = off;
 }
