@@ -207,8 +207,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   uint64_t* acc1_full = wse_full + 1;
   uint64_t* acts_ready = acc1_full + 1;
   uint64_t* acc2_full = acts_ready + 1;
-  uint64_t* xold_full = acc2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xold_full + 1);
+  uint64_t* xold_full = acc2_full + 1;      // [4]: x_old tiles of 64-channel block kb have landed
+  uint64_t* g2_done = xold_full + 4;        // [4]: GEMM2 no longer reads the acts tiles of block kb
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g2_done + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * 128, b = blockIdx.y;
@@ -219,14 +220,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L_NBAR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, L_EPI_THREADS); mbar_init(acc2_full, 1);
-    mbar_init(xold_full, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&xold_full[i], 1); mbar_init(&g2_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (warp >= 4) {   // biases -> smem (read as broadcast float4 in the epilogues)
-    const int e = threadIdx.x - 128;
-    b1s[e] = __ldg(a.b1 + e); b1s[256 + e] = __ldg(a.b1 + 256 + e); b2s[e] = __ldg(a.b2 + e);
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -345,6 +342,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         }
         umma_commit(&empty[4 + jb_hi]);
         if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
+        umma_commit(&g2_done[kb]);
       } else {
         issue_kblock_fast(a_hi, w_hi, d16, IDESC_N16, kb == 0);
         if (NPASS == 3) {
@@ -355,13 +353,16 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     }
     umma_commit(acc2_full);
     CWG_STAMP(8);
+  } else if (warp == 3 && lane == 0) {
+    // ---------------- residual prefetch: as soon as GEMM2 is done with the acts tiles of a 64-channel
+    // block, the x_old (centre tap) tiles of that block are TMA-loaded over them (units kb / 4+kb)
     if (a.has_res) {
-      // x_old (centre tap) tiles -> units 0..7 for the residual add, once GEMM2 no longer reads acts
-      mbar_wait(acc2_full, 0);
-      mbar_arrive_expect_tx(xold_full, 8 * TILE_A);
+      tma_prefetch_desc(&tm_x_lo);
       for (int kb = 0; kb < 4; ++kb) {
-        tma_load_3d(slot(kb), &tm_x_hi, xold_full, kb * 64, t0, b);
-        tma_load_3d(slot(4 + kb), &tm_x_lo, xold_full, kb * 64, t0, b);
+        mbar_wait(&g2_done[kb], 0);
+        mbar_arrive_expect_tx(&xold_full[kb], 2 * TILE_A);
+        tma_load_3d(slot(kb), &tm_x_hi, &xold_full[kb], kb * 64, t0, b);
+        tma_load_3d(slot(4 + kb), &tm_x_lo, &xold_full[kb], kb * 64, t0, b);
       }
     }
   } else if (warp >= 4) {
@@ -375,6 +376,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     const float4* b1t = reinterpret_cast<const float4*>(b1s);
     const float4* b1g = reinterpret_cast<const float4*>(b1s + 256);
 
+    {   // biases -> smem (read as broadcast float4 in the epilogues); off the prologue's critical path
+      const int e = threadIdx.x - 128;
+      b1s[e] = __ldg(a.b1 + e); b1s[256 + e] = __ldg(a.b1 + 256 + e); b2s[e] = __ldg(a.b2 + e);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     // gate: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) -> bf16 planes in slots 0..7 (GEMM2's A operand)
     if (stamp) dbg[0] = clock64();
     mbar_wait(acc1_full, 0);
@@ -440,11 +446,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       uint32_t buf[2][16];
       const int c0 = half * 8;
       tmem_issue16(trow + c0 * 16, buf[0]);
-      mbar_wait(xold_full, 0);          // x_old tiles (hi: units 0..3, lo: units 4..7) have landed
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
+        if ((i & 3) == 0) mbar_wait(&xold_full[c >> 2], 0);   // x_old tiles of this 64-channel block have landed
         tmem_wait16(cur);
         if (i + 1 < 8) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
         uint8_t* thi = slot(c >> 2);
@@ -480,7 +486,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         }
       }
       if (stamp) dbg[10] = clock64();
-      if (quarter == 0 && lane == 0) tma_store_wait_all();
+      if (quarter == 0 && lane == 0) tma_store_wait_read();
     }
     tc_fence_before_sync();
     if (stamp) dbg[4] = clock64();

@@ -162,7 +162,7 @@ k_gate512_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
         }
       }
     }
-    if (quarter == 0 && lane == 0) tma_store_wait_all();
+    if (quarter == 0 && lane == 0) tma_store_wait_read();
     tc_fence_before_sync();
   }
   __syncthreads();
@@ -359,7 +359,7 @@ k_res512_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           }
         }
       }
-      if (quarter == 0 && lane == 0) tma_store_wait_all();
+      if (quarter == 0 && lane == 0) tma_store_wait_read();
     }
     tc_fence_before_sync();
   }

@@ -385,7 +385,7 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
                          "r"(half * 64), "r"(t0), "r"(b), "r"(a.ring_out + a.row % 3)
                        : "memory");
         tma_store_commit();
-        tma_store_wait_all();
+        tma_store_wait_read();
       }
     }
     tc_fence_before_sync();
