@@ -185,8 +185,10 @@ constexpr int L_OFF_B1 = L_OFF_WSE + 16384;            // 212992
 constexpr int L_OFF_B2 = L_OFF_B1 + 2048;              // 215040
 constexpr int L_OFF_BAR = L_OFF_B2 + 1024;             // 216064
 constexpr int L_SMEM = L_OFF_BAR + 256 + 1024;         // 217344
-constexpr int L_THREADS = 384;                         // 12 warps: TMA-A, MMA, TMA-B, spare, 8 epilogue
-constexpr int L_EPI_THREADS = 256;
+constexpr int L_EPI_WARPS = 8;                         // 2 per TMEM lane quarter, each owns 128 channels (16 warps measured no faster)
+constexpr int L_EPI_THREADS = 32 * L_EPI_WARPS;
+constexpr int L_THREADS = 128 + L_EPI_THREADS;         // warps 0-3: TMA-A, MMA, TMA-B, residual prefetch
+constexpr int L_CPG = 16 / (L_EPI_WARPS / 4);          // 16-channel chunks per epilogue column group
 
 template <int NPASS>
 __global__ void __launch_bounds__(L_THREADS, 1)
@@ -366,9 +368,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ---------------- 8 epilogue warps: TMEM lane quarter = warp % 4 (one group-step per lane),
-    // column half = (warp - 4) / 4 (channels [128*half, 128*half + 128)).
-    const int quarter = warp & 3, half = (warp - 4) >> 2, row = quarter * 32 + lane;
+    // ---------------- epilogue warps: TMEM lane quarter = warp % 4 (one group-step per lane),
+    // column group = (warp - 4) / 4 (channels [16*L_CPG*grp, +16*L_CPG)).
+    const int quarter = warp & 3, grp = (warp - 4) >> 2, row = quarter * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool valid = t0 + row < a.Tp;
     const size_t m = (size_t)b * a.Tp + (size_t)min(t0 + row, a.Tp - 1);
@@ -378,8 +380,8 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
     {   // biases -> smem (read as broadcast float4 in the epilogues); off the prologue's critical path
       const int e = threadIdx.x - 128;
-      b1s[e] = __ldg(a.b1 + e); b1s[256 + e] = __ldg(a.b1 + 256 + e); b2s[e] = __ldg(a.b2 + e);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (e < 256) { b1s[e] = __ldg(a.b1 + e); b1s[256 + e] = __ldg(a.b1 + 256 + e); b2s[e] = __ldg(a.b2 + e); }
+      asm volatile("bar.sync 1, %0;" ::"n"(L_EPI_THREADS) : "memory");
     }
     // gate: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) -> bf16 planes in slots 0..7 (GEMM2's A operand)
     if (stamp) dbg[0] = clock64();
@@ -388,14 +390,14 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (stamp) dbg[1] = clock64();
     {
       uint32_t buf[2][32];
-      const int c0 = half * 8;
+      const int c0 = grp * L_CPG;
       tmem_issue16x2(trow + c0 * 16, trow + 256 + c0 * 16, buf[0]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < L_CPG; ++i) {
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
         tmem_wait32(cur);
-        if (i + 1 < 8) tmem_issue16x2(trow + (c + 1) * 16, trow + 256 + (c + 1) * 16, buf[(i + 1) & 1]);
+        if (i + 1 < L_CPG) tmem_issue16x2(trow + (c + 1) * 16, trow + 256 + (c + 1) * 16, buf[(i + 1) & 1]);
         float act[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -415,7 +417,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
     // prefetch this row's folded-`end` accumulator while GEMM2 runs
     float4 eold[4];
-    if (half == 0) {
+    if (grp == 0) {
       const float4* e = reinterpret_cast<const float4*>(a.first ? a.eo_b : a.eo + m * CWG_EO_PAD);
 #pragma unroll
       for (int q = 0; q < 4; ++q) eold[q] = __ldg(e + q);
@@ -425,7 +427,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     mbar_wait(acc2_full, 0);
     tc_fence_after_sync();
     if (stamp) dbg[3] = clock64();
-    if (half == 0) {
+    if (grp == 0) {
       uint32_t sk[16];
       tmem_issue16(trow + 256, sk);
       tmem_wait16(sk);
@@ -444,15 +446,15 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (a.has_res) {
       const float4* b2v = reinterpret_cast<const float4*>(b2s);
       uint32_t buf[2][16];
-      const int c0 = half * 8;
+      const int c0 = grp * L_CPG;
       tmem_issue16(trow + c0 * 16, buf[0]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < L_CPG; ++i) {
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
         if ((i & 3) == 0) mbar_wait(&xold_full[c >> 2], 0);   // x_old tiles of this 64-channel block have landed
         tmem_wait16(cur);
-        if (i + 1 < 8) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
+        if (i + 1 < L_CPG) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
         uint8_t* thi = slot(c >> 2);
         uint8_t* tlo = slot(4 + (c >> 2));
         const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);
@@ -474,9 +476,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         }
         store_split16<true>(r, thi, tlo, row, (c & 3) * 2);     // in place: same thread, same addresses
         if ((i & 3) == 3) {
-          // one 64-channel tile (hi + lo) of this column half is final: store it while the rest computes
+          // one 64-channel tile (hi + lo) of this column group is final: store it while the rest computes
           fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
           if (quarter == 0 && lane == 0) {
             const int kb = c >> 2;
             tma_store_3d(&tm_xo_hi, slot(kb), kb * 64, t0, b);
