@@ -236,11 +236,6 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     // ---------------- producer A: activation tiles (3 dilated taps of x, then the cond hidden H2)
     tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_h_hi);
-    mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL);
-    for (int kb = 0; kb < 4; ++kb) {
-      tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
-      if (NPASS == 3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
-    }
     int s = 0; uint32_t pm = 0;
     for (int kb = 0; kb < 16; ++kb) {
       for (int pl = 0; pl < PL; ++pl) {
@@ -356,8 +351,15 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     umma_commit(acc2_full);
     CWG_STAMP(8);
   } else if (warp == 3 && lane == 0) {
-    // ---------------- residual prefetch: as soon as GEMM2 is done with the acts tiles of a 64-channel
-    // block, the x_old (centre tap) tiles of that block are TMA-loaded over them (units kb / 4+kb)
+    // ---------------- folded-`end` weight tiles (kept off the activation producer: issuing them first
+    // delayed the first A tile by ~1 k cycles), then the residual prefetch: as soon as GEMM2 is done with
+    // the acts tiles of a 64-channel block, the x_old (centre tap) tiles of that block are TMA-loaded
+    // over them (units kb / 4+kb)
+    mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL);
+    for (int kb = 0; kb < 4; ++kb) {
+      tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
+      if (NPASS == 3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
+    }
     if (a.has_res) {
       tma_prefetch_desc(&tm_x_lo);
       for (int kb = 0; kb < 4; ++kb) {
