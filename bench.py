@@ -216,6 +216,75 @@ def run_waveflow(args):
     print(json.dumps(line), flush=True)
 
 
+def run_longform(args):
+    """BASELINE config 4: 12-flow / 512-channel model, one 60-s utterance (T_mel = 5168) cut into
+    halo-overlapped chunks (cookietts_b200.parallel), one chunk per rank, bf16, NCCL gather of the cores."""
+    import torch
+    import torch.distributed as dist
+    from cookietts_b200 import WaveGlow
+    from cookietts_b200.parallel import infer_long_sharded, infer_long, plan_chunks
+    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = "bf16" if args.precision == "bf16x3" and args.config == 4 else args.precision
+    Tm = 5168
+    kw = dict(MODEL_KW, WN_config=dict(MODEL_KW["WN_config"], n_channels=512))
+    model = WaveGlow(precision=precision, **kw)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic_state_dict(OracleConfig(n_channels=512), 1234).items()})
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(4000)            # same inputs on every rank
+    mel = (torch.randn(1, 80, Tm, generator=g) * 2.0 - 5.0).clamp_(-11.5129, 2.0).to(dev)
+    z = torch.randn(1, Tm * 256, generator=g).to(dev)
+    warmup = max(args.warmup, 3)
+
+    def step():
+        if world > 1:
+            return infer_long_sharded(model, mel, sigma=0.666, z=z, n_chunks=world)
+        return model.infer(mel, sigma=0.666, z=z)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        out = step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); t0.record()
+    for _ in range(args.steps):
+        out = step()
+    t1.record(); barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    per_sample_macs, _ = algorithmic_macs(C=512)
+    plan = plan_chunks(Tm, world, model.pack_config)
+    computed = sum(ch.hi - ch.lo for ch in plan)
+    value = Tm * 256 * args.steps / (ms * 1e-3)
+    peak_tf, _, peak_src = measured_peaks()
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": precision, "data": "synthetic",
+            "config": {"workload": f"WaveGlow 12-flow/512-ch inverse pass, one 60-s utterance (T_mel {Tm}) in {world} halo-overlapped chunk(s), sigma 0.666, injected z",
+                       "precision": precision, "parallelism": f"{world} chunk(s) along time, NCCL gather of the cores",
+                       "halo_recompute_factor": computed / Tm},
+            "xrt": value / SR, "algorithmic_tflops": value * per_sample_macs * 2 / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "k_gate512_tc+k_res512_tc", "achieved": value * per_sample_macs * 2 / 1e12 / world,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": value * per_sample_macs * 2 / 1e12 / world / peak_tf,
+                         "peak_source": peak_src, "traffic": None,
+                         "note": "whole-step useful algorithmic FLOP/s per GPU (halo recompute not counted)"},
+            "gpu_launches": int(model.launch_count() * args.steps), "output_finite": bool(torch.isfinite(out).all())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,7 +298,18 @@ def main():
     ap.add_argument("--channels", type=int, default=256, help="WN channels (512 = BASELINE config 4 model)")
     ap.add_argument("--workload", default="waveglow", choices=["waveglow", "waveflow"],
                     help="waveglow = BASELINE config 2 (default, the driver's line); waveflow = config 5 (B=64 x 10 s)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                    help="BASELINE.json config preset (1-based); 0 = use the individual flags (default = config 2)")
     args = ap.parse_args()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config == 1:      # 1 x 1 s (the reference's CPU-runnable case) on the GPU
+        args.batch, args.t_mel = 1, 86
+    elif args.config == 3:    # bf16 WN GEMMs, 256 x 10 s utterances sharded over the ranks (strong scaling)
+        args.precision, args.batch, args.t_mel = "bf16", 256 // world_env, 861
+    elif args.config == 4:    # 512-channel model, 60 s long-form chunked with overlap over the ranks, bf16
+        return run_longform(args)
+    elif args.config == 5:
+        args.workload = "waveflow"
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "waveflow":
@@ -363,7 +443,8 @@ def main():
     }
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.config == 3 else "weak", "vs_baseline": None,
         "dtype": {"bf16x3": "bf16x3 (hi+lo split bf16 operands, 3 MMAs, fp32 accumulate)",
                   "bf16": "bf16 (fp32 accumulate, hi+lo residual)", "ffma": "f32"}[args.precision],
         "data": "synthetic",
