@@ -206,6 +206,9 @@ class WaveGlow(nn.Module):
         mode = _cabi.MODES[self.precision]
         if speaker_id is None:
             speaker_id = speaker_ids
+        if self.multispeaker and speaker_id is None:
+            # the reference fails on a shape mismatch in cond_layers[0] here (glow.py:193-199)
+            raise ValueError("this model has speaker embeddings: pass speaker_id / speaker_ids")
         pc = self.pack_config
         if spect.dim() != 3 or spect.shape[1] != pc.n_mel:
             raise ValueError(f"spect must be [B, {pc.n_mel}, T_mel], got {tuple(spect.shape)}")

@@ -84,7 +84,7 @@ class InjectedNormal:
         assert not self.draws, "reference drew fewer tensors than expected"
 
 
-def run_reference(ref_glow, cfg: OracleConfig, sd_np, mel, z, sigma, dtype):
+def run_reference(ref_glow, cfg: OracleConfig, sd_np, mel, z, sigma, dtype, speaker_id=None):
     torch.manual_seed(0)
     model = ref_glow.WaveGlow(**reference_kwargs(cfg))
     model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd_np.items()}, strict=True)
@@ -102,7 +102,8 @@ def run_reference(ref_glow, cfg: OracleConfig, sd_np, mel, z, sigma, dtype):
     # the shim hands out a DoubleTensor so sigma*z is not rounded to fp32 on the way.
     early_type = torch.DoubleTensor if dtype == torch.float64 else torch.FloatTensor
     with torch.no_grad(), InjectedNormal(draws, early_type):
-        out = model.infer(torch.from_numpy(mel).to(dtype), sigma=sigma)
+        spk = None if speaker_id is None else torch.from_numpy(np.asarray(speaker_id)).long()
+        out = model.infer(torch.from_numpy(mel).to(dtype), speaker_id=spk, sigma=sigma)
     return out.numpy()
 
 
@@ -118,7 +119,12 @@ CASES = {
     "config1": (dict(), 1, 86, 0.666, 1234, 0),
     # 512-channel (config 4 model) on a short clip
     "c512": (dict(n_channels=512), 1, 24, 0.666, 77, 8),
+    # multispeaker: speaker embedding concatenated onto the cond input (glow.py:193-196)
+    "speaker": (dict(n_mel_channels=16, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, win_length=64,
+                     hop_length=16, n_layers=3, n_channels=32, speaker_embed_dim=12), 3, 11, 0.8, 41, 9),
+    "speaker256": (dict(n_flows=4, n_layers=4, speaker_embed_dim=32), 2, 6, 0.666, 42, 10),
 }
+SPEAKERS = {"speaker": [5, 0, 77], "speaker256": [3, 200]}
 
 
 def main():
@@ -129,14 +135,15 @@ def main():
         cfg = OracleConfig(**kw)
         sd = synthetic_state_dict(cfg, wseed)
         mel, z = synthetic_inputs(cfg, batch, t_mel, iseed)
-        out32 = run_reference(ref_glow, cfg, sd, mel, z, sigma, torch.float32)
-        out64 = run_reference(ref_glow, cfg, sd, mel.astype(np.float64), z.astype(np.float64), sigma, torch.float64)
+        spk = SPEAKERS.get(name)
+        out32 = run_reference(ref_glow, cfg, sd, mel, z, sigma, torch.float32, spk)
+        out64 = run_reference(ref_glow, cfg, sd, mel.astype(np.float64), z.astype(np.float64), sigma, torch.float64, spk)
         err = np.abs(out32 - out64).max()
         print(f"{name}: out {out32.shape} rms {np.sqrt((out64 ** 2).mean()):.3f} max {np.abs(out64).max():.3f} "
               f"ref fp32-vs-fp64 max-abs {err:.2e}")
         np.savez_compressed(os.path.join(outdir, f"{name}.npz"),
                             config=json.dumps(kw), batch=batch, t_mel=t_mel, sigma=sigma,
-                            weight_seed=wseed, input_seed=iseed,
+                            weight_seed=wseed, input_seed=iseed, speaker_id=np.asarray(spk if spk is not None else [], np.int64),
                             mel=mel, z=z, audio_ref_fp32=out32, audio_ref_fp64=out64.astype(np.float64))
 
 

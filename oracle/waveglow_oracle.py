@@ -130,13 +130,17 @@ def gate(a: np.ndarray, b: np.ndarray, n_channels: int) -> np.ndarray:
 
 
 def wn_forward(sd: Dict[str, np.ndarray], k: int, cfg: OracleConfig, audio0: np.ndarray,
-               cond: np.ndarray, dtype) -> Tuple[np.ndarray, np.ndarray]:
+               cond: np.ndarray, dtype, speaker_id=None) -> Tuple[np.ndarray, np.ndarray]:
     """`WN.forward` (glow.py:188-222) for flow k; returns (b, s)."""
     p = f"WN.{k}."
     C, L = cfg.n_channels, cfg.n_layers
     x = conv1x1(audio0, _conv_weight(sd, p + "start", dtype), np.asarray(sd[p + "start.bias"], dtype))
     output = np.zeros_like(x)                                            # :190
     spect = cond
+    if cfg.speaker_embed_dim and speaker_id is not None:                 # :193-196
+        emb = np.asarray(sd[p + "speaker_embed.weight"], dtype)[np.asarray(speaker_id)]      # [B, E]
+        emb = np.repeat(emb[:, :, None], cond.shape[2], axis=2)
+        spect = np.concatenate([spect, emb], axis=1)
     for j in range(3):                                                   # :198-199 (linear chain)
         spect = conv1x1(spect, _conv_weight(sd, p + f"cond_layers.{j}", dtype),
                         np.asarray(sd[p + f"cond_layers.{j}.bias"], dtype))
@@ -174,11 +178,9 @@ def split_z(z: np.ndarray, cfg: OracleConfig):
 
 
 def infer_with_z(sd: Dict[str, np.ndarray], cfg: OracleConfig, mel: np.ndarray, z: np.ndarray,
-                 sigma: float, dtype=np.float32) -> np.ndarray:
+                 sigma: float, dtype=np.float32, speaker_id=None) -> np.ndarray:
     """`WaveGlow.infer` (glow.py:314-350) with the latent passed in.
     mel [B, n_mel, T_mel]; z [B, T_mel*hop] standard normal; returns audio [B, T_mel*hop]."""
-    if cfg.speaker_embed_dim:
-        raise NotImplementedError("speaker embedding branch (glow.py:193-196) is not restated")
     mel = np.asarray(mel, dtype)
     z = np.asarray(z, dtype)
     sigma = dtype(sigma)
@@ -190,7 +192,7 @@ def infer_with_z(sd: Dict[str, np.ndarray], cfg: OracleConfig, mel: np.ndarray, 
     for k in reversed(range(cfg.n_flows)):                               # :328
         n_half = audio.shape[1] // 2
         a0, a1 = audio[:, :n_half], audio[:, n_half:]
-        b, s = wn_forward(sd, k, cfg, a0, cond, dtype)                   # :333
+        b, s = wn_forward(sd, k, cfg, a0, cond, dtype, speaker_id)       # :333
         a1 = (a1 - b) / np.exp(s)                                        # :337
         audio = np.concatenate([a0, a1], axis=1)
         W = np.asarray(sd[f"convinv.{k}.conv.weight"], dtype)[:, :, 0]
@@ -247,6 +249,8 @@ def synthetic_state_dict(cfg: OracleConfig, seed: int = 1234) -> Dict[str, np.nd
                 sd[p + f".alpha_i.{i}"] = (rs.uniform(size=1) * 0.02 + 0.09).astype(np.float32)
         sd[p + ".end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
         sd[p + ".end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
+        if cfg.speaker_embed_dim:       # nn.Embedding(512, E) scaled by 0.05 at init, glow.py:131-134
+            sd[p + ".speaker_embed.weight"] = (rs.standard_normal((512, cfg.speaker_embed_dim)) * 0.5).astype(np.float32)
     return sd
 
 

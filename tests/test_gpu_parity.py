@@ -51,6 +51,26 @@ def test_tensor_core_modes_match_reference(precision, name):
     assert snr_db(ref, out) >= TOL[precision]["snr"]
 
 
+@pytest.mark.parametrize("name,precision", [("speaker", "ffma"), ("speaker256", "ffma"), ("speaker256", "bf16x3")])
+def test_speaker_embedding_models(name, precision):
+    """Multispeaker checkpoints (glow.py:193-196): the embedding enters as a per-utterance cond bias;
+    both reference keywords (`speaker_id`, and `speaker_ids` as Denoiser/notebooks pass it) work."""
+    cfg, sd, g = load_golden(name)
+    model = WaveGlow(precision=precision, **module_kwargs(cfg))
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    mel, z = torch.from_numpy(g["mel"]).cuda(), torch.from_numpy(g["z"]).cuda()
+    spk = torch.from_numpy(g["speaker_id"]).cuda()
+    out = model.infer(mel, spk, sigma=float(g["sigma"]), z=z).cpu().numpy()
+    ref = g["audio_ref_fp64"]
+    assert max_abs(out, ref) <= TOL[precision]["max_abs"]
+    assert snr_db(ref, out) >= TOL[precision]["snr"]
+    out2 = model.infer(mel, speaker_ids=spk, sigma=float(g["sigma"]), z=z).cpu().numpy()
+    assert np.array_equal(out, out2)
+    with pytest.raises(ValueError):
+        model.infer(mel, sigma=1.0, z=z)
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE-size checks through size-independent properties (the CPU oracle is too slow there)
 # ---------------------------------------------------------------------------------------------

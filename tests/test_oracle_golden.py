@@ -31,6 +31,16 @@ def test_oracle_fp32_matches_reference_fp32(name):
     assert snr_db(g["audio_ref_fp64"], out) > 100.0
 
 
+@pytest.mark.parametrize("name", ["speaker", "speaker256"])
+def test_oracle_speaker_embedding_branch(name):
+    """glow.py:193-196: per-utterance speaker embedding concatenated onto the cond input."""
+    cfg, sd, g = load_golden(name)
+    out = infer_with_z(sd, cfg, g["mel"], g["z"], float(g["sigma"]), np.float64, speaker_id=g["speaker_id"])
+    assert max_abs(out, g["audio_ref_fp64"]) < 1e-9
+    other = infer_with_z(sd, cfg, g["mel"], g["z"], float(g["sigma"]), np.float64, speaker_id=(g["speaker_id"] + 1) % 512)
+    assert max_abs(other, g["audio_ref_fp64"]) > 1e-3      # the speaker id matters
+
+
 def test_reference_fp32_is_close_to_fp64():
     """Headroom of the north_star fp32 bar (1e-3 / 60 dB): the reference's own fp32 error."""
     for name in CASES:
