@@ -261,7 +261,7 @@ int launch_cond_ffma(const Dims& d, const cwg_weights* w, int flow, const float*
                      const float* cond_bias, float* h2, cudaStream_t s) {
   GemmP p{};
   p.M = d.B * d.Tm; p.N = d.P * d.H; p.K = d.KC;
-  p.W = w->cond_w_f32 + (size_t)flow * p.N * p.K; p.ldw = p.K;
+  p.W = w->cond_w_f32 + (size_t)flow * p.N * d.KCp; p.ldw = d.KCp;
   p.a0 = mel; p.Tm = d.Tm; p.nmel = d.M; p.H = d.H;
   p.o0 = h2; p.bias = cond_bias + (size_t)flow * d.H; p.bias_bstride = d.F * d.H;
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);

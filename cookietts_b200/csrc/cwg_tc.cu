@@ -25,15 +25,14 @@ namespace {
 // mel4 im2col: mel4[b*Tm + f][j*M + ci] = mel[b][ci][f - j] (0 for f < j), bf16 hi / lo planes
 // ------------------------------------------------------------------------------------------
 __global__ void k_im2col_mel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                             int B, int M, int Tm, int J) {
-  long long n = (long long)B * Tm * J * M;
+                             int B, int M, int Tm, int J, int KCp) {
+  long long n = (long long)B * Tm * KCp;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int KC = J * M;
-  long long row = i / KC; int kk = (int)(i - row * KC);
+  long long row = i / KCp; int kk = (int)(i - row * KCp);
   int b = (int)(row / Tm), f = (int)(row - (long long)b * Tm);
   int j = kk / M, ci = kk - j * M;
-  float v = f >= j ? mel[((size_t)b * M + ci) * Tm + (f - j)] : 0.f;
+  float v = (j < J && f >= j) ? mel[((size_t)b * M + ci) * Tm + (f - j)] : 0.f;   // columns >= J*M are zero padding
   __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[i] = h;
   lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -507,23 +506,23 @@ void debug_set_timing(long long* buf) { g_dbg_timing = buf; }
 int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, const float* mel,
                    const float* cond_bias, __nv_bfloat16* h2_planes, __nv_bfloat16* mel4_planes,
                    cudaStream_t s) {
-  const size_t n4 = (size_t)d.B * d.Tm * d.KC;
+  const size_t n4 = (size_t)d.B * d.Tm * d.KCp;
   __nv_bfloat16* m4_hi = mel4_planes; __nv_bfloat16* m4_lo = mel4_planes + n4;
   if (mel != nullptr) {
-    k_im2col_mel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(mel, m4_hi, m4_lo, d.B, d.M, d.Tm, d.J);
+    k_im2col_mel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(mel, m4_hi, m4_lo, d.B, d.M, d.Tm, d.J, d.KCp);
     CWG_CHECK_CUDA(cudaGetLastError());
   }
   const uint64_t rows = (uint64_t)d.B * d.Tm, ncol = (uint64_t)d.P * d.H;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo;
-  if (int r = map_2d(&ta_hi, m4_hi, d.KC, rows, 128)) return r;
-  if (int r = map_2d(&ta_lo, m4_lo, d.KC, rows, 128)) return r;
-  if (int r = map_2d(&tb_hi, w->cond_w_hi, d.KC, (uint64_t)d.F * ncol, 256)) return r;
-  if (int r = map_2d(&tb_lo, w->cond_w_lo, d.KC, (uint64_t)d.F * ncol, 256)) return r;
+  if (int r = map_2d(&ta_hi, m4_hi, d.KCp, rows, 128)) return r;
+  if (int r = map_2d(&ta_lo, m4_lo, d.KCp, rows, 128)) return r;
+  if (int r = map_2d(&tb_hi, w->cond_w_hi, d.KCp, (uint64_t)d.F * ncol, 256)) return r;
+  if (int r = map_2d(&tb_lo, w->cond_w_lo, d.KCp, (uint64_t)d.F * ncol, 256)) return r;
   if (int r = map_2d(&tc_hi, h2_planes, ncol, rows, 128)) return r;
   if (int r = map_2d(&tc_lo, h2_planes + (size_t)d.BT * d.H, ncol, rows, 128)) return r;
   CondArgs a{};
   a.bias = cond_bias + (size_t)flow * d.H; a.bias_bstride = d.F * d.H;
-  a.M = (int)rows; a.Tm = d.Tm; a.B = d.B; a.w_row0 = flow * (int)ncol; a.nkb = d.KC / 64;
+  a.M = (int)rows; a.Tm = d.Tm; a.B = d.B; a.w_row0 = flow * (int)ncol; a.nkb = d.KCp / 64;
   dim3 grid(d.P, (unsigned)((rows + 127) / 128));
   if (npass == 3) {
     if (int r = set_smem(k_cond_tc<3>, CondCfg<3>::SMEM)) return r;

@@ -130,7 +130,8 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
     w_up_p[:, :, :cfg.win_length] = w_up
     w_up5 = w_up_p.reshape(M, M, J, P, G)        # index = j*hop + p*G + g
 
-    cond_w = np.zeros((F, P * H, J * M))
+    KCp = -(-(J * M) // 64) * 64          # row pitch of cond_w: K zero-padded to a multiple of 64
+    cond_w = np.zeros((F, P * H, KCp))
     cond_b = np.zeros((F, H))
     cond_w_spk = np.zeros((F, H, max(E, 1)))
     w1 = np.zeros((F, L, 2 * C, K1))
@@ -154,7 +155,7 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
         w21 = c1 @ c0                                                # [H, M*G + E]
         w21_mel = w21[:, :M * G].reshape(H, M, G)
         a = np.einsum("hmg,cmjpg->phjc", w21_mel, w_up5, optimize=True)   # [P, H, J, M_in]
-        cond_w[k] = a.reshape(P * H, J * M)
+        cond_w[k, :, :J * M] = a.reshape(P * H, J * M)
         cond_b[k] = np.einsum("hmg,m->h", w21_mel, b_up) + c1 @ cb0 + cb1
         if E:
             cond_w_spk[k] = w21[:, M * G:]

@@ -62,7 +62,7 @@ typedef struct cwg_config {
  * N2 = C + CWG_EO_PAD.  fp32 arrays are used by CWG_MODE_FFMA, the bf16 hi/lo planes by the
  * tensor-core modes (lo = bf16(w - float(hi))); unused ones may be NULL. */
 typedef struct cwg_weights {
-  const float*    cond_w_f32;   /* [F][P*H][J*M]   row p*H+h, col j*M+ci               */
+  const float*    cond_w_f32;   /* [F][P*H][KCp]   row p*H+h, col j*M+ci; KCp = J*M rounded up to 64, zero padded */
   const uint16_t* cond_w_hi;    /* same, bf16                                          */
   const uint16_t* cond_w_lo;
   const float*    w1_f32;       /* [F][L][2C][K1]  col tap*C+c | kernel_size*C+h        */

@@ -123,6 +123,8 @@ CASES = {
     "speaker": (dict(n_mel_channels=16, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, win_length=64,
                      hop_length=16, n_layers=3, n_channels=32, speaker_embed_dim=12), 3, 11, 0.8, 41, 9),
     "speaker256": (dict(n_flows=4, n_layers=4, speaker_embed_dim=32), 2, 6, 0.666, 42, 10),
+    # 256 channels with an odd front end: n_mel*J = 80 (padded to 128 in the cond GEMM), 2 phases per frame
+    "mel20_256": (dict(n_mel_channels=20, n_flows=2, n_layers=2, win_length=64, hop_length=16), 2, 40, 0.9, 43, 11),
 }
 SPEAKERS = {"speaker": [5, 0, 77], "speaker256": [3, 200]}
 

@@ -59,7 +59,8 @@ def packed_infer(pk, cfg: PackConfig, mel, z, sigma, emulate=None, cond_bias=Non
         n_rem, n_half = fc[k]
         off = G - n_rem
         # cond GEMM: H2[b, f*P + p, h]
-        h2 = _mm(mel4.reshape(B * Tm, J * M), W("cond_w", k), emulate).reshape(B, Tm, P, H)
+        wc = tuple(None if w is None else w[:, :J * M] for w in W("cond_w", k))     # drop the zero K padding
+        h2 = _mm(mel4.reshape(B * Tm, J * M), wc, emulate).reshape(B, Tm, P, H)
         h2 = h2.reshape(B, Tp, H) + cond_bias[:, k][:, None, :]
         # start
         a0 = audio[:, :, off:off + n_half]

@@ -30,7 +30,7 @@ def run(name, precision):
     return out.cpu().numpy(), g
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "rezero", "config1", "c512"])
+@pytest.mark.parametrize("name", ["tiny", "small", "rezero", "config1", "c512", "mel20_256"])
 def test_ffma_matches_reference(name):
     out, g = run(name, "ffma")
     ref = g["audio_ref_fp64"]
@@ -40,7 +40,7 @@ def test_ffma_matches_reference(name):
     assert max_abs(out, g["audio_ref_fp32"]) <= TOL["ffma"]["max_abs"]
 
 
-@pytest.mark.parametrize("name", ["config1", "c512"])
+@pytest.mark.parametrize("name", ["config1", "c512", "mel20_256"])
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_tensor_core_modes_match_reference(precision, name):
     """config1: the fused 256-channel layer kernel; c512: the two-kernel 512-channel layer."""
