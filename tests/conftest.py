@@ -25,3 +25,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Build cookietts_b200/libcwg.so if the tree is fresh (nvcc cross-compiles without a GPU)."""
+    lib = os.path.join(ROOT, "cookietts_b200", "libcwg.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "cookietts_b200", "csrc"), "-j4"],
+                              stdout=subprocess.DEVNULL)
+    yield
