@@ -35,7 +35,8 @@ class CwgWeights(C.Structure):
 EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
            "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
            "cwg_ax_workspace_bytes", "cwg_ax_infer",
-           "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer")
+           "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer",
+           "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise")
 
 
 class CwgError(RuntimeError):
@@ -82,6 +83,16 @@ def load():
                                       C.c_int, C.c_int, C.c_void_p, C.c_float,
                                       C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_denoise_workspace_bytes.restype = C.c_size_t
+    lib.cwg_denoise_workspace_bytes.argtypes = [C.c_int] * 4
+    lib.cwg_denoise_out_samples.restype = C.c_int
+    lib.cwg_denoise_out_samples.argtypes = [C.c_int] * 3
+    lib.cwg_stft_mean_magnitude.restype = C.c_int
+    lib.cwg_stft_mean_magnitude.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.cwg_denoise.restype = C.c_int
+    lib.cwg_denoise.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     if lib.cwg_abi_version() != ABI_VERSION:
         raise CwgError(f"libcwg.so ABI {lib.cwg_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     _lib = lib

@@ -197,6 +197,26 @@ int cwg_wf_launch_count(const cwg_wf_config* cfg);
 int cwg_wf_layer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode, int flow, int layer, int row,
                  void* x_rings, const void* mel_up, float* eo, int batch, int t_samples, void* cuda_stream);
 
+/* =====================================================================================
+ * Denoiser post-filter: CookieTTS/_4_mtw/waveglow/denoiser.py:59-71 on the conv-based STFT of
+ * CookieTTS/utils/audio/stft.py:79-146 (reflect pad, windowed Fourier bases, window-sum-square synthesis).
+ *   fwd_basis   [2*cutoff][fl]   windowed forward basis (real rows then imaginary rows), cutoff = fl/2 + 1
+ *   inv_basis_t [fl][2*cutoff]   windowed inverse (pinv) basis, transposed
+ *   window_sum  [fl + hop*(NF-1)]  audio_processing.py:7-57, NF = (T + 2*(fl/2) - fl)/hop + 1
+ *   bias_spec   [n_bias][cutoff] mean magnitude of the vocoder's output for a near-silent mel; bias_index [B]
+ *               selects a row per utterance (NULL = row 0)
+ *   out         [B][cwg_denoise_out_samples(T, fl, hop)]
+ * ===================================================================================== */
+size_t cwg_denoise_workspace_bytes(int batch, int n_samples, int filter_length, int hop_length);
+int    cwg_denoise_out_samples(int n_samples, int filter_length, int hop_length);
+int    cwg_stft_mean_magnitude(const float* audio, int batch, int n_samples, int filter_length, int hop_length,
+                               const float* fwd_basis, float* mean_mag, void* workspace, size_t workspace_bytes,
+                               void* cuda_stream);
+int    cwg_denoise(const float* audio, int batch, int n_samples, int filter_length, int hop_length,
+                   const float* fwd_basis, const float* inv_basis_t, const float* window_sum,
+                   const float* bias_spec, const int32_t* bias_index, float strength,
+                   float* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
