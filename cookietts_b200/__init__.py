@@ -7,3 +7,4 @@ from .packing import PackConfig, pack_state_dict  # noqa: F401
 from .waveflow import WaveFlow  # noqa: F401
 from .waveglow_ax import WaveGlowAx  # noqa: F401
 from .denoiser import Denoiser  # noqa: F401
+from . import serving  # noqa: F401

@@ -217,6 +217,16 @@ int    cwg_denoise(const float* audio, int batch, int n_samples, int filter_leng
                    const float* bias_spec, const int32_t* bias_index, float strength,
                    float* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* =====================================================================================
+ * 16-bit PCM output: CookieTTS/_5_infer/t2s_server/text2speech.py:672-694 - per utterance, samples
+ * past n_valid[b] (= output_length*hop; NULL = all of t_stride) become silence, the rest is
+ * (audio * 2**15).astype('int16') (truncation toward zero).  out [B][out_stride]; out_stride may exceed
+ * t_stride (the `cat_silence_s` padding).  saturate = 0 reproduces numpy's wrap-around for |audio| >= 1,
+ * saturate = 1 clips instead.
+ * ===================================================================================== */
+int cwg_pcm16(const float* audio, int batch, int t_stride, const int32_t* n_valid, int16_t* out, int out_stride,
+              int saturate, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ def module_kwargs(cfg):
 def test_library_exports_every_declared_symbol():
     lib = _cabi.load()
     header = open(os.path.join(ROOT, "include", "cwg.h")).read()
-    declared = set(re.findall(r"\b(cwg_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(cwg_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_cabi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name

@@ -87,5 +87,7 @@ def test_denoiser_speaker_dependant_and_zero_strength():
     ref = denoise(st, audio, bias[ids], 0.7)
     assert max_abs(out, ref) < 5e-5
     # strength 0: the filter is the (near-perfect) STFT round trip
-    out0 = den(torch.from_numpy(audio).to(dev), strength=0.0).cpu().numpy()
+    out0 = den(torch.from_numpy(audio).to(dev), speaker_ids=ids.tolist(), strength=0.0).cpu().numpy()
+    with pytest.raises(ValueError):                                      # the reference fails to broadcast [4] - [3] too
+        den(torch.from_numpy(audio).to(dev), strength=0.0)
     assert max_abs(out0[:, 0], audio[:, :out0.shape[2]]) < 1e-4
