@@ -36,7 +36,8 @@ EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_laun
            "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
            "cwg_ax_workspace_bytes", "cwg_ax_infer",
            "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer",
-           "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise", "cwg_pcm16")
+           "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise", "cwg_pcm16",
+           "cwg_conv1d", "cwg_conv_transpose1d", "cwg_resample1d", "cwg_deemphasis")
 
 
 class CwgError(RuntimeError):
@@ -95,6 +96,17 @@ def load():
                                 C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cwg_pcm16.restype = C.c_int
     lib.cwg_pcm16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_conv1d.restype = C.c_int
+    lib.cwg_conv1d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cwg_conv_transpose1d.restype = C.c_int
+    lib.cwg_conv_transpose1d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.cwg_resample1d.restype = C.c_int
+    lib.cwg_resample1d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_int,
+                                   C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.cwg_deemphasis.restype = C.c_int
+    lib.cwg_deemphasis.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     if lib.cwg_abi_version() != ABI_VERSION:
         raise CwgError(f"libcwg.so ABI {lib.cwg_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     _lib = lib

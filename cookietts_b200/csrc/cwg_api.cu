@@ -300,7 +300,7 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
     // coupling inverse of flow k, then (mix_first) mixing of flow k or (else) mixing of flow k-1
     // after the early-z concat, then the start conv of flow k-1
     if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s,
-                                     mix_first ? k : k - 1)) return r;
+                                     mix_first ? k : k - 1, /*ignore_nan=*/1)) return r;
   }
   return 0;
 }

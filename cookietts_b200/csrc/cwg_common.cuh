@@ -65,7 +65,7 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
 // xfmt: 0 = fp32 [BT][C]; 1 = bf16 hi plane followed by lo plane (each [BT][C])
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
-                         const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2);
+                         const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2, int ignore_nan = 0);
 
 int launch_mel_up(int xfmt, const float* mel, void* out, int B, int M, int frames, int frames_padded, int Tp, int H,
                   int linear, cudaStream_t s);

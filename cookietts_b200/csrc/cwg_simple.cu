@@ -123,7 +123,7 @@ constexpr int TB = 32;   // group-steps per block in the boundary kernel
 
 struct BoundaryP {
   long long BT; int G, C;
-  int init, do_flow, do_mix, do_start;
+  int init, do_flow, do_mix, do_start, ignore_nan;
   int n_rem, n_half;          // of flow_done (coupling)
   int n_rem_mix;              // channels of the inverse 1x1 conv applied after the coupling
   int n_rem2, n_half2;        // of flow_next
@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
           float b = e[j], s = e[p.n_half + j];
           a[off + p.n_half + j] = (a[off + p.n_half + j] - b) * expf(-s);
         }
+        if (p.ignore_nan)                              // efficient_model_ax.py:12-15,331-332 (NaN -> 0 after the coupling)
+          for (int c = 0; c < p.n_rem; ++c) if (isnan(a[off + c])) a[off + c] = 0.f;
       }
       if (p.do_mix) {                                 // z = conv1d(z, W^-1), glow.py:98
         const int off = p.G - p.n_rem_mix;
@@ -301,13 +303,13 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
 
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
-                         const float* eo, void* x_out, cudaStream_t s, int mix_flow) {
+                         const float* eo, void* x_out, cudaStream_t s, int mix_flow, int ignore_nan) {
   // mix_flow: flow whose inverse 1x1 conv follows the coupling; -2 = the classic order (flow_done)
   if (mix_flow == -2) mix_flow = flow_done;
   BoundaryP p{};
   p.BT = d.BT; p.G = d.G; p.C = d.C;
   p.init = z != nullptr; p.do_flow = flow_done >= 0; p.do_start = flow_next >= 0; p.do_mix = mix_flow >= 0;
-  p.z = z; p.sigma = sigma; p.audio = audio; p.eo = eo; p.x_out = x_out;
+  p.z = z; p.sigma = sigma; p.audio = audio; p.eo = eo; p.x_out = x_out; p.ignore_nan = ignore_nan;
   if (p.do_flow) flow_channels(cfg, flow_done, &p.n_rem, &p.n_half);
   if (p.do_mix) {
     int nh;

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
+from .ax_frontend import AxFrontEndMixin
 from .packing import split_hi_lo, effective_weight, _np, EO_PAD
 
 COND_PAD = 128
@@ -42,7 +43,7 @@ class WaveFlowPackConfig:
         return self.kernel_h * self.kernel_w * self.n_channels + COND_PAD
 
 
-def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig) -> Dict[str, np.ndarray]:
+def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dict[str, np.ndarray]:
     """fp64 folding of weight-norm, the WN_2d cond layer (extra K columns on the interpolated mel)
     and `end` (into the skip half), to the arrays of `cwg_wf_weights` (include/cwg.h)."""
     F, L, Cc, kh, kw, M = cfg.n_flows, cfg.n_layers, cfg.n_channels, cfg.kernel_h, cfg.kernel_w, cfg.n_mel
@@ -54,6 +55,8 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig) -> Dict[str, np.ndarra
         p = f"WN.{k}.WN."
         w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]           # [2CL, M]
         b_c = _np(sd[p + "cond_layers.0.bias"])
+        if cond_fold is not None:                                          # n_flow_group_conv (ax_frontend.py)
+            w_c, b_c = cond_fold(k, w_c, b_c, sd)
         w_end = _np(sd[p + "end.weight"])[:, :, 0, 0]                      # [2, C]  (log_s, t)
         eo_bias = _np(sd[p + "end.bias"]).copy()
         for i in range(L):
@@ -136,7 +139,7 @@ class _Coupling(nn.Module):
         self.WN = _WN2d(**kw)
 
 
-class WaveFlow(nn.Module):
+class WaveFlow(nn.Module, AxFrontEndMixin):
     """`efficient_model_ax.WaveGlow(..., waveflow=True)` - inverse pass on B200."""
 
     def __init__(self, n_mel_channels, n_flows, n_group, n_early_every, n_early_size, memory_efficient,
@@ -152,18 +155,23 @@ class WaveFlow(nn.Module):
                  iso226_empthasis=False, precision: str = "bf16x3"):
         super().__init__()
         wn = dict(WN_config)
-        self._check_supported(locals(), wn)
+        a = dict(locals())
+        self._check_supported(a, wn)
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
         self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
         self.precision = precision
+        cond_channels = self._fe_build(a, wn)                # model-level front-end (ax_frontend.py)
+        if cond_channels > COND_PAD:
+            raise NotImplementedError(f"cookietts_b200.WaveFlow: the kernels take <= {COND_PAD} cond channels "
+                                      f"(this model feeds {cond_channels})")
         self.pack_config = WaveFlowPackConfig(
-            n_mel=n_mel_channels, n_flows=n_flows, n_group=n_group, n_layers=wn["n_layers"],
+            n_mel=cond_channels, n_flows=n_flows, n_group=n_group, n_layers=wn["n_layers"],
             n_channels=wn["n_channels"], kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
             hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear")
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
-                                           cond_in_channels=n_mel_channels) for _ in range(n_flows)])
+                                           cond_in_channels=self.wn_cond_in_channels) for _ in range(n_flows)])
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -179,13 +187,7 @@ class WaveFlow(nn.Module):
         need(a["upsample_first"] is True, "upsample_first must be True")
         need(a["n_flows"] % 2 == 0, "PermuteHeight requires an even n_flows (efficient_modules.py:370)")
         need(a["n_early_every"] >= a["n_flows"], "early outputs are not supported with waveflow (set n_early_every >= n_flows)")
-        need(not a["speaker_embed"] and not wn.get("speaker_embed_dim", 0), "speaker embeddings are not supported")
-        need(not a["cond_layers"], "model-level cond_layers must be 0")
-        need(not a["transposed_conv_scales"] and not wn.get("transposed_conv_scales"), "TransposedUpsampleNet is not supported")
-        need(not a["group_conv_output_dim"], "n_flow_group_conv is not supported")
-        need(not a["preempthasis"] and not a["preceived_vol_scaling"] and not a["iso226_empthasis"], "pre-emphasis / volume scaling / ISO-226 are not supported")
-        need(not a["use_logvar_channels"] and not a["load_hidden_from_disk"] and not a["spect_scaling"], "logvar / hidden / spect_scaling inputs are not supported")
-        need(not a["memory_efficient"], "memory_efficient is a training feature")
+        need(not wn.get("speaker_embed_dim", 0), "WN-level speaker embeddings are not supported (use the model-level speaker_embed)")
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1, "WN cond_layers must be one 1x1 conv")
         need(wn.get("cond_activation_func", "none") == "none", "WN cond activation is not supported")
         need(not wn.get("seperable_conv") and not wn.get("merge_res_skip") and wn.get("res_skip", True), "separable / merged res_skip variants are not supported")
@@ -193,7 +195,7 @@ class WaveFlow(nn.Module):
         need(wn.get("n_layers_dilations_w") is None and wn.get("n_layers_dilations_h", 1) == 1, "custom dilations are not supported")
         need(wn["n_channels"] == 128 and wn["kernel_size_h"] == 3 and wn["kernel_size_w"] == 3, "kernels are built for n_channels=128, kernel 3x3")
         need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
-        need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 16 and a["n_mel_channels"] <= COND_PAD, "n_group <= 16, n_mel <= 128")
+        need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 16, "hop_length % n_group == 0 and n_group <= 16")
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._packed = None
@@ -214,7 +216,7 @@ class WaveFlow(nn.Module):
             return
         dev = self._device()
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
-        pk = pack_waveflow_state_dict(sd, self.pack_config)
+        pk = pack_waveflow_state_dict(sd, self.pack_config, cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
         for name in WF_WEIGHT_FIELDS:
             arr = pk[name]
@@ -230,7 +232,7 @@ class WaveFlow(nn.Module):
         self._packed, self._packed_key, self._cw = dev_pk, key, w
 
     @torch.no_grad()
-    def inverse(self, z, cond, speaker_ids=None, return_CPU=True, *, _pad_frames: int = 0):
+    def inverse(self, z, cond, speaker_ids=None, return_CPU=True):
         """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
         dev = self._device()
         if dev.type != "cuda":
@@ -243,12 +245,12 @@ class WaveFlow(nn.Module):
             cond = cond + self.shift_spect
         if self.scale_spect != 1.:
             cond = cond * self.scale_spect
-        cond = cond.contiguous()
         z = z.to(device=dev, dtype=torch.float32).contiguous()
-        B, _, frames = cond.shape
         T = z.shape[1]
         with torch.cuda.device(dev):
             self._ensure_packed()
+            cond = self._fe_apply(cond.contiguous(), speaker_ids, T // self.n_group)   # speaker embedding, cond net, upsample net
+            B, _, frames = cond.shape
             nbytes = lib.cwg_wf_workspace_bytes(self._ccfg, mode, B, frames, T)
             if nbytes == 0:
                 raise _cabi.CwgError(lib.cwg_last_error().decode())
@@ -257,10 +259,11 @@ class WaveFlow(nn.Module):
                 self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
             audio = torch.empty(B, T, device=dev, dtype=torch.float32)
-            _cabi.check(lib.cwg_wf_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, _pad_frames,
+            _cabi.check(lib.cwg_wf_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
                                          z.data_ptr(), 1.0, audio.data_ptr(), ws_ptr,
                                          self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
                                          B, T, torch.cuda.current_stream(dev).cuda_stream))
+            audio = self._fe_post(audio)                     # inverse volume map / de-emphasis on the device
         return (audio.cpu() if return_CPU else audio), None
 
     @torch.no_grad()
@@ -277,7 +280,9 @@ class WaveFlow(nn.Module):
         if z is None:
             z = torch.randn(B, samples, device=dev)
         zz = z.to(dev).float() * float(sigma) if sigma > 0 else torch.zeros(B, samples, device=dev)
-        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU, _pad_frames=max(artifact_trimming, 0))
+        if artifact_trimming > 0:                            # F.pad(spect, (0, artifact_trimming), value=0.0), :370-371
+            spect = torch.nn.functional.pad(spect.to(dev).float(), (0, artifact_trimming), value=0.0)
+        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU)
         if artifact_trimming > 0:
             audio = audio[:, :-artifact_trimming * self.hop_length]
         return audio.to(in_dtype)

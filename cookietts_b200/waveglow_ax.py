@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
+from .ax_frontend import AxFrontEndMixin
 from .packing import PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
 
 
@@ -31,7 +32,7 @@ def permute_height_index(k: int, h: int):
     return idx[::-1]
 
 
-def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "lo")) -> Dict[str, np.ndarray]:
+def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "lo"), cond_fold=None) -> Dict[str, np.ndarray]:
     """Arrays of `cwg_weights` for the ax 1-D model.  `pc.cond_hidden` is the padded cond width H
     (>= n_mel); eo rows are ordered [t | log_s] so the shared boundary kernel's (b, s) convention holds
     (AffineCouplingBlock.inverse: `log_s, t = WN(...)`, efficient_modules.py:102-103)."""
@@ -45,6 +46,8 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
         p = f"WN.{k}.WN."
         w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]
         b_c = _np(sd[p + "cond_layers.0.bias"])
+        if cond_fold is not None:                            # n_flow_group_conv in front of the cond layer (ax_frontend.py)
+            w_c, b_c = cond_fold(k, w_c, b_c, sd)
         w_end = _np(sd[p + "end.weight"])[:, :, 0]
         b_end = _np(sd[p + "end.bias"])
         swap = np.r_[n_half:2 * n_half, 0:n_half]            # [t | log_s]
@@ -117,7 +120,7 @@ class _InvConv(nn.Conv1d):
         self.weight.data = w.view(c, c, 1).contiguous()
 
 
-class WaveGlowAx(nn.Module):
+class WaveGlowAx(nn.Module, AxFrontEndMixin):
     """`efficient_model_ax.WaveGlow(..., waveflow=False)` - inverse pass on B200."""
 
     def __init__(self, n_mel_channels, n_flows, n_group, n_early_every, n_early_size, memory_efficient,
@@ -145,12 +148,7 @@ class WaveGlowAx(nn.Module):
         need(self.channel_mixing is not None, "channel_mixing must be '1x1conv' or 'permuteheight'")
         need(self.channel_mixing == "1x1conv" or n_flows % 2 == 0, "PermuteHeight requires an even n_flows")
         need(upsample_first is True, "upsample_first must be True")
-        need(not speaker_embed and not wn.get("speaker_embed_dim", 0), "speaker embeddings are not supported")
-        need(not cond_layers, "model-level cond_layers must be 0")
-        need(not transposed_conv_scales and not wn.get("transposed_conv_scales"), "TransposedUpsampleNet is not supported")
-        need(not group_conv_output_dim, "n_flow_group_conv is not supported")
-        need(not preempthasis and not preceived_vol_scaling and not iso226_empthasis, "pre-emphasis / volume scaling / ISO-226 are not supported")
-        need(not use_logvar_channels and not load_hidden_from_disk and not spect_scaling and not memory_efficient, "unsupported input/training options")
+        need(not wn.get("speaker_embed_dim", 0), "WN-level speaker embeddings are not supported (use the model-level speaker_embed)")
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1 and wn.get("cond_activation_func", "none") == "none",
              "WN cond_layers must be one linear 1x1 conv")
         need(not wn.get("seperable_conv") and not wn.get("merge_res_skip") and wn.get("res_skip", True), "separable / merged res_skip variants are not supported")
@@ -162,10 +160,14 @@ class WaveGlowAx(nn.Module):
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
         self.mix_first, self.upsample_linear = bool(mix_first), wn.get("upsample_mode", "linear") == "linear"
         self.precision = precision
-        self._base = dict(n_mel=n_mel_channels, n_flows=n_flows, n_group=n_group, n_early_every=n_early_every,
+        self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
+        cond_channels = self._fe_build(a, wn)                # model-level front-end (ax_frontend.py)
+        need(precision == "ffma" or cond_channels <= 256,
+             f"the tensor-core kernels take <= 256 cond channels (this model feeds {cond_channels}); use precision='ffma'")
+        self._base = dict(n_mel=cond_channels, n_flows=n_flows, n_group=n_group, n_early_every=n_early_every,
                           n_early_size=n_early_size, win_length=hop_length, hop_length=hop_length,
                           n_layers=wn["n_layers"], n_channels=wn["n_channels"], kernel_size=ks)
-        pc = PackConfig(cond_hidden=n_mel_channels, **self._base)
+        pc = PackConfig(cond_hidden=cond_channels, **self._base)
         pc.validate()
         self.WN = nn.ModuleList()
         self.convinv = nn.ModuleList() if self.channel_mixing == "1x1conv" else []
@@ -173,7 +175,7 @@ class WaveGlowAx(nn.Module):
             if self.channel_mixing == "1x1conv":
                 self.convinv.append(_InvConv(n_rem))
             self.WN.append(_Coupling(n_in=n_half, n_layers=wn["n_layers"], n_channels=wn["n_channels"],
-                                     kernel_size=ks, cond_in_channels=n_mel_channels))
+                                     kernel_size=ks, cond_in_channels=self.wn_cond_in_channels))
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -200,7 +202,8 @@ class WaveGlowAx(nn.Module):
         # tensor-core kernels are built for a 256-wide cond operand; the fp32 path takes it unpadded
         pc = PackConfig(cond_hidden=256 if tensor else self._base["n_mel"], **self._base)
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
-        pk = pack_ax_state_dict(sd, pc, self.channel_mixing, planes=("hi", "lo") if tensor else ("f32",))
+        pk = pack_ax_state_dict(sd, pc, self.channel_mixing, planes=("hi", "lo") if tensor else ("f32",),
+                                cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
         for name, arr in pk.items():
             if arr.dtype == np.uint16:
@@ -214,7 +217,7 @@ class WaveGlowAx(nn.Module):
         self._packed, self._packed_key, self._cw = dev_pk, key, w
 
     @torch.no_grad()
-    def inverse(self, z, cond, speaker_ids=None, return_CPU=True, *, _pad_frames: int = 0):
+    def inverse(self, z, cond, speaker_ids=None, return_CPU=True):
         """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
         dev = self._device()
         if dev.type != "cuda":
@@ -234,12 +237,12 @@ class WaveGlowAx(nn.Module):
             cond = cond + self.shift_spect
         if self.scale_spect != 1.:
             cond = cond * self.scale_spect
-        cond = cond.contiguous()
         z = z.to(device=dev, dtype=torch.float32).contiguous()
-        B, _, frames = cond.shape
         T = z.shape[1]
         with torch.cuda.device(dev):
             self._ensure_packed()
+            cond = self._fe_apply(cond.contiguous(), speaker_ids, T // self.n_group)   # speaker embedding, cond net, upsample net
+            B, _, frames = cond.shape
             nbytes = lib.cwg_ax_workspace_bytes(self._ccfg, mode, B, frames, T)
             if nbytes == 0:
                 raise _cabi.CwgError(lib.cwg_last_error().decode())
@@ -248,11 +251,12 @@ class WaveGlowAx(nn.Module):
                 self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
             audio = torch.empty(B, T, device=dev, dtype=torch.float32)
-            _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, _pad_frames,
+            _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
                                          int(self.upsample_linear), int(self.mix_first), z.data_ptr(), 1.0,
                                          audio.data_ptr(), ws_ptr,
                                          self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
                                          B, T, torch.cuda.current_stream(dev).cuda_stream))
+            audio = self._fe_post(audio)                     # inverse volume map / de-emphasis on the device
         return (audio.cpu() if return_CPU else audio), None
 
     @torch.no_grad()
@@ -269,7 +273,9 @@ class WaveGlowAx(nn.Module):
         if z is None:
             z = torch.randn(B, samples, device=dev)
         zz = z.to(dev).float() * float(sigma) if sigma > 0 else torch.zeros(B, samples, device=dev)
-        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU, _pad_frames=max(artifact_trimming, 0))
+        if artifact_trimming > 0:                            # F.pad(spect, (0, artifact_trimming), value=0.0), :370-371
+            spect = torch.nn.functional.pad(spect.to(dev).float(), (0, artifact_trimming), value=0.0)
+        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU)
         if artifact_trimming > 0:
             audio = audio[:, :-artifact_trimming * self.hop_length]
         return audio.to(in_dtype)

@@ -227,6 +227,32 @@ int    cwg_denoise(const float* audio, int batch, int n_samples, int filter_leng
 int cwg_pcm16(const float* audio, int batch, int t_stride, const int32_t* n_valid, int16_t* out, int out_stride,
               int saturate, void* cuda_stream);
 
+/* =====================================================================================
+ * Conditioning front-end and output filters of the "ax" models, fp32, channels-first [B, C, T]
+ * like the reference tensors.  pad_mode: 0 zeros, 1 replicate, 2 reflect, 3 circular.  act: 0 none, 1 relu,
+ * 2 leaky relu (slope), 3 tanh, 4 sigmoid.
+ *   cwg_conv1d            y = res + out_scale * act(conv1d(x, w[c_out][c_in][k], padding) + bias); res may be NULL.
+ *                         nn.Conv1d of efficient_model_ax.py:74-113 (cond_layers, res_conv), applied at :293-307.
+ *   cwg_conv_transpose1d  y = out_scale * act(conv_transpose1d(x, stride, padding) + bias), nn.ConvTranspose1d of
+ *                         TransposedUpsampleNet (glow_ax.py:201-242).  w_phases is the torch weight [c_in][c_out][k]
+ *                         re-packed per output phase r: [stride][c_out][c_in][ceil(k/stride)], tap jj = w[ci][co][r + stride*jj].
+ *   cwg_resample1d        F.interpolate along T (mode 0 nearest, 1 linear align_corners=True, 2 linear
+ *                         align_corners=False) to t_virtual samples, of which [crop, crop + t_out) are written
+ *                         (or added when accumulate != 0); scale_factor > 0 is the value given to F.interpolate.
+ *   cwg_deemphasis        y[n] = x[n] + coef*y[n-1] per utterance in fp64 (scipy.signal.lfilter([1],[1,-coef]),
+ *                         efficient_model_ax.py:351-355), after the optional inverse volume map (:343-345).
+ * ===================================================================================== */
+int cwg_conv1d(const float* x, int batch, int c_in, int t_in, const float* w, const float* bias, int c_out, int k,
+               int padding, int pad_mode, int act, float slope, float out_scale, const float* res, float* y,
+               void* cuda_stream);
+int cwg_conv_transpose1d(const float* x, int batch, int c_in, int t_in, const float* w_phases, const float* bias,
+                         int c_out, int k, int stride, int padding, int act, float slope, float out_scale, float* y,
+                         void* cuda_stream);
+int cwg_resample1d(const float* x, int batch, int channels, int t_in, long long x_batch_stride, float* y, int t_out,
+                   long long y_batch_stride, int mode, int t_virtual, int crop, float scale_factor, int accumulate,
+                   void* cuda_stream);
+int cwg_deemphasis(const float* x, int batch, int t_samples, double coef, int vol_scaling, float* y, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,20 +128,22 @@ def coupling_inverse(sd, k, cfg, audio_out: np.ndarray, spec_all: np.ndarray, dt
     return np.stack(z, axis=1)
 
 
-def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.float32) -> np.ndarray:
+def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.float32, cond_up=None) -> np.ndarray:
     """WaveGlow.inverse(z, cond) (efficient_model_ax.py:279-357): z [B, T] (already scaled by
-    sigma), cond [B, n_mel, frames] -> audio [B, T]."""
+    sigma), cond [B, n_mel, frames] -> audio [B, T].  `cond_up` (one [B, C, T'] array, or one per flow) replaces
+    the plain interpolation when the model has a conditioning front-end (oracle/ax_frontend_oracle.py)."""
     z = np.asarray(z, dtype)
-    cond = np.asarray(cond, dtype)
     B = z.shape[0]
     zz = z.reshape(B, -1, cfg.n_group).transpose(0, 2, 1)               # :310
     Tp = zz.shape[2]
-    cond_up = upsample_cond(cond, Tp, cfg.upsample_mode)                 # :313-314
+    if cond_up is None:
+        cond_up = upsample_cond(np.asarray(cond, dtype), Tp, cfg.upsample_mode)   # :313-314
     C, L = cfg.n_channels, cfg.n_layers
     for k in reversed(range(cfg.n_flows)):                               # :325
         p = f"WN.{k}.WN.cond_layers.0"
         w_c = _w(sd, p, dtype)[:, :, 0]                                  # [2CL, n_mel]
-        spec_all = np.einsum("oc,bct->bot", w_c, cond_up, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
+        k_cond = cond_up[k] if isinstance(cond_up, (list, tuple)) else cond_up      # :328
+        spec_all = np.einsum("oc,bct->bot", w_c, k_cond, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
         zz = coupling_inverse(sd, k, cfg, zz, spec_all, dtype)           # :331
         zz = permute_height(zz, k)                                       # :336-337 (mix_first)
     return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)    # :346
@@ -165,9 +167,10 @@ def infer_with_z(sd, cfg: WaveFlowConfig, spect: np.ndarray, z: np.ndarray, sigm
     return audio
 
 
-def synthetic_state_dict(cfg: WaveFlowConfig, seed: int = 1234) -> Dict[str, np.ndarray]:
+def synthetic_state_dict(cfg: WaveFlowConfig, seed: int = 1234, cond_in_channels=None) -> Dict[str, np.ndarray]:
     """Seeded checkpoint with the reference ax/WaveFlow key layout (probe-printed: WN.{k}.WN.*,
     4-D conv weights, no convinv parameters for permuteheight); `end` non-zero."""
+    cin = cond_in_channels or cfg.n_mel_channels
     rs = np.random.RandomState(seed)
     sd: Dict[str, np.ndarray] = {}
     C, L, kh, kw = cfg.n_channels, cfg.n_layers, cfg.kernel_size_h, cfg.kernel_size_w
@@ -188,5 +191,5 @@ def synthetic_state_dict(cfg: WaveFlowConfig, seed: int = 1234) -> Dict[str, np.
         wn(p + "start", (C, 1, 1, 1), 1)
         sd[p + "end.weight"] = (rs.standard_normal((2, C, 1, 1)) * 0.02).astype(np.float32)
         sd[p + "end.bias"] = (rs.standard_normal((2,)) * 0.02).astype(np.float32)
-        wn(p + "cond_layers.0", (2 * C * L, cfg.n_mel_channels, 1), cfg.n_mel_channels)
+        wn(p + "cond_layers.0", (2 * C * L, cin, 1), cin)
     return sd

@@ -91,11 +91,14 @@ def mix_inverse(sd, k, cfg: AxConfig, z, dtype):
     return np.einsum("oc,bct->bot", W_inv, z, optimize=True)
 
 
-def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32):
-    z = np.asarray(z, dtype); cond = np.asarray(cond, dtype)
+def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32, cond_up=None, ignore_nan=True):
+    """`cond_up` (one [B, C, T'] array, or one per flow) replaces the plain interpolation when the model has a
+    conditioning front-end (oracle/ax_frontend_oracle.py)."""
+    z = np.asarray(z, dtype)
     B = z.shape[0]
     zz = z.reshape(B, -1, cfg.n_group).transpose(0, 2, 1)               # :310
-    cond_up = upsample_cond(cond, zz.shape[2], cfg.upsample_mode)        # :313-314
+    if cond_up is None:
+        cond_up = upsample_cond(np.asarray(cond, dtype), zz.shape[2], cfg.upsample_mode)   # :313-314
     n_early = sum(1 for k in range(cfg.n_flows) if k % cfg.n_early_every == 0 and k > 0)
     sizes = [cfg.n_early_size] * n_early + [cfg.n_group - cfg.n_early_size * n_early]
     parts, off = [], 0
@@ -107,8 +110,12 @@ def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32):
             zz = mix_inverse(sd, k, cfg, zz, dtype)
         n_half = zz.shape[1] // 2
         a0, a1 = zz[:, :n_half], zz[:, n_half:]
-        log_s, t = wn_forward(sd, k, cfg, a0, cond_up, dtype)            # efficient_modules.py:99-105
-        zz = np.concatenate([a0, (a1 - t) / np.exp(log_s)], axis=1)
+        k_cond = cond_up[k] if isinstance(cond_up, (list, tuple)) else cond_up      # :328
+        log_s, t = wn_forward(sd, k, cfg, a0, k_cond, dtype)             # efficient_modules.py:99-105
+        with np.errstate(all="ignore"):
+            zz = np.concatenate([a0, (a1 - t) / np.exp(log_s)], axis=1)
+        if ignore_nan:                                                   # :331-332 (masked_fill_(isnan, 0))
+            zz = np.where(np.isnan(zz), np.zeros_like(zz), zz)
         if cfg.mix_first:
             zz = mix_inverse(sd, k, cfg, zz, dtype)
         if k % cfg.n_early_every == 0 and k:
@@ -127,7 +134,7 @@ def infer_with_z(sd, cfg: AxConfig, spect, z, sigma, artifact_trimming=1, dtype=
     return audio[:, :-artifact_trimming * cfg.hop_length] if artifact_trimming > 0 else audio
 
 
-def synthetic_state_dict(cfg: AxConfig, seed: int = 1234) -> Dict[str, np.ndarray]:
+def synthetic_state_dict(cfg: AxConfig, seed: int = 1234, cond_in_channels=None) -> Dict[str, np.ndarray]:
     """Reference ax key layout for waveflow=False (probe-printed): `convinv.{k}.weight` (1x1conv mixing
     only), `WN.{k}.WN.{in_layers,res_skip_layers,start,end,cond_layers.0}` with 3-D conv weights."""
     rs = np.random.RandomState(seed)
@@ -155,5 +162,6 @@ def synthetic_state_dict(cfg: AxConfig, seed: int = 1234) -> Dict[str, np.ndarra
         wn(p + "start", (C, n_half, 1), n_half)
         sd[p + "end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
         sd[p + "end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
-        wn(p + "cond_layers.0", (2 * C * L, cfg.n_mel_channels, 1), cfg.n_mel_channels)
+        cin = cond_in_channels or cfg.n_mel_channels
+        wn(p + "cond_layers.0", (2 * C * L, cin, 1), cin)
     return sd
