@@ -67,17 +67,19 @@ class _ToneVocoder(torch.nn.Module):
     def infer(self, mel, sigma=1.0):
         B, _, Tm = mel.shape
         t = torch.arange(Tm * self.hop, device=mel.device, dtype=torch.float32)
-        return 0.5 * torch.sin(t[None] * 0.01 * (1 + torch.arange(B, device=mel.device)[:, None])) * mel.mean((1, 2))[:, None]
+        return 0.5 * torch.sin(t[None] * 0.01 * mel[:, 0, :1]) * mel[:, 1, :1] * sigma
 
 
 @pytest.mark.gpu
 def test_vocode_pcm16_slices_and_trims(tmp_path):
     hop, sr = 64, 8000
     mels = torch.ones(5, 4, 20, device="cuda")
+    mels[:, 0] = torch.arange(1, 6, device="cuda")[:, None]          # per-utterance tone
+    mels[:, 1] = torch.linspace(0.5, 1.5, 5, device="cuda")[:, None]
     lengths = [20, 3, 11, 0, 19]
     voc = _ToneVocoder(hop)
     got = serving.vocode_pcm16(voc, mels, lengths, hop, sr, vocoder_batch_size=2, cat_silence_s=0.01, sigma=0.5)
-    full = voc.infer(mels).cpu().numpy()
+    full = voc.infer(mels, sigma=0.5).cpu().numpy()
     pad = int(0.01 * sr)
     assert len(got) == 5
     for j, n in enumerate(lengths):
