@@ -172,7 +172,12 @@ long long* g_dbg_timing = nullptr;
 // Shared memory: a pool of twelve 16-KB units.
 //   GEMM1: activation (A) tiles [128 x 64] cycle through units 0..3; weight (B) tiles
 //          [256 rows x 64] = 32 KB cycle through the four unit pairs 4..11 (one N=256 MMA group each).
-//   gate : acts hi -> units 0..3, acts lo -> units 4..7 (GEMM1 is complete by then).
+//   gate : acts hi -> TENSOR MEMORY (bf16 pairs in the accumulator columns the gate has already consumed: channel
+//          chunk c of 16 at columns L_ACOL(c)), so GEMM2 reads its A operand from TMEM (".ts" MMA: the N=16
+//          folded-`end` MMAs are then no longer bound by the shared-memory A read); acts lo (bf16x3 only) ->
+//          units 4..7 (GEMM1 is complete by then).
+//   TMEM : GEMM1 accumulators in columns 0..511 (tanh half 0..255, sigmoid half 256..511); after the gate, acts hi
+//          in 0..63 and 128..191, GEMM2 res accumulator in 256..511, folded-`end` accumulator in 64..79.
 //   GEMM2: W2 res tiles [256 x 64] cycle through unit pairs (8,9) and (10,11); epilogue-2 stages
 //          x_new hi/lo in units 0..7.
 // Every tile slot has its own full/empty mbarrier pair and its own phase bit (kept in a bit mask
@@ -188,6 +193,9 @@ constexpr int L_EPI_WARPS = 8;                         // 2 per TMEM lane quarte
 constexpr int L_EPI_THREADS = 32 * L_EPI_WARPS;
 constexpr int L_THREADS = 128 + L_EPI_THREADS;         // warps 0-3: TMA-A, MMA, TMA-B, residual prefetch
 constexpr int L_CPG = 16 / (L_EPI_WARPS / 4);          // 16-channel chunks per epilogue column group
+constexpr uint32_t L_D2_RES = 256, L_D2_EO = 64;       // TMEM columns of the GEMM2 accumulators
+// TMEM column of the packed bf16 acts of 16-channel chunk c: each column group writes behind its own read pointer
+__device__ __forceinline__ uint32_t L_ACOL(int c) { return (uint32_t)((c / L_CPG) * (16 * L_CPG) + (c % L_CPG) * 8); }
 
 template <int NPASS>
 __global__ void __launch_bounds__(L_THREADS, 1)
@@ -313,38 +321,36 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     CWG_STAMP(7);
     jb = 2;
     for (int kb = 0; kb < 4; ++kb) {
-      const uint32_t a_hi = smem_u32(slot(kb)), a_lo = smem_u32(slot(4 + kb));
+      const uint32_t a_lo = smem_u32(slot(4 + kb));
       const uint32_t w_hi = smem_u32(wse(0, kb)), w_lo = smem_u32(wse(1, kb));
-      const uint32_t d16 = tmem + 256;
+      const uint32_t dres = tmem + L_D2_RES, d16 = tmem + L_D2_EO;
+      uint32_t r_hi = 0, r_lo = 0;
+      int jb_hi = 0, jb_lo = 0;
       if (a.has_res) {
-        const int jb_hi = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2;
-        int jb_lo = 0;
+        jb_hi = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2;
         if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2; }
         tc_fence_after_sync();
-        // The N=16 folded-`end` MMAs form a dependent chain on 16 columns; interleaving them with
-        // the N=256 res MMAs hides their issue-to-issue latency.
-        const uint32_t r_hi = smem_u32(bslot(jb_hi)), r_lo = smem_u32(bslot(jb_lo));
+        r_hi = smem_u32(bslot(jb_hi)); r_lo = smem_u32(bslot(jb_lo));
+      }
+      // acts hi is read from TMEM (8 columns per K step of 16), acts lo / weights from shared memory.  The N=16
+      // folded-`end` MMAs form a dependent chain on 16 columns; they are interleaved with the N=256 res MMAs.
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t o = 32 * k;
-          umma_bf16(tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(r_hi + o), IDESC_N256, (kb | k) ? 1u : 0u);
-          umma_bf16(d16, umma_desc_sw128(a_hi + o), umma_desc_sw128(w_hi + o), IDESC_N16, (kb | k) ? 1u : 0u);
-          if (NPASS == 3) {
-            umma_bf16(tmem, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), IDESC_N256, 1u);
-            umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), IDESC_N16, 1u);
-            umma_bf16(tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(r_lo + o), IDESC_N256, 1u);
-            umma_bf16(d16, umma_desc_sw128(a_hi + o), umma_desc_sw128(w_lo + o), IDESC_N16, 1u);
-          }
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u;
+        const uint32_t a_t = tmem + L_ACOL(kb * 4 + k);
+        if (a.has_res) umma_bf16_ts(dres, a_t, umma_desc_sw128(r_hi + o), IDESC_N256, acc);
+        umma_bf16_ts(d16, a_t, umma_desc_sw128(w_hi + o), IDESC_N16, acc);
+        if (NPASS == 3) {
+          if (a.has_res) umma_bf16(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), IDESC_N256, 1u);
+          umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), IDESC_N16, 1u);
+          if (a.has_res) umma_bf16_ts(dres, a_t, umma_desc_sw128(r_lo + o), IDESC_N256, 1u);
+          umma_bf16_ts(d16, a_t, umma_desc_sw128(w_lo + o), IDESC_N16, 1u);
         }
+      }
+      if (a.has_res) {
         umma_commit(&empty[4 + jb_hi]);
         if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
         umma_commit(&g2_done[kb]);
-      } else {
-        issue_kblock_fast(a_hi, w_hi, d16, IDESC_N16, kb == 0);
-        if (NPASS == 3) {
-          issue_kblock_fast(a_lo, w_hi, d16, IDESC_N16, false);
-          issue_kblock_fast(a_hi, w_lo, d16, IDESC_N16, false);
-        }
       }
     }
     umma_commit(acc2_full);
@@ -408,9 +414,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           act[4 * q + 2] = gate<NPASS>(__uint_as_float(cur[4 * q + 2]) + bt.z, __uint_as_float(cur[16 + 4 * q + 2]) + bs.z);
           act[4 * q + 3] = gate<NPASS>(__uint_as_float(cur[4 * q + 3]) + bt.w, __uint_as_float(cur[16 + 4 * q + 3]) + bs.w);
         }
-        store_split16<NPASS == 3>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        store_split16_tmem<NPASS == 3>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
       }
     }
+    tmem_wait_st();
     tc_fence_before_sync();
     fence_proxy_async_smem();
     mbar_arrive(acts_ready);
@@ -430,7 +437,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (stamp) dbg[3] = clock64();
     if (grp == 0) {
       uint32_t sk[16];
-      tmem_issue16(trow + 256, sk);
+      tmem_issue16(trow + L_D2_EO, sk);
       tmem_wait16(sk);
       if (valid) {
         float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
@@ -448,14 +455,14 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       const float4* b2v = reinterpret_cast<const float4*>(b2s);
       uint32_t buf[2][16];
       const int c0 = grp * L_CPG;
-      tmem_issue16(trow + c0 * 16, buf[0]);
+      tmem_issue16(trow + L_D2_RES + c0 * 16, buf[0]);
 #pragma unroll
       for (int i = 0; i < L_CPG; ++i) {
         const int c = c0 + i;
         uint32_t* cur = buf[i & 1];
         if ((i & 3) == 0) mbar_wait(&xold_full[c >> 2], 0);   // x_old tiles of this 64-channel block have landed
         tmem_wait16(cur);
-        if (i + 1 < L_CPG) tmem_issue16(trow + (c + 1) * 16, buf[(i + 1) & 1]);
+        if (i + 1 < L_CPG) tmem_issue16(trow + L_D2_RES + (c + 1) * 16, buf[(i + 1) & 1]);
         uint8_t* thi = slot(c >> 2);
         uint8_t* tlo = slot(4 + (c >> 2));
         const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);

@@ -110,6 +110,26 @@ __device__ __forceinline__ void store_split16(const float* v, uint8_t* tile_hi, 
   }
 }
 
+// 16 fp32 values of one row: bf16 hi packed into 8 TMEM columns (the A operand of a ".ts" MMA), lo (if any) into
+// a 128B-swizzled shared-memory tile.
+template <bool WITH_LO>
+__device__ __forceinline__ void store_split16_tmem(const float* v, uint32_t tmem_hi, uint8_t* tile_lo, int row, int chunk0) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    if (WITH_LO) {
+      float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
+      lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+    }
+  }
+  tmem_st8(tmem_hi, hi);
+  if (WITH_LO) {
+    *reinterpret_cast<uint4*>(tile_lo + sw128_offset(row, chunk0)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(tile_lo + sw128_offset(row, chunk0 + 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
 // tanh(a) * sigmoid(b), glow.py:34-41
 template <int NPASS>
 __device__ __forceinline__ float gate(float a, float b) {
