@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcwg.so")
+LIB_PATH = os.environ.get("CWG_LIB") or os.path.join(_HERE, "libcwg.so")    # CWG_LIB: A/B builds of the kernels
 
 MODE_FFMA, MODE_BF16X3, MODE_BF16 = 0, 1, 2
 MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}

@@ -194,6 +194,18 @@ constexpr int L_EPI_THREADS = 32 * L_EPI_WARPS;
 constexpr int L_THREADS = 128 + L_EPI_THREADS;         // warps 0-3: TMA-A, MMA, TMA-B, residual prefetch
 constexpr int L_CPG = 16 / (L_EPI_WARPS / 4);          // 16-channel chunks per epilogue column group
 constexpr uint32_t L_D2_RES = 256, L_D2_EO = 64;       // TMEM columns of the GEMM2 accumulators
+// The N=16 folded-`end` MMAs cost ~110 cycles each - as much as an N=256 one.  Measured NOT to be the cause: the
+// shared-memory A read (A from TMEM: GEMM2 11.9 k instead of 13.0 k cycles in bf16x3, same in bf16) and the
+// accumulate dependency on the same 16 columns (L_EO_CHAINS = 4 independent accumulators summed in the epilogue:
+// no change).  L_EO_CHAINS is kept as a build-time experiment knob.
+#ifndef CWG_EO_CHAINS
+#define CWG_EO_CHAINS 1
+#endif
+constexpr int L_EO_CHAINS = CWG_EO_CHAINS;
+#ifndef CWG_ACTS_TMEM
+#define CWG_ACTS_TMEM 1
+#endif
+constexpr bool L_ACTS_TMEM = CWG_ACTS_TMEM != 0;
 // TMEM column of the packed bf16 acts of 16-channel chunk c: each column group writes behind its own read pointer
 __device__ __forceinline__ uint32_t L_ACOL(int c) { return (uint32_t)((c / L_CPG) * (16 * L_CPG) + (c % L_CPG) * 8); }
 
@@ -320,10 +332,21 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     mbar_wait(wse_full, 0);
     CWG_STAMP(7);
     jb = 2;
+    int n_eo = 0;                                  // folded-`end` MMAs issued so far (round-robin over the chains)
+    auto mma_a_hi = [&](uint32_t d, int kb, int k, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+      if (L_ACTS_TMEM) umma_bf16_ts(d, tmem + L_ACOL(kb * 4 + k), bdesc, idesc, acc);     // A = acts hi in TMEM
+      else umma_bf16(d, umma_desc_sw128(smem_u32(slot(kb)) + 32 * k), bdesc, idesc, acc);
+    };
+    auto eo_dst = [&](uint32_t* acc) {
+      const int j = n_eo % L_EO_CHAINS;
+      *acc = n_eo >= L_EO_CHAINS ? 1u : 0u;
+      ++n_eo;
+      return tmem + L_D2_EO + 16 * j;
+    };
     for (int kb = 0; kb < 4; ++kb) {
       const uint32_t a_lo = smem_u32(slot(4 + kb));
       const uint32_t w_hi = smem_u32(wse(0, kb)), w_lo = smem_u32(wse(1, kb));
-      const uint32_t dres = tmem + L_D2_RES, d16 = tmem + L_D2_EO;
+      const uint32_t dres = tmem + L_D2_RES;
       uint32_t r_hi = 0, r_lo = 0;
       int jb_hi = 0, jb_lo = 0;
       if (a.has_res) {
@@ -332,19 +355,17 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         tc_fence_after_sync();
         r_hi = smem_u32(bslot(jb_hi)); r_lo = smem_u32(bslot(jb_lo));
       }
-      // acts hi is read from TMEM (8 columns per K step of 16), acts lo / weights from shared memory.  The N=16
-      // folded-`end` MMAs form a dependent chain on 16 columns; they are interleaved with the N=256 res MMAs.
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u;
-        const uint32_t a_t = tmem + L_ACOL(kb * 4 + k);
-        if (a.has_res) umma_bf16_ts(dres, a_t, umma_desc_sw128(r_hi + o), IDESC_N256, acc);
-        umma_bf16_ts(d16, a_t, umma_desc_sw128(w_hi + o), IDESC_N16, acc);
+        uint32_t eacc;
+        if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_hi + o), IDESC_N256, acc);
+        { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_hi + o), IDESC_N16, eacc); }
         if (NPASS == 3) {
           if (a.has_res) umma_bf16(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), IDESC_N256, 1u);
-          umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), IDESC_N16, 1u);
-          if (a.has_res) umma_bf16_ts(dres, a_t, umma_desc_sw128(r_lo + o), IDESC_N256, 1u);
-          umma_bf16_ts(d16, a_t, umma_desc_sw128(w_lo + o), IDESC_N16, 1u);
+          { const uint32_t d16 = eo_dst(&eacc); umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), IDESC_N16, eacc); }
+          if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_lo + o), IDESC_N256, 1u);
+          { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_lo + o), IDESC_N16, eacc); }
         }
       }
       if (a.has_res) {
@@ -414,10 +435,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           act[4 * q + 2] = gate<NPASS>(__uint_as_float(cur[4 * q + 2]) + bt.z, __uint_as_float(cur[16 + 4 * q + 2]) + bs.z);
           act[4 * q + 3] = gate<NPASS>(__uint_as_float(cur[4 * q + 3]) + bt.w, __uint_as_float(cur[16 + 4 * q + 3]) + bs.w);
         }
-        store_split16_tmem<NPASS == 3>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        if (L_ACTS_TMEM) store_split16_tmem<NPASS == 3>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        else store_split16<NPASS == 3>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
       }
     }
-    tmem_wait_st();
+    if (L_ACTS_TMEM) tmem_wait_st();
     tc_fence_before_sync();
     fence_proxy_async_smem();
     mbar_arrive(acts_ready);
@@ -436,18 +458,22 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     tc_fence_after_sync();
     if (stamp) dbg[3] = clock64();
     if (grp == 0) {
-      uint32_t sk[16];
-      tmem_issue16(trow + L_D2_EO, sk);
-      tmem_wait16(sk);
+      float4 v[4] = {eold[0], eold[1], eold[2], eold[3]};
+#pragma unroll
+      for (int j = 0; j < L_EO_CHAINS; ++j) {          // sum of the independent folded-`end` accumulators
+        uint32_t sk[16];
+        tmem_issue16(trow + L_D2_EO + 16 * j, sk);
+        tmem_wait16(sk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q].x += __uint_as_float(sk[4 * q]); v[q].y += __uint_as_float(sk[4 * q + 1]);
+          v[q].z += __uint_as_float(sk[4 * q + 2]); v[q].w += __uint_as_float(sk[4 * q + 3]);
+        }
+      }
       if (valid) {
         float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 v = eold[q];
-          v.x += __uint_as_float(sk[4 * q]); v.y += __uint_as_float(sk[4 * q + 1]);
-          v.z += __uint_as_float(sk[4 * q + 2]); v.w += __uint_as_float(sk[4 * q + 3]);
-          e[q] = v;
-        }
+        for (int q = 0; q < 4; ++q) e[q] = v[q];
       }
     }
     if (stamp) dbg[9] = clock64();
