@@ -210,6 +210,107 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
   }
 }
 
+// Same work for C % 8 == 0, laid out for 128-bit HBM access: one block = TBV group-steps.  Phase 1: thread ->
+// group-step (coupling, NaN flush, W^-1; the audio row is read and written as float4).  Phase 2: warp -> group-step,
+// lane -> 8 consecutive channels of the start conv, so every warp store is one contiguous 512-byte (bf16 hi, then lo)
+// or 1-KB (fp32) run of the channels-last activation row; the lane's 8 x n_half weights stay in registers.
+constexpr int TBV = 256;
+
+template <int XFMT>
+__global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
+  __shared__ __align__(16) float a_s[TBV][CWG_MAX_GROUP / 2];      // the n_half2 inputs of the next start conv
+  const long long m0 = (long long)blockIdx.x * TBV;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const long long m = m0 + tid;
+    if (m < p.BT) {
+      float a[CWG_MAX_GROUP];
+      const float* src = p.init ? p.z + m * p.G : p.audio + m * p.G;
+      if ((p.G & 3) == 0) {
+        for (int g = 0; g < p.G; g += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + g);
+          a[g] = v.x; a[g + 1] = v.y; a[g + 2] = v.z; a[g + 3] = v.w;
+        }
+      } else {
+        for (int g = 0; g < p.G; ++g) a[g] = src[g];
+      }
+      if (p.init) for (int g = 0; g < p.G; ++g) a[g] *= p.sigma;
+      if (p.do_flow) {
+        const int off = p.G - p.n_rem;
+        float e[CWG_EO_PAD];
+        const float4* ev = reinterpret_cast<const float4*>(p.eo + m * CWG_EO_PAD);
+#pragma unroll
+        for (int q = 0; q < CWG_EO_PAD / 4; ++q) { const float4 v = __ldcs(ev + q); e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w; }
+        for (int j = 0; j < p.n_rem - p.n_half; ++j)                 // audio_1 = (audio_1 - b) / exp(s), glow.py:337
+          a[off + p.n_half + j] = (a[off + p.n_half + j] - e[j]) * expf(-e[p.n_half + j]);
+        if (p.ignore_nan)
+          for (int c = 0; c < p.n_rem; ++c) if (isnan(a[off + c])) a[off + c] = 0.f;
+      }
+      if (p.do_mix) {                                                // z = conv1d(z, W^-1), glow.py:98
+        const int off = p.G - p.n_rem_mix;
+        float v[CWG_MAX_GROUP];
+        for (int c = 0; c < p.n_rem_mix; ++c) v[c] = a[off + c];
+        for (int r = 0; r < p.n_rem_mix; ++r) {
+          float acc = 0.f;
+          for (int c = 0; c < p.n_rem_mix; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
+          a[off + r] = acc;
+        }
+      }
+      if (p.init || p.do_flow || p.do_mix) {
+        float* dst = p.audio + m * p.G;
+        if ((p.G & 3) == 0) for (int g = 0; g < p.G; g += 4) *reinterpret_cast<float4*>(dst + g) = make_float4(a[g], a[g + 1], a[g + 2], a[g + 3]);
+        else for (int g = 0; g < p.G; ++g) dst[g] = a[g];
+      }
+      if (p.do_start) {
+        const int off2 = p.G - p.n_rem2;
+        for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) a_s[tid][j] = j < p.n_half2 ? a[off2 + j] : 0.f;
+      }
+    }
+  }
+  if (!p.do_start) return;
+  __syncthreads();
+  const int nrow = (int)min((long long)TBV, p.BT - m0);
+  for (int cg = lane; cg < (p.C >> 3); cg += 32) {                   // audio = start(audio_0), glow.py:189
+    const int c = cg * 8;
+    float w[8][CWG_MAX_GROUP / 2], bias[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bias[i] = __ldg(p.start_b + c + i);
+#pragma unroll
+      for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) w[i][j] = j < p.n_half2 ? __ldg(p.start_w + (c + i) * (CWG_MAX_GROUP / 2) + j) : 0.f;
+    }
+    for (int r = warp; r < nrow; r += TBV / 32) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&a_s[r][0]), a1 = *reinterpret_cast<const float4*>(&a_s[r][4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float acc = bias[i];
+#pragma unroll
+        for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) acc = fmaf(w[i][j], av[j], acc);
+        x[i] = acc;
+      }
+      const size_t idx = (size_t)(m0 + r) * p.C + c;
+      if (XFMT == 0) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.x_out) + idx);
+        o[0] = make_float4(x[0], x[1], x[2], x[3]); o[1] = make_float4(x[4], x[5], x[6], x[7]);
+      } else {
+        __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(p.x_out);
+        __nv_bfloat16* lo = hi + (size_t)p.BT * p.C;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - __low2float(hh), x[2 * i + 1] - __high2float(hh));
+          h[i] = *reinterpret_cast<const uint32_t*>(&hh); l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(hi + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + idx) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
 // mel [B][M][frames] -> cond [B][T'][H] (channels >= M are zero): zero-extended by pad frames and
 // interpolated to T' steps like F.interpolate(mode='linear', align_corners=True) / 'nearest'
 // (efficient_model_ax.py:171-182).  XFMT 0: fp32; 1: bf16 hi plane then lo plane.
@@ -321,9 +422,15 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
     p.start_w = w->start_w + (size_t)flow_next * d.C * (CWG_MAX_GROUP / 2);
     p.start_b = w->start_b + (size_t)flow_next * d.C;
   }
-  unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
-  if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
-  else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);
+  if ((d.C & 7) == 0 && ((uintptr_t)x_out & 15) == 0) {
+    unsigned grid = (unsigned)((d.BT + TBV - 1) / TBV);
+    if (xfmt == 0) k_flow_boundary_v<0><<<grid, TBV, 0, s>>>(p);
+    else           k_flow_boundary_v<1><<<grid, TBV, 0, s>>>(p);
+  } else {
+    unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
+    if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
+    else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);
+  }
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
