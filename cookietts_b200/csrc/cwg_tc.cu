@@ -53,12 +53,14 @@ template <int NPASS>
 struct CondCfg {
   static constexpr int PL = NPASS == 3 ? 2 : 1;
   static constexpr int STAGE = (TILE_A + 2 * TILE_A) * PL;     // A 16 KB + B 32 KB per plane
-  static constexpr int NST = NPASS == 3 ? 2 : 4;
+  // One (bf16x3) / two (bf16) stages of 96 / 48 KB: two CTAs are co-resident per SM (2 x 256 TMEM columns), so one
+  // CTA's loads and MMAs overlap the other's epilogue and stores (the K loop is only 5 k-blocks long).
+  static constexpr int NST = NPASS == 3 ? 1 : 2;
   static constexpr int SMEM = NST * STAGE + 256 + 1024;
 };
 
 template <int NPASS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
           const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo, CondArgs a) {
@@ -122,30 +124,35 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     const float4* bias4 = reinterpret_cast<const float4*>(a.bias + (size_t)b * a.bias_bstride);
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
-    // staging aliases the (now idle) pipeline stages: hi boxes at 0..64 KB, lo boxes at 64..128 KB
+    // staging aliases the (now idle) pipeline stage, 128 columns at a time: hi boxes at 0..32 KB, lo boxes at 32..64 KB
 #pragma unroll 1
-    for (int c = 0; c < 16; ++c) {
-      float v[16];
-      tmem_ld16_sync(trow + c * 16, v);
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+      for (int c = 8 * half; c < 8 * half + 8; ++c) {
+        float v[16];
+        tmem_ld16_sync(trow + c * 16, v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 bb = __ldg(bias4 + c * 4 + q);
-        v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        for (int q = 0; q < 4; ++q) {
+          float4 bb = __ldg(bias4 + c * 4 + q);
+          v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        }
+        uint8_t* thi = smem + ((c >> 2) & 1) * TILE_A;
+        store_split16<NPASS == 3>(v, thi, thi + 2 * TILE_A, row, (c & 3) * 2);
       }
-      uint8_t* thi = smem + (c >> 2) * TILE_A;
-      store_split16<NPASS == 3>(v, thi, thi + 4 * TILE_A, row, (c & 3) * 2);
-    }
-    tc_fence_before_sync();
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-      for (int j = 0; j < 4; ++j) {
-        tma_store_2d(&tm_c_hi, smem + j * TILE_A, p * 256 + j * 64, m0);
-        if (NPASS == 3) tma_store_2d(&tm_c_lo, smem + (4 + j) * TILE_A, p * 256 + j * 64, m0);
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        for (int j = 0; j < 2; ++j) {
+          tma_store_2d(&tm_c_hi, smem + j * TILE_A, p * 256 + (2 * half + j) * 64, m0);
+          if (NPASS == 3) tma_store_2d(&tm_c_lo, smem + (2 + j) * TILE_A, p * 256 + (2 * half + j) * 64, m0);
+        }
+        tma_store_commit();
+        tma_store_wait_read();                 // the second half reuses the staging tiles
       }
-      tma_store_commit();
-      tma_store_wait_all();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    if (warp == 2 && lane == 0) tma_store_wait_all();
   }
   __syncthreads();
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 256); }
