@@ -40,6 +40,28 @@ def build_vocoder(waveglow_config: dict, precision: str = "bf16x3"):
     return WaveGlow(precision=precision, **waveglow_config)
 
 
+def remap_checkpoint_keys(model_dict: dict, nvidia_checkpoint: bool = False) -> dict:
+    """Key renames `load_checkpoint` applies before `load_state_dict` (train.py:98-99,122): NVIDIA/waveglow
+    checkpoints into the ax layout (`.in_layers` -> `.WN.in_layers`, ..., `.conv.weight` -> `.weight`), and the
+    legacy names `invconv1x1` -> `convinv`, `.F.` -> `.WN.`, `WNs.` -> `WN.`."""
+    out = dict(model_dict)
+    if nvidia_checkpoint:
+        out = {k.replace(".in_layers", ".WN.in_layers").replace(".res_skip_layers", ".WN.res_skip_layers")
+                .replace(".start", ".WN.start").replace(".end", ".WN.end").replace(".conv.weight", ".weight"): v
+               for k, v in out.items()}
+    return {k.replace("invconv1x1", "convinv").replace(".F.", ".WN.").replace("WNs.", "WN."): v for k, v in out.items()}
+
+
+def load_checkpoint(model, checkpoint_dict: dict, nvidia_checkpoint: bool = False, strict: bool = True):
+    """`model.load_state_dict` of a reference checkpoint dict (`{'model': state_dict | nn.Module, ...}`,
+    train.py:93-99,135-143); returns the stored iteration (0 if absent)."""
+    sd = checkpoint_dict["model"]
+    if hasattr(sd, "state_dict"):                       # checkpoints that pickled the whole module (train.py:94-95)
+        sd = sd.state_dict()
+    model.load_state_dict(remap_checkpoint_keys(sd, nvidia_checkpoint), strict=strict)
+    return int(checkpoint_dict.get("iteration", 0))
+
+
 def install() -> None:
     glow = types.ModuleType("CookieTTS._4_mtw.waveglow.glow")
     glow.WaveGlow = WaveGlow

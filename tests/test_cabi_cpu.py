@@ -168,3 +168,19 @@ def test_compat_import_paths():
         "print('ok')\n") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_checkpoint_key_remap():
+    """train.py:98-99,122 key renames (NVIDIA checkpoint -> ax layout, legacy names)."""
+    from cookietts_b200.compat import remap_checkpoint_keys, load_checkpoint
+    nv = {"WN.0.in_layers.1.weight_v": 1, "WN.3.res_skip_layers.0.bias": 2, "WN.2.start.weight_g": 3, "WN.2.end.weight": 4,
+          "convinv.5.conv.weight": 5, "upsample.weight": 6}
+    out = remap_checkpoint_keys(nv, nvidia_checkpoint=True)
+    assert set(out) == {"WN.0.WN.in_layers.1.weight_v", "WN.3.WN.res_skip_layers.0.bias", "WN.2.WN.start.weight_g",
+                        "WN.2.WN.end.weight", "convinv.5.weight", "upsample.weight"}
+    legacy = remap_checkpoint_keys({"invconv1x1.0.weight": 1, "WNs.1.F.start.bias": 2})
+    assert set(legacy) == {"convinv.0.weight", "WN.1.WN.start.bias"}
+    cfg, sd, _ = load_golden("tiny")
+    model = WaveGlow(**module_kwargs(cfg))
+    it = load_checkpoint(model, {"model": {k: torch.from_numpy(v) for k, v in sd.items()}, "iteration": 7})
+    assert it == 7
