@@ -430,11 +430,11 @@ def main():
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
         "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
-        # capture committed in profiles/r1_ncu_summary.txt (same command, same shapes)
-        "traffic": {"bf16x3": 1.409e9, "bf16": 1.151e9}.get(args.precision) if (B, Tm) == (16, 861) else None,
+        # capture committed in profiles/r1c_ncu_summary.txt (same command, same shapes)
+        "traffic": {"bf16x3": 1.409e9, "bf16": 1.152e9}.get(args.precision) if (B, Tm) == (16, 861) else None,
         "traffic_unit": "bytes/launch",
         "algorithmic_bytes_per_launch": float(steps_per_launch * {"bf16x3": 3200, "bf16": 2688, "ffma": 0}[args.precision]),
-        "ncu_tensor_pipe_active_pct": {"bf16x3": 59.7, "bf16": 47.0}.get(args.precision),
+        "ncu_tensor_pipe_active_pct": {"bf16x3": 61.6, "bf16": 51.0}.get(args.precision),
         "launches_timed": int(layer_ms.size), "avg_launch_ms": float(layer_avg_ms.mean()),
         "layer_share_of_step": float(layer_avg_ms.sum() / (ms_total / args.steps)),
         "mma_passes": passes, "issued_mma_tflops": achieved * passes,
