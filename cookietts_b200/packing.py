@@ -113,6 +113,21 @@ def effective_weight(sd, prefix: str) -> np.ndarray:
     return _np(sd[prefix + ".weight"])
 
 
+def in_layer_weight_bias(sd, prefix: str):
+    """Dense (weight, bias) of one WN in_layer.  The ax models' `seperable_conv` in_layer is
+    `nn.Sequential(depthwise, pointwise)` with nothing in between (glow_ax.py:350-358, 2-D: :525-531), i.e. a dense
+    conv with W[o, c, ...] = P[o, c] * D[c, 0, ...] and bias P @ b_d + b_p: folded here (exact) so that it runs on
+    the same implicit-GEMM kernels."""
+    if (prefix + ".0.weight_g" in sd) or (prefix + ".0.weight" in sd):
+        d = effective_weight(sd, prefix + ".0")                   # [C, 1, k] or [C, 1, kh, kw]
+        pw = effective_weight(sd, prefix + ".1")                  # [2C, C, 1] or [2C, C, 1, 1]
+        pw2 = pw.reshape(pw.shape[0], pw.shape[1])
+        w = pw2.reshape(pw2.shape + (1,) * (d.ndim - 2)) * d[:, 0][None]
+        b = pw2 @ _np(sd[prefix + ".0.bias"]) + _np(sd[prefix + ".1.bias"])
+        return w, b
+    return effective_weight(sd, prefix), _np(sd[prefix + ".bias"])
+
+
 def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str, np.ndarray]:
     """Returns the arrays of `cwg_weights` (numpy, host) plus
     `cond_b_base` [F][H] and, for multispeaker models, `cond_w_spk` [F][H][E]

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import _cabi
 from .ax_frontend import AxFrontEndMixin
-from .packing import split_hi_lo, effective_weight, _np, EO_PAD
+from .packing import in_layer_weight_bias, split_hi_lo, effective_weight, _np, EO_PAD
 
 COND_PAD = 128
 
@@ -60,10 +60,10 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
         w_end = _np(sd[p + "end.weight"])[:, :, 0, 0]                      # [2, C]  (log_s, t)
         eo_bias = _np(sd[p + "end.bias"]).copy()
         for i in range(L):
-            w_in = effective_weight(sd, p + f"in_layers.{i}")              # [2C, C, kh, kw]
+            w_in, b_in = in_layer_weight_bias(sd, p + f"in_layers.{i}")    # [2C, C, kh, kw]
             w1[k, i, :, :kh * kw * Cc] = w_in.transpose(0, 2, 3, 1).reshape(2 * Cc, kh * kw * Cc)   # col (a*kw+b)*C + c
             w1[k, i, :, kh * kw * Cc:kh * kw * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
-            b1[k, i] = _np(sd[p + f"in_layers.{i}.bias"]) + b_c[2 * Cc * i:2 * Cc * (i + 1)]
+            b1[k, i] = b_in + b_c[2 * Cc * i:2 * Cc * (i + 1)]
             w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0, 0]
             b_rs = _np(sd[p + f"res_skip_layers.{i}.bias"])
             if i < L - 1:
@@ -116,15 +116,20 @@ def _bind(lib):
 class _WN2d(nn.Module):
     """Parameter holder with the layout of glow_ax.py:421-553 (supported subset)."""
 
-    def __init__(self, n_layers, n_channels, kernel_h, kernel_w, cond_in_channels):
+    def __init__(self, n_layers, n_channels, kernel_h, kernel_w, cond_in_channels, seperable_conv=False):
         super().__init__()
         wn = nn.utils.weight_norm
         self.in_layers = nn.ModuleList()
         self.res_skip_layers = nn.ModuleList()
         for i in range(n_layers):
             d = 2 ** i
-            self.in_layers.append(wn(nn.Conv2d(n_channels, 2 * n_channels, (kernel_h, kernel_w), dilation=(1, d),
-                                               padding=(0, ((kernel_w - 1) * d) // 2)), name="weight"))
+            pad = (0, ((kernel_w - 1) * d) // 2)
+            if not seperable_conv:
+                self.in_layers.append(wn(nn.Conv2d(n_channels, 2 * n_channels, (kernel_h, kernel_w), dilation=(1, d), padding=pad), name="weight"))
+            else:                                            # glow_ax.py:525-531
+                self.in_layers.append(nn.Sequential(
+                    wn(nn.Conv2d(n_channels, n_channels, (kernel_h, kernel_w), dilation=(1, d), padding=pad, groups=n_channels), name="weight"),
+                    wn(nn.Conv2d(n_channels, 2 * n_channels, (1, 1)), name="weight")))
             rs = 2 * n_channels if i < n_layers - 1 else n_channels
             self.res_skip_layers.append(wn(nn.Conv2d(n_channels, rs, (1, 1)), name="weight"))
         self.start = wn(nn.Conv2d(1, n_channels, (1, 1)), name="weight")
@@ -171,7 +176,8 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear")
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
-                                           cond_in_channels=self.wn_cond_in_channels) for _ in range(n_flows)])
+                                           cond_in_channels=self.wn_cond_in_channels,
+                                           seperable_conv=bool(wn.get("seperable_conv"))) for _ in range(n_flows)])
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -190,7 +196,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         need(not wn.get("speaker_embed_dim", 0), "WN-level speaker embeddings are not supported (use the model-level speaker_embed)")
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1, "WN cond_layers must be one 1x1 conv")
         need(wn.get("cond_activation_func", "none") == "none", "WN cond activation is not supported")
-        need(not wn.get("seperable_conv") and not wn.get("merge_res_skip") and wn.get("res_skip", True), "separable / merged res_skip variants are not supported")
+        need(not wn.get("merge_res_skip") and wn.get("res_skip", True), "merged / absent res_skip variants are not supported")
         need(wn.get("gated_unit", "GTU") == "GTU", "only the GTU gate is supported")
         need(wn.get("n_layers_dilations_w") is None and wn.get("n_layers_dilations_h", 1) == 1, "custom dilations are not supported")
         need(wn["n_channels"] == 128 and wn["kernel_size_h"] == 3 and wn["kernel_size_w"] == 3, "kernels are built for n_channels=128, kernel 3x3")

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _cabi
 from .ax_frontend import AxFrontEndMixin
-from .packing import PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
+from .packing import in_layer_weight_bias, PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
 
 
 def permute_height_index(k: int, h: int):
@@ -53,10 +53,10 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
         swap = np.r_[n_half:2 * n_half, 0:n_half]            # [t | log_s]
         w_end, eo_bias = w_end[swap], b_end[swap].copy()
         for i in range(L):
-            w_in = effective_weight(sd, p + f"in_layers.{i}")
+            w_in, b_in = in_layer_weight_bias(sd, p + f"in_layers.{i}")
             w1[k, i, :, :ks * Cc] = w_in.transpose(0, 2, 1).reshape(2 * Cc, ks * Cc)
             w1[k, i, :, ks * Cc:ks * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
-            b1[k, i] = _np(sd[p + f"in_layers.{i}.bias"]) + b_c[2 * Cc * i:2 * Cc * (i + 1)]
+            b1[k, i] = b_in + b_c[2 * Cc * i:2 * Cc * (i + 1)]
             w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0]
             b_rs = _np(sd[p + f"res_skip_layers.{i}.bias"])
             if i < L - 1:
@@ -87,15 +87,20 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
 class _WN1d(nn.Module):
     """Parameter holder with the layout of glow_ax.py:245-373 (supported subset)."""
 
-    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels):
+    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels, seperable_conv=False):
         super().__init__()
         wn = nn.utils.weight_norm
         self.in_layers = nn.ModuleList()
         self.res_skip_layers = nn.ModuleList()
         for i in range(n_layers):
             d = 2 ** i
-            self.in_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels, kernel_size, dilation=d,
-                                               padding=(kernel_size * d - d) // 2), name="weight"))
+            pad = (kernel_size * d - d) // 2
+            if not seperable_conv or kernel_size == 1:
+                self.in_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels, kernel_size, dilation=d, padding=pad), name="weight"))
+            else:                                            # glow_ax.py:350-358
+                self.in_layers.append(nn.Sequential(
+                    wn(nn.Conv1d(n_channels, n_channels, kernel_size, dilation=d, padding=pad, groups=n_channels), name="weight"),
+                    wn(nn.Conv1d(n_channels, 2 * n_channels, 1), name="weight")))
             self.res_skip_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels if i < n_layers - 1 else n_channels, 1), name="weight"))
         self.start = wn(nn.Conv1d(n_in, n_channels, 1), name="weight")
         self.end = nn.Conv1d(n_channels, 2 * n_in, 1)
@@ -151,7 +156,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         need(not wn.get("speaker_embed_dim", 0), "WN-level speaker embeddings are not supported (use the model-level speaker_embed)")
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1 and wn.get("cond_activation_func", "none") == "none",
              "WN cond_layers must be one linear 1x1 conv")
-        need(not wn.get("seperable_conv") and not wn.get("merge_res_skip") and wn.get("res_skip", True), "separable / merged res_skip variants are not supported")
+        need(not wn.get("merge_res_skip") and wn.get("res_skip", True), "merged / absent res_skip variants are not supported")
         need(wn.get("gated_unit", "GTU") == "GTU" and wn.get("n_layers_dilations_w") is None, "only the GTU gate with 2^i dilations is supported")
         need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
         ks = wn.get("kernel_size_w") or wn.get("kernel_size")
@@ -175,7 +180,8 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             if self.channel_mixing == "1x1conv":
                 self.convinv.append(_InvConv(n_rem))
             self.WN.append(_Coupling(n_in=n_half, n_layers=wn["n_layers"], n_channels=wn["n_channels"],
-                                     kernel_size=ks, cond_in_channels=self.wn_cond_in_channels))
+                                     kernel_size=ks, cond_in_channels=self.wn_cond_in_channels,
+                                     seperable_conv=bool(wn.get("seperable_conv"))))
         self._packed = None
         self._packed_key = None
         self._workspace = None

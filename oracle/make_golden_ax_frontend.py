@@ -64,6 +64,10 @@ CASES = {
                                          transposed_conv_hidden_dim=32, transposed_conv_kernel_size=[4, 8],
                                          transposed_conv_scales=[2, 8], transposed_conv_output_dim=64, preempthasis=0.9),
                       2, 4, 0.666, 46, 6),
+    # seperable_conv=True: in_layers are Sequential(depthwise, pointwise) (what the author's checkpoints use)
+    "axfe_separable": ("ax", dict(SMALL, seperable_conv=True), dict(speaker_embed=3), 2, 6, 0.8, 47, 7),
+    "axfe_separable_256": ("ax", dict(seperable_conv=True), dict(), 1, 5, 0.666, 48, 8),
+    "axfe_waveflow_separable": ("wf", dict(seperable_conv=True), dict(speaker_embed=8), 1, 4, 0.666, 49, 9),
 }
 
 

@@ -48,7 +48,7 @@ def reference_kwargs(cfg: WaveFlowConfig) -> dict:
     wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size_w=cfg.kernel_size_w,
               kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=None, n_layers_dilations_h=1,
               speaker_embed_dim=0, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
-              cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=False,
+              cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv,
               res_skip=True, merge_res_skip=False, upsample_mode=cfg.upsample_mode)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_flows * 2, n_early_size=2, memory_efficient=0.0, spect_scaling=False,
@@ -75,7 +75,7 @@ def reference_kwargs_ax1d(cfg) -> dict:
     wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, kernel_size_w=None,
               n_layers_dilations_w=None, n_layers_dilations_h=1, speaker_embed_dim=0, rezero=False, cond_layers=1,
               cond_activation_func="none", negative_slope=None, cond_hidden_channels=256, cond_kernel_size=1,
-              cond_padding_mode="zeros", seperable_conv=False, res_skip=True, merge_res_skip=False,
+              cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv, res_skip=True, merge_res_skip=False,
               upsample_mode=cfg.upsample_mode)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size, memory_efficient=0.0,

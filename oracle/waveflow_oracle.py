@@ -39,6 +39,7 @@ class WaveFlowConfig:
     win_length: int = 1024
     hop_length: int = 256
     upsample_mode: str = "linear"   # WN_config['upsample_mode'] used by the model-level interpolate
+    seperable_conv: bool = False    # in_layer = Sequential(depthwise, pointwise), glow_ax.py:525-531
 
 
 def _w(sd, prefix, dtype):
@@ -94,15 +95,25 @@ def wn2d_step(sd, k, cfg: WaveFlowConfig, row: np.ndarray, spec_all: np.ndarray,
             queues[i] = np.zeros((B, C, kh - 1, T), dtype)
         stack = np.concatenate([queues[i], audio[:, :, None, :]], axis=2)   # [B, C, kh, T']  :602
         queues[i] = stack[:, :, 1:]
-        w_in = _w(sd, p + f"in_layers.{i}", dtype)                       # [2C, C, kh, kw]
+        sep = (p + f"in_layers.{i}.0.weight_v") in sd
+        w_in = _w(sd, p + (f"in_layers.{i}.0" if sep else f"in_layers.{i}"), dtype)   # [2C, C, kh, kw] / depthwise [C, 1, kh, kw]
         pad = ((kw - 1) * d) // 2
         sp = np.zeros((B, C, kh, T + 2 * pad), dtype)
         sp[:, :, :, pad:pad + T] = stack
-        acts = np.zeros((B, 2 * C, T), dtype)
-        for a in range(kh):
-            for b in range(kw):
-                acts += np.einsum("oc,bct->bot", w_in[:, :, a, b], sp[:, :, a, b * d:b * d + T], optimize=True)
-        acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None]
+        if sep:                                                          # depthwise, then pointwise (no activation between)
+            dw = np.zeros((B, C, T), dtype)
+            for a in range(kh):
+                for b in range(kw):
+                    dw += w_in[None, :, 0, a, b, None] * sp[:, :, a, b * d:b * d + T]
+            dw += np.asarray(sd[p + f"in_layers.{i}.0.bias"], dtype)[None, :, None]
+            acts = np.einsum("oc,bct->bot", _w(sd, p + f"in_layers.{i}.1", dtype)[:, :, 0, 0], dw, optimize=True) \
+                + np.asarray(sd[p + f"in_layers.{i}.1.bias"], dtype)[None, :, None]
+        else:
+            acts = np.zeros((B, 2 * C, T), dtype)
+            for a in range(kh):
+                for b in range(kw):
+                    acts += np.einsum("oc,bct->bot", w_in[:, :, a, b], sp[:, :, a, b * d:b * d + T], optimize=True)
+            acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None]
         acts += spec_all[:, 2 * C * i:2 * C * (i + 1)]                   # :585-608 (GTU: add, tanh*sigmoid)
         g = np.tanh(acts[:, :C]) * (1.0 / (1.0 + np.exp(-acts[:, C:])))
         w_rs = _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0, 0]
@@ -186,7 +197,11 @@ def synthetic_state_dict(cfg: WaveFlowConfig, seed: int = 1234, cond_in_channels
     for k in range(cfg.n_flows):
         p = f"WN.{k}.WN."
         for i in range(L):
-            wn(p + f"in_layers.{i}", (2 * C, C, kh, kw), C * kh * kw)
+            if cfg.seperable_conv:
+                wn(p + f"in_layers.{i}.0", (C, 1, kh, kw), kh * kw)
+                wn(p + f"in_layers.{i}.1", (2 * C, C, 1, 1), C)
+            else:
+                wn(p + f"in_layers.{i}", (2 * C, C, kh, kw), C * kh * kw)
             wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1, 1), C)
         wn(p + "start", (C, 1, 1, 1), 1)
         sd[p + "end.weight"] = (rs.standard_normal((2, C, 1, 1)) * 0.02).astype(np.float32)

@@ -38,6 +38,7 @@ class AxConfig:
     upsample_mode: str = "linear"
     channel_mixing: str = "1x1conv"      # or "permuteheight"
     mix_first: bool = True
+    seperable_conv: bool = False         # in_layer = Sequential(depthwise, pointwise), glow_ax.py:350-358
 
     def flow_channels(self) -> List[int]:
         out, n_rem = [], self.n_group
@@ -60,14 +61,24 @@ def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype):
     output = None
     for i in range(L):
         d = 2 ** i
-        w_in = _w(sd, p + f"in_layers.{i}", dtype)
+        sep = (p + f"in_layers.{i}.0.weight_v") in sd
+        w_in = _w(sd, p + (f"in_layers.{i}.0" if sep else f"in_layers.{i}"), dtype)
         ks = w_in.shape[2]
         pad = (ks * d - d) // 2
         xp = np.zeros((B, C, T + 2 * pad), dtype); xp[:, :, pad:pad + T] = audio
-        acts = np.zeros((B, 2 * C, T), dtype)
-        for j in range(ks):
-            acts += np.einsum("oc,bct->bot", w_in[:, :, j], xp[:, :, j * d:j * d + T], optimize=True)
-        acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None] + spect[:, 2 * C * i:2 * C * (i + 1)]
+        if sep:                                                          # depthwise, then pointwise (no activation between)
+            dw = np.zeros((B, C, T), dtype)
+            for j in range(ks):
+                dw += w_in[None, :, 0, j, None] * xp[:, :, j * d:j * d + T]
+            dw += np.asarray(sd[p + f"in_layers.{i}.0.bias"], dtype)[None, :, None]
+            acts = np.einsum("oc,bct->bot", _w(sd, p + f"in_layers.{i}.1", dtype)[:, :, 0], dw, optimize=True) \
+                + np.asarray(sd[p + f"in_layers.{i}.1.bias"], dtype)[None, :, None]
+        else:
+            acts = np.zeros((B, 2 * C, T), dtype)
+            for j in range(ks):
+                acts += np.einsum("oc,bct->bot", w_in[:, :, j], xp[:, :, j * d:j * d + T], optimize=True)
+            acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None]
+        acts += spect[:, 2 * C * i:2 * C * (i + 1)]
         g = np.tanh(acts[:, :C]) * (1.0 / (1.0 + np.exp(-acts[:, C:])))
         rs = np.einsum("oc,bct->bot", _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0], g, optimize=True) \
             + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
@@ -157,7 +168,11 @@ def synthetic_state_dict(cfg: AxConfig, seed: int = 1234, cond_in_channels=None)
             sd[f"convinv.{k}.weight"] = (q1 @ np.diag(rs.uniform(0.7, 1.4, size=n_rem)) @ q2).astype(np.float32)[:, :, None]
         p = f"WN.{k}.WN."
         for i in range(L):
-            wn(p + f"in_layers.{i}", (2 * C, C, ks), C * ks)
+            if cfg.seperable_conv and ks > 1:
+                wn(p + f"in_layers.{i}.0", (C, 1, ks), ks)
+                wn(p + f"in_layers.{i}.1", (2 * C, C, 1), C)
+            else:
+                wn(p + f"in_layers.{i}", (2 * C, C, ks), C * ks)
             wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1), C)
         wn(p + "start", (C, n_half, 1), n_half)
         sd[p + "end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)

@@ -9,7 +9,8 @@ from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict as wf_sd
 from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd, inverse as ax_inverse
 from tests.helpers import GOLDEN_DIR
 
-CASES = ["axfe_speaker_cond", "axfe_tconv_crop", "axfe_tconv_interp_group", "axfe_post", "axfe_256", "axfe_waveflow"]
+CASES = ["axfe_speaker_cond", "axfe_tconv_crop", "axfe_tconv_interp_group", "axfe_post", "axfe_256", "axfe_waveflow",
+         "axfe_separable", "axfe_separable_256", "axfe_waveflow_separable"]
 
 
 def load_case(name):
@@ -46,7 +47,7 @@ def module_kwargs(kind, cfg, fe):
         wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, kernel_size_w=None,
                   n_layers_dilations_w=None, n_layers_dilations_h=1, speaker_embed_dim=0, rezero=False, cond_layers=1,
                   cond_activation_func="none", negative_slope=None, cond_hidden_channels=256, cond_kernel_size=1,
-                  cond_padding_mode="zeros", seperable_conv=False, res_skip=True, merge_res_skip=False,
+                  cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv, res_skip=True, merge_res_skip=False,
                   upsample_mode=cfg.upsample_mode)
         kw = dict(n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size, channel_mixing=cfg.channel_mixing,
                   mix_first=cfg.mix_first, waveflow=False)
@@ -54,7 +55,7 @@ def module_kwargs(kind, cfg, fe):
         wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size_w=cfg.kernel_size_w,
                   kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=None, n_layers_dilations_h=1,
                   speaker_embed_dim=0, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
-                  cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=False,
+                  cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv,
                   res_skip=True, merge_res_skip=False, upsample_mode=cfg.upsample_mode)
         kw = dict(n_early_every=cfg.n_flows * 2, n_early_size=2, channel_mixing="permuteheight", mix_first=True, waveflow=True)
     kw.update(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group, memory_efficient=0.0,

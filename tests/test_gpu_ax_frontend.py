@@ -34,14 +34,15 @@ def check(out, ref, precision):
     assert snr_db(ref, out) >= TOL[precision]["snr"]
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if c != "axfe_waveflow"])
+@pytest.mark.parametrize("name", [c for c in CASES if "waveflow" not in c])
 def test_frontend_fp32_cuda_cores(name):
     out, ref = run(name, "ffma")
     check(out, ref, "ffma")
 
 
 @pytest.mark.parametrize("name,precision", [("axfe_256", "bf16x3"), ("axfe_256", "bf16"),
-                                            ("axfe_waveflow", "bf16x3"), ("axfe_waveflow", "bf16")])
+                                            ("axfe_waveflow", "bf16x3"), ("axfe_waveflow", "bf16"),
+                                            ("axfe_separable_256", "bf16x3"), ("axfe_waveflow_separable", "bf16x3")])
 def test_frontend_tensor_cores(name, precision):
     out, ref = run(name, precision)
     check(out, ref, precision)
