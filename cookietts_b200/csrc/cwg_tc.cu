@@ -315,21 +315,26 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
       if (kb == 0) CWG_STAMP(5);
       for (int g = 0; g < 2; ++g) {
+        // Slots are waited for right before their first use and released right after their last one: with a B ring
+        // of one k-block (bf16x3) a weight slot must be refilled (~2 k cycles from free to full) inside the ~3 k
+        // cycles of MMA work of a k-block.
         const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
-        int jb_lo = 0;
-        if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
         tc_fence_after_sync();
         const uint32_t d = tmem + g * 256;
         issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), d, IDESC_N256, kb == 0);
         if (NPASS == 3) {
           issue_kblock_fast(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), d, IDESC_N256, false);
+          umma_commit(&empty[4 + jb_hi]);
+          if (g == 1) umma_commit(&empty[sa_lo]);
+          const int jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+          tc_fence_after_sync();
           issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), d, IDESC_N256, false);
+          umma_commit(&empty[4 + jb_lo]);
+        } else {
+          umma_commit(&empty[4 + jb_hi]);
         }
-        umma_commit(&empty[4 + jb_hi]);
-        if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
       }
       umma_commit(&empty[sa_hi]);
-      if (NPASS == 3) umma_commit(&empty[sa_lo]);
     }
     umma_commit(acc1_full);
     CWG_STAMP(6);
