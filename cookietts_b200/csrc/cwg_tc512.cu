@@ -107,22 +107,24 @@ k_gate512_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
       const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
       int sa_lo = 0;
       if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < 2; ++g) {      // slots are waited for just before first use, released right after last use
         const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
-        int jb_lo = 0;
-        if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
         tc_fence_after_sync();
         const uint32_t d = tmem + g * 256;
         issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), d, IDESC_N256, kb == 0);
         if (NPASS == 3) {
           issue_kblock_fast(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), d, IDESC_N256, false);
+          umma_commit(&empty[4 + jb_hi]);
+          if (g == 1) umma_commit(&empty[sa_lo]);
+          const int jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+          tc_fence_after_sync();
           issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), d, IDESC_N256, false);
+          umma_commit(&empty[4 + jb_lo]);
+        } else {
+          umma_commit(&empty[4 + jb_hi]);
         }
-        umma_commit(&empty[4 + jb_hi]);
-        if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
       }
       umma_commit(&empty[sa_hi]);
-      if (NPASS == 3) umma_commit(&empty[sa_lo]);
     }
     umma_commit(acc1_full);
   } else if (warp >= 4) {

@@ -235,19 +235,21 @@ k_wf_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant
       const int sa_hi = sa; wait_full(sa); sa ^= 1;
       int sa_lo = 0;
       if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa ^= 1; }
-      const int jb_hi = jb; wait_full(W_NA + jb); jb ^= 1;
-      int jb_lo = 0;
-      if (NPASS == 3) { jb_lo = jb; wait_full(W_NA + jb); jb ^= 1; }
+      const int jb_hi = jb; wait_full(W_NA + jb); jb ^= 1;     // slots: waited for just before first use, released after last use
       tc_fence_after_sync();
       issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), tmem, IDESC_N256, kb == 0);
       if (NPASS == 3) {
         issue_kblock_fast(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), tmem, IDESC_N256, false);
+        umma_commit(&empty[W_NA + jb_hi]);
+        umma_commit(&empty[sa_lo]);
+        const int jb_lo = jb; wait_full(W_NA + jb); jb ^= 1;
+        tc_fence_after_sync();
         issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), tmem, IDESC_N256, false);
+        umma_commit(&empty[W_NA + jb_lo]);
+      } else {
+        umma_commit(&empty[W_NA + jb_hi]);
       }
-      umma_commit(&empty[W_NA + jb_hi]);
-      if (NPASS == 3) umma_commit(&empty[W_NA + jb_lo]);
       umma_commit(&empty[sa_hi]);
-      if (NPASS == 3) umma_commit(&empty[sa_lo]);
     }
     umma_commit(acc1_full);
     // GEMM2: [res (128) | folded end (16)] = acts x W2^T, reusing TMEM columns 0..143
