@@ -11,11 +11,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CWG_LIB") or os.path.join(_HERE, "libcwg.so")    # CWG_LIB: A/B builds of the kernels
 
-MODE_FFMA, MODE_BF16X3, MODE_BF16 = 0, 1, 2
-MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+MODE_FFMA, MODE_BF16X3, MODE_BF16, MODE_F16F8 = 0, 1, 2, 3
+MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "f16f8": MODE_F16F8}
 EO_PAD = 16
 MAX_GROUP = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CwgConfig(C.Structure):
@@ -25,7 +25,7 @@ class CwgConfig(C.Structure):
 
 
 WEIGHT_FIELDS = ("cond_w_f32", "cond_w_hi", "cond_w_lo", "w1_f32", "w1_hi", "w1_lo", "b1",
-                 "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv")
+                 "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv", "w1_h8", "w1_l8")
 
 
 class CwgWeights(C.Structure):

@@ -44,7 +44,10 @@ int check_config(const cwg_config* c) {
 }
 
 int check_mode(const cwg_config* c, int mode, bool cond_gemm = true) {
-  CWG_REQUIRE(mode == CWG_MODE_FFMA || mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16, "unknown mode %d", mode);
+  CWG_REQUIRE(mode == CWG_MODE_FFMA || mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16 || mode == CWG_MODE_F16F8,
+              "unknown mode %d", mode);
+  if (mode == CWG_MODE_F16F8)
+    CWG_REQUIRE(c->n_channels == 256 && cond_gemm, "CWG_MODE_F16F8 is built for the 256-channel classic model");
   if (mode != CWG_MODE_FFMA) {
     CWG_REQUIRE((c->n_channels == 256 || c->n_channels == 512) && c->cond_hidden == 256 && c->kernel_size == 3,
                 "tensor-core modes are built for n_channels in {256, 512}, cond_hidden=256, kernel_size=3 "
@@ -66,8 +69,9 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
     ws->pre = (float*)take((size_t)d.BT * 2 * d.C * 4);
     ws->acts = (float*)take((size_t)d.BT * d.C * 4);
   } else {
-    ws->xb[0] = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
-    ws->xb[1] = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);
+    const size_t xe = mode == CWG_MODE_F16F8 ? 6 : 4;       // bytes per element of the x planes (see cwg.h)
+    ws->xb[0] = (__nv_bfloat16*)take((size_t)d.BT * d.C * xe);
+    ws->xb[1] = (__nv_bfloat16*)take((size_t)d.BT * d.C * xe);
     ws->h2b = (__nv_bfloat16*)take((size_t)d.BT * d.H * 2 * 2);
     ws->mel4 = (__nv_bfloat16*)take((size_t)d.B * d.Tm * d.KCp * 2 * 2);
     if (d.C == 512) ws->actsb = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);   // gated activations (two-kernel layer)
@@ -90,6 +94,9 @@ int check_run(const cwg_config* cfg, const cwg_weights* w, int mode, int batch, 
               "batch * T' too large for one call; split the batch");
   CWG_REQUIRE(w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b && w->winv, "missing weight arrays");
   if (mode == CWG_MODE_FFMA) CWG_REQUIRE(w->cond_w_f32 && w->w1_f32 && w->w2_f32, "fp32 weight planes missing");
+  else if (mode == CWG_MODE_F16F8)
+    CWG_REQUIRE(w->cond_w_hi && w->cond_w_lo && w->w1_hi && w->w1_h8 && w->w1_l8 && w->w2_hi && w->w2_lo,
+                "fp16 / e5m2 weight planes missing");
   else CWG_REQUIRE(w->cond_w_hi && w->w1_hi && w->w2_hi && w->cond_w_lo && w->w1_lo && w->w2_lo,
                    "bf16 hi/lo weight planes missing");
   return 0;
@@ -138,7 +145,7 @@ int cwg_cond(const cwg_config* cfg, const cwg_weights* w, int mode, int flow,
   CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
   carve(d, mode, workspace, &ws);
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
-  return launch_cond_tc(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, mel, cond_bias,
+  return launch_cond_tc(d, w, mode_npass(mode), flow, mel, cond_bias,
                         (__nv_bfloat16*)h2_out, ws.mel4, s);
 }
 
@@ -162,10 +169,10 @@ int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow
     CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
     carve(d, mode, workspace, &ws);
     CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
-    return launch_layer_tc512(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, layer, (const __nv_bfloat16*)x_in,
+    return launch_layer_tc512(d, w, mode_npass(mode), flow, layer, (const __nv_bfloat16*)x_in,
                               (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, ws.actsb, eo, s);
   }
-  return launch_layer_tc(d, w, mode == CWG_MODE_BF16X3 ? 3 : 1, flow, layer, (const __nv_bfloat16*)x_in,
+  return launch_layer_tc(d, w, mode_npass(mode), flow, layer, (const __nv_bfloat16*)x_in,
                          (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, eo, s);
 }
 
@@ -176,7 +183,7 @@ int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,
   if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
   CWG_REQUIRE(flow_done < cfg->n_flows && flow_next < cfg->n_flows, "flow out of range");
   Dims d = make_dims(cfg, batch, t_mel);
-  return launch_flow_boundary(cfg, d, w, mode == CWG_MODE_FFMA ? 0 : 1, flow_done, flow_next, z, sigma,
+  return launch_flow_boundary(cfg, d, w, mode_xfmt(mode), flow_done, flow_next, z, sigma,
                               audio, eo, x_out, (cudaStream_t)cuda_stream);
 }
 
@@ -203,8 +210,8 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool tc = mode != CWG_MODE_FFMA;
-  const int npass = mode == CWG_MODE_BF16X3 ? 3 : 1;
-  const int xfmt = tc ? 1 : 0;
+  const int npass = mode_npass(mode);
+  const int xfmt = mode_xfmt(mode);
   const int F = cfg->n_flows, L = cfg->n_layers;
 
   // audio = sigma * z (glow.py:326; early z already sits in its final columns), x = start_{F-1}(audio_0)

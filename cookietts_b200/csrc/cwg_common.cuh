@@ -57,12 +57,20 @@ void set_error(const char* fmt, ...);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// CWG_MODE_F16F8 scaling of the e5m2 correction operands (cookietts_b200/packing.py F8_P, F8_Q)
+constexpr float F8_LO_SCALE = 64.f;            // 2^P applied to activation lo parts (weights hi carry 2^-P)
+constexpr float F8_HI_SCALE = 1.f / 256.f;     // 2^-Q applied to activation hi parts (weights lo carry 2^Q)
+// npass argument of the tensor-core launchers: 1 = bf16, 3 = bf16x3, 2 = f16f8
+inline int mode_npass(int mode) { return mode == CWG_MODE_BF16X3 ? 3 : (mode == CWG_MODE_F16F8 ? 2 : 1); }
+inline int mode_xfmt(int mode) { return mode == CWG_MODE_FFMA ? 0 : (mode == CWG_MODE_F16F8 ? 2 : 1); }
+
 // ---- launchers implemented in cwg_simple.cu (CUDA-core fp32 path + shared boundary kernels) ----
 int launch_cond_ffma(const Dims& d, const cwg_weights* w, int flow, const float* mel,
                      const float* cond_bias, float* h2, cudaStream_t s);
 int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, const float* x_in,
                       float* x_out, const float* h2, float* eo, float* pre, float* acts, cudaStream_t s);
-// xfmt: 0 = fp32 [BT][C]; 1 = bf16 hi plane followed by lo plane (each [BT][C])
+// xfmt: 0 = fp32 [BT][C]; 1 = bf16 hi plane followed by lo plane (each [BT][C]); 2 = CWG_MODE_F16F8 planes
+// (fp16 hi, fp16 lo, e5m2(lo * 2^F8_P), e5m2(hi * 2^-F8_Q))
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
                          const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2, int ignore_nan = 0);

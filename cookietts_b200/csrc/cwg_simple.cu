@@ -8,6 +8,8 @@
 //   layer GEMM2      : res_skip_layers[i], residual/skip update, `end` (folded) :211-222
 //   flow boundary    : affine coupling inverse, W^-1, early-z concat, start conv :329-347, :189
 #include "cwg_common.cuh"
+#include "cwg_sm100.cuh"
+#include <cuda_fp16.h>
 
 namespace cwg {
 
@@ -294,6 +296,30 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
       if (XFMT == 0) {
         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.x_out) + idx);
         o[0] = make_float4(x[0], x[1], x[2], x[3]); o[1] = make_float4(x[4], x[5], x[6], x[7]);
+      } else if (XFMT == 2) {                  // CWG_MODE_F16F8: fp16 hi, fp16 lo, e5m2(lo * 2^P), e5m2(hi * 2^-Q)
+        const size_t plane = (size_t)p.BT * p.C;
+        __half* hi = reinterpret_cast<__half*>(p.x_out);
+        uint8_t* p8 = reinterpret_cast<uint8_t*>(p.x_out) + 4 * plane;
+        uint32_t h[4], l[4];
+        float hf[8], df[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+          hf[2 * i] = __low2float(hh); hf[2 * i + 1] = __high2float(hh);
+          df[2 * i] = x[2 * i] - hf[2 * i]; df[2 * i + 1] = x[2 * i + 1] - hf[2 * i + 1];
+          const __half2 ll = __floats2half2_rn(df[2 * i], df[2 * i + 1]);
+          h[i] = *reinterpret_cast<const uint32_t*>(&hh); l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(hi + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(hi + plane + idx) = make_uint4(l[0], l[1], l[2], l[3]);
+        uint32_t l8[2], h8[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          l8[i] = sm100::pack_e5m2x4(df[4 * i] * F8_LO_SCALE, df[4 * i + 1] * F8_LO_SCALE, df[4 * i + 2] * F8_LO_SCALE, df[4 * i + 3] * F8_LO_SCALE);
+          h8[i] = sm100::pack_e5m2x4(hf[4 * i] * F8_HI_SCALE, hf[4 * i + 1] * F8_HI_SCALE, hf[4 * i + 2] * F8_HI_SCALE, hf[4 * i + 3] * F8_HI_SCALE);
+        }
+        *reinterpret_cast<uint2*>(p8 + idx) = make_uint2(l8[0], l8[1]);
+        *reinterpret_cast<uint2*>(p8 + plane + idx) = make_uint2(h8[0], h8[1]);
       } else {
         __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(p.x_out);
         __nv_bfloat16* lo = hi + (size_t)p.BT * p.C;
@@ -425,8 +451,10 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
   if ((d.C & 7) == 0 && ((uintptr_t)x_out & 15) == 0) {
     unsigned grid = (unsigned)((d.BT + TBV - 1) / TBV);
     if (xfmt == 0) k_flow_boundary_v<0><<<grid, TBV, 0, s>>>(p);
+    else if (xfmt == 2) k_flow_boundary_v<2><<<grid, TBV, 0, s>>>(p);
     else           k_flow_boundary_v<1><<<grid, TBV, 0, s>>>(p);
   } else {
+    CWG_REQUIRE(xfmt != 2, "CWG_MODE_F16F8 needs n_channels % 8 == 0");
     unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
     if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
     else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);

@@ -106,6 +106,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// fp16 x fp16 -> fp32 uses the same kind::f16 instruction with the F16 operand formats.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::f8f6f4, e5m2 x e5m2 -> fp32, both operands K-major (K = 32 per instruction).
+__host__ __device__ constexpr uint32_t umma_idesc_e5m2(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Same with the A operand read from tensor memory ([M lanes] x [K/2 32-bit columns], two bf16 per column, the
 // even-k element in the low half): the ".ts" form.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -131,6 +146,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {    // lo_elem at the lower address
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e5m2x4(float e0, float e1, float e2, float e3) {   // e0 at the lowest address
+  uint16_t a, b;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(a) : "f"(e1), "f"(e0));
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(b) : "f"(e3), "f"(e2));
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+// two packed 16-bit floats -> fp32 (F16: IEEE half, else bf16)
+template <bool F16>
+__device__ __forceinline__ void unpack2(uint32_t w, float& e0, float& e1) {
+  if (F16) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(e0), "=f"(e1) : "r"(w));
+  } else {
+    e0 = __uint_as_float(w << 16); e1 = __uint_as_float(w & 0xFFFF0000u);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo_elem, float hi_elem) {
+  return F16 ? pack_f16x2(lo_elem, hi_elem) : pack_bf16x2(lo_elem, hi_elem);
 }
 // Byte offset of (row, 16-byte chunk) inside a 128B-swizzled tile whose base is 1024-byte aligned.
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {

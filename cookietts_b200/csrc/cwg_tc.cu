@@ -25,7 +25,7 @@ namespace {
 // mel4 im2col: mel4[b*Tm + f][j*M + ci] = mel[b][ci][f - j] (0 for f < j), bf16 hi / lo planes
 // ------------------------------------------------------------------------------------------
 __global__ void k_im2col_mel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                             int B, int M, int Tm, int J, int KCp) {
+                             int B, int M, int Tm, int J, int KCp, int f16) {
   long long n = (long long)B * Tm * KCp;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -33,6 +33,12 @@ __global__ void k_im2col_mel(const float* __restrict__ mel, __nv_bfloat16* __res
   int b = (int)(row / Tm), f = (int)(row - (long long)b * Tm);
   int j = kk / M, ci = kk - j * M;
   float v = (j < J && f >= j) ? mel[((size_t)b * M + ci) * Tm + (f - j)] : 0.f;   // columns >= J*M are zero padding
+  if (f16) {                                                                        // CWG_MODE_F16F8: fp16 hi / lo
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<__half*>(hi)[i] = h;
+    reinterpret_cast<__half*>(lo)[i] = __float2half_rn(v - __half2float(h));
+    return;
+  }
   __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[i] = h;
   lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -51,11 +57,11 @@ struct CondArgs {
 
 template <int NPASS>
 struct CondCfg {
-  static constexpr int PL = NPASS == 3 ? 2 : 1;
+  static constexpr int PL = NPASS != 1 ? 2 : 1;               // NPASS 2 (f16f8): three fp16 products like bf16x3
   static constexpr int STAGE = (TILE_A + 2 * TILE_A) * PL;     // A 16 KB + B 32 KB per plane
   // One (bf16x3) / two (bf16) stages of 96 / 48 KB: two CTAs are co-resident per SM (2 x 256 TMEM columns), so one
   // CTA's loads and MMAs overlap the other's epilogue and stores (the K loop is only 5 k-blocks long).
-  static constexpr int NST = NPASS == 3 ? 1 : 2;
+  static constexpr int NST = NPASS != 1 ? 1 : 2;
   static constexpr int SMEM = NST * STAGE + 256 + 1024;
 };
 
@@ -63,8 +69,11 @@ template <int NPASS>
 __global__ void __launch_bounds__(192, 2)
 k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-          const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo, CondArgs a) {
+          const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
+          const __grid_constant__ CUtensorMap tm_c_h8, CondArgs a) {   // f16f8: tm_c_lo = e5m2 lo*2^P plane, tm_c_h8 = e5m2 hi*2^-Q
   using Cfg = CondCfg<NPASS>;
+  constexpr bool F8 = NPASS == 2;
+  constexpr uint32_t ID256 = F8 ? IDESC_F16_N256 : IDESC_N256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::NST * Cfg::STAGE);
@@ -95,7 +104,7 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
       mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
       tma_load_2d(st, &tm_a_hi, &full[s], kb * 64, m0);
       tma_load_2d(st + TILE_A, &tm_b_hi, &full[s], kb * 64, a.w_row0 + p * 256);
-      if (NPASS == 3) {
+      if (NPASS != 1) {
         tma_load_2d(st + 3 * TILE_A, &tm_a_lo, &full[s], kb * 64, m0);
         tma_load_2d(st + 4 * TILE_A, &tm_b_lo, &full[s], kb * 64, a.w_row0 + p * 256);
       }
@@ -107,10 +116,10 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
       mbar_wait(&full[s], ph);
       tc_fence_after_sync();
       uint32_t st = smem_u32(smem + s * Cfg::STAGE);
-      issue_kblock(st, st + TILE_A, tmem, IDESC_N256, kb == 0);
-      if (NPASS == 3) {
-        issue_kblock(st + 3 * TILE_A, st + TILE_A, tmem, IDESC_N256, false);   // lo * hi
-        issue_kblock(st, st + 4 * TILE_A, tmem, IDESC_N256, false);            // hi * lo
+      issue_kblock(st, st + TILE_A, tmem, ID256, kb == 0);
+      if (NPASS != 1) {
+        issue_kblock(st + 3 * TILE_A, st + TILE_A, tmem, ID256, false);   // lo * hi
+        issue_kblock(st, st + 4 * TILE_A, tmem, ID256, false);            // hi * lo
       }
       umma_commit(&empty[s]);
       ring_advance(s, ph, Cfg::NST);
@@ -137,7 +146,8 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
         }
         uint8_t* thi = smem + ((c >> 2) & 1) * TILE_A;
-        store_split16<NPASS == 3>(v, thi, thi + 2 * TILE_A, row, (c & 3) * 2);
+        if (F8) store_split16_f8(v, thi, nullptr, smem + 2 * TILE_A, smem + 3 * TILE_A, row, (c & 3) * 2, c & 7);
+        else store_split16<NPASS == 3>(v, thi, thi + 2 * TILE_A, row, (c & 3) * 2);
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();
@@ -146,6 +156,10 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         for (int j = 0; j < 2; ++j) {
           tma_store_2d(&tm_c_hi, smem + j * TILE_A, p * 256 + (2 * half + j) * 64, m0);
           if (NPASS == 3) tma_store_2d(&tm_c_lo, smem + (2 + j) * TILE_A, p * 256 + (2 * half + j) * 64, m0);
+        }
+        if (F8) {                                   // one [128 rows x 128 B] e5m2 tile per plane and half
+          tma_store_2d(&tm_c_lo, smem + 2 * TILE_A, p * 256 + half * 128, m0);
+          tma_store_2d(&tm_c_h8, smem + 3 * TILE_A, p * 256 + half * 128, m0);
         }
         tma_store_commit();
         tma_store_wait_read();                 // the second half reuses the staging tiles
@@ -201,6 +215,7 @@ constexpr int L_EPI_THREADS = 32 * L_EPI_WARPS;
 constexpr int L_THREADS = 128 + L_EPI_THREADS;         // warps 0-3: TMA-A, MMA, TMA-B, residual prefetch
 constexpr int L_CPG = 16 / (L_EPI_WARPS / 4);          // 16-channel chunks per epilogue column group
 constexpr uint32_t L_D2_RES = 256, L_D2_EO = 64;       // TMEM columns of the GEMM2 accumulators
+static_assert(L_CPG == 8, "f16f8 stages one 128-channel e5m2 tile per epilogue column group");
 // The N=16 folded-`end` MMAs cost ~110 cycles each - as much as an N=256 one.  Measured NOT to be the cause: the
 // shared-memory A read (A from TMEM: GEMM2 11.9 k instead of 13.0 k cycles in bf16x3, same in bf16) and the
 // accumulate dependency on the same 16 columns (L_EO_CHAINS = 4 independent accumulators summed in the epilogue:
@@ -223,8 +238,19 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
            const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
            const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
            const __grid_constant__ CUtensorMap tm_wse_hi, const __grid_constant__ CUtensorMap tm_wse_lo,
-           const __grid_constant__ CUtensorMap tm_xo_hi, const __grid_constant__ CUtensorMap tm_xo_lo, LayerArgs a) {
-  constexpr int PL = NPASS == 3 ? 2 : 1;
+           const __grid_constant__ CUtensorMap tm_xo_hi, const __grid_constant__ CUtensorMap tm_xo_lo,
+           // e5m2 planes, NPASS == 2 (CWG_MODE_F16F8) only: activations lo*2^P / hi*2^-Q, w1 hi*2^-P / lo*2^Q, x output
+           const __grid_constant__ CUtensorMap tm_x_l8, const __grid_constant__ CUtensorMap tm_x_h8,
+           const __grid_constant__ CUtensorMap tm_h_l8, const __grid_constant__ CUtensorMap tm_h_h8,
+           const __grid_constant__ CUtensorMap tm_w1_h8, const __grid_constant__ CUtensorMap tm_w1_l8,
+           const __grid_constant__ CUtensorMap tm_xo_l8, const __grid_constant__ CUtensorMap tm_xo_h8, LayerArgs a) {
+  // NPASS: 1 = bf16 (hi planes only), 3 = bf16x3 (hi/lo bf16 planes, 3 MMAs), 2 = f16f8: fp16 hi/lo planes, GEMM1 =
+  // one fp16 pass + two e5m2 correction passes over K-blocks of 128 (same 16-KB tiles), GEMM2 = three fp16 passes.
+  constexpr bool F8 = NPASS == 2;
+  constexpr bool X3 = NPASS != 1;                 // lo planes exist (residual, GEMM2 cross terms)
+  constexpr int PL = NPASS == 3 ? 2 : 1;          // planes streamed per k-block in GEMM1 of the bf16 modes
+  constexpr int PL2 = X3 ? 2 : 1;                 // planes of the GEMM2 operands
+  constexpr uint32_t ID256 = F8 ? IDESC_F16_N256 : IDESC_N256, ID16 = F8 ? IDESC_F16_N16 : IDESC_N16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   float* b1s = reinterpret_cast<float*>(smem + L_OFF_B1);
@@ -263,7 +289,25 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     // ---------------- producer A: activation tiles (3 dilated taps of x, then the cond hidden H2)
     tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_h_hi);
     int s = 0; uint32_t pm = 0;
-    for (int kb = 0; kb < 16; ++kb) {
+    if (F8) {
+      // K in groups of 128 channels (taps 0..2 of x: groups 0..5, H2: groups 6, 7); per group two fp16 tiles of 64
+      // channels, then the e5m2 tile of lo*2^P and the e5m2 tile of hi*2^-Q (128 channels = 128 bytes per row)
+      tma_prefetch_desc(&tm_x_l8); tma_prefetch_desc(&tm_x_h8);
+      for (int G = 0; G < 8; ++G)
+        for (int it = 0; it < 4; ++it) {
+          mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
+          pm ^= 1u << s;
+          mbar_arrive_expect_tx(&full[s], TILE_A);
+          const bool cond = G >= 6;
+          const int tt = cond ? t0 : t0 + ((G >> 1) - 1) * a.dil;
+          const int c0 = (cond ? G - 6 : (G & 1)) * 128;
+          if (it < 2) tma_load_3d(slot(s), cond ? &tm_h_hi : &tm_x_hi, &full[s], c0 + it * 64, tt, b);
+          else if (it == 2) tma_load_3d(slot(s), cond ? &tm_h_l8 : &tm_x_l8, &full[s], c0, tt, b);
+          else tma_load_3d(slot(s), cond ? &tm_h_h8 : &tm_x_h8, &full[s], c0, tt, b);
+          s = (s + 1 == L_NA) ? 0 : s + 1;
+        }
+    }
+    for (int kb = 0; kb < (F8 ? 0 : 16); ++kb) {
       for (int pl = 0; pl < PL; ++pl) {
         mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
         pm ^= 1u << s;
@@ -281,7 +325,20 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     // ---------------- producer B: weight tiles [256 rows x 64 k]
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w2_hi);
     int j = 0; uint32_t pm = 0;
-    for (int kb = 0; kb < 16; ++kb)
+    if (F8) {
+      tma_prefetch_desc(&tm_w1_h8); tma_prefetch_desc(&tm_w1_l8);
+      for (int G = 0; G < 8; ++G)
+        for (int it = 0; it < 4; ++it)
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
+            pm ^= 1u << j;
+            mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
+            if (it < 2) tma_load_2d(bslot(j), &tm_w1_hi, &full[4 + j], (2 * G + it) * 64, a.w1_row0 + g * 256);
+            else tma_load_2d(bslot(j), it == 2 ? &tm_w1_h8 : &tm_w1_l8, &full[4 + j], G * 128, a.w1_row0 + g * 256);
+            j = (j + 1) & 3;
+          }
+    }
+    for (int kb = 0; kb < (F8 ? 0 : 16); ++kb)
       for (int g = 0; g < 2; ++g)
         for (int pl = 0; pl < PL; ++pl) {
           mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
@@ -293,7 +350,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (a.has_res) {
       j = 2;
       for (int kb = 0; kb < 4; ++kb)
-        for (int pl = 0; pl < PL; ++pl) {
+        for (int pl = 0; pl < PL2; ++pl) {
           mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
           pm ^= 1u << j;
           mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
@@ -309,7 +366,23 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       cm ^= 1u << bar;
     };
     // GEMM1: pre[128 x 512] = [x taps | H2] (K = 1024) x W1^T, accumulators in TMEM columns 0..511
-    for (int kb = 0; kb < 16; ++kb) {
+    if (F8) {
+      for (int G = 0; G < 8; ++G)
+        for (int it = 0; it < 4; ++it) {
+          const int sa_cur = sa; wait_full(sa); sa = (sa + 1) & 3;
+          if (G == 0 && it == 0) CWG_STAMP(5);
+          for (int g = 0; g < 2; ++g) {
+            const int jb_cur = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+            tc_fence_after_sync();
+            const uint32_t d = tmem + g * 256;
+            if (it < 2) issue_kblock_fast(smem_u32(slot(sa_cur)), smem_u32(bslot(jb_cur)), d, IDESC_F16_N256, G == 0 && it == 0);
+            else issue_kblock_fast_f8(smem_u32(slot(sa_cur)), smem_u32(bslot(jb_cur)), d, IDESC_E5M2_N256);
+            umma_commit(&empty[4 + jb_cur]);
+          }
+          umma_commit(&empty[sa_cur]);
+        }
+    }
+    for (int kb = 0; kb < (F8 ? 0 : 16); ++kb) {
       const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
       int sa_lo = 0;
       if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
@@ -363,7 +436,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       int jb_hi = 0, jb_lo = 0;
       if (a.has_res) {
         jb_hi = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2;
-        if (NPASS == 3) { jb_lo = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2; }
+        if (X3) { jb_lo = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2; }
         tc_fence_after_sync();
         r_hi = smem_u32(bslot(jb_hi)); r_lo = smem_u32(bslot(jb_lo));
       }
@@ -371,18 +444,18 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       for (int k = 0; k < 4; ++k) {
         const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u;
         uint32_t eacc;
-        if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_hi + o), IDESC_N256, acc);
-        { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_hi + o), IDESC_N16, eacc); }
-        if (NPASS == 3) {
-          if (a.has_res) umma_bf16(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), IDESC_N256, 1u);
-          { const uint32_t d16 = eo_dst(&eacc); umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), IDESC_N16, eacc); }
-          if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_lo + o), IDESC_N256, 1u);
-          { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_lo + o), IDESC_N16, eacc); }
+        if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_hi + o), ID256, acc);
+        { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_hi + o), ID16, eacc); }
+        if (X3) {
+          if (a.has_res) umma_bf16(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), ID256, 1u);
+          { const uint32_t d16 = eo_dst(&eacc); umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), ID16, eacc); }
+          if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_lo + o), ID256, 1u);
+          { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_lo + o), ID16, eacc); }
         }
       }
       if (a.has_res) {
         umma_commit(&empty[4 + jb_hi]);
-        if (NPASS == 3) umma_commit(&empty[4 + jb_lo]);
+        if (X3) umma_commit(&empty[4 + jb_lo]);
         umma_commit(&g2_done[kb]);
       }
     }
@@ -393,10 +466,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     // delayed the first A tile by ~1 k cycles), then the residual prefetch: as soon as GEMM2 is done with
     // the acts tiles of a 64-channel block, the x_old (centre tap) tiles of that block are TMA-loaded
     // over them (units kb / 4+kb)
-    mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL);
+    mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL2);
     for (int kb = 0; kb < 4; ++kb) {
       tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
-      if (NPASS == 3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
+      if (X3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
     }
     if (a.has_res) {
       tma_prefetch_desc(&tm_x_lo);
@@ -447,8 +520,8 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           act[4 * q + 2] = gate<NPASS>(__uint_as_float(cur[4 * q + 2]) + bt.z, __uint_as_float(cur[16 + 4 * q + 2]) + bs.z);
           act[4 * q + 3] = gate<NPASS>(__uint_as_float(cur[4 * q + 3]) + bt.w, __uint_as_float(cur[16 + 4 * q + 3]) + bs.w);
         }
-        if (L_ACTS_TMEM) store_split16_tmem<NPASS == 3>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
-        else store_split16<NPASS == 3>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        if (L_ACTS_TMEM) store_split16_tmem<X3, F8>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        else store_split16<X3, F8>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
       }
     }
     if (L_ACTS_TMEM) tmem_wait_st();
@@ -517,10 +590,15 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {   // x_new = x_old(hi + lo) + res, glow.py:217
-          r[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-          r[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+          float h0, h1, l0f, l1f;
+          unpack2<F8>(hw[j], h0, h1); unpack2<F8>(lw[j], l0f, l1f);
+          r[2 * j] += h0 + l0f;
+          r[2 * j + 1] += h1 + l1f;
         }
-        store_split16<true>(r, thi, tlo, row, (c & 3) * 2);     // in place: same thread, same addresses
+        // in place (same thread, same addresses); f16f8 adds the two e5m2 planes of this 128-channel group, staged
+        // in the idle W2 weight slots (units 8 + grp and 10 + grp)
+        if (F8) store_split16_f8(r, thi, tlo, slot(8 + grp), slot(10 + grp), row, (c & 3) * 2, c & 7);
+        else store_split16<true>(r, thi, tlo, row, (c & 3) * 2);
         if ((i & 3) == 3) {
           // one 64-channel tile (hi + lo) of this column group is final: store it while the rest computes
           fence_proxy_async_smem();
@@ -529,6 +607,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
             const int kb = c >> 2;
             tma_store_3d(&tm_xo_hi, slot(kb), kb * 64, t0, b);
             tma_store_3d(&tm_xo_lo, slot(4 + kb), kb * 64, t0, b);
+            if (F8 && i == L_CPG - 1) {
+              tma_store_3d(&tm_xo_l8, slot(8 + grp), grp * 128, t0, b);
+              tma_store_3d(&tm_xo_h8, slot(10 + grp), grp * 128, t0, b);
+            }
             tma_store_commit();
           }
         }
@@ -554,7 +636,7 @@ int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, con
   const size_t n4 = (size_t)d.B * d.Tm * d.KCp;
   __nv_bfloat16* m4_hi = mel4_planes; __nv_bfloat16* m4_lo = mel4_planes + n4;
   if (mel != nullptr) {
-    k_im2col_mel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(mel, m4_hi, m4_lo, d.B, d.M, d.Tm, d.J, d.KCp);
+    k_im2col_mel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(mel, m4_hi, m4_lo, d.B, d.M, d.Tm, d.J, d.KCp, npass == 2);
     CWG_CHECK_CUDA(cudaGetLastError());
   }
   const uint64_t rows = (uint64_t)d.B * d.Tm, ncol = (uint64_t)d.P * d.H;
@@ -564,17 +646,27 @@ int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, con
   if (int r = map_2d(&tb_hi, w->cond_w_hi, d.KCp, (uint64_t)d.F * ncol, 256)) return r;
   if (int r = map_2d(&tb_lo, w->cond_w_lo, d.KCp, (uint64_t)d.F * ncol, 256)) return r;
   if (int r = map_2d(&tc_hi, h2_planes, ncol, rows, 128)) return r;
-  if (int r = map_2d(&tc_lo, h2_planes + (size_t)d.BT * d.H, ncol, rows, 128)) return r;
+  CUtensorMap tc_h8 = tc_hi;
+  if (npass == 2) {       // H2 = [fp16 hi][e5m2 lo*2^P][e5m2 hi*2^-Q]
+    uint8_t* h8 = reinterpret_cast<uint8_t*>(h2_planes) + 2 * (size_t)d.BT * d.H;
+    if (int r = map_2d8(&tc_lo, h8, ncol, rows, 128)) return r;
+    if (int r = map_2d8(&tc_h8, h8 + (size_t)d.BT * d.H, ncol, rows, 128)) return r;
+  } else {
+    if (int r = map_2d(&tc_lo, h2_planes + (size_t)d.BT * d.H, ncol, rows, 128)) return r;
+  }
   CondArgs a{};
   a.bias = cond_bias + (size_t)flow * d.H; a.bias_bstride = d.F * d.H;
   a.M = (int)rows; a.Tm = d.Tm; a.B = d.B; a.w_row0 = flow * (int)ncol; a.nkb = d.KCp / 64;
   dim3 grid(d.P, (unsigned)((rows + 127) / 128));
   if (npass == 3) {
     if (int r = set_smem(k_cond_tc<3>, CondCfg<3>::SMEM)) return r;
-    k_cond_tc<3><<<grid, 192, CondCfg<3>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, a);
+    k_cond_tc<3><<<grid, 192, CondCfg<3>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
+  } else if (npass == 2) {
+    if (int r = set_smem(k_cond_tc<2>, CondCfg<2>::SMEM)) return r;
+    k_cond_tc<2><<<grid, 192, CondCfg<2>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
   } else {
     if (int r = set_smem(k_cond_tc<1>, CondCfg<1>::SMEM)) return r;
-    k_cond_tc<1><<<grid, 192, CondCfg<1>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, a);
+    k_cond_tc<1><<<grid, 192, CondCfg<1>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
   }
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -591,13 +683,28 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
   if (int r = map_act(&th_hi, h2, d.H, d.Tp, d.B)) return r;
   if (int r = map_act(&th_lo, h2 + hplane, d.H, d.Tp, d.B)) return r;
   if (int r = map_2d(&tw1_hi, w->w1_hi, d.K1, fl * 2 * d.C, 256)) return r;
-  if (int r = map_2d(&tw1_lo, w->w1_lo, d.K1, fl * 2 * d.C, 256)) return r;
+  if (int r = map_2d(&tw1_lo, npass == 2 ? w->w1_hi : w->w1_lo, d.K1, fl * 2 * d.C, 256)) return r;   // f16f8 has no w1 lo plane
   if (int r = map_2d(&tw2_hi, w->w2_hi, d.C, fl * d.N2, 256)) return r;
   if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 256)) return r;
   if (int r = map_2d(&tse_hi, w->w2_hi, d.C, fl * d.N2, 16)) return r;
   if (int r = map_2d(&tse_lo, w->w2_lo, d.C, fl * d.N2, 16)) return r;
   if (int r = map_act(&to_hi, x_out, d.C, d.Tp, d.B)) return r;
   if (int r = map_act(&to_lo, x_out + plane, d.C, d.Tp, d.B)) return r;
+  // e5m2 planes (CWG_MODE_F16F8): x = [fp16 hi][fp16 lo][e5m2 lo*2^P][e5m2 hi*2^-Q], H2 = [fp16 hi][e5m2 lo*2^P][e5m2 hi*2^-Q]
+  CUtensorMap tx_l8 = tx_hi, tx_h8 = tx_hi, th_l8 = tx_hi, th_h8 = tx_hi, tw1_h8 = tx_hi, tw1_l8 = tx_hi, to_l8 = tx_hi, to_h8 = tx_hi;
+  if (npass == 2) {
+    const uint8_t* xi8 = reinterpret_cast<const uint8_t*>(x_in) + 4 * plane;
+    uint8_t* xo8 = reinterpret_cast<uint8_t*>(x_out) + 4 * plane;
+    const uint8_t* h8 = reinterpret_cast<const uint8_t*>(h2) + 2 * hplane;
+    if (int r = map_act8(&tx_l8, xi8, d.C, d.Tp, d.B)) return r;
+    if (int r = map_act8(&tx_h8, xi8 + plane, d.C, d.Tp, d.B)) return r;
+    if (int r = map_act8(&th_l8, h8, d.H, d.Tp, d.B)) return r;
+    if (int r = map_act8(&th_h8, h8 + hplane, d.H, d.Tp, d.B)) return r;
+    if (int r = map_2d8(&tw1_h8, w->w1_h8, d.K1, fl * 2 * d.C, 256)) return r;
+    if (int r = map_2d8(&tw1_l8, w->w1_l8, d.K1, fl * 2 * d.C, 256)) return r;
+    if (int r = map_act8(&to_l8, xo8, d.C, d.Tp, d.B)) return r;
+    if (int r = map_act8(&to_h8, xo8 + plane, d.C, d.Tp, d.B)) return r;
+  }
   const size_t idx = (size_t)flow * d.L + layer;
   LayerArgs a{};
   a.b1 = w->b1 + idx * 2 * d.C; a.b2 = w->b2 + idx * d.C; a.eo_b = w->eo_b + (size_t)flow * CWG_EO_PAD;
@@ -607,13 +714,17 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.has_res = layer < d.L - 1; a.first = layer == 0;
   a.dbg = g_dbg_timing;
   dim3 grid((unsigned)((d.Tp + 127) / 128), d.B);
-  if (npass == 3) {
-    if (int r = set_smem(k_layer_tc<3>, L_SMEM)) return r;
-    k_layer_tc<3><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
-  } else {
-    if (int r = set_smem(k_layer_tc<1>, L_SMEM)) return r;
-    k_layer_tc<1><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo, a);
-  }
+#define CWG_LAUNCH_LAYER(NP)                                                                                          \
+  do {                                                                                                                \
+    if (int r = set_smem(k_layer_tc<NP>, L_SMEM)) return r;                                                           \
+    k_layer_tc<NP><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, \
+                                                   tse_lo, to_hi, to_lo, tx_l8, tx_h8, th_l8, th_h8, tw1_h8, tw1_l8,  \
+                                                   to_l8, to_h8, a);                                                  \
+  } while (0)
+  if (npass == 3) CWG_LAUNCH_LAYER(3);
+  else if (npass == 2) CWG_LAUNCH_LAYER(2);
+  else CWG_LAUNCH_LAYER(1);
+#undef CWG_LAUNCH_LAYER
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,13 +31,13 @@ inline PFN_encodeTiled get_encode() {
 
 // bf16 tensor, innermost dim contiguous, 128B swizzle, zero OOB fill. strides_bytes has rank-1 entries.
 inline int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, bool bytes = false) {
   PFN_encodeTiled enc = get_encode();
   CWG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = enc(m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CWG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -56,12 +56,25 @@ inline int map_act(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uin
   return make_map(m, ptr, 3, dims, st, box);
 }
 
+// 8-bit (e5m2) planes: the same tiles measured in bytes - 128 channels x 128 steps / 128 k x box_rows rows = 16 KB units
+inline int map_2d8(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows}; uint64_t st[1] = {cols}; uint32_t box[2] = {128, box_rows};
+  return make_map(m, ptr, 2, dims, st, box, true);
+}
+inline int map_act8(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uint64_t B) {
+  uint64_t dims[3] = {C, Tp, B}; uint64_t st[2] = {C, Tp * C}; uint32_t box[3] = {128, 128, 1};
+  return make_map(m, ptr, 3, dims, st, box, true);
+}
+
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
 constexpr int TILE_A = 128 * 128;      // [128 rows][64 bf16] = 16 KB
 constexpr uint32_t IDESC_N256 = umma_idesc_bf16(128, 256);
 constexpr uint32_t IDESC_N16 = umma_idesc_bf16(128, 16);
+constexpr uint32_t IDESC_F16_N256 = umma_idesc_f16(128, 256);
+constexpr uint32_t IDESC_F16_N16 = umma_idesc_f16(128, 16);
+constexpr uint32_t IDESC_E5M2_N256 = umma_idesc_e5m2(128, 256);
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   uint32_t a = smem_u32(p);
@@ -91,15 +104,16 @@ __device__ __forceinline__ void tmem_ld16_sync(uint32_t ta, float* a) {
 
 // 16 fp32 values of one row -> bf16 hi (and lo) planes, written as 2 x 16-byte chunks into
 // 128B-swizzled tiles (chunks `chunk0`, `chunk0 + 1` of `row`).
-template <bool WITH_LO>
+template <bool WITH_LO, bool F16 = false>
 __device__ __forceinline__ void store_split16(const float* v, uint8_t* tile_hi, uint8_t* tile_lo, int row, int chunk0) {
   uint32_t hi[8], lo[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    hi[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
     if (WITH_LO) {
-      float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
-      lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+      float h0, h1;
+      unpack2<F16>(hi[i], h0, h1);
+      lo[i] = pack2<F16>(v[2 * i] - h0, v[2 * i + 1] - h1);
     }
   }
   *reinterpret_cast<uint4*>(tile_hi + sw128_offset(row, chunk0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -112,15 +126,16 @@ __device__ __forceinline__ void store_split16(const float* v, uint8_t* tile_hi, 
 
 // 16 fp32 values of one row: bf16 hi packed into 8 TMEM columns (the A operand of a ".ts" MMA), lo (if any) into
 // a 128B-swizzled shared-memory tile.
-template <bool WITH_LO>
+template <bool WITH_LO, bool F16 = false>
 __device__ __forceinline__ void store_split16_tmem(const float* v, uint32_t tmem_hi, uint8_t* tile_lo, int row, int chunk0) {
   uint32_t hi[8], lo[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    hi[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
     if (WITH_LO) {
-      float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
-      lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+      float h0, h1;
+      unpack2<F16>(hi[i], h0, h1);
+      lo[i] = pack2<F16>(v[2 * i] - h0, v[2 * i + 1] - h1);
     }
   }
   tmem_st8(tmem_hi, hi);
@@ -130,10 +145,41 @@ __device__ __forceinline__ void store_split16_tmem(const float* v, uint32_t tmem
   }
 }
 
+// CWG_MODE_F16F8: 16 fp32 values of one row -> fp16 hi / lo tiles (as store_split16<true, true>) plus the two e5m2
+// correction planes e5m2((v - hi) * 2^P), e5m2(hi * 2^-Q) as one 16-byte chunk each of [rows x 128 B] tiles.
+__device__ __forceinline__ void store_split16_f8(const float* v, uint8_t* tile_hi, uint8_t* tile_lo, uint8_t* tile_l8,
+                                                 uint8_t* tile_h8, int row, int chunk0_16, int chunk_8) {
+  uint32_t hi[8], lo[8];
+  float d[16], h[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    unpack2<true>(hi[i], h[2 * i], h[2 * i + 1]);
+    d[2 * i] = v[2 * i] - h[2 * i]; d[2 * i + 1] = v[2 * i + 1] - h[2 * i + 1];
+    lo[i] = pack_f16x2(d[2 * i], d[2 * i + 1]);
+  }
+  if (tile_hi) {
+    *reinterpret_cast<uint4*>(tile_hi + sw128_offset(row, chunk0_16)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(tile_hi + sw128_offset(row, chunk0_16 + 1)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  }
+  if (tile_lo) {
+    *reinterpret_cast<uint4*>(tile_lo + sw128_offset(row, chunk0_16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(tile_lo + sw128_offset(row, chunk0_16 + 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  uint32_t l8[4], h8[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    l8[i] = pack_e5m2x4(d[4 * i] * F8_LO_SCALE, d[4 * i + 1] * F8_LO_SCALE, d[4 * i + 2] * F8_LO_SCALE, d[4 * i + 3] * F8_LO_SCALE);
+    h8[i] = pack_e5m2x4(h[4 * i] * F8_HI_SCALE, h[4 * i + 1] * F8_HI_SCALE, h[4 * i + 2] * F8_HI_SCALE, h[4 * i + 3] * F8_HI_SCALE);
+  }
+  *reinterpret_cast<uint4*>(tile_l8 + sw128_offset(row, chunk_8)) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+  *reinterpret_cast<uint4*>(tile_h8 + sw128_offset(row, chunk_8)) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+}
+
 // tanh(a) * sigmoid(b), glow.py:34-41
 template <int NPASS>
 __device__ __forceinline__ float gate(float a, float b) {
-  if (NPASS == 3) {
+  if (NPASS != 1) {
     // (1-u)/((1+u)(1+v)), u = e^-2a, v = e^-b : 2 ex2 + 1 rcp, ~1e-6 relative
     a = fmaxf(a, -15.f);
     float u = __expf(-2.f * a), v = __expf(-b);
@@ -159,6 +205,15 @@ __device__ __forceinline__ void issue_kblock_fast(uint32_t a_addr, uint32_t b_ad
   umma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
   umma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
   umma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+}
+// One 128-deep k-block of e5m2 operands = 4 UMMA K-steps of 32 bytes along the swizzled 128-byte row.
+__device__ __forceinline__ void issue_kblock_fast_f8(uint32_t a_addr, uint32_t b_addr, uint32_t tmem_d, uint32_t idesc) {
+  const uint64_t da = DESC_SW128_HI | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+  const uint64_t db = DESC_SW128_HI | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+  umma_f8(tmem_d, da, db, idesc, 1u);
+  umma_f8(tmem_d, da + 2, db + 2, idesc, 1u);
+  umma_f8(tmem_d, da + 4, db + 4, idesc, 1u);
+  umma_f8(tmem_d, da + 6, db + 6, idesc, 1u);
 }
 
 // 2 x 16 TMEM columns, issued without waiting; pair with tmem_wait32.

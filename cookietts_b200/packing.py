@@ -98,6 +98,37 @@ def split_hi_lo(w64: np.ndarray):
     return hi, lo
 
 
+# ---- "f16f8" mode (CWG_MODE_F16F8): q ~= fp16 hi + fp16 lo for the operands of 3-pass GEMMs, and for the in_layer
+# GEMM one fp16 pass plus two fp8 (e5m2) correction passes: a*w ~= a16*w16 + e5m2(a_lo*2^P)*e5m2(w16*2^-P)
+#                                                                        + e5m2(a16*2^-Q)*e5m2(w_lo*2^Q)
+F8_P, F8_Q = 6, 8
+
+
+def f32_to_e5m2_bits(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even fp32 -> e5m2 (what cvt.rn.satfinite.e5m2x2.f32 does), uint8 bit patterns."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    t = t.clamp(-57344.0, 57344.0)
+    return t.to(torch.float8_e5m2).view(torch.uint8).numpy()
+
+
+def e5m2_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint16) << 8).view(np.float16).astype(np.float32)
+
+
+def split_f16(w64: np.ndarray):
+    """w ~= hi + lo with both in fp16; returns uint16 bit planes."""
+    hi = w64.astype(np.float16)
+    lo = (w64 - hi.astype(np.float64)).astype(np.float16)
+    return hi.view(np.uint16), lo.view(np.uint16)
+
+
+def f8_correction_planes(w64: np.ndarray):
+    """(h8, l8) = (e5m2(w16 * 2^-P), e5m2((w - w16) * 2^Q)) as uint8 bit planes."""
+    w16 = w64.astype(np.float16).astype(np.float64)
+    return f32_to_e5m2_bits(w16 * 2.0 ** -F8_P), f32_to_e5m2_bits((w64 - w16) * 2.0 ** F8_Q)
+
+
 def _np(t) -> np.ndarray:
     if hasattr(t, "detach"):
         t = t.detach().cpu().numpy()
@@ -213,7 +244,11 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
     for name, arr in (("cond_w", cond_w), ("w1", w1), ("w2", w2)):
         if "f32" in planes:
             out[name + "_f32"] = arr.astype(np.float32)
-        if "hi" in planes or "lo" in planes:
+        if "f16f8" in planes:
+            out[name + "_hi"], out[name + "_lo"] = split_f16(arr)
+            if name == "w1":
+                out["w1_h8"], out["w1_l8"] = f8_correction_planes(arr)
+        elif "hi" in planes or "lo" in planes:
             hi, lo = split_hi_lo(arr)
             out[name + "_hi"] = hi
             if "lo" in planes:

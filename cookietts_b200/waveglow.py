@@ -149,7 +149,7 @@ class WaveGlow(nn.Module):
         if self._packed is not None and self._packed_key == key:
             return
         dev = self._device()
-        planes = ("f32",) if self.precision == "ffma" else ("hi", "lo")
+        planes = {"ffma": ("f32",), "f16f8": ("f16f8",)}.get(self.precision, ("hi", "lo"))
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
         pk = pack_state_dict(sd, self.pack_config, planes=planes)
         dev_pk = {}

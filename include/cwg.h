@@ -31,12 +31,16 @@
 extern "C" {
 #endif
 
-#define CWG_ABI_VERSION 1
+#define CWG_ABI_VERSION 2
 
 /* Arithmetic modes of the WN contractions. */
 #define CWG_MODE_FFMA   0   /* fp32 weights/activations, CUDA-core FFMA (exact fp32 semantics)        */
 #define CWG_MODE_BF16X3 1   /* tcgen05 bf16 MMA, operands split hi+lo, 3 products, fp32 accumulate   */
 #define CWG_MODE_BF16   2   /* tcgen05 bf16 MMA, single product, fp32 accumulate + hi/lo residual    */
+#define CWG_MODE_F16F8  3   /* fp32-accurate at 2 MMA passes instead of 3 (256-channel classic model): operands split into
+                               fp16 hi + lo; the in_layer GEMM issues hi*hi in fp16 and the two cross terms as e5m2 fp8
+                               MMAs (twice the rate): a*w ~= a16*w16 + e5m2(a_lo*2^6)*e5m2(w16*2^-6) + e5m2(a16*2^-8)*e5m2(w_lo*2^8);
+                               the small cond and res/skip GEMMs use three fp16 products                                 */
 
 #define CWG_EO_PAD 16       /* padded width of the folded `end` output (2*n_half <= 16)              */
 #define CWG_MAX_GROUP 16    /* n_group <= 16                                                         */
@@ -77,6 +81,9 @@ typedef struct cwg_weights {
   const float*    start_w;      /* [F][C][CWG_MAX_GROUP/2]                              */
   const float*    start_b;      /* [F][C]                                               */
   const float*    winv;         /* [F][CWG_MAX_GROUP][CWG_MAX_GROUP]  W^-1, row major   */
+  /* CWG_MODE_F16F8 only (there *_hi / *_lo are fp16 planes): e5m2 planes of w1, same shape as w1_hi */
+  const uint8_t*  w1_h8;        /* e5m2(fp16(w1) * 2^-6)                                */
+  const uint8_t*  w1_l8;        /* e5m2((w1 - fp16(w1)) * 2^8)                          */
 } cwg_weights;
 
 int         cwg_abi_version(void);
@@ -113,12 +120,14 @@ int cwg_launch_count(const cwg_config* cfg, int mode);
 /* ---- stage-level entry points (tests bisect the pipeline with these) ---------------- */
 
 /* Folded cond chain for one flow: H2 [batch][T'][H] (fp32 in FFMA mode; bf16 hi/lo planes,
- * hi first then lo, each [batch][T'][H], in the tensor-core modes). */
+ * hi first then lo, each [batch][T'][H], in the bf16 modes; in CWG_MODE_F16F8 an fp16 plane followed by the two
+ * e5m2 planes e5m2(lo * 2^6), e5m2(hi * 2^-8), 4 bytes per element in total). */
 int cwg_cond(const cwg_config* cfg, const cwg_weights* w, int mode, int flow,
              const float* mel, const float* cond_bias, void* h2_out,
              void* workspace, size_t workspace_bytes, int batch, int t_mel, void* cuda_stream);
 
-/* One WN layer: x_in -> x_out (fp32 [batch][T'][C] in FFMA mode; hi/lo bf16 planes otherwise),
+/* One WN layer: x_in -> x_out (fp32 [batch][T'][C] in FFMA mode; hi/lo bf16 planes in the bf16 modes; in
+ * CWG_MODE_F16F8 fp16 hi, fp16 lo, e5m2(lo * 2^6), e5m2(hi * 2^-8) planes, 6 bytes per element),
  * eo [batch][T'][CWG_EO_PAD] fp32 accumulated (written when layer == 0). */
 int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow, int layer,
                  const void* x_in, void* x_out, const void* h2, float* eo,

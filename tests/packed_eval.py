@@ -8,7 +8,8 @@ and with `emulate='bf16'/'bf16x3'` to predict the tensor-core modes' error.
 """
 import numpy as np
 
-from cookietts_b200.packing import PackConfig, bf16_bits_to_f32, f32_to_bf16_bits, EO_PAD
+from cookietts_b200.packing import (PackConfig, bf16_bits_to_f32, f32_to_bf16_bits, EO_PAD, F8_P, F8_Q,
+                                    f32_to_e5m2_bits, e5m2_bits_to_f32)
 
 
 def _round_bf16(x):
@@ -21,12 +22,27 @@ def _split(x):
     return hi, lo
 
 
+def _r16(x):
+    return x.astype(np.float16).astype(np.float64)
+
+
+def _r8(x):
+    return e5m2_bits_to_f32(f32_to_e5m2_bits(x.astype(np.float32))).astype(np.float64)
+
+
 def _mm(a, w, emulate):
     """a [rows, K] @ w[N, K]^T with the operand rounding of the chosen mode.
-    w is (w_full, w_hi, w_lo)."""
+    w is (w_full, w_hi, w_lo) or, for the f16f8 in_layer GEMM, (None, w16, (w_h8, w_l8))."""
     w_full, w_hi, w_lo = w
     if emulate is None:
         return a @ w_full.T
+    if emulate == "f16f8":
+        a16 = _r16(a)
+        a_lo = a - a16
+        if isinstance(w_lo, tuple):          # fp16 pass + two e5m2 correction passes (csrc/cwg_tc.cu, GEMM1)
+            w_h8, w_l8 = w_lo
+            return a16 @ w_hi.T + _r8(a_lo * 2.0 ** F8_P) @ w_h8.T + _r8(a16 * 2.0 ** -F8_Q) @ w_l8.T
+        return a16 @ w_hi.T + _r16(a_lo) @ w_hi.T + a16 @ w_lo.T      # fp16 hi/lo, 3 passes
     a_hi, a_lo = _split(a)
     if emulate == "bf16":
         return a_hi @ w_hi.T
@@ -43,6 +59,12 @@ def packed_infer(pk, cfg: PackConfig, mel, z, sigma, emulate=None, cond_bias=Non
         if emulate is None:
             full = pk[name + "_f32"][idx].astype(np.float64)
             return (full, None, None)
+        if emulate == "f16f8":
+            hi = pk[name + "_hi"][idx].view(np.float16).astype(np.float64)
+            if name == "w1":
+                return (None, hi, (e5m2_bits_to_f32(pk["w1_h8"][idx]).astype(np.float64),
+                                   e5m2_bits_to_f32(pk["w1_l8"][idx]).astype(np.float64)))
+            return (None, hi, pk[name + "_lo"][idx].view(np.float16).astype(np.float64))
         hi = bf16_bits_to_f32(pk[name + "_hi"][idx]).astype(np.float64)
         lo = bf16_bits_to_f32(pk[name + "_lo"][idx]).astype(np.float64)
         return (None, hi, lo)

@@ -16,6 +16,7 @@ TOL = {
     "ffma":   dict(max_abs=1e-4, snr=100.0),   # exact fp32 arithmetic, different summation order
     "bf16x3": dict(max_abs=1e-3, snr=60.0),    # the "fp32 path" bar of north_star
     "bf16":   dict(max_abs=5e-2, snr=45.0),    # stated tolerance of the bf16 path
+    "f16f8":  dict(max_abs=1e-3, snr=60.0),    # fp16 pass + two e5m2 correction passes: also an "fp32 path" (same bar)
 }
 
 
@@ -38,6 +39,15 @@ def test_ffma_matches_reference(name):
     assert max_abs(out, ref) <= TOL["ffma"]["max_abs"]
     assert snr_db(ref, out) >= TOL["ffma"]["snr"]
     assert max_abs(out, g["audio_ref_fp32"]) <= TOL["ffma"]["max_abs"]
+
+
+@pytest.mark.parametrize("name,precision", [("config1", "f16f8"), ("mel20_256", "f16f8")])
+def test_f16f8_mode_matches_reference(name, precision):
+    out, g = run(name, precision)
+    ref = g["audio_ref_fp64"]
+    assert np.isfinite(out).all()
+    assert max_abs(out, ref) <= 5e-4          # measured ~1e-4; the bar is 1e-3
+    assert snr_db(ref, out) >= 80.0
 
 
 @pytest.mark.parametrize("name", ["config1", "c512", "mel20_256"])
@@ -101,7 +111,7 @@ def test_full_length_tensor_modes_vs_fp32_cuda_cores():
     exact-fp32 CUDA-core mode, which tests above pin to the reference."""
     mel, z = _inputs(2, 861)
     ref = _model("ffma").infer(mel, sigma=0.666, z=z)
-    for precision in ("bf16x3", "bf16"):
+    for precision in ("bf16x3", "bf16", "f16f8"):
         out = _model(precision).infer(mel, sigma=0.666, z=z)
         assert torch.isfinite(out).all()
         assert float((out - ref).abs().max()) <= TOL[precision]["max_abs"], precision

@@ -28,7 +28,7 @@ def make(precision):
 
 @pytest.fixture(scope="module")
 def models():
-    return {p: make(p) for p in ("ffma", "bf16x3", "bf16")}
+    return {p: make(p) for p in ("ffma", "bf16x3", "bf16", "f16f8")}
 
 
 def workspace(model, mode):
@@ -43,6 +43,31 @@ def split(x):
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16)
     return torch.stack([hi, lo]).contiguous()       # [2, ...]: hi plane then lo plane
+
+
+def f8_planes(x, with_lo16):
+    """CWG_MODE_F16F8 activation planes as one byte buffer: fp16 hi [, fp16 lo], e5m2(lo * 2^6), e5m2(hi * 2^-8)."""
+    hi = x.to(torch.float16)
+    d = x - hi.float()
+    parts = [hi.view(torch.uint8).reshape(-1)]
+    if with_lo16:
+        parts.append(d.to(torch.float16).view(torch.uint8).reshape(-1))
+    parts.append((d * 64.0).to(torch.float8_e5m2).view(torch.uint8).reshape(-1))
+    parts.append((hi.float() / 256.0).to(torch.float8_e5m2).view(torch.uint8).reshape(-1))
+    return torch.cat(parts).contiguous()
+
+
+def f8_decode(buf, shape, with_lo16):
+    """(hi + lo16 [if present], e5m2 lo plane / 2^6, e5m2 hi plane * 2^8) of a plane buffer."""
+    n = int(np.prod(shape))
+    hi = buf[:2 * n].view(torch.float16).reshape(shape).float()
+    off = 2 * n
+    lo = None
+    if with_lo16:
+        lo = buf[off:off + 2 * n].view(torch.float16).reshape(shape).float(); off += 2 * n
+    l8 = buf[off:off + n].view(torch.float8_e5m2).reshape(shape).float() / 64.0
+    h8 = buf[off + n:off + 2 * n].view(torch.float8_e5m2).reshape(shape).float() * 256.0
+    return hi, lo, l8, h8
 
 
 def rel_err(a, b):
@@ -79,6 +104,15 @@ def test_cond_stage(models, flow):
         got = h_t[0].float() + (h_t[1].float() if prec == "bf16x3" else 0)
         assert torch.isfinite(got).all()
         assert rel_err(got, ref) < tol, prec
+    # f16f8: fp16 hi plane + e5m2 planes of the remainder (x 2^6) and of hi (x 2^-8)
+    buf = torch.zeros(4 * B * tp * H, dtype=torch.uint8, device="cuda")
+    run_cond(models["f16f8"], _cabi.MODE_F16F8, flow, mel, buf)
+    hi, _, l8, h8 = f8_decode(buf, (B, tp, H), False)
+    assert rel_err(hi, ref) < 1e-3                                      # fp16 rounding of the result
+    d = ref.float() - hi
+    assert float((l8 - d).abs().max()) <= float(d.abs().max()) * 0.13 + 1e-6      # e5m2: 2 mantissa bits
+    assert float((h8 - hi).abs().max()) <= float(hi.abs().max()) * 0.13
+    assert rel_err(hi + l8, ref) < 2e-4
 
 
 @pytest.mark.parametrize("layer", [0, 3, 6, 7])
@@ -127,3 +161,19 @@ def test_layer_stage(models, layer):
         if layer < pc.n_layers - 1:
             got = xo_t[0].float() + xo_t[1].float()
             assert rel_err(got, x_ref) < tol, (prec, "x")
+    # f16f8: one fp16 pass + two e5m2 correction passes in the in_layer GEMM
+    mt = models["f16f8"]
+    xin, h2p = f8_planes(x, True), f8_planes(h2, False)
+    xo_t = torch.zeros_like(xin)
+    eo_t = eo0.clone()
+    _cabi.check(lib.cwg_wn_layer(mt._ccfg, mt._cw, _cabi.MODE_F16F8, flow, layer, xin.data_ptr(), xo_t.data_ptr(),
+                                 h2p.data_ptr(), eo_t.data_ptr(), 0, 0, B, TM, stream))
+    torch.cuda.synchronize()
+    assert torch.isfinite(eo_t).all()
+    assert rel_err(eo_t, eo_ref) < 2e-4, ("f16f8", "eo")
+    if layer < pc.n_layers - 1:
+        hi, lo, l8, h8 = f8_decode(xo_t, (B, tp, Cc), True)
+        assert rel_err(hi + lo, x_ref) < 2e-4, ("f16f8", "x")
+        d = x_ref.float() - hi
+        assert float((l8 - d).abs().max()) <= float(d.abs().max()) * 0.13 + 1e-5
+        assert float((h8 - hi).abs().max()) <= float(hi.abs().max()) * 0.13

@@ -46,3 +46,28 @@ def test_emulated_tensor_modes_error_budget(mode, snr_min, abs_max):
     ref = g["audio_ref_fp64"]
     assert snr_db(ref, out) > snr_min
     assert max_abs(out, ref) < abs_max
+
+
+def test_f16f8_planes_and_predicted_accuracy():
+    """CWG_MODE_F16F8 packing: the planes decode to what include/cwg.h states, and the numpy evaluation of the kernel
+    arithmetic (fp16 pass + two e5m2 correction passes in the in_layer GEMM, three fp16 passes elsewhere) stays far
+    inside the fp32-path bar on a 256-channel golden case."""
+    from cookietts_b200.packing import F8_P, F8_Q, e5m2_bits_to_f32
+    cfg, sd, g = load_golden("mel20_256")
+    pc = PackConfig(n_mel=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group, n_early_every=cfg.n_early_every,
+                    n_early_size=cfg.n_early_size, win_length=cfg.win_length, hop_length=cfg.hop_length,
+                    n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, cond_hidden=256)
+    pk = pack_state_dict(sd, pc, planes=("f16f8",))
+    ref = pack_state_dict(sd, pc, planes=("f32",))["w1_f32"].astype(np.float64)
+    w16 = pk["w1_hi"].view(np.float16).astype(np.float64)
+    assert np.abs(w16 - ref).max() <= np.abs(ref).max() * 2.0 ** -11
+    h8 = e5m2_bits_to_f32(pk["w1_h8"]).astype(np.float64) * 2.0 ** F8_P
+    l8 = e5m2_bits_to_f32(pk["w1_l8"]).astype(np.float64) * 2.0 ** -F8_Q
+    big = np.abs(w16) > 2.0 ** -8                      # e5m2 normal range after the 2^-6 scaling
+    assert np.abs(h8 - w16)[big].max() <= 0.126 * np.abs(w16)[big].max()
+    assert (np.abs(h8 - w16)[big] <= 0.126 * np.abs(w16)[big]).all()
+    d = ref - w16
+    assert (np.abs(l8 - d) <= 0.126 * np.abs(d) + 2.0 ** -24).all()
+    from tests.packed_eval import packed_infer
+    out = packed_infer(pk, pc, g["mel"], g["z"], float(g["sigma"]), emulate="f16f8")
+    assert max_abs(out, g["audio_ref_fp64"]) < 1e-4
