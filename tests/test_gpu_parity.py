@@ -61,7 +61,7 @@ def test_tensor_core_modes_match_reference(precision, name):
     assert snr_db(ref, out) >= TOL[precision]["snr"]
 
 
-@pytest.mark.parametrize("name,precision", [("speaker", "ffma"), ("speaker256", "ffma"), ("speaker256", "bf16x3")])
+@pytest.mark.parametrize("name,precision", [("speaker", "ffma"), ("speaker256", "ffma"), ("speaker256", "bf16x3"), ("speaker256", "f16f8")])
 def test_speaker_embedding_models(name, precision):
     """Multispeaker checkpoints (glow.py:193-196): the embedding enters as a per-utterance cond bias;
     both reference keywords (`speaker_id`, and `speaker_ids` as Denoiser/notebooks pass it) work."""
@@ -118,7 +118,7 @@ def test_full_length_tensor_modes_vs_fp32_cuda_cores():
         assert _snr(ref, out) >= TOL[precision]["snr"], precision
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "ffma"])
+@pytest.mark.parametrize("precision", ["bf16x3", "ffma", "f16f8"])
 def test_chunked_long_form_equals_unchunked(precision):
     """Halo-chunked inference (cookietts_b200.parallel) reproduces the un-chunked waveform."""
     from cookietts_b200.parallel import infer_long

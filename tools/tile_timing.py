@@ -14,8 +14,13 @@ m = WaveGlow(precision=prec, **bench.MODEL_KW)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.cuda().eval(); m._ensure_packed()
 lib = _cabi.load()
 tp = TM * 32
-x = torch.randn(2, B, tp, 256, device="cuda").to(torch.bfloat16)
-h2 = torch.randn(2, B, tp, 256, device="cuda").to(torch.bfloat16)
+if prec == "f16f8":           # fp16 hi [, fp16 lo], e5m2(lo * 2^6), e5m2(hi * 2^-8) planes (include/cwg.h)
+    from tests.test_gpu_stages import f8_planes
+    x = f8_planes(torch.randn(B, tp, 256, device="cuda"), True)
+    h2 = f8_planes(torch.randn(B, tp, 256, device="cuda"), False)
+else:
+    x = torch.randn(2, B, tp, 256, device="cuda").to(torch.bfloat16)
+    h2 = torch.randn(2, B, tp, 256, device="cuda").to(torch.bfloat16)
 xo = torch.zeros_like(x); eo = torch.zeros(B, tp, 16, device="cuda")
 ntile = (tp + 127) // 128
 dbg = torch.zeros(B * ntile * 16, dtype=torch.int64, device="cuda")
