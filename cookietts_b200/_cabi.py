@@ -25,7 +25,7 @@ class CwgConfig(C.Structure):
 
 
 WEIGHT_FIELDS = ("cond_w_f32", "cond_w_hi", "cond_w_lo", "w1_f32", "w1_hi", "w1_lo", "b1",
-                 "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv", "w1_h8", "w1_l8")
+                 "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv", "w1_h8", "w1_l8", "w2_h8", "w2_l8")
 
 
 class CwgWeights(C.Structure):

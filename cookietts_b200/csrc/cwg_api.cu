@@ -95,7 +95,7 @@ int check_run(const cwg_config* cfg, const cwg_weights* w, int mode, int batch, 
   CWG_REQUIRE(w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b && w->winv, "missing weight arrays");
   if (mode == CWG_MODE_FFMA) CWG_REQUIRE(w->cond_w_f32 && w->w1_f32 && w->w2_f32, "fp32 weight planes missing");
   else if (mode == CWG_MODE_F16F8)
-    CWG_REQUIRE(w->cond_w_hi && w->cond_w_lo && w->w1_hi && w->w1_h8 && w->w1_l8 && w->w2_hi && w->w2_lo,
+    CWG_REQUIRE(w->cond_w_hi && w->cond_w_lo && w->w1_hi && w->w1_h8 && w->w1_l8 && w->w2_hi && w->w2_h8 && w->w2_l8,
                 "fp16 / e5m2 weight planes missing");
   else CWG_REQUIRE(w->cond_w_hi && w->w1_hi && w->w2_hi && w->cond_w_lo && w->w1_lo && w->w2_lo,
                    "bf16 hi/lo weight planes missing");

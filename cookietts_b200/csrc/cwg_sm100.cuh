@@ -158,6 +158,20 @@ __device__ __forceinline__ uint32_t pack_e5m2x4(float e0, float e1, float e2, fl
   asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(b) : "f"(e3), "f"(e2));
   return (uint32_t)a | ((uint32_t)b << 16);
 }
+// Four e5m2 values from two packed fp16 pairs scaled by a power of two: e5m2 is the high byte of fp16, so scale in
+// half2 (FMA pipe), round by adding half an e5m2 ulp to each half (ties away from zero; sign-magnitude, so plain
+// integer add) and gather the high bytes with one PRMT - no conversion-unit instructions.
+__device__ __forceinline__ uint32_t e5m2x4_from_f16x2(uint32_t w0, uint32_t w1, uint32_t scale_f16x2) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 a, b;\n\t"
+      "mul.f16x2 a, %1, %3;\n\tmul.f16x2 b, %2, %3;\n\t"
+      "add.u32 a, a, 0x00800080;\n\tadd.u32 b, b, 0x00800080;\n\t"
+      "prmt.b32 %0, a, b, 0x7531;\n\t}"
+      : "=r"(r) : "r"(w0), "r"(w1), "r"(scale_f16x2));
+  return r;
+}
+constexpr uint32_t F16X2_2P6 = 0x54005400u;    // 64.0 in both halves   (2^F8_P)
+constexpr uint32_t F16X2_2M8 = 0x1C001C00u;    // 1/256 in both halves  (2^-F8_Q)
 // two packed 16-bit floats -> fp32 (F16: IEEE half, else bf16)
 template <bool F16>
 __device__ __forceinline__ void unpack2(uint32_t w, float& e0, float& e1) {

@@ -243,7 +243,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
            const __grid_constant__ CUtensorMap tm_x_l8, const __grid_constant__ CUtensorMap tm_x_h8,
            const __grid_constant__ CUtensorMap tm_h_l8, const __grid_constant__ CUtensorMap tm_h_h8,
            const __grid_constant__ CUtensorMap tm_w1_h8, const __grid_constant__ CUtensorMap tm_w1_l8,
-           const __grid_constant__ CUtensorMap tm_xo_l8, const __grid_constant__ CUtensorMap tm_xo_h8, LayerArgs a) {
+           const __grid_constant__ CUtensorMap tm_xo_l8, const __grid_constant__ CUtensorMap tm_xo_h8,
+           // f16f8: tm_w2_lo / tm_wse_lo are the e5m2 hi*2^-P planes of w2 (boxes of 256 / 16 rows), these the lo*2^Q ones
+           const __grid_constant__ CUtensorMap tm_w2_l8, const __grid_constant__ CUtensorMap tm_wse_l8, LayerArgs a) {
   // NPASS: 1 = bf16 (hi planes only), 3 = bf16x3 (hi/lo bf16 planes, 3 MMAs), 2 = f16f8: fp16 hi/lo planes, GEMM1 =
   // one fp16 pass + two e5m2 correction passes over K-blocks of 128 (same 16-KB tiles), GEMM2 = three fp16 passes.
   constexpr bool F8 = NPASS == 2;
@@ -251,6 +253,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   constexpr int PL = NPASS == 3 ? 2 : 1;          // planes streamed per k-block in GEMM1 of the bf16 modes
   constexpr int PL2 = X3 ? 2 : 1;                 // planes of the GEMM2 operands
   constexpr uint32_t ID256 = F8 ? IDESC_F16_N256 : IDESC_N256, ID16 = F8 ? IDESC_F16_N16 : IDESC_N16;
+  // shared-memory unit of the lo tile of 64-channel block kb of x (residual read / x_new staging).  f16f8: units 4..7
+  // hold the e5m2 acts tiles of the two 128-channel groups during GEMM2 (4 + g: lo*2^P, 6 + g: hi*2^-Q), and group g
+  // frees units 4 + g and 6 + g, so blocks 0, 1 (needed first) take units 4, 6 and blocks 2, 3 take 5, 7.
+  auto lo_unit = [](int kb) { return F8 ? 4 + ((kb & 1) << 1) + (kb >> 1) : 4 + kb; };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   float* b1s = reinterpret_cast<float*>(smem + L_OFF_B1);
@@ -347,7 +353,19 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           tma_load_2d(bslot(j), pl ? &tm_w1_lo : &tm_w1_hi, &full[4 + j], kb * 64, a.w1_row0 + g * 256);
           j = (j + 1) & 3;
         }
-    if (a.has_res) {
+    if (a.has_res && F8) {
+      j = 2;
+      for (int grp = 0; grp < 2; ++grp)
+        for (int it = 0; it < 4; ++it) {          // two fp16 tiles, then the e5m2 hi*2^-P and lo*2^Q tiles of the group
+          mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
+          pm ^= 1u << j;
+          mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
+          if (it < 2) tma_load_2d(bslot(j), &tm_w2_hi, &full[4 + j], (2 * grp + it) * 64, a.w2_row0);
+          else tma_load_2d(bslot(j), it == 2 ? &tm_w2_lo : &tm_w2_l8, &full[4 + j], grp * 128, a.w2_row0);
+          j = j == 2 ? 3 : 2;
+        }
+    }
+    if (a.has_res && !F8) {
       j = 2;
       for (int kb = 0; kb < 4; ++kb)
         for (int pl = 0; pl < PL2; ++pl) {
@@ -428,7 +446,38 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       ++n_eo;
       return tmem + L_D2_EO + 16 * j;
     };
-    for (int kb = 0; kb < 4; ++kb) {
+    if (F8) {
+      // f16f8 GEMM2: per 128-channel group two fp16 k-blocks (A = acts hi in TMEM) and two e5m2 k-blocks of 128
+      // (A = the e5m2 acts tiles in units 4 + grp / 6 + grp); the folded-`end` rows ride along as N=16 MMAs
+      const uint32_t dres = tmem + L_D2_RES, d16 = tmem + L_D2_EO;
+      for (int grp = 0; grp < 2; ++grp) {
+        for (int it = 0; it < 4; ++it) {
+          uint32_t r = 0; int jb_cur = 0;
+          if (a.has_res) { jb_cur = jb; wait_full(4 + jb); jb = jb == 2 ? 3 : 2; tc_fence_after_sync(); r = smem_u32(bslot(jb_cur)); }
+          if (it < 2) {
+            const int kb = 2 * grp + it;
+            const uint32_t wv = smem_u32(wse(0, kb));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u, a_t = tmem + L_ACOL(kb * 4 + k);
+              if (a.has_res) umma_bf16_ts(dres, a_t, umma_desc_sw128(r + o), IDESC_F16_N256, acc);
+              umma_bf16_ts(d16, a_t, umma_desc_sw128(wv + o), IDESC_F16_N16, acc);
+            }
+          } else {
+            const uint32_t av = smem_u32(slot(4 + 2 * (it - 2) + grp)), wv = smem_u32(wse(1, 2 * (it - 2) + grp));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t o = 32 * k;
+              if (a.has_res) umma_f8(dres, umma_desc_sw128(av + o), umma_desc_sw128(r + o), IDESC_E5M2_N256, 1u);
+              umma_f8(d16, umma_desc_sw128(av + o), umma_desc_sw128(wv + o), IDESC_E5M2_N16, 1u);
+            }
+          }
+          if (a.has_res) umma_commit(&empty[4 + jb_cur]);
+        }
+        if (a.has_res) umma_commit(&g2_done[grp]);
+      }
+    }
+    for (int kb = 0; kb < (F8 ? 0 : 4); ++kb) {
       const uint32_t a_lo = smem_u32(slot(4 + kb));
       const uint32_t w_hi = smem_u32(wse(0, kb)), w_lo = smem_u32(wse(1, kb));
       const uint32_t dres = tmem + L_D2_RES;
@@ -469,9 +518,30 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL2);
     for (int kb = 0; kb < 4; ++kb) {
       tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
-      if (X3) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
+      if (X3 && !F8) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
     }
-    if (a.has_res) {
+    if (F8)       // e5m2 planes of the 16 folded-`end` rows: [16 rows x 128 B] per 128-channel group
+      for (int grp = 0; grp < 2; ++grp) {
+        tma_load_2d(wse(1, grp), &tm_wse_lo, wse_full, grp * 128, a.w2_row0 + 256);
+        tma_load_2d(wse(1, 2 + grp), &tm_wse_l8, wse_full, grp * 128, a.w2_row0 + 256);
+      }
+    if (a.has_res && F8) {
+      // acts hi live in TMEM, so the A-ring units 0..3 are free once GEMM1 has completed: the hi tiles of x_old go
+      // there right away; the lo tiles follow as GEMM2 releases the e5m2 acts tiles of each 128-channel group
+      static_assert(!F8 || L_ACTS_TMEM, "f16f8 keeps the fp16 acts plane in tensor memory");
+      tma_prefetch_desc(&tm_x_lo);
+      mbar_wait(acc1_full, 0);
+      for (int kb = 0; kb < 4; ++kb) {
+        mbar_arrive_expect_tx(&xold_full[kb], 2 * TILE_A);
+        tma_load_3d(slot(kb), &tm_x_hi, &xold_full[kb], kb * 64, t0, b);
+      }
+      for (int grp = 0; grp < 2; ++grp) {
+        mbar_wait(&g2_done[grp], 0);
+        for (int kb = 2 * grp; kb < 2 * grp + 2; ++kb)
+          tma_load_3d(slot(lo_unit(kb)), &tm_x_lo, &xold_full[kb], kb * 64, t0, b);
+      }
+    }
+    if (a.has_res && !F8) {
       tma_prefetch_desc(&tm_x_lo);
       for (int kb = 0; kb < 4; ++kb) {
         mbar_wait(&g2_done[kb], 0);
@@ -520,8 +590,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           act[4 * q + 2] = gate<NPASS>(__uint_as_float(cur[4 * q + 2]) + bt.z, __uint_as_float(cur[16 + 4 * q + 2]) + bs.z);
           act[4 * q + 3] = gate<NPASS>(__uint_as_float(cur[4 * q + 3]) + bt.w, __uint_as_float(cur[16 + 4 * q + 3]) + bs.w);
         }
-        if (L_ACTS_TMEM) store_split16_tmem<X3, F8>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
-        else store_split16<X3, F8>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        if (F8) store_split16_tmem_f8(act, trow + L_ACOL(c), slot(4 + (c >> 3)), slot(6 + (c >> 3)), row, c & 7);
+        else if (L_ACTS_TMEM) store_split16_tmem<X3, false>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);
+        else store_split16<X3, false>(act, slot(c >> 2), slot(4 + (c >> 2)), row, (c & 3) * 2);
       }
     }
     if (L_ACTS_TMEM) tmem_wait_st();
@@ -575,7 +646,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         tmem_wait16(cur);
         if (i + 1 < L_CPG) tmem_issue16(trow + L_D2_RES + (c + 1) * 16, buf[(i + 1) & 1]);
         uint8_t* thi = slot(c >> 2);
-        uint8_t* tlo = slot(4 + (c >> 2));
+        uint8_t* tlo = slot(lo_unit(c >> 2));
         const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);
         const uint4 h0 = *reinterpret_cast<const uint4*>(thi + o0), h1 = *reinterpret_cast<const uint4*>(thi + o1);
         const uint4 l0 = *reinterpret_cast<const uint4*>(tlo + o0), l1 = *reinterpret_cast<const uint4*>(tlo + o1);
@@ -606,7 +677,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           if (quarter == 0 && lane == 0) {
             const int kb = c >> 2;
             tma_store_3d(&tm_xo_hi, slot(kb), kb * 64, t0, b);
-            tma_store_3d(&tm_xo_lo, slot(4 + kb), kb * 64, t0, b);
+            tma_store_3d(&tm_xo_lo, slot(lo_unit(kb)), kb * 64, t0, b);
             if (F8 && i == L_CPG - 1) {
               tma_store_3d(&tm_xo_l8, slot(8 + grp), grp * 128, t0, b);
               tma_store_3d(&tm_xo_h8, slot(10 + grp), grp * 128, t0, b);
@@ -685,14 +756,20 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
   if (int r = map_2d(&tw1_hi, w->w1_hi, d.K1, fl * 2 * d.C, 256)) return r;
   if (int r = map_2d(&tw1_lo, npass == 2 ? w->w1_hi : w->w1_lo, d.K1, fl * 2 * d.C, 256)) return r;   // f16f8 has no w1 lo plane
   if (int r = map_2d(&tw2_hi, w->w2_hi, d.C, fl * d.N2, 256)) return r;
-  if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 256)) return r;
+  if (npass != 2) { if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 256)) return r; }
   if (int r = map_2d(&tse_hi, w->w2_hi, d.C, fl * d.N2, 16)) return r;
-  if (int r = map_2d(&tse_lo, w->w2_lo, d.C, fl * d.N2, 16)) return r;
+  if (npass != 2) { if (int r = map_2d(&tse_lo, w->w2_lo, d.C, fl * d.N2, 16)) return r; }
   if (int r = map_act(&to_hi, x_out, d.C, d.Tp, d.B)) return r;
   if (int r = map_act(&to_lo, x_out + plane, d.C, d.Tp, d.B)) return r;
   // e5m2 planes (CWG_MODE_F16F8): x = [fp16 hi][fp16 lo][e5m2 lo*2^P][e5m2 hi*2^-Q], H2 = [fp16 hi][e5m2 lo*2^P][e5m2 hi*2^-Q]
   CUtensorMap tx_l8 = tx_hi, tx_h8 = tx_hi, th_l8 = tx_hi, th_h8 = tx_hi, tw1_h8 = tx_hi, tw1_l8 = tx_hi, to_l8 = tx_hi, to_h8 = tx_hi;
+  CUtensorMap tw2_l8 = tx_hi, tse_l8 = tx_hi;
   if (npass == 2) {
+    // the e5m2 planes of w2: hi*2^-P through the tw2_lo / tse_lo parameters, lo*2^Q through tw2_l8 / tse_l8
+    if (int r = map_2d8(&tw2_lo, w->w2_h8, d.C, fl * d.N2, 256)) return r;
+    if (int r = map_2d8(&tse_lo, w->w2_h8, d.C, fl * d.N2, 16)) return r;
+    if (int r = map_2d8(&tw2_l8, w->w2_l8, d.C, fl * d.N2, 256)) return r;
+    if (int r = map_2d8(&tse_l8, w->w2_l8, d.C, fl * d.N2, 16)) return r;
     const uint8_t* xi8 = reinterpret_cast<const uint8_t*>(x_in) + 4 * plane;
     uint8_t* xo8 = reinterpret_cast<uint8_t*>(x_out) + 4 * plane;
     const uint8_t* h8 = reinterpret_cast<const uint8_t*>(h2) + 2 * hplane;
@@ -719,7 +796,7 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
     if (int r = set_smem(k_layer_tc<NP>, L_SMEM)) return r;                                                           \
     k_layer_tc<NP><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, \
                                                    tse_lo, to_hi, to_lo, tx_l8, tx_h8, th_l8, th_h8, tw1_h8, tw1_l8,  \
-                                                   to_l8, to_h8, a);                                                  \
+                                                   to_l8, to_h8, tw2_l8, tse_l8, a);                                  \
   } while (0)
   if (npass == 3) CWG_LAUNCH_LAYER(3);
   else if (npass == 2) CWG_LAUNCH_LAYER(2);

@@ -75,6 +75,7 @@ constexpr uint32_t IDESC_N16 = umma_idesc_bf16(128, 16);
 constexpr uint32_t IDESC_F16_N256 = umma_idesc_f16(128, 256);
 constexpr uint32_t IDESC_F16_N16 = umma_idesc_f16(128, 16);
 constexpr uint32_t IDESC_E5M2_N256 = umma_idesc_e5m2(128, 256);
+constexpr uint32_t IDESC_E5M2_N16 = umma_idesc_e5m2(128, 16);
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   uint32_t a = smem_u32(p);
@@ -150,13 +151,12 @@ __device__ __forceinline__ void store_split16_tmem(const float* v, uint32_t tmem
 __device__ __forceinline__ void store_split16_f8(const float* v, uint8_t* tile_hi, uint8_t* tile_lo, uint8_t* tile_l8,
                                                  uint8_t* tile_h8, int row, int chunk0_16, int chunk_8) {
   uint32_t hi[8], lo[8];
-  float d[16], h[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    float h0, h1;
     hi[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
-    unpack2<true>(hi[i], h[2 * i], h[2 * i + 1]);
-    d[2 * i] = v[2 * i] - h[2 * i]; d[2 * i + 1] = v[2 * i + 1] - h[2 * i + 1];
-    lo[i] = pack_f16x2(d[2 * i], d[2 * i + 1]);
+    unpack2<true>(hi[i], h0, h1);
+    lo[i] = pack_f16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
   }
   if (tile_hi) {
     *reinterpret_cast<uint4*>(tile_hi + sw128_offset(row, chunk0_16)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -169,8 +169,30 @@ __device__ __forceinline__ void store_split16_f8(const float* v, uint8_t* tile_h
   uint32_t l8[4], h8[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    l8[i] = pack_e5m2x4(d[4 * i] * F8_LO_SCALE, d[4 * i + 1] * F8_LO_SCALE, d[4 * i + 2] * F8_LO_SCALE, d[4 * i + 3] * F8_LO_SCALE);
-    h8[i] = pack_e5m2x4(h[4 * i] * F8_HI_SCALE, h[4 * i + 1] * F8_HI_SCALE, h[4 * i + 2] * F8_HI_SCALE, h[4 * i + 3] * F8_HI_SCALE);
+    l8[i] = e5m2x4_from_f16x2(lo[2 * i], lo[2 * i + 1], F16X2_2P6);
+    h8[i] = e5m2x4_from_f16x2(hi[2 * i], hi[2 * i + 1], F16X2_2M8);
+  }
+  *reinterpret_cast<uint4*>(tile_l8 + sw128_offset(row, chunk_8)) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+  *reinterpret_cast<uint4*>(tile_h8 + sw128_offset(row, chunk_8)) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+}
+
+// CWG_MODE_F16F8 gate output: fp16 hi packed into 8 TMEM columns (A operand of the fp16 ".ts" MMAs) and the two e5m2
+// correction planes as one 16-byte chunk each of [rows x 128 B] shared-memory tiles.
+__device__ __forceinline__ void store_split16_tmem_f8(const float* v, uint32_t tmem_hi, uint8_t* tile_l8, uint8_t* tile_h8,
+                                                      int row, int chunk_8) {
+  uint32_t hi[8], lo[8], l8[4], h8[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float h0, h1;
+    hi[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    unpack2<true>(hi[i], h0, h1);
+    lo[i] = pack_f16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+  }
+  tmem_st8(tmem_hi, hi);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    l8[i] = e5m2x4_from_f16x2(lo[2 * i], lo[2 * i + 1], F16X2_2P6);
+    h8[i] = e5m2x4_from_f16x2(hi[2 * i], hi[2 * i + 1], F16X2_2M8);
   }
   *reinterpret_cast<uint4*>(tile_l8 + sw128_offset(row, chunk_8)) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
   *reinterpret_cast<uint4*>(tile_h8 + sw128_offset(row, chunk_8)) = make_uint4(h8[0], h8[1], h8[2], h8[3]);

@@ -246,8 +246,8 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
             out[name + "_f32"] = arr.astype(np.float32)
         if "f16f8" in planes:
             out[name + "_hi"], out[name + "_lo"] = split_f16(arr)
-            if name == "w1":
-                out["w1_h8"], out["w1_l8"] = f8_correction_planes(arr)
+            if name in ("w1", "w2"):          # GEMMs issued as one fp16 pass + two e5m2 correction passes
+                out[name + "_h8"], out[name + "_l8"] = f8_correction_planes(arr)
         elif "hi" in planes or "lo" in planes:
             hi, lo = split_hi_lo(arr)
             out[name + "_hi"] = hi

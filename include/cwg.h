@@ -40,7 +40,7 @@ extern "C" {
 #define CWG_MODE_F16F8  3   /* fp32-accurate at 2 MMA passes instead of 3 (256-channel classic model): operands split into
                                fp16 hi + lo; the in_layer GEMM issues hi*hi in fp16 and the two cross terms as e5m2 fp8
                                MMAs (twice the rate): a*w ~= a16*w16 + e5m2(a_lo*2^6)*e5m2(w16*2^-6) + e5m2(a16*2^-8)*e5m2(w_lo*2^8);
-                               the small cond and res/skip GEMMs use three fp16 products                                 */
+                               the res/skip GEMM likewise, the small cond GEMM uses three fp16 products                                */
 
 #define CWG_EO_PAD 16       /* padded width of the folded `end` output (2*n_half <= 16)              */
 #define CWG_MAX_GROUP 16    /* n_group <= 16                                                         */
@@ -84,6 +84,8 @@ typedef struct cwg_weights {
   /* CWG_MODE_F16F8 only (there *_hi / *_lo are fp16 planes): e5m2 planes of w1, same shape as w1_hi */
   const uint8_t*  w1_h8;        /* e5m2(fp16(w1) * 2^-6)                                */
   const uint8_t*  w1_l8;        /* e5m2((w1 - fp16(w1)) * 2^8)                          */
+  const uint8_t*  w2_h8;        /* the same two planes of w2 ([F][L][N2][C])            */
+  const uint8_t*  w2_l8;
 } cwg_weights;
 
 int         cwg_abi_version(void);

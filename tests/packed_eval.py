@@ -61,9 +61,9 @@ def packed_infer(pk, cfg: PackConfig, mel, z, sigma, emulate=None, cond_bias=Non
             return (full, None, None)
         if emulate == "f16f8":
             hi = pk[name + "_hi"][idx].view(np.float16).astype(np.float64)
-            if name == "w1":
-                return (None, hi, (e5m2_bits_to_f32(pk["w1_h8"][idx]).astype(np.float64),
-                                   e5m2_bits_to_f32(pk["w1_l8"][idx]).astype(np.float64)))
+            if name in ("w1", "w2"):
+                return (None, hi, (e5m2_bits_to_f32(pk[name + "_h8"][idx]).astype(np.float64),
+                                   e5m2_bits_to_f32(pk[name + "_l8"][idx]).astype(np.float64)))
             return (None, hi, pk[name + "_lo"][idx].view(np.float16).astype(np.float64))
         hi = bf16_bits_to_f32(pk[name + "_hi"][idx]).astype(np.float64)
         lo = bf16_bits_to_f32(pk[name + "_lo"][idx]).astype(np.float64)
