@@ -455,15 +455,16 @@ def main():
         "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
         # capture committed in profiles/r1c_ncu_summary.txt (same command, same shapes)
-        "traffic": {"bf16x3": 1.409e9, "bf16": 1.152e9}.get(args.precision) if (B, Tm) == (16, 861) else None,
+        "traffic": {"f16f8": 1.870e9, "bf16x3": 1.395e9, "bf16": 1.155e9}.get(args.precision) if (B, Tm) == (16, 861) else None,
         "traffic_unit": "bytes/launch",
         "algorithmic_bytes_per_launch": float(steps_per_launch * {"bf16x3": 3200, "bf16": 2688, "ffma": 0, "f16f8": 4224}[args.precision]),
-        "ncu_tensor_pipe_active_pct": {"bf16x3": 61.6, "bf16": 51.0}.get(args.precision),
+        "ncu_tensor_pipe_active_pct": {"f16f8": 49.3, "bf16x3": 66.4, "bf16": 51.6}.get(args.precision),
         "launches_timed": int(layer_ms.size), "avg_launch_ms": float(layer_avg_ms.mean()),
         "layer_share_of_step": float(layer_avg_ms.sum() / (ms_total / args.steps)),
         "mma_passes": passes, "issued_mma_tflops": achieved * passes,
         "note": "achieved = reference's dense FLOPs per layer launch (SURVEY 8d) / CUDA-event duration; "
-                "bf16x3 issues 3 bf16 MMAs per algorithmic MAC, so frac <= 1/3 by construction in that mode",
+                "bf16x3 issues 3 bf16 MMAs per algorithmic MAC (frac <= 1/3 by construction), f16f8 one fp16 MMA plus "
+                "two e5m2 MMAs at twice the rate (frac <= 1/2 against the bf16 peak)",
     }
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
