@@ -47,7 +47,7 @@ int check_mode(const cwg_config* c, int mode, bool cond_gemm = true) {
   CWG_REQUIRE(mode == CWG_MODE_FFMA || mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16 || mode == CWG_MODE_F16F8,
               "unknown mode %d", mode);
   if (mode == CWG_MODE_F16F8)
-    CWG_REQUIRE(c->n_channels == 256 && cond_gemm, "CWG_MODE_F16F8 is built for the 256-channel classic model");
+    CWG_REQUIRE(c->n_channels == 256, "CWG_MODE_F16F8 is built for the 256-channel layer kernel");
   if (mode != CWG_MODE_FFMA) {
     CWG_REQUIRE((c->n_channels == 256 || c->n_channels == 512) && c->cond_hidden == 256 && c->kernel_size == 3,
                 "tensor-core modes are built for n_channels in {256, 512}, cond_hidden=256, kernel_size=3 "
@@ -278,6 +278,7 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   if (int r = ax_check(cfg, mode, batch, frames, t_samples)) return r;
   CWG_REQUIRE(w && w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b && w->winv, "missing weight arrays");
   if (mode == CWG_MODE_FFMA) CWG_REQUIRE(w->w1_f32 && w->w2_f32, "fp32 weight planes missing");
+  else if (mode == CWG_MODE_F16F8) CWG_REQUIRE(w->w1_hi && w->w1_h8 && w->w1_l8 && w->w2_hi && w->w2_h8 && w->w2_l8, "fp16 / e5m2 weight planes missing");
   else CWG_REQUIRE(w->w1_hi && w->w2_hi && w->w1_lo && w->w2_lo, "bf16 hi/lo weight planes missing");
   CWG_REQUIRE(mel && z && audio && pad_frames >= 0, "bad tensor arguments");
   CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
@@ -287,8 +288,8 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool tc = mode != CWG_MODE_FFMA;
-  const int npass = mode == CWG_MODE_BF16X3 ? 3 : 1;
-  const int xfmt = tc ? 1 : 0;
+  const int npass = mode_npass(mode);
+  const int xfmt = mode_xfmt(mode);
   const int F = cfg->n_flows, L = cfg->n_layers;
   void* x0 = tc ? (void*)ws.xb[0] : (void*)ws.x[0];
   void* h2 = tc ? (void*)ws.h2b : (void*)ws.h2;

@@ -366,6 +366,13 @@ __global__ void k_mel_up(const float* __restrict__ mel, void* __restrict__ out, 
   }
   if (XFMT == 0) {
     reinterpret_cast<float*>(out)[i] = v;
+  } else if (XFMT == 2) {                     // CWG_MODE_F16F8 cond planes: fp16 hi, e5m2(lo * 2^P), e5m2(hi * 2^-Q)
+    const __half h = __float2half_rn(v);
+    const float hf = __half2float(h);
+    reinterpret_cast<__half*>(out)[i] = h;
+    uint8_t* p8 = reinterpret_cast<uint8_t*>(out) + 2 * n;
+    p8[i] = (uint8_t)(sm100::pack_e5m2x4((v - hf) * F8_LO_SCALE, 0.f, 0.f, 0.f) & 0xffu);
+    p8[n + i] = (uint8_t)(sm100::pack_e5m2x4(hf * F8_HI_SCALE, 0.f, 0.f, 0.f) & 0xffu);
   } else {
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out);
     __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -380,7 +387,8 @@ int launch_mel_up(int xfmt, const float* mel, void* out, int B, int M, int frame
                   int linear, cudaStream_t s) {
   long long n = (long long)B * Tp * H;
   unsigned grid = (unsigned)((n + 255) / 256);
-  if (xfmt == 0) k_mel_up<0><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
+  if (xfmt == 2) k_mel_up<2><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
+  else if (xfmt == 0) k_mel_up<0><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
   else           k_mel_up<1><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;

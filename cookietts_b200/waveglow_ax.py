@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _cabi
 from .ax_frontend import AxFrontEndMixin
-from .packing import in_layer_weight_bias, PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
+from .packing import in_layer_weight_bias, split_f16, f8_correction_planes, PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
 
 
 def permute_height_index(k: int, h: int):
@@ -79,7 +79,10 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
     for name, arr in (("w1", w1), ("w2", w2)):
         if "f32" in planes:
             out[name + "_f32"] = arr.astype(np.float32)
-        if "hi" in planes:
+        if "f16f8" in planes:                                  # CWG_MODE_F16F8 (packing.py)
+            out[name + "_hi"], out[name + "_lo"] = split_f16(arr)
+            out[name + "_h8"], out[name + "_l8"] = f8_correction_planes(arr)
+        elif "hi" in planes:
             out[name + "_hi"], out[name + "_lo"] = split_hi_lo(arr)
     return out
 
@@ -208,7 +211,8 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         # tensor-core kernels are built for a 256-wide cond operand; the fp32 path takes it unpadded
         pc = PackConfig(cond_hidden=256 if tensor else self._base["n_mel"], **self._base)
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
-        pk = pack_ax_state_dict(sd, pc, self.channel_mixing, planes=("hi", "lo") if tensor else ("f32",),
+        planes = {"ffma": ("f32",), "f16f8": ("f16f8",)}.get(self.precision, ("hi", "lo"))
+        pk = pack_ax_state_dict(sd, pc, self.channel_mixing, planes=planes,
                                 cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
         for name, arr in pk.items():

@@ -14,7 +14,8 @@ from tests.helpers import max_abs
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"ffma": dict(max_abs=1e-4, snr=100.0), "bf16x3": dict(max_abs=1e-3, snr=60.0), "bf16": dict(max_abs=5e-2, snr=40.0)}
+TOL = {"ffma": dict(max_abs=1e-4, snr=100.0), "bf16x3": dict(max_abs=1e-3, snr=60.0), "bf16": dict(max_abs=5e-2, snr=40.0),
+       "f16f8": dict(max_abs=1e-3, snr=60.0)}
 
 
 def run(name, precision):
@@ -42,7 +43,8 @@ def test_frontend_fp32_cuda_cores(name):
 
 @pytest.mark.parametrize("name,precision", [("axfe_256", "bf16x3"), ("axfe_256", "bf16"),
                                             ("axfe_waveflow", "bf16x3"), ("axfe_waveflow", "bf16"),
-                                            ("axfe_separable_256", "bf16x3"), ("axfe_waveflow_separable", "bf16x3")])
+                                            ("axfe_separable_256", "bf16x3"), ("axfe_waveflow_separable", "bf16x3"),
+                                            ("axfe_256", "f16f8"), ("axfe_separable_256", "f16f8")])
 def test_frontend_tensor_cores(name, precision):
     out, ref = run(name, precision)
     check(out, ref, precision)

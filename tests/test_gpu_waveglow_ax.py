@@ -15,7 +15,8 @@ from tests.helpers import GOLDEN_DIR, max_abs
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"ffma": dict(max_abs=1e-4, snr=100.0), "bf16x3": dict(max_abs=1e-3, snr=60.0), "bf16": dict(max_abs=5e-2, snr=40.0)}
+TOL = {"ffma": dict(max_abs=1e-4, snr=100.0), "bf16x3": dict(max_abs=1e-3, snr=60.0), "bf16": dict(max_abs=5e-2, snr=40.0),
+       "f16f8": dict(max_abs=1e-3, snr=60.0)}
 
 
 def run(name, precision):
@@ -42,7 +43,7 @@ def test_ax_fp32_cuda_cores(name):
     assert max_abs(aud, g["infer_ref_fp64"]) <= TOL["ffma"]["max_abs"]
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16", "f16f8"])
 def test_ax_tensor_cores(precision):
     inv, aud, g = run("waveglow_ax_256", precision)
     assert np.isfinite(inv).all()
