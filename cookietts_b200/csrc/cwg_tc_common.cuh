@@ -202,10 +202,15 @@ __device__ __forceinline__ void store_split16_tmem_f8(const float* v, uint32_t t
 template <int NPASS>
 __device__ __forceinline__ float gate(float a, float b) {
   if (NPASS != 1) {
-    // (1-u)/((1+u)(1+v)), u = e^-2a, v = e^-b : 2 ex2 + 1 rcp, ~1e-6 relative
+    // (1-u)/((1+u)(1+v)), u = e^-2a, v = e^-b : 2 ex2 + 1 rcp, ~1e-6 relative.  Raw .ftz MUFU forms: __expf /
+    // __fdividef wrap each MUFU in range-scaling FSETP / predicated FMUL pairs that only matter below 2^-126.
+    // a <= -15 saturates (tanh = -1 to 1e-13); v = inf (b < -88) gives 1/inf = 0, the correct limit.
     a = fmaxf(a, -15.f);
-    float u = __expf(-2.f * a), v = __expf(-b);
-    return __fdividef(1.f - u, (1.f + u) * (1.f + v));
+    float u, v, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(a * -2.8853900817779268f));   // -2 * log2(e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(b * -1.4426950408889634f));   // -log2(e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((1.f + u) * (1.f + v)));
+    return (1.f - u) * r;
   } else {
     float t, s;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(a));
