@@ -455,10 +455,10 @@ def main():
         "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the ncu --set full
         # capture committed in profiles/r1c_ncu_summary.txt (same command, same shapes)
-        "traffic": {"f16f8": 1.870e9, "bf16x3": 1.395e9, "bf16": 1.155e9}.get(args.precision) if (B, Tm) == (16, 861) else None,
+        "traffic": {"f16f8": 1.871e9, "bf16x3": 1.398e9, "bf16": 1.151e9}.get(args.precision) if (B, Tm) == (16, 861) else None,
         "traffic_unit": "bytes/launch",
         "algorithmic_bytes_per_launch": float(steps_per_launch * {"bf16x3": 3200, "bf16": 2688, "ffma": 0, "f16f8": 4224}[args.precision]),
-        "ncu_tensor_pipe_active_pct": {"f16f8": 49.3, "bf16x3": 66.4, "bf16": 51.6}.get(args.precision),
+        "ncu_tensor_pipe_active_pct": {"f16f8": 53.4, "bf16x3": 67.9, "bf16": 51.4}.get(args.precision),
         "launches_timed": int(layer_ms.size), "avg_launch_ms": float(layer_avg_ms.mean()),
         "layer_share_of_step": float(layer_avg_ms.sum() / (ms_total / args.steps)),
         "mma_passes": passes, "issued_mma_tflops": achieved * passes,

@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
         uint32_t l8[2], h8[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          l8[i] = sm100::pack_e5m2x4(df[4 * i] * F8_LO_SCALE, df[4 * i + 1] * F8_LO_SCALE, df[4 * i + 2] * F8_LO_SCALE, df[4 * i + 3] * F8_LO_SCALE);
-          h8[i] = sm100::pack_e5m2x4(hf[4 * i] * F8_HI_SCALE, hf[4 * i + 1] * F8_HI_SCALE, hf[4 * i + 2] * F8_HI_SCALE, hf[4 * i + 3] * F8_HI_SCALE);
+          l8[i] = sm100::e5m2x4_from_f16x2(l[2 * i], l[2 * i + 1], sm100::F16X2_2P6);
+          h8[i] = sm100::e5m2x4_from_f16x2(h[2 * i], h[2 * i + 1], sm100::F16X2_2M8);
         }
         *reinterpret_cast<uint2*>(p8 + idx) = make_uint2(l8[0], l8[1]);
         *reinterpret_cast<uint2*>(p8 + plane + idx) = make_uint2(h8[0], h8[1]);
