@@ -563,7 +563,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
     {   // biases -> smem (read as broadcast float4 in the epilogues); off the prologue's critical path
       const int e = threadIdx.x - 128;
-      if (e < 256) { b1s[e] = __ldg(a.b1 + e); b1s[256 + e] = __ldg(a.b1 + 256 + e); b2s[e] = __ldg(a.b2 + e); }
+      if (e < 256) {     // gate biases pre-multiplied by the argument scales of gate_fused
+        b1s[e] = __ldg(a.b1 + e) * GateK<NPASS>::KA; b1s[256 + e] = __ldg(a.b1 + 256 + e) * GateK<NPASS>::KB;
+        b2s[e] = __ldg(a.b2 + e);
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(L_EPI_THREADS) : "memory");
     }
     // gate: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) -> bf16 planes in slots 0..7 (GEMM2's A operand)
@@ -585,10 +588,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 bt = b1t[c * 4 + q], bs = b1g[c * 4 + q];
-          act[4 * q + 0] = gate<NPASS>(__uint_as_float(cur[4 * q + 0]) + bt.x, __uint_as_float(cur[16 + 4 * q + 0]) + bs.x);
-          act[4 * q + 1] = gate<NPASS>(__uint_as_float(cur[4 * q + 1]) + bt.y, __uint_as_float(cur[16 + 4 * q + 1]) + bs.y);
-          act[4 * q + 2] = gate<NPASS>(__uint_as_float(cur[4 * q + 2]) + bt.z, __uint_as_float(cur[16 + 4 * q + 2]) + bs.z);
-          act[4 * q + 3] = gate<NPASS>(__uint_as_float(cur[4 * q + 3]) + bt.w, __uint_as_float(cur[16 + 4 * q + 3]) + bs.w);
+          act[4 * q + 0] = gate_fused<NPASS>(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[16 + 4 * q + 0]), bt.x, bs.x);
+          act[4 * q + 1] = gate_fused<NPASS>(__uint_as_float(cur[4 * q + 1]), __uint_as_float(cur[16 + 4 * q + 1]), bt.y, bs.y);
+          act[4 * q + 2] = gate_fused<NPASS>(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[16 + 4 * q + 2]), bt.z, bs.z);
+          act[4 * q + 3] = gate_fused<NPASS>(__uint_as_float(cur[4 * q + 3]), __uint_as_float(cur[16 + 4 * q + 3]), bt.w, bs.w);
         }
         if (F8) store_split16_tmem_f8(act, trow + L_ACOL(c), slot(4 + (c >> 3)), slot(6 + (c >> 3)), row, c & 7);
         else if (L_ACTS_TMEM) store_split16_tmem<X3, false>(act, trow + L_ACOL(c), slot(4 + (c >> 2)), row, (c & 3) * 2);

@@ -219,6 +219,29 @@ __device__ __forceinline__ float gate(float a, float b) {
   }
 }
 
+// The same with the bias add folded into the argument scaling: pa, pb are raw accumulator values, ba / bb the biases
+// pre-multiplied by GATE_KA / GATE_KB (done once when the biases are staged in shared memory).
+template <int NPASS> struct GateK {
+  static constexpr float KA = NPASS != 1 ? -2.8853900817779268f : 1.f;     // -2 log2(e) | tanh.approx argument
+  static constexpr float KB = NPASS != 1 ? -1.4426950408889634f : 0.5f;    // -log2(e)   | sigmoid(b) = .5 + .5 tanh(b/2)
+};
+template <int NPASS>
+__device__ __forceinline__ float gate_fused(float pa, float pb, float ba, float bb) {
+  const float ea = fmaf(pa, GateK<NPASS>::KA, ba), eb = fmaf(pb, GateK<NPASS>::KB, bb);
+  if (NPASS != 1) {
+    float u, v, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(fminf(ea, 43.280851f)));   // a >= -15
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(eb));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((1.f + u) * (1.f + v)));
+    return (1.f - u) * r;
+  } else {
+    float t, s;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(ea));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(s) : "f"(eb));
+    return t * fmaf(s, 0.5f, 0.5f);
+  }
+}
+
 __device__ __forceinline__ void ring_advance(int& slot, uint32_t& phase, int n) {
   if (++slot == n) { slot = 0; phase ^= 1u; }
 }

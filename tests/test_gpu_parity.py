@@ -143,9 +143,10 @@ def test_batch_items_are_independent():
     assert torch.equal(alone, out[1:2])
 
 
-def test_ragged_and_minimal_lengths():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_ragged_and_minimal_lengths(precision):
     """T_mel = 1 (32 group-steps, far below one 128-step tile) and lengths that leave ragged tiles."""
-    ref_m, m = _model("ffma"), _model("bf16x3")
+    ref_m, m = _model("ffma"), _model(precision)
     for t_mel in (1, 3, 5, 37):
         mel, z = _inputs(2, t_mel, seed=t_mel)
         ref = ref_m.infer(mel, sigma=1.0, z=z)
@@ -155,8 +156,9 @@ def test_ragged_and_minimal_lengths():
     assert m.infer(torch.zeros(2, 80, 0, device="cuda")).shape == (2, 0)
 
 
-def test_internal_z_draw_and_sigma_zero():
-    m = _model("bf16x3")
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_internal_z_draw_and_sigma_zero(precision):
+    m = _model(precision)
     mel, z = _inputs(1, 20, seed=2)
     a = m.infer(mel, sigma=0.7)              # z drawn internally
     assert a.shape == (1, 20 * 256) and torch.isfinite(a).all()
@@ -181,10 +183,11 @@ def test_weight_update_invalidates_packed_cache():
     assert torch.equal(b, c)
 
 
-def test_infer_is_cuda_graph_capturable():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_infer_is_cuda_graph_capturable(precision):
     """The C ABI never allocates or synchronises and passes tensor maps by value, so a whole infer
     (122 launches) can be captured into a CUDA graph and replayed on new inputs in the same buffers."""
-    m = _model("bf16x3")
+    m = _model(precision)
     mel, z = _inputs(1, 40, seed=11)
     ref = m.infer(mel, sigma=0.666, z=z)                      # warm-up: packs weights, sizes the workspace
     static_mel, static_z = mel.clone(), z.clone()
