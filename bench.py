@@ -156,8 +156,8 @@ def run_waveflow(args):
     import torch
     import torch.distributed as dist
     from cookietts_b200 import WaveFlow
-    from oracle.make_golden_waveflow import reference_kwargs
-    from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict
+    from cookietts_b200.synthetic import WaveFlowConfig, waveflow_reference_kwargs as reference_kwargs
+    from cookietts_b200.synthetic import waveflow_state_dict as synthetic_state_dict
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -226,7 +226,7 @@ def run_longform(args):
     import torch.distributed as dist
     from cookietts_b200 import WaveGlow
     from cookietts_b200.parallel import infer_long_sharded, infer_long, plan_chunks
-    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict
+    from cookietts_b200.synthetic import ModelConfig as OracleConfig, synthetic_state_dict
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -324,7 +324,7 @@ def main():
     import torch
     import torch.distributed as dist
     from cookietts_b200 import WaveGlow
-    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict
+    from cookietts_b200.synthetic import ModelConfig as OracleConfig, synthetic_state_dict   # checkpoint generator, not the oracle
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -44,18 +44,7 @@ def load_reference_ax():
     return WaveGlow
 
 
-def reference_kwargs(cfg: WaveFlowConfig) -> dict:
-    wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size_w=cfg.kernel_size_w,
-              kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=None, n_layers_dilations_h=1,
-              speaker_embed_dim=0, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
-              cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv,
-              res_skip=True, merge_res_skip=False, upsample_mode=cfg.upsample_mode)
-    return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
-                n_early_every=cfg.n_flows * 2, n_early_size=2, memory_efficient=0.0, spect_scaling=False,
-                upsample_mode="normal", upsample_first=True, speaker_embed=0, cond_layers=0,
-                cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
-                cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
-                sampling_rate=22050, channel_mixing="permuteheight", mix_first=True, waveflow=True)
+from cookietts_b200.synthetic import waveflow_reference_kwargs as reference_kwargs  # noqa: E402
 
 
 CASES = {

@@ -27,19 +27,7 @@ import numpy as np
 from .waveglow_oracle import weight_norm_effective
 
 
-@dataclass
-class WaveFlowConfig:
-    n_mel_channels: int = 80
-    n_flows: int = 8
-    n_group: int = 16            # squeeze height h
-    n_layers: int = 8
-    n_channels: int = 128
-    kernel_size_w: int = 3
-    kernel_size_h: int = 3
-    win_length: int = 1024
-    hop_length: int = 256
-    upsample_mode: str = "linear"   # WN_config['upsample_mode'] used by the model-level interpolate
-    seperable_conv: bool = False    # in_layer = Sequential(depthwise, pointwise), glow_ax.py:525-531
+from cookietts_b200.synthetic import WaveFlowConfig, waveflow_state_dict as synthetic_state_dict  # noqa: E402,F401
 
 
 def _w(sd, prefix, dtype):
@@ -176,35 +164,3 @@ def infer_with_z(sd, cfg: WaveFlowConfig, spect: np.ndarray, z: np.ndarray, sigm
     if artifact_trimming > 0:
         audio = audio[:, :-artifact_trimming * cfg.hop_length]           # :381-383
     return audio
-
-
-def synthetic_state_dict(cfg: WaveFlowConfig, seed: int = 1234, cond_in_channels=None) -> Dict[str, np.ndarray]:
-    """Seeded checkpoint with the reference ax/WaveFlow key layout (probe-printed: WN.{k}.WN.*,
-    4-D conv weights, no convinv parameters for permuteheight); `end` non-zero."""
-    cin = cond_in_channels or cfg.n_mel_channels
-    rs = np.random.RandomState(seed)
-    sd: Dict[str, np.ndarray] = {}
-    C, L, kh, kw = cfg.n_channels, cfg.n_layers, cfg.kernel_size_h, cfg.kernel_size_w
-
-    def wn(prefix, shape, fan_in):
-        bound = 1.0 / np.sqrt(fan_in)
-        v = rs.uniform(-bound, bound, size=shape).astype(np.float32)
-        norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=tuple(range(1, v.ndim)), keepdims=True))
-        sd[prefix + ".bias"] = rs.uniform(-bound, bound, size=(shape[0],)).astype(np.float32)
-        sd[prefix + ".weight_g"] = (norm * rs.uniform(0.8, 1.2, size=norm.shape)).astype(np.float32)
-        sd[prefix + ".weight_v"] = v
-
-    for k in range(cfg.n_flows):
-        p = f"WN.{k}.WN."
-        for i in range(L):
-            if cfg.seperable_conv:
-                wn(p + f"in_layers.{i}.0", (C, 1, kh, kw), kh * kw)
-                wn(p + f"in_layers.{i}.1", (2 * C, C, 1, 1), C)
-            else:
-                wn(p + f"in_layers.{i}", (2 * C, C, kh, kw), C * kh * kw)
-            wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1, 1), C)
-        wn(p + "start", (C, 1, 1, 1), 1)
-        sd[p + "end.weight"] = (rs.standard_normal((2, C, 1, 1)) * 0.02).astype(np.float32)
-        sd[p + "end.bias"] = (rs.standard_normal((2,)) * 0.02).astype(np.float32)
-        wn(p + "cond_layers.0", (2 * C * L, cin, 1), cin)
-    return sd

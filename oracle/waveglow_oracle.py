@@ -28,35 +28,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 
-@dataclass
-class OracleConfig:
-    """Constructor arguments of the reference `WaveGlow` (glow.py:226-227) that the
-    inverse pass depends on, plus `WN_config` (glow.py:116-117)."""
-    n_mel_channels: int = 80
-    n_flows: int = 12
-    n_group: int = 8
-    n_early_every: int = 4
-    n_early_size: int = 2
-    win_length: int = 1024
-    hop_length: int = 256
-    n_layers: int = 8
-    n_channels: int = 256
-    kernel_size: int = 3
-    speaker_embed_dim: int = 0
-    rezero: bool = False
-    cond_hidden: int = 256  # literal `hidden_dim = 256`, glow.py:153
-
-    def flow_channels(self) -> List[Tuple[int, int]]:
-        """(n_remaining_channels, n_half) per flow k, glow.py:251-264."""
-        out = []
-        n_half = self.n_group // 2
-        n_rem = self.n_group
-        for k in range(self.n_flows):
-            if k % self.n_early_every == 0 and k > 0:
-                n_half -= self.n_early_size // 2
-                n_rem -= self.n_early_size
-            out.append((n_rem, n_half))
-        return out
+from cookietts_b200.synthetic import ModelConfig as OracleConfig, synthetic_state_dict, synthetic_inputs  # noqa: E402,F401
 
 
 def weight_norm_effective(g: np.ndarray, v: np.ndarray) -> np.ndarray:
@@ -202,64 +174,6 @@ def infer_with_z(sd: Dict[str, np.ndarray], cfg: OracleConfig, mel: np.ndarray, 
             audio = np.concatenate([sigma * z_early[k], audio], axis=1)
     B = audio.shape[0]
     return np.ascontiguousarray(audio.transpose(0, 2, 1)).reshape(B, -1)  # :349
-
-
-# ----------------------------------------------------------------------------------------
-# Deterministic synthetic checkpoints (shared by the golden generator, tests and bench)
-# ----------------------------------------------------------------------------------------
-
-def synthetic_state_dict(cfg: OracleConfig, seed: int = 1234) -> Dict[str, np.ndarray]:
-    """A state_dict with the exact key/shape layout of the reference model
-    (glow.py:136-186,238-241,74-83), filled from a seeded
-    `numpy.random.RandomState` so every machine regenerates identical weights.
-    `end` is NOT zero (the reference zero-inits it, glow.py:141-144, which would make
-    the WN a no-op and parity vacuous)."""
-    rs = np.random.RandomState(seed)
-    sd: Dict[str, np.ndarray] = {}
-
-    def uni(shape, bound):
-        return rs.uniform(-bound, bound, size=shape).astype(np.float32)
-
-    def wn_conv(prefix, co, ci, k):
-        bound = 1.0 / np.sqrt(ci * k)
-        v = uni((co, ci, k), bound)
-        norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True))
-        sd[prefix + ".bias"] = uni((co,), bound)
-        sd[prefix + ".weight_g"] = (norm * rs.uniform(0.8, 1.2, size=norm.shape)).astype(np.float32)
-        sd[prefix + ".weight_v"] = v
-
-    M, G, C, L = cfg.n_mel_channels, cfg.n_group, cfg.n_channels, cfg.n_layers
-    bound = 1.0 / np.sqrt(M * cfg.win_length / cfg.hop_length)
-    sd["upsample.weight"] = uni((M, M, cfg.win_length), bound)
-    sd["upsample.bias"] = uni((M,), bound)
-    for k, (n_rem, n_half) in enumerate(cfg.flow_channels()):
-        q1, _ = np.linalg.qr(rs.standard_normal((n_rem, n_rem)))
-        q2, _ = np.linalg.qr(rs.standard_normal((n_rem, n_rem)))
-        W = q1 @ np.diag(rs.uniform(0.7, 1.4, size=n_rem)) @ q2
-        sd[f"convinv.{k}.conv.weight"] = W.astype(np.float32)[:, :, None]
-        p = f"WN.{k}"
-        wn_conv(p + ".start", C, n_half, 1)
-        wn_conv(p + ".cond_layers.0", cfg.cond_hidden, M * G + cfg.speaker_embed_dim, 1)
-        wn_conv(p + ".cond_layers.1", cfg.cond_hidden, cfg.cond_hidden, 1)
-        wn_conv(p + ".cond_layers.2", 2 * C * L, cfg.cond_hidden, 1)
-        for i in range(L):
-            wn_conv(p + f".in_layers.{i}", 2 * C, C, cfg.kernel_size)
-            wn_conv(p + f".res_skip_layers.{i}", 2 * C if i < L - 1 else C, C, 1)
-            if cfg.rezero:
-                sd[p + f".alpha_i.{i}"] = (rs.uniform(size=1) * 0.02 + 0.09).astype(np.float32)
-        sd[p + ".end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
-        sd[p + ".end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
-        if cfg.speaker_embed_dim:       # nn.Embedding(512, E) scaled by 0.05 at init, glow.py:131-134
-            sd[p + ".speaker_embed.weight"] = (rs.standard_normal((512, cfg.speaker_embed_dim)) * 0.5).astype(np.float32)
-    return sd
-
-
-def synthetic_inputs(cfg: OracleConfig, batch: int, t_mel: int, seed: int = 0):
-    """Synthetic mel = clamp(N(-5, 2^2), -11.5129, 2.0) and z ~ N(0,1)."""
-    rs = np.random.RandomState(seed)
-    mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, t_mel)) * 2.0 - 5.0, -11.5129, 2.0)
-    z = rs.standard_normal((batch, t_mel * cfg.hop_length))
-    return mel.astype(np.float32), z.astype(np.float32)
 
 
 def snr_db(ref: np.ndarray, test: np.ndarray) -> float:
