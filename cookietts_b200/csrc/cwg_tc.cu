@@ -173,6 +173,138 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------
+// cond GEMM as a 2-SM MMA (cta_group::2): a CTA pair computes 256 rows x 256 columns; each CTA stages its own A tile
+// and HALF of the weight tile, so the weight bytes every SM pulls through L2 halve.  Opt-in (CWG_COND_2SM=1): the
+// recipe the WN layer kernel needs next (DESIGN "Known limits" 1), validated here on the simplest GEMM of the path.
+// ------------------------------------------------------------------------------------------
+template <int NPASS>
+struct Cond2Cfg {
+  static constexpr int PL = NPASS != 1 ? 2 : 1;
+  static constexpr int STAGE = 2 * TILE_A * PL;                // per CTA: A 16 KB + B half 16 KB per plane
+  static constexpr int NST = 2;
+  static constexpr int STAGING = 4 * TILE_A;                   // epilogue staging, 128 columns at a time (64 KB)
+  static constexpr int SMEM = (NST * STAGE > STAGING ? NST * STAGE : STAGING) + 256 + 1024;
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(192, 1)
+k_cond_tc2(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,   // 128-row boxes
+           const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
+           const __grid_constant__ CUtensorMap tm_c_h8, CondArgs a) {
+  using Cfg = Cond2Cfg<NPASS>;
+  constexpr bool F8 = NPASS == 2;
+  constexpr uint32_t ID = F8 ? umma_idesc_f16(256, 256) : umma_idesc_bf16(256, 256);
+  constexpr int PIPE = Cfg::NST * Cfg::STAGE > Cfg::STAGING ? Cfg::NST * Cfg::STAGE : Cfg::STAGING;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PIPE);
+  uint64_t* empty = full + Cfg::NST;
+  uint64_t* acc_full = empty + Cfg::NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs), 1 = follower
+  const int p = blockIdx.y, m0 = blockIdx.x * 128;              // the pair = two neighbouring row tiles (cluster along x)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                           // both CTAs' barriers and TMEM exist
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // each CTA loads its own A rows and its half of the weight rows; all bytes are counted on the LEADER's barrier
+    tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* st = smem + s * Cfg::STAGE;
+      const uint32_t lbar = mapa_shared(&full[s], 0);
+      if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE);
+      tma_load_2d_2sm(st, &tm_a_hi, lbar, kb * 64, m0);
+      tma_load_2d_2sm(st + TILE_A, &tm_b_hi, lbar, kb * 64, a.w_row0 + p * 256 + (int)rank * 128);
+      if (NPASS != 1) {
+        tma_load_2d_2sm(st + 2 * TILE_A, &tm_a_lo, lbar, kb * 64, m0);
+        tma_load_2d_2sm(st + 3 * TILE_A, &tm_b_lo, lbar, kb * 64, a.w_row0 + p * 256 + (int)rank * 128);
+      }
+      ring_advance(s, ph, Cfg::NST);
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    int s = 0; uint32_t ph = 0;
+    auto kblock = [&](uint32_t a_addr, uint32_t b_addr, bool first) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_2sm(tmem, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), ID, (first && k == 0) ? 0u : 1u);
+    };
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after_sync();
+      const uint32_t st = smem_u32(smem + s * Cfg::STAGE);
+      kblock(st, st + TILE_A, kb == 0);
+      if (NPASS != 1) {
+        kblock(st + 2 * TILE_A, st + TILE_A, false);             // lo * hi
+        kblock(st, st + 3 * TILE_A, false);                      // hi * lo
+      }
+      umma_commit_2sm(&empty[s]);
+      ring_advance(s, ph, Cfg::NST);
+    }
+    umma_commit_2sm(acc_full);
+  } else if (warp >= 2) {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    int m = m0 + row;
+    int b = min(m / a.Tm, a.B - 1);
+    const float4* bias4 = reinterpret_cast<const float4*>(a.bias + (size_t)b * a.bias_bstride);
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+      for (int c = 8 * half; c < 8 * half + 8; ++c) {
+        float v[16];
+        tmem_ld16_sync(trow + c * 16, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 bb = __ldg(bias4 + c * 4 + q);
+          v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        }
+        uint8_t* thi = smem + ((c >> 2) & 1) * TILE_A;
+        if (F8) store_split16_f8(v, thi, nullptr, smem + 2 * TILE_A, smem + 3 * TILE_A, row, (c & 3) * 2, c & 7);
+        else store_split16<NPASS == 3>(v, thi, thi + 2 * TILE_A, row, (c & 3) * 2);
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        for (int j = 0; j < 2; ++j) {
+          tma_store_2d(&tm_c_hi, smem + j * TILE_A, p * 256 + (2 * half + j) * 64, m0);
+          if (NPASS == 3) tma_store_2d(&tm_c_lo, smem + (2 + j) * TILE_A, p * 256 + (2 * half + j) * 64, m0);
+        }
+        if (F8) {
+          tma_store_2d(&tm_c_lo, smem + 2 * TILE_A, p * 256 + half * 128, m0);
+          tma_store_2d(&tm_c_h8, smem + 3 * TILE_A, p * 256 + half * 128, m0);
+        }
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (warp == 2 && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                           // the pair releases TMEM together
+  if (warp == 1) { __syncwarp(); tmem_dealloc_2sm(tmem, 256); }
+}
+
+// ------------------------------------------------------------------------------------------
 // WN layer
 // ------------------------------------------------------------------------------------------
 struct LayerArgs {
@@ -732,6 +864,28 @@ int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, con
   a.bias = cond_bias + (size_t)flow * d.H; a.bias_bstride = d.F * d.H;
   a.M = (int)rows; a.Tm = d.Tm; a.B = d.B; a.w_row0 = flow * (int)ncol; a.nkb = d.KCp / 64;
   dim3 grid(d.P, (unsigned)((rows + 127) / 128));
+  static const int use_2sm = [] { const char* e = getenv("CWG_COND_2SM"); return e && e[0] == '1'; }();
+  if (use_2sm) {
+    CUtensorMap tb2_hi, tb2_lo;                                  // weight tiles in 128-row halves
+    if (int r = map_2d(&tb2_hi, w->cond_w_hi, d.KCp, (uint64_t)d.F * ncol, 128)) return r;
+    if (int r = map_2d(&tb2_lo, w->cond_w_lo, d.KCp, (uint64_t)d.F * ncol, 128)) return r;
+    // a row tile past the end is zero-filled / clipped by TMA
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((grid.y + 1) & ~1u, grid.x); lc.blockDim = dim3(192); lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+#define CWG_LAUNCH_COND2(NP)                                                                                     \
+    do {                                                                                                         \
+      lc.dynamicSmemBytes = Cond2Cfg<NP>::SMEM;                                                                  \
+      if (int r = set_smem(k_cond_tc2<NP>, Cond2Cfg<NP>::SMEM)) return r;                                        \
+      CWG_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_cond_tc2<NP>, ta_hi, ta_lo, tb2_hi, tb2_lo, tc_hi, tc_lo, tc_h8, a)); \
+    } while (0)
+    if (npass == 3) CWG_LAUNCH_COND2(3); else if (npass == 2) CWG_LAUNCH_COND2(2); else CWG_LAUNCH_COND2(1);
+#undef CWG_LAUNCH_COND2
+    return 0;
+  }
   if (npass == 3) {
     if (int r = set_smem(k_cond_tc<3>, CondCfg<3>::SMEM)) return r;
     k_cond_tc<3><<<grid, 192, CondCfg<3>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
