@@ -363,7 +363,7 @@ constexpr bool L_ACTS_TMEM = CWG_ACTS_TMEM != 0;
 // TMEM column of the packed bf16 acts of 16-channel chunk c: each column group writes behind its own read pointer
 __device__ __forceinline__ uint32_t L_ACOL(int c) { return (uint32_t)((c / L_CPG) * (16 * L_CPG) + (c % L_CPG) * 8); }
 
-template <int NPASS>
+template <int NPASS, bool TWO>
 __global__ void __launch_bounds__(L_THREADS, 1)
 k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
            const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
@@ -384,7 +384,17 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   constexpr bool X3 = NPASS != 1;                 // lo planes exist (residual, GEMM2 cross terms)
   constexpr int PL = NPASS == 3 ? 2 : 1;          // planes streamed per k-block in GEMM1 of the bf16 modes
   constexpr int PL2 = X3 ? 2 : 1;                 // planes of the GEMM2 operands
-  constexpr uint32_t ID256 = F8 ? IDESC_F16_N256 : IDESC_N256, ID16 = F8 ? IDESC_F16_N16 : IDESC_N16;
+  // TWO: 2-SM MMAs (cta_group::2).  Two neighbouring tiles of one utterance form a CTA pair (cluster ranks 0 / 1); the
+  // leader issues every MMA with M = 256, each CTA supplies its own 128 rows of A and HALF of the N rows of every
+  // weight tile (16 KB instead of 32 KB per slot), all TMA completions are counted on the leader's barriers, slots and
+  // accumulators are released / published in both CTAs by multicast commits.
+  // The folded-`end` MMAs are N = 16; the 2-SM A-from-TMEM form needs N >= 32, so there N = 32: the leader stages the 16
+  // real rows, the follower the 16 rows that follow them in w2 (the next layer's first res rows, or TMA zero fill) - they
+  // only produce accumulator columns 16..31, which nobody reads.
+  constexpr int MM = TWO ? 256 : 128, NEO = TWO ? 32 : 16;
+  constexpr uint32_t ID256 = F8 ? umma_idesc_f16(MM, 256) : umma_idesc_bf16(MM, 256), ID16 = F8 ? umma_idesc_f16(MM, NEO) : umma_idesc_bf16(MM, NEO);
+  constexpr uint32_t IDF256 = umma_idesc_f16(MM, 256), IDF16 = umma_idesc_f16(MM, NEO);
+  constexpr uint32_t IDE256 = umma_idesc_e5m2(MM, 256), IDE16 = umma_idesc_e5m2(MM, NEO);
   // shared-memory unit of the lo tile of 64-channel block kb of x (residual read / x_new staging).  f16f8: units 4..7
   // hold the e5m2 acts tiles of the two 128-channel groups during GEMM2 (4 + g: lo*2^P, 6 + g: hi*2^-Q), and group g
   // frees units 4 + g and 6 + g, so blocks 0, 1 (needed first) take units 4, 6 and blocks 2, 3 take 5, 7.
@@ -411,15 +421,40 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L_NBAR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, L_EPI_THREADS); mbar_init(acc2_full, 1);
+    mbar_init(wse_full, 1); mbar_init(acc1_full, 1); mbar_init(acts_ready, (TWO ? 2 : 1) * L_EPI_THREADS); mbar_init(acc2_full, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&xold_full[i], 1); mbar_init(&g2_done[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if (TWO) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   tc_fence_before_sync();
   __syncthreads();
+  if (TWO) cluster_sync_all();                     // both CTAs' barriers and TMEM exist before anything targets them
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // pipeline helpers: in 2-SM mode loads complete on the leader's barrier (armed by the leader for both CTAs' bytes)
+  auto arm = [&](uint64_t* bar, uint32_t bytes) {
+    if (!TWO) mbar_arrive_expect_tx(bar, bytes); else if (leader) mbar_arrive_expect_tx(bar, 2 * bytes);
+  };
+  auto lda3 = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    if (TWO) tma_load_3d_2sm(dst, m, mapa_shared(bar, 0), c0, c1, c2); else tma_load_3d(dst, m, bar, c0, c1, c2);
+  };
+  auto ldb2 = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int row, int half_rows) {
+    if (TWO) tma_load_2d_2sm(dst, m, mapa_shared(bar, 0), c0, row + (int)rank * half_rows); else tma_load_2d(dst, m, bar, c0, row);
+  };
+  auto commit = [&](uint64_t* bar) { if (TWO) umma_commit_2sm(bar); else umma_commit(bar); };
+  auto mma_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) { if (TWO) umma_bf16_2sm(d, ad, bd, id, acc); else umma_bf16(d, ad, bd, id, acc); };
+  auto mma_ts = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t id, uint32_t acc) { if (TWO) umma_bf16_ts_2sm(d, at, bd, id, acc); else umma_bf16_ts(d, at, bd, id, acc); };
+  auto mma_f8 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) { if (TWO) umma_f8_2sm(d, ad, bd, id, acc); else umma_f8(d, ad, bd, id, acc); };
+  auto kblk = [&](uint32_t a_addr, uint32_t b_addr, uint32_t d, uint32_t id, bool first) {
+    const uint64_t da = DESC_SW128_HI | (uint64_t)((a_addr & 0x3FFFF) >> 4), db = DESC_SW128_HI | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+    mma_ss(d, da, db, id, first ? 0u : 1u); mma_ss(d, da + 2, db + 2, id, 1u); mma_ss(d, da + 4, db + 4, id, 1u); mma_ss(d, da + 6, db + 6, id, 1u);
+  };
+  auto kblk8 = [&](uint32_t a_addr, uint32_t b_addr, uint32_t d, uint32_t id) {
+    const uint64_t da = DESC_SW128_HI | (uint64_t)((a_addr & 0x3FFFF) >> 4), db = DESC_SW128_HI | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+    mma_f8(d, da, db, id, 1u); mma_f8(d, da + 2, db + 2, id, 1u); mma_f8(d, da + 4, db + 4, id, 1u); mma_f8(d, da + 6, db + 6, id, 1u);
+  };
   long long* dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define CWG_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
 
@@ -435,13 +470,13 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         for (int it = 0; it < 4; ++it) {
           mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
           pm ^= 1u << s;
-          mbar_arrive_expect_tx(&full[s], TILE_A);
+          arm(&full[s], TILE_A);
           const bool cond = G >= 6;
           const int tt = cond ? t0 : t0 + ((G >> 1) - 1) * a.dil;
           const int c0 = (cond ? G - 6 : (G & 1)) * 128;
-          if (it < 2) tma_load_3d(slot(s), cond ? &tm_h_hi : &tm_x_hi, &full[s], c0 + it * 64, tt, b);
-          else if (it == 2) tma_load_3d(slot(s), cond ? &tm_h_l8 : &tm_x_l8, &full[s], c0, tt, b);
-          else tma_load_3d(slot(s), cond ? &tm_h_h8 : &tm_x_h8, &full[s], c0, tt, b);
+          if (it < 2) lda3(slot(s), cond ? &tm_h_hi : &tm_x_hi, &full[s], c0 + it * 64, tt, b);
+          else if (it == 2) lda3(slot(s), cond ? &tm_h_l8 : &tm_x_l8, &full[s], c0, tt, b);
+          else lda3(slot(s), cond ? &tm_h_h8 : &tm_x_h8, &full[s], c0, tt, b);
           s = (s + 1 == L_NA) ? 0 : s + 1;
         }
     }
@@ -449,12 +484,12 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       for (int pl = 0; pl < PL; ++pl) {
         mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
         pm ^= 1u << s;
-        mbar_arrive_expect_tx(&full[s], TILE_A);
+        arm(&full[s], TILE_A);
         if (kb < 12) {
           int tap = kb >> 2, cb = kb & 3;
-          tma_load_3d(slot(s), pl ? &tm_x_lo : &tm_x_hi, &full[s], cb * 64, t0 + (tap - 1) * a.dil, b);
+          lda3(slot(s), pl ? &tm_x_lo : &tm_x_hi, &full[s], cb * 64, t0 + (tap - 1) * a.dil, b);
         } else {
-          tma_load_3d(slot(s), pl ? &tm_h_lo : &tm_h_hi, &full[s], (kb - 12) * 64, t0, b);
+          lda3(slot(s), pl ? &tm_h_lo : &tm_h_hi, &full[s], (kb - 12) * 64, t0, b);
         }
         s = (s + 1 == L_NA) ? 0 : s + 1;
       }
@@ -470,9 +505,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           for (int g = 0; g < 2; ++g) {
             mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
             pm ^= 1u << j;
-            mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
-            if (it < 2) tma_load_2d(bslot(j), &tm_w1_hi, &full[4 + j], (2 * G + it) * 64, a.w1_row0 + g * 256);
-            else tma_load_2d(bslot(j), it == 2 ? &tm_w1_h8 : &tm_w1_l8, &full[4 + j], G * 128, a.w1_row0 + g * 256);
+            arm(&full[4 + j], TWO ? TILE_A : 2 * TILE_A);
+            if (it < 2) ldb2(bslot(j), &tm_w1_hi, &full[4 + j], (2 * G + it) * 64, a.w1_row0 + g * 256, 128);
+            else ldb2(bslot(j), it == 2 ? &tm_w1_h8 : &tm_w1_l8, &full[4 + j], G * 128, a.w1_row0 + g * 256, 128);
             j = (j + 1) & 3;
           }
     }
@@ -481,8 +516,8 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         for (int pl = 0; pl < PL; ++pl) {
           mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
           pm ^= 1u << j;
-          mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
-          tma_load_2d(bslot(j), pl ? &tm_w1_lo : &tm_w1_hi, &full[4 + j], kb * 64, a.w1_row0 + g * 256);
+          arm(&full[4 + j], TWO ? TILE_A : 2 * TILE_A);
+          ldb2(bslot(j), pl ? &tm_w1_lo : &tm_w1_hi, &full[4 + j], kb * 64, a.w1_row0 + g * 256, 128);
           j = (j + 1) & 3;
         }
     if (a.has_res && F8) {
@@ -491,9 +526,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         for (int it = 0; it < 4; ++it) {          // two fp16 tiles, then the e5m2 hi*2^-P and lo*2^Q tiles of the group
           mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
           pm ^= 1u << j;
-          mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
-          if (it < 2) tma_load_2d(bslot(j), &tm_w2_hi, &full[4 + j], (2 * grp + it) * 64, a.w2_row0);
-          else tma_load_2d(bslot(j), it == 2 ? &tm_w2_lo : &tm_w2_l8, &full[4 + j], grp * 128, a.w2_row0);
+          arm(&full[4 + j], TWO ? TILE_A : 2 * TILE_A);
+          if (it < 2) ldb2(bslot(j), &tm_w2_hi, &full[4 + j], (2 * grp + it) * 64, a.w2_row0, 128);
+          else ldb2(bslot(j), it == 2 ? &tm_w2_lo : &tm_w2_l8, &full[4 + j], grp * 128, a.w2_row0, 128);
           j = j == 2 ? 3 : 2;
         }
     }
@@ -503,13 +538,13 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         for (int pl = 0; pl < PL2; ++pl) {
           mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
           pm ^= 1u << j;
-          mbar_arrive_expect_tx(&full[4 + j], 2 * TILE_A);
-          tma_load_2d(bslot(j), pl ? &tm_w2_lo : &tm_w2_hi, &full[4 + j], kb * 64, a.w2_row0);
+          arm(&full[4 + j], TWO ? TILE_A : 2 * TILE_A);
+          ldb2(bslot(j), pl ? &tm_w2_lo : &tm_w2_hi, &full[4 + j], kb * 64, a.w2_row0, 128);
           j = j == 2 ? 3 : 2;
         }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ---------------- MMA issuer (the leader CTA's thread in 2-SM mode)
     int sa = 0, jb = 0; uint32_t cm = 0;
     auto wait_full = [&](int bar) {               // bar: barrier index (A slot i -> i, B slot j -> 4 + j)
       mbar_wait(&full[bar], (cm >> bar) & 1u);
@@ -525,11 +560,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
             const int jb_cur = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
             tc_fence_after_sync();
             const uint32_t d = tmem + g * 256;
-            if (it < 2) issue_kblock_fast(smem_u32(slot(sa_cur)), smem_u32(bslot(jb_cur)), d, IDESC_F16_N256, G == 0 && it == 0);
-            else issue_kblock_fast_f8(smem_u32(slot(sa_cur)), smem_u32(bslot(jb_cur)), d, IDESC_E5M2_N256);
-            umma_commit(&empty[4 + jb_cur]);
+            if (it < 2) kblk(smem_u32(slot(sa_cur)), smem_u32(bslot(jb_cur)), d, IDF256, G == 0 && it == 0);
+            else kblk8(smem_u32(slot(sa_cur)), smem_u32(bslot(jb_cur)), d, IDE256);
+            commit(&empty[4 + jb_cur]);
           }
-          umma_commit(&empty[sa_cur]);
+          commit(&empty[sa_cur]);
         }
     }
     for (int kb = 0; kb < (F8 ? 0 : 16); ++kb) {
@@ -544,33 +579,33 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
         tc_fence_after_sync();
         const uint32_t d = tmem + g * 256;
-        issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), d, IDESC_N256, kb == 0);
+        kblk(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_hi)), d, ID256, kb == 0);
         if (NPASS == 3) {
-          issue_kblock_fast(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), d, IDESC_N256, false);
-          umma_commit(&empty[4 + jb_hi]);
-          if (g == 1) umma_commit(&empty[sa_lo]);
+          kblk(smem_u32(slot(sa_lo)), smem_u32(bslot(jb_hi)), d, ID256, false);
+          commit(&empty[4 + jb_hi]);
+          if (g == 1) commit(&empty[sa_lo]);
           const int jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
           tc_fence_after_sync();
-          issue_kblock_fast(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), d, IDESC_N256, false);
-          umma_commit(&empty[4 + jb_lo]);
+          kblk(smem_u32(slot(sa_hi)), smem_u32(bslot(jb_lo)), d, ID256, false);
+          commit(&empty[4 + jb_lo]);
         } else {
-          umma_commit(&empty[4 + jb_hi]);
+          commit(&empty[4 + jb_hi]);
         }
       }
-      umma_commit(&empty[sa_hi]);
+      commit(&empty[sa_hi]);
     }
-    umma_commit(acc1_full);
+    commit(acc1_full);
     CWG_STAMP(6);
     // GEMM2: [res | folded end] = acts (smem units 0..3 hi / 4..7 lo) x W2^T
-    mbar_wait(acts_ready, 0);
+    if (TWO) mbar_wait_cluster(acts_ready, 0); else mbar_wait(acts_ready, 0);
     tc_fence_after_sync();
     mbar_wait(wse_full, 0);
     CWG_STAMP(7);
     jb = 2;
     int n_eo = 0;                                  // folded-`end` MMAs issued so far (round-robin over the chains)
     auto mma_a_hi = [&](uint32_t d, int kb, int k, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-      if (L_ACTS_TMEM) umma_bf16_ts(d, tmem + L_ACOL(kb * 4 + k), bdesc, idesc, acc);     // A = acts hi in TMEM
-      else umma_bf16(d, umma_desc_sw128(smem_u32(slot(kb)) + 32 * k), bdesc, idesc, acc);
+      if (L_ACTS_TMEM) mma_ts(d, tmem + L_ACOL(kb * 4 + k), bdesc, idesc, acc);     // A = acts hi in TMEM
+      else mma_ss(d, umma_desc_sw128(smem_u32(slot(kb)) + 32 * k), bdesc, idesc, acc);
     };
     auto eo_dst = [&](uint32_t* acc) {
       const int j = n_eo % L_EO_CHAINS;
@@ -592,21 +627,21 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u, a_t = tmem + L_ACOL(kb * 4 + k);
-              if (a.has_res) umma_bf16_ts(dres, a_t, umma_desc_sw128(r + o), IDESC_F16_N256, acc);
-              umma_bf16_ts(d16, a_t, umma_desc_sw128(wv + o), IDESC_F16_N16, acc);
+              if (a.has_res) mma_ts(dres, a_t, umma_desc_sw128(r + o), IDF256, acc);
+              mma_ts(d16, a_t, umma_desc_sw128(wv + o), IDF16, acc);
             }
           } else {
             const uint32_t av = smem_u32(slot(4 + 2 * (it - 2) + grp)), wv = smem_u32(wse(1, 2 * (it - 2) + grp));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t o = 32 * k;
-              if (a.has_res) umma_f8(dres, umma_desc_sw128(av + o), umma_desc_sw128(r + o), IDESC_E5M2_N256, 1u);
-              umma_f8(d16, umma_desc_sw128(av + o), umma_desc_sw128(wv + o), IDESC_E5M2_N16, 1u);
+              if (a.has_res) mma_f8(dres, umma_desc_sw128(av + o), umma_desc_sw128(r + o), IDE256, 1u);
+              mma_f8(d16, umma_desc_sw128(av + o), umma_desc_sw128(wv + o), IDE16, 1u);
             }
           }
-          if (a.has_res) umma_commit(&empty[4 + jb_cur]);
+          if (a.has_res) commit(&empty[4 + jb_cur]);
         }
-        if (a.has_res) umma_commit(&g2_done[grp]);
+        if (a.has_res) commit(&g2_done[grp]);
       }
     }
     for (int kb = 0; kb < (F8 ? 0 : 4); ++kb) {
@@ -628,34 +663,34 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_hi + o), ID256, acc);
         { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_hi + o), ID16, eacc); }
         if (X3) {
-          if (a.has_res) umma_bf16(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), ID256, 1u);
-          { const uint32_t d16 = eo_dst(&eacc); umma_bf16(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), ID16, eacc); }
+          if (a.has_res) mma_ss(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), ID256, 1u);
+          { const uint32_t d16 = eo_dst(&eacc); mma_ss(d16, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), ID16, eacc); }
           if (a.has_res) mma_a_hi(dres, kb, k, umma_desc_sw128(r_lo + o), ID256, 1u);
           { const uint32_t d16 = eo_dst(&eacc); mma_a_hi(d16, kb, k, umma_desc_sw128(w_lo + o), ID16, eacc); }
         }
       }
       if (a.has_res) {
-        umma_commit(&empty[4 + jb_hi]);
-        if (X3) umma_commit(&empty[4 + jb_lo]);
-        umma_commit(&g2_done[kb]);
+        commit(&empty[4 + jb_hi]);
+        if (X3) commit(&empty[4 + jb_lo]);
+        commit(&g2_done[kb]);
       }
     }
-    umma_commit(acc2_full);
+    commit(acc2_full);
     CWG_STAMP(8);
   } else if (warp == 3 && lane == 0) {
     // ---------------- folded-`end` weight tiles (kept off the activation producer: issuing them first
     // delayed the first A tile by ~1 k cycles), then the residual prefetch: as soon as GEMM2 is done with
     // the acts tiles of a 64-channel block, the x_old (centre tap) tiles of that block are TMA-loaded
     // over them (units kb / 4+kb)
-    mbar_arrive_expect_tx(wse_full, 4 * 2048 * PL2);
+    arm(wse_full, 4 * 2048 * PL2);
     for (int kb = 0; kb < 4; ++kb) {
-      tma_load_2d(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256);
-      if (X3 && !F8) tma_load_2d(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256);
+      ldb2(wse(0, kb), &tm_wse_hi, wse_full, kb * 64, a.w2_row0 + 256, 16);
+      if (X3 && !F8) ldb2(wse(1, kb), &tm_wse_lo, wse_full, kb * 64, a.w2_row0 + 256, 16);
     }
     if (F8)       // e5m2 planes of the 16 folded-`end` rows: [16 rows x 128 B] per 128-channel group
       for (int grp = 0; grp < 2; ++grp) {
-        tma_load_2d(wse(1, grp), &tm_wse_lo, wse_full, grp * 128, a.w2_row0 + 256);
-        tma_load_2d(wse(1, 2 + grp), &tm_wse_l8, wse_full, grp * 128, a.w2_row0 + 256);
+        ldb2(wse(1, grp), &tm_wse_lo, wse_full, grp * 128, a.w2_row0 + 256, 16);
+        ldb2(wse(1, 2 + grp), &tm_wse_l8, wse_full, grp * 128, a.w2_row0 + 256, 16);
       }
     if (a.has_res && F8) {
       // acts hi live in TMEM, so the A-ring units 0..3 are free once GEMM1 has completed: the hi tiles of x_old go
@@ -733,7 +768,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (L_ACTS_TMEM) tmem_wait_st();
     tc_fence_before_sync();
     fence_proxy_async_smem();
-    mbar_arrive(acts_ready);
+    if (TWO && !leader) mbar_arrive_cluster(mapa_shared(acts_ready, 0)); else mbar_arrive(acts_ready);
     if (stamp) dbg[2] = clock64();
 
     // prefetch this row's folded-`end` accumulator while GEMM2 runs
@@ -828,7 +863,8 @@ k_layer_tc(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (stamp) dbg[4] = clock64();
   }
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem, 512); }
+  if (TWO) cluster_sync_all();                     // the pair releases TMEM together; no CTA exits with peer traffic pending
+  if (warp == 1) { __syncwarp(); if (TWO) tmem_dealloc_2sm(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 
@@ -947,17 +983,41 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.w1_row0 = (int)(idx * 2 * d.C); a.w2_row0 = (int)(idx * d.N2);
   a.has_res = layer < d.L - 1; a.first = layer == 0;
   a.dbg = g_dbg_timing;
-  dim3 grid((unsigned)((d.Tp + 127) / 128), d.B);
-#define CWG_LAUNCH_LAYER(NP)                                                                                          \
+  // CWG_LAYER_2SM=1: 2-SM MMAs (cta_group::2).  CTA pairs = neighbouring tiles of one utterance (cluster along x); each
+  // CTA loads half of the N rows of every weight tile, so the weight maps get 128-row boxes.
+  // An odd tile count gets one tile fully past T' (TMA zero-fills its loads and clips its stores).
+  static const int two = [] { const char* e = getenv("CWG_LAYER_2SM"); return e && e[0] == '1'; }();
+  unsigned tiles = (unsigned)((d.Tp + 127) / 128);
+  if (two) {
+    tiles = (tiles + 1) & ~1u;
+    if (int r = map_2d(&tw1_hi, w->w1_hi, d.K1, fl * 2 * d.C, 128)) return r;
+    if (int r = map_2d(&tw2_hi, w->w2_hi, d.C, fl * d.N2, 128)) return r;
+    if (npass == 2) {
+      if (int r = map_2d8(&tw1_h8, w->w1_h8, d.K1, fl * 2 * d.C, 128)) return r;
+      if (int r = map_2d8(&tw1_l8, w->w1_l8, d.K1, fl * 2 * d.C, 128)) return r;
+      if (int r = map_2d8(&tw2_lo, w->w2_h8, d.C, fl * d.N2, 128)) return r;
+      if (int r = map_2d8(&tw2_l8, w->w2_l8, d.C, fl * d.N2, 128)) return r;
+    } else {
+      if (int r = map_2d(&tw1_lo, w->w1_lo, d.K1, fl * 2 * d.C, 128)) return r;
+      if (int r = map_2d(&tw2_lo, w->w2_lo, d.C, fl * d.N2, 128)) return r;
+    }
+  }
+  dim3 grid(tiles, d.B);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid; lc.blockDim = dim3(L_THREADS); lc.dynamicSmemBytes = L_SMEM; lc.stream = s;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 2; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
+  lc.attrs = lattr; lc.numAttrs = two ? 1 : 0;
+#define CWG_LAUNCH_LAYER(NP, TW)                                                                                      \
   do {                                                                                                                \
-    if (int r = set_smem(k_layer_tc<NP>, L_SMEM)) return r;                                                           \
-    k_layer_tc<NP><<<grid, L_THREADS, L_SMEM, s>>>(tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, \
-                                                   tse_lo, to_hi, to_lo, tx_l8, tx_h8, th_l8, th_h8, tw1_h8, tw1_l8,  \
-                                                   to_l8, to_h8, tw2_l8, tse_l8, a);                                  \
+    if (int r = set_smem(k_layer_tc<NP, TW>, L_SMEM)) return r;                                                       \
+    CWG_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_layer_tc<NP, TW>, tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi,    \
+                                      tw2_lo, tse_hi, tse_lo, to_hi, to_lo, tx_l8, tx_h8, th_l8, th_h8, tw1_h8,       \
+                                      tw1_l8, to_l8, to_h8, tw2_l8, tse_l8, a));                                      \
   } while (0)
-  if (npass == 3) CWG_LAUNCH_LAYER(3);
-  else if (npass == 2) CWG_LAUNCH_LAYER(2);
-  else CWG_LAUNCH_LAYER(1);
+  if (two) { if (npass == 3) CWG_LAUNCH_LAYER(3, true); else if (npass == 2) CWG_LAUNCH_LAYER(2, true); else CWG_LAUNCH_LAYER(1, true); }
+  else     { if (npass == 3) CWG_LAUNCH_LAYER(3, false); else if (npass == 2) CWG_LAUNCH_LAYER(2, false); else CWG_LAUNCH_LAYER(1, false); }
 #undef CWG_LAUNCH_LAYER
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
