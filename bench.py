@@ -470,7 +470,7 @@ def main():
         "mma_passes": passes, "issued_mma_tflops": achieved * passes,
         "note": "achieved = reference's dense FLOPs per layer launch (SURVEY 8d) / CUDA-event duration; "
                 "bf16x3 issues 3 bf16 MMAs per algorithmic MAC (frac <= 1/3 by construction), f16f8 one fp16 MMA plus "
-                "two e5m2 MMAs at twice the rate (frac <= 1/2 against the bf16 peak)",
+                "two e5m2 MMAs at nominally twice, measured ~1.5x, the fp16 rate (frac <= ~0.43 against the bf16 peak)",
     }
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
