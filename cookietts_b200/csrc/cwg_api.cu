@@ -3,6 +3,7 @@
 #include "cwg_common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cwg {
@@ -79,10 +80,23 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
   ws->bytes = off;
 }
 
+// C = 256: the persistent sweep kernel (cwg_ps.cu) unless CWG_LAYER_PS=0 asks for the round-1 one-tile-per-CTA kernel
+int g_force_ps = -1;     // cwg_debug_set_layer_kernel: -1 = environment / default, 0 = round-1 kernel, 1 = persistent kernel
+bool use_ps() {
+  static const int v = [] { const char* e = getenv("CWG_LAYER_PS"); return e ? (e[0] != '0') : 1; }();
+  return g_force_ps >= 0 ? g_force_ps != 0 : v != 0;
+}
+
+int layer_tc256(const Dims& d, const cwg_weights* w, int npass, int k, int i, const __nv_bfloat16* x_in,
+                __nv_bfloat16* x_out, const __nv_bfloat16* h2, float* eo, cudaStream_t s) {
+  if (use_ps()) return launch_layer_ps(d, w, npass, k, i, x_in, x_out, h2, eo, s);
+  return launch_layer_tc(d, w, npass, k, i, x_in, x_out, h2, eo, s);
+}
+
 int layer_tc(const Dims& d, const cwg_weights* w, int npass, int k, int i, const Workspace& ws, cudaStream_t s) {
   if (d.C == 512)
     return launch_layer_tc512(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.actsb, ws.eo, s);
-  return launch_layer_tc(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s);
+  return layer_tc256(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s);
 }
 
 int check_run(const cwg_config* cfg, const cwg_weights* w, int mode, int batch, int t_mel) {
@@ -113,6 +127,9 @@ int cwg_abi_version(void) { return CWG_ABI_VERSION; }
 
 // Debug only (not in cwg.h): the WN layer kernel writes 16 clock64 stamps per CTA into `buf`.
 void cwg_debug_set_timing(void* buf) { cwg::debug_set_timing((long long*)buf); }
+// Debug only: the persistent layer kernel writes {start, end, tiles, -} clock64 stamps per CTA (4 x int64 each).
+void cwg_debug_set_layer_kernel(int which) { cwg::g_force_ps = which; }
+void cwg_debug_set_ps_timing(void* buf) { cwg::debug_set_ps_timing((long long*)buf); }
 
 const char* cwg_last_error(void) { return cwg::g_err; }
 
@@ -172,8 +189,8 @@ int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow
     return launch_layer_tc512(d, w, mode_npass(mode), flow, layer, (const __nv_bfloat16*)x_in,
                               (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, ws.actsb, eo, s);
   }
-  return launch_layer_tc(d, w, mode_npass(mode), flow, layer, (const __nv_bfloat16*)x_in,
-                         (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, eo, s);
+  return layer_tc256(d, w, mode_npass(mode), flow, layer, (const __nv_bfloat16*)x_in,
+                     (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, eo, s);
 }
 
 int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,

@@ -87,6 +87,12 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
                     const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
                     float* eo, cudaStream_t s);
 
+// persistent, epilogue-overlapped successor of launch_layer_tc for n_channels = 256 (cwg_ps.cu); the default
+int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
+                    const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
+                    float* eo, cudaStream_t s);
+void debug_set_ps_timing(long long* buf);
+
 // n_channels = 512: two kernels per layer (cwg_tc512.cu); `acts` = bf16 hi/lo planes [B*T'][512]
 int launch_layer_tc512(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
                        const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
