@@ -107,45 +107,119 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(batch, t_mel, repeats, warmup):
-    """The reference's CPU implementation of the path (torch-op port in oracle/, pinned to golden
-    vectors of the real reference) on all host threads; returns (samples/s, seconds per run, threads)."""
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def make_cpu_runner():
+    """The reference's CPU implementation of the path.  Preferred: the reference's OWN `WaveGlow.infer` - the unmodified
+    copy of glow.py that oracle/build_ref.py places in oracle/_ref/ (kind "reference"), driven exactly as
+    oracle/make_golden.py drives it (`Tensor.normal_` patched to hand out the pre-drawn z, the hard-coded
+    `torch.cuda.FloatTensor` of glow.py:343-346 shimmed to the CPU type).  Without oracle/_ref: the torch-op port in
+    oracle/ (kind "port").  Returns (kind, source, run) with run(batch, t_mel) -> (samples, seconds)."""
     import torch
-    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict, synthetic_inputs
-    from oracle.waveglow_torch_port import TorchPort
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    from oracle import build_ref
+    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict, synthetic_inputs, split_z
     cfg = OracleConfig()
     sd = synthetic_state_dict(cfg, 1234)
-    mel, z = synthetic_inputs(cfg, batch, t_mel, 0)
+    ref = build_ref.load()
+    if ref is not None:
+        from oracle.make_golden import InjectedNormal, reference_kwargs
+        torch.manual_seed(0)
+        model = ref.WaveGlow(**reference_kwargs(cfg))
+        model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
+        model.eval()
+
+        def run(batch, t_mel):
+            mel, z = synthetic_inputs(cfg, batch, t_mel, 0)
+            z_main, z_early = split_z(z, cfg)
+            draws = [torch.from_numpy(np.ascontiguousarray(z_main))]
+            draws += [torch.from_numpy(np.ascontiguousarray(z_early[k])) for k in sorted(z_early.keys(), reverse=True)]
+            mel_t = torch.from_numpy(mel)
+            t = time.perf_counter()
+            with torch.no_grad(), InjectedNormal(draws):
+                out = model.infer(mel_t, sigma=0.666)
+            return out.numel(), time.perf_counter() - t
+        return "reference", "oracle/_ref/glow.py::WaveGlow.infer (unmodified copy of the reference module), fp32", run
+
+    from oracle.waveglow_torch_port import TorchPort
     port = TorchPort(sd, cfg, torch.float32)
-    times = []
-    for i in range(warmup + repeats):
+
+    def run_port(batch, t_mel):
+        mel, z = synthetic_inputs(cfg, batch, t_mel, 0)
         t = time.perf_counter()
         out = port.infer(mel, z, 0.666)
-        dt = time.perf_counter() - t
+        return out.size, time.perf_counter() - t
+    return "port", "oracle/waveglow_torch_port.py (torch-op CPU port of glow.py::WaveGlow.infer; oracle/_ref absent), fp32", run_port
+
+
+def timed_cpu(run, batch, t_mel, repeats, warmup, threads):
+    """median / min / max seconds of `repeats` runs after `warmup`, at `threads` torch threads"""
+    import torch
+    torch.set_num_threads(threads)
+    times, n = [], 0
+    for i in range(warmup + repeats):
+        n, dt = run(batch, t_mel)
         if i >= warmup:
             times.append(dt)
     sec = float(np.median(times))
-    return out.size / sec, sec, torch.get_num_threads()
+    return {"batch": batch, "t_mel": t_mel, "threads": torch.get_num_threads(), "samples": int(n), "runs": repeats,
+            "sec_median": sec, "sec_min": float(min(times)), "sec_max": float(max(times)),
+            "samples_per_s": n / sec, "xrt": n / sec / SR}
+
+
+def cpu_baseline_leg():
+    """the reference's infer on this box's host cores - config 1 (1 x 86 frames) at all threads
+    (1 warm-up + median of 5) and at 1 thread (1 + 3), then one utterance of the bench workload (1 x 861) at all threads if
+    the config-1 speed says it fits in ~40 s.  `value` = the largest all-thread shape measured."""
+    kind, source, run = make_cpu_runner()
+    allt = os.cpu_count() or 1
+    runs = [timed_cpu(run, 1, 86, 5, 1, allt), timed_cpu(run, 1, 86, 3, 1, 1)]
+    if runs[0]["sec_median"] * 14.0 < 40.0:           # 861 frames cost >= 10x 86 frames; measured 14-20x
+        runs.append(timed_cpu(run, 1, 861, 1, 0, allt))
+    head = runs[-1] if runs[-1]["threads"] != 1 else runs[0]
+    return {"value": head["samples_per_s"], "unit": "samples/s", "cores": head["threads"], "kind": kind, "xrt": head["xrt"],
+            "sample": f"{head['batch']} x {head['t_mel']} mel frames ({head['samples']} samples), median of {head['runs']}, all host threads",
+            "source": source, "cpu_model": cpu_model_name(), "os_cpu_count": allt, "runs": runs,
+            "spread": "sec_min / sec_max per run list entry; the --impl reference arm repeats the measurement with its own K steps"}
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU `infer` on this box's host cores, all threads.  Each step is a bounded
+    sample of the bench workload: whole utterances of the batch-16 x 861-frame job, the frame count cut down only if a
+    calibration run (config 1) says K + W steps of a full utterance would not end within ~4 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample of the workload: 1 utterance x 2 s of the batch-16 x 10-s job per step
-    b, tm = 1, 172
-    value, sec, threads = cpu_reference_run(b, tm, max(args.steps, 1), max(min(args.warmup, 1), 1))
+    kind, source, run = make_cpu_runner()
+    allt = os.cpu_count() or 1
+    steps, warm = max(args.steps, 1), max(min(args.warmup, 1), 1)
+    cal = timed_cpu(run, 1, 86, 1, 1, allt)
+    b, tm = 1, 861
+    for cand in (861, 430, 172, 86):
+        tm = cand
+        if cal["sec_median"] * (cand / 86.0) * 1.6 * (steps + warm) < 240.0:
+            break
+    r = timed_cpu(run, b, tm, steps, warm, allt)
+    value = r["samples_per_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": r["sec_median"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "WaveGlow 12-flow/256-ch inverse pass, batch 16 x 10 s mels (T_mel 861), sigma 0.666, injected z",
-                   "sample": f"{b} utterance x {tm} mel frames per step"},
+                   "sample": f"{b} utterance x {tm} mel frames per step (one of the 16 utterances of a GPU step"
+                             + ("" if tm == 861 else f", cut to {tm} of 861 frames to bound the run") + ")"},
         "xrt": value / SR,
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{b} x {tm} mel frames ({b * tm * 256} samples) per step, torch-op CPU port of glow.py::WaveGlow.infer, fp32"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": r["threads"], "kind": kind, "source": source,
+                         "cpu_model": cpu_model_name(), "os_cpu_count": allt,
+                         "sample": f"{b} x {tm} mel frames ({r['samples']} samples) per step, median of {steps} steps after {warm} warm-up",
+                         "sec_min": r["sec_min"], "sec_max": r["sec_max"], "calibration_config1": cal},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -496,11 +570,7 @@ def main():
         "output_finite": finite,
     }
     if world == 1 and not args.no_cpu_baseline:
-        b, tm = 1, 172
-        v, sec, threads = cpu_reference_run(b, tm, 3, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "xrt": v / SR,
-                                "sample": f"{b} x {tm} mel frames ({b * tm * 256} samples), median of 3 after 1 warm-up, "
-                                          f"torch-op CPU port of glow.py::WaveGlow.infer, fp32"}
+        line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)
 
 

@@ -157,6 +157,8 @@ class Denoiser(nn.Module):
                 idx = torch.as_tensor(speaker_ids, device=dev).to(torch.int32).contiguous()
                 if idx.numel() != B:
                     raise ValueError("speaker_ids must have one entry per utterance")
+                if int(idx.min()) < 0 or int(idx.max()) >= self.bias_spec.shape[0]:
+                    raise IndexError(f"speaker id out of range for a bias spectrum of {self.bias_spec.shape[0]} rows")
                 idx_ptr = idx.data_ptr()
             elif self.bias_spec.shape[0] not in (1, B):
                 raise ValueError("bias_spec has one row per speaker: pass speaker_ids")

@@ -120,6 +120,20 @@ def infer_long_sharded(model, spect: torch.Tensor, sigma: float = 1.0, z: Option
     return out
 
 
+def slice_per_utterance(kw: dict, idx, n_items: int) -> dict:
+    """Per-utterance keyword arguments (speaker_id / speaker_ids: one entry per utterance) follow the shard: entries
+    `idx` of every tensor / sequence of length `n_items`; scalars and one-element tensors pass through."""
+    out = {}
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == n_items and n_items > 1:
+            out[k] = v[idx] if not isinstance(idx, slice) else v[idx]
+        elif isinstance(v, (list, tuple)) and len(v) == n_items and n_items > 1:
+            out[k] = [v[i] for i in (range(*idx.indices(n_items)) if isinstance(idx, slice) else idx)]
+        else:
+            out[k] = v
+    return out
+
+
 def gather_waveforms(audio_local: torch.Tensor, n_items: int, dst: int = 0) -> Optional[torch.Tensor]:
     """Final collective of the sharded path: gathers every rank's `[B_local, T]` waveforms to
     `dst` and restores utterance order.  Ranks may own different counts (round-robin shards differ
@@ -155,7 +169,7 @@ def infer_sharded(model, spect: torch.Tensor, sigma: float = 1.0, z: Optional[to
     hop = model.pack_config.hop_length
     if idx:
         z_local = z[idx] if z is not None else None
-        audio = model.infer(spect[idx], sigma=sigma, z=z_local, **kw)
+        audio = model.infer(spect[idx], sigma=sigma, z=z_local, **slice_per_utterance(kw, idx, n))
     else:
         audio = torch.zeros(0, spect.shape[2] * hop, device=next(model.parameters()).device)
     return gather_waveforms(audio, n, dst)

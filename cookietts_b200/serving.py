@@ -53,16 +53,24 @@ def vocode_pcm16(vocoder, mels: torch.Tensor, output_lengths: Sequence[int], hop
         raise ValueError("output_lengths must have one entry per mel")
     pad = int(cat_silence_s * sampling_rate) if cat_silence_s else 0
     out: List[np.ndarray] = []
-    for i in range(0, mels.shape[0], vocoder_batch_size):
+    from .parallel import slice_per_utterance
+    n_items = mels.shape[0]
+    for i in range(0, n_items, vocoder_batch_size):
         part = mels[i:i + vocoder_batch_size]
-        audio = vocoder.infer(part, **infer_kwargs) if hasattr(vocoder, "infer") else vocoder(part)
+        sl = slice(i, i + vocoder_batch_size)
+        kw = slice_per_utterance(infer_kwargs, sl, n_items)        # speaker ids follow their utterances
+        audio = vocoder.infer(part, **kw) if hasattr(vocoder, "infer") else vocoder(part)
         if isinstance(audio, tuple):
             audio = audio[0]
         if audio.dim() == 3:
             audio = audio.squeeze(1)
         audio = audio.to(mels.device) if audio.device.type != "cuda" and mels.device.type == "cuda" else audio
         if denoiser is not None:
-            audio = denoiser(audio, strength=denoise_strength).squeeze(1)
+            spk = kw.get("speaker_ids", kw.get("speaker_id"))
+            if spk is not None and getattr(denoiser, "bias_spec", None) is not None and denoiser.bias_spec.shape[0] > 1:
+                audio = denoiser(audio, speaker_ids=spk, strength=denoise_strength).squeeze(1)   # denoiser.py:64-67
+            else:
+                audio = denoiser(audio, strength=denoise_strength).squeeze(1)
         n_valid = [min(n * hop_length, audio.shape[1]) for n in lengths[i:i + vocoder_batch_size]]
         host = pcm16(audio, n_valid, pad, saturate).cpu().numpy()
         out.extend(np.ascontiguousarray(host[j, :n + pad]) for j, n in enumerate(n_valid))

@@ -144,6 +144,13 @@ class WaveGlow(nn.Module):
     def _device(self) -> torch.device:
         return self.upsample.weight.device
 
+    def invalidate(self):
+        """Drop the packed weights; the next `infer` re-packs from the current parameters.  `load_state_dict` and
+        in-place ops on a Parameter bump its version counter and are noticed automatically; edits made through
+        `.data` (`weight.data.zero_()`, a reference-code habit) are not - call this after them."""
+        self._packed, self._packed_key = None, None
+    repack = invalidate
+
     def _ensure_packed(self):
         key = self._weights_key()
         if self._packed is not None and self._packed_key == key:
@@ -209,6 +216,16 @@ class WaveGlow(nn.Module):
         if self.multispeaker and speaker_id is None:
             # the reference fails on a shape mismatch in cond_layers[0] here (glow.py:193-199)
             raise ValueError("this model has speaker embeddings: pass speaker_id / speaker_ids")
+        if self.multispeaker:
+            speaker_id = torch.as_tensor(speaker_id).reshape(-1)
+            if speaker_id.numel() not in (1, spect.shape[0]):
+                # glow.py:195 concatenates the embedding onto the mel along channels: one id per utterance
+                raise ValueError(f"speaker_id must hold 1 or batch = {spect.shape[0]} entries, got {speaker_id.numel()}")
+            n_spk = self.WN[0].speaker_embed.weight.shape[0]
+            if int(speaker_id.min()) < 0 or int(speaker_id.max()) >= n_spk:
+                raise IndexError(f"speaker_id out of range for an embedding table of {n_spk} rows")   # nn.Embedding raises too
+            if speaker_id.numel() == 1 and spect.shape[0] > 1:
+                speaker_id = speaker_id.expand(spect.shape[0])
         pc = self.pack_config
         if spect.dim() != 3 or spect.shape[1] != pc.n_mel:
             raise ValueError(f"spect must be [B, {pc.n_mel}, T_mel], got {tuple(spect.shape)}")

@@ -193,6 +193,14 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         self._packed = None
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
+    def invalidate(self):
+        """Drop the packed weights (and the packed front end); needed only after edits made through `.data`, which do
+        not bump a Parameter's version counter - see cookietts_b200.WaveGlow.invalidate."""
+        self._packed, self._packed_key = None, None
+        if hasattr(self, "_fe_packed"):
+            self._fe_packed, self._fe_key = None, None
+    repack = invalidate
+
     def remove_weightnorm(self):
         return self
 

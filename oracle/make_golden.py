@@ -127,9 +127,35 @@ CASES = {
     "mel20_256": (dict(n_mel_channels=20, n_flows=2, n_layers=2, win_length=64, hop_length=16), 2, 40, 0.9, 43, 11),
 }
 SPEAKERS = {"speaker": [5, 0, 77], "speaker256": [3, 200]}
+# Full-length cases (`python oracle/make_golden.py big`): one utterance of BASELINE.json configs[1] (T_mel = 861, 10 s).
+# mel and z are NOT stored (1.2 MB of noise): tests regenerate them from the seeds with `synthetic_inputs` and check the
+# stored CRC32s, so the file holds only the reference's fp32 and fp64 waveforms.
+BIG_CASES = {
+    "config2_1x861": (dict(), 1, 861, 0.666, 1234, 0),
+}
+
+
+def main_big():
+    import zlib
+    ref_glow = load_reference_glow()
+    outdir = os.path.join(ROOT, "tests", "golden")
+    for name, (kw, batch, t_mel, sigma, wseed, iseed) in BIG_CASES.items():
+        cfg = OracleConfig(**kw)
+        sd = synthetic_state_dict(cfg, wseed)
+        mel, z = synthetic_inputs(cfg, batch, t_mel, iseed)
+        out32 = run_reference(ref_glow, cfg, sd, mel, z, sigma, torch.float32)
+        out64 = run_reference(ref_glow, cfg, sd, mel.astype(np.float64), z.astype(np.float64), sigma, torch.float64)
+        print(f"{name}: out {out32.shape} rms {np.sqrt((out64 ** 2).mean()):.3f} max {np.abs(out64).max():.3f} "
+              f"ref fp32-vs-fp64 max-abs {np.abs(out32 - out64).max():.2e}")
+        np.savez_compressed(os.path.join(outdir, f"{name}.npz"),
+                            config=json.dumps(kw), batch=batch, t_mel=t_mel, sigma=sigma, weight_seed=wseed, input_seed=iseed,
+                            mel_crc32=zlib.crc32(np.ascontiguousarray(mel).tobytes()), z_crc32=zlib.crc32(np.ascontiguousarray(z).tobytes()),
+                            audio_ref_fp32=out32, audio_ref_fp64=out64.astype(np.float64))
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        return main_big()
     ref_glow = load_reference_glow()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)

@@ -81,6 +81,24 @@ def test_speaker_embedding_models(name, precision):
         model.infer(mel, sigma=1.0, z=z)
 
 
+@pytest.mark.parametrize("precision", ["ffma", "bf16x3", "f16f8", "bf16"])
+def test_config2_length_matches_reference_golden(precision):
+    """One utterance of BASELINE config 2 (T_mel = 861, 10 s: 216 tiles, every dilation's halo inside the clip) against
+    the outputs of the unmodified reference run in fp32 and fp64 (tests/golden/config2_1x861.npz)."""
+    from tests.helpers import load_golden_regen
+    cfg, sd, g, mel, z = load_golden_regen("config2_1x861")
+    model = WaveGlow(precision=precision, **module_kwargs(cfg))
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    out = model.infer(torch.from_numpy(mel).cuda(), sigma=float(g["sigma"]), z=torch.from_numpy(z).cuda()).cpu().numpy()
+    ref = g["audio_ref_fp64"]
+    assert out.shape == ref.shape and np.isfinite(out).all()
+    assert max_abs(out, ref) <= TOL[precision]["max_abs"]
+    assert snr_db(ref, out) >= TOL[precision]["snr"]
+    if precision == "ffma":
+        assert max_abs(out, g["audio_ref_fp32"]) <= TOL["ffma"]["max_abs"]
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE-size checks through size-independent properties (the CPU oracle is too slow there)
 # ---------------------------------------------------------------------------------------------

@@ -71,3 +71,17 @@ def test_torch_port_matches_reference(name):
     out = TorchPort(sd, cfg, torch.float32).infer(g["mel"], g["z"], float(g["sigma"]))
     assert max_abs(out, g["audio_ref_fp32"]) < 2e-5
     assert snr_db(g["audio_ref_fp64"], out) > 100.0
+
+
+def test_oracle_port_matches_reference_at_config2_length():
+    """One full-length utterance of BASELINE config 2 (T_mel = 861): the torch-op restatement in fp32 against the
+    reference's fp32 and fp64 outputs (golden made by `python oracle/make_golden.py big`)."""
+    import torch
+    from oracle.waveglow_torch_port import TorchPort
+    from tests.helpers import load_golden_regen
+    cfg, sd, g, mel, z = load_golden_regen("config2_1x861")
+    out = TorchPort(sd, cfg, torch.float32).infer(mel, z, float(g["sigma"]))
+    assert out.shape == g["audio_ref_fp64"].shape
+    assert max_abs(out, g["audio_ref_fp64"]) < 5e-5
+    assert max_abs(out, g["audio_ref_fp32"]) < 5e-5
+    assert snr_db(g["audio_ref_fp64"], out) > 100.0
