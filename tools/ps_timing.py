@@ -5,7 +5,7 @@ import ctypes as C, json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cookietts_b200 import WaveGlow, _cabi
-from cookietts_b200.synthetic import OracleConfig, synthetic_state_dict
+from cookietts_b200.synthetic import ModelConfig as OracleConfig, synthetic_state_dict
 import bench
 from tests.test_gpu_stages import f8_planes
 
@@ -45,6 +45,16 @@ for prec in precs:
             for _ in range(20): run()
             e1.record(); torch.cuda.synchronize()
             res[which] = (e0.elapsed_time(e1) / 20, xo_first, eo_first)
+        # per-CTA clock64 stamps of the persistent kernel: cycles per tile pair
+        dbg = torch.zeros(2 * 148 * 4, dtype=torch.int64, device="cuda")
+        lib.cwg_debug_set_ps_timing(C.c_void_p(dbg.data_ptr())); lib.cwg_debug_set_layer_kernel(1)
+        run(); torch.cuda.synchronize()
+        lib.cwg_debug_set_ps_timing(C.c_void_p(0))
+        dd = dbg.view(-1, 4).cpu().numpy(); dd = dd[dd[:, 2] > 0]
+        cyc = (dd[:, 1] - dd[:, 0]) / dd[:, 2]
+        cyc_info = dict(ctas=int(len(dd)), tiles_min=int(dd[:, 2].min()), tiles_max=int(dd[:, 2].max()),
+                        cycles_per_tile_mean=float(cyc.mean()), cycles_per_tile_min=float(cyc.min()), cycles_per_tile_max=float(cyc.max()),
+                        cta_cycles_max=int((dd[:, 1] - dd[:, 0]).max()))
         lib.cwg_debug_set_layer_kernel(-1)
         (t0, xa, ea), (t1, xb, eb) = res[0], res[1]
         if prec == "f16f8":
@@ -60,7 +70,7 @@ for prec in precs:
                    speedup=round(t0 / t1, 3), alg_tflops_persistent=round(flops / t1 / 1e9, 1),
                    x_out_max_abs_diff=float((da - db).abs().max()) if layer < 7 else None,
                    x_out_identical_bytes=same_bytes if layer < 7 else None,
-                   eo_max_abs_diff=float((ea - eb).abs().max()), eo_max_abs=float(ea.abs().max()))
+                   eo_max_abs_diff=float((ea - eb).abs().max()), eo_max_abs=float(ea.abs().max()), ps_cycles=cyc_info)
         print(json.dumps(rec), flush=True)
         out.append(rec)
     del m
