@@ -15,7 +15,7 @@ MODE_FFMA, MODE_BF16X3, MODE_BF16, MODE_F16F8 = 0, 1, 2, 3
 MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "f16f8": MODE_F16F8}
 EO_PAD = 16
 MAX_GROUP = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CwgConfig(C.Structure):
@@ -28,12 +28,22 @@ WEIGHT_FIELDS = ("cond_w_f32", "cond_w_hi", "cond_w_lo", "w1_f32", "w1_hi", "w1_
                  "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv", "w1_h8", "w1_l8", "w2_h8", "w2_l8")
 
 
+WEIGHT_FIELDS_V3 = ("cond_b_base", "cond_w_spk", "spk_embed")
+
+
 class CwgWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+    _fields_ = ([(n, C.c_void_p) for n in WEIGHT_FIELDS + WEIGHT_FIELDS_V3]
+                + [("speaker_embed_dim", C.c_int32), ("n_speakers", C.c_int32)])
+
+
+class CwgTensor(C.Structure):
+    """cwg_tensor: one state_dict entry (device fp32 data)"""
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
 
 
 EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
-           "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
+           "cwg_state_dict_info", "cwg_packed_bytes", "cwg_pack_workspace_bytes", "cwg_pack_weights", "cwg_packed_view",
+           "cwg_cond_bias", "cwg_nonfinite", "cwg_infer_status", "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
            "cwg_ax_workspace_bytes", "cwg_ax_infer",
            "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer",
            "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise", "cwg_pcm16",
@@ -64,6 +74,23 @@ def load():
     lib.cwg_workspace_bytes.restype = C.c_size_t
     lib.cwg_workspace_bytes.argtypes = [C.POINTER(CwgConfig), C.c_int, C.c_int, C.c_int]
     lib.cwg_launch_count.restype = C.c_int
+    lib.cwg_state_dict_info.restype = C.c_int
+    lib.cwg_state_dict_info.argtypes = [C.POINTER(CwgTensor), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cwg_packed_bytes.restype = C.c_size_t
+    lib.cwg_packed_bytes.argtypes = [C.POINTER(CwgConfig), C.c_int, C.c_int, C.c_int]
+    lib.cwg_pack_workspace_bytes.restype = C.c_size_t
+    lib.cwg_pack_workspace_bytes.argtypes = [C.POINTER(CwgConfig), C.c_int]
+    lib.cwg_pack_weights.restype = C.c_int
+    lib.cwg_pack_weights.argtypes = [C.POINTER(CwgConfig), C.c_int, C.POINTER(CwgTensor), C.c_int, C.c_void_p, C.c_size_t,
+                                     C.c_void_p, C.c_size_t, C.POINTER(CwgWeights), C.c_void_p]
+    lib.cwg_packed_view.restype = C.c_int
+    lib.cwg_packed_view.argtypes = [C.POINTER(CwgConfig), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(CwgWeights)]
+    lib.cwg_nonfinite.restype = C.c_int
+    lib.cwg_nonfinite.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.cwg_infer_status.restype = C.c_int
+    lib.cwg_infer_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cwg_cond_bias.restype = C.c_int
+    lib.cwg_cond_bias.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.cwg_launch_count.argtypes = [C.POINTER(CwgConfig), C.c_int]
     lib.cwg_infer.restype = C.c_int
     lib.cwg_infer.argtypes = [C.POINTER(CwgConfig), C.POINTER(CwgWeights), C.c_int,

@@ -17,9 +17,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local int* g_range_flag = nullptr;
+int* range_flag() { return g_range_flag; }
+void set_range_flag(int* flag) { g_range_flag = flag; }
+
 namespace {
 
 struct Workspace {
+  int* status;            // first word of the workspace: see cwg_infer in cwg.h
   // FFMA mode
   float *x[2], *h2, *pre, *acts;
   // tensor-core modes (each: hi plane then lo plane)
@@ -62,6 +67,7 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return (char*)base + o; };
   memset(ws, 0, sizeof(*ws));
+  ws->status = (int*)take(1024);
   ws->eo = (float*)take((size_t)d.BT * CWG_EO_PAD * sizeof(float));
   if (mode == CWG_MODE_FFMA) {
     ws->x[0] = (float*)take((size_t)d.BT * d.C * 4);
@@ -147,6 +153,7 @@ int cwg_launch_count(const cwg_config* cfg, int mode) {
   int per_layer = mode == CWG_MODE_FFMA ? 3 : (cfg->n_channels == 512 ? 2 : 1);
   int cond = mode == CWG_MODE_FFMA ? 1 : 1;
   int once = mode == CWG_MODE_FFMA ? 1 : 2;   // init boundary (+ mel4 im2col)
+  if (mode == CWG_MODE_F16F8) once += 1;   // non-finite scan of the waveform (range guard)
   return once + cfg->n_flows * (cond + per_layer * cfg->n_layers + 1);
 }
 
@@ -204,6 +211,17 @@ int cwg_flow_boundary(const cwg_config* cfg, const cwg_weights* w, int mode,
                               audio, eo, x_out, (cudaStream_t)cuda_stream);
 }
 
+int cwg_infer_status(const void* workspace, int32_t* status, void* cuda_stream) {
+  CWG_REQUIRE(workspace && status, "cwg_infer_status: NULL argument");
+  CWG_CHECK_CUDA(cudaMemcpyAsync(status, workspace, sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  return 0;
+}
+
+int cwg_nonfinite(const float* x, size_t n, int32_t* flag, void* cuda_stream) {
+  CWG_REQUIRE(x && flag, "cwg_nonfinite: NULL argument");
+  return launch_nonfinite(x, n, (int*)flag, (cudaStream_t)cuda_stream, true);
+}
+
 int cwg_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
               const float* mel, const float* cond_bias, const float* z, float sigma,
               float* audio, void* workspace, size_t workspace_bytes,
@@ -231,6 +249,11 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
   const int xfmt = mode_xfmt(mode);
   const int F = cfg->n_flows, L = cfg->n_layers;
 
+  // status word (first 4 bytes of the workspace): bit 1 (2) = an fp16 plane of CWG_MODE_F16F8 left the fp16 range,
+  // bit 0 (1) = the waveform holds a NaN / Inf.  Zero in the other modes.
+  CWG_CHECK_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(int), s));
+  set_range_flag(mode == CWG_MODE_F16F8 ? ws.status : nullptr);
+  auto run = [&]() -> int {
   // audio = sigma * z (glow.py:326; early z already sits in its final columns), x = start_{F-1}(audio_0)
   void* x0 = tc ? (void*)ws.xb[0] : (void*)ws.x[0];
   if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s)) return r;
@@ -253,6 +276,12 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
     // coupling inverse + W^-1 of flow k, then start conv of flow k-1 (glow.py:329-347, :189)
     if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s)) return r;
   }
+  return 0;
+  };
+  const int rc = run();
+  set_range_flag(nullptr);
+  if (rc) return rc;
+  if (mode == CWG_MODE_F16F8) return launch_nonfinite(audio, (size_t)batch * t_mel * cfg->hop_length, ws.status, s, false);
   return 0;
 }
 

@@ -75,6 +75,13 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
                          const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2, int ignore_nan = 0);
 
+// CWG_MODE_F16F8 range guard: device status word the producers of fp16 planes OR bit 1 (value 2) into when a value leaves
+// +-65504 (set by cwg_infer around its launches; NULL = no check).  Host-side, thread-local.
+int* range_flag();
+void set_range_flag(int* flag);
+
+int launch_nonfinite(const float* x, size_t n, int* flag, cudaStream_t s, bool clear);
+
 int launch_mel_up(int xfmt, const float* mel, void* out, int B, int M, int frames, int frames_padded, int Tp, int H,
                   int linear, cudaStream_t s);
 

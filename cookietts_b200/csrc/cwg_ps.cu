@@ -44,6 +44,7 @@ struct PsArgs {
   int w1_row0, w2_row0;
   int has_res, first;
   int pairs_per_utt, n_pairs;
+  int* range_flag;        // f16f8, last residual layer only: |= 2 when x_new leaves the fp16 range (else NULL)
   long long* dbg;         // optional: per CTA {start, end, tiles} clock64 stamps
 };
 
@@ -504,6 +505,12 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           }
           if (F8) {
             uint32_t nh[8], nl[8], l8[4], h8[4];
+            if (a.range_flag) {      // the layer that consumes this x has no residual: an Inf here would not reach the waveform
+              float mx = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fabsf(r[j]));
+              if (valid && !(mx < 65504.f)) atomicOr(a.range_flag, 2);
+            }
             split16_f8_words(r, nh, nl, l8, h8);
             *reinterpret_cast<uint4*>(u_hi + o0) = make_uint4(nh[0], nh[1], nh[2], nh[3]);
             *reinterpret_cast<uint4*>(u_hi + o1) = make_uint4(nh[4], nh[5], nh[6], nh[7]);
@@ -670,6 +677,7 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.pairs_per_utt = (tiles + 1) / 2;                // an odd tile count gets one tile fully past T' (TMA zero-fills / clips)
   a.n_pairs = a.pairs_per_utt * d.B;
   a.dbg = g_ps_dbg;
+  a.range_flag = (npass == 2 && layer == d.L - 2) ? range_flag() : nullptr;
   int ncl = 0;
   if (int r = (npass == 3 ? max_clusters<3>(&ncl) : npass == 2 ? max_clusters<2>(&ncl) : max_clusters<1>(&ncl))) return r;
   if (ncl > a.n_pairs) ncl = a.n_pairs;

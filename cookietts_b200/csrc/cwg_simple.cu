@@ -132,6 +132,7 @@ struct BoundaryP {
   const float* z; float sigma;
   float* audio; const float* eo;
   const float* winv;          // [MAX_GROUP][MAX_GROUP] of the mixing flow
+  int* range_flag;            // CWG_MODE_F16F8: |= 2 when a start-conv output leaves the fp16 range (may be NULL)
   const float* start_w;       // [C][MAX_GROUP/2] of flow_next
   const float* start_b;       // [C]
   void* x_out;
@@ -302,6 +303,12 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
         uint8_t* p8 = reinterpret_cast<uint8_t*>(p.x_out) + 4 * plane;
         uint32_t h[4], l[4];
         float hf[8], df[8];
+        if (p.range_flag) {
+          float mx = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(x[i]));
+          if (!(mx < 65504.f)) atomicOr(p.range_flag, 2);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
@@ -445,6 +452,7 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
   p.BT = d.BT; p.G = d.G; p.C = d.C;
   p.init = z != nullptr; p.do_flow = flow_done >= 0; p.do_start = flow_next >= 0; p.do_mix = mix_flow >= 0;
   p.z = z; p.sigma = sigma; p.audio = audio; p.eo = eo; p.x_out = x_out; p.ignore_nan = ignore_nan;
+  p.range_flag = xfmt == 2 ? range_flag() : nullptr;
   if (p.do_flow) flow_channels(cfg, flow_done, &p.n_rem, &p.n_half);
   if (p.do_mix) {
     int nh;
@@ -467,6 +475,32 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
     if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
     else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);
   }
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// non-finite scan of a result buffer: *flag |= 1 when any element is NaN / Inf (128-bit loads, grid-stride)
+__global__ void k_nonfinite(const float* __restrict__ x, size_t n, int* __restrict__ flag) {
+  const size_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    // |v| < inf is false for NaN and for +-Inf
+    bad |= !(fabsf(v.x) < INFINITY) | !(fabsf(v.y) < INFINITY) | !(fabsf(v.z) < INFINITY) | !(fabsf(v.w) < INFINITY);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) bad |= !(fabsf(x[(n4 << 2) + threadIdx.x]) < INFINITY);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+int launch_nonfinite(const float* x, size_t n, int* flag, cudaStream_t s, bool clear) {
+  CWG_REQUIRE(((uintptr_t)x & 15) == 0, "cwg_nonfinite: buffer must be 16-byte aligned");
+  if (clear) CWG_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  if (n == 0) return 0;
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks == 0) blocks = 1;
+  k_nonfinite<<<(unsigned)blocks, 256, 0, s>>>(x, n, flag);
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

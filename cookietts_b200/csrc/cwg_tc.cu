@@ -53,6 +53,7 @@ struct CondArgs {
   int M, Tm, B;
   int w_row0;             // flow * P * H
   int nkb;                // KC / 64
+  int* range_flag;        // f16f8: |= 2 when an H2 value leaves the fp16 range (may be NULL)
 };
 
 template <int NPASS>
@@ -144,6 +145,12 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         for (int q = 0; q < 4; ++q) {
           float4 bb = __ldg(bias4 + c * 4 + q);
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        }
+        if (F8 && a.range_flag) {
+          float mx = 0.f;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) mx = fmaxf(mx, fabsf(v[q]));
+          if (!(mx < 65504.f)) atomicOr(a.range_flag, 2);
         }
         uint8_t* thi = smem + ((c >> 2) & 1) * TILE_A;
         if (F8) store_split16_f8(v, thi, nullptr, smem + 2 * TILE_A, smem + 3 * TILE_A, row, (c & 3) * 2, c & 7);
@@ -274,6 +281,12 @@ k_cond_tc2(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ 
         for (int q = 0; q < 4; ++q) {
           float4 bb = __ldg(bias4 + c * 4 + q);
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        }
+        if (F8 && a.range_flag) {
+          float mx = 0.f;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) mx = fmaxf(mx, fabsf(v[q]));
+          if (!(mx < 65504.f)) atomicOr(a.range_flag, 2);
         }
         uint8_t* thi = smem + ((c >> 2) & 1) * TILE_A;
         if (F8) store_split16_f8(v, thi, nullptr, smem + 2 * TILE_A, smem + 3 * TILE_A, row, (c & 3) * 2, c & 7);
@@ -899,6 +912,7 @@ int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, con
   CondArgs a{};
   a.bias = cond_bias + (size_t)flow * d.H; a.bias_bstride = d.F * d.H;
   a.M = (int)rows; a.Tm = d.Tm; a.B = d.B; a.w_row0 = flow * (int)ncol; a.nkb = d.KCp / 64;
+  a.range_flag = npass == 2 ? range_flag() : nullptr;
   dim3 grid(d.P, (unsigned)((rows + 127) / 128));
   static const int use_2sm = [] { const char* e = getenv("CWG_COND_2SM"); return e && e[0] == '1'; }();
   if (use_2sm) {

@@ -30,6 +30,7 @@ class ModelConfig:
     speaker_embed_dim: int = 0
     rezero: bool = False
     cond_hidden: int = 256  # literal `hidden_dim = 256`, glow.py:153
+    end_scale: float = 1.0  # synthetic checkpoints only: multiplier on `end` ~ N(0, 0.02) ("trained-scale" stress cases)
 
     def flow_channels(self) -> List[Tuple[int, int]]:
         """(n_remaining_channels, n_half) per flow k, glow.py:251-264."""
@@ -88,8 +89,8 @@ def synthetic_state_dict(cfg: ModelConfig, seed: int = 1234) -> Dict[str, np.nda
             wn_conv(p + f".res_skip_layers.{i}", 2 * C if i < L - 1 else C, C, 1)
             if cfg.rezero:
                 sd[p + f".alpha_i.{i}"] = (rs.uniform(size=1) * 0.02 + 0.09).astype(np.float32)
-        sd[p + ".end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
-        sd[p + ".end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
+        sd[p + ".end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02 * cfg.end_scale).astype(np.float32)
+        sd[p + ".end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02 * cfg.end_scale).astype(np.float32)
         if cfg.speaker_embed_dim:       # nn.Embedding(512, E) scaled by 0.05 at init, glow.py:131-134
             sd[p + ".speaker_embed.weight"] = (rs.standard_normal((512, cfg.speaker_embed_dim)) * 0.5).astype(np.float32)
     return sd

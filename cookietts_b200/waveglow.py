@@ -18,8 +18,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _cabi
-from .packing import PackConfig, pack_state_dict
+from . import _cabi, _torch_ops
+from .packing import PackConfig
 
 
 class Invertible1x1Conv(nn.Module):
@@ -75,7 +75,7 @@ class WaveGlow(nn.Module):
     def __init__(self, yoyo=False, yoyo_WN=False, n_mel_channels=80, n_flows=12, n_group=8,
                  n_early_every=4, n_early_size=2, memory_efficient=False, spect_scaling=False,
                  upsample_mode="normal", WN_config=None, win_length=1024, hop_length=256,
-                 precision: str = "bf16x3"):
+                 precision: str = "bf16x3", range_guard: bool = True):
         super().__init__()
         if yoyo or yoyo_WN:
             raise ValueError("yoyo models select a different reference class (efficient_model*), not glow.WaveGlow")
@@ -94,6 +94,9 @@ class WaveGlow(nn.Module):
         self.n_flows, self.n_group = n_flows, n_group
         self.n_early_every, self.n_early_size = n_early_every, n_early_size
         self.precision = precision
+        self.range_guard = range_guard     # f16f8: check the fp16 range after every infer and fall back to bf16x3
+        self.last_status = 0
+        self.fallbacks = 0
         self.upsample = nn.ConvTranspose1d(n_mel_channels, n_mel_channels, win_length, stride=hop_length)
         self.WN = nn.ModuleList()
         self.convinv = nn.ModuleList()
@@ -108,9 +111,9 @@ class WaveGlow(nn.Module):
             self.convinv.append(Invertible1x1Conv(n_rem))
             self.WN.append(WN(n_half, n_mel_channels * n_group, **WN_config))
         self.n_remaining_channels = self.pack_config.flow_channels()[-1][0]
-        self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
-        self._workspace = None
+        self._packs = {}
 
     # ------------------------------------------------------------------ checkpoint compatibility
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -125,7 +128,7 @@ class WaveGlow(nn.Module):
                 sd[k[:-7] + ".weight_g"] = norm.to(v.dtype)
             else:
                 sd[k] = v
-        self._packed = None
+        self._packed, self._packed_key, self._packs = None, None, {}
         return super().load_state_dict(sd, strict=strict, **kw)
 
     @staticmethod
@@ -139,7 +142,7 @@ class WaveGlow(nn.Module):
 
     # ------------------------------------------------------------------ packing cache
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision,)
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _device(self) -> torch.device:
         return self.upsample.weight.device
@@ -148,37 +151,75 @@ class WaveGlow(nn.Module):
         """Drop the packed weights; the next `infer` re-packs from the current parameters.  `load_state_dict` and
         in-place ops on a Parameter bump its version counter and are noticed automatically; edits made through
         `.data` (`weight.data.zero_()`, a reference-code habit) are not - call this after them."""
-        self._packed, self._packed_key = None, None
+        self._packed, self._packed_key, self._packs = None, None, {}
     repack = invalidate
 
-    def _ensure_packed(self):
+    def _ensure_packed(self, precision: Optional[str] = None):
+        """Packs the checkpoint on the device (torch.ops.cookietts_b200.waveglow_pack -> cwg_pack_weights, fp64).
+        One blob per precision mode in use (the module's own, plus bf16x3 once the f16f8 range guard needs it)."""
+        precision = precision or self.precision
         key = self._weights_key()
-        if self._packed is not None and self._packed_key == key:
-            return
-        dev = self._device()
-        planes = {"ffma": ("f32",), "f16f8": ("f16f8",)}.get(self.precision, ("hi", "lo"))
-        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
-        pk = pack_state_dict(sd, self.pack_config, planes=planes)
-        dev_pk = {}
-        for name, arr in pk.items():
-            if arr.dtype == np.uint16:
-                arr = arr.view(np.int16)
-            dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
-        w = _cabi.CwgWeights()
-        for f in _cabi.WEIGHT_FIELDS:
-            setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
-        self._packed, self._packed_key, self._cw = dev_pk, key, w
-        self._ccfg = _cabi.make_config(self.pack_config)
-        if self.multispeaker:
-            self._spk_tables = torch.stack([wn.speaker_embed.weight.detach().float() for wn in self.WN]).to(dev)
+        if self._packed_key != key:
+            self._packs, self._packed_key = {}, key
+        if precision not in self._packs:
+            ops, lib = _torch_ops.load(), _cabi.load()
+            mode = _cabi.MODES[precision]
+            sd = self.state_dict()
+            names = list(sd.keys())
+            self._cfg_list = _torch_ops.config_list(self.pack_config)
+            self._embed_dim = self.pack_config.speaker_embed_dim
+            self._n_speakers = int(self.WN[0].speaker_embed.weight.shape[0]) if self.multispeaker else 0
+            blob = ops.waveglow_pack([sd[k] for k in names], "\n".join(names), self._cfg_list, mode)
+            self._ccfg = _cabi.make_config(self.pack_config)
+            w = _cabi.CwgWeights()      # ctypes view of the same blob for the stage-level entry points (tests, tools)
+            base = (blob.data_ptr() + 255) // 256 * 256
+            _cabi.check(lib.cwg_packed_view(self._ccfg, mode, self._embed_dim, self._n_speakers, base, blob.numel() - 256, w))
+            self._packs[precision] = (blob, w)
+        if precision == self.precision:
+            self._packed, self._cw = self._packs[precision]
+
+    def packed_views(self) -> Dict[str, torch.Tensor]:
+        """name -> tensor views into the packed blob (the arrays of cwg_weights this mode uses), for tests and tools."""
+        self._ensure_packed()
+        pc, blob, w = self.pack_config, self._packed, self._cw
+        F, L, C, H = pc.n_flows, pc.n_layers, pc.n_channels, pc.cond_hidden
+        kcp = -(-(pc.taps * pc.n_mel) // 64) * 64
+        E, S = max(self._embed_dim, 1), self._n_speakers
+        shapes = {"cond_w": (F, pc.phases * H, kcp), "w1": (F, L, 2 * C, pc.k1), "w2": (F, L, C + _cabi.EO_PAD, C)}
+        small = {"b1": (F, L, 2 * C), "b2": (F, L, C), "eo_b": (F, _cabi.EO_PAD), "start_w": (F, C, _cabi.MAX_GROUP // 2),
+                 "start_b": (F, C), "winv": (F, _cabi.MAX_GROUP, _cabi.MAX_GROUP), "cond_b_base": (F, H), "cond_w_spk": (F, H, E)}
+        if self._embed_dim:
+            small["spk_embed"] = (F, S, self._embed_dim)
+        f16 = torch.float16 if self.precision == "f16f8" else torch.bfloat16
+
+        def at(ptr, shape, dtype):
+            n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+            off = ptr - blob.data_ptr()
+            return blob[off:off + n].view(dtype).view(shape)
+        out = {}
+        for name, shape in shapes.items():
+            for suffix, dtype in (("_f32", torch.float32), ("_hi", f16), ("_lo", f16), ("_h8", torch.float8_e5m2), ("_l8", torch.float8_e5m2)):
+                ptr = getattr(w, name + suffix, None)
+                if ptr:
+                    out[name + suffix] = at(ptr, shape, dtype)
+        for name, shape in small.items():
+            out[name] = at(getattr(w, name), shape, torch.float32)
+        return out
 
     def _cond_bias(self, batch: int, speaker_ids) -> torch.Tensor:
-        base = self._packed["cond_b_base"]                           # [F, H]
-        bias = base.unsqueeze(0).expand(batch, -1, -1)
-        if self.multispeaker and speaker_ids is not None:            # glow.py:193-196
-            emb = self._spk_tables[:, speaker_ids.to(base.device).long()]          # [F, B, E]
-            bias = bias + torch.einsum("fhe,fbe->bfh", self._packed["cond_w_spk"], emb)
-        return bias.contiguous()
+        """[B, F, H] folded cond-chain bias (cwg_cond_bias; carries the speaker-embedding branch, glow.py:193-196)."""
+        lib = _cabi.load()
+        dev = self._device()
+        out = torch.empty(batch, self.pack_config.n_flows, self.pack_config.cond_hidden, device=dev)
+        ids = None
+        if self.multispeaker and speaker_ids is not None:
+            ids = torch.as_tensor(speaker_ids).reshape(-1).to(device=dev, dtype=torch.long)
+            if ids.numel() == 1 and batch > 1:
+                ids = ids.expand(batch)
+            ids = ids.contiguous()
+        _cabi.check(lib.cwg_cond_bias(self._ccfg, self._cw, ids.data_ptr() if ids is not None else None, batch,
+                                      out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        return out
 
     def draw_z(self, batch: int, t_mel: int, generator=None) -> torch.Tensor:
         """Standard-normal latent [B, T] drawn in the order of the reference's draws
@@ -207,7 +248,6 @@ class WaveGlow(nn.Module):
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("cookietts_b200.WaveGlow.infer needs the module on a CUDA device (no CPU fallback)")
-        lib = _cabi.load()
         if self.precision not in _cabi.MODES:
             raise ValueError(f"precision must be one of {list(_cabi.MODES)}")
         mode = _cabi.MODES[self.precision]
@@ -217,7 +257,7 @@ class WaveGlow(nn.Module):
             # the reference fails on a shape mismatch in cond_layers[0] here (glow.py:193-199)
             raise ValueError("this model has speaker embeddings: pass speaker_id / speaker_ids")
         if self.multispeaker:
-            speaker_id = torch.as_tensor(speaker_id).reshape(-1)
+            speaker_id = torch.as_tensor(speaker_id).reshape(-1).cpu()          # host copy: the range check costs no kernel
             if speaker_id.numel() not in (1, spect.shape[0]):
                 # glow.py:195 concatenates the embedding onto the mel along channels: one id per utterance
                 raise ValueError(f"speaker_id must hold 1 or batch = {spect.shape[0]} entries, got {speaker_id.numel()}")
@@ -226,6 +266,9 @@ class WaveGlow(nn.Module):
                 raise IndexError(f"speaker_id out of range for an embedding table of {n_spk} rows")   # nn.Embedding raises too
             if speaker_id.numel() == 1 and spect.shape[0] > 1:
                 speaker_id = speaker_id.expand(spect.shape[0])
+            speaker_id = speaker_id.long().contiguous()
+        else:
+            speaker_id = None
         pc = self.pack_config
         if spect.dim() != 3 or spect.shape[1] != pc.n_mel:
             raise ValueError(f"spect must be [B, {pc.n_mel}, T_mel], got {tuple(spect.shape)}")
@@ -235,38 +278,34 @@ class WaveGlow(nn.Module):
             return torch.zeros(batch, t_mel * pc.hop_length, device=dev)
         with torch.cuda.device(dev):
             self._ensure_packed()
+            ops = _torch_ops.load()
             T = t_mel * pc.hop_length
             if z is None:
                 z = self.draw_z(batch, t_mel)
             z = z.to(device=dev, dtype=torch.float32).contiguous()
             if tuple(z.shape) != (batch, T):
                 raise ValueError(f"z must be [B, T_mel*hop] = {(batch, T)}, got {tuple(z.shape)}")
-            cond_bias = self._cond_bias(batch, speaker_id)
-            nbytes = lib.cwg_workspace_bytes(self._ccfg, mode, batch, t_mel)
-            if nbytes == 0:
-                raise _cabi.CwgError(lib.cwg_last_error().decode())
-            if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != dev:
-                self._workspace = None
-                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-            ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
-            audio = torch.empty(batch, T, device=dev, dtype=torch.float32)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            ws_bytes = self._workspace.numel() - (ws_ptr - self._workspace.data_ptr())
-            if layer_events is None:
-                _cabi.check(lib.cwg_infer(self._ccfg, self._cw, mode, mel.data_ptr(), cond_bias.data_ptr(),
-                                          z.data_ptr(), float(sigma), audio.data_ptr(), ws_ptr, ws_bytes,
-                                          batch, t_mel, stream))
-            else:
-                import ctypes
+            ev_b, ev_e = [], []
+            if layer_events is not None:
                 begin, end = layer_events
                 for e in list(begin) + list(end):          # torch creates the handle lazily
                     if not e.cuda_event:
                         e.record(torch.cuda.current_stream(dev))
-                arr_b = (ctypes.c_void_p * len(begin))(*[e.cuda_event for e in begin])
-                arr_e = (ctypes.c_void_p * len(end))(*[e.cuda_event for e in end])
-                _cabi.check(lib.cwg_infer_profiled(self._ccfg, self._cw, mode, mel.data_ptr(), cond_bias.data_ptr(),
-                                                   z.data_ptr(), float(sigma), audio.data_ptr(), ws_ptr, ws_bytes,
-                                                   batch, t_mel, stream, arr_b, arr_e, len(begin)))
+                ev_b, ev_e = [int(e.cuda_event) for e in begin], [int(e.cuda_event) for e in end]
+            audio, status = ops.waveglow_infer(self._packed, self._cfg_list, mode, self._embed_dim, self._n_speakers, mel,
+                                               speaker_id, z, float(sigma), ev_b, ev_e)
+            if self.precision == "f16f8" and self.range_guard:
+                # fp16 hi planes: values beyond +-65504 (or a NaN / Inf waveform) are flagged on the device (cwg_infer_status);
+                # reading the flag synchronises this call.  On a hit the call is repeated in bf16x3 (fp32 exponent range).
+                self.last_status = int(status.item())
+                if self.last_status:
+                    import warnings
+                    warnings.warn(f"cookietts_b200.WaveGlow: f16f8 range guard tripped (status {self.last_status}); "
+                                  "re-running this call in bf16x3", RuntimeWarning)
+                    self.fallbacks += 1
+                    self._ensure_packed("bf16x3")
+                    audio, _ = ops.waveglow_infer(self._packs["bf16x3"][0], self._cfg_list, _cabi.MODES["bf16x3"], self._embed_dim,
+                                                  self._n_speakers, mel, speaker_id, z, float(sigma), [], [])
         return audio
 
     def launch_count(self) -> int:

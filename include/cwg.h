@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CWG_ABI_VERSION 2
+#define CWG_ABI_VERSION 3
 
 /* Arithmetic modes of the WN contractions. */
 #define CWG_MODE_FFMA   0   /* fp32 weights/activations, CUDA-core FFMA (exact fp32 semantics)        */
@@ -86,10 +86,54 @@ typedef struct cwg_weights {
   const uint8_t*  w1_l8;        /* e5m2((w1 - fp16(w1)) * 2^8)                          */
   const uint8_t*  w2_h8;        /* the same two planes of w2 ([F][L][N2][C])            */
   const uint8_t*  w2_l8;
+  /* ABI 3: what cwg_cond_bias needs (filled by cwg_pack_weights; NULL / 0 when the caller passes its own cond_bias) */
+  const float*    cond_b_base;  /* [F][H]        bias of the folded cond chain without the speaker branch          */
+  const float*    cond_w_spk;   /* [F][H][E]     speaker columns of cond_layers.1 * cond_layers.0 (glow.py:193-199) */
+  const float*    spk_embed;    /* [F][S][E]     WN.k.speaker_embed.weight of every flow (glow.py:144-147)          */
+  int32_t         speaker_embed_dim;   /* E (0: single-speaker model) */
+  int32_t         n_speakers;          /* S: rows of the embedding tables */
 } cwg_weights;
 
 int         cwg_abi_version(void);
 const char* cwg_last_error(void);
+
+/* ---- checkpoint -> packed weights (replaces the per-forward weight handling of glow.py:136-186, 74-83, 238-241) ----
+ * One entry of the reference checkpoint's state_dict: the parameter names of glow.py, e.g.
+ * "upsample.weight", "WN.3.in_layers.2.weight_g", "WN.3.in_layers.2.weight_v", "WN.3.cond_layers.0.bias",
+ * "WN.3.end.weight", "convinv.3.conv.weight", "WN.3.speaker_embed.weight", "WN.3.alpha_i.2".  Weight-normed
+ * (weight_g / weight_v) and plain (weight) layouts are both accepted, per tensor. */
+typedef struct cwg_tensor {
+  const char*  name;
+  const float* data;        /* DEVICE pointer, fp32, contiguous in the torch layout */
+  int32_t      ndim;
+  int64_t      shape[4];
+} cwg_tensor;
+
+/* speaker_embed_dim / n_speakers (shape of WN.0.speaker_embed.weight, 0 if absent) and rezero (WN.0.alpha_i.0 present)
+ * are properties of the checkpoint; any out pointer may be NULL. */
+int cwg_state_dict_info(const cwg_tensor* sd, int n_tensors, int* speaker_embed_dim, int* n_speakers, int* rezero);
+
+/* Bytes of the packed blob for (cfg, mode) and of the fp64 scratch cwg_pack_weights needs.  0 on error. */
+size_t cwg_packed_bytes(const cwg_config* cfg, int mode, int speaker_embed_dim, int n_speakers);
+size_t cwg_pack_workspace_bytes(const cwg_config* cfg, int speaker_embed_dim);
+
+/* Folds the checkpoint into the arrays of cwg_weights, in fp64, on the device, on `cuda_stream`:
+ * weight-norm folded; cond_layers[1]*cond_layers[0]*squeeze*ConvTranspose1d folded into cond_w; cond_layers[2] appended to
+ * every in_layer's K; `end` folded into the skip rows of res_skip; ReZero alphas folded; W^-1 of every
+ * Invertible1x1Conv.  `packed` (256-byte aligned, cwg_packed_bytes) receives the planes `mode` uses; *out points into it.
+ * Only the planes of `mode` are written (BF16 and BF16X3 share theirs). */
+int cwg_pack_weights(const cwg_config* cfg, int mode, const cwg_tensor* sd, int n_tensors,
+                     void* packed, size_t packed_bytes, void* workspace, size_t workspace_bytes,
+                     cwg_weights* out, void* cuda_stream);
+
+/* Re-derives the cwg_weights pointers of a blob written by cwg_pack_weights (pure host arithmetic). */
+int cwg_packed_view(const cwg_config* cfg, int mode, int speaker_embed_dim, int n_speakers,
+                    void* packed, size_t packed_bytes, cwg_weights* out);
+
+/* cond_bias [batch][F][H] for cwg_infer / cwg_cond: cond_b_base plus, for multispeaker checkpoints, the speaker-embedding
+ * branch glow.py:193-196 (speaker_ids: DEVICE int64 [batch]; required when speaker_embed_dim > 0, else ignored). */
+int cwg_cond_bias(const cwg_config* cfg, const cwg_weights* w, const int64_t* speaker_ids, int batch,
+                  float* cond_bias, void* cuda_stream);
 
 /* Bytes of device workspace cwg_infer needs for (batch, t_mel) in `mode`. 0 on error. */
 size_t cwg_workspace_bytes(const cwg_config* cfg, int mode, int batch, int t_mel);
@@ -115,6 +159,19 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
                        float* audio, void* workspace, size_t workspace_bytes,
                        int batch, int t_mel, void* cuda_stream,
                        void** layer_ev_begin, void** layer_ev_end, int n_events);
+
+/* Status word of the last cwg_infer / cwg_infer_profiled that used `workspace` (the first 4 bytes of the workspace, DEVICE
+ * memory), copied to the DEVICE int32 *status on `cuda_stream`:  0 = fine;  bit 0 (1) = the waveform holds a NaN / Inf;
+ * bit 1 (2) = CWG_MODE_F16F8 only: a value of an fp16 operand plane (cond hidden vector, `start` output, residual stream
+ * entering the last layer) left +-65504, i.e. the result is not trustworthy - re-run in CWG_MODE_BF16X3 (fp32 range).
+ * Other modes always report 0 (they have fp32's exponent range; use cwg_nonfinite for a NaN scan). */
+int cwg_infer_status(const void* workspace, int32_t* status, void* cuda_stream);
+
+/* Range guard of the fp16-based mode: *flag (DEVICE int32) = 1 when x[0..n) holds a NaN or Inf, else 0.  In CWG_MODE_F16F8
+ * the residual stream and the cond hidden vector are stored as fp16 hi + lo planes: a value beyond +-65504 becomes Inf
+ * there, turns into NaN in the next GEMM and reaches the waveform, so a finite waveform proves no overflow happened.
+ * cookietts_b200.WaveGlow re-runs the call in CWG_MODE_BF16X3 (fp32 range) when the flag is set. */
+int cwg_nonfinite(const float* x, size_t n, int32_t* flag, void* cuda_stream);
 
 /* Number of kernels cwg_infer launches for this configuration (bench.py's gpu_launches). */
 int cwg_launch_count(const cwg_config* cfg, int mode);

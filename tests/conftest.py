@@ -31,7 +31,7 @@ def pytest_collection_modifyitems(config, items):
 def _built_library():
     """Build cookietts_b200/libcwg.so if the tree is fresh (nvcc cross-compiles without a GPU)."""
     lib = os.path.join(ROOT, "cookietts_b200", "libcwg.so")
-    if not os.path.exists(lib):
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, "cookietts_b200", "_cwg_torch.so")):
         import subprocess
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "cookietts_b200", "csrc"), "-j4"],
                               stdout=subprocess.DEVNULL)

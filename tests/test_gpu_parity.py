@@ -225,3 +225,47 @@ def test_infer_is_cuda_graph_capturable(precision):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(static_out, m.infer(mel2, sigma=0.666, z=z2))
+
+
+# ---------------------------------------------------------------------------------------------
+# "trained-scale" weights and the f16f8 range guard
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", ["ffma", "bf16x3", "f16f8"])
+def test_trained_scale_stress_checkpoint(precision):
+    """`end` x2.5 (tests/golden/stress.npz, from the unmodified reference): |log_s| ~ 1-2, waveform peak 54, residual stream
+    O(100).  The reference's own fp32 run is 9e-5 off its fp64 run here, so the 1e-3 bar is applied to the waveform
+    normalised to its peak (what it means for audio in [-1, 1]); SNR is scale-free."""
+    out, g = run("stress", precision)
+    ref = g["audio_ref_fp64"]
+    peak = float(np.abs(ref).max())
+    assert peak > 20.0 and np.isfinite(out).all()
+    assert max_abs(out, ref) <= (1e-4 if precision == "ffma" else 1e-3) * peak
+    assert snr_db(ref, out) >= (100.0 if precision == "ffma" else 60.0)
+
+
+def test_f16f8_range_guard_falls_back_to_bf16x3():
+    """`end` x5 makes the flow explode (reference: waveform peak 2e7): the residual stream leaves the fp16 range, the guard
+    (cwg_infer_status) must trip and the call must come back as the bf16x3 result, not as silent garbage."""
+    import warnings
+    from oracle.waveglow_oracle import OracleConfig, synthetic_state_dict, synthetic_inputs
+    cfg = OracleConfig(end_scale=5.0)
+    sd = synthetic_state_dict(cfg, 1234)
+    mel, z = synthetic_inputs(cfg, 1, 86, 0)
+    outs = {}
+    for precision in ("f16f8", "bf16x3"):
+        m = WaveGlow(precision=precision, **module_kwargs(cfg))
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        m = m.cuda().eval()
+        with warnings.catch_warnings(record=True) as wlist:
+            warnings.simplefilter("always")
+            outs[precision] = m.infer(torch.from_numpy(mel).cuda(), sigma=0.666, z=torch.from_numpy(z).cuda()).cpu().numpy()
+        if precision == "f16f8":
+            assert m.last_status != 0 and m.fallbacks == 1
+            assert any("range guard" in str(w.message) for w in wlist)
+    assert np.array_equal(outs["f16f8"], outs["bf16x3"])
+    # and a benign checkpoint never trips it
+    m = _model("f16f8")
+    melb, zb = synthetic_inputs(OracleConfig(), 2, 40, 3)
+    m.infer(torch.from_numpy(melb).cuda(), sigma=0.666, z=torch.from_numpy(zb).cuda())
+    assert m.last_status == 0 and m.fallbacks == 0

@@ -92,7 +92,7 @@ def test_cond_stage(models, flow):
     h_f = torch.zeros(B, tp, H, device="cuda")
     run_cond(models["ffma"], _cabi.MODE_FFMA, flow, mel, h_f)
     # fp64 evaluation of the packed form
-    pk = models["ffma"]._packed
+    pk = models["ffma"].packed_views()
     mel4 = torch.zeros(B, TM, pc.taps * 80, device="cuda", dtype=torch.float64)
     for j in range(pc.taps):
         mel4[:, j:, j * 80:(j + 1) * 80] = mel.double().transpose(1, 2)[:, :TM - j]
@@ -134,7 +134,7 @@ def test_layer_stage(models, layer):
                                  h2.data_ptr(), eo_f.data_ptr(), ptr, n, B, TM, stream))
     torch.cuda.synchronize()
     # fp64 evaluation of the packed form
-    pk = mf._packed
+    pk = mf.packed_views()
     d = 2 ** layer
     xp = torch.zeros(B, tp + 2 * d, Cc, device="cuda", dtype=torch.float64)
     xp[:, d:d + tp] = x.double()
