@@ -55,6 +55,7 @@ constexpr int P_OFF_BAR = P_OFF_B2 + 1024;
 constexpr int P_SMEM = P_OFF_BAR + 256 + 1024;         // 217344
 constexpr int P_EPI_THREADS = 256;
 constexpr int P_THREADS = 128 + P_EPI_THREADS;
+constexpr int PS_DBG_STRIDE = 24;                      // int64 per CTA in the debug buffer: {start, end, tiles, -}, 12 MMA-thread stamps, 8 epilogue stamps
 constexpr uint32_t P_D_RES = 256, P_D_EO = 32;         // TMEM columns of the GEMM2 accumulators
 
 // TMEM column of the packed 16-bit acts of 16-channel chunk c (0..15): sweep g = c / 8 writes into R0 columns the same
@@ -119,8 +120,10 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wse_full, 1); mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(acts_ready, 2 * P_EPI_THREADS); mbar_init(acc2_full, 1);
-    mbar_init(&r_free[0], 2 * (P_EPI_THREADS / 2)); mbar_init(&r_free[1], 2 * P_EPI_THREADS);
+    // epilogue -> MMA hand-offs: ONE elected arrive per warp after __syncwarp (512 per-thread arrives, half of them remote
+    // DSMEM transactions, cost ~1.3-2.9 k cycles per hand-off in the per-tile timeline)
+    mbar_init(acts_ready, 2 * (P_EPI_THREADS / 32)); mbar_init(acc2_full, 1);
+    mbar_init(&r_free[0], 2 * (P_EPI_THREADS / 64)); mbar_init(&r_free[1], 2 * (P_EPI_THREADS / 32));
     mbar_init(&xold_full[0], 1); mbar_init(&xold_full[1], 1);
     fence_barrier_init();
   }
@@ -272,11 +275,16 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     auto commit = [&](uint64_t* bar) { umma_commit_2sm(bar); };
     uint32_t par = 0;
     bool wse_seen = false;
-    for (int p = cluster_id; p < a.n_pairs; p += n_clusters, par ^= 1u) {
+    int it_no = 0;
+    long long* tdbg = a.dbg ? a.dbg + (size_t)blockIdx.x * PS_DBG_STRIDE + 4 : nullptr;
+    for (int p = cluster_id; p < a.n_pairs; p += n_clusters, par ^= 1u, ++it_no) {
+      const bool stamp = tdbg && it_no == 2;
       for (int g = 0; g < 2; ++g) {
+        if (stamp) tdbg[3 * g] = clock64();
         // region R_g is free once the previous tile's epilogues (both CTAs) have read it
         mbar_wait_cluster(&r_free[g], par ^ 1u);
         tc_fence_after_sync();
+        if (stamp) tdbg[3 * g + 1] = clock64();
         const uint32_t d = tmem + g * 256;
         if (F8) {
           for (int G = 0; G < 8; ++G)
@@ -312,11 +320,13 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           }
         }
         commit(&acc_full[g]);
+        if (stamp) tdbg[3 * g + 2] = clock64();
       }
       // GEMM2: [res | folded end] = acts x W2^T; A hi from TMEM (".ts"), lo / e5m2 planes from units 8..11
       if (!wse_seen) { mbar_wait(wse_full, 0); wse_seen = true; }
       mbar_wait_cluster(acts_ready, par);
       tc_fence_after_sync();
+      if (stamp) tdbg[6] = clock64();
       const uint32_t dres = tmem + P_D_RES, d32 = tmem + P_D_EO;
       if (F8) {
         for (int grp = 0; grp < 2; ++grp)
@@ -374,6 +384,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         }
       }
       commit(acc2_full);
+      if (stamp) tdbg[7] = clock64();
     }
   } else if (warp >= 4) {
     // ---------------- epilogue warps: TMEM lane quarter = warp % 4 (one group-step per lane), column group
@@ -411,9 +422,12 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
       // ---- gates: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) (glow.py:34-41), sweep by sweep
 #pragma unroll 1
+      const bool stamp = a.dbg && n_tiles == 2 && warp == 4 && lane == 0;
+      long long* edbg = a.dbg ? a.dbg + (size_t)blockIdx.x * PS_DBG_STRIDE + 16 : nullptr;
       for (int g = 0; g < 2; ++g) {
         mbar_wait(&acc_full[g], par);
         tc_fence_after_sync();
+        if (stamp) edbg[2 * g] = clock64();
         const uint32_t treg = trow + g * 256;
         uint32_t buf[2][32];
         const int i0 = 4 * h;                                       // 16-channel chunk of the sweep: i0 .. i0+3
@@ -436,12 +450,16 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           if (F8) store_split16_tmem_f8(act, trow + P_ACOL(c), slot(8 + (c >> 3)), slot(10 + (c >> 3)), row, c & 7);
           else store_split16_tmem<X3, false>(act, trow + P_ACOL(c), slot(8 + (c >> 2)), row, (c & 3) * 2);
         }
+        if (stamp) edbg[2 * g + 1] = clock64();
       }
       tmem_wait_st();
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      if (leader) mbar_arrive(acts_ready); else mbar_arrive_cluster(ar_bar);
-      if (!a.has_res) { if (leader) mbar_arrive(&r_free[1]); else mbar_arrive_cluster(r1_bar); }   // R1 fully consumed
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(acts_ready); else mbar_arrive_cluster(ar_bar);
+        if (!a.has_res) { if (leader) mbar_arrive(&r_free[1]); else mbar_arrive_cluster(r1_bar); }   // R1 fully consumed
+      }
 
       // prefetch this row's folded-`end` accumulator while GEMM2 runs
       float4 eold[4];
@@ -454,13 +472,17 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       // ---- res / skip
       mbar_wait(acc2_full, par);
       tc_fence_after_sync();
-      if (X3 && a.has_res && ldr) load_xold(2 * h);              // GEMM2 no longer reads units 8..11
-      if (h == 0) {
-        uint32_t sk[16];
+      if (stamp) edbg[4] = clock64();
+      uint32_t sk[16];
+      if (h == 0) {                                              // first of all: release R0 to the next tile's sweep 0
         tmem_issue16(trow + P_D_EO, sk);
         tmem_wait16(sk);
         tc_fence_before_sync();
-        if (leader) mbar_arrive(&r_free[0]); else mbar_arrive_cluster(r0_bar);   // R0: acts consumed by GEMM2, `end` read
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(&r_free[0]); else mbar_arrive_cluster(r0_bar); }   // R0: acts consumed by GEMM2, `end` read
+      }
+      if (X3 && a.has_res && ldr) load_xold(2 * h);              // GEMM2 no longer reads units 8..11
+      if (h == 0) {
         if (valid) {
           float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
 #pragma unroll
@@ -480,9 +502,10 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           if ((i & 3) == 0) { mbar_wait(&xold_full[h], xph); xph ^= 1u; }   // x_old tiles of this 64-channel block have landed
           tmem_wait16(cur);
           if (i + 1 < 8) tmem_issue16(trow + P_D_RES + (c + 1) * 16, buf[(i + 1) & 1]);
-          else {                                                           // last TMEM read of this thread: release R1
+          else {                                                           // last TMEM read of this warp: release R1
             tc_fence_before_sync();
-            if (leader) mbar_arrive(&r_free[1]); else mbar_arrive_cluster(r1_bar);
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(&r_free[1]); else mbar_arrive_cluster(r1_bar); }
           }
           const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);
           const uint4 h0 = *reinterpret_cast<const uint4*>(u_hi + o0), h1 = *reinterpret_cast<const uint4*>(u_hi + o1);
@@ -540,10 +563,11 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         // the staging units become gate outputs of the next tile (written by BOTH column groups)
         asm volatile("bar.sync 1, %0;" ::"n"(P_EPI_THREADS) : "memory");
       }
+      if (stamp) edbg[5] = clock64();
     }
     tc_fence_before_sync();
     if (a.dbg && warp == 4 && lane == 0) {
-      long long* d = a.dbg + (size_t)blockIdx.x * 4;
+      long long* d = a.dbg + (size_t)blockIdx.x * PS_DBG_STRIDE;
       d[0] = t_start; d[1] = clock64(); d[2] = n_tiles;
     }
   }

@@ -106,18 +106,63 @@ def infer_long_sharded(model, spect: torch.Tensor, sigma: float = 1.0, z: Option
     plan = plan_chunks(t_mel, n_chunks or world, pc)
     hop = pc.hop_length
     dev = next(model.parameters()).device
-    # every rank sends a fixed-size buffer: its chunks' cores laid out at their final positions
-    mine = torch.zeros(B, t_mel * hop, device=dev)
+    # every rank sends only the CORES of its chunks, packed back to back into a buffer sized for the largest per-rank
+    # total (cores differ by at most one frame, so the padding is at most one frame per chunk) - not a full-length,
+    # mostly-zero waveform
+    per_rank = [sum(ch.core1 - ch.core0 for ch in plan[r::world]) for r in range(world)]
+    width = max(per_rank) * hop
+    mine = torch.zeros(B, width, device=dev)
+    off = 0
     for ch in plan[rank::world]:
-        mine[:, ch.core0 * hop:ch.core1 * hop] = infer_chunk(model, spect, z, sigma, ch, **kw)
+        n = (ch.core1 - ch.core0) * hop
+        mine[:, off:off + n] = infer_chunk(model, spect, z, sigma, ch, **kw)
+        off += n
     bufs = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
     dist.gather(mine, bufs, dst=dst)
     if rank != dst:
         return None
-    out = torch.empty_like(mine)
+    out = torch.empty(B, t_mel * hop, device=dev)
+    offs = [0] * world
     for i, ch in enumerate(plan):
-        out[:, ch.core0 * hop:ch.core1 * hop] = bufs[i % world][:, ch.core0 * hop:ch.core1 * hop]
+        r, n = i % world, (ch.core1 - ch.core0) * hop
+        out[:, ch.core0 * hop:ch.core1 * hop] = bufs[r][:, offs[r]:offs[r] + n]
+        offs[r] += n
     return out
+
+
+class WaveformGather:
+    """The path's only collective - the final gather of `[B_local, T]` waveforms to rank `dst` - taken off the critical
+    path: `submit(audio)` issues it asynchronously (`async_op=True`: NCCL runs it on its own stream once `audio` is
+    complete) into one of `depth` receive slots, so the gather of call i overlaps the kernels of call i+1 instead of
+    sitting between them.  A slot is only waited for when it is about to be re-used (`depth` calls later) or in
+    `wait_all()`; `result(slot)` is the list of per-rank tensors on `dst` (valid after the wait).  Works on NCCL and gloo."""
+
+    def __init__(self, shape, device, dst: int = 0, depth: int = 2, dtype=torch.float32):
+        import torch.distributed as dist
+        self.dist, self.dst, self.depth = dist, dst, depth
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.bufs = ([[torch.empty(shape, device=device, dtype=dtype) for _ in range(self.world)] for _ in range(depth)]
+                     if self.rank == dst else None)
+        self.pending = [None] * depth
+        self.calls = 0
+
+    def submit(self, audio: torch.Tensor) -> int:
+        slot = self.calls % self.depth
+        if self.pending[slot] is not None:
+            self.pending[slot][0].wait()
+        work = self.dist.gather(audio, self.bufs[slot] if self.bufs is not None else None, dst=self.dst, async_op=True)
+        self.pending[slot] = (work, audio)        # keeps `audio` alive until the collective has consumed it
+        self.calls += 1
+        return slot
+
+    def wait_all(self):
+        for i, p in enumerate(self.pending):
+            if p is not None:
+                p[0].wait()
+                self.pending[i] = None
+
+    def result(self, slot: int):
+        return self.bufs[slot] if self.bufs is not None else None
 
 
 def slice_per_utterance(kw: dict, idx, n_items: int) -> dict:

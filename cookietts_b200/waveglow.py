@@ -294,7 +294,7 @@ class WaveGlow(nn.Module):
                 ev_b, ev_e = [int(e.cuda_event) for e in begin], [int(e.cuda_event) for e in end]
             audio, status = ops.waveglow_infer(self._packed, self._cfg_list, mode, self._embed_dim, self._n_speakers, mel,
                                                speaker_id, z, float(sigma), ev_b, ev_e)
-            if self.precision == "f16f8" and self.range_guard:
+            if self.precision == "f16f8" and self.range_guard and not torch.cuda.is_current_stream_capturing():
                 # fp16 hi planes: values beyond +-65504 (or a NaN / Inf waveform) are flagged on the device (cwg_infer_status);
                 # reading the flag synchronises this call.  On a hit the call is repeated in bf16x3 (fp32 exponent range).
                 self.last_status = int(status.item())

@@ -89,9 +89,10 @@ def test_torch_ops_end_to_end(precision, tol, snr):
     cfgl = _torch_ops.config_list(m.pack_config)
     mode = _cabi.MODES[precision]
     blob = ops.waveglow_pack([torch.from_numpy(sd[k]).cuda() for k in names], "\n".join(names), cfgl, mode)
-    out = ops.waveglow_infer(blob, cfgl, mode, 0, 0, torch.from_numpy(g["mel"]).cuda(), None, torch.from_numpy(g["z"]).cuda(),
-                             float(g["sigma"]), [], [])
+    out, status = ops.waveglow_infer(blob, cfgl, mode, 0, 0, torch.from_numpy(g["mel"]).cuda(), None,
+                                     torch.from_numpy(g["z"]).cuda(), float(g["sigma"]), [], [])
     torch.cuda.synchronize()
+    assert int(status.item()) == 0                 # cwg_infer_status: finite waveform, fp16 planes in range
     out = out.cpu().numpy()
     ref = g["audio_ref_fp64"]
     assert max_abs(out, ref) <= tol and snr_db(ref, out) >= snr

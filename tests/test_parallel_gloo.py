@@ -98,3 +98,35 @@ def test_sharded_infer_gloo_even(tmp_path):
 
 def test_sharded_infer_gloo_uneven(tmp_path):
     _run(5, 2, tmp_path)
+
+
+def _worker_async(rank, world, port, result_file):
+    from cookietts_b200.parallel import WaveformGather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = WaveformGather((3, 16), torch.device("cpu"), dst=0, depth=2)
+    ok = True
+    slots = []
+    for step in range(5):                       # more calls than slots: slot re-use waits for the older collective
+        audio = torch.full((3, 16), float(10 * step + rank))
+        slots.append(g.submit(audio))
+        if rank == 0 and step >= 1:             # the previous call's slot is complete once it has been waited for
+            prev = slots[step - 1]
+            g.pending[prev][0].wait()
+            ok &= all(bool((g.result(prev)[r] == 10 * (step - 1) + r).all()) for r in range(world))
+    g.wait_all()
+    if rank == 0:
+        ok &= all(bool((g.result(slots[-1])[r] == 40 + r).all()) for r in range(world))
+        ok &= slots == [0, 1, 0, 1, 0]
+        torch.save({"ok": ok}, result_file)
+    else:
+        assert g.result(0) is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_async_waveform_gather_gloo(tmp_path):
+    result_file = str(tmp_path / "async.pt")
+    mp.spawn(_worker_async, args=(2, _free_port(), result_file), nprocs=2, join=True)
+    assert torch.load(result_file)["ok"]

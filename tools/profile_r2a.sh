@@ -3,6 +3,7 @@
 # one full capture of k_layer_ps per mode.  Runs under gpurun (one GPU).
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep gpurun_out/launches_*.csv
+python -c "import bench; print(bench.kernel_source_hash())" > gpurun_out/ncu_source_sha256.txt
 timeout 600 python tools/ps_timing.py > gpurun_out/r2_ps_timing.log 2>&1; tail -8 gpurun_out/r2_ps_timing.log
 for p in f16f8 bf16x3 bf16; do
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 366 -c 122 --csv \

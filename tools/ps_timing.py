@@ -46,15 +46,22 @@ for prec in precs:
             e1.record(); torch.cuda.synchronize()
             res[which] = (e0.elapsed_time(e1) / 20, xo_first, eo_first)
         # per-CTA clock64 stamps of the persistent kernel: cycles per tile pair
-        dbg = torch.zeros(2 * 148 * 4, dtype=torch.int64, device="cuda")
+        dbg = torch.zeros(2 * 148 * 24, dtype=torch.int64, device="cuda")
         lib.cwg_debug_set_ps_timing(C.c_void_p(dbg.data_ptr())); lib.cwg_debug_set_layer_kernel(1)
         run(); torch.cuda.synchronize()
         lib.cwg_debug_set_ps_timing(C.c_void_p(0))
-        dd = dbg.view(-1, 4).cpu().numpy(); dd = dd[dd[:, 2] > 0]
+        dall = dbg.view(-1, 24).cpu().numpy(); dd = dall[dall[:, 2] > 0]
         cyc = (dd[:, 1] - dd[:, 0]) / dd[:, 2]
         cyc_info = dict(ctas=int(len(dd)), tiles_min=int(dd[:, 2].min()), tiles_max=int(dd[:, 2].max()),
                         cycles_per_tile_mean=float(cyc.mean()), cycles_per_tile_min=float(cyc.min()), cycles_per_tile_max=float(cyc.max()),
                         cta_cycles_max=int((dd[:, 1] - dd[:, 0]).max()))
+        # third tile of every leader CTA: MMA-thread stamps [4..11] and epilogue stamps [16..21], relative to sweep-0 start
+        lead = dall[0::2]; lead = lead[lead[:, 2] > 2]
+        t0 = lead[:, 4:5]
+        names_m = ["s0_wait_begin", "s0_start", "s0_issued", "s1_wait_begin", "s1_start", "s1_issued", "acts_ready", "gemm2_issued"]
+        names_e = ["acc0_seen", "gate0_done", "acc1_seen", "gate1_done", "acc2_seen", "res_done"]
+        cyc_info["mma_thread"] = {n: float((lead[:, 4 + i:5 + i] - t0).mean()) for i, n in enumerate(names_m)}
+        cyc_info["epilogue"] = {n: float((lead[:, 16 + i:17 + i] - t0).mean()) for i, n in enumerate(names_e)}
         lib.cwg_debug_set_layer_kernel(-1)
         (t0, xa, ea), (t1, xb, eb) = res[0], res[1]
         if prec == "f16f8":

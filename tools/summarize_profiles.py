@@ -50,6 +50,42 @@ for name in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
         lines.append("")
 open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w").write("\n".join(lines))
 
+# machine-readable copy for bench.py (roofline.traffic etc.): keyed by kernel, stamped with a hash of the kernel sources so
+# that a changed kernel is never described by stale numbers
+import hashlib, json, re
+sys.path.insert(0, ROOT)
+from bench import kernel_source_hash
+recs = {}
+for name in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
+    if not name.endswith(".ncu-rep"):
+        continue
+    hdr, units, rows = raw_rows(os.path.join(ROOT, "gpurun_out", name))
+    for r in rows[:1]:
+        k = r[hdr.index("Kernel Name")]
+        mm = re.search(r"(k_[a-z0-9_]+)<([^>]*)>", k)
+        key = f"{mm.group(1)}<{mm.group(2).replace(' ', '')}>" if mm else k.split("(")[0]
+
+        def val(metric):
+            if metric not in hdr:
+                return None
+            i = hdr.index(metric)
+            v = float(r[i].replace(",", ""))
+            return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1.0,
+                        "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[i], 1.0)
+        recs[key] = {
+            "report": name, "capture": "ncu --set full --clock-control none, one launch inside bench.py",
+            "dram_bytes": (val("dram__bytes_read.sum") or 0) + (val("dram__bytes_write.sum") or 0),
+            "l2_to_sm_bytes": val("l1tex__m_xbar2l1tex_read_bytes.sum"),
+            "tensor_pipe_active_pct": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+            "duration_us": val("gpu__time_duration.sum"), "registers": val("launch__registers_per_thread"),
+            "warps_active_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        }
+# the hash of the sources the capture ran from is written on the GPU box by the profile script
+hp = os.path.join(ROOT, "gpurun_out", "ncu_source_sha256.txt")
+src_hash = open(hp).read().strip() if os.path.exists(hp) else "unknown (capture script did not record it)"
+json.dump({"tag": tag, "source_sha256": src_hash, "current_source_sha256_when_summarised": kernel_source_hash(), "kernels": recs},
+          open(os.path.join(out_dir, "r2_ncu.json"), "w"), indent=1)
+
 # launch lists: aggregate per kernel
 for name in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
     if not (name.startswith("launches_") and name.endswith(".csv")):
