@@ -8,3 +8,4 @@ from .waveflow import WaveFlow  # noqa: F401
 from .waveglow_ax import WaveGlowAx  # noqa: F401
 from .denoiser import Denoiser  # noqa: F401
 from . import serving  # noqa: F401
+from .flow_decoder import FlowDecoder  # noqa: F401

@@ -28,7 +28,7 @@ WEIGHT_FIELDS = ("cond_w_f32", "cond_w_hi", "cond_w_lo", "w1_f32", "w1_hi", "w1_
                  "w2_f32", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "winv", "w1_h8", "w1_l8", "w2_h8", "w2_l8")
 
 
-WEIGHT_FIELDS_V3 = ("cond_b_base", "cond_w_spk", "spk_embed")
+WEIGHT_FIELDS_V3 = ("cond_b_base", "cond_w_spk", "spk_embed", "w0_hi", "w0_lo")
 
 
 class CwgWeights(C.Structure):
@@ -47,7 +47,8 @@ EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_laun
            "cwg_ax_workspace_bytes", "cwg_ax_infer",
            "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_launch_count", "cwg_wf_layer",
            "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise", "cwg_pcm16",
-           "cwg_conv1d", "cwg_conv_transpose1d", "cwg_resample1d", "cwg_deemphasis")
+           "cwg_conv1d", "cwg_conv_transpose1d", "cwg_resample1d", "cwg_deemphasis",
+           "cwg_fd_workspace_bytes", "cwg_fd_launch_count", "cwg_fd_inverse")
 
 
 class CwgError(RuntimeError):

@@ -73,7 +73,8 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
 // (fp16 hi, fp16 lo, e5m2(lo * 2^F8_P), e5m2(hi * 2^-F8_Q))
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
-                         const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2, int ignore_nan = 0);
+                         const float* eo, void* x_out, cudaStream_t s, int mix_flow = -2, int ignore_nan = 0,
+                         void* a0_out = nullptr);   // a0_out: write the layer-0-fold planes [BT][16] hi, lo instead of x
 
 // CWG_MODE_F16F8 range guard: device status word the producers of fp16 planes OR bit 1 (value 2) into when a value leaves
 // +-65504 (set by cwg_infer around its launches; NULL = no check).  Host-side, thread-local.
@@ -97,7 +98,8 @@ int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, in
 // persistent, epilogue-overlapped successor of launch_layer_tc for n_channels = 256 (cwg_ps.cu); the default
 int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
                     const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
-                    float* eo, cudaStream_t s);
+                    float* eo, cudaStream_t s, const void* a0 = nullptr, const float* audio = nullptr,
+                    int a_off = 0, int a_nh = 0);
 void debug_set_ps_timing(long long* buf);
 
 // n_channels = 512: two kernels per layer (cwg_tc512.cu); `acts` = bf16 hi/lo planes [B*T'][512]

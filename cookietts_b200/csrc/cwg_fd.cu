@@ -1,0 +1,266 @@
+// Mel-domain flow decoder, inverse pass: the reference's FlowDecoder.inverse
+//   CookieTTS/_2_ttm/flowtts/waveglow/glow.py:302-343 (flows in reverse, mix_first, early z), WN.forward :133-172,
+//   AffineCouplingBlock.inverse modules.py:36-47, InvertibleConv1x1.inverse modules.py:234-250,
+//   and the untts variant (untts/waveglow/glow.py:126-127: constant padding of the first flow's hidden tensor).
+// These decoders run at mel-frame rate (a few hundred steps per utterance, n_group up to 256 channels), three to four
+// orders of magnitude less work than the vocoder, so they are built as fp32 CUDA-core kernels on the reference's own
+// channels-first [B, C, T] layout: one implicit-GEMM conv kernel with four epilogues (store, accumulate, GTU gate, and
+// the W^-1 mixing as a 1x1 conv) plus the coupling update.  Exact fp32 semantics; no tensor-core mode is needed here.
+#include "cwg_common.cuh"
+
+namespace cwg {
+namespace {
+
+constexpr int FBM = 64, FBN = 64, FBK = 16;
+
+struct FdConvP {
+  int B, Cin, T, N, ks, dil;
+  float pad_value;
+  const float* x; long long x_bstride;        // x[b][ci][t] = x[b * x_bstride + ci * T + t]
+  const float* w; const float* bias;          // w [rows][Cin][ks]; EPI 2 also reads rows n + N
+  const float* add; long long add_bstride;    // EPI 2: cond slice [b][2N][t] added to the pre-activation
+  float* y; long long y_bstride;              // y[b][n][t]
+};
+
+// EPI 0: y = conv + bias;  1: y += conv + bias;  2: y = tanh(pre[n]) * sigmoid(pre[n + N]), pre = conv + bias + add (GTU)
+template <int EPI>
+__global__ void __launch_bounds__(256) k_fd_conv(FdConvP p) {
+  __shared__ float As[FBK][FBM + 4];
+  __shared__ float Bs[FBK][FBN + 4];
+  __shared__ float Bg[EPI == 2 ? FBK : 1][FBN + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const long long M = (long long)p.B * p.T;
+  const long long m0 = (long long)blockIdx.x * FBM;
+  const int n0 = blockIdx.y * FBN;
+  const int KD = p.Cin * p.ks;
+  float acc[4][4] = {}, acg[4][4] = {};
+  const int a_row = tid % FBM, a_k = tid / FBM;
+  const long long am = m0 + a_row;
+  int ab = 0, at = 0;
+  const bool a_ok = am < M;
+  if (a_ok) { ab = (int)(am / p.T); at = (int)(am - (long long)ab * p.T); }
+  const int half = p.ks / 2;
+  for (int k0 = 0; k0 < KD; k0 += FBK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kk = a_k + 4 * r, kd = k0 + kk;
+      float v = 0.f;
+      if (a_ok && kd < KD) {
+        const int ci = kd / p.ks, j = kd - ci * p.ks;
+        const int ti = at + p.dil * (j - half);
+        v = (ti >= 0 && ti < p.T) ? __ldg(p.x + (size_t)ab * p.x_bstride + (size_t)ci * p.T + ti) : p.pad_value;
+      }
+      As[kk][a_row] = v;
+      const int idx = tid + r * 256, n = idx / FBK, bk = idx % FBK;
+      const bool ok = n0 + n < p.N && k0 + bk < KD;
+      Bs[bk][n] = ok ? __ldg(p.w + (size_t)(n0 + n) * KD + k0 + bk) : 0.f;
+      if (EPI == 2) Bg[bk][n] = ok ? __ldg(p.w + (size_t)(n0 + n + p.N) * KD + k0 + bk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < FBK; ++kk) {
+      float a[4], b[4], g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][tx + 16 * i]; b[i] = Bs[kk][ty * 4 + i]; if (EPI == 2) g[i] = Bg[kk][ty * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          if (EPI == 2) acg[i][j] = fmaf(a[i], g[j], acg[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + tx + 16 * i;
+    if (m >= M) continue;
+    const int b = (int)(m / p.T), t = (int)(m - (long long)b * p.T);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty * 4 + j;
+      if (n >= p.N) continue;
+      float* yo = p.y + (size_t)b * p.y_bstride + (size_t)n * p.T + t;
+      float v = acc[i][j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+      if (EPI == 0) *yo = v;
+      else if (EPI == 1) *yo += v;
+      else {
+        const float* ad = p.add + (size_t)b * p.add_bstride + t;
+        const float pa = v + __ldg(ad + (size_t)n * p.T);
+        const float pb = acg[i][j] + __ldg(p.bias + n + p.N) + __ldg(ad + (size_t)(n + p.N) * p.T);
+        *yo = tanhf(pa) * (1.f / (1.f + expf(-pb)));                   // GTU, glow.py:33-40
+      }
+    }
+  }
+}
+
+// z1 = (z1 - t) / exp(log_s), e = [log_s | t] (WN returns end(output).chunk(2, 1); modules.py:43-46)
+__global__ void k_fd_coupling(float* __restrict__ z1, long long z_bstride, const float* __restrict__ e, int B, int n_half, int T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * n_half * T) return;
+  const int t = (int)(i % T); const long long bc = i / T;
+  const int c = (int)(bc % n_half), b = (int)(bc / n_half);
+  const float log_s = e[((size_t)b * 2 * n_half + c) * T + t], tt = e[((size_t)b * 2 * n_half + n_half + c) * T + t];
+  float* zp = z1 + (size_t)b * z_bstride + (size_t)c * T + t;
+  *zp = (*zp - tt) / expf(log_s);
+}
+
+__global__ void k_fd_add(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+template <int EPI>
+int conv(const FdConvP& p, cudaStream_t s) {
+  const long long M = (long long)p.B * p.T;
+  dim3 grid((unsigned)((M + FBM - 1) / FBM), (unsigned)((p.N + FBN - 1) / FBN));
+  k_fd_conv<EPI><<<grid, 256, 0, s>>>(p);
+  CWG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int check(const cwg_fd_config* c, int batch, int T) {
+  CWG_REQUIRE(c != nullptr, "cfg is NULL");
+  CWG_REQUIRE(c->n_group >= 2 && c->n_group % 2 == 0 && c->n_flows >= 1 && c->n_early_every >= 1 && c->n_early_size % 2 == 0,
+              "bad n_group / n_flows / early-output settings");
+  CWG_REQUIRE(c->n_layers >= 1 && c->n_layers <= CWG_FD_MAX_LAYERS && c->n_channels >= 1 && c->kernel_size % 2 == 1 && c->cond_channels >= 1,
+              "bad WN settings");
+  CWG_REQUIRE(c->res_skip || c->merge_res_skip, "cannot remove res_skip without merge_res_skip (glow.py:53)");
+  int n_rem = c->n_group;
+  for (int k = 1; k < c->n_flows; ++k) if (k % c->n_early_every == 0) n_rem -= c->n_early_size;
+  CWG_REQUIRE(n_rem >= 2, "too many early outputs for n_group");
+  for (int i = 0; i < c->n_layers; ++i) CWG_REQUIRE(c->dilations[i] >= 1, "dilations must be >= 1");
+  CWG_REQUIRE(batch >= 1 && T >= 1, "batch and T must be >= 1");
+  return 0;
+}
+
+struct FdWs { float *z2, *h, *out, *acts, *c_all, *e; size_t bytes; };
+void carve(const cwg_fd_config* c, int B, int T, void* base, FdWs* ws) {
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n * sizeof(float), 256); return (float*)((char*)base + o); };
+  const size_t BT = (size_t)B * T;
+  ws->z2 = take(BT * c->n_group); ws->h = take(BT * c->n_channels); ws->out = take(BT * c->n_channels);
+  ws->acts = take(BT * c->n_channels); ws->c_all = take(BT * 2 * c->n_channels * c->n_layers); ws->e = take(BT * c->n_group);
+  ws->bytes = off;
+}
+
+}  // namespace
+}  // namespace cwg
+
+using namespace cwg;
+
+extern "C" {
+
+size_t cwg_fd_workspace_bytes(const cwg_fd_config* cfg, int batch, int t_steps) {
+  if (check(cfg, batch, t_steps)) return 0;
+  FdWs ws;
+  carve(cfg, batch, t_steps, nullptr, &ws);
+  return ws.bytes;
+}
+
+int cwg_fd_launch_count(const cwg_fd_config* cfg) {
+  if (check(cfg, 1, 1)) return -1;
+  const int per_layer = 1 + (cfg->res_skip ? (cfg->merge_res_skip ? 1 : 2) : 1);
+  return 1 + cfg->n_flows * (2 + cfg->n_layers * per_layer + 4);
+}
+
+int cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const float* cond, float* z,
+                   void* workspace, size_t workspace_bytes, int batch, int t_steps, void* cuda_stream) {
+  if (int r = check(cfg, batch, t_steps)) return r;
+  CWG_REQUIRE(w && cond && z && workspace, "NULL argument");
+  CWG_REQUIRE(w->start_w && w->start_b && w->cond_w && w->cond_b && w->in_w && w->in_b && w->end_w && w->end_b && w->winv,
+              "missing weight arrays");
+  CWG_REQUIRE(!cfg->res_skip || (w->rs_w && w->rs_b), "res_skip weights missing");
+  FdWs ws;
+  carve(cfg, batch, t_steps, workspace, &ws);
+  CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const int B = batch, T = t_steps, G = cfg->n_group, C = cfg->n_channels, L = cfg->n_layers, ks = cfg->kernel_size, F = cfg->n_flows;
+  const long long zb = (long long)G * T;
+  // per-flow channel counts and offsets into the concatenated arrays
+  int n_rem_k[256];
+  size_t o_start[256], o_end_w[256], o_end_b[256], o_winv[256];
+  CWG_REQUIRE(F <= 256, "n_flows > 256");
+  {
+    int n_rem = G; size_t a = 0, b = 0, c = 0, d = 0;
+    for (int k = 0; k < F; ++k) {
+      if (k % cfg->n_early_every == 0 && k > 0) n_rem -= cfg->n_early_size;
+      n_rem_k[k] = n_rem;
+      const int nh = n_rem / 2;
+      o_start[k] = a; a += (size_t)C * nh;
+      o_end_w[k] = b; b += (size_t)2 * nh * C;
+      o_end_b[k] = c; c += (size_t)2 * nh;
+      o_winv[k] = d; d += (size_t)n_rem * n_rem;
+    }
+  }
+  // the early-output channels never change: both ping-pong buffers carry them from the start
+  CWG_CHECK_CUDA(cudaMemcpyAsync(ws.z2, z, (size_t)B * G * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  float* cur = z; float* other = ws.z2;
+  auto mix = [&](int k) -> int {                     // InvertibleConv1x1.inverse: conv1d with W^-1 over the active channels
+    const int n_rem = n_rem_k[k], off = G - n_rem;
+    FdConvP p{};
+    p.B = B; p.Cin = n_rem; p.T = T; p.N = n_rem; p.ks = 1; p.dil = 1; p.pad_value = 0.f;
+    p.x = cur + (size_t)off * T; p.x_bstride = zb; p.w = w->winv + o_winv[k]; p.bias = nullptr;
+    p.y = other + (size_t)off * T; p.y_bstride = zb;
+    if (int r = conv<0>(p, s)) return r;
+    float* t = cur; cur = other; other = t;
+    return 0;
+  };
+  for (int k = F - 1; k >= 0; --k) {
+    const int n_rem = n_rem_k[k], nh = n_rem / 2, off = G - n_rem;
+    if (!cfg->mix_first) { if (int r = mix(k)) return r; }
+    // ---- WN(z_0, cond): start, cond layer, layers, end
+    FdConvP p{};
+    p.B = B; p.T = T; p.dil = 1; p.pad_value = 0.f;
+    p.Cin = nh; p.N = C; p.ks = 1; p.x = cur + (size_t)off * T; p.x_bstride = zb;
+    p.w = w->start_w + o_start[k]; p.bias = w->start_b + (size_t)k * C; p.y = ws.h; p.y_bstride = (long long)C * T;
+    if (int r = conv<0>(p, s)) return r;
+    p.Cin = cfg->cond_channels; p.N = 2 * C * L; p.x = cond; p.x_bstride = (long long)cfg->cond_channels * T;
+    p.w = w->cond_w + (size_t)k * 2 * C * L * cfg->cond_channels; p.bias = w->cond_b + (size_t)k * 2 * C * L;
+    p.y = ws.c_all; p.y_bstride = (long long)2 * C * L * T;
+    if (int r = conv<0>(p, s)) return r;
+    if (!cfg->merge_res_skip) CWG_CHECK_CUDA(cudaMemsetAsync(ws.out, 0, (size_t)B * C * T * sizeof(float), s));
+    for (int i = 0; i < L; ++i) {
+      const size_t li = (size_t)k * L + i;
+      FdConvP g{};
+      g.B = B; g.T = T; g.Cin = C; g.N = C; g.ks = ks; g.dil = cfg->dilations[i];
+      g.pad_value = k == 0 ? cfg->first_pad_value : 0.f;                        // untts glow.py:80,126
+      g.x = ws.h; g.x_bstride = (long long)C * T; g.w = w->in_w + li * 2 * C * C * ks; g.bias = w->in_b + li * 2 * C;
+      g.add = ws.c_all + (size_t)2 * C * i * T; g.add_bstride = (long long)2 * C * L * T;
+      g.y = ws.acts; g.y_bstride = (long long)C * T;
+      if (int r = conv<2>(g, s)) return r;
+      const bool last = i == L - 1;
+      if (cfg->res_skip) {
+        FdConvP q{};
+        q.B = B; q.T = T; q.Cin = C; q.N = C; q.ks = 1; q.dil = 1; q.x = ws.acts; q.x_bstride = (long long)C * T;
+        q.w = w->rs_w + li * 2 * C * C; q.bias = w->rs_b + li * 2 * C; q.y_bstride = (long long)C * T;
+        if (cfg->merge_res_skip) { q.y = ws.h; if (int r = conv<1>(q, s)) return r; }
+        else if (!last) {
+          q.y = ws.h; if (int r = conv<1>(q, s)) return r;                        // res rows [0, C)
+          q.w += (size_t)C * C; q.bias += C; q.y = ws.out; if (int r = conv<1>(q, s)) return r;   // skip rows [C, 2C)
+        } else { q.y = ws.out; if (int r = conv<1>(q, s)) return r; }
+      } else {
+        // no res_skip layer: res_skip_acts = acts and (merged) h += acts (glow.py:149-155)
+        const long long n = (long long)B * C * T;
+        k_fd_add<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.h, ws.acts, n);
+        CWG_CHECK_CUDA(cudaGetLastError());
+      }
+    }
+    FdConvP e{};
+    e.B = B; e.T = T; e.Cin = C; e.N = 2 * nh; e.ks = 1; e.dil = 1;
+    e.x = cfg->merge_res_skip ? ws.h : ws.out; e.x_bstride = (long long)C * T;
+    e.w = w->end_w + o_end_w[k]; e.bias = w->end_b + o_end_b[k]; e.y = ws.e; e.y_bstride = (long long)2 * nh * T;
+    if (int r = conv<0>(e, s)) return r;
+    {
+      const long long n = (long long)B * nh * T;
+      k_fd_coupling<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur + (size_t)(off + nh) * T, zb, ws.e, B, nh, T);
+      CWG_CHECK_CUDA(cudaGetLastError());
+    }
+    if (cfg->mix_first) { if (int r = mix(k)) return r; }
+  }
+  if (cur != z) CWG_CHECK_CUDA(cudaMemcpyAsync(z, cur, (size_t)B * G * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+}  // extern "C"

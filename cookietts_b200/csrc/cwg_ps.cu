@@ -44,6 +44,15 @@ struct PsArgs {
   int w1_row0, w2_row0;
   int has_res, first;
   int pairs_per_utt, n_pairs;
+  // layer-0 fold (fused0): x_0 = start(audio_0) is never materialised.  GEMM1 contracts the 3 taps of the <= 8 coupling
+  // input channels (+ a constant-1 channel carrying the start bias) with W_in*S (tm_a0_* / tm_w0_*), and the residual
+  // epilogue rebuilds x_old = S a + b in fp32 from the audio state
+  int fused0;
+  const float* audio;     // [B*T'][G] fp32 audio state; audio_0 of row m = audio[m*G + a_off .. + a_nh)
+  int G, a_off, a_nh;
+  const float* start_w;   // [C][CWG_MAX_GROUP/2]
+  const float* start_b;   // [C]
+  int w0_row0;
   int* range_flag;        // f16f8, last residual layer only: |= 2 when x_new leaves the fp16 range (else NULL)
   long long* dbg;         // optional: per CTA {start, end, tiles} clock64 stamps
 };
@@ -52,7 +61,9 @@ constexpr int P_OFF_WSE = 12 * TILE_A;                 // 196608
 constexpr int P_OFF_B1 = P_OFF_WSE + 16384;
 constexpr int P_OFF_B2 = P_OFF_B1 + 2048;
 constexpr int P_OFF_BAR = P_OFF_B2 + 1024;
-constexpr int P_SMEM = P_OFF_BAR + 256 + 1024;         // 217344
+constexpr int P_OFF_S = P_OFF_BAR + 256;               // fused0: start weights [256][8] fp32 + bias [256]
+constexpr int P_SMEM = P_OFF_S + 256 * 8 * 4 + 1024 + 1024;   // 226560 (<= 232448)
+constexpr int TILE_S = 4096;                           // [128 rows][16 x 16-bit], 32B swizzle
 constexpr int P_EPI_THREADS = 256;
 constexpr int P_THREADS = 128 + P_EPI_THREADS;
 constexpr int PS_DBG_STRIDE = 24;                      // int64 per CTA in the debug buffer: {start, end, tiles, -}, 12 MMA-thread stamps, 8 epilogue stamps
@@ -90,7 +101,10 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
            const __grid_constant__ CUtensorMap tm_x_l8, const __grid_constant__ CUtensorMap tm_x_h8,
            const __grid_constant__ CUtensorMap tm_h_l8, const __grid_constant__ CUtensorMap tm_h_h8,
            const __grid_constant__ CUtensorMap tm_w1_h8, const __grid_constant__ CUtensorMap tm_w1_l8,
-           const __grid_constant__ CUtensorMap tm_w2_l8, const __grid_constant__ CUtensorMap tm_wse_l8, PsArgs a) {
+           const __grid_constant__ CUtensorMap tm_w2_l8, const __grid_constant__ CUtensorMap tm_wse_l8,
+           // layer-0 fold: coupling-input planes (16 channels) and folded weights (3 taps x 16), 32B-swizzled 4-KB tiles
+           const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
+           const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_constant__ CUtensorMap tm_w0_lo, PsArgs a) {
   constexpr bool F8 = NPASS == 2;
   constexpr bool X3 = NPASS != 1;                 // the gate produces a second (lo / e5m2) set of acts planes
   constexpr int PL = NPASS == 3 ? 2 : 1;          // planes streamed per k-block in GEMM1 of the bf16 modes
@@ -103,6 +117,8 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   uint8_t* smem = align_1024(smem_raw);
   float* b1s = reinterpret_cast<float*>(smem + P_OFF_B1);
   float* b2s = reinterpret_cast<float*>(smem + P_OFF_B2);
+  float* s_tab = reinterpret_cast<float*>(smem + P_OFF_S);            // fused0 only
+  float* s_bias = s_tab + 256 * 8;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);   // [8]: A slot i -> i, B slot j -> 4 + j
   uint64_t* empty = full + 8;
   uint64_t* wse_full = empty + 8;
@@ -170,10 +186,21 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     for (int p = cluster_id; p < a.n_pairs; p += n_clusters) {
       int b, t0; tile_of(p, b, t0);
       for (int g = 0; g < 2; ++g) {
+        if (a.fused0) {
+          // one ring item per plane: the 3 tap tiles [128 steps x 16 channels] of the coupling input (4 KB each)
+          for (int pl = 0; pl < PL2; ++pl) {
+            mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
+            pm ^= 1u << s;
+            arm(&full[s], 3 * TILE_S);
+            for (int tap = 0; tap < 3; ++tap)
+              lda3(slot(s) + tap * TILE_S, pl ? &tm_a0_lo : &tm_a0_hi, &full[s], 0, t0 + (tap - 1) * a.dil, b);
+            s = (s + 1) & 3;
+          }
+        }
         if (F8) {
           // K in groups of 128 channels (taps 0..2 of x: groups 0..5, H2: groups 6, 7); per group two fp16 tiles of 64
           // channels, then the e5m2 tile of lo*2^P and the e5m2 tile of hi*2^-Q (128 channels = 128 bytes per row)
-          for (int G = 0; G < 8; ++G)
+          for (int G = a.fused0 ? 6 : 0; G < 8; ++G)
             for (int it = 0; it < 4; ++it) {
               mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
               pm ^= 1u << s;
@@ -187,7 +214,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               s = (s + 1) & 3;
             }
         } else {
-          for (int kb = 0; kb < 16; ++kb)
+          for (int kb = a.fused0 ? 12 : 0; kb < 16; ++kb)
             for (int pl = 0; pl < PL; ++pl) {
               mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
               pm ^= 1u << s;
@@ -215,8 +242,19 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     for (int p = cluster_id; p < a.n_pairs; p += n_clusters) {
       for (int g = 0; g < 2; ++g) {
         const int w1_row = a.w1_row0 + (int)rank * 256 + g * 128;
+        if (a.fused0) {
+          const int w0_row = a.w0_row0 + (int)rank * 256 + g * 128;
+          for (int pl = 0; pl < PL2; ++pl) {
+            mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
+            pm ^= 1u << j;
+            arm(&full[4 + j], 3 * TILE_S);
+            for (int tap = 0; tap < 3; ++tap)
+              ldb2(slot(4 + j) + tap * TILE_S, pl ? &tm_w0_lo : &tm_w0_hi, &full[4 + j], tap * 16, w0_row);
+            j = (j + 1) & 3;
+          }
+        }
         if (F8) {
-          for (int G = 0; G < 8; ++G)
+          for (int G = a.fused0 ? 6 : 0; G < 8; ++G)
             for (int it = 0; it < 4; ++it) {
               next_slot();
               if (it < 2) ldb2(slot(4 + j), &tm_w1_hi, &full[4 + j], (2 * G + it) * 64, w1_row);
@@ -224,7 +262,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               j = (j + 1) & 3;
             }
         } else {
-          for (int kb = 0; kb < 16; ++kb)
+          for (int kb = a.fused0 ? 12 : 0; kb < 16; ++kb)
             for (int pl = 0; pl < PL; ++pl) {
               next_slot();
               ldb2(slot(4 + j), pl ? &tm_w1_lo : &tm_w1_hi, &full[4 + j], kb * 64, w1_row);
@@ -286,19 +324,42 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         tc_fence_after_sync();
         if (stamp) tdbg[3 * g + 1] = clock64();
         const uint32_t d = tmem + g * 256;
+        if (a.fused0) {
+          // x part of layer 0: 3 taps x (hi*hi [+ lo*hi + hi*lo]) K = 16 MMAs on the 32B-swizzled 4-KB tiles
+          const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
+          int sa_lo = sa_hi;
+          if (X3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
+          const int jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+          int jb_lo = jb_hi;
+          if (X3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(slot(sa_hi)), a_lo = smem_u32(slot(sa_lo));
+          const uint32_t b_hi = smem_u32(slot(4 + jb_hi)), b_lo = smem_u32(slot(4 + jb_lo));
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            const uint32_t o = tap * TILE_S;
+            umma_bf16_2sm(d, umma_desc_sw32(a_hi + o), umma_desc_sw32(b_hi + o), ID256, tap ? 1u : 0u);
+            if (X3) {
+              umma_bf16_2sm(d, umma_desc_sw32(a_lo + o), umma_desc_sw32(b_hi + o), ID256, 1u);
+              umma_bf16_2sm(d, umma_desc_sw32(a_hi + o), umma_desc_sw32(b_lo + o), ID256, 1u);
+            }
+          }
+          commit(&empty[4 + jb_hi]); commit(&empty[sa_hi]);
+          if (X3) { commit(&empty[4 + jb_lo]); commit(&empty[sa_lo]); }
+        }
         if (F8) {
-          for (int G = 0; G < 8; ++G)
+          for (int G = a.fused0 ? 6 : 0; G < 8; ++G)
             for (int it = 0; it < 4; ++it) {
               const int sa_cur = sa; wait_full(sa); sa = (sa + 1) & 3;
               const int jb_cur = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
               tc_fence_after_sync();
-              if (it < 2) kblk(smem_u32(slot(sa_cur)), smem_u32(slot(4 + jb_cur)), d, ID256, G == 0 && it == 0);
+              if (it < 2) kblk(smem_u32(slot(sa_cur)), smem_u32(slot(4 + jb_cur)), d, ID256, G == 0 && it == 0);      // fused0 starts at G = 6: accumulates
               else kblk8(smem_u32(slot(sa_cur)), smem_u32(slot(4 + jb_cur)), d, IDE256);
               commit(&empty[4 + jb_cur]);
               commit(&empty[sa_cur]);
             }
         } else {
-          for (int kb = 0; kb < 16; ++kb) {
+          for (int kb = a.fused0 ? 12 : 0; kb < 16; ++kb) {
             const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
             int sa_lo = 0;
             if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
@@ -401,6 +462,11 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       const int e = threadIdx.x - 128;
       b1s[e] = __ldg(a.b1 + e) * GateK<NPASS>::KA; b1s[256 + e] = __ldg(a.b1 + 256 + e) * GateK<NPASS>::KB;
       b2s[e] = __ldg(a.b2 + e);
+      if (a.fused0) {          // start conv of this flow: S [256][8] (columns >= n_half are zero) and its bias
+        const float4* sw = reinterpret_cast<const float4*>(a.start_w + (size_t)e * (CWG_MAX_GROUP / 2));
+        reinterpret_cast<float4*>(s_tab)[2 * e] = __ldg(sw); reinterpret_cast<float4*>(s_tab)[2 * e + 1] = __ldg(sw + 1);
+        s_bias[e] = __ldg(a.start_b + e);
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(P_EPI_THREADS) : "memory");
     }
     const uint32_t r0_bar = mapa_shared(&r_free[0], 0), r1_bar = mapa_shared(&r_free[1], 0), ar_bar = mapa_shared(acts_ready, 0);
@@ -418,12 +484,12 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         tma_load_3d(u_lo, &tm_x_lo, &xold_full[h], blk * 64, t0, b);
       };
       // bf16: units 8..11 hold no gate output, so the first x_old block can be fetched a whole tile ahead
-      if (!X3 && a.has_res && ldr) load_xold(2 * h);
+      if (!X3 && a.has_res && !a.fused0 && ldr) load_xold(2 * h);
 
       // ---- gates: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) (glow.py:34-41), sweep by sweep
-#pragma unroll 1
       const bool stamp = a.dbg && n_tiles == 2 && warp == 4 && lane == 0;
       long long* edbg = a.dbg ? a.dbg + (size_t)blockIdx.x * PS_DBG_STRIDE + 16 : nullptr;
+#pragma unroll 1
       for (int g = 0; g < 2; ++g) {
         mbar_wait(&acc_full[g], par);
         tc_fence_after_sync();
@@ -481,7 +547,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&r_free[0]); else mbar_arrive_cluster(r0_bar); }   // R0: acts consumed by GEMM2, `end` read
       }
-      if (X3 && a.has_res && ldr) load_xold(2 * h);              // GEMM2 no longer reads units 8..11
+      if (X3 && a.has_res && !a.fused0 && ldr) load_xold(2 * h);  // GEMM2 no longer reads units 8..11
       if (h == 0) {
         if (valid) {
           float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
@@ -494,12 +560,18 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       if (a.has_res) {
         uint32_t buf[2][16];
         const int c0 = 8 * h;
+        float av[CWG_MAX_GROUP / 2];                 // fused0: this row's coupling input audio_0 (fp32, exact)
+        if (a.fused0) {
+          const float* ar = a.audio + m * a.G + a.a_off;
+#pragma unroll
+          for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) av[j] = (valid && j < a.a_nh) ? __ldg(ar + j) : 0.f;
+        }
         tmem_issue16(trow + P_D_RES + c0 * 16, buf[0]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = c0 + i;
           uint32_t* cur = buf[i & 1];
-          if ((i & 3) == 0) { mbar_wait(&xold_full[h], xph); xph ^= 1u; }   // x_old tiles of this 64-channel block have landed
+          if ((i & 3) == 0 && !a.fused0) { mbar_wait(&xold_full[h], xph); xph ^= 1u; }   // x_old tiles of this 64-channel block have landed
           tmem_wait16(cur);
           if (i + 1 < 8) tmem_issue16(trow + P_D_RES + (c + 1) * 16, buf[(i + 1) & 1]);
           else {                                                           // last TMEM read of this warp: release R1
@@ -508,10 +580,6 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
             if (lane == 0) { if (leader) mbar_arrive(&r_free[1]); else mbar_arrive_cluster(r1_bar); }
           }
           const uint32_t o0 = sw128_offset(row, (c & 3) * 2), o1 = sw128_offset(row, (c & 3) * 2 + 1);
-          const uint4 h0 = *reinterpret_cast<const uint4*>(u_hi + o0), h1 = *reinterpret_cast<const uint4*>(u_hi + o1);
-          const uint4 l0 = *reinterpret_cast<const uint4*>(u_lo + o0), l1 = *reinterpret_cast<const uint4*>(u_lo + o1);
-          const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-          const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
           float r[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -519,12 +587,28 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
             r[4 * q] = __uint_as_float(cur[4 * q]) + bb.x; r[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + bb.y;
             r[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + bb.z; r[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + bb.w;
           }
+          if (a.fused0) {
+            // x_old = start(audio_0) = S a + b in fp32 (glow.py:189), never stored: 8 FMAs per channel, S broadcast from smem
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {   // x_new = x_old(hi + lo) + res, glow.py:217
-            float f0, f1, g0, g1;
-            unpack2<F8>(hw[j], f0, f1); unpack2<F8>(lw[j], g0, g1);
-            r[2 * j] += f0 + g0;
-            r[2 * j + 1] += f1 + g1;
+            for (int q = 0; q < 16; ++q) {
+              const float4 s0 = reinterpret_cast<const float4*>(s_tab)[2 * (c * 16 + q)], s1 = reinterpret_cast<const float4*>(s_tab)[2 * (c * 16 + q) + 1];
+              float x = s_bias[c * 16 + q];
+              x = fmaf(s0.x, av[0], x); x = fmaf(s0.y, av[1], x); x = fmaf(s0.z, av[2], x); x = fmaf(s0.w, av[3], x);
+              x = fmaf(s1.x, av[4], x); x = fmaf(s1.y, av[5], x); x = fmaf(s1.z, av[6], x); x = fmaf(s1.w, av[7], x);
+              r[q] += x;
+            }
+          } else {
+            const uint4 h0 = *reinterpret_cast<const uint4*>(u_hi + o0), h1 = *reinterpret_cast<const uint4*>(u_hi + o1);
+            const uint4 l0 = *reinterpret_cast<const uint4*>(u_lo + o0), l1 = *reinterpret_cast<const uint4*>(u_lo + o1);
+            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // x_new = x_old(hi + lo) + res, glow.py:217
+              float f0, f1, g0, g1;
+              unpack2<F8>(hw[j], f0, f1); unpack2<F8>(lw[j], g0, g1);
+              r[2 * j] += f0 + g0;
+              r[2 * j + 1] += f1 + g1;
+            }
           }
           if (F8) {
             uint32_t nh[8], nl[8], l8[4], h8[4];
@@ -556,8 +640,11 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               tma_store_3d(&tm_xo_lo, u_lo, blk * 64, t0, b);
               tma_store_commit();
               tma_store_wait_read();
-              if (i == 3) load_xold(blk + 1);
+              if (i == 3 && !a.fused0) load_xold(blk + 1);
             }
+            // fused0 has no x_old load (whose mbarrier orders the re-use of the staging tiles in the other path): nobody
+            // may overwrite them before the store above has read them
+            if (a.fused0 && i == 3) asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
           }
         }
         // the staging units become gate outputs of the next tile (written by BOTH column groups)
@@ -583,9 +670,10 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 struct PsMaps {
   CUtensorMap x_hi, x_lo, h_hi, h_lo, w1_hi, w1_lo, w2_hi, w2_lo, wse_hi, wse_lo, xo_hi, xo_lo;
   CUtensorMap x_l8, x_h8, h_l8, h_h8, w1_h8, w1_l8, w2_l8, wse_l8;
+  CUtensorMap a0_hi, a0_lo, w0_hi, w0_lo;
 };
 struct PsKey {
-  const void *x_in, *x_out, *h2, *w1, *w2, *w1b, *w2b;
+  const void *x_in, *x_out, *h2, *w1, *w2, *w1b, *w2b, *a0, *w0;
   int B, Tp, C, H, K1, N2, npass; long long fl;
 };
 struct PsEntry { PsKey key; PsMaps maps; bool used; unsigned long long stamp; };
@@ -594,7 +682,7 @@ thread_local PsEntry g_cache[PS_CACHE];
 thread_local unsigned long long g_stamp = 0;
 
 int build_maps(const Dims& d, const cwg_weights* w, int npass, const __nv_bfloat16* x_in, __nv_bfloat16* x_out,
-               const __nv_bfloat16* h2, PsMaps* m) {
+               const __nv_bfloat16* h2, const void* a0, PsMaps* m) {
   const size_t plane = (size_t)d.BT * d.C, hplane = (size_t)d.BT * d.H;
   const uint64_t fl = (uint64_t)d.F * d.L;
   if (int r = map_act(&m->x_hi, x_in, d.C, d.Tp, d.B)) return r;
@@ -628,16 +716,26 @@ int build_maps(const Dims& d, const cwg_weights* w, int npass, const __nv_bfloat
     if (int r = map_2d(&m->wse_lo, w->w2_lo, d.C, fl * d.N2, 16)) return r;
     m->x_l8 = m->x_h8 = m->h_l8 = m->h_h8 = m->w1_h8 = m->w1_l8 = m->w2_l8 = m->wse_l8 = m->x_hi;
   }
+  if (a0) {      // layer-0 fold: planes hi then lo, each [B*T'][16] 16-bit; folded weights [F][2C][48]
+    const uint16_t* ap = reinterpret_cast<const uint16_t*>(a0);
+    if (int r = map_a0(&m->a0_hi, ap, d.Tp, d.B)) return r;
+    if (int r = map_a0(&m->a0_lo, ap + (size_t)d.BT * 16, d.Tp, d.B)) return r;
+    if (int r = map_w0(&m->w0_hi, w->w0_hi, (uint64_t)d.F * 2 * d.C)) return r;
+    if (int r = map_w0(&m->w0_lo, w->w0_lo, (uint64_t)d.F * 2 * d.C)) return r;
+  } else {
+    m->a0_hi = m->a0_lo = m->w0_hi = m->w0_lo = m->x_hi;
+  }
   return 0;
 }
 
 int get_maps(const Dims& d, const cwg_weights* w, int npass, const __nv_bfloat16* x_in, __nv_bfloat16* x_out,
-             const __nv_bfloat16* h2, const PsMaps** out) {
+             const __nv_bfloat16* h2, const void* a0, const PsMaps** out) {
   PsKey k;
   memset(&k, 0, sizeof(k));
   k.x_in = x_in; k.x_out = x_out; k.h2 = h2; k.w1 = w->w1_hi; k.w2 = w->w2_hi;
   k.w1b = npass == 2 ? (const void*)w->w1_h8 : (const void*)w->w1_lo;
   k.w2b = npass == 2 ? (const void*)w->w2_h8 : (const void*)w->w2_lo;
+  k.a0 = a0; k.w0 = a0 ? (const void*)w->w0_hi : nullptr;
   k.B = d.B; k.Tp = d.Tp; k.C = d.C; k.H = d.H; k.K1 = d.K1; k.N2 = d.N2; k.npass = npass; k.fl = (long long)d.F * d.L;
   int victim = 0;
   for (int i = 0; i < PS_CACHE; ++i) {
@@ -651,7 +749,7 @@ int get_maps(const Dims& d, const cwg_weights* w, int npass, const __nv_bfloat16
   }
   PsEntry& e = g_cache[victim];
   e.used = false;
-  if (int r = build_maps(d, w, npass, x_in, x_out, h2, &e.maps)) return r;
+  if (int r = build_maps(d, w, npass, x_in, x_out, h2, a0, &e.maps)) return r;
   e.key = k; e.used = true; e.stamp = ++g_stamp;
   *out = &e.maps;
   return 0;
@@ -685,9 +783,11 @@ void debug_set_ps_timing(long long* buf) { g_ps_dbg = buf; }
 
 int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
                     const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
-                    float* eo, cudaStream_t s) {
+                    float* eo, cudaStream_t s, const void* a0, const float* audio, int a_off, int a_nh) {
+  // a0 != NULL (layer 0 only): the layer-0 fold - x_in is not read; see PsArgs::fused0
+  CWG_REQUIRE(a0 == nullptr || (layer == 0 && w->w0_hi && w->w0_lo && audio && d.L >= 2), "layer-0 fold: bad arguments");
   const PsMaps* m = nullptr;
-  if (int r = get_maps(d, w, npass, x_in, x_out, h2, &m)) return r;
+  if (int r = get_maps(d, w, npass, x_in, x_out, h2, a0, &m)) return r;
   const size_t plane = (size_t)d.BT * d.C;
   const size_t idx = (size_t)flow * d.L + layer;
   PsArgs a{};
@@ -701,6 +801,9 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.pairs_per_utt = (tiles + 1) / 2;                // an odd tile count gets one tile fully past T' (TMA zero-fills / clips)
   a.n_pairs = a.pairs_per_utt * d.B;
   a.dbg = g_ps_dbg;
+  a.fused0 = a0 != nullptr; a.audio = audio; a.G = d.G; a.a_off = a_off; a.a_nh = a_nh;
+  a.start_w = w->start_w + (size_t)flow * d.C * (CWG_MAX_GROUP / 2); a.start_b = w->start_b + (size_t)flow * d.C;
+  a.w0_row0 = flow * 2 * d.C;
   a.range_flag = (npass == 2 && layer == d.L - 2) ? range_flag() : nullptr;
   int ncl = 0;
   if (int r = (npass == 3 ? max_clusters<3>(&ncl) : npass == 2 ? max_clusters<2>(&ncl) : max_clusters<1>(&ncl))) return r;
@@ -714,7 +817,8 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
 #define CWG_LAUNCH_PS(NP)                                                                                              \
   CWG_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_layer_ps<NP>, m->x_hi, m->x_lo, m->h_hi, m->h_lo, m->w1_hi, m->w1_lo,       \
                                     m->w2_hi, m->w2_lo, m->wse_hi, m->wse_lo, m->xo_hi, m->xo_lo, m->x_l8, m->x_h8,    \
-                                    m->h_l8, m->h_h8, m->w1_h8, m->w1_l8, m->w2_l8, m->wse_l8, a))
+                                    m->h_l8, m->h_h8, m->w1_h8, m->w1_l8, m->w2_l8, m->wse_l8, m->a0_hi, m->a0_lo,  \
+                                    m->w0_hi, m->w0_lo, a))
   if (npass == 3) CWG_LAUNCH_PS(3); else if (npass == 2) CWG_LAUNCH_PS(2); else CWG_LAUNCH_PS(1);
 #undef CWG_LAUNCH_PS
   return 0;

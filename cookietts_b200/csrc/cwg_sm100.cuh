@@ -95,6 +95,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
   return d;
 }
+// The same for a K-major tile whose rows are 32 bytes (16 x 16-bit: exactly one K = 16 MMA step) with the 32-byte swizzle
+// (a TMA box {16, rows} with CU_TENSOR_MAP_SWIZZLE_32B): 8-row groups are 256 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                               // SWIZZLE_32B
+  return d;
+}
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

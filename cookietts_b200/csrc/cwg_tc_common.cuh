@@ -31,14 +31,14 @@ inline PFN_encodeTiled get_encode() {
 
 // bf16 tensor, innermost dim contiguous, 128B swizzle, zero OOB fill. strides_bytes has rank-1 entries.
 inline int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box, bool bytes = false) {
+             const uint32_t* box, bool bytes = false, bool sw32 = false) {
   PFN_encodeTiled enc = get_encode();
   CWG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CWG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -54,6 +54,17 @@ inline int map_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows,
 inline int map_act(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uint64_t B) {
   uint64_t dims[3] = {C, Tp, B}; uint64_t st[2] = {C * 2, Tp * C * 2}; uint32_t box[3] = {64, 128, 1};
   return make_map(m, ptr, 3, dims, st, box);
+}
+
+// layer-0 fold (start conv folded into the in_layer): the coupling input planes [B][T'][16] 16-bit as (16, T', B), box = 16
+// channels x 128 steps (4 KB, 32-byte rows, 32B swizzle), and the folded weights [rows][48] (3 taps x 16), box 16 x 128 rows
+inline int map_a0(CUtensorMap* m, const void* ptr, uint64_t Tp, uint64_t B) {
+  uint64_t dims[3] = {16, Tp, B}; uint64_t st[2] = {32, Tp * 32}; uint32_t box[3] = {16, 128, 1};
+  return make_map(m, ptr, 3, dims, st, box, false, true);
+}
+inline int map_w0(CUtensorMap* m, const void* ptr, uint64_t rows) {
+  uint64_t dims[2] = {48, rows}; uint64_t st[1] = {96}; uint32_t box[2] = {16, 128};
+  return make_map(m, ptr, 2, dims, st, box, false, true);
 }
 
 // 8-bit (e5m2) planes: the same tiles measured in bytes - 128 channels x 128 steps / 128 k x box_rows rows = 16 KB units

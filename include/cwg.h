@@ -90,6 +90,11 @@ typedef struct cwg_weights {
   const float*    cond_b_base;  /* [F][H]        bias of the folded cond chain without the speaker branch          */
   const float*    cond_w_spk;   /* [F][H][E]     speaker columns of cond_layers.1 * cond_layers.0 (glow.py:193-199) */
   const float*    spk_embed;    /* [F][S][E]     WN.k.speaker_embed.weight of every flow (glow.py:144-147)          */
+  /* layer-0 fold (tensor-core modes, C = 256; optional - NULL selects the unfused layer 0): in_layers.0 * start per flow,
+   * [F][2C][48] 16-bit planes (bf16, or fp16 in CWG_MODE_F16F8), col = tap*16 + j: j < n_half the coupling input
+   * channels, j = n_half the start bias (contracted with a constant-1 channel), other columns zero */
+  const uint16_t* w0_hi;
+  const uint16_t* w0_lo;
   int32_t         speaker_embed_dim;   /* E (0: single-speaker model) */
   int32_t         n_speakers;          /* S: rows of the embedding tables */
 } cwg_weights;
@@ -320,6 +325,49 @@ int cwg_resample1d(const float* x, int batch, int channels, int t_in, long long 
                    long long y_batch_stride, int mode, int t_virtual, int crop, float scale_factor, int accumulate,
                    void* cuda_stream);
 int cwg_deemphasis(const float* x, int batch, int t_samples, double coef, int vol_scaling, float* y, void* cuda_stream);
+
+/* =====================================================================================
+ * Mel-domain flow decoders: FlowDecoder.inverse of the reference's text-to-mel models
+ *   CookieTTS/_2_ttm/flowtts/waveglow/glow.py:302-343 (WN.forward :133-172, modules.py:36-47, :234-250) and
+ *   CookieTTS/_2_ttm/untts/waveglow/glow.py (same, plus the constant padding of the first flow's hidden tensor, :80,126).
+ * fp32, the reference's channels-first layout.  z [batch][n_group][T] is updated in place: on entry the latent (already
+ * multiplied by sigma, viewed as the reference's z.view(B, n_group, -1)), on return the mel; the active channels of flow k
+ * are the trailing n_rem_k ones (early outputs sit in front, glow.py:317-321,339-340).  cond [batch][cond_channels][T].
+ * Supported: WN with one 1x1 cond layer without activation (the hparams defaults), any n_layers <= 16 / dilations /
+ * odd kernel size, res_skip on or off, merge_res_skip on or off, mix_first on or off, no decoder-level cond layers.
+ * ===================================================================================== */
+#define CWG_FD_MAX_LAYERS 16
+
+typedef struct cwg_fd_config {
+  int32_t n_group, n_flows, n_early_every, n_early_size, mix_first;
+  int32_t cond_channels;
+  int32_t n_layers, n_channels, kernel_size;
+  int32_t dilations[CWG_FD_MAX_LAYERS];
+  int32_t res_skip;          /* hparams.wn_res_skip       */
+  int32_t merge_res_skip;    /* hparams.wn_merge_res_skip */
+  float   first_pad_value;   /* untts decoder_padding_value: pads the hidden tensor of flow 0's in_layers; 0 for flowtts */
+} cwg_fd_config;
+
+/* Device fp32 arrays, weight-norm folded.  F flows, L layers, C channels, Cc cond channels, ks kernel size; n_rem_k /
+ * n_half_k = n_rem_k / 2 per flow (glow.py:205-220).  "concatenated" = flow after flow with the per-flow shape given. */
+typedef struct cwg_fd_weights {
+  const float* start_w;   /* concatenated [C][n_half_k]                  */
+  const float* start_b;   /* [F][C]                                       */
+  const float* cond_w;    /* [F][2CL][Cc]   WN.cond_layers.0              */
+  const float* cond_b;    /* [F][2CL]                                     */
+  const float* in_w;      /* [F][L][2C][C][ks]                            */
+  const float* in_b;      /* [F][L][2C]                                   */
+  const float* rs_w;      /* [F][L][2C][C]  (rows past the layer's res_skip width unused); NULL when res_skip = 0 */
+  const float* rs_b;      /* [F][L][2C]                                   */
+  const float* end_w;     /* concatenated [2 n_half_k][C]                 */
+  const float* end_b;     /* concatenated [2 n_half_k]                    */
+  const float* winv;      /* concatenated [n_rem_k][n_rem_k]  W^-1, row major */
+} cwg_fd_weights;
+
+size_t cwg_fd_workspace_bytes(const cwg_fd_config* cfg, int batch, int t_steps);
+int    cwg_fd_launch_count(const cwg_fd_config* cfg);
+int    cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const float* cond, float* z,
+                      void* workspace, size_t workspace_bytes, int batch, int t_steps, void* cuda_stream);
 
 #ifdef __cplusplus
 }
