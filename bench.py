@@ -644,6 +644,8 @@ def run_waveglow(args):
         "ncu_tensor_pipe_active_pct": ncu["tensor_pipe_active_pct"] if ncu else None,
         "ncu_source": "profiles/r2_ncu.json (sha256 of csrc matches)" if ncu else None,
         "launches_timed": int(layer_ms.size), "avg_launch_ms": float(layer_avg_ms.mean()),
+        # mean duration by WN layer index (dilation 2^i; layer 0 runs the start-conv fold, the last layer has no residual)
+        "launch_ms_by_layer": [round(float(layer_avg_ms.reshape(12, 8)[:, i].mean()), 4) for i in range(8)],
         "layer_share_of_step": float(layer_avg_ms.sum() / (ms_total / args.steps)),
         "mma_passes": passes, "issued_mma_tflops": achieved * passes,
         "note": "achieved = reference's dense FLOPs per layer launch (SURVEY 8d) / CUDA-event duration; "

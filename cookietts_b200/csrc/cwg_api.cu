@@ -29,6 +29,7 @@ struct Workspace {
   float *x[2], *h2, *pre, *acts;
   // tensor-core modes (each: hi plane then lo plane)
   __nv_bfloat16 *xb[2], *h2b, *mel4, *actsb;
+  void* a0;               // layer-0 fold: planes hi, lo [BT][16] 16-bit
   float* eo;
   size_t bytes;
 };
@@ -82,12 +83,18 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
     ws->h2b = (__nv_bfloat16*)take((size_t)d.BT * d.H * 2 * 2);
     ws->mel4 = (__nv_bfloat16*)take((size_t)d.B * d.Tm * d.KCp * 2 * 2);
     if (d.C == 512) ws->actsb = (__nv_bfloat16*)take((size_t)d.BT * d.C * 2 * 2);   // gated activations (two-kernel layer)
+    ws->a0 = take((size_t)d.BT * 16 * 2 * 2);
   }
   ws->bytes = off;
 }
 
 // C = 256: the persistent sweep kernel (cwg_ps.cu) unless CWG_LAYER_PS=0 asks for the round-1 one-tile-per-CTA kernel
 int g_force_ps = -1;     // cwg_debug_set_layer_kernel: -1 = environment / default, 0 = round-1 kernel, 1 = persistent kernel
+// layer-0 fold (start conv folded into in_layers.0) unless CWG_FUSE_START=0
+bool use_fold() {
+  static const int v = [] { const char* e = getenv("CWG_FUSE_START"); return e ? (e[0] != '0') : 1; }();
+  return v != 0;
+}
 bool use_ps() {
   static const int v = [] { const char* e = getenv("CWG_LAYER_PS"); return e ? (e[0] != '0') : 1; }();
   return g_force_ps >= 0 ? g_force_ps != 0 : v != 0;
@@ -99,9 +106,20 @@ int layer_tc256(const Dims& d, const cwg_weights* w, int npass, int k, int i, co
   return launch_layer_tc(d, w, npass, k, i, x_in, x_out, h2, eo, s);
 }
 
-int layer_tc(const Dims& d, const cwg_weights* w, int npass, int k, int i, const Workspace& ws, cudaStream_t s) {
+// classic model, tensor-core modes: is layer 0 run from the (audio_0 | 1) planes instead of a materialised x_0 ?
+bool fold_active(const Dims& d, const cwg_weights* w) {
+  return d.C == 256 && d.L >= 2 && w->w0_hi && w->w0_lo && use_ps() && use_fold();
+}
+
+int layer_tc(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int npass, int k, int i, const Workspace& ws,
+             const float* audio, cudaStream_t s) {
   if (d.C == 512)
     return launch_layer_tc512(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.actsb, ws.eo, s);
+  if (i == 0 && audio && fold_active(d, w)) {
+    int n_rem, n_half;
+    flow_channels(cfg, k, &n_rem, &n_half);
+    return launch_layer_ps(d, w, npass, k, i, ws.xb[0], ws.xb[1], ws.h2b, ws.eo, s, ws.a0, audio, d.G - n_rem, n_half);
+  }
   return layer_tc256(d, w, npass, k, i, ws.xb[i & 1], ws.xb[(i + 1) & 1], ws.h2b, ws.eo, s);
 }
 
@@ -136,6 +154,21 @@ void cwg_debug_set_timing(void* buf) { cwg::debug_set_timing((long long*)buf); }
 // Debug only: the persistent layer kernel writes {start, end, tiles, -} clock64 stamps per CTA (4 x int64 each).
 void cwg_debug_set_layer_kernel(int which) { cwg::g_force_ps = which; }
 void cwg_debug_set_ps_timing(void* buf) { cwg::debug_set_ps_timing((long long*)buf); }
+
+// Debug only: layer 0 of `flow` through the layer-0 fold (a0 planes built from `audio`, then the fused persistent kernel);
+// x_out / eo as in cwg_wn_layer.  a0_scratch: >= batch*T'*64 bytes.
+int cwg_debug_layer0_fused(const cwg_config* cfg, const cwg_weights* w, int mode, int flow, float* audio, void* x_out,
+                           const void* h2, float* eo, void* a0_scratch, int batch, int t_mel, void* cuda_stream) {
+  if (int r = check_run(cfg, w, mode, batch, t_mel)) return r;
+  CWG_REQUIRE(mode != CWG_MODE_FFMA && cfg->n_channels == 256 && w->w0_hi && w->w0_lo, "layer-0 fold not available for this model / mode");
+  Dims d = make_dims(cfg, batch, t_mel);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (int r = launch_flow_boundary(cfg, d, w, mode_xfmt(mode), -1, flow, nullptr, 1.f, audio, nullptr, x_out, s, -2, 0, a0_scratch)) return r;
+  int n_rem, n_half;
+  flow_channels(cfg, flow, &n_rem, &n_half);
+  return launch_layer_ps(d, w, mode_npass(mode), flow, 0, (const __nv_bfloat16*)x_out, (__nv_bfloat16*)x_out, (const __nv_bfloat16*)h2, eo, s,
+                         a0_scratch, audio, d.G - n_rem, n_half);
+}
 
 const char* cwg_last_error(void) { return cwg::g_err; }
 
@@ -256,7 +289,8 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
   auto run = [&]() -> int {
   // audio = sigma * z (glow.py:326; early z already sits in its final columns), x = start_{F-1}(audio_0)
   void* x0 = tc ? (void*)ws.xb[0] : (void*)ws.x[0];
-  if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s)) return r;
+  void* a0 = (tc && fold_active(d, w)) ? ws.a0 : nullptr;
+  if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s, -2, 0, a0)) return r;
   for (int k = F - 1; k >= 0; --k) {                       // glow.py:328
     if (tc) {
       if (int r = launch_cond_tc(d, w, npass, k, k == F - 1 ? mel : nullptr, cond_bias, ws.h2b, ws.mel4, s)) return r;
@@ -267,14 +301,14 @@ int cwg_infer_profiled(const cwg_config* cfg, const cwg_weights* w, int mode,
       const int ev = (F - 1 - k) * L + i;
       if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_begin[ev], s));
       if (tc) {
-        if (int r = layer_tc(d, w, npass, k, i, ws, s)) return r;
+        if (int r = layer_tc(cfg, d, w, npass, k, i, ws, audio, s)) return r;
       } else {
         if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
       }
       if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_end[ev], s));
     }
     // coupling inverse + W^-1 of flow k, then start conv of flow k-1 (glow.py:329-347, :189)
-    if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s)) return r;
+    if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s, -2, 0, a0)) return r;
   }
   return 0;
   };
@@ -346,7 +380,7 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   for (int k = F - 1; k >= 0; --k) {                       // efficient_model_ax.py:325
     for (int i = 0; i < L; ++i) {
       if (tc) {
-        if (int r = layer_tc(d, w, npass, k, i, ws, s)) return r;
+        if (int r = layer_tc(cfg, d, w, npass, k, i, ws, nullptr, s)) return r;   // ax: no layer-0 fold
       } else {
         if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
       }

@@ -151,6 +151,21 @@ __global__ void k_w2(const double* __restrict__ w_rs, const double* __restrict__
   emit(out, out0 + (size_t)row * C + c, v);
 }
 
+// layer-0 fold: w0[o][tap*16 + j] = sum_c in_layers.0[o][c][tap] * (j < n_half ? start[c][j] : j == n_half ? start_bias[c] : 0)
+__global__ void k_w0(const double* __restrict__ w_in, const double* __restrict__ w_start, const float* __restrict__ b_start,
+                     int C, int ks, int n_half, Planes out, size_t out0) {
+  const int col = threadIdx.x, o = blockIdx.x;             // 48 columns, 2C rows
+  if (col >= 48) return;
+  const int tap = col / 16, j = col - tap * 16;
+  double v = 0.0;
+  if (tap < ks && j <= n_half)
+    for (int c = 0; c < C; ++c)
+      v += w_in[((size_t)o * C + c) * ks + tap] * (j < n_half ? w_start[(size_t)c * n_half + j] : (double)b_start[c]);
+  // only the 16-bit hi / lo planes exist for w0 (three products in every tensor-core mode)
+  Planes p = out; p.h8 = nullptr; p.l8 = nullptr;
+  emit(p, out0 + (size_t)o * 48 + col, v);
+}
+
 struct EoArgs { const float* b_rs[16]; const float* alpha[16]; };
 // eo_b[r] = b_end[r] + sum_i sum_c W_end[r][c] * alpha_i * b_skip_i[c]
 __global__ void k_eo_b(const double* __restrict__ w_end, const float* __restrict__ b_end, EoArgs a, int C, int L, int n2h,
@@ -233,7 +248,7 @@ long long numel(const cwg_tensor* t) {
 
 struct Layout {
   size_t cond_w, w1, w2, b1, b2, eo_b, start_w, start_b, winv, cond_b_base, cond_w_spk, spk_embed;   // element counts
-  size_t off_cond_w[3], off_w1[3], off_w2[3], off_w1_8[2], off_w2_8[2];
+  size_t off_cond_w[3], off_w1[3], off_w2[3], off_w1_8[2], off_w2_8[2], off_w0[2], w0;
   size_t off_b1, off_b2, off_eo_b, off_start_w, off_start_b, off_winv, off_cond_b_base, off_cond_w_spk, off_spk_embed;
   size_t bytes;
 };
@@ -259,6 +274,10 @@ Layout make_layout(const cwg_config* c, int mode, int E, int S) {
       l.off_w1_8[0] = take(l.w1); l.off_w1_8[1] = take(l.w1);
       l.off_w2_8[0] = take(l.w2); l.off_w2_8[1] = take(l.w2);
     }
+    if (d.ks == 3 && C == 256) {                      // layer-0 fold planes (the persistent 256-channel layer kernel)
+      l.w0 = F * 2 * C * 48;
+      l.off_w0[0] = take(l.w0 * 2); l.off_w0[1] = take(l.w0 * 2);
+    }
   }
   l.off_b1 = take(l.b1 * 4); l.off_b2 = take(l.b2 * 4); l.off_eo_b = take(l.eo_b * 4);
   l.off_start_w = take(l.start_w * 4); l.off_start_b = take(l.start_b * 4); l.off_winv = take(l.winv * 4);
@@ -282,6 +301,7 @@ void view(const Layout& l, int mode, int E, int S, void* packed, cwg_weights* w)
       w->w1_h8 = (const uint8_t*)(p + l.off_w1_8[0]); w->w1_l8 = (const uint8_t*)(p + l.off_w1_8[1]);
       w->w2_h8 = (const uint8_t*)(p + l.off_w2_8[0]); w->w2_l8 = (const uint8_t*)(p + l.off_w2_8[1]);
     }
+    if (l.w0) { w->w0_hi = (const uint16_t*)(p + l.off_w0[0]); w->w0_lo = (const uint16_t*)(p + l.off_w0[1]); }
   }
   w->b1 = (const float*)(p + l.off_b1); w->b2 = (const float*)(p + l.off_b2); w->eo_b = (const float*)(p + l.off_eo_b);
   w->start_w = (const float*)(p + l.off_start_w); w->start_b = (const float*)(p + l.off_start_b);
@@ -464,6 +484,11 @@ int cwg_pack_weights(const cwg_config* cfg, int mode, const cwg_tensor* sd, int 
       snprintf(nm, sizeof(nm), "WN.%d.in_layers.%d.bias", k, i); if (int r = need(sd, n_tensors, nm, 2 * C, &b_in)) return r;
       k_w1<<<dim3((d.K1 + 127) / 128, 2 * C), 128, 0, s>>>(w_in, c2, b_in, cb2, C, ks, H, i, p_w1, idx * 2 * C * d.K1,
                                                          (float*)w.b1 + idx * 2 * C);
+      if (i == 0 && w.w0_hi) {
+        Planes p0 = p_w1;
+        p0.hi = (uint16_t*)w.w0_hi; p0.lo = (uint16_t*)w.w0_lo; p0.f32 = nullptr;
+        k_w0<<<2 * C, 64, 0, s>>>(w_in, w_start, b_start, C, ks, n_half, p0, (size_t)k * 2 * C * 48);
+      }
       const int rs_rows = last ? C : 2 * C;
       snprintf(nm, sizeof(nm), "WN.%d.res_skip_layers.%d", k, i);
       if (int r = effective(sd, n_tensors, nm, rs_rows, C, w_rs, s)) return r;

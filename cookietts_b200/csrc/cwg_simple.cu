@@ -136,6 +136,7 @@ struct BoundaryP {
   const float* start_w;       // [C][MAX_GROUP/2] of flow_next
   const float* start_b;       // [C]
   void* x_out;
+  void* a0_out;               // layer-0 fold: planes hi, lo [BT][16] 16-bit of (audio_0 | 1 | 0...) instead of x (tensor-core modes)
 };
 
 // One block handles TB consecutive group-steps (rows of the [B*T'][G] audio state, which IS
@@ -264,13 +265,32 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
         if ((p.G & 3) == 0) for (int g = 0; g < p.G; g += 4) *reinterpret_cast<float4*>(dst + g) = make_float4(a[g], a[g + 1], a[g + 2], a[g + 3]);
         else for (int g = 0; g < p.G; ++g) dst[g] = a[g];
       }
-      if (p.do_start) {
+      if (p.do_start && p.a0_out) {
+        // layer-0 fold: the next flow's first layer contracts (audio_0, 1) with in_layers.0 * start itself; the constant-1
+        // channel carries the start bias and vanishes, like the conv's zero padding, where TMA zero-fills out-of-range steps
+        const int off2 = p.G - p.n_rem2;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = j < p.n_half2 ? a[off2 + j < CWG_MAX_GROUP ? off2 + j : 0] : (j == p.n_half2 ? 1.f : 0.f);
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float h0, h1;
+          hi[j] = sm100::pack2<XFMT == 2>(v[2 * j], v[2 * j + 1]);
+          sm100::unpack2<XFMT == 2>(hi[j], h0, h1);
+          lo[j] = sm100::pack2<XFMT == 2>(v[2 * j] - h0, v[2 * j + 1] - h1);
+        }
+        uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.a0_out) + (size_t)m * 16);
+        uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.a0_out) + ((size_t)p.BT + m) * 16);
+        oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      } else if (p.do_start) {
         const int off2 = p.G - p.n_rem2;
         for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) a_s[tid][j] = j < p.n_half2 ? a[off2 + j] : 0.f;
       }
     }
   }
-  if (!p.do_start) return;
+  if (!p.do_start || p.a0_out) return;
   __syncthreads();
   const int nrow = (int)min((long long)TBV, p.BT - m0);
   for (int cg = lane; cg < (p.C >> 3); cg += 32) {                   // audio = start(audio_0), glow.py:189
@@ -445,7 +465,7 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
 
 int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int xfmt,
                          int flow_done, int flow_next, const float* z, float sigma, float* audio,
-                         const float* eo, void* x_out, cudaStream_t s, int mix_flow, int ignore_nan) {
+                         const float* eo, void* x_out, cudaStream_t s, int mix_flow, int ignore_nan, void* a0_out) {
   // mix_flow: flow whose inverse 1x1 conv follows the coupling; -2 = the classic order (flow_done)
   if (mix_flow == -2) mix_flow = flow_done;
   BoundaryP p{};
@@ -453,6 +473,7 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
   p.init = z != nullptr; p.do_flow = flow_done >= 0; p.do_start = flow_next >= 0; p.do_mix = mix_flow >= 0;
   p.z = z; p.sigma = sigma; p.audio = audio; p.eo = eo; p.x_out = x_out; p.ignore_nan = ignore_nan;
   p.range_flag = xfmt == 2 ? range_flag() : nullptr;
+  p.a0_out = (xfmt != 0 && flow_next >= 0) ? a0_out : nullptr;
   if (p.do_flow) flow_channels(cfg, flow_done, &p.n_rem, &p.n_half);
   if (p.do_mix) {
     int nh;
@@ -471,6 +492,7 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
     else           k_flow_boundary_v<1><<<grid, TBV, 0, s>>>(p);
   } else {
     CWG_REQUIRE(xfmt != 2, "CWG_MODE_F16F8 needs n_channels % 8 == 0");
+    CWG_REQUIRE(p.a0_out == nullptr, "the layer-0 fold needs n_channels % 8 == 0");
     unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
     if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
     else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);

@@ -185,6 +185,7 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
     w2 = np.zeros((F, L, N2, C))
     b2 = np.zeros((F, L, C))
     eo_b = np.zeros((F, EO_PAD))
+    w0 = np.zeros((F, 2 * C, 48))                 # layer-0 fold: in_layers.0 * start, col = tap*16 + j (see include/cwg.h)
     start_w = np.zeros((F, C, MAX_GROUP // 2))
     start_b = np.zeros((F, C))
     winv = np.zeros((F, MAX_GROUP, MAX_GROUP))
@@ -231,6 +232,11 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
         # --- start / inverse 1x1 -------------------------------------------------------
         start_w[k, :, :n_half] = effective_weight(sd, p + "start")[:, :, 0]
         start_b[k] = _np(sd[p + "start.bias"])
+        if ks == 3:
+            w_in0 = effective_weight(sd, p + "in_layers.0")              # [2C, C, 3]
+            for tap in range(3):
+                w0[k, :, tap * 16:tap * 16 + n_half] = w_in0[:, :, tap] @ start_w[k, :, :n_half]
+                w0[k, :, tap * 16 + n_half] = w_in0[:, :, tap] @ start_b[k]
         W = _np(sd[f"convinv.{k}.conv.weight"]).reshape(n_rem, n_rem)
         # the reference inverts in fp32 (glow.py:93); fp64 here is closer to the exact inverse
         winv[k, :n_rem, :n_rem] = np.linalg.inv(W)
@@ -241,6 +247,8 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
         "winv": winv.astype(np.float32),
         "cond_b_base": cond_b.astype(np.float32), "cond_w_spk": cond_w_spk.astype(np.float32),
     }
+    if ks == 3 and C == 256 and "f32" not in planes:
+        out["w0_hi"], out["w0_lo"] = split_f16(w0) if "f16f8" in planes else split_hi_lo(w0)
     for name, arr in (("cond_w", cond_w), ("w1", w1), ("w2", w2)):
         if "f32" in planes:
             out[name + "_f32"] = arr.astype(np.float32)

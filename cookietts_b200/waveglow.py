@@ -204,6 +204,9 @@ class WaveGlow(nn.Module):
                     out[name + suffix] = at(ptr, shape, dtype)
         for name, shape in small.items():
             out[name] = at(getattr(w, name), shape, torch.float32)
+        for name in ("w0_hi", "w0_lo"):
+            if getattr(w, name):
+                out[name] = at(getattr(w, name), (F, 2 * C, 48), f16)
         return out
 
     def _cond_bias(self, batch: int, speaker_ids) -> torch.Tensor:

@@ -118,7 +118,45 @@ def main_ax(WaveGlowAx, outdir):
                             infer_ref_fp32=outs["infer_fp32"], infer_ref_fp64=outs["infer_fp64"])
 
 
+BIG_CASES = {
+    # BASELINE config 5 model on one full-length utterance (10 s, T_mel = 861): `python oracle/make_golden_waveflow.py big`.
+    # Only the reference's `inverse` outputs are stored; mel / z are regenerated from the seed and checked by CRC32.
+    "waveflow_config5_1x861": (dict(), 1, 861, 0.666, 1234, 0),
+}
+
+
+def main_big():
+    import time
+    import zlib
+    WaveGlowAx = load_reference_ax()
+    outdir = os.path.join(ROOT, "tests", "golden")
+    for name, (kw, batch, frames, sigma, wseed, iseed) in BIG_CASES.items():
+        cfg = WaveFlowConfig(**kw)
+        sd = synthetic_state_dict(cfg, wseed)
+        rs = np.random.RandomState(iseed)
+        mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
+        z = rs.standard_normal((batch, frames * cfg.hop_length)).astype(np.float32)
+        outs = {}
+        for dt, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
+            model = WaveGlowAx(**reference_kwargs(cfg))
+            model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
+            model = model.eval().to(dt)
+            t = time.time()
+            with torch.no_grad():
+                inv, _ = model.inverse(torch.from_numpy(z).to(dt) * sigma, torch.from_numpy(mel).to(dt))
+            outs[tag] = inv.numpy()
+            print(f"{name} {tag}: {time.time() - t:.1f} s", flush=True)
+        print(f"{name}: out {outs['fp64'].shape} rms {np.sqrt((outs['fp64'] ** 2).mean()):.3f} "
+              f"fp32-vs-fp64 {np.abs(outs['fp32'] - outs['fp64']).max():.2e}")
+        np.savez_compressed(os.path.join(outdir, f"{name}.npz"), config=json.dumps(kw), batch=batch, frames=frames, sigma=sigma,
+                            weight_seed=wseed, input_seed=iseed, mel_crc32=zlib.crc32(np.ascontiguousarray(mel).tobytes()),
+                            z_crc32=zlib.crc32(np.ascontiguousarray(z).tobytes()),
+                            inverse_ref_fp32=outs["fp32"], inverse_ref_fp64=outs["fp64"].astype(np.float64))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        return main_big()
     WaveGlowAx = load_reference_ax()
     outdir = os.path.join(ROOT, "tests", "golden")
     main_ax(WaveGlowAx, outdir)

@@ -177,3 +177,48 @@ def test_layer_stage(models, layer):
         d = x_ref.float() - hi
         assert float((l8 - d).abs().max()) <= float(d.abs().max()) * 0.13 + 1e-5
         assert float((h8 - hi).abs().max()) <= float(hi.abs().max()) * 0.13
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "f16f8", "bf16"])
+@pytest.mark.parametrize("flow", [11, 5, 2])
+def test_layer0_fold_matches_unfused_layer0(models, prec, flow):
+    """The layer-0 fold (start conv folded into in_layers.0: K = 3 taps x 16 instead of 768, x_0 rebuilt in the epilogue)
+    against the unfused sequence start conv -> layer 0 on the same audio state, for n_half = 4 / 3 / 2."""
+    import ctypes as C
+    lib = _cabi.load()
+    lib.cwg_debug_layer0_fused.restype = C.c_int
+    lib.cwg_debug_layer0_fused.argtypes = [C.POINTER(_cabi.CwgConfig), C.POINTER(_cabi.CwgWeights), C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    m = models[prec]
+    mode = _cabi.MODES[prec]
+    pc = m.pack_config
+    tp, H, Cc = TM * pc.phases, pc.cond_hidden, pc.n_channels
+    torch.manual_seed(100 + flow)
+    audio = torch.randn(B, tp * pc.n_group, device="cuda")
+    h2f = torch.randn(B, tp, H, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    xe = 6 if prec == "f16f8" else 4
+    h2p = f8_planes(h2f, False) if prec == "f16f8" else split(h2f)
+
+    def decode(buf):
+        if prec == "f16f8":
+            hi, lo, _, _ = f8_decode(buf, (B, tp, Cc), True)
+            return hi + lo
+        v = buf.view(torch.bfloat16).view(-1)[:2 * B * tp * Cc].view(2, B, tp, Cc)
+        return v[0].float() + v[1].float()
+    # unfused: start conv of `flow` (cwg_flow_boundary with flow_next), then layer 0 on the x planes
+    x0 = torch.zeros(B * tp * Cc * xe, dtype=torch.uint8, device="cuda")
+    _cabi.check(lib.cwg_flow_boundary(m._ccfg, m._cw, mode, -1, flow, None, 1.0, audio.data_ptr(), None, x0.data_ptr(), B, TM, stream))
+    xo_u = torch.zeros_like(x0); eo_u = torch.zeros(B, tp, 16, device="cuda")
+    _cabi.check(lib.cwg_wn_layer(m._ccfg, m._cw, mode, flow, 0, x0.data_ptr(), xo_u.data_ptr(), h2p.data_ptr(), eo_u.data_ptr(),
+                                 0, 0, B, TM, stream))
+    # fused
+    xo_f = torch.zeros_like(x0); eo_f = torch.zeros(B, tp, 16, device="cuda")
+    a0 = torch.zeros(B * tp * 64, dtype=torch.uint8, device="cuda")
+    _cabi.check(lib.cwg_debug_layer0_fused(m._ccfg, m._cw, mode, flow, audio.data_ptr(), xo_f.data_ptr(), h2p.data_ptr(),
+                                           eo_f.data_ptr(), a0.data_ptr(), B, TM, stream))
+    torch.cuda.synchronize()
+    tol = 3e-2 if prec == "bf16" else 2e-4
+    assert torch.isfinite(eo_f).all()
+    assert rel_err(eo_f, eo_u) < tol, "eo"
+    assert rel_err(decode(xo_f), decode(xo_u)) < tol, "x"

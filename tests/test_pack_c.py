@@ -60,6 +60,11 @@ def test_pack_bf16_planes(name):
         assert float((a - torch.from_numpy(b)).abs().max()) <= 2e-7 * scale, k
         same = (got[k + "_hi"].view(torch.int16).numpy().view(np.uint16) == ref[k + "_hi"]).mean()
         assert same > 0.9999, (k, same)          # identical rounding except where the fp64 sums differ in the last bits
+    if name == "config1":                        # layer-0 fold planes (256-channel models)
+        a = got["w0_hi"].float().double() + got["w0_lo"].float().double()
+        b = bf16_bits_to_f32(ref["w0_hi"]).astype(np.float64) + bf16_bits_to_f32(ref["w0_lo"]).astype(np.float64)
+        assert float((a - torch.from_numpy(b)).abs().max()) <= 2e-7 * np.abs(b).max()
+        assert np.abs(b).max() > 0
 
 
 @pytest.mark.gpu
