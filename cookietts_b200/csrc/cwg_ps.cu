@@ -127,7 +127,8 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
   uint64_t* acc2_full = acts_ready + 1;     // GEMM2 complete (both CTAs)
   uint64_t* r_free = acc2_full + 1;         // [2], leader: TMEM region g may be overwritten by the next tile's sweep g
   uint64_t* xold_full = r_free + 2;         // [2]: x_old block of column group h has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xold_full + 2);
+  uint64_t* acts0_ready = xold_full + 2;    // leader: the gate of sweep 0 (channels [0, 128) of acts) is written in both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acts0_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto slot = [&](int i) { return smem + i * TILE_A; };
@@ -141,6 +142,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     mbar_init(acts_ready, 2 * (P_EPI_THREADS / 32)); mbar_init(acc2_full, 1);
     mbar_init(&r_free[0], 2 * (P_EPI_THREADS / 64)); mbar_init(&r_free[1], 2 * (P_EPI_THREADS / 32));
     mbar_init(&xold_full[0], 1); mbar_init(&xold_full[1], 1);
+    mbar_init(acts0_ready, 2 * (P_EPI_THREADS / 32));
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
@@ -383,67 +385,79 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         commit(&acc_full[g]);
         if (stamp) tdbg[3 * g + 2] = clock64();
       }
-      // GEMM2: [res | folded end] = acts x W2^T; A hi from TMEM (".ts"), lo / e5m2 planes from units 8..11
+      // GEMM2: [res | folded end] = acts x W2^T; A hi from TMEM (".ts"), lo / e5m2 planes from units 8..11.
+      // Channels [0, 128) of acts come from sweep 0's gate, which finished long ago: their folded-`end` MMAs (N = 32,
+      // accumulator R0[32, 64), weights resident) are issued FIRST, under the gate of sweep 1; the res MMAs (whose
+      // accumulator R1 the gate of sweep 1 is still reading) and the second half follow once acts_ready fires.
       if (!wse_seen) { mbar_wait(wse_full, 0); wse_seen = true; }
+      const uint32_t dres = tmem + P_D_RES, d32 = tmem + P_D_EO;
+      auto gemm2 = [&](int half0, int half1, bool do_res, bool end_half0, bool end_half1) {
+        if (F8) {
+          for (int grp = half0; grp < half1; ++grp) {
+            const bool do_end = grp == 0 ? end_half0 : end_half1;
+            for (int it = 0; it < 4; ++it) {
+              uint32_t r = 0; int jb_cur = 0;
+              if (do_res) { jb_cur = jb; wait_full(4 + jb); jb = (jb + 1) & 3; tc_fence_after_sync(); r = smem_u32(slot(4 + jb_cur)); }
+              if (it < 2) {
+                const int kb = 2 * grp + it;
+                const uint32_t wv = smem_u32(wse(0, kb));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u, a_t = tmem + P_ACOL(kb * 4 + k);
+                  if (do_res) umma_bf16_ts_2sm(dres, a_t, umma_desc_sw128(r + o), ID256, acc);
+                  if (do_end) umma_bf16_ts_2sm(d32, a_t, umma_desc_sw128(wv + o), ID32, acc);
+                }
+              } else {
+                const uint32_t av = smem_u32(slot(8 + 2 * (it - 2) + grp)), wv = smem_u32(wse(1, 2 * (it - 2) + grp));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t o = 32 * k;
+                  if (do_res) umma_f8_2sm(dres, umma_desc_sw128(av + o), umma_desc_sw128(r + o), IDE256, 1u);
+                  if (do_end) umma_f8_2sm(d32, umma_desc_sw128(av + o), umma_desc_sw128(wv + o), IDE32, 1u);
+                }
+              }
+              if (do_res) commit(&empty[4 + jb_cur]);
+            }
+          }
+        } else {
+          for (int kb = 2 * half0; kb < 2 * half1; ++kb) {
+            const bool do_end = kb < 2 ? end_half0 : end_half1;
+            const uint32_t a_lo = smem_u32(slot(8 + kb));
+            const uint32_t w_hi = smem_u32(wse(0, kb)), w_lo = smem_u32(wse(1, kb));
+            uint32_t r_hi = 0, r_lo = 0;
+            int jb_hi = 0, jb_lo = 0;
+            if (do_res) {
+              jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
+              if (X3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
+              tc_fence_after_sync();
+              r_hi = smem_u32(slot(4 + jb_hi)); r_lo = smem_u32(slot(4 + jb_lo));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u, a_t = tmem + P_ACOL(kb * 4 + k);
+              if (do_res) umma_bf16_ts_2sm(dres, a_t, umma_desc_sw128(r_hi + o), ID256, acc);
+              if (do_end) umma_bf16_ts_2sm(d32, a_t, umma_desc_sw128(w_hi + o), ID32, acc);
+              if (X3) {
+                if (do_res) umma_bf16_2sm(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), ID256, 1u);
+                if (do_end) umma_bf16_2sm(d32, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), ID32, 1u);
+                if (do_res) umma_bf16_ts_2sm(dres, a_t, umma_desc_sw128(r_lo + o), ID256, 1u);
+                if (do_end) umma_bf16_ts_2sm(d32, a_t, umma_desc_sw128(w_lo + o), ID32, 1u);
+              }
+            }
+            if (do_res) {
+              commit(&empty[4 + jb_hi]);
+              if (X3) commit(&empty[4 + jb_lo]);
+            }
+          }
+        }
+      };
+      mbar_wait_cluster(acts0_ready, par);
+      tc_fence_after_sync();
+      gemm2(0, 1, false, true, false);                 // `end` of channels [0, 128), under the gate of sweep 1
       mbar_wait_cluster(acts_ready, par);
       tc_fence_after_sync();
       if (stamp) tdbg[6] = clock64();
-      const uint32_t dres = tmem + P_D_RES, d32 = tmem + P_D_EO;
-      if (F8) {
-        for (int grp = 0; grp < 2; ++grp)
-          for (int it = 0; it < 4; ++it) {
-            uint32_t r = 0; int jb_cur = 0;
-            if (a.has_res) { jb_cur = jb; wait_full(4 + jb); jb = (jb + 1) & 3; tc_fence_after_sync(); r = smem_u32(slot(4 + jb_cur)); }
-            if (it < 2) {
-              const int kb = 2 * grp + it;
-              const uint32_t wv = smem_u32(wse(0, kb));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u, a_t = tmem + P_ACOL(kb * 4 + k);
-                if (a.has_res) umma_bf16_ts_2sm(dres, a_t, umma_desc_sw128(r + o), ID256, acc);
-                umma_bf16_ts_2sm(d32, a_t, umma_desc_sw128(wv + o), ID32, acc);
-              }
-            } else {
-              const uint32_t av = smem_u32(slot(8 + 2 * (it - 2) + grp)), wv = smem_u32(wse(1, 2 * (it - 2) + grp));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t o = 32 * k;
-                if (a.has_res) umma_f8_2sm(dres, umma_desc_sw128(av + o), umma_desc_sw128(r + o), IDE256, 1u);
-                umma_f8_2sm(d32, umma_desc_sw128(av + o), umma_desc_sw128(wv + o), IDE32, 1u);
-              }
-            }
-            if (a.has_res) commit(&empty[4 + jb_cur]);
-          }
-      } else {
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint32_t a_lo = smem_u32(slot(8 + kb));
-          const uint32_t w_hi = smem_u32(wse(0, kb)), w_lo = smem_u32(wse(1, kb));
-          uint32_t r_hi = 0, r_lo = 0;
-          int jb_hi = 0, jb_lo = 0;
-          if (a.has_res) {
-            jb_hi = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
-            if (X3) { jb_lo = jb; wait_full(4 + jb); jb = (jb + 1) & 3; }
-            tc_fence_after_sync();
-            r_hi = smem_u32(slot(4 + jb_hi)); r_lo = smem_u32(slot(4 + jb_lo));
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t o = 32 * k, acc = (kb | k) ? 1u : 0u, a_t = tmem + P_ACOL(kb * 4 + k);
-            if (a.has_res) umma_bf16_ts_2sm(dres, a_t, umma_desc_sw128(r_hi + o), ID256, acc);
-            umma_bf16_ts_2sm(d32, a_t, umma_desc_sw128(w_hi + o), ID32, acc);
-            if (X3) {
-              if (a.has_res) umma_bf16_2sm(dres, umma_desc_sw128(a_lo + o), umma_desc_sw128(r_hi + o), ID256, 1u);
-              umma_bf16_2sm(d32, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), ID32, 1u);
-              if (a.has_res) umma_bf16_ts_2sm(dres, a_t, umma_desc_sw128(r_lo + o), ID256, 1u);
-              umma_bf16_ts_2sm(d32, a_t, umma_desc_sw128(w_lo + o), ID32, 1u);
-            }
-          }
-          if (a.has_res) {
-            commit(&empty[4 + jb_hi]);
-            if (X3) commit(&empty[4 + jb_lo]);
-          }
-        }
-      }
+      gemm2(0, 2, a.has_res != 0, false, true);        // res of all channels, `end` of channels [128, 256)
       commit(acc2_full);
       if (stamp) tdbg[7] = clock64();
     }
@@ -470,6 +484,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       asm volatile("bar.sync 1, %0;" ::"n"(P_EPI_THREADS) : "memory");
     }
     const uint32_t r0_bar = mapa_shared(&r_free[0], 0), r1_bar = mapa_shared(&r_free[1], 0), ar_bar = mapa_shared(acts_ready, 0);
+    const uint32_t a0_bar = mapa_shared(acts0_ready, 0);
     long long t_start = 0;
     if (a.dbg && warp == 4 && lane == 0) t_start = clock64();
     int n_tiles = 0;
@@ -517,6 +532,13 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           else store_split16_tmem<X3, false>(act, trow + P_ACOL(c), slot(8 + (c >> 2)), row, (c & 3) * 2);
         }
         if (stamp) edbg[2 * g + 1] = clock64();
+        if (g == 0) {                          // acts of channels [0, 128) are complete: their `end` MMAs may start
+          tmem_wait_st();
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { if (leader) mbar_arrive(acts0_ready); else mbar_arrive_cluster(a0_bar); }
+        }
       }
       tmem_wait_st();
       tc_fence_before_sync();

@@ -67,6 +67,16 @@ inline int map_w0(CUtensorMap* m, const void* ptr, uint64_t rows) {
   return make_map(m, ptr, 2, dims, st, box, false, true);
 }
 
+// shared-tap tiles: the same maps with taller boxes (128 + 2 * dilation steps, <= 256)
+inline int map_act_rows(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uint64_t B, uint32_t rows) {
+  uint64_t dims[3] = {C, Tp, B}; uint64_t st[2] = {C * 2, Tp * C * 2}; uint32_t box[3] = {64, rows, 1};
+  return make_map(m, ptr, 3, dims, st, box);
+}
+inline int map_act8_rows(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t Tp, uint64_t B, uint32_t rows) {
+  uint64_t dims[3] = {C, Tp, B}; uint64_t st[2] = {C, Tp * C}; uint32_t box[3] = {128, rows, 1};
+  return make_map(m, ptr, 3, dims, st, box, true);
+}
+
 // 8-bit (e5m2) planes: the same tiles measured in bytes - 128 channels x 128 steps / 128 k x box_rows rows = 16 KB units
 inline int map_2d8(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   uint64_t dims[2] = {cols, rows}; uint64_t st[1] = {cols}; uint32_t box[2] = {128, box_rows};

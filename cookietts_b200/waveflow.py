@@ -146,6 +146,7 @@ class _Coupling(nn.Module):
 
 class WaveFlow(nn.Module, AxFrontEndMixin):
     """`efficient_model_ax.WaveGlow(..., waveflow=True)` - inverse pass on B200."""
+    GRAPH_MAX_FRAMES = 4096
 
     def __init__(self, n_mel_channels, n_flows, n_group, n_early_every, n_early_size, memory_efficient,
                  spect_scaling, upsample_mode, upsample_first, speaker_embed, cond_layers, cond_hidden_channels,
@@ -157,11 +158,12 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                  transposed_conv_hidden_dim=256, transposed_conv_kernel_size=4, transposed_conv_scales=None,
                  transposed_conv_output_dim=256, transposed_conv_residual=False, transposed_conv_residual_linear=False,
                  transposed_conv_res_rezero=False, group_conv_output_dim=None, group_conv_groupped=True,
-                 iso226_empthasis=False, precision: str = "bf16x3"):
+                 iso226_empthasis=False, precision: str = "bf16x3", graphs="auto"):
         super().__init__()
         wn = dict(WN_config)
         a = dict(locals())
         self._check_supported(a, wn)
+        self.graphs, self._graphs = graphs, {}       # CUDA-graph replay: "auto" = calls of <= GRAPH_MAX_FRAMES mel frames in total
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
         self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
@@ -244,6 +246,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self._ccfg = CwgWfConfig(pc.n_mel, pc.n_flows, pc.n_group, pc.n_layers, pc.n_channels, pc.kernel_h, pc.kernel_w,
                                  pc.hop_length, int(pc.upsample_linear))
         self._packed, self._packed_key, self._cw = dev_pk, key, w
+        self._graphs = {}
 
     @torch.no_grad()
     def inverse(self, z, cond, speaker_ids=None, return_CPU=True):
@@ -268,15 +271,45 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             nbytes = lib.cwg_wf_workspace_bytes(self._ccfg, mode, B, frames, T)
             if nbytes == 0:
                 raise _cabi.CwgError(lib.cwg_last_error().decode())
-            if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
-                self._workspace = None
-                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-            ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
-            audio = torch.empty(B, T, device=dev, dtype=torch.float32)
-            _cabi.check(lib.cwg_wf_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
-                                         z.data_ptr(), 1.0, audio.data_ptr(), ws_ptr,
-                                         self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
-                                         B, T, torch.cuda.current_stream(dev).cuda_stream))
+
+            def launch(cond_t, z_t, audio_t, ws_t):
+                ws_ptr = (ws_t.data_ptr() + 1023) // 1024 * 1024
+                _cabi.check(lib.cwg_wf_infer(self._ccfg, self._cw, mode, cond_t.data_ptr(), frames, 0,
+                                             z_t.data_ptr(), 1.0, audio_t.data_ptr(), ws_ptr,
+                                             ws_t.numel() - (ws_ptr - ws_t.data_ptr()),
+                                             B, T, torch.cuda.current_stream(dev).cuda_stream))
+            use_graph = (not torch.cuda.is_current_stream_capturing() and
+                         (self.graphs is True or (self.graphs == "auto" and B * frames <= self.GRAPH_MAX_FRAMES)))
+            if use_graph:
+                # the row-by-row inverse is > 1000 small launches per call: repeated shapes replay a captured CUDA graph
+                key = (B, frames, T, mode)
+                ent = self._graphs.get(key)
+                if ent is None:
+                    if len(self._graphs) >= 4:
+                        self._graphs.pop(next(iter(self._graphs)))
+                    s_cond, s_z = cond.clone(), z.clone()
+                    s_audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+                    s_ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+                    side = torch.cuda.Stream(dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        launch(s_cond, s_z, s_audio, s_ws)       # warm-up outside the capture
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        launch(s_cond, s_z, s_audio, s_ws)
+                    ent = (g, s_cond, s_z, s_audio, s_ws)
+                    self._graphs[key] = ent
+                else:
+                    ent[1].copy_(cond); ent[2].copy_(z)
+                ent[0].replay()
+                audio = ent[3].clone()
+            else:
+                if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
+                    self._workspace = None
+                    self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+                audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+                launch(cond, z, audio, self._workspace)
             audio = self._fe_post(audio)                     # inverse volume map / de-emphasis on the device
         return (audio.cpu() if return_CPU else audio), None
 

@@ -72,10 +72,13 @@ class WN(nn.Module):
 
 
 class WaveGlow(nn.Module):
+    GRAPH_MAX_FRAMES = 2048
+    GRAPH_CACHE = 8
+
     def __init__(self, yoyo=False, yoyo_WN=False, n_mel_channels=80, n_flows=12, n_group=8,
                  n_early_every=4, n_early_size=2, memory_efficient=False, spect_scaling=False,
                  upsample_mode="normal", WN_config=None, win_length=1024, hop_length=256,
-                 precision: str = "bf16x3", range_guard: bool = True):
+                 precision: str = "bf16x3", range_guard: bool = True, graphs="auto"):
         super().__init__()
         if yoyo or yoyo_WN:
             raise ValueError("yoyo models select a different reference class (efficient_model*), not glow.WaveGlow")
@@ -97,6 +100,10 @@ class WaveGlow(nn.Module):
         self.range_guard = range_guard     # f16f8: check the fp16 range after every infer and fall back to bf16x3
         self.last_status = 0
         self.fallbacks = 0
+        # CUDA-graph replay of repeated small shapes (launch-bound regime: ~125 launches per call): "auto" = calls of at
+        # most GRAPH_MAX_FRAMES mel frames in total, True = always, False = never
+        self.graphs = graphs
+        self._graphs = {}
         self.upsample = nn.ConvTranspose1d(n_mel_channels, n_mel_channels, win_length, stride=hop_length)
         self.WN = nn.ModuleList()
         self.convinv = nn.ModuleList()
@@ -160,7 +167,7 @@ class WaveGlow(nn.Module):
         precision = precision or self.precision
         key = self._weights_key()
         if self._packed_key != key:
-            self._packs, self._packed_key = {}, key
+            self._packs, self._packed_key, self._graphs = {}, key, {}
         if precision not in self._packs:
             ops, lib = _torch_ops.load(), _cabi.load()
             mode = _cabi.MODES[precision]
@@ -295,8 +302,13 @@ class WaveGlow(nn.Module):
                     if not e.cuda_event:
                         e.record(torch.cuda.current_stream(dev))
                 ev_b, ev_e = [int(e.cuda_event) for e in begin], [int(e.cuda_event) for e in end]
-            audio, status = ops.waveglow_infer(self._packed, self._cfg_list, mode, self._embed_dim, self._n_speakers, mel,
-                                               speaker_id, z, float(sigma), ev_b, ev_e)
+            use_graph = (layer_events is None and not torch.cuda.is_current_stream_capturing() and
+                         (self.graphs is True or (self.graphs == "auto" and batch * t_mel <= self.GRAPH_MAX_FRAMES)))
+            if use_graph:
+                audio, status = self._graph_infer(ops, mode, mel, speaker_id, z, float(sigma))
+            else:
+                audio, status = ops.waveglow_infer(self._packed, self._cfg_list, mode, self._embed_dim, self._n_speakers, mel,
+                                                   speaker_id, z, float(sigma), ev_b, ev_e)
             if self.precision == "f16f8" and self.range_guard and not torch.cuda.is_current_stream_capturing():
                 # fp16 hi planes: values beyond +-65504 (or a NaN / Inf waveform) are flagged on the device (cwg_infer_status);
                 # reading the flag synchronises this call.  On a hit the call is repeated in bf16x3 (fp32 exponent range).
@@ -310,6 +322,39 @@ class WaveGlow(nn.Module):
                     audio, _ = ops.waveglow_infer(self._packs["bf16x3"][0], self._cfg_list, _cabi.MODES["bf16x3"], self._embed_dim,
                                                   self._n_speakers, mel, speaker_id, z, float(sigma), [], [])
         return audio
+
+    def _graph_infer(self, ops, mode, mel, speaker_id, z, sigma):
+        """Replays the captured launch sequence of this (shape, sigma) on static input buffers; captures it on first use."""
+        dev = mel.device
+        if speaker_id is not None:
+            speaker_id = speaker_id.to(dev)
+        key = (tuple(mel.shape), sigma, mode, speaker_id is not None)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            s_mel, s_z = mel.clone(), z.clone()
+            s_spk = speaker_id.clone() if speaker_id is not None else None
+
+            def run():
+                return ops.waveglow_infer(self._packed, self._cfg_list, mode, self._embed_dim, self._n_speakers, s_mel, s_spk,
+                                          s_z, sigma, [], [])
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                run()                                   # warm-up outside the capture (tensor-map cache, lazy module loads)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = run()
+            ent = (g, s_mel, s_z, s_spk, out)
+            self._graphs[key] = ent
+        else:
+            ent[1].copy_(mel); ent[2].copy_(z)
+            if speaker_id is not None:
+                ent[3].copy_(speaker_id)
+        ent[0].replay()
+        return ent[4][0].clone(), ent[4][1]
 
     def launch_count(self) -> int:
         """Kernels launched by one `infer` call in the current precision mode."""

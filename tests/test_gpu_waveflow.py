@@ -69,3 +69,50 @@ def test_unsupported_options_raise():
     bad = dict(kw, WN_config=dict(kw["WN_config"], n_channels=64))
     with pytest.raises(NotImplementedError):
         WaveFlow(**bad)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_config5_full_length_matches_reference(precision):
+    """One full-length utterance (T_mel = 861, 10 s: 108 tiles per row step) of the config-5 model against the unmodified
+    reference's `inverse` run in fp32 and fp64 (tests/golden/waveflow_config5_1x861.npz; mel / z regenerated from the seed)."""
+    import zlib
+    g = np.load(os.path.join(GOLDEN_DIR, "waveflow_config5_1x861.npz"))
+    cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+    sd = synthetic_state_dict(cfg, int(g["weight_seed"]))
+    rs = np.random.RandomState(int(g["input_seed"]))
+    batch, frames = int(g["batch"]), int(g["frames"])
+    mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
+    z = rs.standard_normal((batch, frames * cfg.hop_length)).astype(np.float32)
+    assert zlib.crc32(np.ascontiguousarray(mel).tobytes()) == int(g["mel_crc32"])
+    assert zlib.crc32(np.ascontiguousarray(z).tobytes()) == int(g["z_crc32"])
+    m = build(cfg, sd, precision)
+    out, _ = m.inverse(torch.from_numpy(z).cuda() * float(g["sigma"]), torch.from_numpy(mel).cuda(), return_CPU=True)
+    ref = g["inverse_ref_fp64"]
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert max_abs(out.numpy(), ref) <= TOL[precision]["max_abs"]
+    assert snr_db(ref, out.numpy()) >= TOL[precision]["snr"]
+
+
+def test_config5_batch_64_full_length_is_consistent():
+    """BASELINE config 5 at its full size (64 x 10 s, bf16x3): utterance 0 carries the golden's inputs and must match the
+    reference's waveform; every utterance is independent of its batch (same bytes as a batch-1 call)."""
+    g = np.load(os.path.join(GOLDEN_DIR, "waveflow_config5_1x861.npz"))
+    cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+    sd = synthetic_state_dict(cfg, int(g["weight_seed"]))
+    rs = np.random.RandomState(int(g["input_seed"]))
+    frames = int(g["frames"])
+    mel0 = np.clip(rs.standard_normal((1, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
+    z0 = rs.standard_normal((1, frames * cfg.hop_length)).astype(np.float32)
+    gen = torch.Generator().manual_seed(7)
+    mel = (torch.randn(64, cfg.n_mel_channels, frames, generator=gen) * 2.0 - 5.0).clamp_(-11.5129, 2.0)
+    z = torch.randn(64, frames * cfg.hop_length, generator=gen)
+    mel[0], z[0] = torch.from_numpy(mel0[0]), torch.from_numpy(z0[0])
+    m = build(cfg, sd, "bf16x3")
+    sigma = float(g["sigma"])
+    out, _ = m.inverse(z.cuda() * sigma, mel.cuda(), return_CPU=True)
+    assert torch.isfinite(out).all()
+    ref = g["inverse_ref_fp64"]
+    assert max_abs(out[:1].numpy(), ref) <= TOL["bf16x3"]["max_abs"]
+    assert snr_db(ref, out[:1].numpy()) >= TOL["bf16x3"]["snr"]
+    one, _ = m.inverse(z[37:38].cuda() * sigma, mel[37:38].cuda(), return_CPU=True)
+    assert torch.equal(one[0], out[37])
