@@ -519,7 +519,18 @@ int cwg_wf_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
                  const float* mel, int frames, int pad_frames, const float* z, float sigma,
                  float* audio, void* workspace, size_t workspace_bytes,
                  int batch, int t_samples, void* cuda_stream) {
+  return cwg_wf_infer_profiled(cfg, w, mode, mel, frames, pad_frames, z, sigma, audio, workspace, workspace_bytes, batch,
+                               t_samples, cuda_stream, nullptr, nullptr, 0);
+}
+
+int cwg_wf_infer_profiled(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
+                          const float* mel, int frames, int pad_frames, const float* z, float sigma,
+                          float* audio, void* workspace, size_t workspace_bytes,
+                          int batch, int t_samples, void* cuda_stream,
+                          void** layer_ev_begin, void** layer_ev_end, int n_events) {
   if (int r = wf_check(cfg, mode, batch, t_samples)) return r;
+  CWG_REQUIRE(n_events == 0 || (layer_ev_begin && layer_ev_end), "event arrays are NULL");
+  int ev = 0;
   CWG_REQUIRE(w && w->w1_hi && w->w1_lo && w->w2_hi && w->w2_lo && w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b,
               "missing weight arrays");
   CWG_REQUIRE(mel && z && audio && frames >= 1 && pad_frames >= 0, "bad tensor arguments");
@@ -548,8 +559,11 @@ int cwg_wf_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
     const bool first_flow = k == F - 1, last_flow = k == 0;
     for (int i = -1; i < h - 1; ++i) {                                  // efficient_modules.py:49,56
       if (i >= 0)
-        for (int l = 0; l < L; ++l)
+        for (int l = 0; l < L; ++l, ++ev) {
+          if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_begin[ev], s));
           if (int r = wf_launch_layer(cfg, d, w, npass, k, l, i, ws.x, ws.mel_up, ws.eo, s)) return r;
+          if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)layer_ev_end[ev], s));
+        }
       const int j = i + 1;                                              // logical row produced now
       WfRowP p{};
       p.BT = d.BT; p.G = h;

@@ -107,6 +107,8 @@ def _bind(lib):
     lib.cwg_wf_infer.argtypes = [C.POINTER(CwgWfConfig), C.POINTER(CwgWfWeights), C.c_int,
                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.cwg_wf_infer_profiled.restype = C.c_int
+    lib.cwg_wf_infer_profiled.argtypes = lib.cwg_wf_infer.argtypes + [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
     lib.cwg_wf_layer.restype = C.c_int
     lib.cwg_wf_layer.argtypes = [C.POINTER(CwgWfConfig), C.POINTER(CwgWfWeights), C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -249,8 +251,9 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self._graphs = {}
 
     @torch.no_grad()
-    def inverse(self, z, cond, speaker_ids=None, return_CPU=True):
-        """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
+    def inverse(self, z, cond, speaker_ids=None, return_CPU=True, *, layer_events=None):
+        """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None).
+        `layer_events` = (begin, end) lists of torch.cuda.Event recorded around the first len(begin) WN_2d layer launches."""
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("cookietts_b200.WaveFlow needs the module on a CUDA device (no CPU fallback)")
@@ -274,11 +277,21 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
 
             def launch(cond_t, z_t, audio_t, ws_t):
                 ws_ptr = (ws_t.data_ptr() + 1023) // 1024 * 1024
-                _cabi.check(lib.cwg_wf_infer(self._ccfg, self._cw, mode, cond_t.data_ptr(), frames, 0,
-                                             z_t.data_ptr(), 1.0, audio_t.data_ptr(), ws_ptr,
-                                             ws_t.numel() - (ws_ptr - ws_t.data_ptr()),
-                                             B, T, torch.cuda.current_stream(dev).cuda_stream))
-            use_graph = (not torch.cuda.is_current_stream_capturing() and
+                arr_b = arr_e = None
+                n_ev = 0
+                if layer_events is not None:
+                    begin, end = layer_events
+                    for e in list(begin) + list(end):
+                        if not e.cuda_event:
+                            e.record(torch.cuda.current_stream(dev))
+                    arr_b = (C.c_void_p * len(begin))(*[e.cuda_event for e in begin])
+                    arr_e = (C.c_void_p * len(end))(*[e.cuda_event for e in end])
+                    n_ev = len(begin)
+                _cabi.check(lib.cwg_wf_infer_profiled(self._ccfg, self._cw, mode, cond_t.data_ptr(), frames, 0,
+                                                      z_t.data_ptr(), 1.0, audio_t.data_ptr(), ws_ptr,
+                                                      ws_t.numel() - (ws_ptr - ws_t.data_ptr()),
+                                                      B, T, torch.cuda.current_stream(dev).cuda_stream, arr_b, arr_e, n_ev))
+            use_graph = (layer_events is None and not torch.cuda.is_current_stream_capturing() and
                          (self.graphs is True or (self.graphs == "auto" and B * frames <= self.GRAPH_MAX_FRAMES)))
             if use_graph:
                 # the row-by-row inverse is > 1000 small launches per call: repeated shapes replay a captured CUDA graph
@@ -314,7 +327,8 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         return (audio.cpu() if return_CPU else audio), None
 
     @torch.no_grad()
-    def infer(self, spect, speaker_ids=None, artifact_trimming=1, sigma=1., t_scaler=1.0, return_CPU=True, *, z=None):
+    def infer(self, spect, speaker_ids=None, artifact_trimming=1, sigma=1., t_scaler=1.0, return_CPU=True, *, z=None,
+              layer_events=None):
         """efficient_model_ax.py:359-388.  `z` ([B, samples], standard normal) injects the latent."""
         if spect.dim() == 2:
             spect = spect[None]
@@ -329,7 +343,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         zz = z.to(dev).float() * float(sigma) if sigma > 0 else torch.zeros(B, samples, device=dev)
         if artifact_trimming > 0:                            # F.pad(spect, (0, artifact_trimming), value=0.0), :370-371
             spect = torch.nn.functional.pad(spect.to(dev).float(), (0, artifact_trimming), value=0.0)
-        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU)
+        audio, _ = self.inverse(zz, spect, speaker_ids, return_CPU=return_CPU, layer_events=layer_events)
         if artifact_trimming > 0:
             audio = audio[:, :-artifact_trimming * self.hop_length]
         return audio.to(in_dtype)

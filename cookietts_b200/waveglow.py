@@ -78,7 +78,7 @@ class WaveGlow(nn.Module):
     def __init__(self, yoyo=False, yoyo_WN=False, n_mel_channels=80, n_flows=12, n_group=8,
                  n_early_every=4, n_early_size=2, memory_efficient=False, spect_scaling=False,
                  upsample_mode="normal", WN_config=None, win_length=1024, hop_length=256,
-                 precision: str = "bf16x3", range_guard: bool = True, graphs="auto"):
+                 precision: str = "auto", range_guard: bool = True, graphs="auto"):
         super().__init__()
         if yoyo or yoyo_WN:
             raise ValueError("yoyo models select a different reference class (efficient_model*), not glow.WaveGlow")
@@ -96,6 +96,11 @@ class WaveGlow(nn.Module):
         self.multispeaker = WN_config["speaker_embed_dim"] > 0
         self.n_flows, self.n_group = n_flows, n_group
         self.n_early_every, self.n_early_size = n_early_every, n_early_size
+        # "auto": the fastest fp32-accurate mode the kernels have for this width - f16f8 (guarded by the fp16 range check with
+        # its bf16x3 fallback) for 256 channels and kernel size 3, bf16x3 for 512 channels, fp32 CUDA cores otherwise
+        if precision == "auto":
+            c, ks = WN_config["n_channels"], WN_config["kernel_size"]
+            precision = "f16f8" if (c == 256 and ks == 3) else ("bf16x3" if (c == 512 and ks == 3) else "ffma")
         self.precision = precision
         self.range_guard = range_guard     # f16f8: check the fp16 range after every infer and fall back to bf16x3
         self.last_status = 0

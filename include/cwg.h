@@ -262,6 +262,14 @@ int cwg_wf_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
                  float* audio, void* workspace, size_t workspace_bytes,
                  int batch, int t_samples, void* cuda_stream);
 
+/* Same; additionally records the caller's cudaEvent_t pairs around the e-th WN_2d layer launch (order: flows n_flows-1..0,
+ * row steps 0..n_group-2, layers 0..n_layers-1) for e < n_events - bench.py times k_wf_layer_tc inside the real call. */
+int cwg_wf_infer_profiled(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
+                          const float* mel, int frames, int pad_frames, const float* z, float sigma,
+                          float* audio, void* workspace, size_t workspace_bytes,
+                          int batch, int t_samples, void* cuda_stream,
+                          void** layer_ev_begin, void** layer_ev_end, int n_events);
+
 int cwg_wf_launch_count(const cwg_wf_config* cfg);
 
 /* Stage entry point (tests): one WN_2d layer of one autoregressive row step.
