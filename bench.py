@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py - WaveGlow inverse pass (mel -> wave) throughput on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision P] [--config C] [--no-extra]
 
 A "step" is one `WaveGlow.infer` over one batch of synthetic 80-bin mels with injected z.
 At N=1 the workload is BASELINE.json configs[1]: 12-flow / 256-channel WaveGlow, batch 16 x 10 s
 (T_mel = 861), sigma 0.666, the fp32-accurate path.  Default precision `f16f8` (fp16 hi*hi plus two e5m2 cross-term
-MMAs in the in_layer GEMM, three fp16 products elsewhere, fp32 accumulate: 6.7e-5 max-abs / 98.8 dB SNR against the
-fp64 reference on config 1, bar 1e-3 / 60 dB); `--precision bf16x3` is the 3-pass variant (3.3e-5 / 107 dB).  The JSON
-line carries a live accuracy check of one utterance of the batch against the exact-fp32 CUDA-core mode.
-For N>1 every rank processes its own batch of the same shape (weak scaling, the path shards by
-utterance) and rank 0 gathers the waveforms over NCCL inside the timed region.
+MMAs in the in_layer and res_skip GEMMs, three fp16 products elsewhere, fp32 accumulate: 1.2e-4 max-abs / 96 dB SNR
+against the fp64 reference on 10-s utterances, bar 1e-3 / 60 dB; guarded by the fp16 range check); `--precision bf16x3` is
+the 3-pass variant (4.5e-5 / 107 dB).  The JSON line carries a live accuracy check of one utterance of the batch against
+the exact-fp32 CUDA-core mode.  For N>1 every rank processes its own batch of the same shape (weak scaling, the path
+shards by utterance) and rank 0 gathers the waveforms over NCCL inside the timed region - asynchronously, so that the
+gather of step i overlaps step i+1; every outstanding gather is waited for before the timed region closes.
 
 One JSON line is printed by rank 0.  `value` = audio samples / s with inputs resident in HBM;
 `e2e` = the same through host buffers (pinned H2D of mel+z, D2H of the waveform) per step;
-`roofline` = the WN layer kernel's algorithmic FLOP/s (timed with CUDA events around every
-layer launch inside the timed steps) against the measured bf16 peak; `cpu_baseline` = the
-torch-op CPU port of the reference on this box's host cores on a bounded sample.
+`roofline` = the WN layer kernel's algorithmic FLOP/s (CUDA events around every layer launch inside the timed steps,
+also by layer index) against the measured bf16 peak, with the ncu figures of the same kernel read from
+profiles/r2_ncu.json when its source hash matches; `cpu_baseline` / `--impl reference` = the reference's own
+`WaveGlow.infer` (oracle/_ref, an unmodified copy of glow.py) on this box's host cores on a bounded sample;
+`extra_configs` = 3-step runs of BASELINE configs 3 (bf16, 256 x 10 s over the ranks), 4 (512-channel model, 60 s in
+halo-overlapped chunks) and 5 (WaveFlow) at the same GPU count (`--no-extra` skips them; `--config N` runs one alone).
 """
 from __future__ import annotations
 
@@ -329,6 +333,9 @@ def run_waveflow(args):
     n_ev = 15 * 8
     ev_b = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
     ev_e = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    for evs in ev_b + ev_e:          # event handles are created lazily: outside the timed region
+        for e in evs:
+            e.record()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); t0.record()
     for i in range(args.steps):
@@ -577,6 +584,9 @@ def run_waveglow(args):
     ev_b = [[torch.cuda.Event(enable_timing=True) for _ in range(n_layers_total)] for _ in range(args.steps)]
     ev_e = [[torch.cuda.Event(enable_timing=True) for _ in range(n_layers_total)] for _ in range(args.steps)]
 
+    for evs in ev_b + ev_e:          # torch creates event handles lazily: do it here, outside the timed region
+        for e in evs:
+            e.record()
     for _ in range(warmup):
         step_resident()
     drain()

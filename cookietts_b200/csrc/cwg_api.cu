@@ -18,8 +18,11 @@ void set_error(const char* fmt, ...) {
 }
 
 static thread_local int* g_range_flag = nullptr;
+static thread_local bool g_range_all = false;
 int* range_flag() { return g_range_flag; }
 void set_range_flag(int* flag) { g_range_flag = flag; }
+bool range_all_layers() { return g_range_all; }
+void set_range_all_layers(bool on) { g_range_all = on; }
 
 namespace {
 
@@ -373,6 +376,10 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   const int F = cfg->n_flows, L = cfg->n_layers;
   void* x0 = tc ? (void*)ws.xb[0] : (void*)ws.x[0];
   void* h2 = tc ? (void*)ws.h2b : (void*)ws.h2;
+  // status word as in cwg_infer (cwg_infer_status): the fp16 planes of CWG_MODE_F16F8 are range-checked
+  CWG_CHECK_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(int), s));
+  set_range_flag(mode == CWG_MODE_F16F8 ? ws.status : nullptr);
+  auto run = [&]() -> int {
   // cond = interpolate(mel) once for all flows (upsample_first), efficient_model_ax.py:313-314
   if (int r = launch_mel_up(xfmt, mel, h2, d.B, d.M, frames, frames + pad_frames, d.Tp, d.H, upsample_linear, s)) return r;
   // z -> audio state; mix_first=False applies the channel mixing of flow F-1 before its coupling
@@ -390,6 +397,14 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
     if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s,
                                      mix_first ? k : k - 1, /*ignore_nan=*/1)) return r;
   }
+  return 0;
+  };
+  set_range_all_layers(true);      // ignore_nan flushes NaNs at every flow boundary: no overflow may rely on reaching the waveform
+  const int rc = run();
+  set_range_all_layers(false);
+  set_range_flag(nullptr);
+  if (rc) return rc;
+  if (mode == CWG_MODE_F16F8) return launch_nonfinite(audio, (size_t)batch * t_samples, ws.status, s, false);
   return 0;
 }
 

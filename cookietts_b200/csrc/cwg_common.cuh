@@ -80,6 +80,9 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
 // +-65504 (set by cwg_infer around its launches; NULL = no check).  Host-side, thread-local.
 int* range_flag();
 void set_range_flag(int* flag);
+// ax models flush NaNs at flow boundaries (ignore_nan), so there every residual layer checks its x_new, not only the last
+bool range_all_layers();
+void set_range_all_layers(bool on);
 
 int launch_nonfinite(const float* x, size_t n, int* flag, cudaStream_t s, bool clear);
 

@@ -826,7 +826,7 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.fused0 = a0 != nullptr; a.audio = audio; a.G = d.G; a.a_off = a_off; a.a_nh = a_nh;
   a.start_w = w->start_w + (size_t)flow * d.C * (CWG_MAX_GROUP / 2); a.start_b = w->start_b + (size_t)flow * d.C;
   a.w0_row0 = flow * 2 * d.C;
-  a.range_flag = (npass == 2 && layer == d.L - 2) ? range_flag() : nullptr;
+  a.range_flag = (npass == 2 && (layer == d.L - 2 || range_all_layers())) ? range_flag() : nullptr;
   int ncl = 0;
   if (int r = (npass == 3 ? max_clusters<3>(&ncl) : npass == 2 ? max_clusters<2>(&ncl) : max_clusters<1>(&ncl))) return r;
   if (ncl > a.n_pairs) ncl = a.n_pairs;

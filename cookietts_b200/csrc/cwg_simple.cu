@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
 // (efficient_model_ax.py:171-182).  XFMT 0: fp32; 1: bf16 hi plane then lo plane.
 template <int XFMT>
 __global__ void k_mel_up(const float* __restrict__ mel, void* __restrict__ out, int B, int M, int frames,
-                         int frames_padded, int Tp, int H, int linear) {
+                         int frames_padded, int Tp, int H, int linear, int* range_flag) {
   long long n = (long long)B * Tp * H;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -396,6 +396,7 @@ __global__ void k_mel_up(const float* __restrict__ mel, void* __restrict__ out, 
   } else if (XFMT == 2) {                     // CWG_MODE_F16F8 cond planes: fp16 hi, e5m2(lo * 2^P), e5m2(hi * 2^-Q)
     const __half h = __float2half_rn(v);
     const float hf = __half2float(h);
+    if (range_flag && !(fabsf(v) < 65504.f)) atomicOr(range_flag, 2);
     reinterpret_cast<__half*>(out)[i] = h;
     uint8_t* p8 = reinterpret_cast<uint8_t*>(out) + 2 * n;
     p8[i] = (uint8_t)(sm100::pack_e5m2x4((v - hf) * F8_LO_SCALE, 0.f, 0.f, 0.f) & 0xffu);
@@ -414,9 +415,9 @@ int launch_mel_up(int xfmt, const float* mel, void* out, int B, int M, int frame
                   int linear, cudaStream_t s) {
   long long n = (long long)B * Tp * H;
   unsigned grid = (unsigned)((n + 255) / 256);
-  if (xfmt == 2) k_mel_up<2><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
-  else if (xfmt == 0) k_mel_up<0><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
-  else           k_mel_up<1><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear);
+  if (xfmt == 2) k_mel_up<2><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear, range_flag());
+  else if (xfmt == 0) k_mel_up<0><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear, nullptr);
+  else           k_mel_up<1><<<grid, 256, 0, s>>>(mel, out, B, M, frames, frames_padded, Tp, H, linear, nullptr);
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

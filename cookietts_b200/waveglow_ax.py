@@ -269,11 +269,21 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                 self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
             audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+            stream = torch.cuda.current_stream(dev).cuda_stream
             _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
                                          int(self.upsample_linear), int(self.mix_first), z.data_ptr(), 1.0,
                                          audio.data_ptr(), ws_ptr,
                                          self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
-                                         B, T, torch.cuda.current_stream(dev).cuda_stream))
+                                         B, T, stream))
+            if self.precision == "f16f8" and not torch.cuda.is_current_stream_capturing():
+                # fp16 range guard (include/cwg.h cwg_infer_status): a value beyond +-65504 in an fp16 operand plane, or a
+                # non-finite waveform, means the f16f8 result cannot be trusted - this model must run in bf16x3
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                _cabi.check(lib.cwg_infer_status(ws_ptr, status.data_ptr(), stream))
+                self.last_status = int(status.item())
+                if self.last_status:
+                    raise _cabi.CwgError(f"WaveGlowAx(precision='f16f8'): fp16 range guard tripped (status {self.last_status}); "
+                                         "construct the model with precision='bf16x3'")
             audio = self._fe_post(audio)                     # inverse volume map / de-emphasis on the device
         return (audio.cpu() if return_CPU else audio), None
 
