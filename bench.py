@@ -483,7 +483,7 @@ def main():
 
 def with_extra_configs(args, line, rank):
     """Short (3-step) runs of BASELINE configs 3, 4 and 5 at this run's GPU count, attached to the headline line as
-    `extra_configs` (still ONE JSON line).  A watchdog prints the headline without them if they overrun."""
+    `extra_configs` (still ONE JSON line), plus the headline workload in the 3-pass `bf16x3` mode.  A watchdog prints the headline without them if they overrun."""
     import copy
     done = {"extras": {}}
 
@@ -496,8 +496,9 @@ def with_extra_configs(args, line, rank):
     timer.daemon = True
     timer.start()
     keep = ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "dtype", "config", "xrt", "algorithmic_tflops",
-            "roofline", "gpu_launches", "output_finite", "e2e")
-    for name, fn, kw in (("config3", run_waveglow, dict(config=3)), ("config4", run_longform, dict(config=4)),
+            "roofline", "gpu_launches", "output_finite", "e2e", "accuracy", "clocks")
+    for name, fn, kw in (("config2_bf16x3", run_waveglow, dict(config=2, precision="bf16x3")),
+                         ("config3", run_waveglow, dict(config=3)), ("config4", run_longform, dict(config=4)),
                          ("config5", run_waveflow, dict(config=5, workload="waveflow"))):
         a = copy.copy(args)
         a.steps, a.warmup, a.no_cpu_baseline, a.precision = 3, 3, True, "bf16"

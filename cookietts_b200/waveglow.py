@@ -364,4 +364,5 @@ class WaveGlow(nn.Module):
     def launch_count(self) -> int:
         """Kernels launched by one `infer` call in the current precision mode."""
         lib = _cabi.load()
-        return int(lib.cwg_launch_count(_cabi.make_config(self.pack_config), _cabi.MODES[self.precision]))
+        # cwg_infer's kernels + the k_cond_bias launch of cwg_cond_bias that waveglow_infer issues before it
+        return int(lib.cwg_launch_count(_cabi.make_config(self.pack_config), _cabi.MODES[self.precision])) + 1
