@@ -1,0 +1,26 @@
+"""Small end-to-end calls of every product path for `compute-sanitizer --tool memcheck python tools/memcheck_small.py`."""
+import os, sys, json
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cookietts_b200 import WaveGlow, FlowDecoder
+from tests.helpers import load_golden
+from tests.test_cabi_cpu import module_kwargs
+from oracle.flow_decoder_oracle import FlowDecoderConfig, synthetic_state_dict as fd_sd
+from oracle.make_golden_flow_decoder import hparams_for
+
+for name in ("mel20_256", "speaker256"):
+    cfg, sd, g = load_golden(name)
+    for prec in ("f16f8", "bf16x3", "bf16", "ffma"):
+        m = WaveGlow(precision=prec, graphs=False, **module_kwargs(cfg))
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.cuda().eval()
+        spk = torch.from_numpy(g["speaker_id"]).cuda() if g["speaker_id"].size else None
+        out = m.infer(torch.from_numpy(g["mel"]).cuda(), spk, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
+        torch.cuda.synchronize()
+        print(name, prec, float(np.abs(out.cpu().numpy() - g["audio_ref_fp64"]).max()), flush=True)
+gf = np.load("tests/golden/fd_untts.npz")
+cfg = FlowDecoderConfig(**json.loads(str(gf["config"])))
+fd = FlowDecoder(hparams_for(cfg, "untts"))
+fd.load_state_dict({k: torch.from_numpy(v) for k, v in fd_sd(cfg, int(gf["weight_seed"])).items()}); fd = fd.cuda().eval()
+o, _ = fd.inverse(torch.from_numpy(gf["z"]).cuda() * float(gf["sigma"]), torch.from_numpy(gf["cond"]).cuda())
+torch.cuda.synchronize()
+print("fd_untts", float(np.abs(o.cpu().numpy() - gf["out_ref_fp64"]).max()), flush=True)
