@@ -24,6 +24,7 @@
 // R1 = [256,512): sweep-1 accumulators, afterwards the res accumulator.
 #include "cwg_tc_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace cwg {
@@ -89,7 +90,8 @@ __device__ __forceinline__ void split16_f8_words(const float* v, uint32_t* hi, u
   }
 }
 
-template <int NPASS>
+// FUSED0: the layer-0 fold variant (compiled separately so that its extra registers do not burden layers 1..L-1)
+template <int NPASS, bool FUSED0>
 __global__ void __launch_bounds__(P_THREADS, 1)
 k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
            const __grid_constant__ CUtensorMap tm_h_hi, const __grid_constant__ CUtensorMap tm_h_lo,
@@ -188,7 +190,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     for (int p = cluster_id; p < a.n_pairs; p += n_clusters) {
       int b, t0; tile_of(p, b, t0);
       for (int g = 0; g < 2; ++g) {
-        if (a.fused0) {
+        if (FUSED0) {
           // one ring item per plane: the 3 tap tiles [128 steps x 16 channels] of the coupling input (4 KB each)
           for (int pl = 0; pl < PL2; ++pl) {
             mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
@@ -202,7 +204,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         if (F8) {
           // K in groups of 128 channels (taps 0..2 of x: groups 0..5, H2: groups 6, 7); per group two fp16 tiles of 64
           // channels, then the e5m2 tile of lo*2^P and the e5m2 tile of hi*2^-Q (128 channels = 128 bytes per row)
-          for (int G = a.fused0 ? 6 : 0; G < 8; ++G)
+          for (int G = FUSED0 ? 6 : 0; G < 8; ++G)
             for (int it = 0; it < 4; ++it) {
               mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
               pm ^= 1u << s;
@@ -216,7 +218,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               s = (s + 1) & 3;
             }
         } else {
-          for (int kb = a.fused0 ? 12 : 0; kb < 16; ++kb)
+          for (int kb = FUSED0 ? 12 : 0; kb < 16; ++kb)
             for (int pl = 0; pl < PL; ++pl) {
               mbar_wait(&empty[s], ((pm >> s) & 1u) ^ 1u);
               pm ^= 1u << s;
@@ -244,7 +246,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     for (int p = cluster_id; p < a.n_pairs; p += n_clusters) {
       for (int g = 0; g < 2; ++g) {
         const int w1_row = a.w1_row0 + (int)rank * 256 + g * 128;
-        if (a.fused0) {
+        if (FUSED0) {
           const int w0_row = a.w0_row0 + (int)rank * 256 + g * 128;
           for (int pl = 0; pl < PL2; ++pl) {
             mbar_wait(&empty[4 + j], ((pm >> j) & 1u) ^ 1u);
@@ -256,7 +258,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           }
         }
         if (F8) {
-          for (int G = a.fused0 ? 6 : 0; G < 8; ++G)
+          for (int G = FUSED0 ? 6 : 0; G < 8; ++G)
             for (int it = 0; it < 4; ++it) {
               next_slot();
               if (it < 2) ldb2(slot(4 + j), &tm_w1_hi, &full[4 + j], (2 * G + it) * 64, w1_row);
@@ -264,7 +266,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               j = (j + 1) & 3;
             }
         } else {
-          for (int kb = a.fused0 ? 12 : 0; kb < 16; ++kb)
+          for (int kb = FUSED0 ? 12 : 0; kb < 16; ++kb)
             for (int pl = 0; pl < PL; ++pl) {
               next_slot();
               ldb2(slot(4 + j), pl ? &tm_w1_lo : &tm_w1_hi, &full[4 + j], kb * 64, w1_row);
@@ -326,7 +328,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         tc_fence_after_sync();
         if (stamp) tdbg[3 * g + 1] = clock64();
         const uint32_t d = tmem + g * 256;
-        if (a.fused0) {
+        if (FUSED0) {
           // x part of layer 0: 3 taps x (hi*hi [+ lo*hi + hi*lo]) K = 16 MMAs on the 32B-swizzled 4-KB tiles
           const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
           int sa_lo = sa_hi;
@@ -350,7 +352,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
           if (X3) { commit(&empty[4 + jb_lo]); commit(&empty[sa_lo]); }
         }
         if (F8) {
-          for (int G = a.fused0 ? 6 : 0; G < 8; ++G)
+          for (int G = FUSED0 ? 6 : 0; G < 8; ++G)
             for (int it = 0; it < 4; ++it) {
               const int sa_cur = sa; wait_full(sa); sa = (sa + 1) & 3;
               const int jb_cur = jb; wait_full(4 + jb); jb = (jb + 1) & 3;
@@ -361,7 +363,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               commit(&empty[sa_cur]);
             }
         } else {
-          for (int kb = a.fused0 ? 12 : 0; kb < 16; ++kb) {
+          for (int kb = FUSED0 ? 12 : 0; kb < 16; ++kb) {
             const int sa_hi = sa; wait_full(sa); sa = (sa + 1) & 3;
             int sa_lo = 0;
             if (NPASS == 3) { sa_lo = sa; wait_full(sa); sa = (sa + 1) & 3; }
@@ -476,7 +478,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       const int e = threadIdx.x - 128;
       b1s[e] = __ldg(a.b1 + e) * GateK<NPASS>::KA; b1s[256 + e] = __ldg(a.b1 + 256 + e) * GateK<NPASS>::KB;
       b2s[e] = __ldg(a.b2 + e);
-      if (a.fused0) {          // start conv of this flow: S [256][8] (columns >= n_half are zero) and its bias
+      if (FUSED0) {          // start conv of this flow: S [256][8] (columns >= n_half are zero) and its bias
         const float4* sw = reinterpret_cast<const float4*>(a.start_w + (size_t)e * (CWG_MAX_GROUP / 2));
         reinterpret_cast<float4*>(s_tab)[2 * e] = __ldg(sw); reinterpret_cast<float4*>(s_tab)[2 * e + 1] = __ldg(sw + 1);
         s_bias[e] = __ldg(a.start_b + e);
@@ -499,7 +501,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         tma_load_3d(u_lo, &tm_x_lo, &xold_full[h], blk * 64, t0, b);
       };
       // bf16: units 8..11 hold no gate output, so the first x_old block can be fetched a whole tile ahead
-      if (!X3 && a.has_res && !a.fused0 && ldr) load_xold(2 * h);
+      if (!X3 && a.has_res && !FUSED0 && ldr) load_xold(2 * h);
 
       // ---- gates: acts = tanh(pre[:, :C]) * sigmoid(pre[:, C:]) (glow.py:34-41), sweep by sweep
       const bool stamp = a.dbg && n_tiles == 2 && warp == 4 && lane == 0;
@@ -569,7 +571,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&r_free[0]); else mbar_arrive_cluster(r0_bar); }   // R0: acts consumed by GEMM2, `end` read
       }
-      if (X3 && a.has_res && !a.fused0 && ldr) load_xold(2 * h);  // GEMM2 no longer reads units 8..11
+      if (X3 && a.has_res && !FUSED0 && ldr) load_xold(2 * h);  // GEMM2 no longer reads units 8..11
       if (h == 0) {
         if (valid) {
           float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
@@ -583,7 +585,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         uint32_t buf[2][16];
         const int c0 = 8 * h;
         float av[CWG_MAX_GROUP / 2];                 // fused0: this row's coupling input audio_0 (fp32, exact)
-        if (a.fused0) {
+        if (FUSED0) {
           const float* ar = a.audio + m * a.G + a.a_off;
 #pragma unroll
           for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) av[j] = (valid && j < a.a_nh) ? __ldg(ar + j) : 0.f;
@@ -593,7 +595,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
         for (int i = 0; i < 8; ++i) {
           const int c = c0 + i;
           uint32_t* cur = buf[i & 1];
-          if ((i & 3) == 0 && !a.fused0) { mbar_wait(&xold_full[h], xph); xph ^= 1u; }   // x_old tiles of this 64-channel block have landed
+          if ((i & 3) == 0 && !FUSED0) { mbar_wait(&xold_full[h], xph); xph ^= 1u; }   // x_old tiles of this 64-channel block have landed
           tmem_wait16(cur);
           if (i + 1 < 8) tmem_issue16(trow + P_D_RES + (c + 1) * 16, buf[(i + 1) & 1]);
           else {                                                           // last TMEM read of this warp: release R1
@@ -609,7 +611,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
             r[4 * q] = __uint_as_float(cur[4 * q]) + bb.x; r[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + bb.y;
             r[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + bb.z; r[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + bb.w;
           }
-          if (a.fused0) {
+          if (FUSED0) {
             // x_old = start(audio_0) = S a + b in fp32 (glow.py:189), never stored: 8 FMAs per channel, S broadcast from smem
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -662,11 +664,11 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
               tma_store_3d(&tm_xo_lo, u_lo, blk * 64, t0, b);
               tma_store_commit();
               tma_store_wait_read();
-              if (i == 3 && !a.fused0) load_xold(blk + 1);
+              if (i == 3 && !FUSED0) load_xold(blk + 1);
             }
             // fused0 has no x_old load (whose mbarrier orders the re-use of the staging tiles in the other path): nobody
             // may overwrite them before the store above has read them
-            if (a.fused0 && i == 3) asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
+            if (FUSED0 && i == 3) asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
           }
         }
         // the staging units become gate outputs of the next tile (written by BOTH column groups)
@@ -777,11 +779,11 @@ int get_maps(const Dims& d, const cwg_weights* w, int npass, const __nv_bfloat16
   return 0;
 }
 
-template <int NPASS>
+template <int NPASS, bool FUSED0>
 int max_clusters(int* out) {
   static int cached = 0;                           // per process; all GPUs of a box are the same part
   if (cached == 0) {
-    CWG_CHECK_CUDA(cudaFuncSetAttribute(k_layer_ps<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    CWG_CHECK_CUDA(cudaFuncSetAttribute(k_layer_ps<NPASS, FUSED0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(2 * 148); lc.blockDim = dim3(P_THREADS); lc.dynamicSmemBytes = P_SMEM;
     cudaLaunchAttribute at[1];
@@ -789,7 +791,7 @@ int max_clusters(int* out) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     int n = 0;
-    CWG_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, k_layer_ps<NPASS>, &lc));
+    CWG_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, k_layer_ps<NPASS, FUSED0>, &lc));
     CWG_REQUIRE(n >= 1, "k_layer_ps does not fit on this device (cudaOccupancyMaxActiveClusters = %d)", n);
     cached = n;
   }
@@ -828,7 +830,10 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.w0_row0 = flow * 2 * d.C;
   a.range_flag = (npass == 2 && (layer == d.L - 2 || range_all_layers())) ? range_flag() : nullptr;
   int ncl = 0;
-  if (int r = (npass == 3 ? max_clusters<3>(&ncl) : npass == 2 ? max_clusters<2>(&ncl) : max_clusters<1>(&ncl))) return r;
+  const bool f0 = a0 != nullptr;
+  if (int r = (npass == 3 ? (f0 ? max_clusters<3, true>(&ncl) : max_clusters<3, false>(&ncl))
+               : npass == 2 ? (f0 ? max_clusters<2, true>(&ncl) : max_clusters<2, false>(&ncl))
+                            : (f0 ? max_clusters<1, true>(&ncl) : max_clusters<1, false>(&ncl)))) return r;
   if (ncl > a.n_pairs) ncl = a.n_pairs;
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(2 * ncl); lc.blockDim = dim3(P_THREADS); lc.dynamicSmemBytes = P_SMEM; lc.stream = s;
@@ -836,12 +841,13 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   lc.attrs = at; lc.numAttrs = 1;
-#define CWG_LAUNCH_PS(NP)                                                                                              \
-  CWG_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_layer_ps<NP>, m->x_hi, m->x_lo, m->h_hi, m->h_lo, m->w1_hi, m->w1_lo,       \
+#define CWG_LAUNCH_PS(NP, F0)                                                                                          \
+  CWG_CHECK_CUDA(cudaLaunchKernelEx(&lc, k_layer_ps<NP, F0>, m->x_hi, m->x_lo, m->h_hi, m->h_lo, m->w1_hi, m->w1_lo,       \
                                     m->w2_hi, m->w2_lo, m->wse_hi, m->wse_lo, m->xo_hi, m->xo_lo, m->x_l8, m->x_h8,    \
                                     m->h_l8, m->h_h8, m->w1_h8, m->w1_l8, m->w2_l8, m->wse_l8, m->a0_hi, m->a0_lo,  \
                                     m->w0_hi, m->w0_lo, a))
-  if (npass == 3) CWG_LAUNCH_PS(3); else if (npass == 2) CWG_LAUNCH_PS(2); else CWG_LAUNCH_PS(1);
+  if (f0) { if (npass == 3) CWG_LAUNCH_PS(3, true); else if (npass == 2) CWG_LAUNCH_PS(2, true); else CWG_LAUNCH_PS(1, true); }
+  else { if (npass == 3) CWG_LAUNCH_PS(3, false); else if (npass == 2) CWG_LAUNCH_PS(2, false); else CWG_LAUNCH_PS(1, false); }
 #undef CWG_LAUNCH_PS
   return 0;
 }

@@ -4,8 +4,9 @@
  *   CookieTTS/_4_mtw/waveglow/glow.py:314-350   WaveGlow.infer(spect, speaker_id, sigma)
  * and the functions it calls (WN.forward :188-222, Invertible1x1Conv.forward(reverse=True)
  * :85-99, fused_add_tanh_sigmoid_multiply :34-41).  The reference has no FFI of its own
- * (pure Python on torch); the binding a maintainer adds is the ctypes stub in
- * INTEGRATION.md, which is what cookietts_b200/_cabi.py does.
+ * (pure Python on torch); the bindings a maintainer adds are in INTEGRATION.md: the torch.ops shim
+ * (cookietts_b200/csrc/torch_ops.cpp, what cookietts_b200.WaveGlow.infer calls) and the ctypes stub
+ * (cookietts_b200/_cabi.py, what the stage-level tests call).
  *
  * Conventions
  *  - Every pointer in cwg_weights / cwg_infer is a DEVICE pointer owned by the caller.
@@ -17,9 +18,10 @@
  *    T = T_mel*hop; latent channel c of group-step s is z[b, s*n_group + c], channels ordered
  *    as the reference stacks them at the end of infer (early outputs of the lowest flow
  *    first, the main latent last; glow.py:326,342-347).
- *  - Packed weights are produced by cookietts_b200/packing.py (weight-norm folded, the
- *    linear cond chain folded with the transposed-conv upsampler, `end` folded into the
- *    skip half of res_skip; see DESIGN.md "Packed weights").
+ *  - Packed weights are produced by cwg_pack_weights below from the reference state_dict (weight-norm folded, the
+ *    linear cond chain folded with the transposed-conv upsampler, `end` folded into the skip half of res_skip,
+ *    `start` folded into in_layers.0; see DESIGN.md "Packed weights").  cookietts_b200/packing.py is the numpy
+ *    statement of the same algebra that the tests hold it to (and that the ax / WaveFlow packers build on).
  */
 #ifndef CWG_H
 #define CWG_H
