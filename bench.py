@@ -658,10 +658,12 @@ def run_waveglow(args):
     achieved = float(flops_per_launch.sum() / (layer_avg_ms.sum() * 1e-3) / 1e12)
     passes = {"bf16x3": 3, "bf16": 1, "ffma": 1, "f16f8": 2}[args.precision]   # f16f8: 1 fp16 + 2 half-cost e5m2 passes in GEMM1
     ps = args.channels == 256 and args.precision != "ffma" and os.environ.get("CWG_LAYER_PS", "1") != "0"
-    kernel = (f"k_layer_ps<{passes}>" if ps else "k_layer_tc") if args.channels == 256 else "k_gate512_tc+k_res512_tc"
+    # k_layer_ps<NPASS, FUSED0>: 7 of the 8 launches per flow are the <NPASS, 0> variant, layer 0 is <NPASS, 1> (start fold)
+    kernel = (f"k_layer_ps<{passes},0>" if ps else "k_layer_tc") if args.channels == 256 else "k_gate512_tc+k_res512_tc"
     if args.precision == "ffma":
         kernel = "k_sgemm"
     ncu = ncu_record(kernel) if (B, Tm) == (16, 861) else None      # captured at the bench's default shape only
+    ncu0 = ncu_record(f"k_layer_ps<{passes},1>") if (ps and (B, Tm) == (16, 861)) else None
     roofline = {
         "bound": "tensor", "kernel": kernel,
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -677,6 +679,9 @@ def run_waveglow(args):
         "l2_to_sm_tbps": (ncu["l2_to_sm_bytes"] / (float(layer_avg_ms.mean()) * 1e-3) / 1e12) if ncu and ncu.get("l2_to_sm_bytes") else None,
         "ncu_tensor_pipe_active_pct": ncu["tensor_pipe_active_pct"] if ncu else None,
         "ncu_source": "profiles/r2_ncu.json (sha256 of csrc matches)" if ncu else None,
+        "ncu_layer0_fold_variant": ({"kernel": f"k_layer_ps<{passes},1>", "traffic": ncu0["dram_bytes"],
+                                     "l2_to_sm_bytes_per_launch": ncu0["l2_to_sm_bytes"],
+                                     "tensor_pipe_active_pct": ncu0["tensor_pipe_active_pct"]} if ncu0 else None),
         "launches_timed": int(layer_ms.size), "avg_launch_ms": float(layer_avg_ms.mean()),
         # mean duration by WN layer index (dilation 2^i; layer 0 runs the start-conv fold, the last layer has no residual)
         "launch_ms_by_layer": [round(float(layer_avg_ms.reshape(12, 8)[:, i].mean()), 4) for i in range(8)],

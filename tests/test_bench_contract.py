@@ -53,7 +53,7 @@ def test_gpu_arm_json_line():
     e = d["e2e"]
     assert e["value"] > 1e7 and e["h2d_bytes_per_step"] == 16 * (80 * 861 + 861 * 256) * 4 and e["d2h_bytes_per_step"] == 16 * 861 * 256 * 4
     r = d["roofline"]
-    assert r["bound"] == "tensor" and r["kernel"] == "k_layer_ps<2>" and r["unit"] == "TFLOP/s"
+    assert r["bound"] == "tensor" and r["kernel"] == "k_layer_ps<2,0>" and r["unit"] == "TFLOP/s"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.2 < r["frac"] < 0.6
     assert r["launches_timed"] == 2 * 96 and len(r["launch_ms_by_layer"]) == 8
     assert r["layer_share_of_step"] < 1.0                       # 96 x avg launch <= step
