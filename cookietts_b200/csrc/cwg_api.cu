@@ -177,6 +177,10 @@ const char* cwg_last_error(void) { return cwg::g_err; }
 
 size_t cwg_workspace_bytes(const cwg_config* cfg, int mode, int batch, int t_mel) {
   if (check_config(cfg) || check_mode(cfg, mode) || batch < 1 || t_mel < 1) return 0;
+  if ((long long)batch * t_mel * (cfg->hop_length / cfg->n_group) >= (1ll << 31) / 4) {
+    set_error("batch * T' too large for one call; split the batch");
+    return 0;
+  }
   Dims d = make_dims(cfg, batch, t_mel);
   Workspace ws;
   carve(d, mode, nullptr, &ws);

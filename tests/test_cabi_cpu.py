@@ -52,6 +52,8 @@ def test_workspace_and_argument_validation():
     assert n_tc < n_f8 < n_ffma
     assert lib.cwg_launch_count(cfg, _cabi.MODE_F16F8) == lib.cwg_launch_count(cfg, _cabi.MODE_BF16X3) + 1   # + the range guard scan
     assert lib.cwg_workspace_bytes(c512, _cabi.MODE_F16F8, 1, 4) == 0 and b"F16F8" in lib.cwg_last_error()
+    # maximum size: batch * T' beyond what one call indexes is refused with a message, not wrapped around
+    assert lib.cwg_workspace_bytes(cfg, _cabi.MODE_F16F8, 4096, 8192) == 0 and b"too large" in lib.cwg_last_error()
     # NULL weights -> error code, not a crash
     rc = lib.cwg_infer(cfg, None, _cabi.MODE_FFMA, None, None, None, 1.0, None, None, 0, 1, 1, None)
     assert rc != 0 and b"NULL" in lib.cwg_last_error()
