@@ -483,6 +483,43 @@ def main():
         print(json.dumps(line), flush=True)
 
 
+def run_config1_latency(args):
+    """BASELINE config 1 on the GPU: one 1-s utterance (T_mel = 86) per call, the module's defaults (f16f8, CUDA-graph
+    replay of the repeated shape); per-call latency by CUDA events over 20 calls, every rank its own copy."""
+    import torch
+    from cookietts_b200 import WaveGlow
+    from cookietts_b200.synthetic import ModelConfig, synthetic_state_dict
+    world, rank, local_rank, dev = dist_setup()
+    model = WaveGlow(**MODEL_KW)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic_state_dict(ModelConfig(), 1234).items()})
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    mel = (torch.randn(1, 80, 86, generator=g) * 2.0 - 5.0).clamp_(-11.5129, 2.0).to(dev)
+    z = torch.randn(1, 86 * 256, generator=g).to(dev)
+    for _ in range(3):
+        out = model.infer(mel, sigma=0.666, z=z)
+    torch.cuda.synchronize()
+    n = 20
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(n):
+        out = model.infer(mel, sigma=0.666, z=z)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / n
+    finite = bool(torch.isfinite(out).all())
+    graph = bool(model._graphs)
+    del model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"value": 86 * 256 / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": n, "ms_per_step": ms, "scaling": "replicas",
+            "dtype": "f16f8", "config": {"workload": "WaveGlow 12-flow/256-ch inverse pass, 1 x 86 mel frames (1.0 s) per call, sigma 0.666, "
+                                         "injected z: per-call latency (11 tile pairs on 74 SM pairs: one pair-time per layer)",
+                                         "cuda_graph_replay": graph},
+            "xrt": 86 * 256 / (ms * 1e-3) / SR, "output_finite": finite}
+
+
 def with_extra_configs(args, line, rank):
     """Short (3-step) runs of BASELINE configs 3, 4 and 5 at this run's GPU count, attached to the headline line as
     `extra_configs` (still ONE JSON line), plus the headline workload in the 3-pass `bf16x3` mode.  A watchdog prints the headline without them if they overrun."""
@@ -499,7 +536,8 @@ def with_extra_configs(args, line, rank):
     timer.start()
     keep = ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "dtype", "config", "xrt", "algorithmic_tflops",
             "roofline", "gpu_launches", "output_finite", "e2e", "accuracy", "clocks")
-    for name, fn, kw in (("config2_bf16x3", run_waveglow, dict(config=2, precision="bf16x3")),
+    for name, fn, kw in (("config1_latency", run_config1_latency, dict(config=1)),
+                         ("config2_bf16x3", run_waveglow, dict(config=2, precision="bf16x3")),
                          ("config3", run_waveglow, dict(config=3)), ("config4", run_longform, dict(config=4)),
                          ("config5", run_waveflow, dict(config=5, workload="waveflow"))):
         a = copy.copy(args)
