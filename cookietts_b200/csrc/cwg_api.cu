@@ -387,11 +387,12 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   // cond = interpolate(mel) once for all flows (upsample_first), efficient_model_ax.py:313-314
   if (int r = launch_mel_up(xfmt, mel, h2, d.B, d.M, frames, frames + pad_frames, d.Tp, d.H, upsample_linear, s)) return r;
   // z -> audio state; mix_first=False applies the channel mixing of flow F-1 before its coupling
-  if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s, mix_first ? -1 : F - 1)) return r;
+  void* a0 = (tc && fold_active(d, w)) ? ws.a0 : nullptr;       // layer-0 fold, as in cwg_infer
+  if (int r = launch_flow_boundary(cfg, d, w, xfmt, -1, F - 1, z, sigma, audio, nullptr, x0, s, mix_first ? -1 : F - 1, 0, a0)) return r;
   for (int k = F - 1; k >= 0; --k) {                       // efficient_model_ax.py:325
     for (int i = 0; i < L; ++i) {
       if (tc) {
-        if (int r = layer_tc(cfg, d, w, npass, k, i, ws, nullptr, s)) return r;   // ax: no layer-0 fold
+        if (int r = layer_tc(cfg, d, w, npass, k, i, ws, audio, s)) return r;
       } else {
         if (int r = launch_layer_ffma(d, w, k, i, ws.x[i & 1], ws.x[(i + 1) & 1], ws.h2, ws.eo, ws.pre, ws.acts, s)) return r;
       }
@@ -399,7 +400,7 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
     // coupling inverse of flow k, then (mix_first) mixing of flow k or (else) mixing of flow k-1
     // after the early-z concat, then the start conv of flow k-1
     if (int r = launch_flow_boundary(cfg, d, w, xfmt, k, k - 1, nullptr, sigma, audio, ws.eo, x0, s,
-                                     mix_first ? k : k - 1, /*ignore_nan=*/1)) return r;
+                                     mix_first ? k : k - 1, /*ignore_nan=*/1, a0)) return r;
   }
   return 0;
   };

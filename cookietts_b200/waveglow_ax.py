@@ -42,6 +42,7 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
     w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, EO_PAD))
     start_w = np.zeros((F, Cc, MAX_GROUP // 2)); start_b = np.zeros((F, Cc))
     winv = np.zeros((F, MAX_GROUP, MAX_GROUP))
+    w0 = np.zeros((F, 2 * Cc, 48))                           # layer-0 fold: in_layers.0 * start (include/cwg.h w0_hi / w0_lo)
     for k, (n_rem, n_half) in enumerate(pc.flow_channels()):
         p = f"WN.{k}.WN."
         w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]
@@ -69,6 +70,11 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
         eo_b[k, :2 * n_half] = eo_bias
         start_w[k, :, :n_half] = effective_weight(sd, p + "start")[:, :, 0]
         start_b[k] = _np(sd[p + "start.bias"])
+        if ks == 3:
+            w_in0, _ = in_layer_weight_bias(sd, p + "in_layers.0")
+            for tap in range(3):
+                w0[k, :, tap * 16:tap * 16 + n_half] = w_in0[:, :, tap] @ start_w[k, :, :n_half]
+                w0[k, :, tap * 16 + n_half] = w_in0[:, :, tap] @ start_b[k]
         if channel_mixing == "permuteheight":
             for c, src in enumerate(permute_height_index(k, n_rem)):
                 winv[k, c, src] = 1.0
@@ -84,6 +90,8 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
             out[name + "_h8"], out[name + "_l8"] = f8_correction_planes(arr)
         elif "hi" in planes:
             out[name + "_hi"], out[name + "_lo"] = split_hi_lo(arr)
+    if ks == 3 and Cc == 256 and "f32" not in planes:
+        out["w0_hi"], out["w0_lo"] = split_f16(w0) if "f16f8" in planes else split_hi_lo(w0)
     return out
 
 
@@ -228,7 +236,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                 arr = arr.view(np.int16)
             dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
         w = _cabi.CwgWeights()
-        for f in _cabi.WEIGHT_FIELDS:
+        for f in _cabi.WEIGHT_FIELDS + ("w0_hi", "w0_lo"):
             setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
         self.pack_config = pc
         self._ccfg = _cabi.make_config(pc)
