@@ -110,4 +110,12 @@ int launch_layer_tc512(const Dims& d, const cwg_weights* w, int npass, int flow,
                        const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
                        __nv_bfloat16* acts, float* eo, cudaStream_t s);
 
+// ---- fp32 CUDA-core WaveFlow path (cwg_wf_ffma.cu), dispatched by cwg_wf_* for CWG_MODE_FFMA ----
+int wff_check(const cwg_wf_config* c, int batch, int t_samples);
+size_t wff_workspace_bytes(const cwg_wf_config* c, int batch, int t_samples);
+int wff_launch_count(const cwg_wf_config* c);
+int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* mel, int frames, int pad_frames,
+              const float* z, float sigma, float* audio, void* workspace, size_t workspace_bytes, int batch, int t_samples,
+              cudaStream_t s, void** ev_begin, void** ev_end, int n_events);
+
 }  // namespace cwg

@@ -492,6 +492,7 @@ extern "C" {
 
 size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples) {
   (void)frames;
+  if (mode == CWG_MODE_FFMA) return wff_workspace_bytes(cfg, batch, t_samples);
   if (wf_check(cfg, mode, batch, t_samples)) return 0;
   WfDims d = wf_dims(cfg, batch, t_samples);
   WfWorkspace ws;
@@ -528,6 +529,13 @@ int cwg_wf_infer_profiled(const cwg_wf_config* cfg, const cwg_wf_weights* w, int
                           float* audio, void* workspace, size_t workspace_bytes,
                           int batch, int t_samples, void* cuda_stream,
                           void** layer_ev_begin, void** layer_ev_end, int n_events) {
+  if (mode == CWG_MODE_FFMA) {
+    CWG_REQUIRE(n_events == 0 || (layer_ev_begin && layer_ev_end), "event arrays are NULL");
+    CWG_REQUIRE(mel && z && audio && frames >= 1 && pad_frames >= 0, "bad tensor arguments");
+    CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
+    return wff_infer(cfg, w, mel, frames, pad_frames, z, sigma, audio, workspace, workspace_bytes, batch, t_samples,
+                     (cudaStream_t)cuda_stream, layer_ev_begin, layer_ev_end, n_events);
+  }
   if (int r = wf_check(cfg, mode, batch, t_samples)) return r;
   CWG_REQUIRE(n_events == 0 || (layer_ev_begin && layer_ev_end), "event arrays are NULL");
   int ev = 0;

@@ -1,0 +1,245 @@
+// WaveFlow inverse pass on the fp32 CUDA cores (CWG_MODE_FFMA of cwg_wf_infer): the exact-fp32 cross-check of the
+// tensor-core WaveFlow kernels (cwg_wf.cu) and the path for every WN_2d shape those are not specialised for - any even
+// channel count, any kernel (kernel_h x odd kernel_w, e.g. the 7x7 depthwise-separable in_layers of the reference's trained
+// WaveFlow checkpoints, folded to a dense conv at pack time), squeeze heights up to 32, any number of cond channels.
+// Same algorithm, same packed-weight layout and same host loop as cwg_wf.cu:
+//   efficient_model_ax.py:279-357 WaveGlow.inverse, efficient_modules.py:42-65 WaveFlowCoupling.inverse (row by row),
+//   glow_ax.py:556-635 WN_2d.forward with its per-layer conv queue (a ring of kernel_h rows per layer here),
+//   efficient_modules.py:360-403 PermuteHeight (host-side column bookkeeping).
+#include "cwg_common.cuh"
+
+namespace cwg {
+namespace {
+
+constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int WFF_MAX_GROUP = 32;
+
+struct WffGemmP {
+  long long BT; int Tp, C, KH, KW, M;      // M = cond channels
+  int N, K;                                // output columns, contraction length
+  const float* W; const float* bias;       // W [N][K]
+  // GEMM1 (in_layer + cond): x ring of this layer [KH][BT][C]; newest row index `row`; mel_up [BT][M]
+  const float* ring; const float* mel; int row, dil;
+  float* pre;                              // [BT][2C]
+  // GEMM2 (res_skip + folded end): acts [BT][C]; x_cur = ring slot of `row`; x_next = next layer's slot (NULL: last layer)
+  const float* acts; const float* x_cur; float* x_next; float* eo; const float* eo_b; int first;
+};
+
+template <int MODE>     // 0: GEMM1, 1: GEMM2
+__device__ __forceinline__ float wff_a(const WffGemmP& p, long long m, int kk) {
+  if (m >= p.BT || kk >= p.K) return 0.f;
+  if (MODE == 1) return __ldg(p.acts + (size_t)m * p.C + kk);
+  const int kx = p.KH * p.KW * p.C;
+  if (kk >= kx) return __ldg(p.mel + (size_t)m * p.M + (kk - kx));
+  const int a = kk / (p.KW * p.C), rem = kk - a * p.KW * p.C;
+  const int b = rem / p.C, c = rem - b * p.C;
+  const int src_row = p.row - (p.KH - 1 - a);                     // causal in height: padding_h = kernel_h - 1 on top
+  if (src_row < 0) return 0.f;                                    // the zero-initialised conv queue (glow_ax.py:597-602)
+  const long long ub = m / p.Tp; const int t = (int)(m - ub * p.Tp);
+  const int tt = t + (b - p.KW / 2) * p.dil;                      // 'same' zero padding in width
+  if (tt < 0 || tt >= p.Tp) return 0.f;
+  return __ldg(p.ring + ((size_t)(src_row % p.KH) * p.BT + (size_t)ub * p.Tp + tt) * p.C + c);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_wff_gemm(WffGemmP p) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const long long m0 = (long long)blockIdx.x * GM;
+  const int n0 = blockIdx.y * GN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < p.K; k0 += GK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256, row = idx / GK, kk = idx % GK;
+      As[kk][row] = wff_a<MODE>(p, m0 + row, k0 + kk);
+      Bs[kk][row] = (n0 + row < p.N && k0 + kk < p.K) ? __ldg(p.W + (size_t)(n0 + row) * p.K + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= p.BT) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      if (MODE == 0) {
+        p.pre[(size_t)m * p.N + n] = acc[i][j] + __ldg(p.bias + n);
+      } else if (n < p.C) {                                       // x = x + res (glow_ax.py:620-626)
+        if (p.x_next) p.x_next[(size_t)m * p.C + n] = __ldg(p.x_cur + (size_t)m * p.C + n) + acc[i][j] + __ldg(p.bias + n);
+      } else {                                                    // folded `end` of the skip path: (log_s, t)
+        const int e = n - p.C;
+        float* q = p.eo + (size_t)m * CWG_EO_PAD + e;
+        *q = (p.first ? __ldg(p.eo_b + e) : *q) + acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void k_wff_gate(const float* __restrict__ pre, float* __restrict__ acts, long long n, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long m = i / C; const int c = (int)(i - m * C);
+  const float a = pre[m * 2 * C + c], b = pre[m * 2 * C + C + c];
+  acts[i] = tanhf(a) * (1.f / (1.f + expf(-b)));                  // GTU, glow_ax.py:36-43
+}
+
+__global__ void k_wff_mel_up(const float* __restrict__ mel, float* __restrict__ out, int B, int M, int frames,
+                             int frames_padded, int Tp, int linear) {
+  const long long n = (long long)B * Tp * M;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % M); const long long m = i / M;
+  const int t = (int)(m % Tp), b = (int)(m / Tp);
+  const float* row = mel + ((size_t)b * M + c) * frames;
+  auto at = [&](int f) { return f < frames ? row[f] : 0.f; };
+  float v;
+  if (linear) {                                                   // F.interpolate(mode='linear', align_corners=True)
+    const double src = Tp > 1 ? (double)t * (double)(frames_padded - 1) / (double)(Tp - 1) : 0.0;
+    const int i0 = min((int)floor(src), frames_padded - 1), i1 = min(i0 + 1, frames_padded - 1);
+    const float w = (float)(src - (double)i0);
+    v = at(i0) * (1.f - w) + at(i1) * w;
+  } else {
+    v = at(min((int)floor((double)t * ((double)frames_padded / (double)Tp)), frames_padded - 1));
+  }
+  out[i] = v;
+}
+
+// finishes AR step row-1 and prepares step row (see k_wf_row in cwg_wf.cu)
+__global__ void k_wff_row(long long BT, int G, int C, const float* __restrict__ in, float in_scale, int col_in,
+                          float* __restrict__ out, int col_out, const float* __restrict__ eo, int do_couple,
+                          const float* __restrict__ start_w, const float* __restrict__ start_b, float* __restrict__ x0) {
+  const long long m = blockIdx.x;
+  __shared__ float vs;
+  if (threadIdx.x == 0) {
+    float v = in[m * G + col_in] * in_scale;
+    if (do_couple) v = (v - eo[m * CWG_EO_PAD + 1]) * expf(-eo[m * CWG_EO_PAD]);   // efficient_modules.py:62-63
+    out[m * G + col_out] = v;
+    vs = v;
+  }
+  if (x0 == nullptr) return;
+  __syncthreads();
+  const float v = vs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) x0[(size_t)m * C + c] = fmaf(__ldg(start_w + c), v, __ldg(start_b + c));
+}
+
+void wff_perm(int k, int h, int* idx) {               // PermuteHeight index list of flow k (efficient_modules.py:341-353)
+  if (k % 4 == 2 || k % 4 == 3) {
+    const int half = h / 2;
+    for (int i = 0; i < half; ++i) idx[i] = half - 1 - i;
+    for (int i = half; i < h; ++i) idx[i] = h - 1 - (i - half);
+  } else {
+    for (int i = 0; i < h; ++i) idx[i] = h - 1 - i;
+  }
+}
+
+struct WffWs { float *eo, *state, *mel_up, *x, *pre, *acts; size_t bytes; };
+void wff_carve(const cwg_wf_config* c, long long BT, void* base, WffWs* ws) {
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n * sizeof(float), 1024); return (float*)((char*)base + o); };
+  ws->eo = take((size_t)BT * CWG_EO_PAD); ws->state = take((size_t)BT * c->n_group); ws->mel_up = take((size_t)BT * c->n_mel);
+  ws->x = take((size_t)c->n_layers * c->kernel_h * BT * c->n_channels);
+  ws->pre = take((size_t)BT * 2 * c->n_channels); ws->acts = take((size_t)BT * c->n_channels);
+  ws->bytes = off;
+}
+
+}  // namespace
+
+int wff_check(const cwg_wf_config* c, int batch, int t_samples) {
+  CWG_REQUIRE(c != nullptr, "cfg is NULL");
+  CWG_REQUIRE(c->n_channels >= 2 && c->n_channels % 2 == 0 && c->kernel_h >= 1 && c->kernel_h <= 16 && c->kernel_w >= 1 &&
+              c->kernel_w % 2 == 1 && c->kernel_w <= 15, "fp32 WaveFlow path: n_channels even, 1 <= kernel_h <= 16, odd kernel_w <= 15");
+  CWG_REQUIRE(c->n_group >= 2 && c->n_group <= WFF_MAX_GROUP, "n_group must be in [2, %d]", WFF_MAX_GROUP);
+  CWG_REQUIRE(c->n_mel >= 1 && c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_mel / n_flows / n_layers");
+  CWG_REQUIRE(batch >= 1 && t_samples >= c->n_group && t_samples % c->n_group == 0, "t_samples must be a positive multiple of n_group");
+  return 0;
+}
+
+size_t wff_workspace_bytes(const cwg_wf_config* c, int batch, int t_samples) {
+  if (wff_check(c, batch, t_samples)) return 0;
+  WffWs ws;
+  wff_carve(c, (long long)batch * (t_samples / c->n_group), nullptr, &ws);
+  return ws.bytes + 1024;
+}
+
+int wff_launch_count(const cwg_wf_config* c) {
+  return 1 + c->n_flows * (c->n_group + (c->n_group - 1) * c->n_layers * 3);
+}
+
+int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* mel, int frames, int pad_frames,
+              const float* z, float sigma, float* audio, void* workspace, size_t workspace_bytes, int batch, int t_samples,
+              cudaStream_t s, void** ev_begin, void** ev_end, int n_events) {
+  if (int r = wff_check(cfg, batch, t_samples)) return r;
+  CWG_REQUIRE(w && w->w1_f32 && w->w2_f32 && w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b, "fp32 weight arrays missing");
+  const int h = cfg->n_group, F = cfg->n_flows, L = cfg->n_layers, C = cfg->n_channels, KH = cfg->kernel_h, KW = cfg->kernel_w, M = cfg->n_mel;
+  const int Tp = t_samples / h;
+  const long long BT = (long long)batch * Tp;
+  WffWs ws;
+  wff_carve(cfg, BT, workspace, &ws);
+  CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+  const int K1 = KH * KW * C + M, N2 = C + CWG_EO_PAD;
+  {
+    const long long n = BT * M;
+    k_wff_mel_up<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mel, ws.mel_up, batch, M, frames, frames + pad_frames, Tp, cfg->upsample_linear);
+    CWG_CHECK_CUDA(cudaGetLastError());
+  }
+  int phys[WFF_MAX_GROUP], perm[WFF_MAX_GROUP], nxt[WFF_MAX_GROUP];
+  for (int c = 0; c < h; ++c) phys[c] = c;
+  const size_t slot = (size_t)BT * C;                              // one ring row of one layer
+  int ev = 0;
+  for (int k = F - 1; k >= 0; --k) {
+    wff_perm(k, h, perm);
+    const bool first_flow = k == F - 1, last_flow = k == 0;
+    for (int i = -1; i < h - 1; ++i) {
+      if (i >= 0) {
+        for (int l = 0; l < L; ++l, ++ev) {
+          if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)ev_begin[ev], s));
+          const size_t idx = (size_t)k * L + l;
+          WffGemmP p{};
+          p.BT = BT; p.Tp = Tp; p.C = C; p.KH = KH; p.KW = KW; p.M = M;
+          p.N = 2 * C; p.K = K1; p.W = w->w1_f32 + idx * 2 * C * K1; p.bias = w->b1 + idx * 2 * C;
+          p.ring = ws.x + (size_t)l * KH * slot; p.mel = ws.mel_up; p.row = i; p.dil = 1 << l; p.pre = ws.pre;
+          dim3 g1((unsigned)((BT + GM - 1) / GM), (unsigned)((2 * C + GN - 1) / GN));
+          k_wff_gemm<0><<<g1, 256, 0, s>>>(p);
+          const long long n = BT * C;
+          k_wff_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.pre, ws.acts, n, C);
+          WffGemmP q{};
+          q.BT = BT; q.Tp = Tp; q.C = C; q.N = N2; q.K = C; q.W = w->w2_f32 + idx * N2 * C; q.bias = w->b2 + idx * C;
+          q.acts = ws.acts; q.x_cur = ws.x + ((size_t)l * KH + (i % KH)) * slot;
+          q.x_next = l < L - 1 ? ws.x + ((size_t)(l + 1) * KH + (i % KH)) * slot : nullptr;
+          q.eo = ws.eo; q.eo_b = w->eo_b + (size_t)k * CWG_EO_PAD; q.first = l == 0;
+          dim3 g2((unsigned)((BT + GM - 1) / GM), (unsigned)((C + 2 + GN - 1) / GN));     // res rows + the 2 folded-end rows
+          q.N = C + 2;
+          k_wff_gemm<1><<<g2, 256, 0, s>>>(q);
+          CWG_CHECK_CUDA(cudaGetLastError());
+          if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)ev_end[ev], s));
+        }
+      }
+      const int j = i + 1;                                         // logical row produced now
+      float* x0 = j < h - 1 ? ws.x + (size_t)(j % KH) * slot : nullptr;        // ring of layer 0
+      k_wff_row<<<(unsigned)BT, 128, 0, s>>>(BT, h, C, first_flow ? z : ws.state, first_flow ? sigma : 1.f, phys[j],
+                                            last_flow ? audio : ws.state, last_flow ? perm[j] : phys[j], ws.eo, i >= 0,
+                                            w->start_w + (size_t)k * C, w->start_b + (size_t)k * C, x0);
+      CWG_CHECK_CUDA(cudaGetLastError());
+    }
+    for (int c = 0; c < h; ++c) nxt[c] = phys[perm[c]];
+    for (int c = 0; c < h; ++c) phys[c] = nxt[c];
+  }
+  return 0;
+}
+
+}  // namespace cwg

@@ -37,10 +37,11 @@ class WaveFlowPackConfig:
     kernel_w: int = 3
     hop_length: int = 256
     upsample_linear: bool = True
+    fp32: bool = False           # CWG_MODE_FFMA layout: fp32 planes, cond columns not padded
 
     @property
     def k1(self) -> int:
-        return self.kernel_h * self.kernel_w * self.n_channels + COND_PAD
+        return self.kernel_h * self.kernel_w * self.n_channels + (self.n_mel if self.fp32 else COND_PAD)
 
 
 def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dict[str, np.ndarray]:
@@ -79,8 +80,11 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
     out = {"b1": b1.astype(np.float32), "b2": b2.astype(np.float32), "eo_b": eo_b.astype(np.float32),
            "start_w": start_w.astype(np.float32), "start_b": start_b.astype(np.float32),
            "w1_f64": w1, "w2_f64": w2}
-    out["w1_hi"], out["w1_lo"] = split_hi_lo(w1)
-    out["w2_hi"], out["w2_lo"] = split_hi_lo(w2)
+    if cfg.fp32:
+        out["w1_f32"], out["w2_f32"] = w1.astype(np.float32), w2.astype(np.float32)
+    else:
+        out["w1_hi"], out["w1_lo"] = split_hi_lo(w1)
+        out["w2_hi"], out["w2_lo"] = split_hi_lo(w2)
     return out
 
 
@@ -89,7 +93,7 @@ class CwgWfConfig(C.Structure):
                                           "kernel_h", "kernel_w", "hop_length", "upsample_linear")]
 
 
-WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b")
+WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "w1_f32", "w2_f32")
 
 
 class CwgWfWeights(C.Structure):
@@ -164,20 +168,20 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         super().__init__()
         wn = dict(WN_config)
         a = dict(locals())
-        self._check_supported(a, wn)
+        self._check_supported(a, wn, precision)
         self.graphs, self._graphs = graphs, {}       # CUDA-graph replay: "auto" = calls of <= GRAPH_MAX_FRAMES mel frames in total
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
         self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
         self.precision = precision
         cond_channels = self._fe_build(a, wn)                # model-level front-end (ax_frontend.py)
-        if cond_channels > COND_PAD:
+        if cond_channels > COND_PAD and precision != "ffma":
             raise NotImplementedError(f"cookietts_b200.WaveFlow: the kernels take <= {COND_PAD} cond channels "
                                       f"(this model feeds {cond_channels})")
         self.pack_config = WaveFlowPackConfig(
             n_mel=cond_channels, n_flows=n_flows, n_group=n_group, n_layers=wn["n_layers"],
             n_channels=wn["n_channels"], kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
-            hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear")
+            hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear", fp32=precision == "ffma")
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
                                            cond_in_channels=self.wn_cond_in_channels,
@@ -187,7 +191,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self._workspace = None
 
     @staticmethod
-    def _check_supported(a, wn):
+    def _check_supported(a, wn, precision="bf16x3"):
         def need(cond, msg):
             if not cond:
                 raise NotImplementedError("cookietts_b200.WaveFlow: " + msg)
@@ -203,9 +207,16 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         need(not wn.get("merge_res_skip") and wn.get("res_skip", True), "merged / absent res_skip variants are not supported")
         need(wn.get("gated_unit", "GTU") == "GTU", "only the GTU gate is supported")
         need(wn.get("n_layers_dilations_w") is None and wn.get("n_layers_dilations_h", 1) == 1, "custom dilations are not supported")
-        need(wn["n_channels"] == 128 and wn["kernel_size_h"] == 3 and wn["kernel_size_w"] == 3, "kernels are built for n_channels=128, kernel 3x3")
+        need(precision in ("bf16x3", "bf16", "ffma"), "precision must be 'bf16x3', 'bf16' or 'ffma'")
+        if precision == "ffma":      # fp32 CUDA-core path (csrc/cwg_wf_ffma.cu): general WN_2d shapes
+            need(wn["n_channels"] % 2 == 0 and 1 <= wn["kernel_size_h"] <= 16 and wn["kernel_size_w"] % 2 == 1 and wn["kernel_size_w"] <= 15,
+                 "precision='ffma' takes even n_channels, kernel_size_h <= 16 and odd kernel_size_w <= 15")
+            need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 32, "hop_length % n_group == 0 and n_group <= 32")
+        else:
+            need(wn["n_channels"] == 128 and wn["kernel_size_h"] == 3 and wn["kernel_size_w"] == 3,
+                 "the tensor-core kernels are built for n_channels=128, kernel 3x3 (precision='ffma' runs other shapes)")
+            need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 16, "hop_length % n_group == 0 and n_group <= 16 (32 with precision='ffma')")
         need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
-        need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 16, "hop_length % n_group == 0 and n_group <= 16")
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._packed = None
@@ -237,13 +248,15 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         pk = pack_waveflow_state_dict(sd, self.pack_config, cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
         for name in WF_WEIGHT_FIELDS:
+            if name not in pk:
+                continue
             arr = pk[name]
             if arr.dtype == np.uint16:
                 arr = arr.view(np.int16)
             dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
         w = CwgWfWeights()
         for f in WF_WEIGHT_FIELDS:
-            setattr(w, f, dev_pk[f].data_ptr())
+            setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
         pc = self.pack_config
         self._ccfg = CwgWfConfig(pc.n_mel, pc.n_flows, pc.n_group, pc.n_layers, pc.n_channels, pc.kernel_h, pc.kernel_w,
                                  pc.hop_length, int(pc.upsample_linear))

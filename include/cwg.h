@@ -251,6 +251,10 @@ typedef struct cwg_wf_weights {
   const float*    eo_b;    /* [F][CWG_EO_PAD]                                                */
   const float*    start_w; /* [F][C]   Conv2d(1, C, 1x1)                                     */
   const float*    start_b; /* [F][C]                                                         */
+  /* CWG_MODE_FFMA (fp32 CUDA cores; any even C, any kernel_h x odd kernel_w, n_group <= 32, any n_mel): the same two
+   * matrices in fp32 with K1 = kernel_h*kernel_w*C + n_mel (the cond columns are not padded); hi / lo may then be NULL */
+  const float*    w1_f32;
+  const float*    w2_f32;
 } cwg_wf_weights;
 
 size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples);
@@ -258,7 +262,8 @@ size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int
 /* WaveGlow.inverse of the ax model (explicit latent): mel [batch][n_mel][frames] fp32, zero-extended
  * to frames + pad_frames (infer's artifact_trimming pad, efficient_model_ax.py:370-371) and
  * interpolated to T' = t_samples / n_group steps; z [batch][t_samples] standard normal (scaled by
- * sigma inside); audio [batch][t_samples] out.  mode: CWG_MODE_BF16X3 or CWG_MODE_BF16. */
+ * sigma inside); audio [batch][t_samples] out.  mode: CWG_MODE_BF16X3 or CWG_MODE_BF16 (tcgen05 kernels: C = 128, 3x3,
+ * n_group <= 16, n_mel <= 128), or CWG_MODE_FFMA (exact fp32 on the CUDA cores, general shapes; csrc/cwg_wf_ffma.cu). */
 int cwg_wf_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, int mode,
                  const float* mel, int frames, int pad_frames, const float* z, float sigma,
                  float* audio, void* workspace, size_t workspace_bytes,

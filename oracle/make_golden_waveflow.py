@@ -56,6 +56,15 @@ CASES = {
     "waveflow_small": (dict(n_mel_channels=80, n_flows=8, n_group=16, n_layers=4, n_channels=32), 1, 3, 0.666, 23, 3),
     # BASELINE config 5 model (8 flows, h=16, 8 x 128, 3x3) on a short clip
     "waveflow_config5": (dict(), 1, 12, 0.666, 1234, 0),
+    # shapes only the fp32 CUDA-core path runs (precision="ffma"): the layout of the author's trained WaveFlow checkpoints -
+    # squeeze height 20, depthwise-separable 7x7 in_layers (SURVEY 8d config-5 note) - at a small width, and a dense 5x3 kernel
+    "waveflow_sep7": (dict(n_mel_channels=10, n_flows=4, n_group=20, n_layers=3, n_channels=16, kernel_size_h=7,
+                           kernel_size_w=7, seperable_conv=True, win_length=160, hop_length=40), 2, 6, 0.9, 24, 4),
+    "waveflow_5x3": (dict(n_mel_channels=12, n_flows=2, n_group=8, n_layers=2, n_channels=64, kernel_size_h=5,
+                          kernel_size_w=3, win_length=64, hop_length=16), 1, 9, 1.0, 25, 5),
+    # the trained-checkpoint layout at full width (128 channels, h = 20, 8 flows, 8 layers, separable 7x7), short clip
+    "waveflow_sep7_128": (dict(n_group=20, kernel_size_h=7, kernel_size_w=7, seperable_conv=True, win_length=1200,
+                               hop_length=300), 1, 4, 0.666, 26, 6),
 }
 
 
@@ -159,8 +168,12 @@ def main():
         return main_big()
     WaveGlowAx = load_reference_ax()
     outdir = os.path.join(ROOT, "tests", "golden")
-    main_ax(WaveGlowAx, outdir)
+    only = set(sys.argv[1:])                         # optional: names of the cases to (re)generate
+    if not only:
+        main_ax(WaveGlowAx, outdir)
     for name, (kw, batch, frames, sigma, wseed, iseed) in CASES.items():
+        if only and name not in only:
+            continue
         cfg = WaveFlowConfig(**kw)
         sd = synthetic_state_dict(cfg, wseed)
         rs = np.random.RandomState(iseed)

@@ -46,6 +46,44 @@ def test_config5_model_matches_reference(precision):
     assert snr_db(ref2, aud.numpy()) >= TOL[precision]["snr"]
 
 
+@pytest.mark.parametrize("name", ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config5",
+                                  "waveflow_5x3", "waveflow_sep7", "waveflow_sep7_128"])
+def test_fp32_cuda_core_mode_matches_reference(name):
+    """precision="ffma" (csrc/cwg_wf_ffma.cu): exact fp32 on the CUDA cores for any WN_2d shape - incl. the layout of the
+    reference author's trained WaveFlow checkpoints (squeeze height 20, depthwise-separable 7x7 in_layers, 128 channels),
+    which the 3x3 / 128-channel tensor-core kernels do not take - against the unmodified reference's fp64 waveform."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+    sd = synthetic_state_dict(cfg, int(g["weight_seed"]))
+    m = build(cfg, sd, "ffma")
+    sigma = float(g["sigma"])
+    z, mel = torch.from_numpy(g["z"]).cuda(), torch.from_numpy(g["mel"]).cuda()
+    out, _ = m.inverse(z * sigma, mel, return_CPU=True)
+    ref = g["inverse_ref_fp64"]
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert max_abs(out.numpy(), ref) <= 1e-4 and snr_db(ref, out.numpy()) >= 100.0
+    assert max_abs(out.numpy(), g["inverse_ref_fp32"]) <= 1e-4
+    aud = m.infer(mel, sigma=sigma, z=z)
+    assert aud.shape == g["infer_ref_fp64"].shape
+    assert max_abs(aud.numpy(), g["infer_ref_fp64"]) <= 1e-4
+
+
+def test_tensor_core_modes_against_fp32_mode_on_device():
+    """The on-device exact-fp32 cross-check of the tensor-core WaveFlow kernels at a shape the CPU oracle is too slow for
+    (config-5 model, 4 x 200 frames)."""
+    cfg = WaveFlowConfig()
+    sd = synthetic_state_dict(cfg, 1234)
+    g = torch.Generator().manual_seed(3)
+    mel = (torch.randn(4, 80, 200, generator=g) * 2 - 5).clamp_(-11.5129, 2.0).cuda()
+    z = (torch.randn(4, 200 * 256, generator=g) * 0.666).cuda()
+    ref, _ = build(cfg, sd, "ffma").inverse(z, mel, return_CPU=False)
+    for precision in ("bf16x3", "bf16"):
+        out, _ = build(cfg, sd, precision).inverse(z, mel, return_CPU=False)
+        assert float((out - ref).abs().max()) <= TOL[precision]["max_abs"], precision
+        err = (out - ref).double()
+        assert float(10 * torch.log10(ref.double().pow(2).sum() / err.pow(2).sum())) >= TOL[precision]["snr"], precision
+
+
 def test_ragged_batch_against_oracle():
     """Batch 2, T' = 5*256/16 = 80 (one ragged tile), nearest-neighbour upsampling."""
     cfg = WaveFlowConfig(upsample_mode="nearest")
@@ -68,7 +106,8 @@ def test_unsupported_options_raise():
         WaveFlow(**bad)
     bad = dict(kw, WN_config=dict(kw["WN_config"], n_channels=64))
     with pytest.raises(NotImplementedError):
-        WaveFlow(**bad)
+        WaveFlow(**bad)                                     # tensor-core kernels: 128 channels only ...
+    assert WaveFlow(precision="ffma", **bad) is not None    # ... the fp32 CUDA-core mode takes the rest
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])

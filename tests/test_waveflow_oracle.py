@@ -10,7 +10,9 @@ from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict, inverse
 from oracle.waveglow_oracle import snr_db
 from tests.helpers import GOLDEN_DIR, max_abs
 
-CASES = ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config5"]
+CASES = ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config5",
+         # general WN_2d shapes: dense 5x3, depthwise-separable 7x7 at squeeze height 20 (16 and 128 channels)
+         "waveflow_5x3", "waveflow_sep7", "waveflow_sep7_128"]
 
 
 def load(name):
