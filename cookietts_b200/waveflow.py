@@ -169,6 +169,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         wn = dict(WN_config)
         a = dict(locals())
         self._check_supported(a, wn, precision)
+        self._graph_seen = set()
         self.graphs, self._graphs = graphs, {}       # CUDA-graph replay: "auto" = calls of <= GRAPH_MAX_FRAMES mel frames in total
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
         self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
@@ -306,6 +307,12 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                                                       B, T, torch.cuda.current_stream(dev).cuda_stream, arr_b, arr_e, n_ev))
             use_graph = (layer_events is None and not torch.cuda.is_current_stream_capturing() and
                          (self.graphs is True or (self.graphs == "auto" and B * frames <= self.GRAPH_MAX_FRAMES)))
+            if use_graph and self.graphs == "auto" and (B, frames, T, mode) not in self._graphs:
+                if (B, frames, T, mode) not in self._graph_seen:       # capture a shape the second time it is seen
+                    if len(self._graph_seen) > 64:
+                        self._graph_seen.clear()
+                    self._graph_seen.add((B, frames, T, mode))
+                    use_graph = False
             if use_graph:
                 # the row-by-row inverse is > 1000 small launches per call: repeated shapes replay a captured CUDA graph
                 key = (B, frames, T, mode)

@@ -109,6 +109,7 @@ class WaveGlow(nn.Module):
         # most GRAPH_MAX_FRAMES mel frames in total, True = always, False = never
         self.graphs = graphs
         self._graphs = {}
+        self._graph_seen = set()
         self.upsample = nn.ConvTranspose1d(n_mel_channels, n_mel_channels, win_length, stride=hop_length)
         self.WN = nn.ModuleList()
         self.convinv = nn.ModuleList()
@@ -309,6 +310,15 @@ class WaveGlow(nn.Module):
                 ev_b, ev_e = [int(e.cuda_event) for e in begin], [int(e.cuda_event) for e in end]
             use_graph = (layer_events is None and not torch.cuda.is_current_stream_capturing() and
                          (self.graphs is True or (self.graphs == "auto" and batch * t_mel <= self.GRAPH_MAX_FRAMES)))
+            if use_graph and self.graphs == "auto":
+                # "auto" captures a shape the second time it is seen: a stream of ever-new lengths (a TTS server) would pay
+                # a warm-up run and a capture per call for nothing
+                gkey = (tuple(mel.shape), float(sigma), mode, speaker_id is not None)
+                if gkey not in self._graphs and gkey not in self._graph_seen:
+                    if len(self._graph_seen) > 64:
+                        self._graph_seen.clear()
+                    self._graph_seen.add(gkey)
+                    use_graph = False
             if use_graph:
                 audio, status = self._graph_infer(ops, mode, mel, speaker_id, z, float(sigma))
             else:

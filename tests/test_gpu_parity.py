@@ -269,3 +269,20 @@ def test_f16f8_range_guard_falls_back_to_bf16x3():
     melb, zb = synthetic_inputs(OracleConfig(), 2, 40, 3)
     m.infer(torch.from_numpy(melb).cuda(), sigma=0.666, z=torch.from_numpy(zb).cuda())
     assert m.last_status == 0 and m.fallbacks == 0
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_module_graph_replay_of_repeated_shapes(precision):
+    """graphs="auto": the first call of a shape runs eagerly, the second captures a CUDA graph, later calls replay it on new
+    inputs (static buffers) - every result equals the eager module's, and a different sigma / shape gets its own graph."""
+    m_g, m_e = _model(precision), _model(precision)
+    m_e.graphs = False
+    for i in range(4):
+        mel, z = _inputs(2, 24, seed=20 + i)
+        a, b = m_g.infer(mel, sigma=0.7, z=z), m_e.infer(mel, sigma=0.7, z=z)
+        assert torch.equal(a, b), i
+        assert len(m_g._graphs) == (0 if i == 0 else 1)
+    mel, z = _inputs(2, 24, seed=30)
+    for _ in range(2):
+        assert torch.equal(m_g.infer(mel, sigma=0.9, z=z), m_e.infer(mel, sigma=0.9, z=z))
+    assert len(m_g._graphs) == 2 and not m_e._graphs
