@@ -67,7 +67,7 @@ struct CondCfg {
 };
 
 template <int NPASS>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
           const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
@@ -127,7 +127,9 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     }
     umma_commit(acc_full);
   } else if (warp >= 2) {
-    const int quarter = warp & 3, row = quarter * 32 + lane;
+    // 8 epilogue warps: TMEM lane quarter = warp % 4 (one row per lane), column group cg = (warp - 2) / 4 takes 4 of the 8
+    // 16-column chunks of each 128-column half
+    const int quarter = warp & 3, cg = (warp - 2) >> 2, row = quarter * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     int m = m0 + row;
     int b = min(m / a.Tm, a.B - 1);
@@ -138,7 +140,7 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
-      for (int c = 8 * half; c < 8 * half + 8; ++c) {
+      for (int c = 8 * half + 4 * cg; c < 8 * half + 4 * cg + 4; ++c) {
         float v[16];
         tmem_ld16_sync(trow + c * 16, v);
 #pragma unroll
@@ -158,7 +160,7 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) {
         for (int j = 0; j < 2; ++j) {
           tma_store_2d(&tm_c_hi, smem + j * TILE_A, p * 256 + (2 * half + j) * 64, m0);
@@ -171,7 +173,7 @@ k_cond_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         tma_store_commit();
         tma_store_wait_read();                 // the second half reuses the staging tiles
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (warp == 2 && lane == 0) tma_store_wait_all();
   }
@@ -938,13 +940,13 @@ int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, con
   }
   if (npass == 3) {
     if (int r = set_smem(k_cond_tc<3>, CondCfg<3>::SMEM)) return r;
-    k_cond_tc<3><<<grid, 192, CondCfg<3>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
+    k_cond_tc<3><<<grid, 320, CondCfg<3>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
   } else if (npass == 2) {
     if (int r = set_smem(k_cond_tc<2>, CondCfg<2>::SMEM)) return r;
-    k_cond_tc<2><<<grid, 192, CondCfg<2>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
+    k_cond_tc<2><<<grid, 320, CondCfg<2>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
   } else {
     if (int r = set_smem(k_cond_tc<1>, CondCfg<1>::SMEM)) return r;
-    k_cond_tc<1><<<grid, 192, CondCfg<1>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
+    k_cond_tc<1><<<grid, 320, CondCfg<1>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_hi, tc_lo, tc_h8, a);
   }
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
