@@ -606,13 +606,47 @@ def run_waveglow(args):
         gather(audio)
         return audio
 
+    # end-to-end step through host buffers: every step copies ITS inputs from pinned host memory and ITS waveform back,
+    # inside the timed region.  The copies run on a second stream so that the upload of step i+1 and the download of step
+    # i-1 overlap the kernels of step i (double-buffered device inputs; events order buffer re-use).
+    copy_stream = torch.cuda.Stream(dev)
+    in_d = [(torch.empty_like(mel_d), torch.empty_like(z_d)) for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]        # upload into slot finished
+    in_free = [torch.cuda.Event() for _ in range(2)]         # infer that read the slot finished
+    out_done = torch.cuda.Event()
+    e2e_state = {"i": 0, "primed": False}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(in_free[slot])
+            in_d[slot][0].copy_(mel_h, non_blocking=True)
+            in_d[slot][1].copy_(z_h, non_blocking=True)
+            in_ready[slot].record(copy_stream)
+
     def step_e2e():
-        m = mel_h.to(dev, non_blocking=True)
-        zz = z_h.to(dev, non_blocking=True)
-        audio = model.infer(m, sigma=0.666, z=zz)
+        i = e2e_state["i"]
+        slot = i & 1
+        if not e2e_state["primed"]:
+            upload(slot)
+            e2e_state["primed"] = True
+        upload(slot ^ 1)                                     # next step's inputs travel while this step computes
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(in_ready[slot])
+        audio = model.infer(in_d[slot][0], sigma=0.666, z=in_d[slot][1])
+        in_free[slot].record(main)
         gather(audio)
-        out_h.copy_(audio, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(copy_stream):                 # this step's waveform goes back while the next step computes
+            copy_stream.wait_event(done)
+            out_h.copy_(audio, non_blocking=True)
+            audio.record_stream(copy_stream)
+            out_done.record(copy_stream)
+        e2e_state["i"] = i + 1
         return audio
+
+    def drain_e2e():
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)     # the last download is inside the timed region
 
     def max_over_ranks(ms):
         if world == 1:
@@ -649,14 +683,17 @@ def run_waveglow(args):
     layer_ms = np.array([[ev_b[i][j].elapsed_time(ev_e[i][j]) for j in range(n_layers_total)] for i in range(args.steps)])
 
     # ---- timed region 2: end to end through host buffers ----------------------------------
+    for e in in_free:
+        e.record()
     for _ in range(2):
         step_e2e()
-    drain()
+    drain(); drain_e2e()
     barrier()
+    e2e_state["primed"] = False          # the first timed step uploads its own inputs inside the timed region
     t0.record()
     for _ in range(args.steps):
         step_e2e()
-    drain()
+    drain(); drain_e2e()
     t1.record()
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
@@ -749,7 +786,9 @@ def run_waveglow(args):
         "accuracy": accuracy,
         "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(mel_h.numel() * 4 + z_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
-                "xrt": e2e / SR},
+                "xrt": e2e / SR,
+                "copies": "every step uploads its mel + z from pinned host memory and downloads its waveform inside the timed "
+                          "region, on a second stream: the upload of step i+1 and the download of step i-1 overlap step i"},
         "gpu_launches": launches,
         "roofline": roofline,
         "output_finite": finite,
