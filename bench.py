@@ -454,8 +454,9 @@ def main():
     ap.add_argument("--channels", type=int, default=256, help="WN channels (512 = BASELINE config 4 model)")
     ap.add_argument("--workload", default="waveglow", choices=["waveglow", "waveflow"],
                     help="waveglow = BASELINE config 2 (default, the driver's line); waveflow = config 5 (B=64 x 10 s)")
-    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
-                    help="BASELINE.json config preset (1-based); 0 = use the individual flags (default = config 2)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5, 6],
+                    help="BASELINE.json config preset (1-based); 0 = use the individual flags (default = config 2); "
+                         "6 = the reference notebook's 48-flow ax WaveGlow, batch-1 latency (not a BASELINE.json config)")
     args = ap.parse_args()
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.precision is None:
@@ -472,6 +473,9 @@ def main():
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if args.config == 4:
         line = run_longform(args)
+    elif args.config == 6:
+        args.nb_precision = args.precision if any(a.startswith("--precision") for a in sys.argv[1:]) else "f16f8"
+        line = run_notebook_latency(args)
     elif args.workload == "waveflow":
         line = run_waveflow(args)
     else:
@@ -520,6 +524,54 @@ def run_config1_latency(args):
             "xrt": 86 * 256 / (ms * 1e-3) / SR, "output_finite": finite}
 
 
+def run_notebook_latency(args):
+    """The one configuration the reference itself records a speed for (scripts/WaveGlowFlow Inference Speed Testing.ipynb,
+    cells 2 and 4): its 48-flow / n_group-24 ax WaveGlow, batch 1, the 5.8375-s 48-kHz utterance (467 mel frames of hop
+    600), speaker id 0, sigma 1.0 - `waveglow.infer(mel, speaker_ids=..., sigma=...)` timed per call on the device.  The
+    notebook's own output: 1.27 s per call = 4.6x real time (fp16, the author's GPU); random-init weights of that
+    architecture here (module init, `end` ~ N(0, 0.02) instead of the all-zero training init)."""
+    import torch
+    from cookietts_b200 import WaveGlowAx
+    from cookietts_b200.synthetic import notebook_ax_kwargs
+    world, rank, local_rank, dev = dist_setup()
+    precision = getattr(args, "nb_precision", None) or "f16f8"
+    torch.manual_seed(1234)
+    model = WaveGlowAx(precision=precision, **notebook_ax_kwargs())
+    with torch.no_grad():
+        for c in model.WN:
+            c.WN.end.weight.normal_(0.0, 0.02); c.WN.end.bias.normal_(0.0, 0.02)
+    model = model.to(dev).eval()
+    frames, hop, sr = 467, 600, 48000
+    g = torch.Generator().manual_seed(1)
+    mel = (torch.randn(1, 160, frames, generator=g) * 2.0 - 5.0).clamp_(-11.5129, 2.0).to(dev)
+    ids = torch.zeros(1, dtype=torch.long, device=dev)
+    z = torch.randn(1, frames * hop, generator=g).to(dev)
+    for _ in range(3):
+        out = model.infer(mel, speaker_ids=ids, sigma=1.0, return_CPU=False, z=z)
+    torch.cuda.synchronize()
+    n = 10
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(n):
+        out = model.infer(mel, speaker_ids=ids, sigma=1.0, return_CPU=False, z=z)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / n
+    samples = int(out.shape[1])
+    finite = bool(torch.isfinite(out).all())
+    del model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": n, "ms_per_step": ms, "scaling": "replicas",
+            "dtype": precision,
+            "config": {"workload": "ax WaveGlow of the reference's speed-test notebook (48 flows, n_group 24, 8 x 256 WN with "
+                                   "96-dim speaker embeddings, upsample_first=False), 1 x 467 mel frames (5.84 s at 48 kHz) per "
+                                   "call, speaker id 0, sigma 1.0, injected z: per-call latency of infer()",
+                       "reference_recorded": "1.27 s per call = 4.6x real time at 48 kHz (notebook cell 4 output, fp16, the author's GPU)"},
+            "xrt": samples / (ms * 1e-3) / sr, "xrt_sample_rate": sr, "output_finite": finite}
+
+
 def with_extra_configs(args, line, rank):
     """Short (3-step) runs of BASELINE configs 3, 4 and 5 at this run's GPU count, attached to the headline line as
     `extra_configs` (still ONE JSON line), plus the headline workload in the 3-pass `bf16x3` mode.  A watchdog prints the headline without them if they overrun."""
@@ -539,7 +591,8 @@ def with_extra_configs(args, line, rank):
     for name, fn, kw in (("config1_latency", run_config1_latency, dict(config=1)),
                          ("config2_bf16x3", run_waveglow, dict(config=2, precision="bf16x3")),
                          ("config3", run_waveglow, dict(config=3)), ("config4", run_longform, dict(config=4)),
-                         ("config5", run_waveflow, dict(config=5, workload="waveflow"))):
+                         ("config5", run_waveflow, dict(config=5, workload="waveflow")),
+                         ("notebook_ax_latency", run_notebook_latency, dict(config=6))):
         a = copy.copy(args)
         a.steps, a.warmup, a.no_cpu_baseline, a.precision = 3, 3, True, "bf16"
         for k, v in kw.items():

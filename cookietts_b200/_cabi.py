@@ -13,9 +13,9 @@ LIB_PATH = os.environ.get("CWG_LIB") or os.path.join(_HERE, "libcwg.so")    # CW
 
 MODE_FFMA, MODE_BF16X3, MODE_BF16, MODE_F16F8 = 0, 1, 2, 3
 MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "f16f8": MODE_F16F8}
-EO_PAD = 16
-MAX_GROUP = 16
-ABI_VERSION = 3
+EO_PAD = 16          # narrow layout; see packing.group_pad / include/cwg.h CWG_GROUP_PAD
+MAX_GROUP = 32
+ABI_VERSION = 4
 
 
 class CwgConfig(C.Structure):
@@ -44,7 +44,7 @@ class CwgTensor(C.Structure):
 EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_launch_count",
            "cwg_state_dict_info", "cwg_packed_bytes", "cwg_pack_workspace_bytes", "cwg_pack_weights", "cwg_packed_view",
            "cwg_cond_bias", "cwg_nonfinite", "cwg_infer_status", "cwg_infer", "cwg_infer_profiled", "cwg_cond", "cwg_wn_layer", "cwg_flow_boundary",
-           "cwg_ax_workspace_bytes", "cwg_ax_infer",
+           "cwg_ax_workspace_bytes", "cwg_ax_infer", "cwg_ax_speaker_bias",
            "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_infer_profiled", "cwg_wf_launch_count", "cwg_wf_layer",
            "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise", "cwg_pcm16",
            "cwg_conv1d", "cwg_conv_transpose1d", "cwg_resample1d", "cwg_deemphasis",

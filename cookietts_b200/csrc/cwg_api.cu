@@ -58,6 +58,8 @@ int check_mode(const cwg_config* c, int mode, bool cond_gemm = true) {
               "unknown mode %d", mode);
   if (mode == CWG_MODE_F16F8)
     CWG_REQUIRE(c->n_channels == 256, "CWG_MODE_F16F8 is built for the 256-channel layer kernel");
+  if (mode != CWG_MODE_FFMA && c->n_group > 16)
+    CWG_REQUIRE(c->n_channels == 256, "n_group > 16 runs in CWG_MODE_FFMA or, for n_channels = 256, in the tensor-core modes");
   if (mode != CWG_MODE_FFMA) {
     CWG_REQUIRE((c->n_channels == 256 || c->n_channels == 512) && c->cond_hidden == 256 && c->kernel_size == 3,
                 "tensor-core modes are built for n_channels in {256, 512}, cond_hidden=256, kernel_size=3 "
@@ -72,7 +74,7 @@ void carve(const Dims& d, int mode, void* base, Workspace* ws) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return (char*)base + o; };
   memset(ws, 0, sizeof(*ws));
   ws->status = (int*)take(1024);
-  ws->eo = (float*)take((size_t)d.BT * CWG_EO_PAD * sizeof(float));
+  ws->eo = (float*)take((size_t)d.BT * d.MG * sizeof(float));
   if (mode == CWG_MODE_FFMA) {
     ws->x[0] = (float*)take((size_t)d.BT * d.C * 4);
     ws->x[1] = (float*)take((size_t)d.BT * d.C * 4);
@@ -111,7 +113,7 @@ int layer_tc256(const Dims& d, const cwg_weights* w, int npass, int k, int i, co
 
 // classic model, tensor-core modes: is layer 0 run from the (audio_0 | 1) planes instead of a materialised x_0 ?
 bool fold_active(const Dims& d, const cwg_weights* w) {
-  return d.C == 256 && d.L >= 2 && w->w0_hi && w->w0_lo && use_ps() && use_fold();
+  return d.C == 256 && d.L >= 2 && d.MG == 16 && w->w0_hi && w->w0_lo && use_ps() && use_fold();
 }
 
 int layer_tc(const cwg_config* cfg, const Dims& d, const cwg_weights* w, int npass, int k, int i, const Workspace& ws,
@@ -143,6 +145,24 @@ int check_run(const cwg_config* cfg, const cwg_weights* w, int mode, int batch, 
   return 0;
 }
 
+
+// b1_batch[b][fl][n] = b1[fl][n] + <spk_w[fl][n][:], spk_embed[f][id_b][:]>  (glow_ax.py:378-381 folded into the gate bias)
+__global__ void k_ax_speaker_bias(const float* __restrict__ b1, const float* __restrict__ spk_w,
+                                  const float* __restrict__ spk_embed, const int64_t* __restrict__ ids, int E, int S,
+                                  int L, int N, int FL, float* __restrict__ out) {
+  extern __shared__ float emb_s[];
+  const int fl = blockIdx.x, b = blockIdx.y, f = fl / L;
+  long long id = ids[b];
+  id = id < 0 ? 0 : (id >= S ? S - 1 : id);          // cwg_ax_speaker_bias rejects out-of-range ids on the host side
+  for (int e = threadIdx.x; e < E; e += blockDim.x) emb_s[e] = spk_embed[((size_t)f * S + id) * E + e];
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* wr = spk_w + ((size_t)fl * N + n) * E;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(__ldg(wr + e), emb_s[e], acc);
+    out[((size_t)b * FL + fl) * N + n] = b1[(size_t)fl * N + n] + acc;
+  }
+}
 }  // namespace
 }  // namespace cwg
 
@@ -361,7 +381,7 @@ size_t cwg_ax_workspace_bytes(const cwg_config* cfg, int mode, int batch, int fr
 int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
                  const float* mel, int frames, int pad_frames, int upsample_linear, int mix_first,
                  const float* z, float sigma, float* audio, void* workspace, size_t workspace_bytes,
-                 int batch, int t_samples, void* cuda_stream) {
+                 int batch, int t_samples, const float* b1_batch, void* cuda_stream) {
   if (int r = ax_check(cfg, mode, batch, frames, t_samples)) return r;
   CWG_REQUIRE(w && w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b && w->winv, "missing weight arrays");
   if (mode == CWG_MODE_FFMA) CWG_REQUIRE(w->w1_f32 && w->w2_f32, "fp32 weight planes missing");
@@ -370,11 +390,13 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   CWG_REQUIRE(mel && z && audio && pad_frames >= 0, "bad tensor arguments");
   CWG_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 1024) == 0, "workspace must be 1024-byte aligned");
   Dims d = ax_dims(cfg, batch, frames, t_samples);
+  d.b1_batch = b1_batch;             // per-utterance gate bias (WN-level speaker embedding, cwg_ax_speaker_bias) or NULL
   Workspace ws;
   carve(d, mode, workspace, &ws);
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool tc = mode != CWG_MODE_FFMA;
+  CWG_REQUIRE(!tc || use_ps() || (d.MG == 16 && !b1_batch), "n_group > 16 / per-utterance gate biases need the persistent layer kernel");
   const int npass = mode_npass(mode);
   const int xfmt = mode_xfmt(mode);
   const int F = cfg->n_flows, L = cfg->n_layers;
@@ -410,6 +432,19 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
   set_range_flag(nullptr);
   if (rc) return rc;
   if (mode == CWG_MODE_F16F8) return launch_nonfinite(audio, (size_t)batch * t_samples, ws.status, s, false);
+  return 0;
+}
+
+int cwg_ax_speaker_bias(const cwg_config* cfg, const float* b1, const float* spk_w, const float* spk_embed,
+                        int speaker_embed_dim, int n_speakers, const int64_t* speaker_ids, int batch,
+                        float* b1_batch, void* cuda_stream) {
+  if (int r = check_config(cfg)) return r;
+  CWG_REQUIRE(b1 && spk_w && spk_embed && speaker_ids && b1_batch, "cwg_ax_speaker_bias: NULL argument");
+  CWG_REQUIRE(speaker_embed_dim >= 1 && speaker_embed_dim <= 4096 && n_speakers >= 1 && batch >= 1, "cwg_ax_speaker_bias: bad sizes");
+  const int FL = cfg->n_flows * cfg->n_layers, N = 2 * cfg->n_channels;
+  k_ax_speaker_bias<<<dim3(FL, batch), 256, speaker_embed_dim * sizeof(float), (cudaStream_t)cuda_stream>>>(
+      b1, spk_w, spk_embed, speaker_ids, speaker_embed_dim, n_speakers, cfg->n_layers, N, FL, b1_batch);
+  CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -15,8 +15,10 @@ struct Dims {
   int B, Tm, Tp;        // batch, mel frames, group-steps T' = Tm * P
   int F, L, C, H;       // flows, WN layers, WN channels, cond hidden
   int G, M, P, J, ks;   // n_group, n_mel, phases hop/G, upsampler taps, WN kernel size
-  int K1, N2, KC, KCp;  // ks*C + H, C + CWG_EO_PAD, J*M, J*M padded to a multiple of 64 (cond_w row pitch)
+  int K1, N2, KC, KCp;  // ks*C + H, C + MG, J*M, J*M padded to a multiple of 64 (cond_w row pitch)
+  int MG;               // group padding CWG_GROUP_PAD(G): 16, or 32 for 16 < n_group <= 32 (include/cwg.h)
   long long BT;         // B * Tp
+  const float* b1_batch;   // per-utterance gate bias [B][F][L][2C] (ax WN-level speaker embedding) or NULL: w->b1
 };
 
 inline Dims make_dims(const cwg_config* c, int batch, int t_mel) {
@@ -26,7 +28,8 @@ inline Dims make_dims(const cwg_config* c, int batch, int t_mel) {
   d.G = c->n_group; d.M = c->n_mel; d.P = c->hop_length / c->n_group;
   d.J = (c->win_length + c->hop_length - 1) / c->hop_length; d.ks = c->kernel_size;
   d.Tp = t_mel * d.P;
-  d.K1 = d.ks * d.C + d.H; d.N2 = d.C + CWG_EO_PAD; d.KC = d.J * d.M; d.KCp = (d.KC + 63) / 64 * 64;
+  d.MG = CWG_GROUP_PAD(c->n_group); d.b1_batch = nullptr;
+  d.K1 = d.ks * d.C + d.H; d.N2 = d.C + d.MG; d.KC = d.J * d.M; d.KCp = (d.KC + 63) / 64 * 64;
   d.BT = (long long)batch * d.Tp;
   return d;
 }

@@ -169,9 +169,9 @@ __global__ void k_w0(const double* __restrict__ w_in, const double* __restrict__
 struct EoArgs { const float* b_rs[16]; const float* alpha[16]; };
 // eo_b[r] = b_end[r] + sum_i sum_c W_end[r][c] * alpha_i * b_skip_i[c]
 __global__ void k_eo_b(const double* __restrict__ w_end, const float* __restrict__ b_end, EoArgs a, int C, int L, int n2h,
-                       float* __restrict__ eo_b) {
+                       int mg, float* __restrict__ eo_b) {
   const int r = threadIdx.x;
-  if (r >= CWG_EO_PAD) return;
+  if (r >= mg) return;
   double s = 0.0;
   if (r < n2h) {
     s = (double)b_end[r];
@@ -184,16 +184,16 @@ __global__ void k_eo_b(const double* __restrict__ w_end, const float* __restrict
   eo_b[r] = (float)s;
 }
 
-__global__ void k_start(const double* __restrict__ w, const float* __restrict__ b, int C, int n_half, float* __restrict__ start_w,
+__global__ void k_start(const double* __restrict__ w, const float* __restrict__ b, int C, int n_half, int mg, float* __restrict__ start_w,
                         float* __restrict__ start_b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) start_w[(size_t)c * (CWG_MAX_GROUP / 2) + j] = j < n_half ? (float)w[(size_t)c * n_half + j] : 0.f;
+  for (int j = 0; j < mg / 2; ++j) start_w[(size_t)c * (mg / 2) + j] = j < n_half ? (float)w[(size_t)c * n_half + j] : 0.f;
   start_b[c] = b[c];
 }
 
-// W^-1 of the n x n mixing matrix (glow.py:93 inverts in fp32; fp64 here), zero-padded to [MAX_GROUP][MAX_GROUP]
-__global__ void k_winv(const float* __restrict__ W, int n, float* __restrict__ out, int* __restrict__ singular) {
+// W^-1 of the n x n mixing matrix (glow.py:93 inverts in fp32; fp64 here), zero-padded to [mg][mg] (mg = CWG_GROUP_PAD(n_group))
+__global__ void k_winv(const float* __restrict__ W, int n, int mg, float* __restrict__ out, int* __restrict__ singular) {
   __shared__ double a[CWG_MAX_GROUP][2 * CWG_MAX_GROUP];
   if (threadIdx.x != 0) return;
   for (int i = 0; i < n; ++i)
@@ -211,8 +211,8 @@ __global__ void k_winv(const float* __restrict__ W, int n, float* __restrict__ o
       if (f != 0.0) for (int j = 0; j < 2 * n; ++j) a[r][j] -= f * a[col][j];
     }
   }
-  for (int i = 0; i < CWG_MAX_GROUP; ++i)
-    for (int j = 0; j < CWG_MAX_GROUP; ++j) out[i * CWG_MAX_GROUP + j] = (i < n && j < n) ? (float)a[i][n + j] : 0.f;
+  for (int i = 0; i < mg; ++i)
+    for (int j = 0; j < mg; ++j) out[i * mg + j] = (i < n && j < n) ? (float)a[i][n + j] : 0.f;
 }
 
 // cond_bias[b][f][h] = cond_b_base[f][h] + sum_e cond_w_spk[f][h][e] * speaker_embed_f[ids[b]][e]   (glow.py:193-196)
@@ -259,8 +259,8 @@ Layout make_layout(const cwg_config* c, int mode, int E, int S) {
   const Dims d = make_dims(c, 1, 1);
   const size_t F = d.F, L = d.L, C = d.C, H = d.H;
   l.cond_w = F * d.P * H * d.KCp; l.w1 = F * L * 2 * C * d.K1; l.w2 = F * L * d.N2 * C;
-  l.b1 = F * L * 2 * C; l.b2 = F * L * C; l.eo_b = F * CWG_EO_PAD;
-  l.start_w = F * C * (CWG_MAX_GROUP / 2); l.start_b = F * C; l.winv = F * CWG_MAX_GROUP * CWG_MAX_GROUP;
+  l.b1 = F * L * 2 * C; l.b2 = F * L * C; l.eo_b = F * (size_t)d.MG;
+  l.start_w = F * C * (size_t)(d.MG / 2); l.start_b = F * C; l.winv = F * (size_t)d.MG * d.MG;
   l.cond_b_base = F * H; l.cond_w_spk = F * H * (size_t)(E > 0 ? E : 1); l.spk_embed = F * (size_t)S * E;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -334,7 +334,7 @@ int inspect(const cwg_tensor* sd, int n, int* E, int* S, int* rezero) {
 size_t pack_ws_bytes(const cwg_config* c, int E) {
   const Dims d = make_dims(c, 1, 1);
   const size_t C = d.C, H = d.H, L = d.L, n0 = (size_t)d.M * d.G + E;
-  size_t dbl = 2 * H * n0 + H * H + 2 * C * L * H + 2 * C * C * d.ks + 2 * C * C + (size_t)CWG_EO_PAD * C + C * (CWG_MAX_GROUP / 2);
+  size_t dbl = 2 * H * n0 + H * H + 2 * C * L * H + 2 * C * C * d.ks + 2 * C * C + (size_t)CWG_MAX_GROUP * C + C * (CWG_MAX_GROUP / 2);
   return dbl * 8 + 8 * 256 + 256;
 }
 
@@ -424,7 +424,7 @@ int cwg_pack_weights(const cwg_config* cfg, int mode, const cwg_tensor* sd, int 
   double* w21 = ws;           ws += (size_t)H * n0;
   double* w_in = ws;          ws += (size_t)2 * C * C * ks;
   double* w_rs = ws;          ws += (size_t)2 * C * C;
-  double* w_end = ws;         ws += (size_t)CWG_EO_PAD * C;
+  double* w_end = ws;         ws += (size_t)CWG_MAX_GROUP * C;
   double* w_start = ws;       ws += (size_t)C * (CWG_MAX_GROUP / 2);
   int* singular = (int*)ws;
   CWG_CHECK_CUDA(cudaMemsetAsync(singular, 0, sizeof(int), s));
@@ -467,11 +467,11 @@ int cwg_pack_weights(const cwg_config* cfg, int mode, const cwg_tensor* sd, int 
     snprintf(nm, sizeof(nm), "WN.%d.start", k); if (int r = effective(sd, n_tensors, nm, C, n_half, w_start, s)) return r;
     const float* b_start;
     snprintf(nm, sizeof(nm), "WN.%d.start.bias", k); if (int r = need(sd, n_tensors, nm, C, &b_start)) return r;
-    k_start<<<(C + 127) / 128, 128, 0, s>>>(w_start, b_start, C, n_half, (float*)w.start_w + (size_t)k * C * (CWG_MAX_GROUP / 2),
+    k_start<<<(C + 127) / 128, 128, 0, s>>>(w_start, b_start, C, n_half, d.MG, (float*)w.start_w + (size_t)k * C * (d.MG / 2),
                                            (float*)w.start_b + (size_t)k * C);
     const float* Wm;
     snprintf(nm, sizeof(nm), "convinv.%d.conv.weight", k); if (int r = need(sd, n_tensors, nm, (long long)n_rem * n_rem, &Wm)) return r;
-    k_winv<<<1, 32, 0, s>>>(Wm, n_rem, (float*)w.winv + (size_t)k * CWG_MAX_GROUP * CWG_MAX_GROUP, singular);
+    k_winv<<<1, 32, 0, s>>>(Wm, n_rem, d.MG, (float*)w.winv + (size_t)k * d.MG * d.MG, singular);
     // ---- layers
     EoArgs ea;
     memset(&ea, 0, sizeof(ea));
@@ -497,7 +497,7 @@ int cwg_pack_weights(const cwg_config* cfg, int mode, const cwg_tensor* sd, int 
       k_w2<<<dim3((C + 127) / 128, d.N2), 128, 0, s>>>(w_rs, w_end, ea.b_rs[i], ea.alpha[i], C, n2h, last ? 1 : 0, p_w2,
                                                      idx * d.N2 * C, (float*)w.b2 + idx * C);
     }
-    k_eo_b<<<1, 32, 0, s>>>(w_end, b_end, ea, C, L, n2h, (float*)w.eo_b + (size_t)k * CWG_EO_PAD);
+    k_eo_b<<<1, 32, 0, s>>>(w_end, b_end, ea, C, L, n2h, d.MG, (float*)w.eo_b + (size_t)k * d.MG);
     CWG_CHECK_CUDA(cudaGetLastError());
   }
   *out = w;

@@ -37,8 +37,10 @@ namespace {
 struct PsArgs {
   const float* b1;        // [2C]
   const float* b2;        // [C]
-  const float* eo_b;      // [16]
-  float* eo;              // [B*T'][16]
+  const float* eo_b;      // [MG]
+  float* eo;              // [B*T'][MG], MG = eo_pitch (16; 32 for the wide group layout, include/cwg.h CWG_GROUP_PAD)
+  int eo_pitch;           // wide (32): the follower's 16 folded-`end` rows are real and column group 1 accumulates them
+  long long b1_bstride;   // floats between the gate biases of consecutive utterances (ax WN speaker embedding); 0: shared
   uint8_t* xo_l8;         // f16f8: e5m2 planes of x_out, written with plain 16-byte stores
   uint8_t* xo_h8;
   int Tp, dil;
@@ -51,7 +53,7 @@ struct PsArgs {
   int fused0;
   const float* audio;     // [B*T'][G] fp32 audio state; audio_0 of row m = audio[m*G + a_off .. + a_nh)
   int G, a_off, a_nh;
-  const float* start_w;   // [C][CWG_MAX_GROUP/2]
+  const float* start_w;   // [C][8] (the fold takes the narrow layout, n_half <= 8, only)
   const float* start_b;   // [C]
   int w0_row0;
   int* range_flag;        // f16f8, last residual layer only: |= 2 when x_new leaves the fp16 range (else NULL)
@@ -142,7 +144,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     // epilogue -> MMA hand-offs: ONE elected arrive per warp after __syncwarp (512 per-thread arrives, half of them remote
     // DSMEM transactions, cost ~1.3-2.9 k cycles per hand-off in the per-tile timeline)
     mbar_init(acts_ready, 2 * (P_EPI_THREADS / 32)); mbar_init(acc2_full, 1);
-    mbar_init(&r_free[0], 2 * (P_EPI_THREADS / 64)); mbar_init(&r_free[1], 2 * (P_EPI_THREADS / 32));
+    mbar_init(&r_free[0], a.eo_pitch == 32 ? 2 * (P_EPI_THREADS / 32) : 2 * (P_EPI_THREADS / 64)); mbar_init(&r_free[1], 2 * (P_EPI_THREADS / 32));
     mbar_init(&xold_full[0], 1); mbar_init(&xold_full[1], 1);
     mbar_init(acts0_ready, 2 * (P_EPI_THREADS / 32));
     fence_barrier_init();
@@ -479,7 +481,7 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       b1s[e] = __ldg(a.b1 + e) * GateK<NPASS>::KA; b1s[256 + e] = __ldg(a.b1 + 256 + e) * GateK<NPASS>::KB;
       b2s[e] = __ldg(a.b2 + e);
       if (FUSED0) {          // start conv of this flow: S [256][8] (columns >= n_half are zero) and its bias
-        const float4* sw = reinterpret_cast<const float4*>(a.start_w + (size_t)e * (CWG_MAX_GROUP / 2));
+        const float4* sw = reinterpret_cast<const float4*>(a.start_w + (size_t)e * 8);
         reinterpret_cast<float4*>(s_tab)[2 * e] = __ldg(sw); reinterpret_cast<float4*>(s_tab)[2 * e + 1] = __ldg(sw + 1);
         s_bias[e] = __ldg(a.start_b + e);
       }
@@ -491,10 +493,19 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
     if (a.dbg && warp == 4 && lane == 0) t_start = clock64();
     int n_tiles = 0;
     uint32_t par = 0, xph = 0;
+    int b_cur = 0;
     for (int p = cluster_id; p < a.n_pairs; p += n_clusters, par ^= 1u, ++n_tiles) {
       int b, t0; tile_of(p, b, t0);
       const bool valid = t0 + row < a.Tp;
       const size_t m = (size_t)b * a.Tp + (size_t)min(t0 + row, a.Tp - 1);
+      if (a.b1_bstride != 0 && b != b_cur) {    // per-utterance gate bias (b is uniform over the CTA): reload on a change
+        b_cur = b;
+        asm volatile("bar.sync 1, %0;" ::"n"(P_EPI_THREADS) : "memory");     // every warp is past the previous tile's gates
+        const int e = threadIdx.x - 128;
+        const float* bb = a.b1 + (size_t)b * a.b1_bstride;
+        b1s[e] = __ldg(bb + e) * GateK<NPASS>::KA; b1s[256 + e] = __ldg(bb + 256 + e) * GateK<NPASS>::KB;
+        asm volatile("bar.sync 1, %0;" ::"n"(P_EPI_THREADS) : "memory");
+      }
       auto load_xold = [&](int blk) {          // ldr only: x_old (centre tap) tiles of a 64-channel block -> staging
         mbar_arrive_expect_tx(&xold_full[h], 2 * TILE_A);
         tma_load_3d(u_hi, &tm_x_hi, &xold_full[h], blk * 64, t0, b);
@@ -553,8 +564,9 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
 
       // prefetch this row's folded-`end` accumulator while GEMM2 runs
       float4 eold[4];
-      if (h == 0) {
-        const float4* e = reinterpret_cast<const float4*>(a.first ? a.eo_b : a.eo + m * CWG_EO_PAD);
+      const bool eo_mine = h == 0 || a.eo_pitch == 32;     // wide layout: column group 1 owns outputs [16, 32)
+      if (eo_mine) {
+        const float4* e = reinterpret_cast<const float4*>(a.first ? a.eo_b + 16 * h : a.eo + m * a.eo_pitch + 16 * h);
 #pragma unroll
         for (int q = 0; q < 4; ++q) eold[q] = __ldg(e + q);
       }
@@ -564,17 +576,17 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       tc_fence_after_sync();
       if (stamp) edbg[4] = clock64();
       uint32_t sk[16];
-      if (h == 0) {                                              // first of all: release R0 to the next tile's sweep 0
-        tmem_issue16(trow + P_D_EO, sk);
+      if (eo_mine) {                                             // first of all: release R0 to the next tile's sweep 0
+        tmem_issue16(trow + P_D_EO + 16 * h, sk);
         tmem_wait16(sk);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&r_free[0]); else mbar_arrive_cluster(r0_bar); }   // R0: acts consumed by GEMM2, `end` read
       }
       if (X3 && a.has_res && !FUSED0 && ldr) load_xold(2 * h);  // GEMM2 no longer reads units 8..11
-      if (h == 0) {
+      if (eo_mine) {
         if (valid) {
-          float4* e = reinterpret_cast<float4*>(a.eo + m * CWG_EO_PAD);
+          float4* e = reinterpret_cast<float4*>(a.eo + m * a.eo_pitch + 16 * h);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             e[q] = make_float4(eold[q].x + __uint_as_float(sk[4 * q]), eold[q].y + __uint_as_float(sk[4 * q + 1]),
@@ -584,11 +596,11 @@ k_layer_ps(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ 
       if (a.has_res) {
         uint32_t buf[2][16];
         const int c0 = 8 * h;
-        float av[CWG_MAX_GROUP / 2];                 // fused0: this row's coupling input audio_0 (fp32, exact)
+        float av[8];                                 // fused0: this row's coupling input audio_0 (fp32, exact)
         if (FUSED0) {
           const float* ar = a.audio + m * a.G + a.a_off;
 #pragma unroll
-          for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) av[j] = (valid && j < a.a_nh) ? __ldg(ar + j) : 0.f;
+          for (int j = 0; j < 8; ++j) av[j] = (valid && j < a.a_nh) ? __ldg(ar + j) : 0.f;
         }
         tmem_issue16(trow + P_D_RES + c0 * 16, buf[0]);
 #pragma unroll
@@ -809,14 +821,15 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
                     const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
                     float* eo, cudaStream_t s, const void* a0, const float* audio, int a_off, int a_nh) {
   // a0 != NULL (layer 0 only): the layer-0 fold - x_in is not read; see PsArgs::fused0
-  CWG_REQUIRE(a0 == nullptr || (layer == 0 && w->w0_hi && w->w0_lo && audio && d.L >= 2), "layer-0 fold: bad arguments");
+  CWG_REQUIRE(a0 == nullptr || (layer == 0 && w->w0_hi && w->w0_lo && audio && d.L >= 2 && d.MG == 16), "layer-0 fold: bad arguments");
   const PsMaps* m = nullptr;
   if (int r = get_maps(d, w, npass, x_in, x_out, h2, a0, &m)) return r;
   const size_t plane = (size_t)d.BT * d.C;
   const size_t idx = (size_t)flow * d.L + layer;
   PsArgs a{};
-  a.b1 = w->b1 + idx * 2 * d.C; a.b2 = w->b2 + idx * d.C; a.eo_b = w->eo_b + (size_t)flow * CWG_EO_PAD;
-  a.eo = eo;
+  a.b1 = w->b1 + idx * 2 * d.C; a.b2 = w->b2 + idx * d.C; a.eo_b = w->eo_b + (size_t)flow * d.MG;
+  if (d.b1_batch) { a.b1 = d.b1_batch + idx * 2 * d.C; a.b1_bstride = (long long)d.F * d.L * 2 * d.C; }
+  a.eo = eo; a.eo_pitch = d.MG;
   a.xo_l8 = reinterpret_cast<uint8_t*>(x_out) + 4 * plane; a.xo_h8 = a.xo_l8 + plane;
   a.Tp = d.Tp; a.dil = 1 << layer;
   a.w1_row0 = (int)(idx * 2 * d.C); a.w2_row0 = (int)(idx * d.N2);
@@ -826,7 +839,7 @@ int launch_layer_ps(const Dims& d, const cwg_weights* w, int npass, int flow, in
   a.n_pairs = a.pairs_per_utt * d.B;
   a.dbg = g_ps_dbg;
   a.fused0 = a0 != nullptr; a.audio = audio; a.G = d.G; a.a_off = a_off; a.a_nh = a_nh;
-  a.start_w = w->start_w + (size_t)flow * d.C * (CWG_MAX_GROUP / 2); a.start_b = w->start_b + (size_t)flow * d.C;
+  a.start_w = w->start_w + (size_t)flow * d.C * (d.MG / 2); a.start_b = w->start_b + (size_t)flow * d.C;
   a.w0_row0 = flow * 2 * d.C;
   a.range_flag = (npass == 2 && (layer == d.L - 2 || range_all_layers())) ? range_flag() : nullptr;
   int ncl = 0;

@@ -24,8 +24,8 @@ struct GemmP {
   int Tm, Tp, nmel, C, ks, dil, H;
   float* o0; float* o1;
   const float* bias; const float* bias2; const float* xin;
-  int bias_bstride;                 // cond: batch stride of the per-utterance bias
-  int has_res, first;
+  long long bias_bstride;           // cond / gate: batch stride of a per-utterance bias (0: shared)
+  int has_res, first, eo_pad;       // eo_pad: row pitch MG of the folded-`end` accumulator
 };
 
 // A(m, kk) for the three GEMMs.
@@ -57,14 +57,14 @@ __device__ __forceinline__ void store_c(const GemmP& p, int m, int n, float acc)
   if (EMODE == 0) {             // H2[m][n] (+ per-utterance cond bias of channel n % H)
     int b = m / p.Tm;
     p.o0[(size_t)m * p.N + n] = acc + __ldg(p.bias + (size_t)b * p.bias_bstride + (n % p.H));
-  } else if (EMODE == 1) {      // pre-activation
-    p.o0[(size_t)m * p.N + n] = acc + __ldg(p.bias + n);
+  } else if (EMODE == 1) {      // pre-activation (+ the per-utterance gate bias of the ax WN-level speaker embedding)
+    p.o0[(size_t)m * p.N + n] = acc + __ldg(p.bias + (size_t)(m / p.Tp) * p.bias_bstride + n);
   } else {                      // res / folded end
     if (n < p.C) {
       if (p.has_res) p.o0[(size_t)m * p.C + n] = __ldg(p.xin + (size_t)m * p.C + n) + acc + __ldg(p.bias + n);
     } else {
       int j = n - p.C;
-      float* e = p.o1 + (size_t)m * CWG_EO_PAD + j;
+      float* e = p.o1 + (size_t)m * p.eo_pad + j;
       *e = (p.first ? __ldg(p.bias2 + j) : *e) + acc;
     }
   }
@@ -131,9 +131,9 @@ struct BoundaryP {
   int n_rem2, n_half2;        // of flow_next
   const float* z; float sigma;
   float* audio; const float* eo;
-  const float* winv;          // [MAX_GROUP][MAX_GROUP] of the mixing flow
+  const float* winv;          // [MG][MG] of the mixing flow
   int* range_flag;            // CWG_MODE_F16F8: |= 2 when a start-conv output leaves the fp16 range (may be NULL)
-  const float* start_w;       // [C][MAX_GROUP/2] of flow_next
+  const float* start_w;       // [C][MG/2] of flow_next
   const float* start_b;       // [C]
   void* x_out;
   void* a0_out;               // layer-0 fold: planes hi, lo [BT][16] 16-bit of (audio_0 | 1 | 0...) instead of x (tensor-core modes)
@@ -142,20 +142,21 @@ struct BoundaryP {
 // One block handles TB consecutive group-steps (rows of the [B*T'][G] audio state, which IS
 // the [B, T] output buffer: latent channel c of step s lives at audio[b, s*G + c], so the
 // early-z concat (glow.py:342-347) and the final un-squeeze (:349) are no-ops by layout).
-template <int XFMT>
+// MG = CWG_GROUP_PAD(n_group): 16, or 32 for the wide layout (16 < n_group <= 32)
+template <int XFMT, int MG>
 __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
-  __shared__ float a_s[TB][CWG_MAX_GROUP];
+  __shared__ float a_s[TB][MG];
   const long long m0 = (long long)blockIdx.x * TB;
   const int tid = threadIdx.x;
   if (tid < TB) {
     long long m = m0 + tid;
     if (m < p.BT) {
-      float a[CWG_MAX_GROUP];
+      float a[MG];
       for (int g = 0; g < p.G; ++g)
         a[g] = p.init ? p.sigma * p.z[m * p.G + g] : p.audio[m * p.G + g];
       if (p.do_flow) {
         const int off = p.G - p.n_rem;
-        const float* e = p.eo + m * CWG_EO_PAD;
+        const float* e = p.eo + m * MG;
         for (int j = 0; j < p.n_rem - p.n_half; ++j) {
           // audio_1 = (audio_1 - b) / exp(s), glow.py:337
           float b = e[j], s = e[p.n_half + j];
@@ -166,11 +167,11 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
       }
       if (p.do_mix) {                                 // z = conv1d(z, W^-1), glow.py:98
         const int off = p.G - p.n_rem_mix;
-        float v[CWG_MAX_GROUP];
+        float v[MG];
         for (int c = 0; c < p.n_rem_mix; ++c) v[c] = a[off + c];
         for (int r = 0; r < p.n_rem_mix; ++r) {
           float acc = 0.f;
-          for (int c = 0; c < p.n_rem_mix; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
+          for (int c = 0; c < p.n_rem_mix; ++c) acc = fmaf(__ldg(p.winv + r * MG + c), v[c], acc);
           a[off + r] = acc;
         }
       }
@@ -188,10 +189,10 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
   const int npair = p.C >> 1, rpar = tid >> 7;
   for (int cp = tid & 127; cp < npair; cp += 128) {
     const int c = 2 * cp;
-    float w0[CWG_MAX_GROUP / 2], w1[CWG_MAX_GROUP / 2];
+    float w0[MG / 2], w1[MG / 2];
     for (int j = 0; j < p.n_half2; ++j) {
-      w0[j] = __ldg(p.start_w + c * (CWG_MAX_GROUP / 2) + j);
-      w1[j] = __ldg(p.start_w + (c + 1) * (CWG_MAX_GROUP / 2) + j);
+      w0[j] = __ldg(p.start_w + c * (MG / 2) + j);
+      w1[j] = __ldg(p.start_w + (c + 1) * (MG / 2) + j);
     }
     const float bias0 = __ldg(p.start_b + c), bias1 = __ldg(p.start_b + c + 1);
     for (int r = rpar; r < nrow; r += 2) {
@@ -220,15 +221,15 @@ __global__ void __launch_bounds__(256) k_flow_boundary(BoundaryP p) {
 // or 1-KB (fp32) run of the channels-last activation row; the lane's 8 x n_half weights stay in registers.
 constexpr int TBV = 256;
 
-template <int XFMT>
+template <int XFMT, int MG>
 __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
-  __shared__ __align__(16) float a_s[TBV][CWG_MAX_GROUP / 2];      // the n_half2 inputs of the next start conv
+  __shared__ __align__(16) float a_s[TBV][MG / 2];      // the n_half2 inputs of the next start conv
   const long long m0 = (long long)blockIdx.x * TBV;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const long long m = m0 + tid;
     if (m < p.BT) {
-      float a[CWG_MAX_GROUP];
+      float a[MG];
       const float* src = p.init ? p.z + m * p.G : p.audio + m * p.G;
       if ((p.G & 3) == 0) {
         for (int g = 0; g < p.G; g += 4) {
@@ -241,10 +242,10 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
       if (p.init) for (int g = 0; g < p.G; ++g) a[g] *= p.sigma;
       if (p.do_flow) {
         const int off = p.G - p.n_rem;
-        float e[CWG_EO_PAD];
-        const float4* ev = reinterpret_cast<const float4*>(p.eo + m * CWG_EO_PAD);
+        float e[MG];
+        const float4* ev = reinterpret_cast<const float4*>(p.eo + m * MG);
 #pragma unroll
-        for (int q = 0; q < CWG_EO_PAD / 4; ++q) { const float4 v = __ldcs(ev + q); e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w; }
+        for (int q = 0; q < MG / 4; ++q) { const float4 v = __ldcs(ev + q); e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w; }
         for (int j = 0; j < p.n_rem - p.n_half; ++j)                 // audio_1 = (audio_1 - b) / exp(s), glow.py:337
           a[off + p.n_half + j] = (a[off + p.n_half + j] - e[j]) * expf(-e[p.n_half + j]);
         if (p.ignore_nan)
@@ -252,11 +253,11 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
       }
       if (p.do_mix) {                                                // z = conv1d(z, W^-1), glow.py:98
         const int off = p.G - p.n_rem_mix;
-        float v[CWG_MAX_GROUP];
+        float v[MG];
         for (int c = 0; c < p.n_rem_mix; ++c) v[c] = a[off + c];
         for (int r = 0; r < p.n_rem_mix; ++r) {
           float acc = 0.f;
-          for (int c = 0; c < p.n_rem_mix; ++c) acc = fmaf(__ldg(p.winv + r * CWG_MAX_GROUP + c), v[c], acc);
+          for (int c = 0; c < p.n_rem_mix; ++c) acc = fmaf(__ldg(p.winv + r * MG + c), v[c], acc);
           a[off + r] = acc;
         }
       }
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
         const int off2 = p.G - p.n_rem2;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = j < p.n_half2 ? a[off2 + j < CWG_MAX_GROUP ? off2 + j : 0] : (j == p.n_half2 ? 1.f : 0.f);
+        for (int j = 0; j < 16; ++j) v[j] = j < p.n_half2 ? a[off2 + j < MG ? off2 + j : 0] : (j == p.n_half2 ? 1.f : 0.f);
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -286,21 +287,74 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
         ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       } else if (p.do_start) {
         const int off2 = p.G - p.n_rem2;
-        for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) a_s[tid][j] = j < p.n_half2 ? a[off2 + j] : 0.f;
+        for (int j = 0; j < MG / 2; ++j) a_s[tid][j] = j < p.n_half2 ? a[off2 + j] : 0.f;
       }
     }
   }
   if (!p.do_start || p.a0_out) return;
   __syncthreads();
   const int nrow = (int)min((long long)TBV, p.BT - m0);
+  if (MG != 16) {
+    // wide layout (n_half2 <= 16): lane -> 4 consecutive channels, so that the 4 x 16 weights still fit in registers
+    for (int cg = lane; cg < (p.C >> 2); cg += 32) {
+      const int c = cg * 4;
+      float w[4][MG / 2], bias[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bias[i] = __ldg(p.start_b + c + i);
+#pragma unroll
+        for (int j = 0; j < MG / 2; ++j) w[i][j] = j < p.n_half2 ? __ldg(p.start_w + (c + i) * (MG / 2) + j) : 0.f;
+      }
+      for (int r = warp; r < nrow; r += TBV / 32) {
+        float x[4] = {bias[0], bias[1], bias[2], bias[3]};
+#pragma unroll
+        for (int jq = 0; jq < MG / 8; ++jq) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&a_s[r][4 * jq]);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[i] = fmaf(w[i][4 * jq + j], av[j], x[i]);
+        }
+        const size_t idx = (size_t)(m0 + r) * p.C + c;
+        if (XFMT == 0) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.x_out) + idx) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+          constexpr bool F16 = XFMT == 2;
+          const size_t plane = (size_t)p.BT * p.C;
+          uint16_t* hi = reinterpret_cast<uint16_t*>(p.x_out);
+          if (F16 && p.range_flag) {
+            const float mx = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
+            if (!(mx < 65504.f)) atomicOr(p.range_flag, 2);
+          }
+          uint32_t h[2], l[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float h0, h1;
+            h[i] = sm100::pack2<F16>(x[2 * i], x[2 * i + 1]);
+            sm100::unpack2<F16>(h[i], h0, h1);
+            l[i] = sm100::pack2<F16>(x[2 * i] - h0, x[2 * i + 1] - h1);
+          }
+          *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h[0], h[1]);
+          *reinterpret_cast<uint2*>(hi + plane + idx) = make_uint2(l[0], l[1]);
+          if (F16) {                          // e5m2(lo * 2^P), e5m2(hi * 2^-Q) planes
+            uint8_t* p8 = reinterpret_cast<uint8_t*>(p.x_out) + 4 * plane;
+            *reinterpret_cast<uint32_t*>(p8 + idx) = sm100::e5m2x4_from_f16x2(l[0], l[1], sm100::F16X2_2P6);
+            *reinterpret_cast<uint32_t*>(p8 + plane + idx) = sm100::e5m2x4_from_f16x2(h[0], h[1], sm100::F16X2_2M8);
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int cg = lane; cg < (p.C >> 3); cg += 32) {                   // audio = start(audio_0), glow.py:189
     const int c = cg * 8;
-    float w[8][CWG_MAX_GROUP / 2], bias[8];
+    float w[8][MG / 2], bias[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       bias[i] = __ldg(p.start_b + c + i);
 #pragma unroll
-      for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) w[i][j] = j < p.n_half2 ? __ldg(p.start_w + (c + i) * (CWG_MAX_GROUP / 2) + j) : 0.f;
+      for (int j = 0; j < MG / 2; ++j) w[i][j] = j < p.n_half2 ? __ldg(p.start_w + (c + i) * (MG / 2) + j) : 0.f;
     }
     for (int r = warp; r < nrow; r += TBV / 32) {
       const float4 a0 = *reinterpret_cast<const float4*>(&a_s[r][0]), a1 = *reinterpret_cast<const float4*>(&a_s[r][4]);
@@ -310,7 +364,7 @@ __global__ void __launch_bounds__(TBV) k_flow_boundary_v(BoundaryP p) {
       for (int i = 0; i < 8; ++i) {
         float acc = bias[i];
 #pragma unroll
-        for (int j = 0; j < CWG_MAX_GROUP / 2; ++j) acc = fmaf(w[i][j], av[j], acc);
+        for (int j = 0; j < MG / 2; ++j) acc = fmaf(w[i][j], av[j], acc);
         x[i] = acc;
       }
       const size_t idx = (size_t)(m0 + r) * p.C + c;
@@ -428,7 +482,7 @@ int launch_cond_ffma(const Dims& d, const cwg_weights* w, int flow, const float*
   p.M = d.B * d.Tm; p.N = d.P * d.H; p.K = d.KC;
   p.W = w->cond_w_f32 + (size_t)flow * p.N * d.KCp; p.ldw = d.KCp;
   p.a0 = mel; p.Tm = d.Tm; p.nmel = d.M; p.H = d.H;
-  p.o0 = h2; p.bias = cond_bias + (size_t)flow * d.H; p.bias_bstride = d.F * d.H;
+  p.o0 = h2; p.bias = cond_bias + (size_t)flow * d.H; p.bias_bstride = (long long)d.F * d.H;
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
   k_sgemm<0, 0><<<grid, 256, 0, s>>>(p);
   CWG_CHECK_CUDA(cudaGetLastError());
@@ -443,6 +497,7 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
   p.W = w->w1_f32 + fl * (size_t)(2 * d.C) * d.K1; p.ldw = d.K1;
   p.a0 = x_in; p.a1 = h2; p.Tp = d.Tp; p.C = d.C; p.ks = d.ks; p.dil = 1 << layer; p.H = d.H;
   p.o0 = pre; p.bias = w->b1 + fl * (size_t)(2 * d.C);
+  if (d.b1_batch) { p.bias = d.b1_batch + fl * (size_t)(2 * d.C); p.bias_bstride = (long long)d.F * d.L * 2 * d.C; }
   dim3 g1((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
   k_sgemm<1, 1><<<g1, 256, 0, s>>>(p);
   CWG_CHECK_CUDA(cudaGetLastError());
@@ -456,7 +511,7 @@ int launch_layer_ffma(const Dims& d, const cwg_weights* w, int flow, int layer, 
   q.W = w->w2_f32 + fl * (size_t)d.N2 * d.C; q.ldw = d.C;
   q.a0 = acts; q.C = d.C;
   q.o0 = x_out; q.o1 = eo; q.xin = x_in;
-  q.bias = w->b2 + fl * (size_t)d.C; q.bias2 = w->eo_b + (size_t)flow * CWG_EO_PAD;
+  q.bias = w->b2 + fl * (size_t)d.C; q.bias2 = w->eo_b + (size_t)flow * d.MG; q.eo_pad = d.MG;
   q.has_res = layer < d.L - 1; q.first = layer == 0;
   dim3 g2((q.M + BM - 1) / BM, (q.N + BN - 1) / BN);
   k_sgemm<2, 2><<<g2, 256, 0, s>>>(q);
@@ -479,24 +534,37 @@ int launch_flow_boundary(const cwg_config* cfg, const Dims& d, const cwg_weights
   if (p.do_mix) {
     int nh;
     flow_channels(cfg, mix_flow, &p.n_rem_mix, &nh);
-    p.winv = w->winv + (size_t)mix_flow * CWG_MAX_GROUP * CWG_MAX_GROUP;
+    p.winv = w->winv + (size_t)mix_flow * d.MG * d.MG;
   }
   if (p.do_start) {
     flow_channels(cfg, flow_next, &p.n_rem2, &p.n_half2);
-    p.start_w = w->start_w + (size_t)flow_next * d.C * (CWG_MAX_GROUP / 2);
+    p.start_w = w->start_w + (size_t)flow_next * d.C * (d.MG / 2);
     p.start_b = w->start_b + (size_t)flow_next * d.C;
   }
+  const bool wide = d.MG != 16;
+  CWG_REQUIRE(!wide || p.a0_out == nullptr, "the layer-0 fold takes n_group <= 16");
   if ((d.C & 7) == 0 && ((uintptr_t)x_out & 15) == 0) {
     unsigned grid = (unsigned)((d.BT + TBV - 1) / TBV);
-    if (xfmt == 0) k_flow_boundary_v<0><<<grid, TBV, 0, s>>>(p);
-    else if (xfmt == 2) k_flow_boundary_v<2><<<grid, TBV, 0, s>>>(p);
-    else           k_flow_boundary_v<1><<<grid, TBV, 0, s>>>(p);
+    if (wide) {
+      if (xfmt == 0) k_flow_boundary_v<0, 32><<<grid, TBV, 0, s>>>(p);
+      else if (xfmt == 2) k_flow_boundary_v<2, 32><<<grid, TBV, 0, s>>>(p);
+      else           k_flow_boundary_v<1, 32><<<grid, TBV, 0, s>>>(p);
+    } else {
+      if (xfmt == 0) k_flow_boundary_v<0, 16><<<grid, TBV, 0, s>>>(p);
+      else if (xfmt == 2) k_flow_boundary_v<2, 16><<<grid, TBV, 0, s>>>(p);
+      else           k_flow_boundary_v<1, 16><<<grid, TBV, 0, s>>>(p);
+    }
   } else {
     CWG_REQUIRE(xfmt != 2, "CWG_MODE_F16F8 needs n_channels % 8 == 0");
     CWG_REQUIRE(p.a0_out == nullptr, "the layer-0 fold needs n_channels % 8 == 0");
     unsigned grid = (unsigned)((d.BT + TB - 1) / TB);
-    if (xfmt == 0) k_flow_boundary<0><<<grid, 256, 0, s>>>(p);
-    else           k_flow_boundary<1><<<grid, 256, 0, s>>>(p);
+    if (wide) {
+      if (xfmt == 0) k_flow_boundary<0, 32><<<grid, 256, 0, s>>>(p);
+      else           k_flow_boundary<1, 32><<<grid, 256, 0, s>>>(p);
+    } else {
+      if (xfmt == 0) k_flow_boundary<0, 16><<<grid, 256, 0, s>>>(p);
+      else           k_flow_boundary<1, 16><<<grid, 256, 0, s>>>(p);
+    }
   }
   CWG_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -955,6 +955,8 @@ int launch_cond_tc(const Dims& d, const cwg_weights* w, int npass, int flow, con
 int launch_layer_tc(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
                     const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
                     float* eo, cudaStream_t s) {
+  CWG_REQUIRE(d.MG == 16 && d.b1_batch == nullptr,
+              "the one-tile-per-CTA layer kernel takes n_group <= 16 and a shared gate bias (unset CWG_LAYER_PS)");
   const size_t plane = (size_t)d.BT * d.C, hplane = (size_t)d.BT * d.H;
   const uint64_t fl = (uint64_t)d.F * d.L;
   CUtensorMap tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo;

@@ -374,6 +374,7 @@ k_res512_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 int launch_layer_tc512(const Dims& d, const cwg_weights* w, int npass, int flow, int layer,
                        const __nv_bfloat16* x_in, __nv_bfloat16* x_out, const __nv_bfloat16* h2,
                        __nv_bfloat16* acts, float* eo, cudaStream_t s) {
+  CWG_REQUIRE(d.MG == 16 && d.b1_batch == nullptr, "the 512-channel kernels take n_group <= 16 and a shared gate bias");
   const size_t plane = (size_t)d.BT * d.C, hplane = (size_t)d.BT * d.H;
   const uint64_t fl = (uint64_t)d.F * d.L;
   CUtensorMap tx_hi, tx_lo, th_hi, th_lo, tw1_hi, tw1_lo, ta_hi, ta_lo, tw2_hi, tw2_lo, tse_hi, tse_lo, to_hi, to_lo;

@@ -22,6 +22,7 @@ namespace {
 constexpr int WF_C = 128, WF_KH = 3, WF_KW = 3, WF_HP = CWG_WF_COND_PAD;
 constexpr int WF_K1 = WF_KH * WF_KW * WF_C + WF_HP;     // 1280
 constexpr int WF_N2 = WF_C + CWG_EO_PAD;                // 144
+constexpr int WF_TC_MAX_GROUP = 16;                    // squeeze height of the tensor-core path (the fp32 path takes <= 32)
 constexpr uint32_t IDESC_N144 = umma_idesc_bf16(128, 144);
 
 struct WfDims {
@@ -419,7 +420,7 @@ int wf_check(const cwg_wf_config* c, int mode, int batch, int t_samples) {
   CWG_REQUIRE(mode == CWG_MODE_BF16X3 || mode == CWG_MODE_BF16, "WaveFlow supports the tensor-core modes only");
   CWG_REQUIRE(c->n_channels == WF_C && c->kernel_h == WF_KH && c->kernel_w == WF_KW,
               "WaveFlow kernels are built for n_channels=128 and a 3x3 kernel (got %d, %dx%d)", c->n_channels, c->kernel_h, c->kernel_w);
-  CWG_REQUIRE(c->n_group >= 2 && c->n_group <= CWG_MAX_GROUP, "n_group must be in [2, %d]", CWG_MAX_GROUP);
+  CWG_REQUIRE(c->n_group >= 2 && c->n_group <= WF_TC_MAX_GROUP, "n_group must be in [2, %d]", WF_TC_MAX_GROUP);
   CWG_REQUIRE(c->n_mel >= 1 && c->n_mel <= WF_HP, "n_mel must be <= %d", WF_HP);
   CWG_REQUIRE(c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_flows / n_layers");
   CWG_REQUIRE(batch >= 1 && t_samples >= c->n_group && t_samples % c->n_group == 0, "t_samples must be a positive multiple of n_group");
@@ -559,7 +560,7 @@ int cwg_wf_infer_profiled(const cwg_wf_config* cfg, const cwg_wf_weights* w, int
     CWG_CHECK_CUDA(cudaGetLastError());
   }
   // phys[c]: physical column of logical height row c in the state buffer (PermuteHeight is bookkeeping)
-  int phys[CWG_MAX_GROUP], perm[CWG_MAX_GROUP], nxt[CWG_MAX_GROUP];
+  int phys[WF_TC_MAX_GROUP], perm[WF_TC_MAX_GROUP], nxt[WF_TC_MAX_GROUP];
   for (int c = 0; c < h; ++c) phys[c] = c;
   const unsigned row_grid = (unsigned)((d.BT + 63) / 64);
   for (int k = F - 1; k >= 0; --k) {                                   // efficient_model_ax.py:325

@@ -21,8 +21,14 @@ from typing import Dict, List, Tuple
 
 import numpy as np
 
-EO_PAD = 16
-MAX_GROUP = 16
+EO_PAD = 16          # narrow layout (n_group <= 16), also what the WaveFlow kernels use
+MAX_GROUP = 32
+
+
+def group_pad(n_group: int) -> int:
+    """include/cwg.h CWG_GROUP_PAD: padding MG of the arrays indexed by latent channels (start_w [F][C][MG/2],
+    winv [F][MG][MG], eo_b [F][MG], w2 [F][L][C + MG][C]): 16, or 32 for 16 < n_group <= 32."""
+    return 16 if n_group <= 16 else 32
 
 
 @dataclass(frozen=True)
@@ -166,7 +172,8 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
     cfg.validate()
     F, L, C, H = cfg.n_flows, cfg.n_layers, cfg.n_channels, cfg.cond_hidden
     M, G, P, J, ks = cfg.n_mel, cfg.n_group, cfg.phases, cfg.taps, cfg.kernel_size
-    K1, N2, E = cfg.k1, C + EO_PAD, cfg.speaker_embed_dim
+    MG = group_pad(G)
+    K1, N2, E = cfg.k1, C + MG, cfg.speaker_embed_dim
 
     w_up = _np(sd["upsample.weight"])            # [M_in, M_out, win]
     b_up = _np(sd["upsample.bias"])
@@ -184,11 +191,11 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
     b1 = np.zeros((F, L, 2 * C))
     w2 = np.zeros((F, L, N2, C))
     b2 = np.zeros((F, L, C))
-    eo_b = np.zeros((F, EO_PAD))
+    eo_b = np.zeros((F, MG))
     w0 = np.zeros((F, 2 * C, 48))                 # layer-0 fold: in_layers.0 * start, col = tap*16 + j (see include/cwg.h)
-    start_w = np.zeros((F, C, MAX_GROUP // 2))
+    start_w = np.zeros((F, C, MG // 2))
     start_b = np.zeros((F, C))
-    winv = np.zeros((F, MAX_GROUP, MAX_GROUP))
+    winv = np.zeros((F, MG, MG))
 
     for k, (n_rem, n_half) in enumerate(cfg.flow_channels()):
         p = f"WN.{k}."
@@ -232,7 +239,7 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
         # --- start / inverse 1x1 -------------------------------------------------------
         start_w[k, :, :n_half] = effective_weight(sd, p + "start")[:, :, 0]
         start_b[k] = _np(sd[p + "start.bias"])
-        if ks == 3:
+        if ks == 3 and MG == 16:
             w_in0 = effective_weight(sd, p + "in_layers.0")              # [2C, C, 3]
             for tap in range(3):
                 w0[k, :, tap * 16:tap * 16 + n_half] = w_in0[:, :, tap] @ start_w[k, :, :n_half]
@@ -247,7 +254,7 @@ def pack_state_dict(sd, cfg: PackConfig, planes=("f32", "hi", "lo")) -> Dict[str
         "winv": winv.astype(np.float32),
         "cond_b_base": cond_b.astype(np.float32), "cond_w_spk": cond_w_spk.astype(np.float32),
     }
-    if ks == 3 and C == 256 and "f32" not in planes:
+    if ks == 3 and C == 256 and MG == 16 and "f32" not in planes:
         out["w0_hi"], out["w0_lo"] = split_f16(w0) if "f16f8" in planes else split_hi_lo(w0)
     for name, arr in (("cond_w", cond_w), ("w1", w1), ("w2", w2)):
         if "f32" in planes:

@@ -171,3 +171,20 @@ def waveflow_reference_kwargs(cfg: WaveFlowConfig) -> dict:
                 sampling_rate=22050, channel_mixing="permuteheight", mix_first=True, waveflow=True)
 
 
+
+
+def notebook_ax_kwargs() -> dict:
+    """Constructor kwargs of the one model the reference records an inference speed for: `waveglow_config` of
+    scripts/WaveGlowFlow Inference Speed Testing.ipynb cell 2, merged with its data_config's win / hop length the way
+    cell 3 does.  48 flows, n_group 24, early outputs every 16 flows, 8 x 256 WN with its own 96-dim speaker embedding,
+    a 3-layer residual ReZero cond net, `upsample_first: false` (every WN interpolates its cond-layer output)."""
+    wn = {"n_layers": 8, "n_channels": 256, "kernel_size_w": 3, "n_layers_dilations_w": None, "n_layers_dilations_h": 1,
+          "speaker_embed_dim": 96, "rezero": False, "cond_layers": 1, "cond_activation_func": "none", "negative_slope": 0.5,
+          "cond_hidden_channels": 256, "cond_padding_mode": "replicate", "seperable_conv": 0, "res_skip": True,
+          "merge_res_skip": False, "upsample_mode": "linear", "cond_kernel_size": 1}
+    return {"n_mel_channels": 160, "preceived_vol_scaling": False, "waveflow": False, "channel_mixing": "permute",
+            "mix_first": False, "n_flows": 48, "n_group": 24, "n_early_every": 16, "n_early_size": 2, "memory_efficient": 0.0,
+            "spect_scaling": False, "upsample_mode": "normal", "WN_config": wn, "speaker_embed": 96, "cond_layers": 3,
+            "cond_activation_func": "lrelu", "negative_slope": 0.5, "cond_hidden_channels": 256, "cond_output_channels": 256,
+            "cond_residual": True, "cond_res_rezero": True, "cond_padding_mode": "replicate", "upsample_first": False,
+            "cond_kernel_size": 2, "win_length": 2400, "hop_length": 600}

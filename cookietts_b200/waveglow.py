@@ -198,9 +198,10 @@ class WaveGlow(nn.Module):
         F, L, C, H = pc.n_flows, pc.n_layers, pc.n_channels, pc.cond_hidden
         kcp = -(-(pc.taps * pc.n_mel) // 64) * 64
         E, S = max(self._embed_dim, 1), self._n_speakers
-        shapes = {"cond_w": (F, pc.phases * H, kcp), "w1": (F, L, 2 * C, pc.k1), "w2": (F, L, C + _cabi.EO_PAD, C)}
-        small = {"b1": (F, L, 2 * C), "b2": (F, L, C), "eo_b": (F, _cabi.EO_PAD), "start_w": (F, C, _cabi.MAX_GROUP // 2),
-                 "start_b": (F, C), "winv": (F, _cabi.MAX_GROUP, _cabi.MAX_GROUP), "cond_b_base": (F, H), "cond_w_spk": (F, H, E)}
+        mg = 16 if pc.n_group <= 16 else 32                  # include/cwg.h CWG_GROUP_PAD
+        shapes = {"cond_w": (F, pc.phases * H, kcp), "w1": (F, L, 2 * C, pc.k1), "w2": (F, L, C + mg, C)}
+        small = {"b1": (F, L, 2 * C), "b2": (F, L, C), "eo_b": (F, mg), "start_w": (F, C, mg // 2),
+                 "start_b": (F, C), "winv": (F, mg, mg), "cond_b_base": (F, H), "cond_w_spk": (F, H, E)}
         if self._embed_dim:
             small["spk_embed"] = (F, S, self._embed_dim)
         f16 = torch.float16 if self.precision == "f16f8" else torch.bfloat16

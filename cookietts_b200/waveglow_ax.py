@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _cabi
 from .ax_frontend import AxFrontEndMixin
-from .packing import in_layer_weight_bias, split_f16, f8_correction_planes, PackConfig, split_hi_lo, effective_weight, _np, EO_PAD, MAX_GROUP
+from .packing import in_layer_weight_bias, split_f16, f8_correction_planes, PackConfig, split_hi_lo, effective_weight, _np, MAX_GROUP, group_pad
 
 
 def permute_height_index(k: int, h: int):
@@ -32,21 +32,32 @@ def permute_height_index(k: int, h: int):
     return idx[::-1]
 
 
-def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "lo"), cond_fold=None) -> Dict[str, np.ndarray]:
+def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "lo"), cond_fold=None,
+                       wn_speaker_dim: int = 0) -> Dict[str, np.ndarray]:
     """Arrays of `cwg_weights` for the ax 1-D model.  `pc.cond_hidden` is the padded cond width H
     (>= n_mel); eo rows are ordered [t | log_s] so the shared boundary kernel's (b, s) convention holds
-    (AffineCouplingBlock.inverse: `log_s, t = WN(...)`, efficient_modules.py:102-103)."""
+    (AffineCouplingBlock.inverse: `log_s, t = WN(...)`, efficient_modules.py:102-103).  Arrays indexed by latent
+    channels are padded to MG = group_pad(n_group) (include/cwg.h CWG_GROUP_PAD).  `wn_speaker_dim` > 0: the last
+    columns of every WN's cond layer multiply its own speaker embedding (glow_ax.py:284-286, :378-381); they are
+    returned as `spk_w` [F][L][2C][E] next to the tables `spk_embed` [F][S][E] (cwg_ax_speaker_bias)."""
     F, L, Cc, H, ks, M = pc.n_flows, pc.n_layers, pc.n_channels, pc.cond_hidden, pc.kernel_size, pc.n_mel
-    K1, N2 = ks * Cc + H, Cc + EO_PAD
+    MG, E = group_pad(pc.n_group), int(wn_speaker_dim)
+    K1, N2 = ks * Cc + H, Cc + MG
     w1 = np.zeros((F, L, 2 * Cc, K1)); b1 = np.zeros((F, L, 2 * Cc))
-    w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, EO_PAD))
-    start_w = np.zeros((F, Cc, MAX_GROUP // 2)); start_b = np.zeros((F, Cc))
-    winv = np.zeros((F, MAX_GROUP, MAX_GROUP))
+    w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, MG))
+    start_w = np.zeros((F, Cc, MG // 2)); start_b = np.zeros((F, Cc))
+    winv = np.zeros((F, MG, MG))
     w0 = np.zeros((F, 2 * Cc, 48))                           # layer-0 fold: in_layers.0 * start (include/cwg.h w0_hi / w0_lo)
+    spk_w = np.zeros((F, L, 2 * Cc, max(E, 1)), np.float32)
+    spk_embed = []
     for k, (n_rem, n_half) in enumerate(pc.flow_channels()):
         p = f"WN.{k}.WN."
         w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]
         b_c = _np(sd[p + "cond_layers.0.bias"])
+        if E:                                                # [cond channels | speaker embedding], glow_ax.py:381
+            spk_w[k] = w_c[:, w_c.shape[1] - E:].reshape(L, 2 * Cc, E)
+            w_c = w_c[:, :w_c.shape[1] - E]
+            spk_embed.append(np.asarray(_np(sd[p + "speaker_embed.weight"]), np.float32))
         if cond_fold is not None:                            # n_flow_group_conv in front of the cond layer (ax_frontend.py)
             w_c, b_c = cond_fold(k, w_c, b_c, sd)
         w_end = _np(sd[p + "end.weight"])[:, :, 0]
@@ -70,7 +81,7 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
         eo_b[k, :2 * n_half] = eo_bias
         start_w[k, :, :n_half] = effective_weight(sd, p + "start")[:, :, 0]
         start_b[k] = _np(sd[p + "start.bias"])
-        if ks == 3:
+        if ks == 3 and MG == 16:
             w_in0, _ = in_layer_weight_bias(sd, p + "in_layers.0")
             for tap in range(3):
                 w0[k, :, tap * 16:tap * 16 + n_half] = w_in0[:, :, tap] @ start_w[k, :, :n_half]
@@ -82,6 +93,8 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
             winv[k, :n_rem, :n_rem] = np.linalg.inv(_np(sd[f"convinv.{k}.weight"]).reshape(n_rem, n_rem))
     out = {"b1": b1.astype(np.float32), "b2": b2.astype(np.float32), "eo_b": eo_b.astype(np.float32),
            "start_w": start_w.astype(np.float32), "start_b": start_b.astype(np.float32), "winv": winv.astype(np.float32)}
+    if E:
+        out["spk_w"], out["spk_embed"] = spk_w, np.stack(spk_embed)
     for name, arr in (("w1", w1), ("w2", w2)):
         if "f32" in planes:
             out[name + "_f32"] = arr.astype(np.float32)
@@ -90,7 +103,7 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
             out[name + "_h8"], out[name + "_l8"] = f8_correction_planes(arr)
         elif "hi" in planes:
             out[name + "_hi"], out[name + "_lo"] = split_hi_lo(arr)
-    if ks == 3 and Cc == 256 and "f32" not in planes:
+    if ks == 3 and Cc == 256 and MG == 16 and "f32" not in planes:
         out["w0_hi"], out["w0_lo"] = split_f16(w0) if "f16f8" in planes else split_hi_lo(w0)
     return out
 
@@ -98,9 +111,12 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
 class _WN1d(nn.Module):
     """Parameter holder with the layout of glow_ax.py:245-373 (supported subset)."""
 
-    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels, seperable_conv=False):
+    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels, seperable_conv=False, speaker_embed_dim=0):
         super().__init__()
         wn = nn.utils.weight_norm
+        cond_in_channels += speaker_embed_dim                # glow_ax.py:255
+        if speaker_embed_dim:
+            self.speaker_embed = nn.Embedding(512, speaker_embed_dim)     # glow_ax.py:284-286
         self.in_layers = nn.ModuleList()
         self.res_skip_layers = nn.ModuleList()
         for i in range(n_layers):
@@ -163,15 +179,22 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             "permuteheight" if mixing in "waveflowpermuteheightpermutechannelpermute" else None)
         need(self.channel_mixing is not None, "channel_mixing must be '1x1conv' or 'permuteheight'")
         need(self.channel_mixing == "1x1conv" or n_flows % 2 == 0, "PermuteHeight requires an even n_flows")
-        need(upsample_first is True, "upsample_first must be True")
-        need(not wn.get("speaker_embed_dim", 0), "WN-level speaker embeddings are not supported (use the model-level speaker_embed)")
+        # upsample_first=False: every WN applies its cond layer at frame rate and interpolates the result (glow_ax.py:389,
+        # :361-373).  With the one linear 1x1 cond layer required below the two commute - interpolation weights sum to 1 - so
+        # the same kernels run it: interpolate the cond input once, contract it inside every layer's GEMM (include/cwg.h).
+        need(upsample_first is True or upsample_first is False, "upsample_first must be True or False")
+        need(upsample_first is True or not transposed_conv_scales,
+             "upsample_first=False with a model-level TransposedUpsampleNet (the reference never calls it there)")
+        self.wn_speaker_embed_dim = int(wn.get("speaker_embed_dim", 0) or 0)
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1 and wn.get("cond_activation_func", "none") == "none",
              "WN cond_layers must be one linear 1x1 conv")
         need(not wn.get("merge_res_skip") and wn.get("res_skip", True), "merged / absent res_skip variants are not supported")
         need(wn.get("gated_unit", "GTU") == "GTU" and wn.get("n_layers_dilations_w") is None, "only the GTU gate with 2^i dilations is supported")
         need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
         ks = wn.get("kernel_size_w") or wn.get("kernel_size")
-        need(hop_length % n_group == 0 and n_group <= MAX_GROUP, "hop_length % n_group == 0 and n_group <= 16")
+        need(hop_length % n_group == 0 and n_group <= MAX_GROUP, f"hop_length % n_group == 0 and n_group <= {MAX_GROUP}")
+        need(n_group <= 16 or precision == "ffma" or wn["n_channels"] == 256,
+             "n_group > 16 runs in precision='ffma' or, for 256 WN channels, on the tensor-core kernels")
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
         self.mix_first, self.upsample_linear = bool(mix_first), wn.get("upsample_mode", "linear") == "linear"
@@ -192,7 +215,8 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                 self.convinv.append(_InvConv(n_rem))
             self.WN.append(_Coupling(n_in=n_half, n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                      kernel_size=ks, cond_in_channels=self.wn_cond_in_channels,
-                                     seperable_conv=bool(wn.get("seperable_conv"))))
+                                     seperable_conv=bool(wn.get("seperable_conv")),
+                                     speaker_embed_dim=self.wn_speaker_embed_dim))
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -229,7 +253,8 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
         planes = {"ffma": ("f32",), "f16f8": ("f16f8",)}.get(self.precision, ("hi", "lo"))
         pk = pack_ax_state_dict(sd, pc, self.channel_mixing, planes=planes,
-                                cond_fold=self.group_conv_fold if self._fe_group else None)
+                                cond_fold=self.group_conv_fold if self._fe_group else None,
+                                wn_speaker_dim=self.wn_speaker_embed_dim)
         dev_pk = {}
         for name, arr in pk.items():
             if arr.dtype == np.uint16:
@@ -255,7 +280,10 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             lib.cwg_ax_infer.restype = C.c_int
             lib.cwg_ax_infer.argtypes = [C.POINTER(_cabi.CwgConfig), C.POINTER(_cabi.CwgWeights), C.c_int,
                                          C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
-                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            lib.cwg_ax_speaker_bias.restype = C.c_int
+            lib.cwg_ax_speaker_bias.argtypes = [C.POINTER(_cabi.CwgConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
             lib._ax_bound = True
         mode = _cabi.MODES[self.precision]
         cond = cond.to(device=dev, dtype=torch.float32)
@@ -278,11 +306,26 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
             audio = torch.empty(B, T, device=dev, dtype=torch.float32)
             stream = torch.cuda.current_stream(dev).cuda_stream
+            b1_batch = None
+            if self.wn_speaker_embed_dim:                    # WN-level speaker embedding -> per-utterance gate bias
+                if speaker_ids is None:
+                    raise Exception("This WaveGlow model has WN-level speaker embeddings and requires speaker ids.")
+                ids = torch.as_tensor(speaker_ids, device=dev).long().view(-1).contiguous()
+                if ids.numel() != B:
+                    raise ValueError(f"speaker_ids must hold one id per utterance ({B}), got {ids.numel()}")
+                n_spk = self._packed["spk_embed"].shape[1]
+                if not torch.cuda.is_current_stream_capturing() and (int(ids.min()) < 0 or int(ids.max()) >= n_spk):
+                    raise IndexError(f"speaker id out of range [0, {n_spk})")
+                pc = self.pack_config
+                b1_batch = torch.empty(B, pc.n_flows, pc.n_layers, 2 * pc.n_channels, device=dev, dtype=torch.float32)
+                _cabi.check(lib.cwg_ax_speaker_bias(self._ccfg, self._packed["b1"].data_ptr(), self._packed["spk_w"].data_ptr(),
+                                                    self._packed["spk_embed"].data_ptr(), self.wn_speaker_embed_dim, n_spk,
+                                                    ids.data_ptr(), B, b1_batch.data_ptr(), stream))
             _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
                                          int(self.upsample_linear), int(self.mix_first), z.data_ptr(), 1.0,
                                          audio.data_ptr(), ws_ptr,
                                          self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
-                                         B, T, stream))
+                                         B, T, b1_batch.data_ptr() if b1_batch is not None else None, stream))
             if self.precision == "f16f8" and not torch.cuda.is_current_stream_capturing():
                 # fp16 range guard (include/cwg.h cwg_infer_status): a value beyond +-65504 in an fp16 operand plane, or a
                 # non-finite waveform, means the f16f8 result cannot be trusted - this model must run in bf16x3

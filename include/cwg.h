@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CWG_ABI_VERSION 3
+#define CWG_ABI_VERSION 4
 
 /* Arithmetic modes of the WN contractions. */
 #define CWG_MODE_FFMA   0   /* fp32 weights/activations, CUDA-core FFMA (exact fp32 semantics)        */
@@ -44,8 +44,13 @@ extern "C" {
                                MMAs (twice the rate): a*w ~= a16*w16 + e5m2(a_lo*2^6)*e5m2(w16*2^-6) + e5m2(a16*2^-8)*e5m2(w_lo*2^8);
                                the res/skip GEMM likewise, the small cond GEMM uses three fp16 products                                */
 
-#define CWG_EO_PAD 16       /* padded width of the folded `end` output (2*n_half <= 16)              */
-#define CWG_MAX_GROUP 16    /* n_group <= 16                                                         */
+#define CWG_EO_PAD 16       /* padded width of the folded `end` output for n_group <= 16 (2*n_half <= 16) */
+#define CWG_MAX_GROUP 32    /* n_group <= 32                                                         */
+/* ABI 4: group padding MG of the arrays indexed by latent channels.  n_group <= 16 keeps the round-1 layout (MG = 16);
+ * 16 < n_group <= 32 (the ax notebook model: n_group 24) doubles it.  start_w is [F][C][MG/2], winv [F][MG][MG], the
+ * folded `end` output (eo, eo_b, the last rows of w2) is MG wide and N2 = C + MG.  The wide layout runs in CWG_MODE_FFMA
+ * and, for n_channels = 256, in the tensor-core modes (cwg_ps.cu; layer 0 unfolded). */
+#define CWG_GROUP_PAD(n_group) ((n_group) <= 16 ? 16 : 32)
 
 /* Mirrors the constructor arguments of the reference WaveGlow (glow.py:226-227) and
  * WN_config (glow.py:116-117) that the inverse pass depends on. */
@@ -65,7 +70,7 @@ typedef struct cwg_config {
 
 /* Device pointers to the packed weights.  F = n_flows, L = n_layers, C = n_channels,
  * H = cond_hidden, P = hop/n_group, J = ceil(win/hop), M = n_mel, K1 = kernel_size*C + H,
- * N2 = C + CWG_EO_PAD.  fp32 arrays are used by CWG_MODE_FFMA, the bf16 hi/lo planes by the
+ * N2 = C + MG, MG = CWG_GROUP_PAD(n_group).  fp32 arrays are used by CWG_MODE_FFMA, the bf16 hi/lo planes by the
  * tensor-core modes (lo = bf16(w - float(hi))); unused ones may be NULL. */
 typedef struct cwg_weights {
   const float*    cond_w_f32;   /* [F][P*H][KCp]   row p*H+h, col j*M+ci; KCp = J*M rounded up to 64, zero padded */
@@ -79,10 +84,10 @@ typedef struct cwg_weights {
   const uint16_t* w2_hi;
   const uint16_t* w2_lo;
   const float*    b2;           /* [F][L][C]       res bias (0 for the last layer)      */
-  const float*    eo_b;         /* [F][CWG_EO_PAD] end bias + end*(sum of skip biases)  */
-  const float*    start_w;      /* [F][C][CWG_MAX_GROUP/2]                              */
+  const float*    eo_b;         /* [F][MG]         end bias + end*(sum of skip biases)  */
+  const float*    start_w;      /* [F][C][MG/2]                                         */
   const float*    start_b;      /* [F][C]                                               */
-  const float*    winv;         /* [F][CWG_MAX_GROUP][CWG_MAX_GROUP]  W^-1, row major   */
+  const float*    winv;         /* [F][MG][MG]     W^-1, row major                      */
   /* CWG_MODE_F16F8 only (there *_hi / *_lo are fp16 planes): e5m2 planes of w1, same shape as w1_hi */
   const uint8_t*  w1_h8;        /* e5m2(fp16(w1) * 2^-6)                                */
   const uint8_t*  w1_l8;        /* e5m2((w1 - fp16(w1)) * 2^8)                          */
@@ -194,7 +199,7 @@ int cwg_cond(const cwg_config* cfg, const cwg_weights* w, int mode, int flow,
 
 /* One WN layer: x_in -> x_out (fp32 [batch][T'][C] in FFMA mode; hi/lo bf16 planes in the bf16 modes; in
  * CWG_MODE_F16F8 fp16 hi, fp16 lo, e5m2(lo * 2^6), e5m2(hi * 2^-8) planes, 6 bytes per element),
- * eo [batch][T'][CWG_EO_PAD] fp32 accumulated (written when layer == 0). */
+ * eo [batch][T'][MG] fp32 accumulated (written when layer == 0). */
 int cwg_wn_layer(const cwg_config* cfg, const cwg_weights* w, int mode, int flow, int layer,
                  const void* x_in, void* x_out, const void* h2, float* eo,
                  void* workspace, size_t workspace_bytes, int batch, int t_mel, void* cuda_stream);
@@ -217,7 +222,20 @@ size_t cwg_ax_workspace_bytes(const cwg_config* cfg, int mode, int batch, int fr
 int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
                  const float* mel, int frames, int pad_frames, int upsample_linear, int mix_first,
                  const float* z, float sigma, float* audio, void* workspace, size_t workspace_bytes,
-                 int batch, int t_samples, void* cuda_stream);
+                 int batch, int t_samples, const float* b1_batch, void* cuda_stream);
+
+/* WN-level speaker embedding (glow_ax.py:284-286, :378-381: every flow's WN concatenates speaker_embed(speaker_id),
+ * constant over time, to its cond input before the 1x1 cond layer).  A time-constant input of a 1x1 conv is a bias, so
+ * the branch is evaluated once per call instead of per group-step:
+ *   b1_batch[b][f][l][n] = b1[f][l][n] + sum_e spk_w[f][l][n][e] * spk_embed[f][speaker_ids[b]][e]
+ * spk_w [F][L][2C][E] holds the speaker columns of every flow's cond_layers.0, spk_embed [F][S][E] the embedding tables.
+ * The result ([batch][F][L][2C] fp32, device) is what cwg_ax_infer takes as `b1_batch` (NULL: the shared w->b1).  The
+ * same commutation - interpolate(conv1x1(x)) == conv1x1(interpolate(x)) because the interpolation weights sum to 1 - is
+ * what lets `upsample_first=False` models (cond layer at frame rate, then WN._upsample_mels, glow_ax.py:361-373, :389)
+ * run on the same kernels. */
+int cwg_ax_speaker_bias(const cwg_config* cfg, const float* b1, const float* spk_w, const float* spk_embed,
+                        int speaker_embed_dim, int n_speakers, const int64_t* speaker_ids, int batch,
+                        float* b1_batch, void* cuda_stream);
 
 /* =====================================================================================
  * WaveFlow (BASELINE config 5): the reference's "ax" model with waveflow=True
@@ -232,7 +250,7 @@ int cwg_ax_infer(const cwg_config* cfg, const cwg_weights* w, int mode,
 typedef struct cwg_wf_config {
   int32_t n_mel;
   int32_t n_flows;
-  int32_t n_group;        /* squeeze height h (<= CWG_MAX_GROUP) */
+  int32_t n_group;        /* squeeze height h (<= 16 in the tensor-core modes, <= 32 in CWG_MODE_FFMA) */
   int32_t n_layers;
   int32_t n_channels;     /* 128 */
   int32_t kernel_h, kernel_w;   /* 3, 3 */

@@ -27,6 +27,7 @@ class FrontEndConfig:
     n_group: int = 8
     hop_length: int = 16
     upsample_mode: str = "linear"
+    upsample_first: bool = True            # False: the model-level upsampling is skipped (efficient_model_ax.py:313)
     speaker_embed: int = 0
     cond_layers: int = 0
     cond_hidden_channels: int = 16
@@ -147,7 +148,9 @@ def frontend(sd, fe: FrontEndConfig, spect, speaker_ids, n_steps: int, dtype=np.
     else:
         cond = cond_res
     interpolation_required = True
-    if fe.has_upsample_net():                              # glow_ax.py:228-242
+    if not fe.upsample_first:                              # efficient_model_ax.py:313: `if self.upsample_early is True`
+        pass
+    elif fe.has_upsample_net():                            # glow_ax.py:228-242
         scales = fe.transposed_conv_scales
         x = cond
         ks = fe.transposed_conv_kernel_size
@@ -165,7 +168,9 @@ def frontend(sd, fe: FrontEndConfig, spect, speaker_ids, n_steps: int, dtype=np.
             x[:, :rc] += interp_linear_half_pixel(cond, int(np.prod(scales)))[:, :rc]
         cond = x
         interpolation_required = int(np.prod(scales)) != fe.hop_length // fe.n_group
-    if interpolation_required and cond.shape[2] != n_steps:     # efficient_model_ax.py:174-175
+    if not fe.upsample_first:
+        pass
+    elif interpolation_required and cond.shape[2] != n_steps:   # efficient_model_ax.py:174-175
         cond = upsample_cond(cond, n_steps, fe.upsample_mode)
     else:                                                  # :176-181
         pad_l = (cond.shape[2] - n_steps) // 2

@@ -32,6 +32,14 @@ from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd  #
 SMALL = dict(n_mel_channels=8, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, n_layers=3, n_channels=16,
              win_length=64, hop_length=16)
 
+# notebook cell 2: waveglow_config / WN_config / data_config (hop_length 600, win_length 2400), see the cases below
+NB = dict(n_mel_channels=160, n_flows=48, n_group=24, n_early_every=16, n_early_size=2, n_layers=8, n_channels=256,
+          win_length=2400, hop_length=600, channel_mixing="permuteheight", mix_first=False, wn_speaker_embed_dim=96,
+          upsample_first=False)
+NB_FE = dict(speaker_embed=96, cond_layers=3, cond_activation_func="lrelu", negative_slope=0.5, cond_hidden_channels=256,
+             cond_output_channels=256, cond_residual=True, cond_res_rezero=True, cond_padding_mode="replicate",
+             cond_kernel_size=2)
+
 # name: (kind, model kwargs, front-end kwargs, batch, frames, sigma, weight seed, input seed)
 CASES = {
     "axfe_speaker_cond": ("ax", SMALL, dict(speaker_embed=4, cond_layers=2, cond_hidden_channels=10, cond_output_channels=12,
@@ -68,6 +76,16 @@ CASES = {
     "axfe_separable": ("ax", dict(SMALL, seperable_conv=True), dict(speaker_embed=3), 2, 6, 0.8, 47, 7),
     "axfe_separable_256": ("ax", dict(seperable_conv=True), dict(), 1, 5, 0.666, 48, 8),
     "axfe_waveflow_separable": ("wf", dict(seperable_conv=True), dict(speaker_embed=8), 1, 4, 0.666, 49, 9),
+    # ---- the layout of `scripts/WaveGlowFlow Inference Speed Testing.ipynb` cell 2 (the one config the reference records a
+    # speed for): n_group 24 with early outputs, 'permute' mixing after the coupling, WN-level speaker embeddings,
+    # upsample_first=False, residual ReZero cond net with 'lrelu' and replicate padding.  Small widths (fp32 path) ...
+    "axfe_nb_small": ("ax", dict(NB, n_mel_channels=8, n_flows=6, n_early_every=2, n_layers=3, n_channels=16, win_length=192,
+                                 hop_length=48, wn_speaker_embed_dim=5),
+                      dict(NB_FE, speaker_embed=4, cond_hidden_channels=10), 3, 7, 0.8, 50, 10),
+    # ... the notebook's WN (8 x 256, 160 mels, 96 + 96 speaker dims, hop 600) with 6 of its 48 flows ...
+    "axfe_nb_256": ("ax", dict(NB, n_flows=6, n_early_every=2), dict(NB_FE), 2, 4, 0.9, 51, 11),
+    # ... and the notebook's model itself (48 flows, early outputs every 16) on a short clip
+    "axfe_notebook": ("ax", dict(NB), dict(NB_FE), 1, 5, 1.0, 52, 12),
 }
 
 
@@ -79,10 +97,11 @@ def build_case(kind, mkw, fkw):
         cfg = WaveFlowConfig(**mkw)
         base = reference_kwargs(cfg)
     fe = FrontEndConfig(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
-                        hop_length=cfg.hop_length, upsample_mode=cfg.upsample_mode, **fkw)
+                        hop_length=cfg.hop_length, upsample_mode=cfg.upsample_mode,
+                        upsample_first=getattr(cfg, "upsample_first", True), **fkw)
     kw = dict(base)
     for f in dataclasses.fields(fe):
-        if f.name in ("n_mel_channels", "n_flows", "n_group", "hop_length", "upsample_mode"):
+        if f.name in ("n_mel_channels", "n_flows", "n_group", "hop_length", "upsample_mode", "upsample_first"):
             continue
         kw[f.name] = getattr(fe, f.name)
     return cfg, fe, kw
@@ -98,7 +117,10 @@ def main():
     np.product = np.prod                                   # removed in numpy 2; the reference still calls it
     Model = load_reference_ax()
     outdir = os.path.join(ROOT, "tests", "golden")
+    only = set(sys.argv[1:])
     for name, (kind, mkw, fkw, batch, frames, sigma, wseed, iseed) in CASES.items():
+        if only and name not in only:
+            continue
         cfg, fe, kw = build_case(kind, mkw, fkw)
         sd = state_dict_for(kind, cfg, fe, wseed)
         rs = np.random.RandomState(iseed)

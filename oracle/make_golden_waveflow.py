@@ -71,13 +71,13 @@ CASES = {
 def reference_kwargs_ax1d(cfg) -> dict:
     """Constructor kwargs of the ax model with waveflow=False for an oracle.waveglow_ax_oracle.AxConfig."""
     wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, kernel_size_w=None,
-              n_layers_dilations_w=None, n_layers_dilations_h=1, speaker_embed_dim=0, rezero=False, cond_layers=1,
+              n_layers_dilations_w=None, n_layers_dilations_h=1, speaker_embed_dim=cfg.wn_speaker_embed_dim, rezero=False, cond_layers=1,
               cond_activation_func="none", negative_slope=None, cond_hidden_channels=256, cond_kernel_size=1,
               cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv, res_skip=True, merge_res_skip=False,
               upsample_mode=cfg.upsample_mode)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size, memory_efficient=0.0,
-                spect_scaling=False, upsample_mode="normal", upsample_first=True, speaker_embed=0, cond_layers=0,
+                spect_scaling=False, upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,
                 cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
                 cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
                 sampling_rate=22050, channel_mixing=cfg.channel_mixing, mix_first=cfg.mix_first, waveflow=False)

@@ -7,9 +7,11 @@ TEST INFRASTRUCTURE ONLY (same rules as waveglow_oracle.py).  numpy restatement 
   efficient_modules.py:94-105    AffineCouplingBlock.inverse (non-memory-efficient branch)
   glow_ax.py:375-418             WN.forward (1-D, one 1x1 cond layer, GTU gate)
   efficient_modules.py:269-286   InvertibleConv1x1.inverse   |  :360-403 PermuteHeight.inverse
-for the subset the B200 build supports: upsample_first=True with model-level F.interpolate, no
-model-level cond layers / upsample net / speaker embedding, channel_mixing '1x1conv' or
-'permuteheight', mix_first True or False, early outputs.
+  glow_ax.py:284-286,378-381     WN-level speaker embedding   |  :361-373,389 WN._upsample_mels (upsample_first=False)
+for the subset the B200 build supports: upsample_first=True with model-level F.interpolate or upsample_first=False
+(every WN interpolates its own cond-layer output), channel_mixing '1x1conv' or 'permuteheight', mix_first True or
+False, early outputs, n_group <= 32, optional WN-level speaker embedding.  The model-level conditioning front-end
+(speaker embedding, cond layers, upsample net, group conv) is restated in ax_frontend_oracle.py.
 
 Parity status: PINNED by oracle/make_golden_waveflow.py (cases `waveglow_ax_*`).
 """
@@ -39,6 +41,8 @@ class AxConfig:
     channel_mixing: str = "1x1conv"      # or "permuteheight"
     mix_first: bool = True
     seperable_conv: bool = False         # in_layer = Sequential(depthwise, pointwise), glow_ax.py:350-358
+    wn_speaker_embed_dim: int = 0        # WN_config['speaker_embed_dim'], glow_ax.py:255,284-286
+    upsample_first: bool = True          # False: cond stays at frame rate until WN._upsample_mels, glow_ax.py:389
 
     def flow_channels(self) -> List[int]:
         out, n_rem = [], self.n_group
@@ -49,15 +53,21 @@ class AxConfig:
         return out
 
 
-def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype):
-    """glow_ax.WN.forward (:375-418): returns (log_s, t)."""
+def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
+    """glow_ax.WN.forward (:375-418): returns (log_s, t).  `cond_up` is at T' rate (upsample_first=True) or at frame
+    rate (upsample_first=False: interpolated after the cond layer, :389)."""
     p = f"WN.{k}.WN."
     C, L = cfg.n_channels, cfg.n_layers
     audio = np.einsum("oc,bct->bot", _w(sd, p + "start", dtype)[:, :, 0], audio0, optimize=True) \
         + np.asarray(sd[p + "start.bias"], dtype)[None, :, None]
+    B, _, T = audio.shape
+    if cfg.wn_speaker_embed_dim and speaker_ids is not None:             # :378-381
+        emb = np.asarray(sd[p + "speaker_embed.weight"], dtype)[np.asarray(speaker_ids)]
+        cond_up = np.concatenate([cond_up, np.repeat(emb[:, :, None], cond_up.shape[2], axis=2)], axis=1)
     spect = np.einsum("oc,bct->bot", _w(sd, p + "cond_layers.0", dtype)[:, :, 0], cond_up, optimize=True) \
         + np.asarray(sd[p + "cond_layers.0.bias"], dtype)[None, :, None]
-    B, _, T = audio.shape
+    if not cfg.upsample_first:                                           # :389 -> _upsample_mels :361-373 (no WN upsample net:
+        spect = upsample_cond(spect, T, cfg.upsample_mode)               # interpolation_required, F.interpolate to audio length)
     output = None
     for i in range(L):
         d = 2 ** i
@@ -102,14 +112,16 @@ def mix_inverse(sd, k, cfg: AxConfig, z, dtype):
     return np.einsum("oc,bct->bot", W_inv, z, optimize=True)
 
 
-def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32, cond_up=None, ignore_nan=True):
+def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32, cond_up=None, ignore_nan=True, speaker_ids=None):
     """`cond_up` (one [B, C, T'] array, or one per flow) replaces the plain interpolation when the model has a
-    conditioning front-end (oracle/ax_frontend_oracle.py)."""
+    conditioning front-end (oracle/ax_frontend_oracle.py); with upsample_first=False it is at frame rate."""
     z = np.asarray(z, dtype)
     B = z.shape[0]
     zz = z.reshape(B, -1, cfg.n_group).transpose(0, 2, 1)               # :310
     if cond_up is None:
-        cond_up = upsample_cond(np.asarray(cond, dtype), zz.shape[2], cfg.upsample_mode)   # :313-314
+        cond_up = np.asarray(cond, dtype)
+        if cfg.upsample_first:
+            cond_up = upsample_cond(cond_up, zz.shape[2], cfg.upsample_mode)   # :313-314
     n_early = sum(1 for k in range(cfg.n_flows) if k % cfg.n_early_every == 0 and k > 0)
     sizes = [cfg.n_early_size] * n_early + [cfg.n_group - cfg.n_early_size * n_early]
     parts, off = [], 0
@@ -122,7 +134,7 @@ def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32, cond_up=None, ignore_n
         n_half = zz.shape[1] // 2
         a0, a1 = zz[:, :n_half], zz[:, n_half:]
         k_cond = cond_up[k] if isinstance(cond_up, (list, tuple)) else cond_up      # :328
-        log_s, t = wn_forward(sd, k, cfg, a0, k_cond, dtype)             # efficient_modules.py:99-105
+        log_s, t = wn_forward(sd, k, cfg, a0, k_cond, dtype, speaker_ids)   # efficient_modules.py:99-105
         with np.errstate(all="ignore"):
             zz = np.concatenate([a0, (a1 - t) / np.exp(log_s)], axis=1)
         if ignore_nan:                                                   # :331-332 (masked_fill_(isnan, 0))
@@ -177,6 +189,8 @@ def synthetic_state_dict(cfg: AxConfig, seed: int = 1234, cond_in_channels=None)
         wn(p + "start", (C, n_half, 1), n_half)
         sd[p + "end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
         sd[p + "end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
-        cin = cond_in_channels or cfg.n_mel_channels
+        cin = (cond_in_channels or cfg.n_mel_channels) + cfg.wn_speaker_embed_dim
         wn(p + "cond_layers.0", (2 * C * L, cin, 1), cin)
+        if cfg.wn_speaker_embed_dim:
+            sd[p + "speaker_embed.weight"] = rs.standard_normal((512, cfg.wn_speaker_embed_dim)).astype(np.float32)
     return sd

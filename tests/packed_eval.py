@@ -8,7 +8,7 @@ and with `emulate='bf16'/'bf16x3'` to predict the tensor-core modes' error.
 """
 import numpy as np
 
-from cookietts_b200.packing import (PackConfig, bf16_bits_to_f32, f32_to_bf16_bits, EO_PAD, F8_P, F8_Q,
+from cookietts_b200.packing import (PackConfig, bf16_bits_to_f32, f32_to_bf16_bits, F8_P, F8_Q,
                                     f32_to_e5m2_bits, e5m2_bits_to_f32)
 
 
@@ -95,7 +95,7 @@ def packed_infer(pk, cfg: PackConfig, mel, z, sigma, emulate=None, cond_bias=Non
             a = np.concatenate([xp[:, tap * d:tap * d + Tp] for tap in range(ks)] + [h2], axis=2)  # [B,T',K1]
             pre = _mm(a.reshape(B * Tp, -1), W("w1", k, i), emulate) + pk["b1"][k, i].astype(np.float64)
             acts = np.tanh(pre[:, :C]) / (1.0 + np.exp(-pre[:, C:]))
-            rs = _mm(acts, W("w2", k, i), emulate).reshape(B, Tp, C + EO_PAD)
+            rs = _mm(acts, W("w2", k, i), emulate).reshape(B, Tp, -1)          # C + MG (packing.group_pad)
             if i < L - 1:
                 x = x + rs[:, :, :C] + pk["b2"][k, i].astype(np.float64)
             eo = eo + rs[:, :, C:]
@@ -103,4 +103,48 @@ def packed_infer(pk, cfg: PackConfig, mel, z, sigma, emulate=None, cond_bias=Non
         a1 = (audio[:, :, off + n_half:] - b) * np.exp(-s)
         v = np.concatenate([a0, a1], axis=2)
         audio[:, :, off:] = v @ pk["winv"][k][:n_rem, :n_rem].astype(np.float64).T
+    return audio.reshape(B, Tp * G)
+
+
+def packed_ax_inverse(pk, cfg: PackConfig, cond_up, z, mix_first: bool, speaker_ids=None):
+    """What cwg_ax_infer computes from `waveglow_ax.pack_ax_state_dict` (fp32 planes, fp64 arithmetic): cond_up
+    [B, n_mel, T'] is the interpolated cond input (k_mel_up), z [B, T] the already scaled latent.  WN-level speaker
+    embeddings enter as the per-utterance gate bias of cwg_ax_speaker_bias."""
+    B = z.shape[0]
+    G, C, L, ks, H, M = cfg.n_group, cfg.n_channels, cfg.n_layers, cfg.kernel_size, cfg.cond_hidden, cfg.n_mel
+    Tp = z.shape[1] // G
+    audio = z.astype(np.float64).reshape(B, Tp, G).copy()
+    h2 = np.zeros((B, Tp, H)); h2[:, :, :M] = np.asarray(cond_up, np.float64).transpose(0, 2, 1)
+    b1 = np.broadcast_to(pk["b1"].astype(np.float64)[None], (B,) + pk["b1"].shape)
+    if "spk_w" in pk:
+        emb = pk["spk_embed"].astype(np.float64)[:, np.asarray(speaker_ids)]                   # [F, B, E]
+        b1 = b1 + np.einsum("flne,fbe->bfln", pk["spk_w"].astype(np.float64), emb)
+    fc = cfg.flow_channels()
+
+    def mix(k):
+        n_rem = fc[k][0]
+        audio[:, :, G - n_rem:] = audio[:, :, G - n_rem:] @ pk["winv"][k][:n_rem, :n_rem].astype(np.float64).T
+    for k in reversed(range(cfg.n_flows)):
+        n_rem, n_half = fc[k]
+        off = G - n_rem
+        if not mix_first:
+            mix(k)
+        a0 = audio[:, :, off:off + n_half]
+        x = a0 @ pk["start_w"][k][:, :n_half].astype(np.float64).T + pk["start_b"][k].astype(np.float64)
+        eo = np.tile(pk["eo_b"][k].astype(np.float64), (B, Tp, 1))
+        for i in range(L):
+            d = 2 ** i
+            xp = np.zeros((B, Tp + 2 * d * (ks // 2), C))
+            xp[:, d * (ks // 2):d * (ks // 2) + Tp] = x
+            a = np.concatenate([xp[:, tap * d:tap * d + Tp] for tap in range(ks)] + [h2], axis=2)
+            pre = a @ pk["w1_f32"][k, i].astype(np.float64).T + b1[:, k, i][:, None, :]
+            acts = np.tanh(pre[:, :, :C]) / (1.0 + np.exp(-pre[:, :, C:]))
+            rs = acts @ pk["w2_f32"][k, i].astype(np.float64).T
+            if i < L - 1:
+                x = x + rs[:, :, :C] + pk["b2"][k, i].astype(np.float64)
+            eo = eo + rs[:, :, C:]
+        t, log_s = eo[:, :, :n_half], eo[:, :, n_half:2 * n_half]          # eo rows are ordered [t | log_s]
+        audio[:, :, off + n_half:] = (audio[:, :, off + n_half:] - t) * np.exp(-log_s)
+        if mix_first:
+            mix(k)
     return audio.reshape(B, Tp * G)

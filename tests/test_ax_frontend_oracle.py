@@ -30,3 +30,25 @@ def test_dropin_state_dict_layout(name):
     for k, v in sd.items():
         assert tuple(own[k].shape) == tuple(v.shape), k
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+
+
+def test_notebook_model_constructs_with_the_reference_layout():
+    """`notebook_ax_kwargs()` is cell 2 of the reference's speed-test notebook; the module built from it has exactly the
+    parameter names / shapes of the checkpoint the reference loaded with strict=True when `axfe_notebook` was generated,
+    and the case's own kwargs describe the same model."""
+    from cookietts_b200 import WaveGlowAx
+    from cookietts_b200.synthetic import notebook_ax_kwargs
+    kind, cfg, fe, sd, g = load_case("axfe_notebook")
+    model = WaveGlowAx(precision="f16f8", **notebook_ax_kwargs())
+    own = model.state_dict()
+    assert set(own.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    other = WaveGlowAx(precision="f16f8", **module_kwargs(kind, cfg, fe))
+    assert {k: tuple(v.shape) for k, v in other.state_dict().items()} == {k: tuple(v.shape) for k, v in own.items()}
+    assert (model.n_group, model.n_flows, model.mix_first, model.channel_mixing, model.wn_speaker_embed_dim) == (24, 48, False, "permuteheight", 96)
+    # variants that do not commute with the interpolation still raise
+    kw = notebook_ax_kwargs()
+    kw["WN_config"] = dict(kw["WN_config"], cond_layers=2)
+    with pytest.raises(NotImplementedError):
+        WaveGlowAx(**kw)

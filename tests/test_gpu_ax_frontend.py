@@ -44,10 +44,37 @@ def test_frontend_fp32_cuda_cores(name):
 @pytest.mark.parametrize("name,precision", [("axfe_256", "bf16x3"), ("axfe_256", "bf16"),
                                             ("axfe_waveflow", "bf16x3"), ("axfe_waveflow", "bf16"),
                                             ("axfe_separable_256", "bf16x3"), ("axfe_waveflow_separable", "bf16x3"),
-                                            ("axfe_256", "f16f8"), ("axfe_separable_256", "f16f8")])
+                                            ("axfe_256", "f16f8"), ("axfe_separable_256", "f16f8"),
+                                            # the notebook layout: n_group 24 (wide group padding), WN-level speaker
+                                            # embeddings (two utterances, two speakers), upsample_first=False
+                                            ("axfe_nb_256", "bf16x3"), ("axfe_nb_256", "bf16"), ("axfe_nb_256", "f16f8")])
 def test_frontend_tensor_cores(name, precision):
     out, ref = run(name, precision)
     check(out, ref, precision)
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_notebook_model(precision):
+    """The one configuration the reference records a speed for (scripts/WaveGlowFlow Inference Speed Testing.ipynb
+    cell 2: 48 flows, n_group 24, 8 x 256 WN with 96-dim speaker embeddings, upsample_first=False) against the reference's
+    own output for a seeded synthetic checkpoint (oracle/make_golden_ax_frontend.py, case axfe_notebook)."""
+    out, ref = run("axfe_notebook", precision)
+    check(out, ref, precision)
+
+
+def test_wn_speaker_ids_are_per_utterance():
+    """Each utterance gets its own speaker's gate bias: a batch equals its utterances run one at a time."""
+    kind, cfg, fe, sd, g = load_case("axfe_nb_256")
+    m = WaveGlowAx(precision="bf16x3", **module_kwargs(kind, cfg, fe))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    m = m.cuda().eval()
+    mel, z, spk = torch.from_numpy(g["mel"]).cuda(), torch.from_numpy(g["z"]).cuda(), torch.from_numpy(g["speaker_ids"]).cuda()
+    both = m.infer(mel, speaker_ids=spk, sigma=0.9, z=z)
+    for b in range(mel.shape[0]):
+        one = m.infer(mel[b:b + 1], speaker_ids=spk[b:b + 1], sigma=0.9, z=z[b:b + 1])
+        assert torch.equal(one[0], both[b])
+    swapped = m.infer(mel, speaker_ids=spk.flip(0), sigma=0.9, z=z)
+    assert not torch.allclose(swapped, both)
 
 
 def test_missing_speaker_ids_raise():

@@ -71,3 +71,33 @@ def test_f16f8_planes_and_predicted_accuracy():
     from tests.packed_eval import packed_infer
     out = packed_infer(pk, pc, g["mel"], g["z"], float(g["sigma"]), emulate="f16f8")
     assert max_abs(out, g["audio_ref_fp64"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["axfe_speaker_cond", "axfe_nb_small"])
+def test_ax_packed_form_matches_reference(name):
+    """The ax packing - including the wide group layout (n_group 24), the WN-level speaker embedding as a per-utterance gate
+    bias and upsample_first=False run as interpolate-then-contract - reproduces the reference's own output."""
+    from cookietts_b200.waveglow_ax import pack_ax_state_dict
+    from oracle.ax_frontend_oracle import frontend
+    from oracle.waveflow_oracle import upsample_cond
+    from tests.ax_frontend_helpers import load_case
+    from tests.packed_eval import packed_ax_inverse
+    kind, cfg, fe, sd, g = load_case(name)
+    mel = np.concatenate([g["mel"].astype(np.float64), np.zeros(g["mel"].shape[:2] + (1,))], axis=2)   # artifact_trimming
+    samples = (mel.shape[2] - 1) * cfg.hop_length
+    samples -= samples % cfg.n_group
+    cond = frontend(sd, fe, mel, g["speaker_ids"], samples // cfg.n_group, np.float64)
+    if cond.shape[2] != samples // cfg.n_group:            # frame-rate cond: what cwg_ax_infer's k_mel_up interpolates
+        cond = upsample_cond(cond, samples // cfg.n_group, cfg.upsample_mode)
+    pc = PackConfig(n_mel=cond.shape[1], n_flows=cfg.n_flows, n_group=cfg.n_group, n_early_every=cfg.n_early_every,
+                    n_early_size=cfg.n_early_size, win_length=cfg.hop_length, hop_length=cfg.hop_length, n_layers=cfg.n_layers,
+                    n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, cond_hidden=cond.shape[1])
+    pk = pack_ax_state_dict(sd, pc, cfg.channel_mixing, planes=("f32",), wn_speaker_dim=cfg.wn_speaker_embed_dim)
+    mg = 16 if cfg.n_group <= 16 else 32
+    assert pk["eo_b"].shape == (cfg.n_flows, mg) and pk["winv"].shape == (cfg.n_flows, mg, mg)
+    assert pk["start_w"].shape[2] == mg // 2 and pk["w2_f32"].shape[2] == cfg.n_channels + mg
+    z = g["z"].astype(np.float64)[:, :samples] * float(g["sigma"])
+    out = packed_ax_inverse(pk, pc, cond, z, cfg.mix_first, g["speaker_ids"])[:, :-cfg.hop_length]
+    ref = g["infer_ref_fp64"]
+    assert out.shape == ref.shape
+    assert max_abs(out, ref) < 5e-5 and snr_db(ref, out) > 90.0
