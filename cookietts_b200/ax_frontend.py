@@ -189,7 +189,7 @@ class AxFrontEndMixin:
         key = tuple((p.data_ptr(), p._version) for p in self._fe_params())
         if self._fe_packed is not None and self._fe_key == key:
             return self._fe_packed
-        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
+        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items() if not k.startswith(("WN.", "convinv."))}
         up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev)
         pk = {"cond": [], "tconv": []}
         for i in range(len(self.cond_layers)):
@@ -201,6 +201,10 @@ class AxFrontEndMixin:
                 w = sd[f"upsample_net.t_convs.{idx}.weight"]
                 pk["tconv"].append((up(repack_conv_transpose(w, s)), up(sd[f"upsample_net.t_convs.{idx}.bias"]),
                                     w.shape[0], w.shape[1], k, s, p, act))
+        # host copies of the scalar gates, so that applying the front-end never synchronises (CUDA-graph capturable)
+        pk["alpha"] = float(np.asarray(sd["alpha"]).reshape(-1)[0]) if hasattr(self, "alpha") else 1.0
+        if hasattr(self, "upsample_net") and self.upsample_net.res_weight is not None:
+            pk["res_weight"] = float(np.asarray(sd["upsample_net.res_weight"]).reshape(-1)[0])
         self._fe_packed, self._fe_key = pk, key
         return pk
 
@@ -239,7 +243,7 @@ class AxFrontEndMixin:
             res = None
             if self.cond_residual:
                 res = self._conv1d(lib, cond, *pk["res_conv"], 0, 0, ACT_NONE, 0.0) if "res_conv" in pk else cond
-            alpha = float(self.alpha) if hasattr(self, "alpha") else 1.0
+            alpha = pk["alpha"]
             h = cond
             n = len(pk["cond"])
             for i, (w, b) in enumerate(pk["cond"]):
@@ -255,8 +259,7 @@ class AxFrontEndMixin:
                 Bh, _, T = h.shape
                 t_out = (T - 1) * s - 2 * p + k
                 y = torch.empty(Bh, cout, t_out, device=dev, dtype=torch.float32)
-                scale = float(net.res_weight) if (i == n - 1 and net.residual and net.res_weight is not None
-                                                  and float(net.res_weight) != 0.0) else 1.0
+                scale = pk["res_weight"] if (i == n - 1 and net.residual and pk.get("res_weight", 0.0) != 0.0) else 1.0
                 _cabi.check(lib.cwg_conv_transpose1d(h.data_ptr(), Bh, cin, T, w.data_ptr(), b.data_ptr(), cout, k, s, p,
                                                      ACT_LRELU if has_act else ACT_NONE, 0.4, scale, y.data_ptr(), stream))
                 h = y

@@ -8,6 +8,12 @@ cond layer (glow_ax.py:297-312) rides as extra K columns of each in_layer GEMM; 
 packed as a permutation matrix in the W^-1 slot.  Interface mirrored: constructor keywords
 (efficient_model_ax.py:19-20), state_dict layout (`convinv.{k}.weight`, `WN.{k}.WN.*`), `inverse(z,
 cond)` (:279) and `infer(...)` (:359-388).  Unsupported options raise at construction.
+
+Also covered: `n_group` up to 32 (wide group padding, include/cwg.h CWG_GROUP_PAD), WN-level speaker embeddings
+(glow_ax.py:284-286, :378-381 - a time-constant cond input, folded into a per-utterance gate bias by
+cwg_ax_speaker_bias) and `upsample_first=False` (glow_ax.py:389: the WN interpolates its cond-layer output; with the
+one linear 1x1 cond layer required here that equals contracting the interpolated cond input, which is what the kernels
+do) - together the model of the reference's speed-test notebook (`synthetic.notebook_ax_kwargs`).
 """
 from __future__ import annotations
 
@@ -165,7 +171,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                  transposed_conv_hidden_dim=256, transposed_conv_kernel_size=4, transposed_conv_scales=None,
                  transposed_conv_output_dim=256, transposed_conv_residual=False, transposed_conv_residual_linear=False,
                  transposed_conv_res_rezero=False, group_conv_output_dim=None, group_conv_groupped=True,
-                 iso226_empthasis=False, precision: str = "bf16x3"):
+                 iso226_empthasis=False, precision: str = "bf16x3", graphs="auto"):
         super().__init__()
         wn = dict(WN_config)
         a = locals()
@@ -220,6 +226,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         self._packed = None
         self._packed_key = None
         self._workspace = None
+        self.graphs, self._graphs, self._graph_seen = graphs, {}, set()   # CUDA-graph replay of repeated small shapes
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._packed = None
@@ -228,7 +235,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
     def invalidate(self):
         """Drop the packed weights (and the packed front end); needed only after edits made through `.data`, which do
         not bump a Parameter's version counter - see cookietts_b200.WaveGlow.invalidate."""
-        self._packed, self._packed_key = None, None
+        self._packed, self._packed_key, self._graphs = None, None, {}
         if hasattr(self, "_fe_packed"):
             self._fe_packed, self._fe_key = None, None
     repack = invalidate
@@ -265,14 +272,9 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
         self.pack_config = pc
         self._ccfg = _cabi.make_config(pc)
-        self._packed, self._packed_key, self._cw = dev_pk, key, w
+        self._packed, self._packed_key, self._cw, self._graphs = dev_pk, key, w, {}
 
-    @torch.no_grad()
-    def inverse(self, z, cond, speaker_ids=None, return_CPU=True):
-        """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
-        dev = self._device()
-        if dev.type != "cuda":
-            raise RuntimeError("cookietts_b200.WaveGlowAx needs the module on a CUDA device (no CPU fallback)")
+    def _bind(self):
         lib = _cabi.load()
         if not getattr(lib, "_ax_bound", False):
             lib.cwg_ax_workspace_bytes.restype = C.c_size_t
@@ -285,57 +287,121 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             lib.cwg_ax_speaker_bias.argtypes = [C.POINTER(_cabi.CwgConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
             lib._ax_bound = True
+        return lib
+
+    def _run(self, z, cond, ids):
+        """Every launch of one inverse pass on the current stream, no host synchronisation (CUDA-graph capturable once the
+        workspace exists): conditioning front-end, per-utterance speaker bias, flows, output filters.
+        Returns (audio [B, T] on the device, status word tensor or None)."""
+        dev = z.device
+        lib = self._bind()
         mode = _cabi.MODES[self.precision]
+        T = z.shape[1]
+        cond = self._fe_apply(cond, ids, T // self.n_group)  # speaker embedding, cond net, upsample net
+        B, _, frames = cond.shape
+        nbytes = lib.cwg_ax_workspace_bytes(self._ccfg, mode, B, frames, T)
+        if nbytes == 0:
+            raise _cabi.CwgError(lib.cwg_last_error().decode())
+        if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("WaveGlowAx: the workspace must exist before a CUDA-graph capture (run the shape once first)")
+            self._graphs = {}                                # captured graphs hold the old workspace's address
+            self._workspace = None
+            self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+        audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        b1_batch = None
+        if self.wn_speaker_embed_dim:                        # WN-level speaker embedding -> per-utterance gate bias
+            pc = self.pack_config
+            b1_batch = torch.empty(B, pc.n_flows, pc.n_layers, 2 * pc.n_channels, device=dev, dtype=torch.float32)
+            _cabi.check(lib.cwg_ax_speaker_bias(self._ccfg, self._packed["b1"].data_ptr(), self._packed["spk_w"].data_ptr(),
+                                                self._packed["spk_embed"].data_ptr(), self.wn_speaker_embed_dim,
+                                                self._packed["spk_embed"].shape[1], ids.data_ptr(), B, b1_batch.data_ptr(), stream))
+        _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
+                                     int(self.upsample_linear), int(self.mix_first), z.data_ptr(), 1.0,
+                                     audio.data_ptr(), ws_ptr,
+                                     self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
+                                     B, T, b1_batch.data_ptr() if b1_batch is not None else None, stream))
+        status = None
+        if self.precision == "f16f8":
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            _cabi.check(lib.cwg_infer_status(ws_ptr, status.data_ptr(), stream))
+        return self._fe_post(audio), status                  # inverse volume map / de-emphasis on the device
+
+    def _graph_run(self, z, cond, ids):
+        """Replays the captured launch sequence of this shape on static input buffers; captures it on first use."""
+        dev = z.device
+        key = (tuple(z.shape), tuple(cond.shape), self.precision, ids is not None)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            s_z, s_cond, s_ids = z.clone(), cond.clone(), (ids.clone() if ids is not None else None)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._run(s_z, s_cond, s_ids)                # warm-up outside the capture (workspace, tensor-map cache)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._run(s_z, s_cond, s_ids)
+            ent = (g, s_z, s_cond, s_ids, out)
+            self._graphs[key] = ent
+        else:
+            ent[1].copy_(z); ent[2].copy_(cond)
+            if ids is not None:
+                ent[3].copy_(ids)
+        ent[0].replay()
+        return ent[4][0].clone(), ent[4][1]
+
+    GRAPH_CACHE = 4
+    GRAPH_MAX_STEPS = 1 << 16        # graphs="auto": calls of at most this many group-steps (B * T / n_group) in total
+
+    @torch.no_grad()
+    def inverse(self, z, cond, speaker_ids=None, return_CPU=True):
+        """efficient_model_ax.py:279-357: z [B, T] (already scaled), cond [B, n_mel, frames] -> (audio, None)."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("cookietts_b200.WaveGlowAx needs the module on a CUDA device (no CPU fallback)")
         cond = cond.to(device=dev, dtype=torch.float32)
         if self.shift_spect != 0.:
             cond = cond + self.shift_spect
         if self.scale_spect != 1.:
             cond = cond * self.scale_spect
+        cond = cond.contiguous()
         z = z.to(device=dev, dtype=torch.float32).contiguous()
-        T = z.shape[1]
+        B, T = z.shape
+        capturing = torch.cuda.is_current_stream_capturing()
         with torch.cuda.device(dev):
             self._ensure_packed()
-            cond = self._fe_apply(cond.contiguous(), speaker_ids, T // self.n_group)   # speaker embedding, cond net, upsample net
-            B, _, frames = cond.shape
-            nbytes = lib.cwg_ax_workspace_bytes(self._ccfg, mode, B, frames, T)
-            if nbytes == 0:
-                raise _cabi.CwgError(lib.cwg_last_error().decode())
-            if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
-                self._workspace = None
-                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-            ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
-            audio = torch.empty(B, T, device=dev, dtype=torch.float32)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            b1_batch = None
-            if self.wn_speaker_embed_dim:                    # WN-level speaker embedding -> per-utterance gate bias
+            ids = None
+            if self.wn_speaker_embed_dim or self.speaker_embed_dim:
                 if speaker_ids is None:
-                    raise Exception("This WaveGlow model has WN-level speaker embeddings and requires speaker ids.")
+                    raise Exception("This WaveFlow/WaveGlow model requires speaker ids or speaker embeddings.")
                 ids = torch.as_tensor(speaker_ids, device=dev).long().view(-1).contiguous()
                 if ids.numel() != B:
                     raise ValueError(f"speaker_ids must hold one id per utterance ({B}), got {ids.numel()}")
-                n_spk = self._packed["spk_embed"].shape[1]
-                if not torch.cuda.is_current_stream_capturing() and (int(ids.min()) < 0 or int(ids.max()) >= n_spk):
-                    raise IndexError(f"speaker id out of range [0, {n_spk})")
-                pc = self.pack_config
-                b1_batch = torch.empty(B, pc.n_flows, pc.n_layers, 2 * pc.n_channels, device=dev, dtype=torch.float32)
-                _cabi.check(lib.cwg_ax_speaker_bias(self._ccfg, self._packed["b1"].data_ptr(), self._packed["spk_w"].data_ptr(),
-                                                    self._packed["spk_embed"].data_ptr(), self.wn_speaker_embed_dim, n_spk,
-                                                    ids.data_ptr(), B, b1_batch.data_ptr(), stream))
-            _cabi.check(lib.cwg_ax_infer(self._ccfg, self._cw, mode, cond.data_ptr(), frames, 0,
-                                         int(self.upsample_linear), int(self.mix_first), z.data_ptr(), 1.0,
-                                         audio.data_ptr(), ws_ptr,
-                                         self._workspace.numel() - (ws_ptr - self._workspace.data_ptr()),
-                                         B, T, b1_batch.data_ptr() if b1_batch is not None else None, stream))
-            if self.precision == "f16f8" and not torch.cuda.is_current_stream_capturing():
+                if not capturing and (int(ids.min()) < 0 or int(ids.max()) >= 512):
+                    raise IndexError("speaker id out of range [0, 512)")
+            # repeated small shapes are launch-latency bound (one tile pair per layer): replay them as a CUDA graph from
+            # their second occurrence on, like cookietts_b200.WaveGlow
+            gkey = (tuple(z.shape), tuple(cond.shape), self.precision)
+            use_graph = (not capturing and (self.graphs is True or
+                                            (self.graphs == "auto" and B * (T // self.n_group) <= self.GRAPH_MAX_STEPS)))
+            if use_graph and self.graphs == "auto" and gkey not in self._graph_seen:
+                if len(self._graph_seen) > 64:
+                    self._graph_seen.clear()
+                self._graph_seen.add(gkey)
+                use_graph = False
+            audio, status = self._graph_run(z, cond, ids) if use_graph else self._run(z, cond, ids)
+            if status is not None and not capturing:
                 # fp16 range guard (include/cwg.h cwg_infer_status): a value beyond +-65504 in an fp16 operand plane, or a
                 # non-finite waveform, means the f16f8 result cannot be trusted - this model must run in bf16x3
-                status = torch.zeros(1, dtype=torch.int32, device=dev)
-                _cabi.check(lib.cwg_infer_status(ws_ptr, status.data_ptr(), stream))
                 self.last_status = int(status.item())
                 if self.last_status:
                     raise _cabi.CwgError(f"WaveGlowAx(precision='f16f8'): fp16 range guard tripped (status {self.last_status}); "
                                          "construct the model with precision='bf16x3'")
-            audio = self._fe_post(audio)                     # inverse volume map / de-emphasis on the device
         return (audio.cpu() if return_CPU else audio), None
 
     @torch.no_grad()

@@ -159,3 +159,28 @@ def test_deemphasis_kernel(T, coef, vol):
     xd = torch.from_numpy(x).cuda(); y = torch.empty_like(xd)
     _cabi.check(lib.cwg_deemphasis(xd.data_ptr(), 3, T, coef, vol, y.data_ptr(), _stream()))
     assert max_abs(y.cpu().numpy(), ref) < 2e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_ax_graph_replay_matches_eager():
+    """graphs="auto": the second call of a shape is captured, later calls replay it on static buffers - same numbers as
+    the eager launches, new inputs (mel, z, speaker ids) are honoured, and a weight edit drops the captured graphs."""
+    kind, cfg, fe, sd, g = load_case("axfe_nb_256")
+    kw = module_kwargs(kind, cfg, fe)
+    eager = WaveGlowAx(precision="f16f8", graphs=False, **kw)
+    auto = WaveGlowAx(precision="f16f8", **kw)
+    for m in (eager, auto):
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        m.cuda().eval()
+    mel, z, spk = torch.from_numpy(g["mel"]).cuda(), torch.from_numpy(g["z"]).cuda(), torch.from_numpy(g["speaker_ids"]).cuda()
+    ref = eager.infer(mel, speaker_ids=spk, sigma=0.9, z=z)
+    outs = [auto.infer(mel, speaker_ids=spk, sigma=0.9, z=z) for _ in range(4)]
+    assert len(auto._graphs) == 1
+    for o in outs:
+        assert torch.equal(o, ref)
+    mel2, z2, spk2 = mel * 0.5 - 1.0, z.flip(1).contiguous(), spk.flip(0).contiguous()
+    assert torch.equal(auto.infer(mel2, speaker_ids=spk2, sigma=0.9, z=z2), eager.infer(mel2, speaker_ids=spk2, sigma=0.9, z=z2))
+    with torch.no_grad():
+        for m in (eager, auto):
+            m.WN[0].WN.end.bias.add_(0.05)
+    out3 = auto.infer(mel, speaker_ids=spk, sigma=0.9, z=z)
+    assert torch.equal(out3, eager.infer(mel, speaker_ids=spk, sigma=0.9, z=z)) and not torch.equal(out3, ref)
