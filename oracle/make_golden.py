@@ -128,6 +128,11 @@ CASES = {
     # chaotic beyond that: at x3 the reference's own fp32 and fp64 runs already differ by 2e-2)
     "stress": (dict(end_scale=2.5), 1, 86, 0.666, 1234, 0),
     "mel20_256": (dict(n_mel_channels=20, n_flows=2, n_layers=2, win_length=64, hop_length=16), 2, 40, 0.9, 43, 11),
+    # n_group > 16: the wide group padding (include/cwg.h CWG_GROUP_PAD) on the classic model - small (fp32 path) and 256-ch
+    "group24": (dict(n_mel_channels=8, n_flows=6, n_group=24, n_early_every=2, n_early_size=2, win_length=96, hop_length=48,
+                     n_layers=3, n_channels=16), 2, 9, 0.9, 44, 12),
+    "group24_256": (dict(n_mel_channels=20, n_flows=3, n_group=24, n_early_every=2, n_early_size=4, win_length=192,
+                         hop_length=48, n_layers=3), 2, 30, 0.8, 45, 13),
 }
 SPEAKERS = {"speaker": [5, 0, 77], "speaker256": [3, 200]}
 # Full-length cases (`python oracle/make_golden.py big`): one utterance of BASELINE.json configs[1] (T_mel = 861, 10 s).

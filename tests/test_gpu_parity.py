@@ -31,7 +31,7 @@ def run(name, precision):
     return out.cpu().numpy(), g
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "rezero", "config1", "c512", "mel20_256"])
+@pytest.mark.parametrize("name", ["tiny", "small", "rezero", "config1", "c512", "mel20_256", "group24", "group24_256"])
 def test_ffma_matches_reference(name):
     out, g = run(name, "ffma")
     ref = g["audio_ref_fp64"]
@@ -41,7 +41,7 @@ def test_ffma_matches_reference(name):
     assert max_abs(out, g["audio_ref_fp32"]) <= TOL["ffma"]["max_abs"]
 
 
-@pytest.mark.parametrize("name,precision", [("config1", "f16f8"), ("mel20_256", "f16f8")])
+@pytest.mark.parametrize("name,precision", [("config1", "f16f8"), ("mel20_256", "f16f8"), ("group24_256", "f16f8")])
 def test_f16f8_mode_matches_reference(name, precision):
     out, g = run(name, precision)
     ref = g["audio_ref_fp64"]
@@ -50,7 +50,7 @@ def test_f16f8_mode_matches_reference(name, precision):
     assert snr_db(ref, out) >= 80.0
 
 
-@pytest.mark.parametrize("name", ["config1", "c512", "mel20_256"])
+@pytest.mark.parametrize("name", ["config1", "c512", "mel20_256", "group24_256"])
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_tensor_core_modes_match_reference(precision, name):
     """config1: the fused 256-channel layer kernel; c512: the two-kernel 512-channel layer."""

@@ -6,7 +6,7 @@ import pytest
 from oracle.waveglow_oracle import infer_with_z, snr_db
 from tests.helpers import load_golden, max_abs
 
-CASES = ["tiny", "small", "rezero", "config1", "c512", "mel20_256"]
+CASES = ["tiny", "small", "rezero", "config1", "c512", "mel20_256", "group24", "group24_256"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -35,7 +35,7 @@ def _planes(name, planes):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["tiny", "rezero", "speaker", "config1", "c512"])
+@pytest.mark.parametrize("name", ["tiny", "rezero", "speaker", "config1", "c512", "group24"])
 def test_pack_fp32_planes(name):
     got, ref, m = _planes(name, ("f32",))
     for k in ("cond_w_f32", "w1_f32", "w2_f32", "b1", "b2", "eo_b", "start_w", "start_b", "winv", "cond_b_base"):
@@ -50,7 +50,7 @@ def test_pack_fp32_planes(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["config1", "c512"])
+@pytest.mark.parametrize("name", ["config1", "c512", "group24_256"])
 def test_pack_bf16_planes(name):
     got, ref, _ = _planes(name, ("hi", "lo"))
     for k in ("cond_w", "w1", "w2"):

@@ -17,7 +17,7 @@ def pack_cfg(cfg):
                       speaker_embed_dim=cfg.speaker_embed_dim, rezero=cfg.rezero)
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "rezero"])
+@pytest.mark.parametrize("name", ["tiny", "small", "rezero", "group24"])
 def test_packed_form_matches_reference(name):
     cfg, sd, g = load_golden(name)
     pc = pack_cfg(cfg)
