@@ -20,7 +20,9 @@ also by layer index) against the measured bf16 peak, with the ncu figures of the
 profiles/r2_ncu.json when its source hash matches; `cpu_baseline` / `--impl reference` = the reference's own
 `WaveGlow.infer` (oracle/_ref, an unmodified copy of glow.py) on this box's host cores on a bounded sample;
 `extra_configs` = 3-step runs of BASELINE configs 3 (bf16, 256 x 10 s over the ranks), 4 (512-channel model, 60 s in
-halo-overlapped chunks) and 5 (WaveFlow) at the same GPU count (`--no-extra` skips them; `--config N` runs one alone).
+halo-overlapped chunks) and 5 (WaveFlow) at the same GPU count, config 1's per-call latency and the per-call latency of
+the one model the reference itself records a speed for (its speed-test notebook's 48-flow ax WaveGlow, `--config 6`);
+`--no-extra` skips them, `--config N` runs one alone.
 """
 from __future__ import annotations
 
