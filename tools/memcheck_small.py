@@ -24,3 +24,21 @@ fd.load_state_dict({k: torch.from_numpy(v) for k, v in fd_sd(cfg, int(gf["weight
 o, _ = fd.inverse(torch.from_numpy(gf["z"]).cuda() * float(gf["sigma"]), torch.from_numpy(gf["cond"]).cuda())
 torch.cuda.synchronize()
 print("fd_untts", float(np.abs(o.cpu().numpy() - gf["out_ref_fp64"]).max()), flush=True)
+# wide group layout (n_group 24), WN-level speaker embeddings (per-utterance gate bias), upsample_first=False; classic wide
+from cookietts_b200 import WaveGlowAx
+from tests.ax_frontend_helpers import load_case, module_kwargs as ax_kwargs
+kind, cfg, fe, sd, g = load_case("axfe_nb_256")
+for prec in ("f16f8", "bf16x3", "bf16", "ffma"):
+    m = WaveGlowAx(precision=prec, graphs=False, **ax_kwargs(kind, cfg, fe))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.cuda().eval()
+    out = m.infer(torch.from_numpy(g["mel"]).cuda(), speaker_ids=torch.from_numpy(g["speaker_ids"]).cuda(), sigma=float(g["sigma"]),
+                  z=torch.from_numpy(g["z"]).cuda())
+    torch.cuda.synchronize()
+    print("axfe_nb_256", prec, float(np.abs(out.numpy() - g["infer_ref_fp64"]).max()), flush=True)
+cfg, sd, g = load_golden("group24_256")
+for prec in ("f16f8", "bf16x3", "ffma"):
+    m = WaveGlow(precision=prec, graphs=False, **module_kwargs(cfg))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.cuda().eval()
+    out = m.infer(torch.from_numpy(g["mel"]).cuda(), None, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
+    torch.cuda.synchronize()
+    print("group24_256", prec, float(np.abs(out.cpu().numpy() - g["audio_ref_fp64"]).max()), flush=True)
