@@ -15,7 +15,7 @@ MODE_FFMA, MODE_BF16X3, MODE_BF16, MODE_F16F8 = 0, 1, 2, 3
 MODES = {"ffma": MODE_FFMA, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "f16f8": MODE_F16F8}
 EO_PAD = 16          # narrow layout; see packing.group_pad / include/cwg.h CWG_GROUP_PAD
 MAX_GROUP = 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class CwgConfig(C.Structure):
@@ -48,7 +48,8 @@ EXPORTS = ("cwg_abi_version", "cwg_last_error", "cwg_workspace_bytes", "cwg_laun
            "cwg_wf_workspace_bytes", "cwg_wf_infer", "cwg_wf_infer_profiled", "cwg_wf_launch_count", "cwg_wf_layer",
            "cwg_denoise_workspace_bytes", "cwg_denoise_out_samples", "cwg_stft_mean_magnitude", "cwg_denoise", "cwg_pcm16",
            "cwg_conv1d", "cwg_conv_transpose1d", "cwg_resample1d", "cwg_deemphasis",
-           "cwg_fd_workspace_bytes", "cwg_fd_launch_count", "cwg_fd_inverse")
+           "cwg_fd_workspace_bytes", "cwg_fd_launch_count", "cwg_fd_inverse",
+           "cwg_axg_workspace_bytes", "cwg_axg_launch_count", "cwg_axg_flow", "cwg_group_transpose")
 
 
 class CwgError(RuntimeError):

@@ -6,6 +6,10 @@
 // orders of magnitude less work than the vocoder, so they are built as fp32 CUDA-core kernels on the reference's own
 // channels-first [B, C, T] layout: one implicit-GEMM conv kernel with four epilogues (store, accumulate, GTU gate, and
 // the W^-1 mixing as a 1x1 conv) plus the coupling update.  Exact fp32 semantics; no tensor-core mode is needed here.
+//
+// The same kernels serve the general fp32 mode of the ax vocoder's 1-D WN (cwg_axg_flow, include/cwg.h): the WN_config
+// variants of glow_ax.py:245-418 outside the packed layer kernels' specialisation - the 14 gated units of glow_ax.py:36-198,
+// listed dilations, merge_res_skip / res_skip=False, multi-layer cond stacks (evaluated by the caller).
 #include "cwg_common.cuh"
 
 namespace cwg {
@@ -16,13 +20,37 @@ constexpr int FBM = 64, FBN = 64, FBK = 16;
 struct FdConvP {
   int B, Cin, T, N, ks, dil;
   float pad_value;
+  int gate;                                   // EPI 2: CWG_GATE_* (0 = GTU)
   const float* x; long long x_bstride;        // x[b][ci][t] = x[b * x_bstride + ci * T + t]
   const float* w; const float* bias;          // w [rows][Cin][ks]; EPI 2 also reads rows n + N
   const float* add; long long add_bstride;    // EPI 2: cond slice [b][2N][t] added to the pre-activation
   float* y; long long y_bstride;              // y[b][n][t]
 };
 
-// EPI 0: y = conv + bias;  1: y += conv + bias;  2: y = tanh(pre[n]) * sigmoid(pre[n + N]), pre = conv + bias + add (GTU)
+// The gated units of glow_ax.py:36-166 on the two halves (a, b) of the pre-activation.  The SIREN variants scale the first
+// half by 16 in place before the sine (:113,:131,:140,:149); rrelu in eval mode is leaky_relu((lower + upper) / 2).
+__device__ __forceinline__ float gated_unit(int gate, float a, float b) {
+  float fa, fb;
+  switch (gate) {
+    case CWG_GATE_GLU: fa = a; break;
+    case CWG_GATE_GTSU: case CWG_GATE_GTSRU: fa = a - tanhf(a); break;
+    case CWG_GATE_GSIU: fa = sinf(a); break;
+    case CWG_GATE_GSIRU: case CWG_GATE_GSIRRU: case CWG_GATE_GSIRLRU: case CWG_GATE_GSIRRLRU: fa = sinf(16.f * a); break;
+    default: fa = tanhf(a);
+  }
+  switch (gate) {
+    case CWG_GATE_GTRU: case CWG_GATE_GTSRU: case CWG_GATE_GSIRRU: fb = fmaxf(b, 0.f); break;
+    case CWG_GATE_GTLRU: case CWG_GATE_GSIRLRU: fb = b > 0.f ? b : 0.01f * b; break;
+    case CWG_GATE_GSIRRLRU: fb = b > 0.f ? b : 0.055f * b; break;
+    case CWG_GATE_TTU: fb = tanhf(b); break;
+    case CWG_GATE_STU: fb = 1.0507009873554804934f * (b > 0.f ? b : 1.6732632423543772848f * expm1f(b)); break;
+    case CWG_GATE_SPTU: fb = b > 20.f ? b : log1pf(expf(b)); break;
+    default: fb = 1.f / (1.f + expf(-b));
+  }
+  return fa * fb;
+}
+
+// EPI 0: y = conv + bias;  1: y += conv + bias;  2: y = gated_unit(pre[n], pre[n + N]), pre = conv + bias + add
 template <int EPI>
 __global__ void __launch_bounds__(256) k_fd_conv(FdConvP p) {
   __shared__ float As[FBK][FBM + 4];
@@ -89,21 +117,41 @@ __global__ void __launch_bounds__(256) k_fd_conv(FdConvP p) {
         const float* ad = p.add + (size_t)b * p.add_bstride + t;
         const float pa = v + __ldg(ad + (size_t)n * p.T);
         const float pb = acg[i][j] + __ldg(p.bias + n + p.N) + __ldg(ad + (size_t)(n + p.N) * p.T);
-        *yo = tanhf(pa) * (1.f / (1.f + expf(-pb)));                   // GTU, glow.py:33-40
+        *yo = gated_unit(p.gate, pa, pb);                               // GTU: glow.py:33-40
       }
     }
   }
 }
 
 // z1 = (z1 - t) / exp(log_s), e = [log_s | t] (WN returns end(output).chunk(2, 1); modules.py:43-46)
-__global__ void k_fd_coupling(float* __restrict__ z1, long long z_bstride, const float* __restrict__ e, int B, int n_half, int T) {
+__global__ void k_fd_coupling(float* __restrict__ z1, long long z_bstride, const float* __restrict__ e, int B, int n_half, int T,
+                              int ignore_nan = 0) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * n_half * T) return;
   const int t = (int)(i % T); const long long bc = i / T;
   const int c = (int)(bc % n_half), b = (int)(bc / n_half);
   const float log_s = e[((size_t)b * 2 * n_half + c) * T + t], tt = e[((size_t)b * 2 * n_half + n_half + c) * T + t];
   float* zp = z1 + (size_t)b * z_bstride + (size_t)c * T + t;
-  *zp = (*zp - tt) / expf(log_s);
+  float v = (*zp - tt) / expf(log_s);
+  if (ignore_nan && v != v) v = 0.f;                                 // efficient_model_ax.py:331-332
+  *zp = v;
+}
+
+// z.view(B, -1, G).transpose(1, 2) and back: 32 x 32 tiles through shared memory
+__global__ void k_axg_transpose(const float* __restrict__ in, float* __restrict__ out, int T, int G, int to_cf) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+  const float* ib = in + (size_t)b * T * G; float* ob = out + (size_t)b * T * G;
+  // channels-last element (t, g) = [t * G + g]; channels-first = [g * T + t]
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    if (to_cf) { const int t = t0 + r, g = g0 + threadIdx.x; if (t < T && g < G) tile[r][threadIdx.x] = ib[(size_t)t * G + g]; }
+    else       { const int g = g0 + r, t = t0 + threadIdx.x; if (t < T && g < G) tile[r][threadIdx.x] = ib[(size_t)g * T + t]; }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    if (to_cf) { const int g = g0 + r, t = t0 + threadIdx.x; if (t < T && g < G) ob[(size_t)g * T + t] = tile[threadIdx.x][r]; }
+    else       { const int t = t0 + r, g = g0 + threadIdx.x; if (t < T && g < G) ob[(size_t)t * G + g] = tile[threadIdx.x][r]; }
+  }
 }
 
 __global__ void k_fd_add(float* __restrict__ y, const float* __restrict__ x, long long n) {
@@ -142,6 +190,27 @@ void carve(const cwg_fd_config* c, int B, int T, void* base, FdWs* ws) {
   const size_t BT = (size_t)B * T;
   ws->z2 = take(BT * c->n_group); ws->h = take(BT * c->n_channels); ws->out = take(BT * c->n_channels);
   ws->acts = take(BT * c->n_channels); ws->c_all = take(BT * 2 * c->n_channels * c->n_layers); ws->e = take(BT * c->n_group);
+  ws->bytes = off;
+}
+
+int axg_check(const cwg_axg_config* c, int batch, int T) {
+  CWG_REQUIRE(c != nullptr, "cfg is NULL");
+  CWG_REQUIRE(c->n_group >= 2 && c->n_rem >= 2 && c->n_rem % 2 == 0 && c->n_rem <= c->n_group, "bad n_group / n_rem");
+  CWG_REQUIRE(c->n_layers >= 1 && c->n_layers <= CWG_FD_MAX_LAYERS && c->n_channels >= 1 && c->kernel_size % 2 == 1, "bad WN settings");
+  CWG_REQUIRE(c->res_skip || c->merge_res_skip || c->n_layers == 1, "cannot remove res_skip without merge_res_skip (glow_ax.py:259)");
+  CWG_REQUIRE(c->gate >= 0 && c->gate < CWG_GATE_COUNT, "unknown gated unit %d", c->gate);
+  for (int i = 0; i < c->n_layers; ++i) CWG_REQUIRE(c->dilations[i] >= 1, "dilations must be >= 1");
+  CWG_REQUIRE(batch >= 1 && T >= 1, "batch and T must be >= 1");
+  return 0;
+}
+
+struct AxgWs { float *z2, *h, *out, *acts, *e; size_t bytes; };
+void axg_carve(const cwg_axg_config* c, int B, int T, void* base, AxgWs* ws) {
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n * sizeof(float), 256); return (float*)((char*)base + o); };
+  const size_t BT = (size_t)B * T;
+  ws->z2 = take(BT * c->n_group); ws->h = take(BT * c->n_channels); ws->out = take(BT * c->n_channels);
+  ws->acts = take(BT * c->n_channels); ws->e = take(BT * c->n_group);
   ws->bytes = off;
 }
 
@@ -260,6 +329,94 @@ int cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const floa
     if (cfg->mix_first) { if (int r = mix(k)) return r; }
   }
   if (cur != z) CWG_CHECK_CUDA(cudaMemcpyAsync(z, cur, (size_t)B * G * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+size_t cwg_axg_workspace_bytes(const cwg_axg_config* cfg, int batch, int t_steps) {
+  if (axg_check(cfg, batch, t_steps)) return 0;
+  AxgWs ws;
+  axg_carve(cfg, batch, t_steps, nullptr, &ws);
+  return ws.bytes;
+}
+
+int cwg_axg_launch_count(const cwg_axg_config* cfg) {
+  if (axg_check(cfg, 1, 1)) return -1;
+  const bool split = cfg->res_skip && !cfg->merge_res_skip;
+  return 2 /* mix + copy-back */ + 2 /* start, memset */ + cfg->n_layers * 2 + (split ? cfg->n_layers - 1 : 0) + 2 /* end, coupling */;
+}
+
+// One flow of efficient_model_ax.py:325-340 with glow_ax.WN.forward :375-418 in the general form.
+int cwg_axg_flow(const cwg_axg_config* cfg, const cwg_axg_weights* w, const float* c_all, float* z,
+                 void* workspace, size_t workspace_bytes, int batch, int t_steps, void* cuda_stream) {
+  if (int r = axg_check(cfg, batch, t_steps)) return r;
+  CWG_REQUIRE(w && c_all && z && workspace, "NULL argument");
+  CWG_REQUIRE(w->start_w && w->start_b && w->in_w && w->in_b && w->end_w && w->end_b && w->winv, "missing weight arrays");
+  CWG_REQUIRE(!cfg->res_skip || (w->rs_w && w->rs_b), "res_skip weights missing");
+  AxgWs ws;
+  axg_carve(cfg, batch, t_steps, workspace, &ws);
+  CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const int B = batch, T = t_steps, G = cfg->n_group, C = cfg->n_channels, L = cfg->n_layers, ks = cfg->kernel_size;
+  const int n_rem = cfg->n_rem, nh = n_rem / 2, off = G - n_rem;
+  const long long zb = (long long)G * T, cb = (long long)C * T;
+  auto mix = [&]() -> int {                          // InvertibleConv1x1.inverse / PermuteHeight.inverse over the active rows
+    FdConvP p{};
+    p.B = B; p.Cin = n_rem; p.T = T; p.N = n_rem; p.ks = 1; p.dil = 1;
+    p.x = z + (size_t)off * T; p.x_bstride = zb; p.w = w->winv; p.bias = nullptr;
+    p.y = ws.z2 + (size_t)off * T; p.y_bstride = zb;
+    if (int r = conv<0>(p, s)) return r;
+    CWG_CHECK_CUDA(cudaMemcpy2DAsync(z + (size_t)off * T, (size_t)zb * sizeof(float), ws.z2 + (size_t)off * T, (size_t)zb * sizeof(float),
+                                     (size_t)n_rem * T * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  };
+  if (!cfg->mix_first) { if (int r = mix()) return r; }
+  FdConvP p{};
+  p.B = B; p.T = T; p.dil = 1; p.Cin = nh; p.N = C; p.ks = 1; p.x = z + (size_t)off * T; p.x_bstride = zb;
+  p.w = w->start_w; p.bias = w->start_b; p.y = ws.h; p.y_bstride = cb;
+  if (int r = conv<0>(p, s)) return r;                                              // glow_ax.py:376
+  CWG_CHECK_CUDA(cudaMemsetAsync(ws.out, 0, (size_t)B * C * T * sizeof(float), s));
+  const bool split = cfg->res_skip && !cfg->merge_res_skip;
+  for (int i = 0; i < L; ++i) {
+    FdConvP g{};
+    g.B = B; g.T = T; g.Cin = C; g.N = C; g.ks = ks; g.dil = cfg->dilations[i]; g.gate = cfg->gate;
+    g.x = ws.h; g.x_bstride = cb; g.w = w->in_w + (size_t)i * 2 * C * C * ks; g.bias = w->in_b + (size_t)i * 2 * C;
+    g.add = c_all + (size_t)2 * C * i * T; g.add_bstride = (long long)2 * C * L * T;
+    g.y = ws.acts; g.y_bstride = cb;
+    if (int r = conv<2>(g, s)) return r;                                            // :394-397
+    if (cfg->res_skip) {
+      FdConvP q{};
+      q.B = B; q.T = T; q.Cin = C; q.N = C; q.ks = 1; q.dil = 1; q.x = ws.acts; q.x_bstride = cb;
+      q.w = w->rs_w + (size_t)i * 2 * C * C; q.bias = w->rs_b + (size_t)i * 2 * C; q.y_bstride = cb;
+      if (split && i < L - 1) {                                                     // :402-404, :409-411
+        q.y = ws.h; if (int r = conv<1>(q, s)) return r;
+        q.w += (size_t)C * C; q.bias += C;
+      }
+      q.y = ws.out; if (int r = conv<1>(q, s)) return r;                            // :406, :413 (merged: the hidden tensor stays)
+    } else {
+      const long long n = (long long)B * C * T;                                     // :399: res_skip_acts = acts
+      k_fd_add<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.out, ws.acts, n);
+      CWG_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  FdConvP e{};
+  e.B = B; e.T = T; e.Cin = C; e.N = 2 * nh; e.ks = 1; e.dil = 1; e.x = ws.out; e.x_bstride = cb;
+  e.w = w->end_w; e.bias = w->end_b; e.y = ws.e; e.y_bstride = (long long)2 * nh * T;
+  if (int r = conv<0>(e, s)) return r;                                              // :418
+  {
+    const long long n = (long long)B * nh * T;
+    k_fd_coupling<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z + (size_t)(off + nh) * T, zb, ws.e, B, nh, T, cfg->ignore_nan);
+    CWG_CHECK_CUDA(cudaGetLastError());
+  }
+  if (cfg->mix_first) { if (int r = mix()) return r; }
+  return 0;
+}
+
+int cwg_group_transpose(const float* in, float* out, int batch, int t_steps, int n_group, int to_channels_first, void* cuda_stream) {
+  CWG_REQUIRE(in && out && in != out, "in / out must be distinct device buffers");
+  CWG_REQUIRE(batch >= 1 && batch <= 65535 && t_steps >= 1 && n_group >= 1, "bad shape");
+  dim3 grid((unsigned)((t_steps + 31) / 32), (unsigned)((n_group + 31) / 32), (unsigned)batch);
+  k_axg_transpose<<<grid, dim3(32, 8), 0, (cudaStream_t)cuda_stream>>>(in, out, t_steps, n_group, to_channels_first);
+  CWG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -14,10 +14,18 @@ Also covered: `n_group` up to 32 (wide group padding, include/cwg.h CWG_GROUP_PA
 cwg_ax_speaker_bias) and `upsample_first=False` (glow_ax.py:389: the WN interpolates its cond-layer output; with the
 one linear 1x1 cond layer required here that equals contracting the interpolated cond input, which is what the kernels
 do) - together the model of the reference's speed-test notebook (`synthetic.notebook_ax_kwargs`).
+
+WN_config variants outside that specialisation run in the GENERAL fp32 mode (`cwg_axg_flow`, csrc/cwg_fd.cu - CUDA-core
+implicit-GEMM convs on the reference's channels-first layout, one C call per flow): every gated unit of glow_ax.py:36-198
+(`gated_unit`), listed dilations (`n_layers_dilations_w`, :331-335), `merge_res_skip` / `res_skip=False` (:259-263,:352,
+:399-414), WN cond stacks of several layers / kernel sizes / padding modes / activations (:297-329,:383-387; evaluated
+per flow with cwg_conv1d, interpolated with cwg_resample1d when `upsample_first=False`), any even n_group.  Such a model
+always computes in fp32 (`precision` is forced to "ffma" with a warning).
 """
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import Dict
 
 import numpy as np
@@ -25,7 +33,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .ax_frontend import AxFrontEndMixin
+from .ax_frontend import AxFrontEndMixin, _cond_act, PAD_MODES, ACT_NONE
 from .packing import in_layer_weight_bias, split_f16, f8_correction_planes, PackConfig, split_hi_lo, effective_weight, _np, MAX_GROUP, group_pad
 
 
@@ -114,10 +122,58 @@ def pack_ax_state_dict(sd, pc: PackConfig, channel_mixing: str, planes=("hi", "l
     return out
 
 
+# glow_ax.py:168-198 get_gate_func names -> CWG_GATE_* (include/cwg.h)
+GATED_UNITS = {"GTU": 0, "GTRU": 1, "GTLRU": 2, "GLU": 3, "TTU": 4, "STU": 5, "GTSU": 6, "SPTU": 7, "GSIU": 8, "GSIRU": 9,
+               "GTSRU": 10, "GSIRRU": 11, "GSIRLRU": 12, "GSIRRLRU": 13}
+MAX_GENERAL_LAYERS = 16          # CWG_FD_MAX_LAYERS
+
+
+class CwgAxgConfig(C.Structure):
+    """cwg_axg_config (include/cwg.h)"""
+    _fields_ = ([(n, C.c_int32) for n in ("n_group", "n_rem", "mix_first", "n_layers", "n_channels", "kernel_size")]
+                + [("dilations", C.c_int32 * MAX_GENERAL_LAYERS)]
+                + [(n, C.c_int32) for n in ("res_skip", "merge_res_skip", "gate", "ignore_nan")])
+
+
+AXG_WEIGHT_FIELDS = ("start_w", "start_b", "in_w", "in_b", "rs_w", "rs_b", "end_w", "end_b", "winv")
+
+
+class CwgAxgWeights(C.Structure):
+    """cwg_axg_weights (include/cwg.h)"""
+    _fields_ = [(n, C.c_void_p) for n in AXG_WEIGHT_FIELDS]
+
+
+def pack_ax_general(sd, k: int, n_rem: int, n_layers: int, n_channels: int, kernel_size: int, res_skip: bool,
+                    channel_mixing: str) -> Dict[str, np.ndarray]:
+    """fp32 arrays of `cwg_axg_weights` for flow k (weight-norm folded, separable in_layers folded to dense)."""
+    Cc, L, ks, p = n_channels, n_layers, kernel_size, f"WN.{k}.WN."
+    in_w = np.zeros((L, 2 * Cc, Cc, ks)); in_b = np.zeros((L, 2 * Cc))
+    rs_w = np.zeros((L, 2 * Cc, Cc)); rs_b = np.zeros((L, 2 * Cc))
+    for i in range(L):
+        in_w[i], in_b[i] = in_layer_weight_bias(sd, p + f"in_layers.{i}")
+        if res_skip:
+            w = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0]
+            rs_w[i, :w.shape[0]] = w
+            rs_b[i, :w.shape[0]] = _np(sd[p + f"res_skip_layers.{i}.bias"])
+    if channel_mixing == "permuteheight":
+        winv = np.zeros((n_rem, n_rem))
+        for c, src in enumerate(permute_height_index(k, n_rem)):
+            winv[c, src] = 1.0
+    else:
+        winv = np.linalg.inv(_np(sd[f"convinv.{k}.weight"]).reshape(n_rem, n_rem))
+    out = {"start_w": effective_weight(sd, p + "start")[:, :, 0], "start_b": _np(sd[p + "start.bias"]), "in_w": in_w, "in_b": in_b,
+           "end_w": _np(sd[p + "end.weight"])[:, :, 0], "end_b": _np(sd[p + "end.bias"]), "winv": winv}
+    if res_skip:
+        out["rs_w"], out["rs_b"] = rs_w, rs_b
+    return {n: np.ascontiguousarray(a, dtype=np.float32) for n, a in out.items()}
+
+
 class _WN1d(nn.Module):
     """Parameter holder with the layout of glow_ax.py:245-373 (supported subset)."""
 
-    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels, seperable_conv=False, speaker_embed_dim=0):
+    def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels, seperable_conv=False, speaker_embed_dim=0,
+                 dilations=None, res_skip=True, merge_res_skip=False, cond_layers=1, cond_hidden_channels=256,
+                 cond_kernel_size=1, cond_padding_mode="zeros"):
         super().__init__()
         wn = nn.utils.weight_norm
         cond_in_channels += speaker_embed_dim                # glow_ax.py:255
@@ -126,7 +182,7 @@ class _WN1d(nn.Module):
         self.in_layers = nn.ModuleList()
         self.res_skip_layers = nn.ModuleList()
         for i in range(n_layers):
-            d = 2 ** i
+            d = 2 ** i if dilations is None else dilations[i]
             pad = (kernel_size * d - d) // 2
             if not seperable_conv or kernel_size == 1:
                 self.in_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels, kernel_size, dilation=d, padding=pad), name="weight"))
@@ -134,11 +190,18 @@ class _WN1d(nn.Module):
                 self.in_layers.append(nn.Sequential(
                     wn(nn.Conv1d(n_channels, n_channels, kernel_size, dilation=d, padding=pad, groups=n_channels), name="weight"),
                     wn(nn.Conv1d(n_channels, 2 * n_channels, 1), name="weight")))
-            self.res_skip_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels if i < n_layers - 1 else n_channels, 1), name="weight"))
+            if res_skip:                                     # glow_ax.py:352-362
+                wide = i < n_layers - 1 and not merge_res_skip
+                self.res_skip_layers.append(wn(nn.Conv1d(n_channels, 2 * n_channels if wide else n_channels, 1), name="weight"))
         self.start = wn(nn.Conv1d(n_in, n_channels, 1), name="weight")
         self.end = nn.Conv1d(n_channels, 2 * n_in, 1)
         self.end.weight.data.zero_(); self.end.bias.data.zero_()
-        self.cond_layers = nn.ModuleList([wn(nn.Conv1d(cond_in_channels, 2 * n_channels * n_layers, 1), name="weight")])
+        if cond_layers:                                      # glow_ax.py:297-314
+            kc = 2 * cond_kernel_size - 1
+            dims = [cond_in_channels] + [cond_hidden_channels] * (cond_layers - 1) + [2 * n_channels * n_layers]
+            self.cond_layers = nn.ModuleList([
+                wn(nn.Conv1d(di, do, kc, padding=(kc - 1) // 2, padding_mode=cond_padding_mode), name="weight")
+                for di, do in zip(dims[:-1], dims[1:])])
 
 
 class _Coupling(nn.Module):
@@ -192,13 +255,41 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         need(upsample_first is True or not transposed_conv_scales,
              "upsample_first=False with a model-level TransposedUpsampleNet (the reference never calls it there)")
         self.wn_speaker_embed_dim = int(wn.get("speaker_embed_dim", 0) or 0)
-        need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1 and wn.get("cond_activation_func", "none") == "none",
-             "WN cond_layers must be one linear 1x1 conv")
-        need(not wn.get("merge_res_skip") and wn.get("res_skip", True), "merged / absent res_skip variants are not supported")
-        need(wn.get("gated_unit", "GTU") == "GTU" and wn.get("n_layers_dilations_w") is None, "only the GTU gate with 2^i dilations is supported")
+        # ---- WN_config variants: anything outside the packed layer kernels' specialisation (one linear 1x1 cond layer, GTU,
+        # 2^i dilations, split res_skip) runs in the general fp32 mode, cwg_axg_flow
+        gate = str(wn.get("gated_unit", "GTU")).upper()
+        need(gate in GATED_UNITS, "gated_unit is invalid (glow_ax.py:168-198)")
+        L = int(wn["n_layers"])
+        dil = wn.get("n_layers_dilations_w")
+        if isinstance(dil, int):
+            dil = [dil] * L                                  # glow_ax.py:331-333
+        need(dil is None or (len(dil) >= L and all(int(d) >= 1 for d in dil[:L])), "n_layers_dilations_w needs one dilation >= 1 per layer")
+        self._dilations = None if dil is None else [int(d) for d in dil[:L]]
+        if self._dilations == [2 ** i for i in range(L)]:
+            self._dilations = None
+        self._res_skip, self._merge = bool(wn.get("res_skip", True)), bool(wn.get("merge_res_skip", False))
+        if not (self._res_skip or self._merge or L == 1):
+            raise AssertionError("Cannot remove res_skip without using merge_res_skip")      # glow_ax.py:259
+        self._wn_cond = dict(layers=int(wn.get("cond_layers", 1) or 0), hidden=int(wn.get("cond_hidden_channels", 256)),
+                             kernel_size=int(wn.get("cond_kernel_size", 1)), padding_mode=wn.get("cond_padding_mode", "zeros"),
+                             act=_cond_act(wn.get("cond_activation_func", "none"), wn.get("negative_slope")) if wn.get("cond_layers", 1) else (ACT_NONE, 0.0),
+                             out_act=bool(wn.get("cond_out_activation_func", True)))
+        need(self._wn_cond["padding_mode"] in PAD_MODES, "WN cond_padding_mode must be zeros / replicate / reflect / circular")
+        linear_cond = self._wn_cond["layers"] == 1 and self._wn_cond["kernel_size"] == 1 and self._wn_cond["act"][0] == ACT_NONE
+        self._gate = GATED_UNITS[gate]
+        self.general = bool(self._gate or self._dilations is not None or self._merge or not self._res_skip or not linear_cond
+                            or n_group > MAX_GROUP)
+        need(not self.general or L <= MAX_GENERAL_LAYERS, f"the general fp32 mode takes <= {MAX_GENERAL_LAYERS} WN layers")
+        if self.general and precision != "ffma":
+            warnings.warn(f"cookietts_b200.WaveGlowAx: this WN_config (gated_unit {gate}, dilations {self._dilations}, "
+                          f"merge_res_skip {self._merge}, res_skip {self._res_skip}, cond stack {self._wn_cond['layers']} x "
+                          f"k{2 * self._wn_cond['kernel_size'] - 1}) runs in the general fp32 CUDA-core mode; precision "
+                          f"'{precision}' -> 'ffma'")
+            precision = "ffma"
         need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
         ks = wn.get("kernel_size_w") or wn.get("kernel_size")
-        need(hop_length % n_group == 0 and n_group <= MAX_GROUP, f"hop_length % n_group == 0 and n_group <= {MAX_GROUP}")
+        need(hop_length % n_group == 0 and n_group % 2 == 0 and (n_group <= MAX_GROUP or self.general),
+             f"hop_length % n_group == 0, n_group even and <= {MAX_GROUP}")
         need(n_group <= 16 or precision == "ffma" or wn["n_channels"] == 256,
              "n_group > 16 runs in precision='ffma' or, for 256 WN channels, on the tensor-core kernels")
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
@@ -213,7 +304,9 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                           n_early_size=n_early_size, win_length=hop_length, hop_length=hop_length,
                           n_layers=wn["n_layers"], n_channels=wn["n_channels"], kernel_size=ks)
         pc = PackConfig(cond_hidden=cond_channels, **self._base)
-        pc.validate()
+        if not self.general:
+            pc.validate()
+        need(pc.flow_channels()[-1][1] >= 1, "too many early outputs for n_group")
         self.WN = nn.ModuleList()
         self.convinv = nn.ModuleList() if self.channel_mixing == "1x1conv" else []
         for n_rem, n_half in pc.flow_channels():
@@ -222,7 +315,10 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             self.WN.append(_Coupling(n_in=n_half, n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                      kernel_size=ks, cond_in_channels=self.wn_cond_in_channels,
                                      seperable_conv=bool(wn.get("seperable_conv")),
-                                     speaker_embed_dim=self.wn_speaker_embed_dim))
+                                     speaker_embed_dim=self.wn_speaker_embed_dim, dilations=self._dilations,
+                                     res_skip=self._res_skip, merge_res_skip=self._merge, cond_layers=self._wn_cond["layers"],
+                                     cond_hidden_channels=self._wn_cond["hidden"], cond_kernel_size=self._wn_cond["kernel_size"],
+                                     cond_padding_mode=self._wn_cond["padding_mode"]))
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -254,6 +350,8 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         if self._packed is not None and self._packed_key == key:
             return
         dev = self._device()
+        if self.general:
+            return self._ensure_packed_general(dev, key)
         tensor = self.precision != "ffma"
         # tensor-core kernels are built for a 256-wide cond operand; the fp32 path takes it unpadded
         pc = PackConfig(cond_hidden=256 if tensor else self._base["n_mel"], **self._base)
@@ -274,6 +372,106 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         self._ccfg = _cabi.make_config(pc)
         self._packed, self._packed_key, self._cw, self._graphs = dev_pk, key, w, {}
 
+    # ------------------------------------------------------------------ general fp32 mode (cwg_axg_flow)
+    def _ensure_packed_general(self, dev, key):
+        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
+        b = self._base
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        flows = []
+        pc = PackConfig(cond_hidden=b["n_mel"], **b)
+        dil = self._dilations or [2 ** i for i in range(b["n_layers"])]
+        for k, (n_rem, n_half) in enumerate(pc.flow_channels()):
+            arrs = {n: up(a) for n, a in pack_ax_general(sd, k, n_rem, b["n_layers"], b["n_channels"], b["kernel_size"],
+                                                         self._res_skip, self.channel_mixing).items()}
+            w = CwgAxgWeights()
+            for f in AXG_WEIGHT_FIELDS:
+                setattr(w, f, arrs[f].data_ptr() if f in arrs else None)
+            cfg = CwgAxgConfig(n_group=b["n_group"], n_rem=n_rem, mix_first=int(self.mix_first), n_layers=b["n_layers"],
+                               n_channels=b["n_channels"], kernel_size=b["kernel_size"], res_skip=int(self._res_skip),
+                               merge_res_skip=int(self._merge), gate=self._gate, ignore_nan=1)
+            for i, d in enumerate(dil):
+                cfg.dilations[i] = d
+            p = f"WN.{k}.WN."
+            cond = [(up(effective_weight(sd, p + f"cond_layers.{i}")), up(sd[p + f"cond_layers.{i}.bias"]))
+                    for i in range(self._wn_cond["layers"])]
+            emb = up(sd[p + "speaker_embed.weight"]) if self.wn_speaker_embed_dim else None
+            group = None
+            if self._fe_group:                                # flow k's slice of n_flow_group_conv, applied explicitly here
+                wg, bg = self.group_conv_fold(k, np.eye(self._fe_group[0]), np.zeros(self._fe_group[0]), sd)
+                group = (up(wg[:, :, None]), up(bg))
+            flows.append(dict(cfg=cfg, w=w, arrs=arrs, cond=cond, emb=emb, group=group))
+        self.pack_config = pc
+        self._packed, self._packed_key, self._graphs = {"flows": flows}, key, {}
+
+    def _bind_general(self):
+        lib = _cabi.load()
+        if not getattr(lib, "_axg_bound", False):
+            lib.cwg_axg_workspace_bytes.restype = C.c_size_t
+            lib.cwg_axg_workspace_bytes.argtypes = [C.POINTER(CwgAxgConfig), C.c_int, C.c_int]
+            lib.cwg_axg_flow.restype = C.c_int
+            lib.cwg_axg_flow.argtypes = [C.POINTER(CwgAxgConfig), C.POINTER(CwgAxgWeights), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+            lib.cwg_group_transpose.restype = C.c_int
+            lib.cwg_group_transpose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            lib._axg_bound = True
+        return lib
+
+    def _resample(self, lib, x, t_out, stream):
+        """F.interpolate(x, size=t_out, mode, align_corners=True for 'linear') - efficient_model_ax.py:175, glow_ax.py:365"""
+        B, ch, t_in = x.shape
+        y = torch.empty(B, ch, t_out, device=x.device, dtype=torch.float32)
+        _cabi.check(lib.cwg_resample1d(x.data_ptr(), B, ch, t_in, ch * t_in, y.data_ptr(), t_out, ch * t_out,
+                                       1 if self.upsample_linear else 0, t_out, 0, 0.0, 0, stream))
+        return y
+
+    def _run_general(self, z, cond, ids):
+        """The inverse pass in the general fp32 mode: front-end, then per flow (last to first) the WN's own cond stack
+        (glow_ax.py:378-389) and one cwg_axg_flow call (mixing, WN, coupling, ignore_nan)."""
+        dev = z.device
+        lib = self._bind_general()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        B, T = z.shape
+        G = self.n_group
+        Tp = T // G
+        cond = self._fe_apply(cond, ids, Tp)
+        if self.upsample_first and cond.shape[2] != Tp:      # efficient_model_ax.py:313-314 (the upsample net already ran)
+            cond = self._resample(lib, cond, Tp, stream)
+        flows = self._packed["flows"]
+        nbytes = max(lib.cwg_axg_workspace_bytes(C.byref(f["cfg"]), B, Tp) for f in flows)
+        if nbytes == 0:
+            raise _cabi.CwgError(lib.cwg_last_error().decode())
+        if self._workspace is None or self._workspace.numel() < nbytes + 1024 or self._workspace.device != dev:
+            self._workspace = None
+            self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+        ws_bytes = self._workspace.numel() - (ws_ptr - self._workspace.data_ptr())
+        zc = torch.empty(B, G, Tp, device=dev, dtype=torch.float32)
+        _cabi.check(lib.cwg_group_transpose(z.data_ptr(), zc.data_ptr(), B, Tp, G, 1, stream))
+        wc = self._wn_cond
+        pad, pad_mode = (2 * wc["kernel_size"] - 2) // 2, PAD_MODES[wc["padding_mode"]]
+        act, slope = wc["act"]
+        for k in range(self.n_flows - 1, -1, -1):            # efficient_model_ax.py:325
+            f = flows[k]
+            x = cond
+            if f["group"] is not None:                       # :316-317,:328
+                x = self._conv1d(lib, x, *f["group"], 0, 0, ACT_NONE, 0.0)
+            if f["emb"] is not None:                         # glow_ax.py:378-381
+                x = torch.cat([x, f["emb"][ids][:, :, None].expand(-1, -1, x.shape[2])], dim=1).contiguous()
+            n = len(f["cond"])
+            for i, (w, b) in enumerate(f["cond"]):           # :383-387
+                a = act if (wc["out_act"] or i != n - 1) else ACT_NONE
+                x = self._conv1d(lib, x, w, b, pad, pad_mode, a, slope)
+            if not self.upsample_first and x.shape[2] != Tp:   # :389, _upsample_mels :361-373 without a WN upsample net
+                x = self._resample(lib, x, Tp, stream)
+            need_ch = 2 * self._base["n_channels"] * self._base["n_layers"]
+            if x.shape[1] != need_ch or x.shape[2] != Tp:
+                raise RuntimeError(f"WN {k}: cond stack output {tuple(x.shape)} != [B, {need_ch}, {Tp}]")
+            _cabi.check(lib.cwg_axg_flow(C.byref(f["cfg"]), C.byref(f["w"]), x.data_ptr(), zc.data_ptr(), ws_ptr, ws_bytes,
+                                         B, Tp, stream))
+        audio = torch.empty(B, T, device=dev, dtype=torch.float32)
+        _cabi.check(lib.cwg_group_transpose(zc.data_ptr(), audio.data_ptr(), B, Tp, G, 0, stream))
+        return self._fe_post(audio), None
+
     def _bind(self):
         lib = _cabi.load()
         if not getattr(lib, "_ax_bound", False):
@@ -293,6 +491,8 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         """Every launch of one inverse pass on the current stream, no host synchronisation (CUDA-graph capturable once the
         workspace exists): conditioning front-end, per-utterance speaker bias, flows, output filters.
         Returns (audio [B, T] on the device, status word tensor or None)."""
+        if self.general:
+            return self._run_general(z, cond, ids)
         dev = z.device
         lib = self._bind()
         mode = _cabi.MODES[self.precision]
@@ -387,7 +587,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             # repeated small shapes are launch-latency bound (one tile pair per layer): replay them as a CUDA graph from
             # their second occurrence on, like cookietts_b200.WaveGlow
             gkey = (tuple(z.shape), tuple(cond.shape), self.precision)
-            use_graph = (not capturing and (self.graphs is True or
+            use_graph = (not capturing and not self.general and (self.graphs is True or
                                             (self.graphs == "auto" and B * (T // self.n_group) <= self.GRAPH_MAX_STEPS)))
             if use_graph and self.graphs == "auto" and gkey not in self._graph_seen:
                 if len(self._graph_seen) > 64:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CWG_ABI_VERSION 4
+#define CWG_ABI_VERSION 5
 
 /* Arithmetic modes of the WN contractions. */
 #define CWG_MODE_FFMA   0   /* fp32 weights/activations, CUDA-core FFMA (exact fp32 semantics)        */
@@ -401,6 +401,69 @@ size_t cwg_fd_workspace_bytes(const cwg_fd_config* cfg, int batch, int t_steps);
 int    cwg_fd_launch_count(const cwg_fd_config* cfg);
 int    cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const float* cond, float* z,
                       void* workspace, size_t workspace_bytes, int batch, int t_steps, void* cuda_stream);
+
+/* =====================================================================================
+ * General fp32 mode of the ax 1-D WN (glow_ax.py:245-418) for the WN_config variants the packed tensor-core / FFMA layer
+ * kernels are not specialised for: any of the 14 gated units of glow_ax.py:36-198, listed dilations
+ * (n_layers_dilations_w, :331-335), merge_res_skip / res_skip=False (:259-263,:352,:399-414: the hidden tensor is then
+ * never updated and every layer's res_skip output is accumulated), and WN cond stacks of several layers / activations /
+ * kernel sizes (:297-329) - the caller evaluates the cond stack (cwg_conv1d, cwg_resample1d) and hands over its output
+ * c_all [batch][2*C*L][T'].  One call = one flow of WaveGlow.inverse (efficient_model_ax.py:325-340): channel mixing
+ * (before or after, mix_first), WN, AffineCouplingBlock.inverse (efficient_modules.py:99-105), ignore_nan.
+ * z is the reference's channels-first view [batch][n_group][T'] (cwg_group_transpose converts from / to [batch][T]),
+ * updated in place; the active channels of the flow are the trailing n_rem rows.
+ * ===================================================================================== */
+#define CWG_GATE_GTU      0   /* tanh * sigmoid          */
+#define CWG_GATE_GTRU     1   /* tanh * relu             */
+#define CWG_GATE_GTLRU    2   /* tanh * leaky_relu(0.01) */
+#define CWG_GATE_GLU      3   /* x * sigmoid             */
+#define CWG_GATE_TTU      4   /* tanh * tanh             */
+#define CWG_GATE_STU      5   /* tanh * selu             */
+#define CWG_GATE_GTSU     6   /* tanhshrink * sigmoid    */
+#define CWG_GATE_SPTU     7   /* tanh * softplus         */
+#define CWG_GATE_GSIU     8   /* sin * sigmoid           */
+#define CWG_GATE_GSIRU    9   /* sin(16 x) * sigmoid     */
+#define CWG_GATE_GTSRU    10  /* tanhshrink * relu       */
+#define CWG_GATE_GSIRRU   11  /* sin(16 x) * relu        */
+#define CWG_GATE_GSIRLRU  12  /* sin(16 x) * leaky_relu(0.01) */
+#define CWG_GATE_GSIRRLRU 13  /* sin(16 x) * rrelu(0.01, 0.1) in eval mode = leaky_relu(0.055) */
+#define CWG_GATE_COUNT    14
+
+typedef struct cwg_axg_config {
+  int32_t n_group;           /* rows of z                                               */
+  int32_t n_rem;             /* active (trailing) channels of this flow, even            */
+  int32_t mix_first;         /* 1: coupling then mixing, 0: mixing then coupling         */
+  int32_t n_layers, n_channels, kernel_size;
+  int32_t dilations[CWG_FD_MAX_LAYERS];
+  int32_t res_skip;          /* WN_config['res_skip']                                    */
+  int32_t merge_res_skip;    /* WN_config['merge_res_skip']                              */
+  int32_t gate;              /* CWG_GATE_*                                               */
+  int32_t ignore_nan;        /* efficient_model_ax.py:331-332                            */
+} cwg_axg_config;
+
+/* Device fp32 arrays of ONE flow, weight-norm folded, separable in_layers folded to dense (C = n_channels, L = n_layers,
+ * ks = kernel_size, n_half = n_rem / 2). */
+typedef struct cwg_axg_weights {
+  const float* start_w;   /* [C][n_half]                                                  */
+  const float* start_b;   /* [C]                                                          */
+  const float* in_w;      /* [L][2C][C][ks]                                               */
+  const float* in_b;      /* [L][2C]                                                      */
+  const float* rs_w;      /* [L][2C][C]  rows past a layer's res_skip width unused; NULL when res_skip = 0 */
+  const float* rs_b;      /* [L][2C]                                                      */
+  const float* end_w;     /* [2 n_half][C]   rows: log_s then t                           */
+  const float* end_b;     /* [2 n_half]                                                   */
+  const float* winv;      /* [n_rem][n_rem]  W^-1 (or the PermuteHeight permutation matrix), row major */
+} cwg_axg_weights;
+
+size_t cwg_axg_workspace_bytes(const cwg_axg_config* cfg, int batch, int t_steps);
+int    cwg_axg_launch_count(const cwg_axg_config* cfg);
+int    cwg_axg_flow(const cwg_axg_config* cfg, const cwg_axg_weights* w, const float* c_all, float* z,
+                    void* workspace, size_t workspace_bytes, int batch, int t_steps, void* cuda_stream);
+
+/* z.view(B, -1, n_group).transpose(1, 2) and back (efficient_model_ax.py:310,347): to_channels_first = 1 reads
+ * in [batch][T'][n_group] and writes out [batch][n_group][T']; 0 is the inverse. */
+int cwg_group_transpose(const float* in, float* out, int batch, int t_steps, int n_group, int to_channels_first,
+                        void* cuda_stream);
 
 #ifdef __cplusplus
 }

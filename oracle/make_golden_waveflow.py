@@ -71,10 +71,12 @@ CASES = {
 def reference_kwargs_ax1d(cfg) -> dict:
     """Constructor kwargs of the ax model with waveflow=False for an oracle.waveglow_ax_oracle.AxConfig."""
     wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size=cfg.kernel_size, kernel_size_w=None,
-              n_layers_dilations_w=None, n_layers_dilations_h=1, speaker_embed_dim=cfg.wn_speaker_embed_dim, rezero=False, cond_layers=1,
-              cond_activation_func="none", negative_slope=None, cond_hidden_channels=256, cond_kernel_size=1,
-              cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv, res_skip=True, merge_res_skip=False,
-              upsample_mode=cfg.upsample_mode)
+              n_layers_dilations_w=cfg.dilations_w, n_layers_dilations_h=1, speaker_embed_dim=cfg.wn_speaker_embed_dim, rezero=False,
+              cond_layers=cfg.wn_cond_layers, cond_activation_func=cfg.wn_cond_activation_func, negative_slope=cfg.wn_negative_slope,
+              cond_hidden_channels=cfg.wn_cond_hidden_channels, cond_kernel_size=cfg.wn_cond_kernel_size,
+              cond_padding_mode=cfg.wn_cond_padding_mode, seperable_conv=cfg.seperable_conv, res_skip=cfg.res_skip,
+              merge_res_skip=cfg.merge_res_skip, upsample_mode=cfg.upsample_mode, gated_unit=cfg.gated_unit,
+              cond_out_activation_func=cfg.wn_cond_out_activation_func)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size, memory_efficient=0.0,
                 spect_scaling=False, upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,
@@ -82,6 +84,9 @@ def reference_kwargs_ax1d(cfg) -> dict:
                 cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
                 sampling_rate=22050, channel_mixing=cfg.channel_mixing, mix_first=cfg.mix_first, waveflow=False)
 
+
+_V = dict(n_mel_channels=8, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, n_layers=3, n_channels=16,
+          win_length=64, hop_length=16)
 
 AX_CASES = {
     "waveglow_ax_tiny": (dict(n_mel_channels=8, n_flows=4, n_group=8, n_early_every=2, n_early_size=2, n_layers=3,
@@ -93,17 +98,42 @@ AX_CASES = {
                                  n_channels=8, win_length=64, hop_length=16, mix_first=False), 1, 6, 0.9, 33, 3),
     # the classic-sized model (12 flows, 8 x 256) in its ax form, short clip
     "waveglow_ax_256": (dict(), 1, 10, 0.666, 1234, 0),
+    # ---- WN_config variants served by the general fp32 mode (include/cwg.h cwg_axg_flow)
+    # the author's "best and fastest converging unit" (glow_ax.py:128), listed dilations, separable in_layers
+    "waveglow_axv_gsirru": (dict(_V, gated_unit="GSIRRU", dilations_w=[1, 3, 2], seperable_conv=True), 2, 7, 0.8, 61, 11),
+    # merged res_skip: the hidden tensor is never updated, every layer adds C channels to the output
+    "waveglow_axv_merge": (dict(_V, merge_res_skip=True, gated_unit="GTLRU", channel_mixing="permuteheight", mix_first=False),
+                           2, 6, 0.9, 62, 12),
+    # no res_skip layers at all (the gated activations are accumulated), constant dilation, softplus unit
+    "waveglow_axv_noskip": (dict(_V, res_skip=False, merge_res_skip=True, gated_unit="SPTU", dilations_w=2), 1, 8, 1.0, 63, 13),
+    # a 2-layer WN cond stack with 3-tap replicate-padded convs and LeakyReLU between (not after) the layers, at frame rate
+    # (upsample_first=False: the WN interpolates the stack's output), WN-level speaker embedding
+    "waveglow_axv_cond": (dict(_V, wn_cond_layers=2, wn_cond_hidden_channels=12, wn_cond_kernel_size=2,
+                               wn_cond_padding_mode="replicate", wn_cond_activation_func="relu", wn_negative_slope=0.3,
+                               wn_cond_out_activation_func=False, upsample_first=False, wn_speaker_embed_dim=5, gated_unit="GLU"),
+                          2, 7, 0.8, 64, 14),
+    # every remaining unit on one tiny model each (one flow pair, 2 layers)
+    **{f"waveglow_axv_unit_{u.lower()}": (dict(_V, n_flows=2, n_early_every=4, n_layers=2, gated_unit=u), 1, 5, 0.9, 70 + i, 20 + i)
+       for i, u in enumerate(["GTRU", "TTU", "STU", "GTSU", "GSIU", "GSIRU", "GTSRU", "GSIRLRU", "GSIRRLRU"])},
+    # the 8 x 256 model with the GSIRRU unit, merged res_skip and custom dilations (a realistic width through the general mode)
+    "waveglow_axv_256": (dict(n_flows=4, n_early_every=2, gated_unit="GSIU", merge_res_skip=True,
+                              dilations_w=[1, 2, 4, 8, 16, 32, 64, 1]), 1, 6, 0.666, 65, 15),
 }
 
 
-def main_ax(WaveGlowAx, outdir):
+def main_ax(WaveGlowAx, outdir, only=()):
     from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd
+    np.product = np.prod                                   # removed in numpy 2; the reference still calls it
     for name, (kw, batch, frames, sigma, wseed, iseed) in AX_CASES.items():
+        if only and name not in only:
+            continue
         cfg = AxConfig(**kw)
         sd = ax_sd(cfg, wseed)
         rs = np.random.RandomState(iseed)
         mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
         z = rs.standard_normal((batch, frames * cfg.hop_length)).astype(np.float32)
+        spk = rs.randint(0, 512, size=(batch,)).astype(np.int64) if cfg.wn_speaker_embed_dim else None
+        ids = torch.from_numpy(spk) if spk is not None else None
         outs = {}
         for dt, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
             model = WaveGlowAx(**reference_kwargs_ax1d(cfg))
@@ -113,16 +143,17 @@ def main_ax(WaveGlowAx, outdir):
                 for conv in model.convinv:        # W_inverse is always created fp32 (efficient_modules.py:271-275)
                     conv.W_inverse = conv.weight.squeeze().double().inverse().unsqueeze(-1)
             with torch.no_grad():
-                inv, _ = model.inverse(torch.from_numpy(z).to(dt) * sigma, torch.from_numpy(mel).to(dt))
+                inv, _ = model.inverse(torch.from_numpy(z).to(dt) * sigma, torch.from_numpy(mel).to(dt), speaker_ids=ids)
                 outs["inverse_" + tag] = inv.numpy()
                 with InjectedNormal([torch.from_numpy(z)]):
-                    aud = model.infer(torch.from_numpy(mel).to(dt), sigma=sigma)
+                    aud = model.infer(torch.from_numpy(mel).to(dt), speaker_ids=ids, sigma=sigma)
                 outs["infer_" + tag] = aud.numpy()
         e1 = np.abs(outs["inverse_fp32"] - outs["inverse_fp64"]).max()
         print(f"{name}: inverse {outs['inverse_fp64'].shape} infer {outs['infer_fp64'].shape} "
               f"rms {np.sqrt((outs['inverse_fp64'] ** 2).mean()):.3f} fp32-vs-fp64 {e1:.2e}")
         np.savez_compressed(os.path.join(outdir, f"{name}.npz"), config=json.dumps(kw), batch=batch, frames=frames,
                             sigma=sigma, weight_seed=wseed, input_seed=iseed, mel=mel, z=z,
+                            speaker_ids=spk if spk is not None else np.zeros((0,), np.int64),
                             inverse_ref_fp32=outs["inverse_fp32"], inverse_ref_fp64=outs["inverse_fp64"],
                             infer_ref_fp32=outs["infer_fp32"], infer_ref_fp64=outs["infer_fp64"])
 
@@ -169,8 +200,8 @@ def main():
     WaveGlowAx = load_reference_ax()
     outdir = os.path.join(ROOT, "tests", "golden")
     only = set(sys.argv[1:])                         # optional: names of the cases to (re)generate
-    if not only:
-        main_ax(WaveGlowAx, outdir)
+    if not only or any(n in AX_CASES for n in only):
+        main_ax(WaveGlowAx, outdir, only)
     for name, (kw, batch, frames, sigma, wseed, iseed) in CASES.items():
         if only and name not in only:
             continue

@@ -10,15 +10,18 @@ TEST INFRASTRUCTURE ONLY (same rules as waveglow_oracle.py).  numpy restatement 
   glow_ax.py:284-286,378-381     WN-level speaker embedding   |  :361-373,389 WN._upsample_mels (upsample_first=False)
 for the subset the B200 build supports: upsample_first=True with model-level F.interpolate or upsample_first=False
 (every WN interpolates its own cond-layer output), channel_mixing '1x1conv' or 'permuteheight', mix_first True or
-False, early outputs, n_group <= 32, optional WN-level speaker embedding.  The model-level conditioning front-end
-(speaker embedding, cond layers, upsample net, group conv) is restated in ax_frontend_oracle.py.
+False, early outputs, n_group <= 32, optional WN-level speaker embedding, and the WN_config variants of the general fp32
+mode (include/cwg.h cwg_axg_flow): the 14 gated units glow_ax.py:36-198, listed dilations :331-335, merge_res_skip /
+res_skip=False :259-263,:352,:399-414, WN cond stacks of several layers with activations / kernel sizes / padding modes
+:297-329,:383-387.  The model-level conditioning front-end (speaker embedding, cond layers, upsample net, group conv) is
+restated in ax_frontend_oracle.py.
 
-Parity status: PINNED by oracle/make_golden_waveflow.py (cases `waveglow_ax_*`).
+Parity status: PINNED by oracle/make_golden_waveflow.py (cases `waveglow_ax_*`, `waveglow_axv_*`).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import numpy as np
 
@@ -43,6 +46,27 @@ class AxConfig:
     seperable_conv: bool = False         # in_layer = Sequential(depthwise, pointwise), glow_ax.py:350-358
     wn_speaker_embed_dim: int = 0        # WN_config['speaker_embed_dim'], glow_ax.py:255,284-286
     upsample_first: bool = True          # False: cond stays at frame rate until WN._upsample_mels, glow_ax.py:389
+    # ---- WN_config variants (general fp32 mode); the defaults are the layout of the packed layer kernels
+    gated_unit: str = "GTU"              # glow_ax.py:168-198
+    dilations_w: Optional[List[int]] = None   # WN_config['n_layers_dilations_w'] (list, or one int for all layers), :331-335
+    res_skip: bool = True
+    merge_res_skip: bool = False
+    wn_cond_layers: int = 1
+    wn_cond_hidden_channels: int = 256
+    wn_cond_kernel_size: int = 1         # the conv has 2k - 1 taps (:301)
+    wn_cond_padding_mode: str = "zeros"
+    wn_cond_activation_func: str = "none"
+    wn_negative_slope: Optional[float] = None
+    wn_cond_out_activation_func: bool = True
+
+    def dilation(self, i: int) -> int:
+        if self.dilations_w is None:
+            return 2 ** i
+        return int(self.dilations_w) if isinstance(self.dilations_w, int) else int(self.dilations_w[i])
+
+    def is_variant(self) -> bool:
+        return (self.gated_unit.upper() != "GTU" or self.dilations_w is not None or not self.res_skip or self.merge_res_skip
+                or self.wn_cond_layers != 1 or self.wn_cond_kernel_size != 1 or self.wn_cond_activation_func.lower() != "none")
 
     def flow_channels(self) -> List[int]:
         out, n_rem = [], self.n_group
@@ -51,6 +75,34 @@ class AxConfig:
                 n_rem -= self.n_early_size
             out.append(n_rem)
         return out
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def _selu(x):
+    return 1.0507009873554804934193349852946 * np.where(x > 0, x, 1.6732632423543772848170429916717 * np.expm1(np.minimum(x, 0)))
+
+
+def _softplus(x):                                            # F.softplus: beta 1, threshold 20
+    return np.where(x > 20, x, np.log1p(np.exp(np.minimum(x, 20))))
+
+
+def _lrelu(slope):
+    return lambda x: np.where(x > 0, x, slope * x)
+
+
+_tanhshrink = lambda x: x - np.tanh(x)
+_sin16 = lambda x: np.sin(16 * x)                            # in_act[:, :n].mul_(16) then sin, glow_ax.py:113-114
+_relu = lambda x: np.maximum(x, 0)
+# name -> (unit of the first half, unit of the second half), glow_ax.py:36-166; rrelu(0.01, 0.1) in eval mode has slope 0.055
+GATED_UNITS = {
+    "GTU": (np.tanh, _sigmoid), "GTRU": (np.tanh, _relu), "GTLRU": (np.tanh, _lrelu(0.01)), "GLU": (lambda x: x, _sigmoid),
+    "TTU": (np.tanh, np.tanh), "STU": (np.tanh, _selu), "GTSU": (_tanhshrink, _sigmoid), "SPTU": (np.tanh, _softplus),
+    "GSIU": (np.sin, _sigmoid), "GSIRU": (_sin16, _sigmoid), "GTSRU": (_tanhshrink, _relu), "GSIRRU": (_sin16, _relu),
+    "GSIRLRU": (_sin16, _lrelu(0.01)), "GSIRRLRU": (_sin16, _lrelu(0.055)),
+}
 
 
 def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
@@ -64,13 +116,25 @@ def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
     if cfg.wn_speaker_embed_dim and speaker_ids is not None:             # :378-381
         emb = np.asarray(sd[p + "speaker_embed.weight"], dtype)[np.asarray(speaker_ids)]
         cond_up = np.concatenate([cond_up, np.repeat(emb[:, :, None], cond_up.shape[2], axis=2)], axis=1)
-    spect = np.einsum("oc,bct->bot", _w(sd, p + "cond_layers.0", dtype)[:, :, 0], cond_up, optimize=True) \
-        + np.asarray(sd[p + "cond_layers.0.bias"], dtype)[None, :, None]
+    if cfg.wn_cond_layers == 1 and cfg.wn_cond_kernel_size == 1 and cfg.wn_cond_activation_func.lower() == "none":
+        spect = np.einsum("oc,bct->bot", _w(sd, p + "cond_layers.0", dtype)[:, :, 0], cond_up, optimize=True) \
+            + np.asarray(sd[p + "cond_layers.0.bias"], dtype)[None, :, None]
+    else:                                                                # general cond stack, :297-329 / :383-387
+        from .ax_frontend_oracle import conv1d, _act
+        spect = cond_up
+        pad = (2 * cfg.wn_cond_kernel_size - 1 - 1) // 2
+        for i in range(cfg.wn_cond_layers):
+            spect = conv1d(spect, _w(sd, p + f"cond_layers.{i}", dtype), np.asarray(sd[p + f"cond_layers.{i}.bias"], dtype),
+                           pad, cfg.wn_cond_padding_mode)
+            if cfg.wn_cond_activation_func.lower() != "none" and (cfg.wn_cond_out_activation_func or i != cfg.wn_cond_layers - 1):
+                spect = _act(spect, cfg.wn_cond_activation_func, cfg.wn_negative_slope)
     if not cfg.upsample_first:                                           # :389 -> _upsample_mels :361-373 (no WN upsample net:
         spect = upsample_cond(spect, T, cfg.upsample_mode)               # interpolation_required, F.interpolate to audio length)
     output = None
+    unit_a, unit_b = GATED_UNITS[cfg.gated_unit.upper()]
+    split = cfg.res_skip and not cfg.merge_res_skip
     for i in range(L):
-        d = 2 ** i
+        d = cfg.dilation(i)
         sep = (p + f"in_layers.{i}.0.weight_v") in sd
         w_in = _w(sd, p + (f"in_layers.{i}.0" if sep else f"in_layers.{i}"), dtype)
         ks = w_in.shape[2]
@@ -89,13 +153,16 @@ def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
                 acts += np.einsum("oc,bct->bot", w_in[:, :, j], xp[:, :, j * d:j * d + T], optimize=True)
             acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None]
         acts += spect[:, 2 * C * i:2 * C * (i + 1)]
-        g = np.tanh(acts[:, :C]) * (1.0 / (1.0 + np.exp(-acts[:, C:])))
-        rs = np.einsum("oc,bct->bot", _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0], g, optimize=True) \
-            + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
-        if i < L - 1:
+        g = unit_a(acts[:, :C]) * unit_b(acts[:, C:])
+        if cfg.res_skip:
+            rs = np.einsum("oc,bct->bot", _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0], g, optimize=True) \
+                + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
+        else:
+            rs = g                                                       # :399
+        if split and i < L - 1:                                          # :402-404, :409-411
             audio = audio + rs[:, :C]
             skip = rs[:, C:]
-        else:
+        else:                                                            # last layer, or merged: the hidden tensor stays (:406, :413)
             skip = rs
         output = skip if output is None else output + skip
     end = np.einsum("oc,bct->bot", np.asarray(sd[p + "end.weight"], dtype)[:, :, 0], output, optimize=True) \
@@ -185,12 +252,16 @@ def synthetic_state_dict(cfg: AxConfig, seed: int = 1234, cond_in_channels=None)
                 wn(p + f"in_layers.{i}.1", (2 * C, C, 1), C)
             else:
                 wn(p + f"in_layers.{i}", (2 * C, C, ks), C * ks)
-            wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1), C)
+            if cfg.res_skip:
+                wn(p + f"res_skip_layers.{i}", (2 * C if (i < L - 1 and not cfg.merge_res_skip) else C, C, 1), C)
         wn(p + "start", (C, n_half, 1), n_half)
         sd[p + "end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * 0.02).astype(np.float32)
         sd[p + "end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
         cin = (cond_in_channels or cfg.n_mel_channels) + cfg.wn_speaker_embed_dim
-        wn(p + "cond_layers.0", (2 * C * L, cin, 1), cin)
+        kc = 2 * cfg.wn_cond_kernel_size - 1
+        dims = [cin] + [cfg.wn_cond_hidden_channels] * (cfg.wn_cond_layers - 1) + [2 * C * L]
+        for i, (di, do) in enumerate(zip(dims[:-1], dims[1:])):
+            wn(p + f"cond_layers.{i}", (do, di, kc), di * kc)
         if cfg.wn_speaker_embed_dim:
             sd[p + "speaker_embed.weight"] = rs.standard_normal((512, cfg.wn_speaker_embed_dim)).astype(np.float32)
     return sd

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_cabi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cwg_abi_version() == _cabi.ABI_VERSION == 4
+    assert lib.cwg_abi_version() == _cabi.ABI_VERSION == 5
 
 
 def test_workspace_and_argument_validation():
