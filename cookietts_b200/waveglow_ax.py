@@ -255,6 +255,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         need(upsample_first is True or not transposed_conv_scales,
              "upsample_first=False with a model-level TransposedUpsampleNet (the reference never calls it there)")
         self.wn_speaker_embed_dim = int(wn.get("speaker_embed_dim", 0) or 0)
+        self.upsample_first = bool(upsample_first)
         # ---- WN_config variants: anything outside the packed layer kernels' specialisation (one linear 1x1 cond layer, GTU,
         # 2^i dilations, split res_skip) runs in the general fp32 mode, cwg_axg_flow
         gate = str(wn.get("gated_unit", "GTU")).upper()
