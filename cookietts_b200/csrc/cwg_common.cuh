@@ -60,6 +60,32 @@ void set_error(const char* fmt, ...);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// The gated units of glow_ax.py:36-166 on the two halves (a, b) of the pre-activation (gate = CWG_GATE_*).  The SIREN
+// variants scale the first half by 16 in place before the sine (:113,:131,:140,:149); rrelu in eval mode is
+// leaky_relu((lower + upper) / 2).
+#ifdef __CUDACC__
+__device__ __forceinline__ float gated_unit(int gate, float a, float b) {
+  float fa, fb;
+  switch (gate) {
+    case CWG_GATE_GLU: fa = a; break;
+    case CWG_GATE_GTSU: case CWG_GATE_GTSRU: fa = a - tanhf(a); break;
+    case CWG_GATE_GSIU: fa = sinf(a); break;
+    case CWG_GATE_GSIRU: case CWG_GATE_GSIRRU: case CWG_GATE_GSIRLRU: case CWG_GATE_GSIRRLRU: fa = sinf(16.f * a); break;
+    default: fa = tanhf(a);
+  }
+  switch (gate) {
+    case CWG_GATE_GTRU: case CWG_GATE_GTSRU: case CWG_GATE_GSIRRU: fb = fmaxf(b, 0.f); break;
+    case CWG_GATE_GTLRU: case CWG_GATE_GSIRLRU: fb = b > 0.f ? b : 0.01f * b; break;
+    case CWG_GATE_GSIRRLRU: fb = b > 0.f ? b : 0.055f * b; break;
+    case CWG_GATE_TTU: fb = tanhf(b); break;
+    case CWG_GATE_STU: fb = 1.0507009873554804934f * (b > 0.f ? b : 1.6732632423543772848f * expm1f(b)); break;
+    case CWG_GATE_SPTU: fb = b > 20.f ? b : log1pf(expf(b)); break;
+    default: fb = 1.f / (1.f + expf(-b));
+  }
+  return fa * fb;
+}
+#endif
+
 // CWG_MODE_F16F8 scaling of the e5m2 correction operands (cookietts_b200/packing.py F8_P, F8_Q)
 constexpr float F8_LO_SCALE = 64.f;            // 2^P applied to activation lo parts (weights hi carry 2^-P)
 constexpr float F8_HI_SCALE = 1.f / 256.f;     // 2^-Q applied to activation hi parts (weights lo carry 2^Q)

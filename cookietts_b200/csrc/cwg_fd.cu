@@ -27,29 +27,6 @@ struct FdConvP {
   float* y; long long y_bstride;              // y[b][n][t]
 };
 
-// The gated units of glow_ax.py:36-166 on the two halves (a, b) of the pre-activation.  The SIREN variants scale the first
-// half by 16 in place before the sine (:113,:131,:140,:149); rrelu in eval mode is leaky_relu((lower + upper) / 2).
-__device__ __forceinline__ float gated_unit(int gate, float a, float b) {
-  float fa, fb;
-  switch (gate) {
-    case CWG_GATE_GLU: fa = a; break;
-    case CWG_GATE_GTSU: case CWG_GATE_GTSRU: fa = a - tanhf(a); break;
-    case CWG_GATE_GSIU: fa = sinf(a); break;
-    case CWG_GATE_GSIRU: case CWG_GATE_GSIRRU: case CWG_GATE_GSIRLRU: case CWG_GATE_GSIRRLRU: fa = sinf(16.f * a); break;
-    default: fa = tanhf(a);
-  }
-  switch (gate) {
-    case CWG_GATE_GTRU: case CWG_GATE_GTSRU: case CWG_GATE_GSIRRU: fb = fmaxf(b, 0.f); break;
-    case CWG_GATE_GTLRU: case CWG_GATE_GSIRLRU: fb = b > 0.f ? b : 0.01f * b; break;
-    case CWG_GATE_GSIRRLRU: fb = b > 0.f ? b : 0.055f * b; break;
-    case CWG_GATE_TTU: fb = tanhf(b); break;
-    case CWG_GATE_STU: fb = 1.0507009873554804934f * (b > 0.f ? b : 1.6732632423543772848f * expm1f(b)); break;
-    case CWG_GATE_SPTU: fb = b > 20.f ? b : log1pf(expf(b)); break;
-    default: fb = 1.f / (1.f + expf(-b));
-  }
-  return fa * fb;
-}
-
 // EPI 0: y = conv + bias;  1: y += conv + bias;  2: y = gated_unit(pre[n], pre[n + N]), pre = conv + bias + add
 template <int EPI>
 __global__ void __launch_bounds__(256) k_fd_conv(FdConvP p) {

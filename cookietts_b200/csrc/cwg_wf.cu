@@ -423,6 +423,10 @@ int wf_check(const cwg_wf_config* c, int mode, int batch, int t_samples) {
   CWG_REQUIRE(c->n_group >= 2 && c->n_group <= WF_TC_MAX_GROUP, "n_group must be in [2, %d]", WF_TC_MAX_GROUP);
   CWG_REQUIRE(c->n_mel >= 1 && c->n_mel <= WF_HP, "n_mel must be <= %d", WF_HP);
   CWG_REQUIRE(c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_flows / n_layers");
+  CWG_REQUIRE(c->gate == CWG_GATE_GTU, "the tensor-core WaveFlow kernels implement the GTU gate only (use CWG_MODE_FFMA)");
+  for (int l = 0; l < c->n_layers; ++l)
+    CWG_REQUIRE((c->dilations_w[l] == 0 || c->dilations_w[l] == (1 << l)) && c->dilations_h[l] <= 1,
+                "the tensor-core WaveFlow kernels take dilation_w 2^i and dilation_h 1 only (use CWG_MODE_FFMA)");
   CWG_REQUIRE(batch >= 1 && t_samples >= c->n_group && t_samples % c->n_group == 0, "t_samples must be a positive multiple of n_group");
   return 0;
 }

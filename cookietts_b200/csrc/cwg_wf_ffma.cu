@@ -6,6 +6,9 @@
 //   efficient_model_ax.py:279-357 WaveGlow.inverse, efficient_modules.py:42-65 WaveFlowCoupling.inverse (row by row),
 //   glow_ax.py:556-635 WN_2d.forward with its per-layer conv queue (a ring of kernel_h rows per layer here),
 //   efficient_modules.py:360-403 PermuteHeight (host-side column bookkeeping).
+// WN_config variants (ABI 5): every gated unit of glow_ax.py:168-198, listed width / height dilations (:513-517; the ring
+// of a layer holds (kernel_h - 1) * dilation_h + 1 rows), merge_res_skip / res_skip=False (packing only: zero res rows),
+// WN-level speaker embeddings (a per-utterance gate bias, cwg_wf_weights.b1_batch).
 #include "cwg_common.cuh"
 
 namespace cwg {
@@ -16,6 +19,7 @@ constexpr int WFF_MAX_GROUP = 32;
 
 struct WffGemmP {
   long long BT; int Tp, C, KH, KW, M;      // M = cond channels
+  int dil_h, ring_rows; long long bias_bstride;   // ring_rows = (KH - 1) * max dil_h + 1; bias_bstride: per-utterance b1 (0: shared)
   int N, K;                                // output columns, contraction length
   const float* W; const float* bias;       // W [N][K]
   // GEMM1 (in_layer + cond): x ring of this layer [KH][BT][C]; newest row index `row`; mel_up [BT][M]
@@ -33,12 +37,12 @@ __device__ __forceinline__ float wff_a(const WffGemmP& p, long long m, int kk) {
   if (kk >= kx) return __ldg(p.mel + (size_t)m * p.M + (kk - kx));
   const int a = kk / (p.KW * p.C), rem = kk - a * p.KW * p.C;
   const int b = rem / p.C, c = rem - b * p.C;
-  const int src_row = p.row - (p.KH - 1 - a);                     // causal in height: padding_h = kernel_h - 1 on top
+  const int src_row = p.row - (p.KH - 1 - a) * p.dil_h;           // causal in height: padding_h = (kernel_h - 1) * dilation_h on top
   if (src_row < 0) return 0.f;                                    // the zero-initialised conv queue (glow_ax.py:597-602)
   const long long ub = m / p.Tp; const int t = (int)(m - ub * p.Tp);
   const int tt = t + (b - p.KW / 2) * p.dil;                      // 'same' zero padding in width
   if (tt < 0 || tt >= p.Tp) return 0.f;
-  return __ldg(p.ring + ((size_t)(src_row % p.KH) * p.BT + (size_t)ub * p.Tp + tt) * p.C + c);
+  return __ldg(p.ring + ((size_t)(src_row % p.ring_rows) * p.BT + (size_t)ub * p.Tp + tt) * p.C + c);
 }
 
 template <int MODE>
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(256) k_wff_gemm(WffGemmP p) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
       if (MODE == 0) {
-        p.pre[(size_t)m * p.N + n] = acc[i][j] + __ldg(p.bias + n);
+        p.pre[(size_t)m * p.N + n] = acc[i][j] + __ldg(p.bias + (m / p.Tp) * p.bias_bstride + n);
       } else if (n < p.C) {                                       // x = x + res (glow_ax.py:620-626)
         if (p.x_next) p.x_next[(size_t)m * p.C + n] = __ldg(p.x_cur + (size_t)m * p.C + n) + acc[i][j] + __ldg(p.bias + n);
       } else {                                                    // folded `end` of the skip path: (log_s, t)
@@ -90,12 +94,12 @@ __global__ void __launch_bounds__(256) k_wff_gemm(WffGemmP p) {
   }
 }
 
-__global__ void k_wff_gate(const float* __restrict__ pre, float* __restrict__ acts, long long n, int C) {
+__global__ void k_wff_gate(const float* __restrict__ pre, float* __restrict__ acts, long long n, int C, int gate) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long m = i / C; const int c = (int)(i - m * C);
   const float a = pre[m * 2 * C + c], b = pre[m * 2 * C + C + c];
-  acts[i] = tanhf(a) * (1.f / (1.f + expf(-b)));                  // GTU, glow_ax.py:36-43
+  acts[i] = gate == CWG_GATE_GTU ? tanhf(a) * (1.f / (1.f + expf(-b))) : gated_unit(gate, a, b);   // glow_ax.py:36-166
 }
 
 __global__ void k_wff_mel_up(const float* __restrict__ mel, float* __restrict__ out, int B, int M, int frames,
@@ -147,12 +151,20 @@ void wff_perm(int k, int h, int* idx) {               // PermuteHeight index lis
   }
 }
 
+inline int wff_dil_w(const cwg_wf_config* c, int l) { return c->dilations_w[l] > 0 ? c->dilations_w[l] : 1 << l; }
+inline int wff_dil_h(const cwg_wf_config* c, int l) { return c->dilations_h[l] > 0 ? c->dilations_h[l] : 1; }
+inline int wff_ring_rows(const cwg_wf_config* c) {
+  int mx = 1;
+  for (int l = 0; l < c->n_layers; ++l) mx = wff_dil_h(c, l) > mx ? wff_dil_h(c, l) : mx;
+  return (c->kernel_h - 1) * mx + 1;
+}
+
 struct WffWs { float *eo, *state, *mel_up, *x, *pre, *acts; size_t bytes; };
 void wff_carve(const cwg_wf_config* c, long long BT, void* base, WffWs* ws) {
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align_up(off + n * sizeof(float), 1024); return (float*)((char*)base + o); };
   ws->eo = take((size_t)BT * CWG_EO_PAD); ws->state = take((size_t)BT * c->n_group); ws->mel_up = take((size_t)BT * c->n_mel);
-  ws->x = take((size_t)c->n_layers * c->kernel_h * BT * c->n_channels);
+  ws->x = take((size_t)c->n_layers * wff_ring_rows(c) * BT * c->n_channels);
   ws->pre = take((size_t)BT * 2 * c->n_channels); ws->acts = take((size_t)BT * c->n_channels);
   ws->bytes = off;
 }
@@ -166,6 +178,9 @@ int wff_check(const cwg_wf_config* c, int batch, int t_samples) {
   CWG_REQUIRE(c->n_group >= 2 && c->n_group <= WFF_MAX_GROUP, "n_group must be in [2, %d]", WFF_MAX_GROUP);
   CWG_REQUIRE(c->n_mel >= 1 && c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_mel / n_flows / n_layers");
   CWG_REQUIRE(batch >= 1 && t_samples >= c->n_group && t_samples % c->n_group == 0, "t_samples must be a positive multiple of n_group");
+  CWG_REQUIRE(c->gate >= 0 && c->gate < CWG_GATE_COUNT, "unknown gated unit %d", c->gate);
+  for (int l = 0; l < c->n_layers; ++l)
+    CWG_REQUIRE(c->dilations_w[l] >= 0 && c->dilations_h[l] >= 0 && c->dilations_h[l] <= 64, "bad dilations of layer %d", l);
   return 0;
 }
 
@@ -192,6 +207,7 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
   wff_carve(cfg, BT, workspace, &ws);
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
   const int K1 = KH * KW * C + M, N2 = C + CWG_EO_PAD;
+  const int R = wff_ring_rows(cfg);                                // rows of every layer's conv queue
   {
     const long long n = BT * M;
     k_wff_mel_up<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mel, ws.mel_up, batch, M, frames, frames + pad_frames, Tp, cfg->upsample_linear);
@@ -212,15 +228,17 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
           WffGemmP p{};
           p.BT = BT; p.Tp = Tp; p.C = C; p.KH = KH; p.KW = KW; p.M = M;
           p.N = 2 * C; p.K = K1; p.W = w->w1_f32 + idx * 2 * C * K1; p.bias = w->b1 + idx * 2 * C;
-          p.ring = ws.x + (size_t)l * KH * slot; p.mel = ws.mel_up; p.row = i; p.dil = 1 << l; p.pre = ws.pre;
+          p.ring = ws.x + (size_t)l * R * slot; p.mel = ws.mel_up; p.row = i; p.dil = wff_dil_w(cfg, l); p.pre = ws.pre;
+          p.dil_h = wff_dil_h(cfg, l); p.ring_rows = R;
+          if (w->b1_batch) { p.bias = w->b1_batch + idx * 2 * C; p.bias_bstride = (long long)F * L * 2 * C; }
           dim3 g1((unsigned)((BT + GM - 1) / GM), (unsigned)((2 * C + GN - 1) / GN));
           k_wff_gemm<0><<<g1, 256, 0, s>>>(p);
           const long long n = BT * C;
-          k_wff_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.pre, ws.acts, n, C);
+          k_wff_gate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.pre, ws.acts, n, C, cfg->gate);
           WffGemmP q{};
           q.BT = BT; q.Tp = Tp; q.C = C; q.N = N2; q.K = C; q.W = w->w2_f32 + idx * N2 * C; q.bias = w->b2 + idx * C;
-          q.acts = ws.acts; q.x_cur = ws.x + ((size_t)l * KH + (i % KH)) * slot;
-          q.x_next = l < L - 1 ? ws.x + ((size_t)(l + 1) * KH + (i % KH)) * slot : nullptr;
+          q.acts = ws.acts; q.x_cur = ws.x + ((size_t)l * R + (i % R)) * slot;
+          q.x_next = l < L - 1 ? ws.x + ((size_t)(l + 1) * R + (i % R)) * slot : nullptr;
           q.eo = ws.eo; q.eo_b = w->eo_b + (size_t)k * CWG_EO_PAD; q.first = l == 0;
           dim3 g2((unsigned)((BT + GM - 1) / GM), (unsigned)((C + 2 + GN - 1) / GN));     // res rows + the 2 folded-end rows
           q.N = C + 2;
@@ -230,7 +248,7 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
         }
       }
       const int j = i + 1;                                         // logical row produced now
-      float* x0 = j < h - 1 ? ws.x + (size_t)(j % KH) * slot : nullptr;        // ring of layer 0
+      float* x0 = j < h - 1 ? ws.x + (size_t)(j % R) * slot : nullptr;         // ring of layer 0
       k_wff_row<<<(unsigned)BT, 128, 0, s>>>(BT, h, C, first_flow ? z : ws.state, first_flow ? sigma : 1.f, phys[j],
                                             last_flow ? audio : ws.state, last_flow ? perm[j] : phys[j], ws.eo, i >= 0,
                                             w->start_w + (size_t)k * C, w->start_b + (size_t)k * C, x0);

@@ -122,6 +122,22 @@ class WaveFlowConfig:
     hop_length: int = 256
     upsample_mode: str = "linear"   # WN_config['upsample_mode'] used by the model-level interpolate
     seperable_conv: bool = False    # in_layer = Sequential(depthwise, pointwise), glow_ax.py:525-531
+    # ---- WN_config variants (the fp32 CUDA-core mode runs them; the defaults are what the tensor-core kernels take)
+    gated_unit: str = "GTU"         # glow_ax.py:168-198
+    dilations_w: object = None      # n_layers_dilations_w: None (2^i), one int, or a list (glow_ax.py:506-514)
+    dilations_h: object = 1         # n_layers_dilations_h: one int or a list (:509-513)
+    res_skip: bool = True
+    merge_res_skip: bool = False
+    wn_speaker_embed_dim: int = 0   # WN_config['speaker_embed_dim'], glow_ax.py:464-466
+    upsample_first: bool = True     # False: the WN interpolates its cond-layer output (glow_ax.py:578-579)
+
+    def dilation_w(self, i: int) -> int:
+        if self.dilations_w is None:
+            return 2 ** i
+        return int(self.dilations_w) if isinstance(self.dilations_w, int) else int(self.dilations_w[i])
+
+    def dilation_h(self, i: int) -> int:
+        return int(self.dilations_h) if isinstance(self.dilations_h, int) else int(self.dilations_h[i])
 
 
 
@@ -149,23 +165,26 @@ def waveflow_state_dict(cfg: WaveFlowConfig, seed: int = 1234, cond_in_channels=
                 wn(p + f"in_layers.{i}.1", (2 * C, C, 1, 1), C)
             else:
                 wn(p + f"in_layers.{i}", (2 * C, C, kh, kw), C * kh * kw)
-            wn(p + f"res_skip_layers.{i}", (2 * C if i < L - 1 else C, C, 1, 1), C)
+            if cfg.res_skip:
+                wn(p + f"res_skip_layers.{i}", (2 * C if (i < L - 1 and not cfg.merge_res_skip) else C, C, 1, 1), C)
         wn(p + "start", (C, 1, 1, 1), 1)
         sd[p + "end.weight"] = (rs.standard_normal((2, C, 1, 1)) * 0.02).astype(np.float32)
         sd[p + "end.bias"] = (rs.standard_normal((2,)) * 0.02).astype(np.float32)
-        wn(p + "cond_layers.0", (2 * C * L, cin, 1), cin)
+        wn(p + "cond_layers.0", (2 * C * L, cin + cfg.wn_speaker_embed_dim, 1), cin + cfg.wn_speaker_embed_dim)
+        if cfg.wn_speaker_embed_dim:
+            sd[p + "speaker_embed.weight"] = rs.standard_normal((512, cfg.wn_speaker_embed_dim)).astype(np.float32)
     return sd
 
 
 def waveflow_reference_kwargs(cfg: WaveFlowConfig) -> dict:
     wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size_w=cfg.kernel_size_w,
-              kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=None, n_layers_dilations_h=1,
-              speaker_embed_dim=0, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
+              kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=cfg.dilations_w, n_layers_dilations_h=cfg.dilations_h,
+              speaker_embed_dim=cfg.wn_speaker_embed_dim, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
               cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv,
-              res_skip=True, merge_res_skip=False, upsample_mode=cfg.upsample_mode)
+              res_skip=cfg.res_skip, merge_res_skip=cfg.merge_res_skip, upsample_mode=cfg.upsample_mode, gated_unit=cfg.gated_unit)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_flows * 2, n_early_size=2, memory_efficient=0.0, spect_scaling=False,
-                upsample_mode="normal", upsample_first=True, speaker_embed=0, cond_layers=0,
+                upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,
                 cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
                 cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
                 sampling_rate=22050, channel_mixing="permuteheight", mix_first=True, waveflow=True)

@@ -8,10 +8,17 @@ oracle/make_golden_waveflow.py loading the same dict into the real reference wit
 `inverse(z, cond)` (:279) and `infer(spect, speaker_ids=None, artifact_trimming=1, sigma=1.,
 t_scaler=1.0, return_CPU=True)` (:359-388).  Everything outside the supported subset raises at
 construction (see `_check_supported`); there is no CPU fallback.
+
+WN_config variants of WN_2d run in the fp32 CUDA-core mode (csrc/cwg_wf_ffma.cu; a tensor-core `precision` is switched to
+"ffma" with a warning): every gated unit of glow_ax.py:168-198, listed width / height dilations (:506-517), `merge_res_skip` /
+`res_skip=False` (:541-553,:610-626 - the hidden tensor is then never updated: zero res rows at pack time), WN-level speaker
+embeddings (:464-466,:567-570 - a per-utterance gate bias), `upsample_first=False` (:578-579 - interpolation commutes with
+the one linear 1x1 cond layer).
 """
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -38,6 +45,13 @@ class WaveFlowPackConfig:
     hop_length: int = 256
     upsample_linear: bool = True
     fp32: bool = False           # CWG_MODE_FFMA layout: fp32 planes, cond columns not padded
+    # WN_config variants (fp32 mode only; the defaults are what the tensor-core kernels implement)
+    gate: int = 0                # CWG_GATE_* (include/cwg.h)
+    dilations_w: tuple = ()      # () = 2^i
+    dilations_h: tuple = ()      # () = 1
+    res_skip: bool = True
+    merge_res_skip: bool = False
+    wn_speaker_dim: int = 0      # WN-level speaker embedding: the last columns of every cond layer
 
     @property
     def k1(self) -> int:
@@ -52,10 +66,17 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
     w1 = np.zeros((F, L, 2 * Cc, K1)); b1 = np.zeros((F, L, 2 * Cc))
     w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, EO_PAD))
     start_w = np.zeros((F, Cc)); start_b = np.zeros((F, Cc))
+    E = int(cfg.wn_speaker_dim)
+    spk_w = np.zeros((F, L, 2 * Cc, max(E, 1)), np.float32)
+    spk_embed = []
     for k in range(F):
         p = f"WN.{k}.WN."
-        w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]           # [2CL, M]
+        w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]           # [2CL, M (+ E)]
         b_c = _np(sd[p + "cond_layers.0.bias"])
+        if E:                                                              # [cond channels | speaker embedding], glow_ax.py:570
+            spk_w[k] = w_c[:, w_c.shape[1] - E:].reshape(L, 2 * Cc, E)
+            w_c = w_c[:, :w_c.shape[1] - E]
+            spk_embed.append(np.asarray(_np(sd[p + "speaker_embed.weight"]), np.float32))
         if cond_fold is not None:                                          # n_flow_group_conv (ax_frontend.py)
             w_c, b_c = cond_fold(k, w_c, b_c, sd)
         w_end = _np(sd[p + "end.weight"])[:, :, 0, 0]                      # [2, C]  (log_s, t)
@@ -65,12 +86,15 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
             w1[k, i, :, :kh * kw * Cc] = w_in.transpose(0, 2, 3, 1).reshape(2 * Cc, kh * kw * Cc)   # col (a*kw+b)*C + c
             w1[k, i, :, kh * kw * Cc:kh * kw * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
             b1[k, i] = b_in + b_c[2 * Cc * i:2 * Cc * (i + 1)]
-            w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0, 0]
-            b_rs = _np(sd[p + f"res_skip_layers.{i}.bias"])
-            if i < L - 1:
+            if cfg.res_skip:
+                w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0, 0]
+                b_rs = _np(sd[p + f"res_skip_layers.{i}.bias"])
+            else:                                                          # res_skip_acts = acts, glow_ax.py:610
+                w_rs, b_rs = np.eye(Cc), np.zeros(Cc)
+            if i < L - 1 and cfg.res_skip and not cfg.merge_res_skip:
                 w2[k, i, :Cc] = w_rs[:Cc]; b2[k, i] = b_rs[:Cc]
                 w_skip, b_skip = w_rs[Cc:], b_rs[Cc:]
-            else:
+            else:                  # last layer, or merged: everything goes to the output and the hidden tensor stays (:613-626)
                 w_skip, b_skip = w_rs, b_rs
             w2[k, i, Cc:Cc + 2] = w_end @ w_skip
             eo_bias += w_end @ b_skip
@@ -80,6 +104,8 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
     out = {"b1": b1.astype(np.float32), "b2": b2.astype(np.float32), "eo_b": eo_b.astype(np.float32),
            "start_w": start_w.astype(np.float32), "start_b": start_b.astype(np.float32),
            "w1_f64": w1, "w2_f64": w2}
+    if E:
+        out["spk_w"], out["spk_embed"] = spk_w, np.stack(spk_embed)
     if cfg.fp32:
         out["w1_f32"], out["w2_f32"] = w1.astype(np.float32), w2.astype(np.float32)
     else:
@@ -89,15 +115,16 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
 
 
 class CwgWfConfig(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("n_mel", "n_flows", "n_group", "n_layers", "n_channels",
-                                          "kernel_h", "kernel_w", "hop_length", "upsample_linear")]
+    _fields_ = ([(n, C.c_int32) for n in ("n_mel", "n_flows", "n_group", "n_layers", "n_channels",
+                                           "kernel_h", "kernel_w", "hop_length", "upsample_linear", "gate")]
+                + [("dilations_w", C.c_int32 * 16), ("dilations_h", C.c_int32 * 16)])
 
 
 WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "w1_f32", "w2_f32")
 
 
 class CwgWfWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch",)]
 
 
 def _bind(lib):
@@ -122,22 +149,28 @@ def _bind(lib):
 class _WN2d(nn.Module):
     """Parameter holder with the layout of glow_ax.py:421-553 (supported subset)."""
 
-    def __init__(self, n_layers, n_channels, kernel_h, kernel_w, cond_in_channels, seperable_conv=False):
+    def __init__(self, n_layers, n_channels, kernel_h, kernel_w, cond_in_channels, seperable_conv=False, dilations_w=(),
+                 dilations_h=(), res_skip=True, merge_res_skip=False, speaker_embed_dim=0):
         super().__init__()
         wn = nn.utils.weight_norm
+        cond_in_channels += speaker_embed_dim                # glow_ax.py:431
+        if speaker_embed_dim:
+            self.speaker_embed = nn.Embedding(512, speaker_embed_dim)     # glow_ax.py:464-466
         self.in_layers = nn.ModuleList()
         self.res_skip_layers = nn.ModuleList()
         for i in range(n_layers):
-            d = 2 ** i
+            d = dilations_w[i] if dilations_w else 2 ** i
+            dh = dilations_h[i] if dilations_h else 1
             pad = (0, ((kernel_w - 1) * d) // 2)
             if not seperable_conv:
-                self.in_layers.append(wn(nn.Conv2d(n_channels, 2 * n_channels, (kernel_h, kernel_w), dilation=(1, d), padding=pad), name="weight"))
+                self.in_layers.append(wn(nn.Conv2d(n_channels, 2 * n_channels, (kernel_h, kernel_w), dilation=(dh, d), padding=pad), name="weight"))
             else:                                            # glow_ax.py:525-531
                 self.in_layers.append(nn.Sequential(
-                    wn(nn.Conv2d(n_channels, n_channels, (kernel_h, kernel_w), dilation=(1, d), padding=pad, groups=n_channels), name="weight"),
+                    wn(nn.Conv2d(n_channels, n_channels, (kernel_h, kernel_w), dilation=(dh, d), padding=pad, groups=n_channels), name="weight"),
                     wn(nn.Conv2d(n_channels, 2 * n_channels, (1, 1)), name="weight")))
-            rs = 2 * n_channels if i < n_layers - 1 else n_channels
-            self.res_skip_layers.append(wn(nn.Conv2d(n_channels, rs, (1, 1)), name="weight"))
+            if res_skip:                                     # glow_ax.py:541-553
+                rs = 2 * n_channels if (i < n_layers - 1 and not merge_res_skip) else n_channels
+                self.res_skip_layers.append(wn(nn.Conv2d(n_channels, rs, (1, 1)), name="weight"))
         self.start = wn(nn.Conv2d(1, n_channels, (1, 1)), name="weight")
         self.end = nn.Conv2d(n_channels, 2, (1, 1))
         self.end.weight.data.zero_(); self.end.bias.data.zero_()
@@ -168,13 +201,15 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         super().__init__()
         wn = dict(WN_config)
         a = dict(locals())
-        self._check_supported(a, wn, precision)
+        precision = self._check_supported(a, wn, precision)
+        v = self._variant
         self._graph_seen = set()
         self.graphs, self._graphs = graphs, {}       # CUDA-graph replay: "auto" = calls of <= GRAPH_MAX_FRAMES mel frames in total
         self.n_flows, self.n_group, self.hop_length = n_flows, n_group, hop_length
         self.n_mel_channels, self.sampling_rate, self.win_size = n_mel_channels, sampling_rate, win_length
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
         self.precision = precision
+        self.wn_speaker_embed_dim = v["speaker_dim"]
         cond_channels = self._fe_build(a, wn)                # model-level front-end (ax_frontend.py)
         if cond_channels > COND_PAD and precision != "ffma":
             raise NotImplementedError(f"cookietts_b200.WaveFlow: the kernels take <= {COND_PAD} cond channels "
@@ -182,42 +217,69 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self.pack_config = WaveFlowPackConfig(
             n_mel=cond_channels, n_flows=n_flows, n_group=n_group, n_layers=wn["n_layers"],
             n_channels=wn["n_channels"], kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
-            hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear", fp32=precision == "ffma")
+            hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear", fp32=precision == "ffma",
+            gate=v["gate"], dilations_w=v["dilations_w"], dilations_h=v["dilations_h"], res_skip=v["res_skip"],
+            merge_res_skip=v["merge"], wn_speaker_dim=v["speaker_dim"])
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
                                            cond_in_channels=self.wn_cond_in_channels,
-                                           seperable_conv=bool(wn.get("seperable_conv"))) for _ in range(n_flows)])
+                                           seperable_conv=bool(wn.get("seperable_conv")), dilations_w=v["dilations_w"],
+                                           dilations_h=v["dilations_h"], res_skip=v["res_skip"], merge_res_skip=v["merge"],
+                                           speaker_embed_dim=v["speaker_dim"]) for _ in range(n_flows)])
         self._packed = None
         self._packed_key = None
         self._workspace = None
 
-    @staticmethod
-    def _check_supported(a, wn, precision="bf16x3"):
+    def _check_supported(self, a, wn, precision="bf16x3"):
+        """Raises for what is not built; returns the precision the model runs in (WN_config variants force "ffma")."""
+        from .waveglow_ax import GATED_UNITS
+
         def need(cond, msg):
             if not cond:
                 raise NotImplementedError("cookietts_b200.WaveFlow: " + msg)
         need(a["waveflow"], "only waveflow=True (WN_2d) is built; use cookietts_b200.WaveGlow for the classic model")
         need(str(a["channel_mixing"]).lower() in "waveflowpermuteheightpermutechannelpermute", "channel_mixing must be 'permuteheight'")
         need(a["mix_first"], "mix_first=False is not supported")
-        need(a["upsample_first"] is True, "upsample_first must be True")
+        need(a["upsample_first"] is True or (a["upsample_first"] is False and not a["transposed_conv_scales"]),
+             "upsample_first must be True, or False without a model-level TransposedUpsampleNet")
         need(a["n_flows"] % 2 == 0, "PermuteHeight requires an even n_flows (efficient_modules.py:370)")
         need(a["n_early_every"] >= a["n_flows"], "early outputs are not supported with waveflow (set n_early_every >= n_flows)")
-        need(not wn.get("speaker_embed_dim", 0), "WN-level speaker embeddings are not supported (use the model-level speaker_embed)")
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1, "WN cond_layers must be one 1x1 conv")
         need(wn.get("cond_activation_func", "none") == "none", "WN cond activation is not supported")
-        need(not wn.get("merge_res_skip") and wn.get("res_skip", True), "merged / absent res_skip variants are not supported")
-        need(wn.get("gated_unit", "GTU") == "GTU", "only the GTU gate is supported")
-        need(wn.get("n_layers_dilations_w") is None and wn.get("n_layers_dilations_h", 1) == 1, "custom dilations are not supported")
         need(precision in ("bf16x3", "bf16", "ffma"), "precision must be 'bf16x3', 'bf16' or 'ffma'")
+        # ---- WN_config variants (fp32 CUDA-core mode)
+        L = int(wn["n_layers"])
+        gate = str(wn.get("gated_unit", "GTU")).upper()
+        need(gate in GATED_UNITS, "gated_unit is invalid (glow_ax.py:168-198)")
+        dw, dh = wn.get("n_layers_dilations_w"), wn.get("n_layers_dilations_h", 1)
+        dw = [dw] * L if isinstance(dw, int) else dw
+        dh = [dh] * L if isinstance(dh, int) else dh
+        need(dw is None or (len(dw) >= L and all(int(d) >= 1 for d in dw[:L])), "n_layers_dilations_w needs one dilation >= 1 per layer")
+        need(dh is not None and len(dh) >= L and all(1 <= int(d) <= 64 for d in dh[:L]), "n_layers_dilations_h needs one dilation in [1, 64] per layer")
+        dw = () if dw is None or [int(d) for d in dw[:L]] == [2 ** i for i in range(L)] else tuple(int(d) for d in dw[:L])
+        dh = () if all(int(d) == 1 for d in dh[:L]) else tuple(int(d) for d in dh[:L])
+        res_skip, merge = bool(wn.get("res_skip", True)), bool(wn.get("merge_res_skip", False))
+        if not (res_skip or merge):
+            raise AssertionError("Cannot remove res_skip without using merge_res_skip")      # glow_ax.py:434
+        self._variant = dict(gate=GATED_UNITS[gate], dilations_w=dw, dilations_h=dh, res_skip=res_skip, merge=merge,
+                             speaker_dim=int(wn.get("speaker_embed_dim", 0) or 0))
+        variant = bool(self._variant["gate"] or dw or dh or merge or not res_skip or self._variant["speaker_dim"])
+        if variant and precision != "ffma":
+            warnings.warn(f"cookietts_b200.WaveFlow: this WN_config (gated_unit {gate}, dilations_w {dw or '2^i'}, dilations_h "
+                          f"{dh or 1}, merge_res_skip {merge}, res_skip {res_skip}, WN speaker_embed_dim "
+                          f"{self._variant['speaker_dim']}) runs in the fp32 CUDA-core mode; precision '{precision}' -> 'ffma'")
+            precision = "ffma"
         if precision == "ffma":      # fp32 CUDA-core path (csrc/cwg_wf_ffma.cu): general WN_2d shapes
             need(wn["n_channels"] % 2 == 0 and 1 <= wn["kernel_size_h"] <= 16 and wn["kernel_size_w"] % 2 == 1 and wn["kernel_size_w"] <= 15,
                  "precision='ffma' takes even n_channels, kernel_size_h <= 16 and odd kernel_size_w <= 15")
             need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 32, "hop_length % n_group == 0 and n_group <= 32")
+            need(L <= 16, "n_layers <= 16")
         else:
             need(wn["n_channels"] == 128 and wn["kernel_size_h"] == 3 and wn["kernel_size_w"] == 3,
                  "the tensor-core kernels are built for n_channels=128, kernel 3x3 (precision='ffma' runs other shapes)")
             need(a["hop_length"] % a["n_group"] == 0 and a["n_group"] <= 16, "hop_length % n_group == 0 and n_group <= 16 (32 with precision='ffma')")
         need(wn.get("upsample_mode", "linear") in ("linear", "nearest"), "upsample_mode must be 'linear' or 'nearest'")
+        return precision
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._packed = None
@@ -248,7 +310,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
         pk = pack_waveflow_state_dict(sd, self.pack_config, cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
-        for name in WF_WEIGHT_FIELDS:
+        for name in WF_WEIGHT_FIELDS + ("spk_w", "spk_embed"):
             if name not in pk:
                 continue
             arr = pk[name]
@@ -260,7 +322,11 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
         pc = self.pack_config
         self._ccfg = CwgWfConfig(pc.n_mel, pc.n_flows, pc.n_group, pc.n_layers, pc.n_channels, pc.kernel_h, pc.kernel_w,
-                                 pc.hop_length, int(pc.upsample_linear))
+                                 pc.hop_length, int(pc.upsample_linear), pc.gate)
+        for i, d in enumerate(pc.dilations_w):
+            self._ccfg.dilations_w[i] = d
+        for i, d in enumerate(pc.dilations_h):
+            self._ccfg.dilations_h[i] = d
         self._packed, self._packed_key, self._cw = dev_pk, key, w
         self._graphs = {}
 
@@ -288,6 +354,28 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             nbytes = lib.cwg_wf_workspace_bytes(self._ccfg, mode, B, frames, T)
             if nbytes == 0:
                 raise _cabi.CwgError(lib.cwg_last_error().decode())
+            b1_batch = None
+            if self.wn_speaker_embed_dim:                    # WN-level speaker embedding -> per-utterance gate bias
+                if speaker_ids is None:
+                    raise Exception("This WaveFlow/WaveGlow model requires speaker ids or speaker embeddings.")
+                ids = torch.as_tensor(speaker_ids, device=dev).long().view(-1).contiguous()
+                if ids.numel() != B:
+                    raise ValueError(f"speaker_ids must hold one id per utterance ({B}), got {ids.numel()}")
+                if int(ids.min()) < 0 or int(ids.max()) >= 512:
+                    raise IndexError("speaker id out of range [0, 512)")
+                pc = self.pack_config
+                lib.cwg_ax_speaker_bias.restype = C.c_int
+                lib.cwg_ax_speaker_bias.argtypes = [C.POINTER(_cabi.CwgConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+                dims = _cabi.CwgConfig(n_mel=pc.n_mel, n_flows=pc.n_flows, n_group=pc.n_group, n_early_every=pc.n_flows, n_early_size=2,
+                                       win_length=pc.hop_length, hop_length=pc.hop_length, n_layers=pc.n_layers,
+                                       n_channels=pc.n_channels, kernel_size=pc.kernel_w, cond_hidden=pc.n_mel)
+                b1_batch = torch.empty(B, pc.n_flows, pc.n_layers, 2 * pc.n_channels, device=dev, dtype=torch.float32)
+                _cabi.check(lib.cwg_ax_speaker_bias(dims, self._packed["b1"].data_ptr(), self._packed["spk_w"].data_ptr(),
+                                                    self._packed["spk_embed"].data_ptr(), self.wn_speaker_embed_dim,
+                                                    self._packed["spk_embed"].shape[1], ids.data_ptr(), B, b1_batch.data_ptr(),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+            self._cw.b1_batch = b1_batch.data_ptr() if b1_batch is not None else None
 
             def launch(cond_t, z_t, audio_t, ws_t):
                 ws_ptr = (ws_t.data_ptr() + 1023) // 1024 * 1024
@@ -305,7 +393,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                                                       z_t.data_ptr(), 1.0, audio_t.data_ptr(), ws_ptr,
                                                       ws_t.numel() - (ws_ptr - ws_t.data_ptr()),
                                                       B, T, torch.cuda.current_stream(dev).cuda_stream, arr_b, arr_e, n_ev))
-            use_graph = (layer_events is None and not torch.cuda.is_current_stream_capturing() and
+            use_graph = (layer_events is None and b1_batch is None and not torch.cuda.is_current_stream_capturing() and
                          (self.graphs is True or (self.graphs == "auto" and B * frames <= self.GRAPH_MAX_FRAMES)))
             if use_graph and self.graphs == "auto" and (B, frames, T, mode) not in self._graphs:
                 if (B, frames, T, mode) not in self._graph_seen:       # capture a shape the second time it is seen

@@ -256,6 +256,10 @@ typedef struct cwg_wf_config {
   int32_t kernel_h, kernel_w;   /* 3, 3 */
   int32_t hop_length;
   int32_t upsample_linear;      /* 1: F.interpolate(mode='linear', align_corners=True); 0: 'nearest' */
+  /* ABI 5 - WN_config variants of WN_2d, CWG_MODE_FFMA only (the tensor-core kernels take the defaults: all zero) */
+  int32_t gate;                 /* CWG_GATE_* (glow_ax.py:168-198); 0 = GTU                                        */
+  int32_t dilations_w[16];      /* n_layers_dilations_w (glow_ax.py:514); 0 = the default 2^i                      */
+  int32_t dilations_h[16];      /* n_layers_dilations_h (:513,:517: causal padding (kernel_h-1)*dilation_h); 0 = 1 */
 } cwg_wf_config;
 
 /* K1 = kernel_h*kernel_w*C + CWG_WF_COND_PAD, N2 = C + CWG_EO_PAD */
@@ -263,7 +267,8 @@ typedef struct cwg_wf_weights {
   const uint16_t* w1_hi;   /* [F][L][2C][K1]  col (kh*kw_n + kw)*C + c | 9C + mel channel   */
   const uint16_t* w1_lo;
   const float*    b1;      /* [F][L][2C]      in_layer bias + cond layer bias slice          */
-  const uint16_t* w2_hi;   /* [F][L][N2][C]   rows <C res (0 for last layer), C: log_s, C+1: t (end folded) */
+  const uint16_t* w2_hi;   /* [F][L][N2][C]   rows <C res (0 for last layer; all 0 with merge_res_skip, where the hidden
+                              tensor is never updated, glow_ax.py:613-626), C: log_s, C+1: t (end folded) */
   const uint16_t* w2_lo;
   const float*    b2;      /* [F][L][C]                                                      */
   const float*    eo_b;    /* [F][CWG_EO_PAD]                                                */
@@ -273,6 +278,10 @@ typedef struct cwg_wf_weights {
    * matrices in fp32 with K1 = kernel_h*kernel_w*C + n_mel (the cond columns are not padded); hi / lo may then be NULL */
   const float*    w1_f32;
   const float*    w2_f32;
+  /* ABI 5, CWG_MODE_FFMA, optional (NULL: the shared b1): per-utterance gate bias [batch][F][L][2C] of this call - the
+   * WN-level speaker embedding (glow_ax.py:464-466,:567-570) is a time-constant input of the 1x1 cond layer, i.e. a bias;
+   * cwg_ax_speaker_bias evaluates it */
+  const float*    b1_batch;
 } cwg_wf_weights;
 
 size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples);

@@ -47,6 +47,8 @@ def load_reference_ax():
 from cookietts_b200.synthetic import waveflow_reference_kwargs as reference_kwargs  # noqa: E402
 
 
+_WV = dict(n_mel_channels=8, n_flows=4, n_group=8, n_layers=3, n_channels=16, win_length=64, hop_length=16)
+
 CASES = {
     # name: (cfg kwargs, batch, frames, sigma, weight seed, input seed)
     "waveflow_tiny": (dict(n_mel_channels=8, n_flows=4, n_group=8, n_layers=3, n_channels=16,
@@ -65,6 +67,13 @@ CASES = {
     # the trained-checkpoint layout at full width (128 channels, h = 20, 8 flows, 8 layers, separable 7x7), short clip
     "waveflow_sep7_128": (dict(n_group=20, kernel_size_h=7, kernel_size_w=7, seperable_conv=True, win_length=1200,
                                hop_length=300), 1, 4, 0.666, 26, 6),
+    # ---- WN_config variants (fp32 CUDA-core mode): gated units, width / height dilations, merged / absent res_skip,
+    # WN-level speaker embedding with upsample_first=False
+    "waveflow_v_gate": (dict(_WV, gated_unit="GSIU", dilations_w=[1, 3, 2], dilations_h=2), 2, 6, 0.8, 81, 31),
+    "waveflow_v_merge": (dict(_WV, merge_res_skip=True, gated_unit="GTRU", kernel_size_h=2), 2, 5, 0.9, 82, 32),
+    "waveflow_v_noskip": (dict(_WV, res_skip=False, merge_res_skip=True, gated_unit="TTU", dilations_w=2), 1, 7, 1.0, 83, 33),
+    "waveflow_v_speaker": (dict(_WV, wn_speaker_embed_dim=4, upsample_first=False, dilations_h=[1, 2, 1], gated_unit="GTSU"),
+                           2, 6, 0.8, 84, 34),
 }
 
 
@@ -123,7 +132,6 @@ AX_CASES = {
 
 def main_ax(WaveGlowAx, outdir, only=()):
     from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd
-    np.product = np.prod                                   # removed in numpy 2; the reference still calls it
     for name, (kw, batch, frames, sigma, wseed, iseed) in AX_CASES.items():
         if only and name not in only:
             continue
@@ -198,6 +206,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         return main_big()
     WaveGlowAx = load_reference_ax()
+    np.product = np.prod                                   # removed in numpy 2; the reference still calls it
     outdir = os.path.join(ROOT, "tests", "golden")
     only = set(sys.argv[1:])                         # optional: names of the cases to (re)generate
     if not only or any(n in AX_CASES for n in only):
@@ -210,6 +219,8 @@ def main():
         rs = np.random.RandomState(iseed)
         mel = np.clip(rs.standard_normal((batch, cfg.n_mel_channels, frames)) * 2.0 - 5.0, -11.5129, 2.0).astype(np.float32)
         z = rs.standard_normal((batch, frames * cfg.hop_length)).astype(np.float32)
+        spk = rs.randint(0, 512, size=(batch,)).astype(np.int64) if cfg.wn_speaker_embed_dim else None
+        ids = torch.from_numpy(spk) if spk is not None else None
         outs = {}
         for dt, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
             model = WaveGlowAx(**reference_kwargs(cfg))
@@ -218,17 +229,18 @@ def main():
             with torch.no_grad():
                 # (1) explicit-z API: inverse(z, cond) on the un-padded mel
                 zz = torch.from_numpy(z).to(dt) * sigma
-                inv, _ = model.inverse(zz, torch.from_numpy(mel).to(dt))
+                inv, _ = model.inverse(zz, torch.from_numpy(mel).to(dt), speaker_ids=ids)
                 outs["inverse_" + tag] = inv.numpy()
                 # (2) infer(): pads one zero frame, draws z [B, frames*hop] with std=sigma, trims hop
                 with InjectedNormal([torch.from_numpy(z)]):
-                    aud = model.infer(torch.from_numpy(mel).to(dt), sigma=sigma)
+                    aud = model.infer(torch.from_numpy(mel).to(dt), speaker_ids=ids, sigma=sigma)
                 outs["infer_" + tag] = aud.numpy()
         e1 = np.abs(outs["inverse_fp32"] - outs["inverse_fp64"]).max()
         print(f"{name}: inverse {outs['inverse_fp64'].shape} infer {outs['infer_fp64'].shape} "
               f"rms {np.sqrt((outs['inverse_fp64'] ** 2).mean()):.3f} fp32-vs-fp64 {e1:.2e}")
         np.savez_compressed(os.path.join(outdir, f"{name}.npz"), config=json.dumps(kw), batch=batch, frames=frames,
                             sigma=sigma, weight_seed=wseed, input_seed=iseed, mel=mel, z=z,
+                            speaker_ids=spk if spk is not None else np.zeros((0,), np.int64),
                             inverse_ref_fp32=outs["inverse_fp32"], inverse_ref_fp64=outs["inverse_fp64"],
                             infer_ref_fp32=outs["infer_fp32"], infer_ref_fp64=outs["infer_fp64"])
 

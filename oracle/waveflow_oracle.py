@@ -11,7 +11,9 @@ TEST INFRASTRUCTURE ONLY (same rules as waveglow_oracle.py).  numpy restatement 
 for the configuration subset the B200 build supports (and config 5 pins):
 waveflow=True, channel_mixing='permuteheight', mix_first=True, upsample_first=True, no model-level
 cond layers / upsample net / speaker embedding, WN_2d with one 1x1 cond layer, full (non-separable)
-kernel (kh, kw), dilation_h = 1, dilation_w = 2^i, GTU gate, res_skip without merge.
+kernel (kh, kw), dilation_h = 1, dilation_w = 2^i, GTU gate, res_skip without merge - plus the WN_config variants the fp32
+CUDA-core mode runs: the 14 gated units (glow_ax.py:168-198), listed width / height dilations (:506-517), merge_res_skip /
+res_skip=False (:541-553,:610-626), WN-level speaker embeddings (:464-466,:567-570), upsample_first=False (:578-579).
 
 Parity status: PINNED - `oracle/make_golden_waveflow.py` runs the unmodified reference model
 (`inverse` with explicit z and `infer` with the RNG draw replaced) and stores
@@ -66,6 +68,11 @@ def permute_height(x: np.ndarray, k: int) -> np.ndarray:
     return x[:, idx]
 
 
+def _gated_units():
+    from .waveglow_ax_oracle import GATED_UNITS
+    return GATED_UNITS
+
+
 def wn2d_step(sd, k, cfg: WaveFlowConfig, row: np.ndarray, spec_all: np.ndarray, queues, dtype):
     """One autoregressive step of WN_2d (glow_ax.py:556-635) with conv queues.
     row [B, T'] is the newest height row; spec_all [B, 2CL, T'] the cond-layer output;
@@ -77,12 +84,16 @@ def wn2d_step(sd, k, cfg: WaveFlowConfig, row: np.ndarray, spec_all: np.ndarray,
     w_s = _w(sd, p + "start", dtype).reshape(C)
     audio = w_s[None, :, None] * row[:, None, :] + np.asarray(sd[p + "start.bias"], dtype)[None, :, None]   # :558
     output = np.zeros_like(audio)
+    unit_a, unit_b = _gated_units()[cfg.gated_unit.upper()]
+    split = cfg.res_skip and not cfg.merge_res_skip
     for i in range(L):
-        d = 2 ** i
+        d, dh = cfg.dilation_w(i), cfg.dilation_h(i)
+        pad_h = (kh - 1) * dh                                            # :517
         if queues[i] is None:                                            # :597-599
-            queues[i] = np.zeros((B, C, kh - 1, T), dtype)
-        stack = np.concatenate([queues[i], audio[:, :, None, :]], axis=2)   # [B, C, kh, T']  :602
-        queues[i] = stack[:, :, 1:]
+            queues[i] = np.zeros((B, C, pad_h, T), dtype)
+        full = np.concatenate([queues[i], audio[:, :, None, :]], axis=2)    # [B, C, pad_h + 1, T']  :602
+        queues[i] = full[:, :, 1:]
+        stack = full[:, :, ::dh]                                         # the kh rows a height-dilated kernel touches
         sep = (p + f"in_layers.{i}.0.weight_v") in sd
         w_in = _w(sd, p + (f"in_layers.{i}.0" if sep else f"in_layers.{i}"), dtype)   # [2C, C, kh, kw] / depthwise [C, 1, kh, kw]
         pad = ((kw - 1) * d) // 2
@@ -103,10 +114,13 @@ def wn2d_step(sd, k, cfg: WaveFlowConfig, row: np.ndarray, spec_all: np.ndarray,
                     acts += np.einsum("oc,bct->bot", w_in[:, :, a, b], sp[:, :, a, b * d:b * d + T], optimize=True)
             acts += np.asarray(sd[p + f"in_layers.{i}.bias"], dtype)[None, :, None]
         acts += spec_all[:, 2 * C * i:2 * C * (i + 1)]                   # :585-608 (GTU: add, tanh*sigmoid)
-        g = np.tanh(acts[:, :C]) * (1.0 / (1.0 + np.exp(-acts[:, C:])))
-        w_rs = _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0, 0]
-        rs = np.einsum("oc,bct->bot", w_rs, g, optimize=True) + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
-        if i < L - 1:                                                    # :613-626
+        g = unit_a(acts[:, :C]) * unit_b(acts[:, C:])
+        if cfg.res_skip:
+            w_rs = _w(sd, p + f"res_skip_layers.{i}", dtype)[:, :, 0, 0]
+            rs = np.einsum("oc,bct->bot", w_rs, g, optimize=True) + np.asarray(sd[p + f"res_skip_layers.{i}.bias"], dtype)[None, :, None]
+        else:
+            rs = g                                                       # :610
+        if split and i < L - 1:                                          # :613-626 (merged: the hidden tensor stays)
             audio = audio + rs[:, :C]
             output = output + rs[:, C:]
         else:
@@ -127,7 +141,7 @@ def coupling_inverse(sd, k, cfg, audio_out: np.ndarray, spec_all: np.ndarray, dt
     return np.stack(z, axis=1)
 
 
-def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.float32, cond_up=None) -> np.ndarray:
+def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.float32, cond_up=None, speaker_ids=None) -> np.ndarray:
     """WaveGlow.inverse(z, cond) (efficient_model_ax.py:279-357): z [B, T] (already scaled by
     sigma), cond [B, n_mel, frames] -> audio [B, T].  `cond_up` (one [B, C, T'] array, or one per flow) replaces
     the plain interpolation when the model has a conditioning front-end (oracle/ax_frontend_oracle.py)."""
@@ -136,13 +150,20 @@ def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.f
     zz = z.reshape(B, -1, cfg.n_group).transpose(0, 2, 1)               # :310
     Tp = zz.shape[2]
     if cond_up is None:
-        cond_up = upsample_cond(np.asarray(cond, dtype), Tp, cfg.upsample_mode)   # :313-314
+        cond_up = np.asarray(cond, dtype)
+        if cfg.upsample_first:
+            cond_up = upsample_cond(cond_up, Tp, cfg.upsample_mode)      # :313-314
     C, L = cfg.n_channels, cfg.n_layers
     for k in reversed(range(cfg.n_flows)):                               # :325
         p = f"WN.{k}.WN.cond_layers.0"
-        w_c = _w(sd, p, dtype)[:, :, 0]                                  # [2CL, n_mel]
+        w_c = _w(sd, p, dtype)[:, :, 0]                                  # [2CL, n_mel (+ speaker dims)]
         k_cond = cond_up[k] if isinstance(cond_up, (list, tuple)) else cond_up      # :328
+        if cfg.wn_speaker_embed_dim:                                     # glow_ax.py:567-570
+            emb = np.asarray(sd[f"WN.{k}.WN.speaker_embed.weight"], dtype)[np.asarray(speaker_ids)]
+            k_cond = np.concatenate([k_cond, np.repeat(emb[:, :, None], k_cond.shape[2], axis=2)], axis=1)
         spec_all = np.einsum("oc,bct->bot", w_c, k_cond, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
+        if not cfg.upsample_first:                                       # glow_ax.py:578-579 (no WN upsample net)
+            spec_all = upsample_cond(spec_all, Tp, cfg.upsample_mode)
         zz = coupling_inverse(sd, k, cfg, zz, spec_all, dtype)           # :331
         zz = permute_height(zz, k)                                       # :336-337 (mix_first)
     return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)    # :346

@@ -155,3 +155,30 @@ def test_config5_batch_64_full_length_is_consistent():
     assert snr_db(ref, out[:1].numpy()) >= TOL["bf16x3"]["snr"]
     one, _ = m.inverse(z[37:38].cuda() * sigma, mel[37:38].cuda(), return_CPU=True)
     assert torch.equal(one[0], out[37])
+
+
+@pytest.mark.parametrize("name", ["waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker"])
+def test_wn2d_config_variants_match_reference(name):
+    """WN_config variants of WN_2d in the fp32 CUDA-core mode - gated units, width / height dilations (deeper conv queues),
+    merged / absent res_skip, WN-level speaker embedding with upsample_first=False (glow_ax.py:168-198,:464-466,:506-517,
+    :541-553,:567-579,:610-626) - against the unmodified reference's fp64 waveform.  A tensor-core precision request is
+    switched to fp32 with a warning."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+    sd = synthetic_state_dict(cfg, int(g["weight_seed"]))
+    with pytest.warns(UserWarning, match="fp32 CUDA-core"):
+        m = build(cfg, sd, "bf16x3")
+    assert m.precision == "ffma"
+    sigma = float(g["sigma"])
+    z, mel = torch.from_numpy(g["z"]).cuda(), torch.from_numpy(g["mel"]).cuda()
+    ids = torch.from_numpy(g["speaker_ids"]).cuda() if g["speaker_ids"].size else None
+    out, _ = m.inverse(z * sigma, mel, speaker_ids=ids, return_CPU=True)
+    ref = g["inverse_ref_fp64"]
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert max_abs(out.numpy(), ref) <= 1e-4 and snr_db(ref, out.numpy()) >= 100.0
+    aud = m.infer(mel, speaker_ids=ids, sigma=sigma, z=z)
+    assert aud.shape == g["infer_ref_fp64"].shape
+    assert max_abs(aud.numpy(), g["infer_ref_fp64"]) <= 1e-4
+    if ids is not None:                                       # ids are checked like the reference's embedding lookup
+        with pytest.raises(ValueError):
+            m.inverse(z * sigma, mel, speaker_ids=ids[:1])

@@ -12,7 +12,9 @@ from tests.helpers import GOLDEN_DIR, max_abs
 
 CASES = ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config5",
          # general WN_2d shapes: dense 5x3, depthwise-separable 7x7 at squeeze height 20 (16 and 128 channels)
-         "waveflow_5x3", "waveflow_sep7", "waveflow_sep7_128"]
+         "waveflow_5x3", "waveflow_sep7", "waveflow_sep7_128",
+         # WN_config variants: gated units, width / height dilations, merged / absent res_skip, WN speaker embedding
+         "waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker"]
 
 
 def load(name):
@@ -24,7 +26,8 @@ def load(name):
 @pytest.mark.parametrize("name", CASES)
 def test_inverse_fp64(name):
     cfg, sd, g = load(name)
-    out = inverse(sd, cfg, g["z"].astype(np.float64) * float(g["sigma"]), g["mel"], np.float64)
+    ids = g["speaker_ids"] if "speaker_ids" in g.files and g["speaker_ids"].size else None
+    out = inverse(sd, cfg, g["z"].astype(np.float64) * float(g["sigma"]), g["mel"], np.float64, speaker_ids=ids)
     assert max_abs(out, g["inverse_ref_fp64"]) < 1e-9
 
 
