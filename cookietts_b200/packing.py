@@ -123,21 +123,20 @@ def e5m2_bits_to_f32(b: np.ndarray) -> np.ndarray:
 
 
 def split_f16(w64: np.ndarray):
-    """w ~= hi + lo with both in fp16; returns uint16 bit planes.  (torch does the conversions: numpy's scalar
-    float64 -> float16 path is ~50x slower, which matters for the 270 M parameters of the notebook ax model; `lo` is taken
-    from the hi that was actually stored, so the split is exact to 2^-22 either way.)"""
-    import torch
-    w = torch.from_numpy(np.ascontiguousarray(w64, dtype=np.float64))
-    hi = w.to(torch.float16)
-    lo = (w - hi.to(torch.float64)).to(torch.float16)
-    return hi.view(torch.int16).numpy().view(np.uint16), lo.view(torch.int16).numpy().view(np.uint16)
+    """w ~= hi + lo with both in fp16; returns uint16 bit planes.  numpy converts float64 -> float16 with ONE rounding,
+    like the device's cvt.rn.f16.f64 (cwg_pack.cu); torch's CPU conversion goes through float32 and rounds twice, which
+    moves values on an fp16 tie by one ulp - up to 6e-8 in the subnormal range the lo planes of small weights live in."""
+    w64 = np.ascontiguousarray(w64, dtype=np.float64)
+    hi = w64.astype(np.float16)
+    lo = (w64 - hi.astype(np.float64)).astype(np.float16)
+    return hi.view(np.uint16), lo.view(np.uint16)
 
 
 def f8_correction_planes(w64: np.ndarray):
     """(h8, l8) = (e5m2(w16 * 2^-P), e5m2((w - w16) * 2^Q)) as uint8 bit planes."""
     import torch
     w = torch.from_numpy(np.ascontiguousarray(w64, dtype=np.float64))
-    w16 = w.to(torch.float16).to(torch.float64)
+    w16 = torch.from_numpy(w64.astype(np.float16).astype(np.float64))      # one rounding (see split_f16)
     h = (w16 * 2.0 ** -F8_P).to(torch.float32).clamp_(-57344.0, 57344.0).to(torch.float8_e5m2).view(torch.uint8).numpy()
     l = ((w - w16) * 2.0 ** F8_Q).to(torch.float32).clamp_(-57344.0, 57344.0).to(torch.float8_e5m2).view(torch.uint8).numpy()
     return h, l
