@@ -143,7 +143,8 @@ class AxFrontEndMixin:
                                                       rezero=a["transposed_conv_res_rezero"])
             self.interpolation_required = bool(int(np.prod(scales)) != self.upsample_factor)
             ch = t_out
-        need(not wn.get("transposed_conv_scales"), "the WN-level TransposedUpsampleNet (upsample_first=False) is not supported")
+        need(not wn.get("transposed_conv_scales") or getattr(self, "general", False),
+             "a WN-level TransposedUpsampleNet is served by WaveGlowAx's general fp32 mode only")
         # ---- n_flow_group_conv (efficient_model_ax.py:128-131)
         self._fe_group = None
         if a["group_conv_output_dim"]:
@@ -219,6 +220,21 @@ class AxFrontEndMixin:
                                    y.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
         return y
 
+    @staticmethod
+    def _tconv_chain(lib, h, tconvs, stream, last_scale=1.0):
+        """TransposedUpsampleNet.forward without the residual (glow_ax.py:233-236): ConvTranspose1d (+ LeakyReLU(0.4)) per
+        entry of `tconvs` = (w_phases, bias, c_in, c_out, k, stride, padding, has_act); the last output is scaled by
+        `last_scale` (ReZero res_weight)."""
+        n = len(tconvs)
+        for i, (w, b, cin, cout, k, s, p, has_act) in enumerate(tconvs):
+            Bh, _, T = h.shape
+            y = torch.empty(Bh, cout, (T - 1) * s - 2 * p + k, device=h.device, dtype=torch.float32)
+            _cabi.check(lib.cwg_conv_transpose1d(h.data_ptr(), Bh, cin, T, w.data_ptr(), b.data_ptr(), cout, k, s, p,
+                                                 ACT_LRELU if has_act else ACT_NONE, 0.4, last_scale if i == n - 1 else 1.0,
+                                                 y.data_ptr(), stream))
+            h = y
+        return h
+
     @torch.no_grad()
     def _fe_apply(self, spect: torch.Tensor, speaker_ids, n_steps: int) -> torch.Tensor:
         """spect [B, n_mel, frames] fp32 on the device (already shifted/scaled and zero-padded by `infer`) -> the cond
@@ -255,14 +271,8 @@ class AxFrontEndMixin:
             x_in = cond
             h = cond
             n = len(pk["tconv"])
-            for i, (w, b, cin, cout, k, s, p, has_act) in enumerate(pk["tconv"]):
-                Bh, _, T = h.shape
-                t_out = (T - 1) * s - 2 * p + k
-                y = torch.empty(Bh, cout, t_out, device=dev, dtype=torch.float32)
-                scale = pk["res_weight"] if (i == n - 1 and net.residual and pk.get("res_weight", 0.0) != 0.0) else 1.0
-                _cabi.check(lib.cwg_conv_transpose1d(h.data_ptr(), Bh, cin, T, w.data_ptr(), b.data_ptr(), cout, k, s, p,
-                                                     ACT_LRELU if has_act else ACT_NONE, 0.4, scale, y.data_ptr(), stream))
-                h = y
+            last_scale = pk["res_weight"] if (net.residual and pk.get("res_weight", 0.0) != 0.0) else 1.0
+            h = self._tconv_chain(lib, h, pk["tconv"], stream, last_scale)
             if net.residual:                                   # glow_ax.py:229-241
                 sf = int(np.prod(net.scales))
                 t_virtual = x_in.shape[2] * sf

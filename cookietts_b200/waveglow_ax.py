@@ -33,7 +33,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .ax_frontend import AxFrontEndMixin, _cond_act, PAD_MODES, ACT_NONE
+from .ax_frontend import AxFrontEndMixin, TransposedUpsampleNet, repack_conv_transpose, _cond_act, PAD_MODES, ACT_NONE
 from .packing import in_layer_weight_bias, split_f16, f8_correction_planes, PackConfig, split_hi_lo, effective_weight, _np, MAX_GROUP, group_pad
 
 
@@ -173,7 +173,7 @@ class _WN1d(nn.Module):
 
     def __init__(self, n_in, n_layers, n_channels, kernel_size, cond_in_channels, seperable_conv=False, speaker_embed_dim=0,
                  dilations=None, res_skip=True, merge_res_skip=False, cond_layers=1, cond_hidden_channels=256,
-                 cond_kernel_size=1, cond_padding_mode="zeros"):
+                 cond_kernel_size=1, cond_padding_mode="zeros", tconv=None):
         super().__init__()
         wn = nn.utils.weight_norm
         cond_in_channels += speaker_embed_dim                # glow_ax.py:255
@@ -196,9 +196,14 @@ class _WN1d(nn.Module):
         self.start = wn(nn.Conv1d(n_in, n_channels, 1), name="weight")
         self.end = nn.Conv1d(n_channels, 2 * n_in, 1)
         self.end.weight.data.zero_(); self.end.bias.data.zero_()
+        cond_out = 2 * n_channels * n_layers
+        if tconv:                                            # WN-level upsample net (upsample_first=False), glow_ax.py:288-295,:302
+            self.upsample_net = TransposedUpsampleNet(tconv["hidden"], cond_out, tconv["hidden"], tconv["kernel_size"],
+                                                      tconv["scales"], use_last_layer_act_func=False)
+            cond_out = tconv["hidden"]
         if cond_layers:                                      # glow_ax.py:297-314
             kc = 2 * cond_kernel_size - 1
-            dims = [cond_in_channels] + [cond_hidden_channels] * (cond_layers - 1) + [2 * n_channels * n_layers]
+            dims = [cond_in_channels] + [cond_hidden_channels] * (cond_layers - 1) + [cond_out]
             self.cond_layers = nn.ModuleList([
                 wn(nn.Conv1d(di, do, kc, padding=(kc - 1) // 2, padding_mode=cond_padding_mode), name="weight")
                 for di, do in zip(dims[:-1], dims[1:])])
@@ -276,7 +281,14 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                              act=_cond_act(wn.get("cond_activation_func", "none"), wn.get("negative_slope")) if wn.get("cond_layers", 1) else (ACT_NONE, 0.0),
                              out_act=bool(wn.get("cond_out_activation_func", True)))
         need(self._wn_cond["padding_mode"] in PAD_MODES, "WN cond_padding_mode must be zeros / replicate / reflect / circular")
-        linear_cond = self._wn_cond["layers"] == 1 and self._wn_cond["kernel_size"] == 1 and self._wn_cond["act"][0] == ACT_NONE
+        self._wn_tconv = None
+        if wn.get("transposed_conv_scales") and wn.get("transposed_conv_hidden_dim", 256) and wn.get("transposed_conv_kernel_size", 4):
+            need(upsample_first is False, "a WN-level TransposedUpsampleNet needs upsample_first=False (glow_ax.py:302,:389: with "
+                                          "upsample_first=True the reference builds it but feeds the WN the wrong channel count)")
+            self._wn_tconv = dict(scales=[int(x) for x in wn["transposed_conv_scales"]], hidden=int(wn.get("transposed_conv_hidden_dim", 256)),
+                                  kernel_size=wn.get("transposed_conv_kernel_size", 4))
+        linear_cond = (self._wn_cond["layers"] == 1 and self._wn_cond["kernel_size"] == 1 and self._wn_cond["act"][0] == ACT_NONE
+                       and self._wn_tconv is None)
         self._gate = GATED_UNITS[gate]
         self.general = bool(self._gate or self._dilations is not None or self._merge or not self._res_skip or not linear_cond
                             or n_group > MAX_GROUP)
@@ -319,7 +331,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
                                      speaker_embed_dim=self.wn_speaker_embed_dim, dilations=self._dilations,
                                      res_skip=self._res_skip, merge_res_skip=self._merge, cond_layers=self._wn_cond["layers"],
                                      cond_hidden_channels=self._wn_cond["hidden"], cond_kernel_size=self._wn_cond["kernel_size"],
-                                     cond_padding_mode=self._wn_cond["padding_mode"]))
+                                     cond_padding_mode=self._wn_cond["padding_mode"], tconv=self._wn_tconv))
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -396,11 +408,17 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             cond = [(up(effective_weight(sd, p + f"cond_layers.{i}")), up(sd[p + f"cond_layers.{i}.bias"]))
                     for i in range(self._wn_cond["layers"])]
             emb = up(sd[p + "speaker_embed.weight"]) if self.wn_speaker_embed_dim else None
+            tconv = []
+            if self._wn_tconv:
+                for (idx, kk, st, pd, act) in self.WN[k].WN.upsample_net.layers:
+                    wt = sd[p + f"upsample_net.t_convs.{idx}.weight"]
+                    tconv.append((up(repack_conv_transpose(wt, st)), up(sd[p + f"upsample_net.t_convs.{idx}.bias"]),
+                                  wt.shape[0], wt.shape[1], kk, st, pd, act))
             group = None
             if self._fe_group:                                # flow k's slice of n_flow_group_conv, applied explicitly here
                 wg, bg = self.group_conv_fold(k, np.eye(self._fe_group[0]), np.zeros(self._fe_group[0]), sd)
                 group = (up(wg[:, :, None]), up(bg))
-            flows.append(dict(cfg=cfg, w=w, arrs=arrs, cond=cond, emb=emb, group=group))
+            flows.append(dict(cfg=cfg, w=w, arrs=arrs, cond=cond, emb=emb, group=group, tconv=tconv))
         self.pack_config = pc
         self._packed, self._packed_key, self._graphs = {"flows": flows}, key, {}
 
@@ -462,7 +480,20 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             for i, (w, b) in enumerate(f["cond"]):           # :383-387
                 a = act if (wc["out_act"] or i != n - 1) else ACT_NONE
                 x = self._conv1d(lib, x, w, b, pad, pad_mode, a, slope)
-            if not self.upsample_first and x.shape[2] != Tp:   # :389, _upsample_mels :361-373 without a WN upsample net
+            if not self.upsample_first and f["tconv"]:       # :389, _upsample_mels :361-373 with the WN's upsample net
+                x = self._tconv_chain(lib, x, f["tconv"], stream)
+                if int(np.prod(self._wn_tconv["scales"])) != self.hop_length // G and x.shape[2] != Tp:   # interpolation_required
+                    x = self._resample(lib, x, Tp, stream)
+                else:                                        # centre crop :367-372
+                    diff = x.shape[2] - Tp
+                    if diff <= 0 or diff // 2 == 0 or x.shape[2] - 2 * (diff // 2) != Tp:
+                        raise RuntimeError(f"WN {k}: upsampled cond length {x.shape[2]} cannot be cropped to {Tp} group-steps "
+                                           "(the reference's slice is empty or mis-sized here too)")
+                    y = torch.empty(B, x.shape[1], Tp, device=dev, dtype=torch.float32)
+                    _cabi.check(lib.cwg_resample1d(x.data_ptr(), B, x.shape[1], x.shape[2], x.shape[1] * x.shape[2], y.data_ptr(),
+                                                   Tp, x.shape[1] * Tp, 0, x.shape[2], diff // 2, 0.0, 0, stream))
+                    x = y
+            elif not self.upsample_first and x.shape[2] != Tp:   # ... without one: interpolation_required, F.interpolate
                 x = self._resample(lib, x, Tp, stream)
             need_ch = 2 * self._base["n_channels"] * self._base["n_layers"]
             if x.shape[1] != need_ch or x.shape[2] != Tp:

@@ -86,6 +86,9 @@ def reference_kwargs_ax1d(cfg) -> dict:
               cond_padding_mode=cfg.wn_cond_padding_mode, seperable_conv=cfg.seperable_conv, res_skip=cfg.res_skip,
               merge_res_skip=cfg.merge_res_skip, upsample_mode=cfg.upsample_mode, gated_unit=cfg.gated_unit,
               cond_out_activation_func=cfg.wn_cond_out_activation_func)
+    if cfg.wn_tconv_scales:                     # WN-level TransposedUpsampleNet (glow_ax.py:288-295)
+        wn.update(transposed_conv_scales=list(cfg.wn_tconv_scales), transposed_conv_hidden_dim=cfg.wn_tconv_hidden_dim,
+                  transposed_conv_kernel_size=cfg.wn_tconv_kernel_size)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_early_every, n_early_size=cfg.n_early_size, memory_efficient=0.0,
                 spect_scaling=False, upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,
@@ -121,6 +124,15 @@ AX_CASES = {
                                wn_cond_padding_mode="replicate", wn_cond_activation_func="relu", wn_negative_slope=0.3,
                                wn_cond_out_activation_func=False, upsample_first=False, wn_speaker_embed_dim=5, gated_unit="GLU"),
                           2, 7, 0.8, 64, 14),
+    # WN-level TransposedUpsampleNet (upsample_first=False): 2-layer activated cond stack -> 10 hidden channels -> two
+    # transposed convs (x2, x1... product 2 = hop / n_group: centre crop; infer only - `inverse` on an un-padded mel hits
+    # the reference's empty-slice bug, glow_ax.py:367-372) ...
+    "waveglow_axv_tconv_crop": (dict(_V, n_group=8, hop_length=16, upsample_first=False, wn_cond_layers=2, wn_cond_hidden_channels=9,
+                                     wn_cond_activation_func="tanh", wn_tconv_scales=[2], wn_tconv_hidden_dim=10,
+                                     wn_tconv_kernel_size=4, gated_unit="GTRU"), 2, 7, 0.8, 66, 16),
+    # ... and with a scale product (3 x 2 = 6) != hop / n_group (4): the upsampled cond is interpolated to T'
+    "waveglow_axv_tconv_interp": (dict(_V, n_group=4, hop_length=16, upsample_first=False, wn_tconv_scales=[3, 2],
+                                       wn_tconv_hidden_dim=6, wn_tconv_kernel_size=[5, 4]), 1, 6, 0.9, 67, 17),
     # every remaining unit on one tiny model each (one flow pair, 2 layers)
     **{f"waveglow_axv_unit_{u.lower()}": (dict(_V, n_flows=2, n_early_every=4, n_layers=2, gated_unit=u), 1, 5, 0.9, 70 + i, 20 + i)
        for i, u in enumerate(["GTRU", "TTU", "STU", "GTSU", "GSIU", "GSIRU", "GTSRU", "GSIRLRU", "GSIRRLRU"])},
@@ -151,11 +163,14 @@ def main_ax(WaveGlowAx, outdir, only=()):
                 for conv in model.convinv:        # W_inverse is always created fp32 (efficient_modules.py:271-275)
                     conv.W_inverse = conv.weight.squeeze().double().inverse().unsqueeze(-1)
             with torch.no_grad():
-                inv, _ = model.inverse(torch.from_numpy(z).to(dt) * sigma, torch.from_numpy(mel).to(dt), speaker_ids=ids)
-                outs["inverse_" + tag] = inv.numpy()
                 with InjectedNormal([torch.from_numpy(z)]):
                     aud = model.infer(torch.from_numpy(mel).to(dt), speaker_ids=ids, sigma=sigma)
                 outs["infer_" + tag] = aud.numpy()
+                if name.endswith("_crop"):        # inverse(z, mel) with an un-padded mel: the reference's crop is empty there
+                    outs["inverse_" + tag] = aud.numpy()
+                else:
+                    inv, _ = model.inverse(torch.from_numpy(z).to(dt) * sigma, torch.from_numpy(mel).to(dt), speaker_ids=ids)
+                    outs["inverse_" + tag] = inv.numpy()
         e1 = np.abs(outs["inverse_fp32"] - outs["inverse_fp64"]).max()
         print(f"{name}: inverse {outs['inverse_fp64'].shape} infer {outs['infer_fp64'].shape} "
               f"rms {np.sqrt((outs['inverse_fp64'] ** 2).mean()):.3f} fp32-vs-fp64 {e1:.2e}")

@@ -58,6 +58,11 @@ class AxConfig:
     wn_cond_activation_func: str = "none"
     wn_negative_slope: Optional[float] = None
     wn_cond_out_activation_func: bool = True
+    # WN-level TransposedUpsampleNet (upsample_first=False; glow_ax.py:288-295,:361-373): cond stack -> hidden_dim channels ->
+    # ConvTranspose1d chain (LeakyReLU(0.4) between, not after) -> 2CL channels -> F.interpolate or centre crop
+    wn_tconv_scales: Optional[List[int]] = None
+    wn_tconv_hidden_dim: int = 256
+    wn_tconv_kernel_size: object = 4     # int or one per scale
 
     def dilation(self, i: int) -> int:
         if self.dilations_w is None:
@@ -66,7 +71,8 @@ class AxConfig:
 
     def is_variant(self) -> bool:
         return (self.gated_unit.upper() != "GTU" or self.dilations_w is not None or not self.res_skip or self.merge_res_skip
-                or self.wn_cond_layers != 1 or self.wn_cond_kernel_size != 1 or self.wn_cond_activation_func.lower() != "none")
+                or self.wn_cond_layers != 1 or self.wn_cond_kernel_size != 1 or self.wn_cond_activation_func.lower() != "none"
+                or bool(self.wn_tconv_scales))
 
     def flow_channels(self) -> List[int]:
         out, n_rem = [], self.n_group
@@ -116,7 +122,7 @@ def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
     if cfg.wn_speaker_embed_dim and speaker_ids is not None:             # :378-381
         emb = np.asarray(sd[p + "speaker_embed.weight"], dtype)[np.asarray(speaker_ids)]
         cond_up = np.concatenate([cond_up, np.repeat(emb[:, :, None], cond_up.shape[2], axis=2)], axis=1)
-    if cfg.wn_cond_layers == 1 and cfg.wn_cond_kernel_size == 1 and cfg.wn_cond_activation_func.lower() == "none":
+    if cfg.wn_cond_layers == 1 and cfg.wn_cond_kernel_size == 1 and cfg.wn_cond_activation_func.lower() == "none" and not cfg.wn_tconv_scales:
         spect = np.einsum("oc,bct->bot", _w(sd, p + "cond_layers.0", dtype)[:, :, 0], cond_up, optimize=True) \
             + np.asarray(sd[p + "cond_layers.0.bias"], dtype)[None, :, None]
     else:                                                                # general cond stack, :297-329 / :383-387
@@ -128,8 +134,22 @@ def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
                            pad, cfg.wn_cond_padding_mode)
             if cfg.wn_cond_activation_func.lower() != "none" and (cfg.wn_cond_out_activation_func or i != cfg.wn_cond_layers - 1):
                 spect = _act(spect, cfg.wn_cond_activation_func, cfg.wn_negative_slope)
-    if not cfg.upsample_first:                                           # :389 -> _upsample_mels :361-373 (no WN upsample net:
-        spect = upsample_cond(spect, T, cfg.upsample_mode)               # interpolation_required, F.interpolate to audio length)
+    if not cfg.upsample_first and cfg.wn_tconv_scales:                   # :389 -> _upsample_mels :361-373 with the WN's upsample net
+        from .ax_frontend_oracle import conv_transpose1d
+        ks, n = cfg.wn_tconv_kernel_size, len(cfg.wn_tconv_scales)
+        for i, sc in enumerate(cfg.wn_tconv_scales):
+            kk = ks[i] if isinstance(ks, (list, tuple)) else ks
+            spect = conv_transpose1d(spect, np.asarray(sd[p + f"upsample_net.t_convs.{2 * i}.weight"], dtype),
+                                     np.asarray(sd[p + f"upsample_net.t_convs.{2 * i}.bias"], dtype), sc, (kk - sc) // 2)
+            if i < n - 1:                                                # use_last_layer_act_func=False (:294)
+                spect = np.where(spect >= 0, spect, spect * dtype(0.4))
+        if int(np.prod(cfg.wn_tconv_scales)) != cfg.hop_length // cfg.n_group and spect.shape[2] != T:   # interpolation_required
+            spect = upsample_cond(spect, T, cfg.upsample_mode)
+        else:                                                            # centre crop :367-372
+            pad_l, pad_r = (spect.shape[2] - T) // 2, (-(T - spect.shape[2])) // 2
+            spect = spect[:, :, pad_l:spect.shape[2] - pad_r] if pad_r else spect[:, :, pad_l:0]
+    elif not cfg.upsample_first:                                         # no WN upsample net: interpolation_required,
+        spect = upsample_cond(spect, T, cfg.upsample_mode)               # F.interpolate to the audio length
     output = None
     unit_a, unit_b = GATED_UNITS[cfg.gated_unit.upper()]
     split = cfg.res_skip and not cfg.merge_res_skip
@@ -213,14 +233,14 @@ def inverse(sd, cfg: AxConfig, z, cond, dtype=np.float32, cond_up=None, ignore_n
     return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)
 
 
-def infer_with_z(sd, cfg: AxConfig, spect, z, sigma, artifact_trimming=1, dtype=np.float32):
+def infer_with_z(sd, cfg: AxConfig, spect, z, sigma, artifact_trimming=1, dtype=np.float32, speaker_ids=None):
     spect = np.asarray(spect, dtype)
     if artifact_trimming > 0:
         spect = np.concatenate([spect, np.zeros(spect.shape[:2] + (artifact_trimming,), dtype)], axis=2)
     samples = (spect.shape[2] - 1) * cfg.hop_length
     samples -= samples % cfg.n_group
     assert z.shape[1] == samples
-    audio = inverse(sd, cfg, np.asarray(z, dtype) * dtype(sigma), spect, dtype)
+    audio = inverse(sd, cfg, np.asarray(z, dtype) * dtype(sigma), spect, dtype, speaker_ids=speaker_ids)
     return audio[:, :-artifact_trimming * cfg.hop_length] if artifact_trimming > 0 else audio
 
 
@@ -259,9 +279,18 @@ def synthetic_state_dict(cfg: AxConfig, seed: int = 1234, cond_in_channels=None)
         sd[p + "end.bias"] = (rs.standard_normal((2 * n_half,)) * 0.02).astype(np.float32)
         cin = (cond_in_channels or cfg.n_mel_channels) + cfg.wn_speaker_embed_dim
         kc = 2 * cfg.wn_cond_kernel_size - 1
-        dims = [cin] + [cfg.wn_cond_hidden_channels] * (cfg.wn_cond_layers - 1) + [2 * C * L]
+        cond_out = cfg.wn_tconv_hidden_dim if cfg.wn_tconv_scales else 2 * C * L        # glow_ax.py:302
+        dims = [cin] + [cfg.wn_cond_hidden_channels] * (cfg.wn_cond_layers - 1) + [cond_out]
         for i, (di, do) in enumerate(zip(dims[:-1], dims[1:])):
             wn(p + f"cond_layers.{i}", (do, di, kc), di * kc)
+        if cfg.wn_tconv_scales:                                          # TransposedUpsampleNet(hidden, 2CL, hidden, ...), :290-294
+            n = len(cfg.wn_tconv_scales)
+            for i, sc in enumerate(cfg.wn_tconv_scales):
+                kk = cfg.wn_tconv_kernel_size[i] if isinstance(cfg.wn_tconv_kernel_size, (list, tuple)) else cfg.wn_tconv_kernel_size
+                ci, co = cfg.wn_tconv_hidden_dim, (2 * C * L if i == n - 1 else cfg.wn_tconv_hidden_dim)
+                bound = 1.0 / np.sqrt(ci * kk / sc)
+                sd[p + f"upsample_net.t_convs.{2 * i}.weight"] = rs.uniform(-bound, bound, size=(ci, co, kk)).astype(np.float32)
+                sd[p + f"upsample_net.t_convs.{2 * i}.bias"] = rs.uniform(-bound, bound, size=(co,)).astype(np.float32)
         if cfg.wn_speaker_embed_dim:
             sd[p + "speaker_embed.weight"] = rs.standard_normal((512, cfg.wn_speaker_embed_dim)).astype(np.float32)
     return sd

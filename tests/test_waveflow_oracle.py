@@ -68,7 +68,8 @@ def test_ax_1d_oracle_matches_reference(name):
         assert max_abs(out2, g["infer_ref_fp64"]) < 1e-9
 
 
-AXV_CASES = ["waveglow_axv_gsirru", "waveglow_axv_merge", "waveglow_axv_noskip", "waveglow_axv_cond", "waveglow_axv_256"] + [
+AXV_CASES = ["waveglow_axv_gsirru", "waveglow_axv_merge", "waveglow_axv_noskip", "waveglow_axv_cond", "waveglow_axv_256",
+             "waveglow_axv_tconv_crop", "waveglow_axv_tconv_interp"] + [
     "waveglow_axv_unit_" + u for u in ("gtru", "ttu", "stu", "gtsu", "gsiu", "gsiru", "gtsru", "gsirlru", "gsirrlru")]
 
 
@@ -76,13 +77,18 @@ AXV_CASES = ["waveglow_axv_gsirru", "waveglow_axv_merge", "waveglow_axv_noskip",
 def test_ax_wn_variants_oracle_matches_reference(name):
     """The WN_config variants (gated units, listed dilations, merged / absent res_skip, multi-layer cond stacks, glow_ax.py:
     168-198,:297-335,:399-414) of oracle/waveglow_ax_oracle.py against the unmodified reference."""
-    from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd, inverse as ax_inverse
+    from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd, inverse as ax_inverse, infer_with_z as ax_infer
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     cfg = AxConfig(**json.loads(str(g["config"])))
     assert cfg.is_variant()
     sd = ax_sd(cfg, int(g["weight_seed"]))
     ids = g["speaker_ids"] if g["speaker_ids"].size else None
-    out = ax_inverse(sd, cfg, g["z"].astype(np.float64) * float(g["sigma"]), g["mel"], np.float64, speaker_ids=ids)
     # the SIREN units multiply rounding differences by 16 per layer: scale the bar with the reference's own fp32-vs-fp64 gap
-    gap = max_abs(g["inverse_ref_fp32"], g["inverse_ref_fp64"])
-    assert max_abs(out, g["inverse_ref_fp64"]) < max(1e-9, 1e-4 * gap)
+    gap = max_abs(g["infer_ref_fp32"], g["infer_ref_fp64"])
+    if not name.endswith("_crop"):       # (the reference's centre crop is empty for `inverse` on an un-padded mel)
+        out = ax_inverse(sd, cfg, g["z"].astype(np.float64) * float(g["sigma"]), g["mel"], np.float64, speaker_ids=ids)
+        assert max_abs(out, g["inverse_ref_fp64"]) < max(1e-9, 1e-4 * max_abs(g["inverse_ref_fp32"], g["inverse_ref_fp64"]))
+    if cfg.n_channels <= 16:
+        out2 = ax_infer(sd, cfg, g["mel"], g["z"], float(g["sigma"]), 1, np.float64, speaker_ids=ids)
+        assert out2.shape == g["infer_ref_fp64"].shape
+        assert max_abs(out2, g["infer_ref_fp64"]) < max(1e-9, 1e-4 * gap)
