@@ -8,7 +8,8 @@
 //   efficient_modules.py:360-403 PermuteHeight (host-side column bookkeeping).
 // WN_config variants (ABI 5): every gated unit of glow_ax.py:168-198, listed width / height dilations (:513-517; the ring
 // of a layer holds (kernel_h - 1) * dilation_h + 1 rows), merge_res_skip / res_skip=False (packing only: zero res rows),
-// WN-level speaker embeddings (a per-utterance gate bias, cwg_wf_weights.b1_batch).
+// WN-level speaker embeddings (a per-utterance gate bias, cwg_wf_weights.b1_batch), early outputs (efficient_model_ax.py:
+// 319-322,:339-340: a flow works on the trailing n_rem height rows only) and mix_first = 0 (PermuteHeight before the coupling).
 #include "cwg_common.cuh"
 
 namespace cwg {
@@ -141,6 +142,19 @@ __global__ void k_wff_row(long long BT, int G, int C, const float* __restrict__ 
   for (int c = threadIdx.x; c < C; c += blockDim.x) x0[(size_t)m * C + c] = fmaf(__ldg(start_w + c), v, __ldg(start_b + c));
 }
 
+__global__ void k_wff_scale(const float* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scale;
+}
+
+// rows the flow k works on (efficient_model_ax.py:151-167)
+inline int wff_n_rem(const cwg_wf_config* c, int k) {
+  int n = c->n_group;
+  if (c->n_early_every > 0)
+    for (int j = 1; j <= k; ++j) if (j % c->n_early_every == 0) n -= c->n_early_size;
+  return n;
+}
+
 void wff_perm(int k, int h, int* idx) {               // PermuteHeight index list of flow k (efficient_modules.py:341-353)
   if (k % 4 == 2 || k % 4 == 3) {
     const int half = h / 2;
@@ -181,6 +195,7 @@ int wff_check(const cwg_wf_config* c, int batch, int t_samples) {
   CWG_REQUIRE(c->gate >= 0 && c->gate < CWG_GATE_COUNT, "unknown gated unit %d", c->gate);
   for (int l = 0; l < c->n_layers; ++l)
     CWG_REQUIRE(c->dilations_w[l] >= 0 && c->dilations_h[l] >= 0 && c->dilations_h[l] <= 64, "bad dilations of layer %d", l);
+  CWG_REQUIRE(c->n_early_every >= 0 && c->n_early_size >= 0 && wff_n_rem(c, c->n_flows - 1) >= 2, "too many early outputs for n_group");
   return 0;
 }
 
@@ -192,7 +207,9 @@ size_t wff_workspace_bytes(const cwg_wf_config* c, int batch, int t_samples) {
 }
 
 int wff_launch_count(const cwg_wf_config* c) {
-  return 1 + c->n_flows * (c->n_group + (c->n_group - 1) * c->n_layers * 3);
+  int n = 1 + (wff_n_rem(c, c->n_flows - 1) < c->n_group ? 1 : 0);
+  for (int k = 0; k < c->n_flows; ++k) { const int h = wff_n_rem(c, k); n += h + (h - 1) * c->n_layers * 3; }
+  return n;
 }
 
 int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* mel, int frames, int pad_frames,
@@ -213,13 +230,28 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
     k_wff_mel_up<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mel, ws.mel_up, batch, M, frames, frames + pad_frames, Tp, cfg->upsample_linear);
     CWG_CHECK_CUDA(cudaGetLastError());
   }
+  // phys[c]: column of the [BT][G] state that holds logical height row c.  A flow with early outputs in front of it
+  // (efficient_model_ax.py:319-322,:339-340) works on the trailing n_rem logical rows only.
   int phys[WFF_MAX_GROUP], perm[WFF_MAX_GROUP], nxt[WFF_MAX_GROUP];
-  for (int c = 0; c < h; ++c) phys[c] = c;
+  const int G = cfg->n_group;
+  for (int c = 0; c < G; ++c) phys[c] = c;
   const size_t slot = (size_t)BT * C;                              // one ring row of one layer
+  const bool early = wff_n_rem(cfg, F - 1) < G;
+  if (early) {                                                     // rows the first flow does not touch must be sigma * z too
+    const long long n = BT * G;
+    k_wff_scale<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, ws.state, n, sigma);
+    CWG_CHECK_CUDA(cudaGetLastError());
+  }
+  auto permute = [&](int h, int off) {
+    for (int c = 0; c < h; ++c) nxt[c] = phys[off + perm[c]];
+    for (int c = 0; c < h; ++c) phys[off + c] = nxt[c];
+  };
   int ev = 0;
   for (int k = F - 1; k >= 0; --k) {
+    const int h = wff_n_rem(cfg, k), off = G - h;                  // active rows: logical off .. G-1
     wff_perm(k, h, perm);
-    const bool first_flow = k == F - 1, last_flow = k == 0;
+    const bool from_z = k == F - 1 && !early, last_flow = k == 0;
+    if (cfg->mix_first_off) permute(h, off);                       // mix_first = 0: PermuteHeight.inverse before the coupling
     for (int i = -1; i < h - 1; ++i) {
       if (i >= 0) {
         for (int l = 0; l < L; ++l, ++ev) {
@@ -247,15 +279,17 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
           if (ev < n_events) CWG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)ev_end[ev], s));
         }
       }
-      const int j = i + 1;                                         // logical row produced now
+      const int j = i + 1;                                         // active row produced now (logical row off + j)
       float* x0 = j < h - 1 ? ws.x + (size_t)(j % R) * slot : nullptr;         // ring of layer 0
-      k_wff_row<<<(unsigned)BT, 128, 0, s>>>(BT, h, C, first_flow ? z : ws.state, first_flow ? sigma : 1.f, phys[j],
-                                            last_flow ? audio : ws.state, last_flow ? perm[j] : phys[j], ws.eo, i >= 0,
+      // the last flow (h = G, off = 0) writes the waveform in its final logical order: after the coupling the mixing moves
+      // row j to perm[j] (an involution); with mix_first = 0 nothing follows the coupling
+      const int col_out = last_flow ? (cfg->mix_first_off ? j : perm[j]) : phys[off + j];
+      k_wff_row<<<(unsigned)BT, 128, 0, s>>>(BT, G, C, from_z ? z : ws.state, from_z ? sigma : 1.f, phys[off + j],
+                                            last_flow ? audio : ws.state, col_out, ws.eo, i >= 0,
                                             w->start_w + (size_t)k * C, w->start_b + (size_t)k * C, x0);
       CWG_CHECK_CUDA(cudaGetLastError());
     }
-    for (int c = 0; c < h; ++c) nxt[c] = phys[perm[c]];
-    for (int c = 0; c < h; ++c) phys[c] = nxt[c];
+    if (!cfg->mix_first_off) permute(h, off);                      // mix_first: PermuteHeight.inverse after the coupling
   }
   return 0;
 }

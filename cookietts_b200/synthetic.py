@@ -130,6 +130,18 @@ class WaveFlowConfig:
     merge_res_skip: bool = False
     wn_speaker_embed_dim: int = 0   # WN_config['speaker_embed_dim'], glow_ax.py:464-466
     upsample_first: bool = True     # False: the WN interpolates its cond-layer output (glow_ax.py:578-579)
+    n_early_every: int = 0          # early outputs (efficient_model_ax.py:151-167); 0 = none
+    n_early_size: int = 2
+    mix_first: bool = True          # False: PermuteHeight before the coupling (efficient_model_ax.py:326-337)
+
+    def flow_rows(self):
+        """Height rows each flow works on."""
+        out, n = [], self.n_group
+        for k in range(self.n_flows):
+            if self.n_early_every and k % self.n_early_every == 0 and k > 0:
+                n -= self.n_early_size
+            out.append(n)
+        return out
 
     def dilation_w(self, i: int) -> int:
         if self.dilations_w is None:
@@ -183,11 +195,11 @@ def waveflow_reference_kwargs(cfg: WaveFlowConfig) -> dict:
               cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv,
               res_skip=cfg.res_skip, merge_res_skip=cfg.merge_res_skip, upsample_mode=cfg.upsample_mode, gated_unit=cfg.gated_unit)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
-                n_early_every=cfg.n_flows * 2, n_early_size=2, memory_efficient=0.0, spect_scaling=False,
+                n_early_every=cfg.n_early_every or cfg.n_flows * 2, n_early_size=cfg.n_early_size, memory_efficient=0.0, spect_scaling=False,
                 upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,
                 cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
                 cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
-                sampling_rate=22050, channel_mixing="permuteheight", mix_first=True, waveflow=True)
+                sampling_rate=22050, channel_mixing="permuteheight", mix_first=cfg.mix_first, waveflow=True)
 
 
 

@@ -13,7 +13,8 @@ WN_config variants of WN_2d run in the fp32 CUDA-core mode (csrc/cwg_wf_ffma.cu;
 "ffma" with a warning): every gated unit of glow_ax.py:168-198, listed width / height dilations (:506-517), `merge_res_skip` /
 `res_skip=False` (:541-553,:610-626 - the hidden tensor is then never updated: zero res rows at pack time), WN-level speaker
 embeddings (:464-466,:567-570 - a per-utterance gate bias), `upsample_first=False` (:578-579 - interpolation commutes with
-the one linear 1x1 cond layer).
+the one linear 1x1 cond layer), early outputs (efficient_model_ax.py:151-167,:319-340 - a flow works on the trailing
+n_rem height rows) and `mix_first=False`.
 """
 from __future__ import annotations
 
@@ -52,6 +53,9 @@ class WaveFlowPackConfig:
     res_skip: bool = True
     merge_res_skip: bool = False
     wn_speaker_dim: int = 0      # WN-level speaker embedding: the last columns of every cond layer
+    n_early_every: int = 0       # early outputs; 0 = none
+    n_early_size: int = 0
+    mix_first: bool = True
 
     @property
     def k1(self) -> int:
@@ -117,7 +121,8 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
 class CwgWfConfig(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_mel", "n_flows", "n_group", "n_layers", "n_channels",
                                            "kernel_h", "kernel_w", "hop_length", "upsample_linear", "gate")]
-                + [("dilations_w", C.c_int32 * 16), ("dilations_h", C.c_int32 * 16)])
+                + [("dilations_w", C.c_int32 * 16), ("dilations_h", C.c_int32 * 16)]
+                + [(n, C.c_int32) for n in ("n_early_every", "n_early_size", "mix_first_off")])
 
 
 WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "w1_f32", "w2_f32")
@@ -219,7 +224,8 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             n_channels=wn["n_channels"], kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
             hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear", fp32=precision == "ffma",
             gate=v["gate"], dilations_w=v["dilations_w"], dilations_h=v["dilations_h"], res_skip=v["res_skip"],
-            merge_res_skip=v["merge"], wn_speaker_dim=v["speaker_dim"])
+            merge_res_skip=v["merge"], wn_speaker_dim=v["speaker_dim"], n_early_every=v["n_early_every"],
+            n_early_size=v["n_early_size"], mix_first=v["mix_first"])
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
                                            cond_in_channels=self.wn_cond_in_channels,
@@ -239,11 +245,12 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                 raise NotImplementedError("cookietts_b200.WaveFlow: " + msg)
         need(a["waveflow"], "only waveflow=True (WN_2d) is built; use cookietts_b200.WaveGlow for the classic model")
         need(str(a["channel_mixing"]).lower() in "waveflowpermuteheightpermutechannelpermute", "channel_mixing must be 'permuteheight'")
-        need(a["mix_first"], "mix_first=False is not supported")
         need(a["upsample_first"] is True or (a["upsample_first"] is False and not a["transposed_conv_scales"]),
              "upsample_first must be True, or False without a model-level TransposedUpsampleNet")
         need(a["n_flows"] % 2 == 0, "PermuteHeight requires an even n_flows (efficient_modules.py:370)")
-        need(a["n_early_every"] >= a["n_flows"], "early outputs are not supported with waveflow (set n_early_every >= n_flows)")
+        early = a["n_early_every"] < a["n_flows"]
+        n_rem = a["n_group"] - a["n_early_size"] * ((a["n_flows"] - 1) // a["n_early_every"])
+        need(not early or (a["n_early_size"] >= 1 and n_rem >= 2), "too many early outputs for n_group")
         need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1, "WN cond_layers must be one 1x1 conv")
         need(wn.get("cond_activation_func", "none") == "none", "WN cond activation is not supported")
         need(precision in ("bf16x3", "bf16", "ffma"), "precision must be 'bf16x3', 'bf16' or 'ffma'")
@@ -262,12 +269,16 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         if not (res_skip or merge):
             raise AssertionError("Cannot remove res_skip without using merge_res_skip")      # glow_ax.py:434
         self._variant = dict(gate=GATED_UNITS[gate], dilations_w=dw, dilations_h=dh, res_skip=res_skip, merge=merge,
-                             speaker_dim=int(wn.get("speaker_embed_dim", 0) or 0))
-        variant = bool(self._variant["gate"] or dw or dh or merge or not res_skip or self._variant["speaker_dim"])
+                             speaker_dim=int(wn.get("speaker_embed_dim", 0) or 0),
+                             n_early_every=int(a["n_early_every"]) if early else 0, n_early_size=int(a["n_early_size"]) if early else 0,
+                             mix_first=bool(a["mix_first"]))
+        variant = bool(self._variant["gate"] or dw or dh or merge or not res_skip or self._variant["speaker_dim"] or early
+                       or not a["mix_first"])
         if variant and precision != "ffma":
             warnings.warn(f"cookietts_b200.WaveFlow: this WN_config (gated_unit {gate}, dilations_w {dw or '2^i'}, dilations_h "
                           f"{dh or 1}, merge_res_skip {merge}, res_skip {res_skip}, WN speaker_embed_dim "
-                          f"{self._variant['speaker_dim']}) runs in the fp32 CUDA-core mode; precision '{precision}' -> 'ffma'")
+                          f"{self._variant['speaker_dim']}, early outputs {early}, mix_first {bool(a['mix_first'])}) runs in the "
+                          f"fp32 CUDA-core mode; precision '{precision}' -> 'ffma'")
             precision = "ffma"
         if precision == "ffma":      # fp32 CUDA-core path (csrc/cwg_wf_ffma.cu): general WN_2d shapes
             need(wn["n_channels"] % 2 == 0 and 1 <= wn["kernel_size_h"] <= 16 and wn["kernel_size_w"] % 2 == 1 and wn["kernel_size_w"] <= 15,
@@ -327,6 +338,8 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             self._ccfg.dilations_w[i] = d
         for i, d in enumerate(pc.dilations_h):
             self._ccfg.dilations_h[i] = d
+        self._ccfg.n_early_every, self._ccfg.n_early_size = pc.n_early_every, pc.n_early_size
+        self._ccfg.mix_first_off = 0 if pc.mix_first else 1
         self._packed, self._packed_key, self._cw = dev_pk, key, w
         self._graphs = {}
 

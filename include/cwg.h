@@ -260,6 +260,9 @@ typedef struct cwg_wf_config {
   int32_t gate;                 /* CWG_GATE_* (glow_ax.py:168-198); 0 = GTU                                        */
   int32_t dilations_w[16];      /* n_layers_dilations_w (glow_ax.py:514); 0 = the default 2^i                      */
   int32_t dilations_h[16];      /* n_layers_dilations_h (:513,:517: causal padding (kernel_h-1)*dilation_h); 0 = 1 */
+  int32_t n_early_every;        /* early outputs (efficient_model_ax.py:151-167,:319-340): 0 = none; a flow then works on  */
+  int32_t n_early_size;         /*   the trailing n_rem height rows only                                                    */
+  int32_t mix_first_off;        /* 1: mix_first = False (PermuteHeight.inverse BEFORE the coupling, :326-337); 0: after    */
 } cwg_wf_config;
 
 /* K1 = kernel_h*kernel_w*C + CWG_WF_COND_PAD, N2 = C + CWG_EO_PAD */

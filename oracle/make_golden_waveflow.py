@@ -72,6 +72,9 @@ CASES = {
     "waveflow_v_gate": (dict(_WV, gated_unit="GSIU", dilations_w=[1, 3, 2], dilations_h=2), 2, 6, 0.8, 81, 31),
     "waveflow_v_merge": (dict(_WV, merge_res_skip=True, gated_unit="GTRU", kernel_size_h=2), 2, 5, 0.9, 82, 32),
     "waveflow_v_noskip": (dict(_WV, res_skip=False, merge_res_skip=True, gated_unit="TTU", dilations_w=2), 1, 7, 1.0, 83, 33),
+    # early outputs (flows 2, 3 work on 6 of the 8 height rows) and PermuteHeight before the coupling
+    "waveflow_v_early": (dict(_WV, n_early_every=2, n_early_size=2), 2, 6, 0.9, 85, 35),
+    "waveflow_v_mixlast": (dict(_WV, n_early_every=2, n_early_size=2, mix_first=False, gated_unit="GLU"), 1, 7, 0.8, 86, 36),
     "waveflow_v_speaker": (dict(_WV, wn_speaker_embed_dim=4, upsample_first=False, dilations_h=[1, 2, 1], gated_unit="GTSU"),
                            2, 6, 0.8, 84, 34),
 }

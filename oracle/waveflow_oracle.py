@@ -154,6 +154,13 @@ def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.f
         if cfg.upsample_first:
             cond_up = upsample_cond(cond_up, Tp, cfg.upsample_mode)      # :313-314
     C, L = cfg.n_channels, cfg.n_layers
+    rows = cfg.flow_rows()
+    n_early = sum(1 for k in range(cfg.n_flows) if cfg.n_early_every and k % cfg.n_early_every == 0 and k > 0)
+    remained, off = [], 0
+    for _ in range(n_early):                                             # :319-322
+        remained.append(zz[:, off:off + cfg.n_early_size]); off += cfg.n_early_size
+    zz = zz[:, off:]
+    assert zz.shape[1] == rows[-1]
     for k in reversed(range(cfg.n_flows)):                               # :325
         p = f"WN.{k}.WN.cond_layers.0"
         w_c = _w(sd, p, dtype)[:, :, 0]                                  # [2CL, n_mel (+ speaker dims)]
@@ -164,8 +171,13 @@ def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.f
         spec_all = np.einsum("oc,bct->bot", w_c, k_cond, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
         if not cfg.upsample_first:                                       # glow_ax.py:578-579 (no WN upsample net)
             spec_all = upsample_cond(spec_all, Tp, cfg.upsample_mode)
+        if not cfg.mix_first:
+            zz = permute_height(zz, k)                                   # :326-327
         zz = coupling_inverse(sd, k, cfg, zz, spec_all, dtype)           # :331
-        zz = permute_height(zz, k)                                       # :336-337 (mix_first)
+        if cfg.mix_first:
+            zz = permute_height(zz, k)                                   # :336-337
+        if cfg.n_early_every and k % cfg.n_early_every == 0 and k:
+            zz = np.concatenate([remained.pop(), zz], axis=1)            # :339-340
     return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)    # :346
 
 

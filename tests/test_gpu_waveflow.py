@@ -157,11 +157,12 @@ def test_config5_batch_64_full_length_is_consistent():
     assert torch.equal(one[0], out[37])
 
 
-@pytest.mark.parametrize("name", ["waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker"])
+@pytest.mark.parametrize("name", ["waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker",
+                                  "waveflow_v_early", "waveflow_v_mixlast"])
 def test_wn2d_config_variants_match_reference(name):
     """WN_config variants of WN_2d in the fp32 CUDA-core mode - gated units, width / height dilations (deeper conv queues),
     merged / absent res_skip, WN-level speaker embedding with upsample_first=False (glow_ax.py:168-198,:464-466,:506-517,
-    :541-553,:567-579,:610-626) - against the unmodified reference's fp64 waveform.  A tensor-core precision request is
+    :541-553,:567-579,:610-626), early outputs and mix_first=False (efficient_model_ax.py:319-340) - against the unmodified reference's fp64 waveform.  A tensor-core precision request is
     switched to fp32 with a warning."""
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     cfg = WaveFlowConfig(**json.loads(str(g["config"])))
