@@ -42,3 +42,30 @@ for prec in ("f16f8", "bf16x3", "ffma"):
     out = m.infer(torch.from_numpy(g["mel"]).cuda(), None, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
     torch.cuda.synchronize()
     print("group24_256", prec, float(np.abs(out.cpu().numpy() - g["audio_ref_fp64"]).max()), flush=True)
+# round 2, general fp32 modes: WN_config variants of the ax 1-D WN (cwg_axg_flow) and of WN_2d (cwg_wf_ffma.cu)
+if True:
+    import warnings
+    from cookietts_b200 import WaveFlow
+    from oracle.make_golden_waveflow import reference_kwargs_ax1d, reference_kwargs
+    from oracle.waveglow_ax_oracle import AxConfig, synthetic_state_dict as ax_sd
+    from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict as wf_sd
+    warnings.simplefilter("ignore")
+    for name in ("waveglow_axv_gsirru", "waveglow_axv_merge", "waveglow_axv_noskip", "waveglow_axv_cond", "waveglow_axv_tconv_crop",
+                 "waveglow_axv_tconv_interp"):
+        g = np.load(f"tests/golden/{name}.npz")
+        cfg = AxConfig(**json.loads(str(g["config"])))
+        m = WaveGlowAx(precision="ffma", **reference_kwargs_ax1d(cfg))
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in ax_sd(cfg, int(g["weight_seed"])).items()}); m = m.cuda().eval()
+        ids = torch.from_numpy(g["speaker_ids"]).cuda() if g["speaker_ids"].size else None
+        out = m.infer(torch.from_numpy(g["mel"]).cuda(), speaker_ids=ids, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
+        torch.cuda.synchronize()
+        print(name, float(np.abs(out.numpy() - g["infer_ref_fp64"]).max()), flush=True)
+    for name in ("waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker", "waveflow_v_early", "waveflow_v_mixlast"):
+        g = np.load(f"tests/golden/{name}.npz")
+        cfg = WaveFlowConfig(**json.loads(str(g["config"])))
+        m = WaveFlow(precision="ffma", graphs=False, **reference_kwargs(cfg))
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in wf_sd(cfg, int(g["weight_seed"])).items()}); m = m.cuda().eval()
+        ids = torch.from_numpy(g["speaker_ids"]).cuda() if g["speaker_ids"].size else None
+        out = m.infer(torch.from_numpy(g["mel"]).cuda(), speaker_ids=ids, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
+        torch.cuda.synchronize()
+        print(name, float(np.abs(out.numpy() - g["infer_ref_fp64"]).max()), flush=True)
