@@ -47,8 +47,16 @@ def test_notebook_model_constructs_with_the_reference_layout():
     other = WaveGlowAx(precision="f16f8", **module_kwargs(kind, cfg, fe))
     assert {k: tuple(v.shape) for k, v in other.state_dict().items()} == {k: tuple(v.shape) for k, v in own.items()}
     assert (model.n_group, model.n_flows, model.mix_first, model.channel_mixing, model.wn_speaker_embed_dim) == (24, 48, False, "permuteheight", 96)
-    # variants that do not commute with the interpolation still raise
+    # variants that do not commute with the interpolation leave the packed kernels: general fp32 mode, with a warning
     kw = notebook_ax_kwargs()
-    kw["WN_config"] = dict(kw["WN_config"], cond_layers=2)
+    kw["WN_config"] = dict(kw["WN_config"], cond_layers=2, n_layers=2)
+    kw["n_flows"] = 2
+    with pytest.warns(UserWarning, match="general fp32"):
+        m2 = WaveGlowAx(**kw)
+    assert m2.general and m2.precision == "ffma"
+    assert "WN.0.WN.cond_layers.1.weight_v" in m2.state_dict()
+    # what is still not built raises: a WN-level upsample net with upsample_first=True (the reference mis-sizes it)
+    kw["WN_config"] = dict(kw["WN_config"], transposed_conv_scales=[2])
+    kw["upsample_first"] = True
     with pytest.raises(NotImplementedError):
         WaveGlowAx(**kw)
