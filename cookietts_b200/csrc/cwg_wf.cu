@@ -424,7 +424,8 @@ int wf_check(const cwg_wf_config* c, int mode, int batch, int t_samples) {
   CWG_REQUIRE(c->n_mel >= 1 && c->n_mel <= WF_HP, "n_mel must be <= %d", WF_HP);
   CWG_REQUIRE(c->n_flows >= 1 && c->n_layers >= 1 && c->n_layers <= 16, "bad n_flows / n_layers");
   CWG_REQUIRE(c->gate == CWG_GATE_GTU, "the tensor-core WaveFlow kernels implement the GTU gate only (use CWG_MODE_FFMA)");
-  CWG_REQUIRE(c->n_early_every == 0 && c->mix_first_off == 0, "early outputs / mix_first = 0 run in CWG_MODE_FFMA only");
+  CWG_REQUIRE(c->n_early_every == 0 && c->mix_first_off == 0 && c->mixing_conv == 0,
+              "early outputs / mix_first = 0 / 1x1conv mixing run in CWG_MODE_FFMA only");
   for (int l = 0; l < c->n_layers; ++l)
     CWG_REQUIRE((c->dilations_w[l] == 0 || c->dilations_w[l] == (1 << l)) && c->dilations_h[l] <= 1,
                 "the tensor-core WaveFlow kernels take dilation_w 2^i and dilation_h 1 only (use CWG_MODE_FFMA)");

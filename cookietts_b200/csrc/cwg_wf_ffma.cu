@@ -147,6 +147,21 @@ __global__ void k_wff_scale(const float* __restrict__ in, float* __restrict__ ou
   if (i < n) out[i] = in[i] * scale;
 }
 
+// InvertibleConv1x1.inverse over the active height rows (efficient_modules.py:269-286): out[off + c] = sum_j Winv[c][j] in[off + j]
+__global__ void k_wff_mix(const float* __restrict__ in, float* __restrict__ out, long long BT, int G, int off, int h,
+                          const float* __restrict__ winv) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= BT) return;
+  float v[WFF_MAX_GROUP];
+  for (int j = 0; j < h; ++j) v[j] = in[m * G + off + j];
+  for (int c = 0; c < h; ++c) {
+    float acc = 0.f;
+    for (int j = 0; j < h; ++j) acc = fmaf(__ldg(winv + c * WFF_MAX_GROUP + j), v[j], acc);
+    out[m * G + off + c] = acc;
+  }
+  if (out != in) for (int j = 0; j < off; ++j) out[m * G + j] = in[m * G + j];      // early rows ride along to the waveform
+}
+
 // rows the flow k works on (efficient_model_ax.py:151-167)
 inline int wff_n_rem(const cwg_wf_config* c, int k) {
   int n = c->n_group;
@@ -207,7 +222,7 @@ size_t wff_workspace_bytes(const cwg_wf_config* c, int batch, int t_samples) {
 }
 
 int wff_launch_count(const cwg_wf_config* c) {
-  int n = 1 + (wff_n_rem(c, c->n_flows - 1) < c->n_group ? 1 : 0);
+  int n = 1 + (wff_n_rem(c, c->n_flows - 1) < c->n_group ? 1 : 0) + (c->mixing_conv ? c->n_flows + 1 : 0);
   for (int k = 0; k < c->n_flows; ++k) { const int h = wff_n_rem(c, k); n += h + (h - 1) * c->n_layers * 3; }
   return n;
 }
@@ -236,7 +251,9 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
   const int G = cfg->n_group;
   for (int c = 0; c < G; ++c) phys[c] = c;
   const size_t slot = (size_t)BT * C;                              // one ring row of one layer
-  const bool early = wff_n_rem(cfg, F - 1) < G;
+  const bool conv_mix = cfg->mixing_conv != 0;                     // dense mixing: rows stay where they are (phys = identity)
+  CWG_REQUIRE(!conv_mix || w->winv, "mixing_conv needs cwg_wf_weights.winv");
+  const bool early = wff_n_rem(cfg, F - 1) < G || conv_mix;        // (the dense mixing reads / writes the state buffer)
   if (early) {                                                     // rows the first flow does not touch must be sigma * z too
     const long long n = BT * G;
     k_wff_scale<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, ws.state, n, sigma);
@@ -246,12 +263,22 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
     for (int c = 0; c < h; ++c) nxt[c] = phys[off + perm[c]];
     for (int c = 0; c < h; ++c) phys[off + c] = nxt[c];
   };
+  auto mix = [&](int k, int h, int off, float* dst) -> int {
+    k_wff_mix<<<(unsigned)((BT + 127) / 128), 128, 0, s>>>(ws.state, dst, BT, G, off, h,
+                                                          w->winv + (size_t)k * WFF_MAX_GROUP * WFF_MAX_GROUP);
+    CWG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  };
   int ev = 0;
   for (int k = F - 1; k >= 0; --k) {
     const int h = wff_n_rem(cfg, k), off = G - h;                  // active rows: logical off .. G-1
     wff_perm(k, h, perm);
     const bool from_z = k == F - 1 && !early, last_flow = k == 0;
-    if (cfg->mix_first_off) permute(h, off);                       // mix_first = 0: PermuteHeight.inverse before the coupling
+    // the last flow writes the waveform itself - unless a dense mixing still follows its coupling
+    const bool to_audio = last_flow && !(conv_mix && !cfg->mix_first_off);
+    if (cfg->mix_first_off) {                                      // mix_first = 0: mixing inverse before the coupling
+      if (conv_mix) { if (int r = mix(k, h, off, ws.state)) return r; } else permute(h, off);
+    }
     for (int i = -1; i < h - 1; ++i) {
       if (i >= 0) {
         for (int l = 0; l < L; ++l, ++ev) {
@@ -283,13 +310,15 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
       float* x0 = j < h - 1 ? ws.x + (size_t)(j % R) * slot : nullptr;         // ring of layer 0
       // the last flow (h = G, off = 0) writes the waveform in its final logical order: after the coupling the mixing moves
       // row j to perm[j] (an involution); with mix_first = 0 nothing follows the coupling
-      const int col_out = last_flow ? (cfg->mix_first_off ? j : perm[j]) : phys[off + j];
+      const int col_out = to_audio ? ((cfg->mix_first_off || conv_mix) ? j : perm[j]) : phys[off + j];
       k_wff_row<<<(unsigned)BT, 128, 0, s>>>(BT, G, C, from_z ? z : ws.state, from_z ? sigma : 1.f, phys[off + j],
-                                            last_flow ? audio : ws.state, col_out, ws.eo, i >= 0,
+                                            to_audio ? audio : ws.state, col_out, ws.eo, i >= 0,
                                             w->start_w + (size_t)k * C, w->start_b + (size_t)k * C, x0);
       CWG_CHECK_CUDA(cudaGetLastError());
     }
-    if (!cfg->mix_first_off) permute(h, off);                      // mix_first: PermuteHeight.inverse after the coupling
+    if (!cfg->mix_first_off) {                                     // mix_first: mixing inverse after the coupling
+      if (conv_mix) { if (int r = mix(k, h, off, last_flow ? audio : ws.state)) return r; } else permute(h, off);
+    }
   }
   return 0;
 }

@@ -133,6 +133,7 @@ class WaveFlowConfig:
     n_early_every: int = 0          # early outputs (efficient_model_ax.py:151-167); 0 = none
     n_early_size: int = 2
     mix_first: bool = True          # False: PermuteHeight before the coupling (efficient_model_ax.py:326-337)
+    channel_mixing: str = "permuteheight"   # or "1x1conv": InvertibleConv1x1 over the height rows
 
     def flow_rows(self):
         """Height rows each flow works on."""
@@ -171,6 +172,11 @@ def waveflow_state_dict(cfg: WaveFlowConfig, seed: int = 1234, cond_in_channels=
 
     for k in range(cfg.n_flows):
         p = f"WN.{k}.WN."
+        if cfg.channel_mixing == "1x1conv":
+            n_rem = cfg.flow_rows()[k]
+            q1, _ = np.linalg.qr(rs.standard_normal((n_rem, n_rem)))
+            q2, _ = np.linalg.qr(rs.standard_normal((n_rem, n_rem)))
+            sd[f"convinv.{k}.weight"] = (q1 @ np.diag(rs.uniform(0.7, 1.4, size=n_rem)) @ q2).astype(np.float32)[:, :, None]
         for i in range(L):
             if cfg.seperable_conv:
                 wn(p + f"in_layers.{i}.0", (C, 1, kh, kw), kh * kw)
@@ -199,7 +205,7 @@ def waveflow_reference_kwargs(cfg: WaveFlowConfig) -> dict:
                 upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,
                 cond_hidden_channels=256, cond_output_channels=256, cond_kernel_size=1, cond_residual=False,
                 cond_padding_mode="zeros", WN_config=wn, win_length=cfg.win_length, hop_length=cfg.hop_length,
-                sampling_rate=22050, channel_mixing="permuteheight", mix_first=cfg.mix_first, waveflow=True)
+                sampling_rate=22050, channel_mixing=cfg.channel_mixing, mix_first=cfg.mix_first, waveflow=True)
 
 
 

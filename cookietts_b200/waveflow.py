@@ -14,7 +14,7 @@ WN_config variants of WN_2d run in the fp32 CUDA-core mode (csrc/cwg_wf_ffma.cu;
 `res_skip=False` (:541-553,:610-626 - the hidden tensor is then never updated: zero res rows at pack time), WN-level speaker
 embeddings (:464-466,:567-570 - a per-utterance gate bias), `upsample_first=False` (:578-579 - interpolation commutes with
 the one linear 1x1 cond layer), early outputs (efficient_model_ax.py:151-167,:319-340 - a flow works on the trailing
-n_rem height rows) and `mix_first=False`.
+n_rem height rows), `mix_first=False` and `channel_mixing='1x1conv'` (InvertibleConv1x1 over the height rows).
 """
 from __future__ import annotations
 
@@ -56,6 +56,7 @@ class WaveFlowPackConfig:
     n_early_every: int = 0       # early outputs; 0 = none
     n_early_size: int = 0
     mix_first: bool = True
+    mixing_conv: bool = False    # channel_mixing='1x1conv'
 
     @property
     def k1(self) -> int:
@@ -110,6 +111,12 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
            "w1_f64": w1, "w2_f64": w2}
     if E:
         out["spk_w"], out["spk_embed"] = spk_w, np.stack(spk_embed)
+    if cfg.mixing_conv:                                        # W^-1 of every InvertibleConv1x1, padded to [F][32][32]
+        winv = np.zeros((F, 32, 32))
+        for k in range(F):
+            wk = _np(sd[f"convinv.{k}.weight"])[:, :, 0]
+            winv[k, :wk.shape[0], :wk.shape[0]] = np.linalg.inv(wk)
+        out["winv"] = winv.astype(np.float32)
     if cfg.fp32:
         out["w1_f32"], out["w2_f32"] = w1.astype(np.float32), w2.astype(np.float32)
     else:
@@ -122,14 +129,14 @@ class CwgWfConfig(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_mel", "n_flows", "n_group", "n_layers", "n_channels",
                                            "kernel_h", "kernel_w", "hop_length", "upsample_linear", "gate")]
                 + [("dilations_w", C.c_int32 * 16), ("dilations_h", C.c_int32 * 16)]
-                + [(n, C.c_int32) for n in ("n_early_every", "n_early_size", "mix_first_off")])
+                + [(n, C.c_int32) for n in ("n_early_every", "n_early_size", "mix_first_off", "mixing_conv")])
 
 
 WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "start_w", "start_b", "w1_f32", "w2_f32")
 
 
 class CwgWfWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch",)]
+    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch", "winv")]
 
 
 def _bind(lib):
@@ -225,13 +232,21 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear", fp32=precision == "ffma",
             gate=v["gate"], dilations_w=v["dilations_w"], dilations_h=v["dilations_h"], res_skip=v["res_skip"],
             merge_res_skip=v["merge"], wn_speaker_dim=v["speaker_dim"], n_early_every=v["n_early_every"],
-            n_early_size=v["n_early_size"], mix_first=v["mix_first"])
+            n_early_size=v["n_early_size"], mix_first=v["mix_first"], mixing_conv=v["mixing_conv"])
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
                                            cond_in_channels=self.wn_cond_in_channels,
                                            seperable_conv=bool(wn.get("seperable_conv")), dilations_w=v["dilations_w"],
                                            dilations_h=v["dilations_h"], res_skip=v["res_skip"], merge_res_skip=v["merge"],
                                            speaker_embed_dim=v["speaker_dim"]) for _ in range(n_flows)])
+        if v["mixing_conv"]:                                 # efficient_model_ax.py:137-139,:163 (`convinv.{k}.weight`)
+            from .waveglow_ax import _InvConv
+            rows, n = [], n_group
+            for k in range(n_flows):
+                if v["n_early_every"] and k % v["n_early_every"] == 0 and k > 0:
+                    n -= v["n_early_size"]
+                rows.append(n)
+            self.convinv = nn.ModuleList([_InvConv(n) for n in rows])
         self._packed = None
         self._packed_key = None
         self._workspace = None
@@ -244,10 +259,12 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             if not cond:
                 raise NotImplementedError("cookietts_b200.WaveFlow: " + msg)
         need(a["waveflow"], "only waveflow=True (WN_2d) is built; use cookietts_b200.WaveGlow for the classic model")
-        need(str(a["channel_mixing"]).lower() in "waveflowpermuteheightpermutechannelpermute", "channel_mixing must be 'permuteheight'")
+        mixing = str(a["channel_mixing"]).lower()
+        conv_mix = mixing in "1x1convinvertibleconv1x1invconv"
+        need(conv_mix or mixing in "waveflowpermuteheightpermutechannelpermute", "channel_mixing must be '1x1conv' or 'permuteheight'")
         need(a["upsample_first"] is True or (a["upsample_first"] is False and not a["transposed_conv_scales"]),
              "upsample_first must be True, or False without a model-level TransposedUpsampleNet")
-        need(a["n_flows"] % 2 == 0, "PermuteHeight requires an even n_flows (efficient_modules.py:370)")
+        need(conv_mix or a["n_flows"] % 2 == 0, "PermuteHeight requires an even n_flows (efficient_modules.py:370)")
         early = a["n_early_every"] < a["n_flows"]
         n_rem = a["n_group"] - a["n_early_size"] * ((a["n_flows"] - 1) // a["n_early_every"])
         need(not early or (a["n_early_size"] >= 1 and n_rem >= 2), "too many early outputs for n_group")
@@ -271,13 +288,13 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self._variant = dict(gate=GATED_UNITS[gate], dilations_w=dw, dilations_h=dh, res_skip=res_skip, merge=merge,
                              speaker_dim=int(wn.get("speaker_embed_dim", 0) or 0),
                              n_early_every=int(a["n_early_every"]) if early else 0, n_early_size=int(a["n_early_size"]) if early else 0,
-                             mix_first=bool(a["mix_first"]))
+                             mix_first=bool(a["mix_first"]), mixing_conv=conv_mix)
         variant = bool(self._variant["gate"] or dw or dh or merge or not res_skip or self._variant["speaker_dim"] or early
-                       or not a["mix_first"])
+                       or not a["mix_first"] or conv_mix)
         if variant and precision != "ffma":
             warnings.warn(f"cookietts_b200.WaveFlow: this WN_config (gated_unit {gate}, dilations_w {dw or '2^i'}, dilations_h "
                           f"{dh or 1}, merge_res_skip {merge}, res_skip {res_skip}, WN speaker_embed_dim "
-                          f"{self._variant['speaker_dim']}, early outputs {early}, mix_first {bool(a['mix_first'])}) runs in the "
+                          f"{self._variant['speaker_dim']}, early outputs {early}, mix_first {bool(a['mix_first'])}, channel_mixing {'1x1conv' if conv_mix else 'permuteheight'}) runs in the "
                           f"fp32 CUDA-core mode; precision '{precision}' -> 'ffma'")
             precision = "ffma"
         if precision == "ffma":      # fp32 CUDA-core path (csrc/cwg_wf_ffma.cu): general WN_2d shapes
@@ -321,7 +338,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
         pk = pack_waveflow_state_dict(sd, self.pack_config, cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
-        for name in WF_WEIGHT_FIELDS + ("spk_w", "spk_embed"):
+        for name in WF_WEIGHT_FIELDS + ("spk_w", "spk_embed", "winv"):
             if name not in pk:
                 continue
             arr = pk[name]
@@ -329,7 +346,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                 arr = arr.view(np.int16)
             dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
         w = CwgWfWeights()
-        for f in WF_WEIGHT_FIELDS:
+        for f in WF_WEIGHT_FIELDS + ("winv",):
             setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
         pc = self.pack_config
         self._ccfg = CwgWfConfig(pc.n_mel, pc.n_flows, pc.n_group, pc.n_layers, pc.n_channels, pc.kernel_h, pc.kernel_w,
@@ -340,6 +357,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             self._ccfg.dilations_h[i] = d
         self._ccfg.n_early_every, self._ccfg.n_early_size = pc.n_early_every, pc.n_early_size
         self._ccfg.mix_first_off = 0 if pc.mix_first else 1
+        self._ccfg.mixing_conv = int(pc.mixing_conv)
         self._packed, self._packed_key, self._cw = dev_pk, key, w
         self._graphs = {}
 

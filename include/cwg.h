@@ -263,6 +263,8 @@ typedef struct cwg_wf_config {
   int32_t n_early_every;        /* early outputs (efficient_model_ax.py:151-167,:319-340): 0 = none; a flow then works on  */
   int32_t n_early_size;         /*   the trailing n_rem height rows only                                                    */
   int32_t mix_first_off;        /* 1: mix_first = False (PermuteHeight.inverse BEFORE the coupling, :326-337); 0: after    */
+  int32_t mixing_conv;          /* 1: channel_mixing = '1x1conv' (InvertibleConv1x1 over the height rows, efficient_modules.py */
+                                /*    :269-286; cwg_wf_weights.winv); 0: PermuteHeight                                        */
 } cwg_wf_config;
 
 /* K1 = kernel_h*kernel_w*C + CWG_WF_COND_PAD, N2 = C + CWG_EO_PAD */
@@ -285,6 +287,9 @@ typedef struct cwg_wf_weights {
    * WN-level speaker embedding (glow_ax.py:464-466,:567-570) is a time-constant input of the 1x1 cond layer, i.e. a bias;
    * cwg_ax_speaker_bias evaluates it */
   const float*    b1_batch;
+  /* ABI 5, CWG_MODE_FFMA, mixing_conv = 1: W^-1 of every flow's InvertibleConv1x1, [F][32][32] row major (the flow's
+   * n_rem x n_rem matrix in the top-left corner) */
+  const float*    winv;
 } cwg_wf_weights;
 
 size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples);

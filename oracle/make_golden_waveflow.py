@@ -75,6 +75,9 @@ CASES = {
     # early outputs (flows 2, 3 work on 6 of the 8 height rows) and PermuteHeight before the coupling
     "waveflow_v_early": (dict(_WV, n_early_every=2, n_early_size=2), 2, 6, 0.9, 85, 35),
     "waveflow_v_mixlast": (dict(_WV, n_early_every=2, n_early_size=2, mix_first=False, gated_unit="GLU"), 1, 7, 0.8, 86, 36),
+    # InvertibleConv1x1 over the height rows instead of PermuteHeight, after / before the coupling, with early outputs
+    "waveflow_v_conv": (dict(_WV, channel_mixing="1x1conv", n_early_every=2, n_early_size=2), 2, 6, 0.9, 87, 37),
+    "waveflow_v_conv_mixlast": (dict(_WV, channel_mixing="1x1conv", mix_first=False), 1, 7, 0.8, 88, 38),
     "waveflow_v_speaker": (dict(_WV, wn_speaker_embed_dim=4, upsample_first=False, dilations_h=[1, 2, 1], gated_unit="GTSU"),
                            2, 6, 0.8, 84, 34),
 }
@@ -244,6 +247,9 @@ def main():
             model = WaveGlowAx(**reference_kwargs(cfg))
             model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
             model = model.eval().to(dt)
+            if dt == torch.float64 and cfg.channel_mixing == "1x1conv":
+                for conv in model.convinv:        # W_inverse is always created fp32 (efficient_modules.py:271-275)
+                    conv.W_inverse = conv.weight.squeeze().double().inverse().unsqueeze(-1)
             with torch.no_grad():
                 # (1) explicit-z API: inverse(z, cond) on the un-padded mel
                 zz = torch.from_numpy(z).to(dt) * sigma

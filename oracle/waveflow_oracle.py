@@ -171,11 +171,17 @@ def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.f
         spec_all = np.einsum("oc,bct->bot", w_c, k_cond, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
         if not cfg.upsample_first:                                       # glow_ax.py:578-579 (no WN upsample net)
             spec_all = upsample_cond(spec_all, Tp, cfg.upsample_mode)
+        def mix(x):                                                      # PermuteHeight.inverse or InvertibleConv1x1.inverse
+            if cfg.channel_mixing == "permuteheight":
+                return permute_height(x, k)
+            W = np.asarray(sd[f"convinv.{k}.weight"], np.float64)[:, :, 0]      # efficient_modules.py:269-286
+            W_inv = np.linalg.inv(W) if dtype == np.float64 else np.linalg.inv(W.astype(np.float32))
+            return np.einsum("oc,bct->bot", W_inv.astype(dtype), x, optimize=True)
         if not cfg.mix_first:
-            zz = permute_height(zz, k)                                   # :326-327
+            zz = mix(zz)                                                 # :326-327
         zz = coupling_inverse(sd, k, cfg, zz, spec_all, dtype)           # :331
         if cfg.mix_first:
-            zz = permute_height(zz, k)                                   # :336-337
+            zz = mix(zz)                                                 # :336-337
         if cfg.n_early_every and k % cfg.n_early_every == 0 and k:
             zz = np.concatenate([remained.pop(), zz], axis=1)            # :339-340
     return np.ascontiguousarray(zz.transpose(0, 2, 1)).reshape(B, -1)    # :346

@@ -14,7 +14,8 @@ CASES = ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config
          # general WN_2d shapes: dense 5x3, depthwise-separable 7x7 at squeeze height 20 (16 and 128 channels)
          "waveflow_5x3", "waveflow_sep7", "waveflow_sep7_128",
          # WN_config variants: gated units, width / height dilations, merged / absent res_skip, WN speaker embedding
-         "waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker", "waveflow_v_early", "waveflow_v_mixlast"]
+         "waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker", "waveflow_v_early", "waveflow_v_mixlast",
+         "waveflow_v_conv", "waveflow_v_conv_mixlast"]
 
 
 def load(name):
