@@ -144,7 +144,7 @@ class AxFrontEndMixin:
             self.interpolation_required = bool(int(np.prod(scales)) != self.upsample_factor)
             ch = t_out
         need(not wn.get("transposed_conv_scales") or getattr(self, "general", False),
-             "a WN-level TransposedUpsampleNet is served by WaveGlowAx's general fp32 mode only")
+             "a WN-level TransposedUpsampleNet is served by the general fp32 modes only")
         # ---- n_flow_group_conv (efficient_model_ax.py:128-131)
         self._fe_group = None
         if a["group_conv_output_dim"]:
@@ -234,6 +234,52 @@ class AxFrontEndMixin:
                                                  y.data_ptr(), stream))
             h = y
         return h
+
+    def _wn_resample(self, lib, x, t_out, stream):
+        """F.interpolate(x, size=t_out, mode, align_corners=True for 'linear') - efficient_model_ax.py:175, glow_ax.py:365"""
+        B, ch, t_in = x.shape
+        y = torch.empty(B, ch, t_out, device=x.device, dtype=torch.float32)
+        _cabi.check(lib.cwg_resample1d(x.data_ptr(), B, ch, t_in, ch * t_in, y.data_ptr(), t_out, ch * t_out,
+                                       1 if self.upsample_linear else 0, t_out, 0, 0.0, 0, stream))
+        return y
+
+    def _wn_cond_apply(self, lib, cond, f, ids, Tp, stream, flow, crop_2d=False):
+        """The cond path of ONE flow's WN in its general form (glow_ax.py:378-389 / WN_2d :565-579): flow slice of
+        n_flow_group_conv, WN-level speaker embedding, the cond stack (self._wn_cond: depth, kernel, padding mode, activation,
+        out_act), then - with upsample_first=False - the WN's own upsample net and crop / interpolation (_upsample_mels :361-373;
+        WN_2d crops with its own rule :545-553).  `f` holds this flow's device weights: group, emb, cond [(w, b)], tconv.
+        Returns [B, 2*C*L, Tp]."""
+        wc = self._wn_cond
+        pad, pad_mode = (2 * wc["kernel_size"] - 2) // 2, PAD_MODES[wc["padding_mode"]]
+        act, slope = wc["act"]
+        x = cond
+        B = x.shape[0]
+        if f.get("group") is not None:                       # efficient_model_ax.py:316-317,:328
+            x = self._conv1d(lib, x, *f["group"], 0, 0, ACT_NONE, 0.0)
+        if f.get("emb") is not None:                         # glow_ax.py:378-381
+            x = torch.cat([x, f["emb"][ids][:, :, None].expand(-1, -1, x.shape[2])], dim=1).contiguous()
+        n = len(f["cond"])
+        for i, (w, b) in enumerate(f["cond"]):               # :383-387
+            a = act if (wc["out_act"] or i != n - 1) else ACT_NONE
+            x = self._conv1d(lib, x, w, b, pad, pad_mode, a, slope)
+        if not self.upsample_first and f.get("tconv"):       # :389, _upsample_mels with the WN's upsample net
+            x = self._tconv_chain(lib, x, f["tconv"], stream)
+            if int(np.prod(self._wn_tconv["scales"])) != self.hop_length // self.n_group and x.shape[2] != Tp:   # interpolation_required
+                x = self._wn_resample(lib, x, Tp, stream)
+            else:                                            # centre crop
+                diff = x.shape[2] - Tp
+                pad_l = diff // 2
+                pad_r = pad_l + (pad_l % 2) if crop_2d else pad_l     # WN_2d: cond[:, :, pad:-(pad + pad % 2)], glow_ax.py:550-552
+                if diff <= 0 or pad_r == 0 or x.shape[2] - pad_l - pad_r != Tp:
+                    raise RuntimeError(f"WN {flow}: upsampled cond length {x.shape[2]} cannot be cropped to {Tp} group-steps "
+                                       "(the reference's slice is empty or mis-sized here too)")
+                y = torch.empty(B, x.shape[1], Tp, device=x.device, dtype=torch.float32)
+                _cabi.check(lib.cwg_resample1d(x.data_ptr(), B, x.shape[1], x.shape[2], x.shape[1] * x.shape[2], y.data_ptr(),
+                                               Tp, x.shape[1] * Tp, 0, x.shape[2], pad_l, 0.0, 0, stream))
+                x = y
+        elif not self.upsample_first and x.shape[2] != Tp:   # ... without one: interpolation_required, F.interpolate
+            x = self._wn_resample(lib, x, Tp, stream)
+        return x
 
     @torch.no_grad()
     def _fe_apply(self, spect: torch.Tensor, speaker_ids, n_steps: int) -> torch.Tensor:

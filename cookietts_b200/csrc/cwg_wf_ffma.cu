@@ -21,6 +21,7 @@ constexpr int WFF_MAX_GROUP = 32;
 struct WffGemmP {
   long long BT; int Tp, C, KH, KW, M;      // M = cond channels
   int dil_h, ring_rows; long long bias_bstride;   // ring_rows = (KH - 1) * max dil_h + 1; bias_bstride: per-utterance b1 (0: shared)
+  const float* c_add; long long c_bstride;        // GEMM1: caller-evaluated cond slice [B][..][Tp] added to the pre-activation, or NULL
   int N, K;                                // output columns, contraction length
   const float* W; const float* bias;       // W [N][K]
   // GEMM1 (in_layer + cond): x ring of this layer [KH][BT][C]; newest row index `row`; mel_up [BT][M]
@@ -83,7 +84,10 @@ __global__ void __launch_bounds__(256) k_wff_gemm(WffGemmP p) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
       if (MODE == 0) {
-        p.pre[(size_t)m * p.N + n] = acc[i][j] + __ldg(p.bias + (m / p.Tp) * p.bias_bstride + n);
+        const long long ub = m / p.Tp;
+        float v = acc[i][j] + __ldg(p.bias + ub * p.bias_bstride + n);
+        if (p.c_add) v += __ldg(p.c_add + ub * p.c_bstride + (size_t)n * p.Tp + (m - ub * p.Tp));
+        p.pre[(size_t)m * p.N + n] = v;
       } else if (n < p.C) {                                       // x = x + res (glow_ax.py:620-626)
         if (p.x_next) p.x_next[(size_t)m * p.C + n] = __ldg(p.x_cur + (size_t)m * p.C + n) + acc[i][j] + __ldg(p.bias + n);
       } else {                                                    // folded `end` of the skip path: (log_s, t)
@@ -232,7 +236,8 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
               cudaStream_t s, void** ev_begin, void** ev_end, int n_events) {
   if (int r = wff_check(cfg, batch, t_samples)) return r;
   CWG_REQUIRE(w && w->w1_f32 && w->w2_f32 && w->b1 && w->b2 && w->eo_b && w->start_w && w->start_b, "fp32 weight arrays missing");
-  const int h = cfg->n_group, F = cfg->n_flows, L = cfg->n_layers, C = cfg->n_channels, KH = cfg->kernel_h, KW = cfg->kernel_w, M = cfg->n_mel;
+  const int h = cfg->n_group, F = cfg->n_flows, L = cfg->n_layers, C = cfg->n_channels, KH = cfg->kernel_h, KW = cfg->kernel_w;
+  const int M = w->c_all ? 0 : cfg->n_mel;                         // caller-evaluated cond path: no cond columns in w1
   const int Tp = t_samples / h;
   const long long BT = (long long)batch * Tp;
   WffWs ws;
@@ -240,7 +245,7 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
   const int K1 = KH * KW * C + M, N2 = C + CWG_EO_PAD;
   const int R = wff_ring_rows(cfg);                                // rows of every layer's conv queue
-  {
+  if (M > 0) {
     const long long n = BT * M;
     k_wff_mel_up<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mel, ws.mel_up, batch, M, frames, frames + pad_frames, Tp, cfg->upsample_linear);
     CWG_CHECK_CUDA(cudaGetLastError());
@@ -290,6 +295,10 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
           p.ring = ws.x + (size_t)l * R * slot; p.mel = ws.mel_up; p.row = i; p.dil = wff_dil_w(cfg, l); p.pre = ws.pre;
           p.dil_h = wff_dil_h(cfg, l); p.ring_rows = R;
           if (w->b1_batch) { p.bias = w->b1_batch + idx * 2 * C; p.bias_bstride = (long long)F * L * 2 * C; }
+          if (w->c_all) {
+            p.c_bstride = (long long)2 * C * L * Tp;
+            p.c_add = w->c_all + (size_t)k * batch * p.c_bstride + (size_t)2 * C * l * Tp;
+          }
           dim3 g1((unsigned)((BT + GM - 1) / GM), (unsigned)((2 * C + GN - 1) / GN));
           k_wff_gemm<0><<<g1, 256, 0, s>>>(p);
           const long long n = BT * C;

@@ -134,6 +134,17 @@ class WaveFlowConfig:
     n_early_size: int = 2
     mix_first: bool = True          # False: PermuteHeight before the coupling (efficient_model_ax.py:326-337)
     channel_mixing: str = "permuteheight"   # or "1x1conv": InvertibleConv1x1 over the height rows
+    # WN cond path in its general form (glow_ax.py:476-505,:565-579); the defaults are the one linear 1x1 layer
+    wn_cond_layers: int = 1
+    wn_cond_hidden_channels: int = 256
+    wn_cond_kernel_size: int = 1            # the conv has 2k - 1 taps
+    wn_cond_padding_mode: str = "zeros"
+    wn_cond_activation_func: str = "none"
+    wn_negative_slope: object = None
+    wn_cond_out_activation_func: bool = True
+    wn_tconv_scales: object = None          # WN-level TransposedUpsampleNet (upsample_first=False)
+    wn_tconv_hidden_dim: int = 256
+    wn_tconv_kernel_size: object = 4
 
     def flow_rows(self):
         """Height rows each flow works on."""
@@ -188,18 +199,36 @@ def waveflow_state_dict(cfg: WaveFlowConfig, seed: int = 1234, cond_in_channels=
         wn(p + "start", (C, 1, 1, 1), 1)
         sd[p + "end.weight"] = (rs.standard_normal((2, C, 1, 1)) * 0.02).astype(np.float32)
         sd[p + "end.bias"] = (rs.standard_normal((2,)) * 0.02).astype(np.float32)
-        wn(p + "cond_layers.0", (2 * C * L, cin + cfg.wn_speaker_embed_dim, 1), cin + cfg.wn_speaker_embed_dim)
+        kc = 2 * cfg.wn_cond_kernel_size - 1
+        cond_out = cfg.wn_tconv_hidden_dim if cfg.wn_tconv_scales else 2 * C * L                       # glow_ax.py:481
+        dims = [cin + cfg.wn_speaker_embed_dim] + [cfg.wn_cond_hidden_channels] * (cfg.wn_cond_layers - 1) + [cond_out]
+        for i, (di, do) in enumerate(zip(dims[:-1], dims[1:])):
+            wn(p + f"cond_layers.{i}", (do, di, kc), di * kc)
         if cfg.wn_speaker_embed_dim:
             sd[p + "speaker_embed.weight"] = rs.standard_normal((512, cfg.wn_speaker_embed_dim)).astype(np.float32)
+        if cfg.wn_tconv_scales:                                          # TransposedUpsampleNet(hidden, 2CL, hidden, ...), :468-473
+            n = len(cfg.wn_tconv_scales)
+            for i, sc in enumerate(cfg.wn_tconv_scales):
+                kk = cfg.wn_tconv_kernel_size[i] if isinstance(cfg.wn_tconv_kernel_size, (list, tuple)) else cfg.wn_tconv_kernel_size
+                ci, co = cfg.wn_tconv_hidden_dim, (2 * C * L if i == n - 1 else cfg.wn_tconv_hidden_dim)
+                bound = 1.0 / np.sqrt(ci * kk / sc)
+                sd[p + f"upsample_net.t_convs.{2 * i}.weight"] = rs.uniform(-bound, bound, size=(ci, co, kk)).astype(np.float32)
+                sd[p + f"upsample_net.t_convs.{2 * i}.bias"] = rs.uniform(-bound, bound, size=(co,)).astype(np.float32)
     return sd
 
 
 def waveflow_reference_kwargs(cfg: WaveFlowConfig) -> dict:
     wn = dict(n_layers=cfg.n_layers, n_channels=cfg.n_channels, kernel_size_w=cfg.kernel_size_w,
               kernel_size_h=cfg.kernel_size_h, n_layers_dilations_w=cfg.dilations_w, n_layers_dilations_h=cfg.dilations_h,
-              speaker_embed_dim=cfg.wn_speaker_embed_dim, rezero=False, cond_layers=1, cond_activation_func="none", negative_slope=None,
-              cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", seperable_conv=cfg.seperable_conv,
-              res_skip=cfg.res_skip, merge_res_skip=cfg.merge_res_skip, upsample_mode=cfg.upsample_mode, gated_unit=cfg.gated_unit)
+              speaker_embed_dim=cfg.wn_speaker_embed_dim, rezero=False, cond_layers=cfg.wn_cond_layers,
+              cond_activation_func=cfg.wn_cond_activation_func, negative_slope=cfg.wn_negative_slope,
+              cond_hidden_channels=cfg.wn_cond_hidden_channels, cond_kernel_size=cfg.wn_cond_kernel_size,
+              cond_padding_mode=cfg.wn_cond_padding_mode, seperable_conv=cfg.seperable_conv,
+              res_skip=cfg.res_skip, merge_res_skip=cfg.merge_res_skip, upsample_mode=cfg.upsample_mode, gated_unit=cfg.gated_unit,
+              cond_out_activation_func=cfg.wn_cond_out_activation_func)
+    if cfg.wn_tconv_scales:
+        wn.update(transposed_conv_scales=list(cfg.wn_tconv_scales), transposed_conv_hidden_dim=cfg.wn_tconv_hidden_dim,
+                  transposed_conv_kernel_size=cfg.wn_tconv_kernel_size)
     return dict(n_mel_channels=cfg.n_mel_channels, n_flows=cfg.n_flows, n_group=cfg.n_group,
                 n_early_every=cfg.n_early_every or cfg.n_flows * 2, n_early_size=cfg.n_early_size, memory_efficient=0.0, spect_scaling=False,
                 upsample_mode="normal", upsample_first=cfg.upsample_first, speaker_embed=0, cond_layers=0,

@@ -14,7 +14,10 @@ WN_config variants of WN_2d run in the fp32 CUDA-core mode (csrc/cwg_wf_ffma.cu;
 `res_skip=False` (:541-553,:610-626 - the hidden tensor is then never updated: zero res rows at pack time), WN-level speaker
 embeddings (:464-466,:567-570 - a per-utterance gate bias), `upsample_first=False` (:578-579 - interpolation commutes with
 the one linear 1x1 cond layer), early outputs (efficient_model_ax.py:151-167,:319-340 - a flow works on the trailing
-n_rem height rows), `mix_first=False` and `channel_mixing='1x1conv'` (InvertibleConv1x1 over the height rows).
+n_rem height rows), `mix_first=False`, `channel_mixing='1x1conv'` (InvertibleConv1x1 over the height rows), and WN cond
+paths in their general form (several layers / activations / kernel sizes / padding modes, a WN-level TransposedUpsampleNet;
+glow_ax.py:476-505,:565-579): the module evaluates every flow's cond path with the front-end kernels and hands the result
+to `cwg_wf_infer` (`cwg_wf_weights.c_all`).
 """
 from __future__ import annotations
 
@@ -28,7 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .ax_frontend import AxFrontEndMixin
+from .ax_frontend import AxFrontEndMixin, TransposedUpsampleNet, repack_conv_transpose, _cond_act, PAD_MODES, ACT_NONE
 from .packing import in_layer_weight_bias, split_hi_lo, effective_weight, _np, EO_PAD
 
 COND_PAD = 128
@@ -57,9 +60,12 @@ class WaveFlowPackConfig:
     n_early_size: int = 0
     mix_first: bool = True
     mixing_conv: bool = False    # channel_mixing='1x1conv'
+    cond_external: bool = False  # the WN cond path is evaluated by the module (cwg_wf_weights.c_all): no cond columns in w1
 
     @property
     def k1(self) -> int:
+        if self.cond_external:
+            return self.kernel_h * self.kernel_w * self.n_channels
         return self.kernel_h * self.kernel_w * self.n_channels + (self.n_mel if self.fp32 else COND_PAD)
 
 
@@ -76,20 +82,24 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
     spk_embed = []
     for k in range(F):
         p = f"WN.{k}.WN."
-        w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]           # [2CL, M (+ E)]
-        b_c = _np(sd[p + "cond_layers.0.bias"])
-        if E:                                                              # [cond channels | speaker embedding], glow_ax.py:570
+        if cfg.cond_external:                                              # cond path evaluated by the module
+            w_c, b_c = np.zeros((2 * Cc * L, 0)), np.zeros(2 * Cc * L)
+        else:
+            w_c = effective_weight(sd, p + "cond_layers.0")[:, :, 0]       # [2CL, M (+ E)]
+            b_c = _np(sd[p + "cond_layers.0.bias"])
+        if E and not cfg.cond_external:                                                              # [cond channels | speaker embedding], glow_ax.py:570
             spk_w[k] = w_c[:, w_c.shape[1] - E:].reshape(L, 2 * Cc, E)
             w_c = w_c[:, :w_c.shape[1] - E]
             spk_embed.append(np.asarray(_np(sd[p + "speaker_embed.weight"]), np.float32))
-        if cond_fold is not None:                                          # n_flow_group_conv (ax_frontend.py)
+        if cond_fold is not None and not cfg.cond_external:                # n_flow_group_conv (ax_frontend.py)
             w_c, b_c = cond_fold(k, w_c, b_c, sd)
         w_end = _np(sd[p + "end.weight"])[:, :, 0, 0]                      # [2, C]  (log_s, t)
         eo_bias = _np(sd[p + "end.bias"]).copy()
         for i in range(L):
             w_in, b_in = in_layer_weight_bias(sd, p + f"in_layers.{i}")    # [2C, C, kh, kw]
             w1[k, i, :, :kh * kw * Cc] = w_in.transpose(0, 2, 3, 1).reshape(2 * Cc, kh * kw * Cc)   # col (a*kw+b)*C + c
-            w1[k, i, :, kh * kw * Cc:kh * kw * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
+            if not cfg.cond_external:
+                w1[k, i, :, kh * kw * Cc:kh * kw * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
             b1[k, i] = b_in + b_c[2 * Cc * i:2 * Cc * (i + 1)]
             if cfg.res_skip:
                 w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0, 0]
@@ -109,7 +119,7 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
     out = {"b1": b1.astype(np.float32), "b2": b2.astype(np.float32), "eo_b": eo_b.astype(np.float32),
            "start_w": start_w.astype(np.float32), "start_b": start_b.astype(np.float32),
            "w1_f64": w1, "w2_f64": w2}
-    if E:
+    if E and not cfg.cond_external:
         out["spk_w"], out["spk_embed"] = spk_w, np.stack(spk_embed)
     if cfg.mixing_conv:                                        # W^-1 of every InvertibleConv1x1, padded to [F][32][32]
         winv = np.zeros((F, 32, 32))
@@ -136,7 +146,7 @@ WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "sta
 
 
 class CwgWfWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch", "winv")]
+    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch", "winv", "c_all")]
 
 
 def _bind(lib):
@@ -162,7 +172,8 @@ class _WN2d(nn.Module):
     """Parameter holder with the layout of glow_ax.py:421-553 (supported subset)."""
 
     def __init__(self, n_layers, n_channels, kernel_h, kernel_w, cond_in_channels, seperable_conv=False, dilations_w=(),
-                 dilations_h=(), res_skip=True, merge_res_skip=False, speaker_embed_dim=0):
+                 dilations_h=(), res_skip=True, merge_res_skip=False, speaker_embed_dim=0, cond_layers=1,
+                 cond_hidden_channels=256, cond_kernel_size=1, cond_padding_mode="zeros", tconv=None):
         super().__init__()
         wn = nn.utils.weight_norm
         cond_in_channels += speaker_embed_dim                # glow_ax.py:431
@@ -186,7 +197,17 @@ class _WN2d(nn.Module):
         self.start = wn(nn.Conv2d(1, n_channels, (1, 1)), name="weight")
         self.end = nn.Conv2d(n_channels, 2, (1, 1))
         self.end.weight.data.zero_(); self.end.bias.data.zero_()
-        self.cond_layers = nn.ModuleList([wn(nn.Conv1d(cond_in_channels, 2 * n_channels * n_layers, 1), name="weight")])
+        cond_out = 2 * n_channels * n_layers
+        if tconv:                                            # WN-level upsample net (upsample_first=False), glow_ax.py:468-473,:481
+            self.upsample_net = TransposedUpsampleNet(tconv["hidden"], cond_out, tconv["hidden"], tconv["kernel_size"],
+                                                      tconv["scales"], use_last_layer_act_func=False)
+            cond_out = tconv["hidden"]
+        if cond_layers:                                      # glow_ax.py:476-493
+            kc = 2 * cond_kernel_size - 1
+            dims = [cond_in_channels] + [cond_hidden_channels] * (cond_layers - 1) + [cond_out]
+            self.cond_layers = nn.ModuleList([
+                wn(nn.Conv1d(di, do, kc, padding=(kc - 1) // 2, padding_mode=cond_padding_mode), name="weight")
+                for di, do in zip(dims[:-1], dims[1:])])
 
 
 class _Coupling(nn.Module):
@@ -222,6 +243,9 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self.shift_spect, self.scale_spect = shift_spect, scale_spect
         self.precision = precision
         self.wn_speaker_embed_dim = v["speaker_dim"]
+        self.general = v["cond_external"]                    # (ax_frontend._fe_build: a WN-level upsample net needs it)
+        self._wn_cond, self._wn_tconv = v["wn_cond"], v["wn_tconv"]
+        self.upsample_first, self.upsample_linear = bool(upsample_first), wn.get("upsample_mode", "linear") == "linear"
         cond_channels = self._fe_build(a, wn)                # model-level front-end (ax_frontend.py)
         if cond_channels > COND_PAD and precision != "ffma":
             raise NotImplementedError(f"cookietts_b200.WaveFlow: the kernels take <= {COND_PAD} cond channels "
@@ -232,13 +256,17 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             hop_length=hop_length, upsample_linear=wn["upsample_mode"] == "linear", fp32=precision == "ffma",
             gate=v["gate"], dilations_w=v["dilations_w"], dilations_h=v["dilations_h"], res_skip=v["res_skip"],
             merge_res_skip=v["merge"], wn_speaker_dim=v["speaker_dim"], n_early_every=v["n_early_every"],
-            n_early_size=v["n_early_size"], mix_first=v["mix_first"], mixing_conv=v["mixing_conv"])
+            n_early_size=v["n_early_size"], mix_first=v["mix_first"], mixing_conv=v["mixing_conv"],
+            cond_external=v["cond_external"])
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
                                            cond_in_channels=self.wn_cond_in_channels,
                                            seperable_conv=bool(wn.get("seperable_conv")), dilations_w=v["dilations_w"],
                                            dilations_h=v["dilations_h"], res_skip=v["res_skip"], merge_res_skip=v["merge"],
-                                           speaker_embed_dim=v["speaker_dim"]) for _ in range(n_flows)])
+                                           speaker_embed_dim=v["speaker_dim"], cond_layers=v["wn_cond"]["layers"],
+                                           cond_hidden_channels=v["wn_cond"]["hidden"], cond_kernel_size=v["wn_cond"]["kernel_size"],
+                                           cond_padding_mode=v["wn_cond"]["padding_mode"], tconv=v["wn_tconv"])
+                                 for _ in range(n_flows)])
         if v["mixing_conv"]:                                 # efficient_model_ax.py:137-139,:163 (`convinv.{k}.weight`)
             from .waveglow_ax import _InvConv
             rows, n = [], n_group
@@ -268,8 +296,17 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         early = a["n_early_every"] < a["n_flows"]
         n_rem = a["n_group"] - a["n_early_size"] * ((a["n_flows"] - 1) // a["n_early_every"])
         need(not early or (a["n_early_size"] >= 1 and n_rem >= 2), "too many early outputs for n_group")
-        need(wn.get("cond_layers", 1) == 1 and wn.get("cond_kernel_size", 1) == 1, "WN cond_layers must be one 1x1 conv")
-        need(wn.get("cond_activation_func", "none") == "none", "WN cond activation is not supported")
+        wn_cond = dict(layers=int(wn.get("cond_layers", 1) or 0), hidden=int(wn.get("cond_hidden_channels", 256)),
+                       kernel_size=int(wn.get("cond_kernel_size", 1)), padding_mode=wn.get("cond_padding_mode", "zeros"),
+                       act=_cond_act(wn.get("cond_activation_func", "none"), wn.get("negative_slope")) if wn.get("cond_layers", 1) else (ACT_NONE, 0.0),
+                       out_act=bool(wn.get("cond_out_activation_func", True)))
+        need(wn_cond["padding_mode"] in PAD_MODES, "WN cond_padding_mode must be zeros / replicate / reflect / circular")
+        wn_tconv = None
+        if wn.get("transposed_conv_scales") and wn.get("transposed_conv_hidden_dim", 256) and wn.get("transposed_conv_kernel_size", 4):
+            need(a["upsample_first"] is False, "a WN-level TransposedUpsampleNet needs upsample_first=False (glow_ax.py:481,:578)")
+            wn_tconv = dict(scales=[int(x) for x in wn["transposed_conv_scales"]], hidden=int(wn.get("transposed_conv_hidden_dim", 256)),
+                            kernel_size=wn.get("transposed_conv_kernel_size", 4))
+        cond_external = not (wn_cond["layers"] == 1 and wn_cond["kernel_size"] == 1 and wn_cond["act"][0] == ACT_NONE and wn_tconv is None)
         need(precision in ("bf16x3", "bf16", "ffma"), "precision must be 'bf16x3', 'bf16' or 'ffma'")
         # ---- WN_config variants (fp32 CUDA-core mode)
         L = int(wn["n_layers"])
@@ -288,13 +325,15 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self._variant = dict(gate=GATED_UNITS[gate], dilations_w=dw, dilations_h=dh, res_skip=res_skip, merge=merge,
                              speaker_dim=int(wn.get("speaker_embed_dim", 0) or 0),
                              n_early_every=int(a["n_early_every"]) if early else 0, n_early_size=int(a["n_early_size"]) if early else 0,
-                             mix_first=bool(a["mix_first"]), mixing_conv=conv_mix)
-        variant = bool(self._variant["gate"] or dw or dh or merge or not res_skip or self._variant["speaker_dim"] or early
+                             mix_first=bool(a["mix_first"]), mixing_conv=conv_mix, wn_cond=wn_cond, wn_tconv=wn_tconv,
+                             cond_external=cond_external)
+        variant = bool(cond_external or self._variant["gate"] or dw or dh or merge or not res_skip or self._variant["speaker_dim"] or early
                        or not a["mix_first"] or conv_mix)
         if variant and precision != "ffma":
             warnings.warn(f"cookietts_b200.WaveFlow: this WN_config (gated_unit {gate}, dilations_w {dw or '2^i'}, dilations_h "
                           f"{dh or 1}, merge_res_skip {merge}, res_skip {res_skip}, WN speaker_embed_dim "
-                          f"{self._variant['speaker_dim']}, early outputs {early}, mix_first {bool(a['mix_first'])}, channel_mixing {'1x1conv' if conv_mix else 'permuteheight'}) runs in the "
+                          f"{self._variant['speaker_dim']}, early outputs {early}, mix_first {bool(a['mix_first'])}, channel_mixing {'1x1conv' if conv_mix else 'permuteheight'}, cond stack {wn_cond['layers']} x k{2 * wn_cond['kernel_size'] - 1}"
+                          f"{' + upsample net' if wn_tconv else ''}) runs in the "
                           f"fp32 CUDA-core mode; precision '{precision}' -> 'ffma'")
             precision = "ffma"
         if precision == "ffma":      # fp32 CUDA-core path (csrc/cwg_wf_ffma.cu): general WN_2d shapes
@@ -358,6 +397,26 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         self._ccfg.n_early_every, self._ccfg.n_early_size = pc.n_early_every, pc.n_early_size
         self._ccfg.mix_first_off = 0 if pc.mix_first else 1
         self._ccfg.mixing_conv = int(pc.mixing_conv)
+        if pc.cond_external:                                 # per-flow device weights of the WN cond paths (_wn_cond_apply)
+            up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev)
+            flows = []
+            for k in range(pc.n_flows):
+                p = f"WN.{k}.WN."
+                cond = [(up(effective_weight(sd, p + f"cond_layers.{i}")), up(sd[p + f"cond_layers.{i}.bias"]))
+                        for i in range(self._wn_cond["layers"])]
+                emb = up(sd[p + "speaker_embed.weight"]) if self.wn_speaker_embed_dim else None
+                tconv = []
+                if self._wn_tconv:
+                    for (idx, kk, st, pd, act) in self.WN[k].WN.upsample_net.layers:
+                        wt = sd[p + f"upsample_net.t_convs.{idx}.weight"]
+                        tconv.append((up(repack_conv_transpose(wt, st)), up(sd[p + f"upsample_net.t_convs.{idx}.bias"]),
+                                      wt.shape[0], wt.shape[1], kk, st, pd, act))
+                group = None
+                if self._fe_group:
+                    wg, bg = self.group_conv_fold(k, np.eye(self._fe_group[0]), np.zeros(self._fe_group[0]), sd)
+                    group = (up(wg[:, :, None]), up(bg))
+                flows.append(dict(cond=cond, emb=emb, tconv=tconv, group=group))
+            dev_pk["flows"] = flows
         self._packed, self._packed_key, self._cw = dev_pk, key, w
         self._graphs = {}
 
@@ -386,7 +445,30 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             if nbytes == 0:
                 raise _cabi.CwgError(lib.cwg_last_error().decode())
             b1_batch = None
-            if self.wn_speaker_embed_dim:                    # WN-level speaker embedding -> per-utterance gate bias
+            c_all = None
+            if self.pack_config.cond_external:               # general WN cond paths: evaluated here, flow by flow
+                Tp = T // self.n_group
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                ids = None
+                if self.wn_speaker_embed_dim:
+                    if speaker_ids is None:
+                        raise Exception("This WaveFlow/WaveGlow model requires speaker ids or speaker embeddings.")
+                    ids = torch.as_tensor(speaker_ids, device=dev).long().view(-1).contiguous()
+                    if ids.numel() != B:
+                        raise ValueError(f"speaker_ids must hold one id per utterance ({B}), got {ids.numel()}")
+                    if int(ids.min()) < 0 or int(ids.max()) >= 512:
+                        raise IndexError("speaker id out of range [0, 512)")
+                if self.upsample_first and cond.shape[2] != Tp:          # efficient_model_ax.py:313-314
+                    cond = self._wn_resample(lib, cond, Tp, stream)
+                pc = self.pack_config
+                need_ch = 2 * pc.n_channels * pc.n_layers
+                c_all = torch.empty(pc.n_flows, B, need_ch, Tp, device=dev, dtype=torch.float32)
+                for k in range(pc.n_flows):
+                    x = self._wn_cond_apply(lib, cond, self._packed["flows"][k], ids, Tp, stream, k, crop_2d=True)
+                    if tuple(x.shape) != (B, need_ch, Tp):
+                        raise RuntimeError(f"WN {k}: cond path output {tuple(x.shape)} != [{B}, {need_ch}, {Tp}]")
+                    c_all[k].copy_(x)
+            elif self.wn_speaker_embed_dim:                  # WN-level speaker embedding -> per-utterance gate bias
                 if speaker_ids is None:
                     raise Exception("This WaveFlow/WaveGlow model requires speaker ids or speaker embeddings.")
                 ids = torch.as_tensor(speaker_ids, device=dev).long().view(-1).contiguous()
@@ -407,6 +489,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                                                     self._packed["spk_embed"].shape[1], ids.data_ptr(), B, b1_batch.data_ptr(),
                                                     torch.cuda.current_stream(dev).cuda_stream))
             self._cw.b1_batch = b1_batch.data_ptr() if b1_batch is not None else None
+            self._cw.c_all = c_all.data_ptr() if c_all is not None else None
 
             def launch(cond_t, z_t, audio_t, ws_t):
                 ws_ptr = (ws_t.data_ptr() + 1023) // 1024 * 1024
@@ -424,7 +507,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                                                       z_t.data_ptr(), 1.0, audio_t.data_ptr(), ws_ptr,
                                                       ws_t.numel() - (ws_ptr - ws_t.data_ptr()),
                                                       B, T, torch.cuda.current_stream(dev).cuda_stream, arr_b, arr_e, n_ev))
-            use_graph = (layer_events is None and b1_batch is None and not torch.cuda.is_current_stream_capturing() and
+            use_graph = (layer_events is None and b1_batch is None and c_all is None and not torch.cuda.is_current_stream_capturing() and
                          (self.graphs is True or (self.graphs == "auto" and B * frames <= self.GRAPH_MAX_FRAMES)))
             if use_graph and self.graphs == "auto" and (B, frames, T, mode) not in self._graphs:
                 if (B, frames, T, mode) not in self._graph_seen:       # capture a shape the second time it is seen

@@ -435,14 +435,6 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
             lib._axg_bound = True
         return lib
 
-    def _resample(self, lib, x, t_out, stream):
-        """F.interpolate(x, size=t_out, mode, align_corners=True for 'linear') - efficient_model_ax.py:175, glow_ax.py:365"""
-        B, ch, t_in = x.shape
-        y = torch.empty(B, ch, t_out, device=x.device, dtype=torch.float32)
-        _cabi.check(lib.cwg_resample1d(x.data_ptr(), B, ch, t_in, ch * t_in, y.data_ptr(), t_out, ch * t_out,
-                                       1 if self.upsample_linear else 0, t_out, 0, 0.0, 0, stream))
-        return y
-
     def _run_general(self, z, cond, ids):
         """The inverse pass in the general fp32 mode: front-end, then per flow (last to first) the WN's own cond stack
         (glow_ax.py:378-389) and one cwg_axg_flow call (mixing, WN, coupling, ignore_nan)."""
@@ -454,7 +446,7 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         Tp = T // G
         cond = self._fe_apply(cond, ids, Tp)
         if self.upsample_first and cond.shape[2] != Tp:      # efficient_model_ax.py:313-314 (the upsample net already ran)
-            cond = self._resample(lib, cond, Tp, stream)
+            cond = self._wn_resample(lib, cond, Tp, stream)
         flows = self._packed["flows"]
         nbytes = max(lib.cwg_axg_workspace_bytes(C.byref(f["cfg"]), B, Tp) for f in flows)
         if nbytes == 0:
@@ -466,35 +458,9 @@ class WaveGlowAx(nn.Module, AxFrontEndMixin):
         ws_bytes = self._workspace.numel() - (ws_ptr - self._workspace.data_ptr())
         zc = torch.empty(B, G, Tp, device=dev, dtype=torch.float32)
         _cabi.check(lib.cwg_group_transpose(z.data_ptr(), zc.data_ptr(), B, Tp, G, 1, stream))
-        wc = self._wn_cond
-        pad, pad_mode = (2 * wc["kernel_size"] - 2) // 2, PAD_MODES[wc["padding_mode"]]
-        act, slope = wc["act"]
         for k in range(self.n_flows - 1, -1, -1):            # efficient_model_ax.py:325
             f = flows[k]
-            x = cond
-            if f["group"] is not None:                       # :316-317,:328
-                x = self._conv1d(lib, x, *f["group"], 0, 0, ACT_NONE, 0.0)
-            if f["emb"] is not None:                         # glow_ax.py:378-381
-                x = torch.cat([x, f["emb"][ids][:, :, None].expand(-1, -1, x.shape[2])], dim=1).contiguous()
-            n = len(f["cond"])
-            for i, (w, b) in enumerate(f["cond"]):           # :383-387
-                a = act if (wc["out_act"] or i != n - 1) else ACT_NONE
-                x = self._conv1d(lib, x, w, b, pad, pad_mode, a, slope)
-            if not self.upsample_first and f["tconv"]:       # :389, _upsample_mels :361-373 with the WN's upsample net
-                x = self._tconv_chain(lib, x, f["tconv"], stream)
-                if int(np.prod(self._wn_tconv["scales"])) != self.hop_length // G and x.shape[2] != Tp:   # interpolation_required
-                    x = self._resample(lib, x, Tp, stream)
-                else:                                        # centre crop :367-372
-                    diff = x.shape[2] - Tp
-                    if diff <= 0 or diff // 2 == 0 or x.shape[2] - 2 * (diff // 2) != Tp:
-                        raise RuntimeError(f"WN {k}: upsampled cond length {x.shape[2]} cannot be cropped to {Tp} group-steps "
-                                           "(the reference's slice is empty or mis-sized here too)")
-                    y = torch.empty(B, x.shape[1], Tp, device=dev, dtype=torch.float32)
-                    _cabi.check(lib.cwg_resample1d(x.data_ptr(), B, x.shape[1], x.shape[2], x.shape[1] * x.shape[2], y.data_ptr(),
-                                                   Tp, x.shape[1] * Tp, 0, x.shape[2], diff // 2, 0.0, 0, stream))
-                    x = y
-            elif not self.upsample_first and x.shape[2] != Tp:   # ... without one: interpolation_required, F.interpolate
-                x = self._resample(lib, x, Tp, stream)
+            x = self._wn_cond_apply(lib, cond, f, ids, Tp, stream, k)
             need_ch = 2 * self._base["n_channels"] * self._base["n_layers"]
             if x.shape[1] != need_ch or x.shape[2] != Tp:
                 raise RuntimeError(f"WN {k}: cond stack output {tuple(x.shape)} != [B, {need_ch}, {Tp}]")

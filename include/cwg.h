@@ -290,6 +290,10 @@ typedef struct cwg_wf_weights {
   /* ABI 5, CWG_MODE_FFMA, mixing_conv = 1: W^-1 of every flow's InvertibleConv1x1, [F][32][32] row major (the flow's
    * n_rem x n_rem matrix in the top-left corner) */
   const float*    winv;
+  /* ABI 5, CWG_MODE_FFMA, optional: the output of every flow's WN cond path evaluated by the caller - multi-layer / activated
+   * cond stacks, a WN-level TransposedUpsampleNet (glow_ax.py:476-505,:565-579) - as [F][batch][2*C*L][T'] fp32.  When set,
+   * w1_f32 has no cond columns (K1 = kernel_h*kernel_w*C), b1 holds the in_layer biases only and `mel` is not read. */
+  const float*    c_all;
 } cwg_wf_weights;
 
 size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples);

@@ -78,6 +78,12 @@ CASES = {
     # InvertibleConv1x1 over the height rows instead of PermuteHeight, after / before the coupling, with early outputs
     "waveflow_v_conv": (dict(_WV, channel_mixing="1x1conv", n_early_every=2, n_early_size=2), 2, 6, 0.9, 87, 37),
     "waveflow_v_conv_mixlast": (dict(_WV, channel_mixing="1x1conv", mix_first=False), 1, 7, 0.8, 88, 38),
+    # a 2-layer WN cond stack (3-tap reflect-padded convs, sigmoid between the layers) and a WN-level TransposedUpsampleNet
+    # whose scale product (3) differs from hop / n_group (2): the upsampled cond is interpolated to T' (upsample_first=False)
+    "waveflow_v_cond": (dict(_WV, wn_cond_layers=2, wn_cond_hidden_channels=11, wn_cond_kernel_size=2, wn_cond_padding_mode="reflect",
+                             wn_cond_activation_func="sigmoid", wn_cond_out_activation_func=False, gated_unit="GTLRU"), 2, 6, 0.9, 89, 39),
+    "waveflow_v_tconv": (dict(_WV, upsample_first=False, wn_tconv_scales=[3], wn_tconv_hidden_dim=7, wn_tconv_kernel_size=5,
+                              wn_speaker_embed_dim=3), 1, 7, 0.8, 90, 40),
     "waveflow_v_speaker": (dict(_WV, wn_speaker_embed_dim=4, upsample_first=False, dilations_h=[1, 2, 1], gated_unit="GTSU"),
                            2, 6, 0.8, 84, 34),
 }

@@ -162,15 +162,9 @@ def inverse(sd, cfg: WaveFlowConfig, z: np.ndarray, cond: np.ndarray, dtype=np.f
     zz = zz[:, off:]
     assert zz.shape[1] == rows[-1]
     for k in reversed(range(cfg.n_flows)):                               # :325
-        p = f"WN.{k}.WN.cond_layers.0"
-        w_c = _w(sd, p, dtype)[:, :, 0]                                  # [2CL, n_mel (+ speaker dims)]
         k_cond = cond_up[k] if isinstance(cond_up, (list, tuple)) else cond_up      # :328
-        if cfg.wn_speaker_embed_dim:                                     # glow_ax.py:567-570
-            emb = np.asarray(sd[f"WN.{k}.WN.speaker_embed.weight"], dtype)[np.asarray(speaker_ids)]
-            k_cond = np.concatenate([k_cond, np.repeat(emb[:, :, None], k_cond.shape[2], axis=2)], axis=1)
-        spec_all = np.einsum("oc,bct->bot", w_c, k_cond, optimize=True) + np.asarray(sd[p + ".bias"], dtype)[None, :, None]
-        if not cfg.upsample_first:                                       # glow_ax.py:578-579 (no WN upsample net)
-            spec_all = upsample_cond(spec_all, Tp, cfg.upsample_mode)
+        from .waveglow_ax_oracle import wn_cond_path                     # speaker embedding, cond stack, WN-level upsampling
+        spec_all = wn_cond_path(sd, f"WN.{k}.WN.", cfg, k_cond, Tp, dtype, speaker_ids, crop_2d=True)   # glow_ax.py:565-579
         def mix(x):                                                      # PermuteHeight.inverse or InvertibleConv1x1.inverse
             if cfg.channel_mixing == "permuteheight":
                 return permute_height(x, k)

@@ -111,14 +111,11 @@ GATED_UNITS = {
 }
 
 
-def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
-    """glow_ax.WN.forward (:375-418): returns (log_s, t).  `cond_up` is at T' rate (upsample_first=True) or at frame
-    rate (upsample_first=False: interpolated after the cond layer, :389)."""
-    p = f"WN.{k}.WN."
+def wn_cond_path(sd, p, cfg, cond_up, T, dtype, speaker_ids=None, crop_2d=False):
+    """The cond path of one WN (glow_ax.py:378-389; WN_2d :565-579): WN-level speaker embedding, cond stack, and with
+    upsample_first=False the WN's upsample net + crop / interpolation (_upsample_mels :361-373; WN_2d's crop rule :545-553 with
+    `crop_2d`).  `cfg` is an AxConfig or a WaveFlowConfig (same field names).  Returns [B, 2CL, T]."""
     C, L = cfg.n_channels, cfg.n_layers
-    audio = np.einsum("oc,bct->bot", _w(sd, p + "start", dtype)[:, :, 0], audio0, optimize=True) \
-        + np.asarray(sd[p + "start.bias"], dtype)[None, :, None]
-    B, _, T = audio.shape
     if cfg.wn_speaker_embed_dim and speaker_ids is not None:             # :378-381
         emb = np.asarray(sd[p + "speaker_embed.weight"], dtype)[np.asarray(speaker_ids)]
         cond_up = np.concatenate([cond_up, np.repeat(emb[:, :, None], cond_up.shape[2], axis=2)], axis=1)
@@ -147,9 +144,23 @@ def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
             spect = upsample_cond(spect, T, cfg.upsample_mode)
         else:                                                            # centre crop :367-372
             pad_l, pad_r = (spect.shape[2] - T) // 2, (-(T - spect.shape[2])) // 2
+            if crop_2d:                                                  # WN_2d: cond[:, :, pad:-(pad + pad % 2)]
+                pad_r = pad_l + pad_l % 2
             spect = spect[:, :, pad_l:spect.shape[2] - pad_r] if pad_r else spect[:, :, pad_l:0]
     elif not cfg.upsample_first:                                         # no WN upsample net: interpolation_required,
         spect = upsample_cond(spect, T, cfg.upsample_mode)               # F.interpolate to the audio length
+    return spect
+
+
+def wn_forward(sd, k, cfg: AxConfig, audio0, cond_up, dtype, speaker_ids=None):
+    """glow_ax.WN.forward (:375-418): returns (log_s, t).  `cond_up` is at T' rate (upsample_first=True) or at frame
+    rate (upsample_first=False: interpolated after the cond layer, :389)."""
+    p = f"WN.{k}.WN."
+    C, L = cfg.n_channels, cfg.n_layers
+    audio = np.einsum("oc,bct->bot", _w(sd, p + "start", dtype)[:, :, 0], audio0, optimize=True) \
+        + np.asarray(sd[p + "start.bias"], dtype)[None, :, None]
+    B, _, T = audio.shape
+    spect = wn_cond_path(sd, p, cfg, cond_up, T, dtype, speaker_ids)
     output = None
     unit_a, unit_b = GATED_UNITS[cfg.gated_unit.upper()]
     split = cfg.res_skip and not cfg.merge_res_skip

@@ -158,7 +158,8 @@ def test_config5_batch_64_full_length_is_consistent():
 
 
 @pytest.mark.parametrize("name", ["waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker",
-                                  "waveflow_v_early", "waveflow_v_mixlast", "waveflow_v_conv", "waveflow_v_conv_mixlast"])
+                                  "waveflow_v_early", "waveflow_v_mixlast", "waveflow_v_conv", "waveflow_v_conv_mixlast",
+                                  "waveflow_v_cond", "waveflow_v_tconv"])
 def test_wn2d_config_variants_match_reference(name):
     """WN_config variants of WN_2d in the fp32 CUDA-core mode - gated units, width / height dilations (deeper conv queues),
     merged / absent res_skip, WN-level speaker embedding with upsample_first=False (glow_ax.py:168-198,:464-466,:506-517,

@@ -15,7 +15,7 @@ CASES = ["waveflow_tiny", "waveflow_nearest", "waveflow_small", "waveflow_config
          "waveflow_5x3", "waveflow_sep7", "waveflow_sep7_128",
          # WN_config variants: gated units, width / height dilations, merged / absent res_skip, WN speaker embedding
          "waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker", "waveflow_v_early", "waveflow_v_mixlast",
-         "waveflow_v_conv", "waveflow_v_conv_mixlast"]
+         "waveflow_v_conv", "waveflow_v_conv_mixlast", "waveflow_v_cond", "waveflow_v_tconv"]
 
 
 def load(name):
