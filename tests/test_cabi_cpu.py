@@ -191,3 +191,58 @@ def test_checkpoint_key_remap():
     model = WaveGlow(**module_kwargs(cfg))
     it = load_checkpoint(model, {"model": {k: torch.from_numpy(v) for k, v in sd.items()}, "iteration": 7})
     assert it == 7
+
+
+@pytest.mark.parametrize("variant", [dict(merge_res_skip=True, gated_unit="GTRU"), dict(res_skip=False, merge_res_skip=True, gated_unit="SPTU"),
+                                     dict(dilations_w=[3, 1], dilations_h=2, gated_unit="GSIU")])
+def test_waveflow_variant_packing_cpu(variant):
+    """WN_2d config variants in the packed fp32 layout (merged / absent res_skip = zero res rows, height dilations = deeper conv
+    queues, gated units): replaying cwg_wf_ffma.cu's per-row layer loop in numpy on the packed arrays reproduces the oracle's
+    WN_2d steps."""
+    import warnings
+    from cookietts_b200 import WaveFlow
+    from cookietts_b200.waveflow import pack_waveflow_state_dict
+    from oracle.make_golden_waveflow import reference_kwargs
+    from oracle.waveflow_oracle import WaveFlowConfig, synthetic_state_dict, wn2d_step, _w
+    from oracle.waveglow_ax_oracle import GATED_UNITS
+    cfg = WaveFlowConfig(n_mel_channels=6, n_flows=2, n_group=8, n_layers=2, n_channels=8, win_length=32, hop_length=8, **variant)
+    sd = synthetic_state_dict(cfg, 6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = WaveFlow(**reference_kwargs(cfg))
+    assert m.precision == "ffma"
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    pk = pack_waveflow_state_dict(sd, m.pack_config)
+    rs = np.random.RandomState(1)
+    B, T, Cc, L, kh, kw = 2, 23, cfg.n_channels, cfg.n_layers, cfg.kernel_size_h, cfg.kernel_size_w
+    n_rows = 6
+    rows = rs.standard_normal((n_rows, B, T))
+    cond_up = rs.standard_normal((B, cfg.n_mel_channels, T))
+    k = 1
+    w_c = _w(sd, f"WN.{k}.WN.cond_layers.0", np.float64)[:, :, 0]
+    spec_all = np.einsum("oc,bct->bot", w_c, cond_up) + np.asarray(sd[f"WN.{k}.WN.cond_layers.0.bias"], np.float64)[None, :, None]
+    queues = [None] * L
+    ua, ub = GATED_UNITS[cfg.gated_unit.upper()]
+    hist = [[] for _ in range(L + 1)]                 # hist[l][r]: layer-l input at row r, [B, T, C] (the conv queues of the kernel)
+    for r in range(n_rows):
+        log_s, t = wn2d_step(sd, k, cfg, rows[r], spec_all, queues, np.float64)
+        hist[0].append(pk["start_w"][k].astype(np.float64)[None, None, :] * rows[r][:, :, None] + pk["start_b"][k].astype(np.float64))
+        eo = np.tile(pk["eo_b"][k].astype(np.float64), (B, T, 1))
+        for l in range(L):
+            d, dh = cfg.dilation_w(l), cfg.dilation_h(l)
+            pad = ((kw - 1) * d) // 2
+            cols = []
+            for a in range(kh):
+                rr = r - (kh - 1 - a) * dh            # wff_a: src_row = row - (KH - 1 - a) * dil_h
+                src = hist[l][rr] if rr >= 0 else np.zeros((B, T, Cc))
+                xp = np.zeros((B, T + 2 * pad, Cc)); xp[:, pad:pad + T] = src
+                cols += [xp[:, b * d:b * d + T] for b in range(kw)]
+            a_mat = np.concatenate(cols + [cond_up.transpose(0, 2, 1)], axis=2)
+            pre = a_mat @ pk["w1_f64"][k, l].T + pk["b1"][k, l].astype(np.float64)
+            acts = ua(pre[..., :Cc]) * ub(pre[..., Cc:])
+            rsk = acts @ pk["w2_f64"][k, l].T
+            hist[l + 1].append(hist[l][r] + rsk[..., :Cc] + pk["b2"][k, l].astype(np.float64))
+            eo = eo + rsk[..., Cc:]
+        assert np.abs(eo[..., 0] - log_s).max() < 1e-9 and np.abs(eo[..., 1] - t).max() < 1e-9, r
+        if cfg.merge_res_skip:                        # the hidden tensor is never updated
+            assert all(np.array_equal(hist[l][r], hist[0][r]) for l in range(1, L))
