@@ -214,8 +214,8 @@ int cwg_fd_launch_count(const cwg_fd_config* cfg) {
 int cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const float* cond, float* z,
                    void* workspace, size_t workspace_bytes, int batch, int t_steps, void* cuda_stream) {
   if (int r = check(cfg, batch, t_steps)) return r;
-  CWG_REQUIRE(w && cond && z && workspace, "NULL argument");
-  CWG_REQUIRE(w->start_w && w->start_b && w->cond_w && w->cond_b && w->in_w && w->in_b && w->end_w && w->end_b && w->winv,
+  CWG_REQUIRE(w && z && workspace && (cond || w->c_all), "NULL argument");
+  CWG_REQUIRE(w->start_w && w->start_b && (w->c_all || (w->cond_w && w->cond_b)) && w->in_w && w->in_b && w->end_w && w->end_b && w->winv,
               "missing weight arrays");
   CWG_REQUIRE(!cfg->res_skip || (w->rs_w && w->rs_b), "res_skip weights missing");
   FdWs ws;
@@ -262,10 +262,15 @@ int cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const floa
     p.Cin = nh; p.N = C; p.ks = 1; p.x = cur + (size_t)off * T; p.x_bstride = zb;
     p.w = w->start_w + o_start[k]; p.bias = w->start_b + (size_t)k * C; p.y = ws.h; p.y_bstride = (long long)C * T;
     if (int r = conv<0>(p, s)) return r;
-    p.Cin = cfg->cond_channels; p.N = 2 * C * L; p.x = cond; p.x_bstride = (long long)cfg->cond_channels * T;
-    p.w = w->cond_w + (size_t)k * 2 * C * L * cfg->cond_channels; p.bias = w->cond_b + (size_t)k * 2 * C * L;
-    p.y = ws.c_all; p.y_bstride = (long long)2 * C * L * T;
-    if (int r = conv<0>(p, s)) return r;
+    const float* c_all = ws.c_all;
+    if (w->c_all) {                                                                 // cond stack evaluated by the caller
+      c_all = w->c_all + (size_t)k * B * 2 * C * L * T;
+    } else {
+      p.Cin = cfg->cond_channels; p.N = 2 * C * L; p.x = cond; p.x_bstride = (long long)cfg->cond_channels * T;
+      p.w = w->cond_w + (size_t)k * 2 * C * L * cfg->cond_channels; p.bias = w->cond_b + (size_t)k * 2 * C * L;
+      p.y = ws.c_all; p.y_bstride = (long long)2 * C * L * T;
+      if (int r = conv<0>(p, s)) return r;
+    }
     if (!cfg->merge_res_skip) CWG_CHECK_CUDA(cudaMemsetAsync(ws.out, 0, (size_t)B * C * T * sizeof(float), s));
     for (int i = 0; i < L; ++i) {
       const size_t li = (size_t)k * L + i;
@@ -273,7 +278,7 @@ int cwg_fd_inverse(const cwg_fd_config* cfg, const cwg_fd_weights* w, const floa
       g.B = B; g.T = T; g.Cin = C; g.N = C; g.ks = ks; g.dil = cfg->dilations[i];
       g.pad_value = k == 0 ? cfg->first_pad_value : 0.f;                        // untts glow.py:80,126
       g.x = ws.h; g.x_bstride = (long long)C * T; g.w = w->in_w + li * 2 * C * C * ks; g.bias = w->in_b + li * 2 * C;
-      g.add = ws.c_all + (size_t)2 * C * i * T; g.add_bstride = (long long)2 * C * L * T;
+      g.add = c_all + (size_t)2 * C * i * T; g.add_bstride = (long long)2 * C * L * T;
       g.y = ws.acts; g.y_bstride = (long long)C * T;
       if (int r = conv<2>(g, s)) return r;
       const bool last = i == L - 1;

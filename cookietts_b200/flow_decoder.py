@@ -10,9 +10,12 @@ channels-first layout - these decoders run at mel-frame rate, a few GFLOP per ut
 direction) raises; there is no CPU fallback.
 
 Supported: the hparams defaults of both models and their WN variants - any n_group / n_flows / early outputs, mix_first on
-or off, WN with one 1x1 cond layer without activation, 1..16 layers with 2^i / constant / listed dilations, res_skip
-and merge_res_skip on or off, the untts `decoder_padding_value`.  Decoder-level cond layers (cond_layers > 0,
-cond_residual), separable convs, several WN cond layers and cond activations raise NotImplementedError.
+or off, 1..16 layers with 2^i / constant / listed dilations, res_skip and merge_res_skip on or off, the untts
+`decoder_padding_value`, depthwise-separable in_layers (folded to dense convs at pack time - exact, also under the constant
+padding), WN cond stacks of several layers / kernel sizes / padding modes with an activation after every layer (evaluated
+by the module with `cwg_conv1d` and handed over as `cwg_fd_weights.c_all`).  Decoder-level cond layers (cond_layers > 0,
+cond_residual, cond_res_rezero) raise NotImplementedError: the reference's own constructor fails on them (glow.py:196-201
+reads undefined names), so there is nothing to be faithful to.
 """
 from __future__ import annotations
 
@@ -36,10 +39,13 @@ class CwgFdConfig(C.Structure):
 
 
 FD_WEIGHT_FIELDS = ("start_w", "start_b", "cond_w", "cond_b", "in_w", "in_b", "rs_w", "rs_b", "end_w", "end_b", "winv")
+# glow.py:89-101: 'lrelu' is relu; 'relu' (meant to be LeakyReLU(0.2)) raises NameError in the reference's constructor
+FD_COND_ACTS = {"none": 0, "lrelu": 1, "tanh": 3, "sigmoid": 4}
+FD_PAD_MODES = {"zeros": 0, "replicate": 1, "reflect": 2, "circular": 3}
 
 
 class CwgFdWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in FD_WEIGHT_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in FD_WEIGHT_FIELDS + ("c_all",)]
 
 
 def _bind(lib):
@@ -75,13 +81,21 @@ class _WN(nn.Module):
         self.end = nn.Conv1d(C_, 2 * n_in_channels, 1)
         self.end.weight.data.zero_()
         self.end.bias.data.zero_()
-        self.cond_layers = nn.ModuleList([wn(nn.Conv1d(cond_in_channels, 2 * C_ * L, 1), name="weight")])
+        kc = hp.wn_cond_kernel_size
+        dims = [cond_in_channels] + [hp.wn_cond_hidden_channels] * (hp.wn_cond_layers - 1) + [2 * C_ * L]
+        self.cond_layers = nn.ModuleList([                    # glow.py:74-87
+            wn(nn.Conv1d(di, do, kc, padding=(kc - 1) // 2, padding_mode=hp.wn_cond_padding_mode), name="weight")
+            for di, do in zip(dims[:-1], dims[1:])])
         self.res_skip_layers = nn.ModuleList()
         dil = hp.wn_dilations_w
         for i in range(L):
             d = 2 ** i if dil is None else (dil if isinstance(dil, int) else dil[i])
             pad = (ks * d - d) // 2 if not getattr(hp, "_explicit_pad", False) else 0
-            self.in_layers.append(wn(nn.Conv1d(C_, 2 * C_, ks, dilation=d, padding=pad), name="weight"))
+            if not hp.wn_seperable_conv or ks == 1:
+                self.in_layers.append(wn(nn.Conv1d(C_, 2 * C_, ks, dilation=d, padding=pad), name="weight"))
+            else:                                            # glow.py:115-121
+                self.in_layers.append(nn.Sequential(wn(nn.Conv1d(C_, C_, ks, dilation=d, padding=pad, groups=C_), name="weight"),
+                                                    wn(nn.Conv1d(C_, 2 * C_, 1), name="weight")))
             if hp.wn_res_skip:
                 rs = 2 * C_ if (i < L - 1 and not hp.wn_merge_res_skip) else C_
                 self.res_skip_layers.append(wn(nn.Conv1d(C_, rs, 1), name="weight"))
@@ -113,9 +127,14 @@ class FlowDecoder(nn.Module):
         assert hp.n_group % 2 == 0
         need(getattr(hp, "cond_layers", 0) == 0, "decoder-level cond_layers > 0")
         need(not getattr(hp, "cond_res_rezero", False), "cond_res_rezero")
-        need(hp.wn_cond_layers == 1 and hp.wn_cond_kernel_size == 1, "WN cond net other than one 1x1 layer")
-        need(str(hp.wn_cond_act_func).lower() == "none", "WN cond activation")
-        need((not hp.wn_seperable_conv) or hp.wn_kernel_size == 1, "wn_seperable_conv")
+        assert hp.wn_cond_layers > 0, "cond_layers must be greater than 0"      # glow.py:53
+        need(hp.wn_cond_kernel_size % 2 == 1, "even wn_cond_kernel_size (the reference's output length then differs from its input's)")
+        need(str(hp.wn_cond_act_func).lower() in FD_COND_ACTS, "wn_cond_act_func must be none / lrelu / tanh / sigmoid "
+                                                                 "('relu' raises NameError in the reference, glow.py:96)")
+        need(hp.wn_cond_padding_mode in FD_PAD_MODES, "wn_cond_padding_mode must be zeros / replicate / reflect / circular")
+        self.cond_external = not (hp.wn_cond_layers == 1 and hp.wn_cond_kernel_size == 1 and str(hp.wn_cond_act_func).lower() == "none")
+        self.cond_stack = dict(layers=hp.wn_cond_layers, pad=(hp.wn_cond_kernel_size - 1) // 2,
+                               pad_mode=FD_PAD_MODES[hp.wn_cond_padding_mode], act=FD_COND_ACTS[str(hp.wn_cond_act_func).lower()])
         need(hp.wn_res_skip or hp.wn_merge_res_skip, "wn_res_skip=False needs wn_merge_res_skip=True (glow.py:53)")
         need(hp.wn_n_layers <= FD_MAX_LAYERS, f"more than {FD_MAX_LAYERS} WN layers")
         self.n_flows, self.n_group = hp.n_flows, hp.n_group
@@ -169,11 +188,17 @@ class FlowDecoder(nn.Module):
             p = f"WN.{k}.WN."
             parts["start_w"].append(_eff(sd, p + "start")[:, :, 0].reshape(-1))
             parts["start_b"].append(sd[p + "start.bias"].double())
-            parts["cond_w"].append(_eff(sd, p + "cond_layers.0")[:, :, 0].reshape(-1))
-            parts["cond_b"].append(sd[p + "cond_layers.0.bias"].double())
+            if not self.cond_external:
+                parts["cond_w"].append(_eff(sd, p + "cond_layers.0")[:, :, 0].reshape(-1))
+                parts["cond_b"].append(sd[p + "cond_layers.0.bias"].double())
             for i in range(L):
-                parts["in_w"].append(_eff(sd, p + f"in_layers.{i}").reshape(-1))
-                parts["in_b"].append(sd[p + f"in_layers.{i}.bias"].double())
+                if p + f"in_layers.{i}.0.bias" in sd:        # separable: W[o, c, j] = P[o, c] * D[c, j], b = P b_d + b_p (exact)
+                    dwt, pwt = _eff(sd, p + f"in_layers.{i}.0")[:, 0], _eff(sd, p + f"in_layers.{i}.1")[:, :, 0]
+                    parts["in_w"].append((pwt[:, :, None] * dwt[None]).reshape(-1))
+                    parts["in_b"].append(pwt @ sd[p + f"in_layers.{i}.0.bias"].double() + sd[p + f"in_layers.{i}.1.bias"].double())
+                else:
+                    parts["in_w"].append(_eff(sd, p + f"in_layers.{i}").reshape(-1))
+                    parts["in_b"].append(sd[p + f"in_layers.{i}.bias"].double())
                 if w["res_skip"]:
                     rw = torch.zeros(2 * Cc, Cc, dtype=torch.float64)
                     rb = torch.zeros(2 * Cc, dtype=torch.float64)
@@ -197,6 +222,10 @@ class FlowDecoder(nn.Module):
                           first_pad_value=self.first_pad_value)
         for i, d in enumerate(self.dilations):
             cfg.dilations[i] = int(d)
+        if self.cond_external:                               # per-flow cond stacks, evaluated in `inverse` with cwg_conv1d
+            dev_pk["cond_stack"] = [[(_eff(sd, f"WN.{k}.WN.cond_layers.{j}").float().contiguous().to(dev),
+                                      sd[f"WN.{k}.WN.cond_layers.{j}.bias"].float().contiguous().to(dev))
+                                     for j in range(self.cond_stack["layers"])] for k in range(F)]
         self._packed, self._packed_key, self._cw, self._ccfg = dev_pk, key, cw, cfg
 
     @torch.no_grad()
@@ -227,6 +256,21 @@ class FlowDecoder(nn.Module):
                 self._workspace = None
                 self._workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             ws_ptr = (self._workspace.data_ptr() + 255) // 256 * 256
+            c_all = None
+            if self.cond_external:                           # glow.py:145-148: every layer is followed by the activation
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                cs = self.cond_stack
+                c_all = torch.empty(self.n_flows, B, 2 * self.wn["n_channels"] * self.wn["n_layers"], T, device=dev, dtype=torch.float32)
+                for k in range(self.n_flows):
+                    x = cc
+                    layers = self._packed["cond_stack"][k]
+                    for j, (wj, bj) in enumerate(layers):
+                        last = j == len(layers) - 1
+                        y = c_all[k] if last else torch.empty(B, wj.shape[0], T, device=dev, dtype=torch.float32)
+                        _cabi.check(lib.cwg_conv1d(x.data_ptr(), B, wj.shape[1], T, wj.data_ptr(), bj.data_ptr(), wj.shape[0],
+                                                   wj.shape[2], cs["pad"], cs["pad_mode"], cs["act"], 0.0, 1.0, None, y.data_ptr(), stream))
+                        x = y
+            self._cw.c_all = c_all.data_ptr() if c_all is not None else None
             _cabi.check(lib.cwg_fd_inverse(self._ccfg, self._cw, cc.data_ptr(), zz.data_ptr(), ws_ptr, nbytes, B, T,
                                            torch.cuda.current_stream(dev).cuda_stream))
         return zz.view(B, self.n_mel_channels, -1), None

@@ -416,6 +416,9 @@ typedef struct cwg_fd_weights {
   const float* end_w;     /* concatenated [2 n_half_k][C]                 */
   const float* end_b;     /* concatenated [2 n_half_k]                    */
   const float* winv;      /* concatenated [n_rem_k][n_rem_k]  W^-1, row major */
+  /* ABI 5, optional: the output of every flow's WN cond stack evaluated by the caller (several cond layers / kernel sizes /
+   * activations, glow.py:74-101,:145-148) as [F][batch][2CL][T]; cond_w / cond_b and `cond` are then not read */
+  const float* c_all;
 } cwg_fd_weights;
 
 size_t cwg_fd_workspace_bytes(const cwg_fd_config* cfg, int batch, int t_steps);

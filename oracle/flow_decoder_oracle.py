@@ -36,6 +36,13 @@ class FlowDecoderConfig:
     wn_merge_res_skip: bool = True
     first_pad_value: float = 0.0      # untts decoder_padding_value (hidden-tensor padding of flow 0's WN)
     end_std: float = 0.05             # synthetic checkpoints only: std of the (non-zero) `end` weights
+    # WN variants (glow.py:74-101,:109-126,:145-148): separable in_layers, cond stacks with an activation after EVERY layer
+    wn_seperable_conv: bool = False
+    wn_cond_layers: int = 1
+    wn_cond_hidden_channels: int = 256
+    wn_cond_kernel_size: int = 1      # taps of the cond convs (odd; 'same' padding)
+    wn_cond_padding_mode: str = "zeros"
+    wn_cond_act_func: str = "none"    # 'lrelu' (= relu in the reference), 'tanh', 'sigmoid'; 'relu' raises NameError upstream
 
     def dilations(self) -> List[int]:
         if self.wn_dilations_w is None:
@@ -82,11 +89,36 @@ def wn_forward(sd, k, cfg: FlowDecoderConfig, z0, cond):
     p = f"WN.{k}.WN."
     C = cfg.wn_n_channels
     h = _conv1d(z0, _eff(sd, p + "start"), sd[p + "start.bias"].astype(np.float64))
-    c = _conv1d(cond, _eff(sd, p + "cond_layers.0"), sd[p + "cond_layers.0.bias"].astype(np.float64))
+    c = cond
+    for j in range(cfg.wn_cond_layers):                                  # glow.py:145-148
+        w_c, b_c = _eff(sd, p + f"cond_layers.{j}"), sd[p + f"cond_layers.{j}.bias"].astype(np.float64)
+        kc = w_c.shape[2]
+        mode = {"zeros": "constant", "replicate": "edge", "reflect": "reflect", "circular": "wrap"}[cfg.wn_cond_padding_mode]
+        cp = np.pad(c, ((0, 0), (0, 0), ((kc - 1) // 2,) * 2), mode=mode)
+        c = sum(np.einsum("oc,bct->bot", w_c[:, :, t], cp[:, :, t:t + c.shape[2]]) for t in range(kc)) + b_c[None, :, None]
+        act = cfg.wn_cond_act_func.lower()
+        if act == "lrelu":
+            c = np.maximum(c, 0)                                         # 'lrelu' maps to relu, glow.py:93-94
+        elif act == "tanh":
+            c = np.tanh(c)
+        elif act == "sigmoid":
+            c = 1.0 / (1.0 + np.exp(-c))
+        else:
+            assert act == "none", act
     out = np.zeros_like(h)
     pad = cfg.first_pad_value if k == 0 else 0.0
     for i, d in enumerate(cfg.dilations()):
-        pre = _conv1d(h, _eff(sd, p + f"in_layers.{i}"), sd[p + f"in_layers.{i}.bias"].astype(np.float64), d, pad)
+        if cfg.wn_seperable_conv and cfg.wn_kernel_size > 1:            # depthwise then pointwise, glow.py:115-121
+            dw = _eff(sd, p + f"in_layers.{i}.0")                        # [C, 1, k]
+            ks = dw.shape[2]
+            pp = (ks * d - d) // 2
+            hp = np.full(h.shape[:2] + (h.shape[2] + 2 * pp,), pad, dtype=h.dtype)
+            hp[:, :, pp:pp + h.shape[2]] = h
+            dwo = sum(dw[None, :, 0, t, None] * hp[:, :, t * d:t * d + h.shape[2]] for t in range(ks)) \
+                + sd[p + f"in_layers.{i}.0.bias"].astype(np.float64)[None, :, None]
+            pre = _conv1d(dwo, _eff(sd, p + f"in_layers.{i}.1"), sd[p + f"in_layers.{i}.1.bias"].astype(np.float64))
+        else:
+            pre = _conv1d(h, _eff(sd, p + f"in_layers.{i}"), sd[p + f"in_layers.{i}.bias"].astype(np.float64), d, pad)
         pre = pre + c[:, 2 * C * i:2 * C * (i + 1)]
         acts = np.tanh(pre[:, :C]) / (1.0 + np.exp(-pre[:, C:]))
         if cfg.wn_res_skip:
@@ -159,11 +191,17 @@ def synthetic_state_dict(cfg: FlowDecoderConfig, seed: int) -> Dict[str, np.ndar
         sd[f"convinv.{k}.weight"] = (q1 @ np.diag(rs.uniform(0.7, 1.4, size=n_rem)) @ q2).astype(np.float32)[:, :, None]
         p = f"WN.{k}.WN"
         for i in range(L):
-            wn_conv(p + f".in_layers.{i}", 2 * C, C, ks)
+            if cfg.wn_seperable_conv and ks > 1:
+                wn_conv(p + f".in_layers.{i}.0", C, 1, ks)
+                wn_conv(p + f".in_layers.{i}.1", 2 * C, C, 1)
+            else:
+                wn_conv(p + f".in_layers.{i}", 2 * C, C, ks)
         wn_conv(p + ".start", C, n_half, 1)
         sd[p + ".end.weight"] = (rs.standard_normal((2 * n_half, C, 1)) * cfg.end_std).astype(np.float32)
         sd[p + ".end.bias"] = (rs.standard_normal((2 * n_half,)) * cfg.end_std).astype(np.float32)
-        wn_conv(p + ".cond_layers.0", 2 * C * L, cfg.cond_channels, 1)
+        dims = [cfg.cond_channels] + [cfg.wn_cond_hidden_channels] * (cfg.wn_cond_layers - 1) + [2 * C * L]
+        for j, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
+            wn_conv(p + f".cond_layers.{j}", co, ci, cfg.wn_cond_kernel_size)
         if cfg.wn_res_skip:
             for i in range(L):
                 wn_conv(p + f".res_skip_layers.{i}", cfg.rs_channels(i), C, 1)
