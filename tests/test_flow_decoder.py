@@ -12,7 +12,7 @@ from oracle.flow_decoder_oracle import FlowDecoderConfig, synthetic_state_dict, 
 from oracle.make_golden_flow_decoder import hparams_for
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["fd_small", "fd_flowtts", "fd_layers", "fd_untts"]
+NAMES = ["fd_small", "fd_flowtts", "fd_layers", "fd_untts", "fd_separable", "fd_condstack"]
 
 
 def load(name):
@@ -51,9 +51,12 @@ def test_unsupported_variants_raise():
     with pytest.raises(NotImplementedError):
         FlowDecoder(hp)
     hp = hparams_for(cfg, "flowtts")
-    hp.wn_cond_act_func = "tanh"
+    hp.wn_cond_act_func = "relu"                   # NameError in the reference's own constructor (glow.py:96)
     with pytest.raises(NotImplementedError):
         FlowDecoder(hp)
+    hp = hparams_for(cfg, "flowtts")
+    hp.wn_cond_layers, hp.wn_cond_act_func = 2, "tanh"      # WN cond stacks are served (fd_condstack golden)
+    assert FlowDecoder(hp).cond_external
 
 
 @pytest.mark.gpu
