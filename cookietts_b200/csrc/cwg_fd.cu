@@ -15,7 +15,7 @@
 namespace cwg {
 namespace {
 
-constexpr int FBM = 64, FBN = 64, FBK = 16;
+constexpr int FBM = 128, FBN = 64, FBK = 16;
 
 struct FdConvP {
   int B, Cin, T, N, ks, dil;
@@ -27,59 +27,95 @@ struct FdConvP {
   float* y; long long y_bstride;              // y[b][n][t]
 };
 
+// Implicit-GEMM conv1d on [B, C, T]: rows m = (b, t), columns n = output channel, K ordered TAP-MAJOR (k = tap * Cin + ci) so
+// that a 16-deep k-tile normally lies inside one tap and the gather needs no per-element division.  128 x 64 block tile,
+// 256 threads, 8 (rows, as two groups of 4: m = tx*4 + i and 64 + tx*4 + i, conflict-free LDS.128) x 4 (columns) per thread;
+// the next k-tile is fetched into registers while the current one is multiplied.
 // EPI 0: y = conv + bias;  1: y += conv + bias;  2: y = gated_unit(pre[n], pre[n + N]), pre = conv + bias + add
 template <int EPI>
-__global__ void __launch_bounds__(256) k_fd_conv(FdConvP p) {
-  __shared__ float As[FBK][FBM + 4];
-  __shared__ float Bs[FBK][FBN + 4];
-  __shared__ float Bg[EPI == 2 ? FBK : 1][FBN + 4];
+__global__ void __launch_bounds__(256, 2) k_fd_conv(FdConvP p) {
+  __shared__ __align__(16) float As[FBK][FBM + 4];
+  __shared__ __align__(16) float Bs[FBK][FBN + 4];
+  __shared__ __align__(16) float Bg[EPI == 2 ? FBK : 1][FBN + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const long long M = (long long)p.B * p.T;
   const long long m0 = (long long)blockIdx.x * FBM;
   const int n0 = blockIdx.y * FBN;
   const int KD = p.Cin * p.ks;
-  float acc[4][4] = {}, acg[4][4] = {};
-  const int a_row = tid % FBM, a_k = tid / FBM;
+  float acc[8][4] = {}, acg[EPI == 2 ? 8 : 1][4] = {};
+  const int a_row = tid % FBM, a_k = tid / FBM;              // a_k in {0, 1}: this thread gathers k = a_k + 2r of every tile
   const long long am = m0 + a_row;
   int ab = 0, at = 0;
   const bool a_ok = am < M;
   if (a_ok) { ab = (int)(am / p.T); at = (int)(am - (long long)ab * p.T); }
+  const float* xrow = p.x + (size_t)ab * p.x_bstride;
   const int half = p.ks / 2;
-  for (int k0 = 0; k0 < KD; k0 += FBK) {
+  const int b_n = tid / FBK, b_k = tid % FBK;                // weights: rows b_n + 16 r', column b_k of the tile
+  float ra[8], rb[4], rg[EPI == 2 ? 4 : 1];
+  auto fetch = [&](int k0) {
+    const int j0 = k0 / p.Cin, j1 = min(k0 + FBK - 1, KD - 1) / p.Cin;      // block-uniform
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int kk = a_k + 4 * r, kd = k0 + kk;
+    for (int r = 0; r < 8; ++r) {
+      const int kd = k0 + a_k + 2 * r;
       float v = 0.f;
       if (a_ok && kd < KD) {
-        const int ci = kd / p.ks, j = kd - ci * p.ks;
+        const int j = j0 == j1 ? j0 : kd / p.Cin;
+        const int ci = kd - j * p.Cin;
         const int ti = at + p.dil * (j - half);
-        v = (ti >= 0 && ti < p.T) ? __ldg(p.x + (size_t)ab * p.x_bstride + (size_t)ci * p.T + ti) : p.pad_value;
+        v = (ti >= 0 && ti < p.T) ? __ldg(xrow + (size_t)ci * p.T + ti) : p.pad_value;
       }
-      As[kk][a_row] = v;
-      const int idx = tid + r * 256, n = idx / FBK, bk = idx % FBK;
-      const bool ok = n0 + n < p.N && k0 + bk < KD;
-      Bs[bk][n] = ok ? __ldg(p.w + (size_t)(n0 + n) * KD + k0 + bk) : 0.f;
-      if (EPI == 2) Bg[bk][n] = ok ? __ldg(p.w + (size_t)(n0 + n + p.N) * KD + k0 + bk) : 0.f;
+      ra[r] = v;
     }
+    const int kd = k0 + b_k;
+    const int j = j0 == j1 ? j0 : kd / p.Cin;
+    const int wcol = (kd - j * p.Cin) * p.ks + j;            // w[n][ci][j]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = n0 + b_n + 16 * r;
+      const bool ok = n < p.N && kd < KD;
+      rb[r] = ok ? __ldg(p.w + (size_t)n * KD + wcol) : 0.f;
+      if (EPI == 2) rg[r] = ok ? __ldg(p.w + (size_t)(n + p.N) * KD + wcol) : 0.f;
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) As[a_k + 2 * r][a_row] = ra[r];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      Bs[b_k][b_n + 16 * r] = rb[r];
+      if (EPI == 2) Bg[b_k][b_n + 16 * r] = rg[r];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < KD; k0 += FBK) {
+    stage();
     __syncthreads();
+    if (k0 + FBK < KD) fetch(k0 + FBK);
 #pragma unroll
     for (int kk = 0; kk < FBK; ++kk) {
-      float a[4], b[4], g[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + tx * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][tx + 16 * i]; b[i] = Bs[kk][ty * 4 + i]; if (EPI == 2) g[i] = Bg[kk][ty * 4 + i]; }
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (EPI == 2) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&Bg[kk][ty * 4]);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-          if (EPI == 2) acg[i][j] = fmaf(a[i], g[j], acg[i][j]);
-        }
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acg[i][j] = fmaf(a[i], g[j], acg[i][j]);
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + tx + 16 * i;
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
     if (m >= M) continue;
     const int b = (int)(m / p.T), t = (int)(m - (long long)b * p.T);
 #pragma unroll
