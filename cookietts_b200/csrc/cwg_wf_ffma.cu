@@ -99,6 +99,29 @@ __global__ void __launch_bounds__(256) k_wff_gemm(WffGemmP p) {
   }
 }
 
+// Depthwise part of a separable in_layer (glow_ax.py:525-528): d[m][c] = b[c] + sum_{a,b} w[c][a][b] * x_queue[row - (KH-1-a)*dil_h]
+// [t + (b - KW/2)*dil_w][c], causal in height (zero queue), 'same' zero padding in width.  One thread per (group-step, channel).
+__global__ void k_wff_depthwise(long long BT, int Tp, int C, int KH, int KW, const float* __restrict__ ring, int row, int dil_w,
+                                int dil_h, int ring_rows, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BT * C) return;
+  const long long m = i / C; const int c = (int)(i - m * C);
+  const long long ub = m / Tp; const int t = (int)(m - ub * Tp);
+  float acc = __ldg(bias + c);
+  const float* wc = w + (size_t)c * KH * KW;
+  for (int a = 0; a < KH; ++a) {
+    const int src_row = row - (KH - 1 - a) * dil_h;
+    if (src_row < 0) continue;
+    const float* base = ring + ((size_t)(src_row % ring_rows) * BT + (size_t)ub * Tp) * C + c;
+    for (int b = 0; b < KW; ++b) {
+      const int tt = t + (b - KW / 2) * dil_w;
+      if (tt >= 0 && tt < Tp) acc = fmaf(__ldg(wc + a * KW + b), __ldg(base + (size_t)tt * C), acc);
+    }
+  }
+  out[i] = acc;
+}
+
 __global__ void k_wff_gate(const float* __restrict__ pre, float* __restrict__ acts, long long n, int C, int gate) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -192,13 +215,14 @@ inline int wff_ring_rows(const cwg_wf_config* c) {
   return (c->kernel_h - 1) * mx + 1;
 }
 
-struct WffWs { float *eo, *state, *mel_up, *x, *pre, *acts; size_t bytes; };
+struct WffWs { float *eo, *state, *mel_up, *x, *pre, *acts, *dwo; size_t bytes; };
 void wff_carve(const cwg_wf_config* c, long long BT, void* base, WffWs* ws) {
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align_up(off + n * sizeof(float), 1024); return (float*)((char*)base + o); };
   ws->eo = take((size_t)BT * CWG_EO_PAD); ws->state = take((size_t)BT * c->n_group); ws->mel_up = take((size_t)BT * c->n_mel);
   ws->x = take((size_t)c->n_layers * wff_ring_rows(c) * BT * c->n_channels);
   ws->pre = take((size_t)BT * 2 * c->n_channels); ws->acts = take((size_t)BT * c->n_channels);
+  ws->dwo = take((size_t)BT * c->n_channels);                      // depthwise output of a separable in_layer
   ws->bytes = off;
 }
 
@@ -227,7 +251,7 @@ size_t wff_workspace_bytes(const cwg_wf_config* c, int batch, int t_samples) {
 
 int wff_launch_count(const cwg_wf_config* c) {
   int n = 1 + (wff_n_rem(c, c->n_flows - 1) < c->n_group ? 1 : 0) + (c->mixing_conv ? c->n_flows + 1 : 0);
-  for (int k = 0; k < c->n_flows; ++k) { const int h = wff_n_rem(c, k); n += h + (h - 1) * c->n_layers * 3; }
+  for (int k = 0; k < c->n_flows; ++k) { const int h = wff_n_rem(c, k); n += h + (h - 1) * c->n_layers * 3; }   // (+1 per layer when separable)
   return n;
 }
 
@@ -243,7 +267,9 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
   WffWs ws;
   wff_carve(cfg, BT, workspace, &ws);
   CWG_REQUIRE(ws.bytes <= workspace_bytes, "workspace too small: need %zu, got %zu", ws.bytes, workspace_bytes);
-  const int K1 = KH * KW * C + M, N2 = C + CWG_EO_PAD;
+  const bool sep = w->dw_w != nullptr;                             // separable in_layers: depthwise kernel, then a 1x1 GEMM
+  CWG_REQUIRE(!sep || w->dw_b, "dw_b missing");
+  const int K1 = (sep ? C : KH * KW * C) + M, N2 = C + CWG_EO_PAD;
   const int R = wff_ring_rows(cfg);                                // rows of every layer's conv queue
   if (M > 0) {
     const long long n = BT * M;
@@ -294,6 +320,12 @@ int wff_infer(const cwg_wf_config* cfg, const cwg_wf_weights* w, const float* me
           p.N = 2 * C; p.K = K1; p.W = w->w1_f32 + idx * 2 * C * K1; p.bias = w->b1 + idx * 2 * C;
           p.ring = ws.x + (size_t)l * R * slot; p.mel = ws.mel_up; p.row = i; p.dil = wff_dil_w(cfg, l); p.pre = ws.pre;
           p.dil_h = wff_dil_h(cfg, l); p.ring_rows = R;
+          if (sep) {
+            const long long n = BT * C;
+            k_wff_depthwise<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(BT, Tp, C, KH, KW, p.ring, i, p.dil, p.dil_h, R,
+                                                                          w->dw_w + idx * C * KH * KW, w->dw_b + idx * C, ws.dwo);
+            p.KH = 1; p.KW = 1; p.ring = ws.dwo; p.row = 0; p.dil = 1; p.dil_h = 1; p.ring_rows = 1;   // pointwise 1x1 on d
+          }
           if (w->b1_batch) { p.bias = w->b1_batch + idx * 2 * C; p.bias_bstride = (long long)F * L * 2 * C; }
           if (w->c_all) {
             p.c_bstride = (long long)2 * C * L * Tp;

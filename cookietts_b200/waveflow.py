@@ -61,20 +61,27 @@ class WaveFlowPackConfig:
     mix_first: bool = True
     mixing_conv: bool = False    # channel_mixing='1x1conv'
     cond_external: bool = False  # the WN cond path is evaluated by the module (cwg_wf_weights.c_all): no cond columns in w1
+    sep_dw: bool = False         # fp32 mode: separable in_layers stay separable (cwg_wf_weights.dw_w / dw_b + a 1x1 GEMM)
+
+    @property
+    def kx(self) -> int:
+        """x columns of w1: the dense kh*kw*C taps, or the C pointwise inputs of a separable in_layer"""
+        return self.n_channels if self.sep_dw else self.kernel_h * self.kernel_w * self.n_channels
 
     @property
     def k1(self) -> int:
         if self.cond_external:
-            return self.kernel_h * self.kernel_w * self.n_channels
-        return self.kernel_h * self.kernel_w * self.n_channels + (self.n_mel if self.fp32 else COND_PAD)
+            return self.kx
+        return self.kx + (self.n_mel if self.fp32 else COND_PAD)
 
 
 def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dict[str, np.ndarray]:
     """fp64 folding of weight-norm, the WN_2d cond layer (extra K columns on the interpolated mel)
     and `end` (into the skip half), to the arrays of `cwg_wf_weights` (include/cwg.h)."""
     F, L, Cc, kh, kw, M = cfg.n_flows, cfg.n_layers, cfg.n_channels, cfg.kernel_h, cfg.kernel_w, cfg.n_mel
-    K1, N2 = cfg.k1, Cc + EO_PAD
+    K1, N2, KX = cfg.k1, Cc + EO_PAD, cfg.kx
     w1 = np.zeros((F, L, 2 * Cc, K1)); b1 = np.zeros((F, L, 2 * Cc))
+    dw_w = np.zeros((F, L, Cc, kh * kw)); dw_b = np.zeros((F, L, Cc))
     w2 = np.zeros((F, L, N2, Cc)); b2 = np.zeros((F, L, Cc)); eo_b = np.zeros((F, EO_PAD))
     start_w = np.zeros((F, Cc)); start_b = np.zeros((F, Cc))
     E = int(cfg.wn_speaker_dim)
@@ -96,10 +103,16 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
         w_end = _np(sd[p + "end.weight"])[:, :, 0, 0]                      # [2, C]  (log_s, t)
         eo_bias = _np(sd[p + "end.bias"]).copy()
         for i in range(L):
-            w_in, b_in = in_layer_weight_bias(sd, p + f"in_layers.{i}")    # [2C, C, kh, kw]
-            w1[k, i, :, :kh * kw * Cc] = w_in.transpose(0, 2, 3, 1).reshape(2 * Cc, kh * kw * Cc)   # col (a*kw+b)*C + c
+            if cfg.sep_dw:                                                 # depthwise stays a depthwise kernel, pointwise is the GEMM
+                dw_w[k, i] = effective_weight(sd, p + f"in_layers.{i}.0")[:, 0].reshape(Cc, kh * kw)
+                dw_b[k, i] = _np(sd[p + f"in_layers.{i}.0.bias"])
+                w1[k, i, :, :Cc] = effective_weight(sd, p + f"in_layers.{i}.1")[:, :, 0, 0]
+                b_in = _np(sd[p + f"in_layers.{i}.1.bias"])
+            else:
+                w_in, b_in = in_layer_weight_bias(sd, p + f"in_layers.{i}")    # [2C, C, kh, kw]
+                w1[k, i, :, :kh * kw * Cc] = w_in.transpose(0, 2, 3, 1).reshape(2 * Cc, kh * kw * Cc)   # col (a*kw+b)*C + c
             if not cfg.cond_external:
-                w1[k, i, :, kh * kw * Cc:kh * kw * Cc + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
+                w1[k, i, :, KX:KX + M] = w_c[2 * Cc * i:2 * Cc * (i + 1)]
             b1[k, i] = b_in + b_c[2 * Cc * i:2 * Cc * (i + 1)]
             if cfg.res_skip:
                 w_rs = effective_weight(sd, p + f"res_skip_layers.{i}")[:, :, 0, 0]
@@ -121,6 +134,8 @@ def pack_waveflow_state_dict(sd, cfg: WaveFlowPackConfig, cond_fold=None) -> Dic
            "w1_f64": w1, "w2_f64": w2}
     if E and not cfg.cond_external:
         out["spk_w"], out["spk_embed"] = spk_w, np.stack(spk_embed)
+    if cfg.sep_dw:
+        out["dw_w"], out["dw_b"] = dw_w.astype(np.float32), dw_b.astype(np.float32)
     if cfg.mixing_conv:                                        # W^-1 of every InvertibleConv1x1, padded to [F][32][32]
         winv = np.zeros((F, 32, 32))
         for k in range(F):
@@ -146,7 +161,7 @@ WF_WEIGHT_FIELDS = ("w1_hi", "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "eo_b", "sta
 
 
 class CwgWfWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch", "winv", "c_all")]
+    _fields_ = [(n, C.c_void_p) for n in WF_WEIGHT_FIELDS + ("b1_batch", "winv", "c_all", "dw_w", "dw_b")]
 
 
 def _bind(lib):
@@ -185,7 +200,7 @@ class _WN2d(nn.Module):
             d = dilations_w[i] if dilations_w else 2 ** i
             dh = dilations_h[i] if dilations_h else 1
             pad = (0, ((kernel_w - 1) * d) // 2)
-            if not seperable_conv:
+            if not seperable_conv or (kernel_h == 1 and kernel_w == 1):      # glow_ax.py:520
                 self.in_layers.append(wn(nn.Conv2d(n_channels, 2 * n_channels, (kernel_h, kernel_w), dilation=(dh, d), padding=pad), name="weight"))
             else:                                            # glow_ax.py:525-531
                 self.in_layers.append(nn.Sequential(
@@ -257,7 +272,8 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
             gate=v["gate"], dilations_w=v["dilations_w"], dilations_h=v["dilations_h"], res_skip=v["res_skip"],
             merge_res_skip=v["merge"], wn_speaker_dim=v["speaker_dim"], n_early_every=v["n_early_every"],
             n_early_size=v["n_early_size"], mix_first=v["mix_first"], mixing_conv=v["mixing_conv"],
-            cond_external=v["cond_external"])
+            cond_external=v["cond_external"],
+            sep_dw=bool(wn.get("seperable_conv")) and precision == "ffma" and (wn["kernel_size_h"], wn["kernel_size_w"]) != (1, 1))
         self.WN = nn.ModuleList([_Coupling(n_layers=wn["n_layers"], n_channels=wn["n_channels"],
                                            kernel_h=wn["kernel_size_h"], kernel_w=wn["kernel_size_w"],
                                            cond_in_channels=self.wn_cond_in_channels,
@@ -377,7 +393,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
         pk = pack_waveflow_state_dict(sd, self.pack_config, cond_fold=self.group_conv_fold if self._fe_group else None)
         dev_pk = {}
-        for name in WF_WEIGHT_FIELDS + ("spk_w", "spk_embed", "winv"):
+        for name in WF_WEIGHT_FIELDS + ("spk_w", "spk_embed", "winv", "dw_w", "dw_b"):
             if name not in pk:
                 continue
             arr = pk[name]
@@ -385,7 +401,7 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                 arr = arr.view(np.int16)
             dev_pk[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
         w = CwgWfWeights()
-        for f in WF_WEIGHT_FIELDS + ("winv",):
+        for f in WF_WEIGHT_FIELDS + ("winv", "dw_w", "dw_b"):
             setattr(w, f, dev_pk[f].data_ptr() if f in dev_pk else None)
         pc = self.pack_config
         self._ccfg = CwgWfConfig(pc.n_mel, pc.n_flows, pc.n_group, pc.n_layers, pc.n_channels, pc.kernel_h, pc.kernel_w,

@@ -294,6 +294,12 @@ typedef struct cwg_wf_weights {
    * cond stacks, a WN-level TransposedUpsampleNet (glow_ax.py:476-505,:565-579) - as [F][batch][2*C*L][T'] fp32.  When set,
    * w1_f32 has no cond columns (K1 = kernel_h*kernel_w*C), b1 holds the in_layer biases only and `mel` is not read. */
   const float*    c_all;
+  /* ABI 5, CWG_MODE_FFMA, optional: depthwise-separable in_layers (glow_ax.py:525-531) kept separable instead of folded to a
+   * dense kernel_h x kernel_w conv (the layout of the reference author's trained checkpoints: 7x7 -> 49x fewer MACs).
+   * dw_w [F][L][C][kernel_h*kernel_w], dw_b [F][L][C]: the depthwise conv; w1_f32 is then [F][L][2C][C + n_mel]
+   * (pointwise weights | cond layer), b1 the pointwise + cond biases. */
+  const float*    dw_w;
+  const float*    dw_b;
 } cwg_wf_weights;
 
 size_t cwg_wf_workspace_bytes(const cwg_wf_config* cfg, int mode, int batch, int frames, int t_samples);

@@ -60,7 +60,7 @@ if True:
         out = m.infer(torch.from_numpy(g["mel"]).cuda(), speaker_ids=ids, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
         torch.cuda.synchronize()
         print(name, float(np.abs(out.numpy() - g["infer_ref_fp64"]).max()), flush=True)
-    for name in ("waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker", "waveflow_v_early", "waveflow_v_mixlast",
+    for name in ("waveflow_sep7", "waveflow_v_gate", "waveflow_v_merge", "waveflow_v_noskip", "waveflow_v_speaker", "waveflow_v_early", "waveflow_v_mixlast",
                  "waveflow_v_conv", "waveflow_v_conv_mixlast", "waveflow_v_cond", "waveflow_v_tconv"):
         g = np.load(f"tests/golden/{name}.npz")
         cfg = WaveFlowConfig(**json.loads(str(g["config"])))
