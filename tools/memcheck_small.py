@@ -56,7 +56,7 @@ if True:
         cfg = AxConfig(**json.loads(str(g["config"])))
         m = WaveGlowAx(precision="ffma", **reference_kwargs_ax1d(cfg))
         m.load_state_dict({k: torch.from_numpy(v) for k, v in ax_sd(cfg, int(g["weight_seed"])).items()}); m = m.cuda().eval()
-        ids = torch.from_numpy(g["speaker_ids"]).cuda() if g["speaker_ids"].size else None
+        ids = torch.from_numpy(g["speaker_ids"]).cuda() if "speaker_ids" in g.files and g["speaker_ids"].size else None
         out = m.infer(torch.from_numpy(g["mel"]).cuda(), speaker_ids=ids, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
         torch.cuda.synchronize()
         print(name, float(np.abs(out.numpy() - g["infer_ref_fp64"]).max()), flush=True)
@@ -66,7 +66,7 @@ if True:
         cfg = WaveFlowConfig(**json.loads(str(g["config"])))
         m = WaveFlow(precision="ffma", graphs=False, **reference_kwargs(cfg))
         m.load_state_dict({k: torch.from_numpy(v) for k, v in wf_sd(cfg, int(g["weight_seed"])).items()}); m = m.cuda().eval()
-        ids = torch.from_numpy(g["speaker_ids"]).cuda() if g["speaker_ids"].size else None
+        ids = torch.from_numpy(g["speaker_ids"]).cuda() if "speaker_ids" in g.files and g["speaker_ids"].size else None
         out = m.infer(torch.from_numpy(g["mel"]).cuda(), speaker_ids=ids, sigma=float(g["sigma"]), z=torch.from_numpy(g["z"]).cuda())
         torch.cuda.synchronize()
         print(name, float(np.abs(out.numpy() - g["infer_ref_fp64"]).max()), flush=True)
