@@ -21,7 +21,8 @@ profiles/r2_ncu.json when its source hash matches; `cpu_baseline` / `--impl refe
 `WaveGlow.infer` (oracle/_ref, an unmodified copy of glow.py) on this box's host cores on a bounded sample;
 `extra_configs` = 3-step runs of BASELINE configs 3 (bf16, 256 x 10 s over the ranks), 4 (512-channel model, 60 s in
 halo-overlapped chunks) and 5 (WaveFlow) at the same GPU count, config 1's per-call latency and the per-call latency of
-the one model the reference itself records a speed for (its speed-test notebook's 48-flow ax WaveGlow, `--config 6`);
+the one model the reference itself records a speed for (its speed-test notebook's 48-flow ax WaveGlow, `--config 6`), and the
+per-call latency of WaveFlow in the layout of the author's trained checkpoints (h = 20, separable 7x7; fp32 CUDA-core mode);
 `--no-extra` skips them, `--config N` runs one alone.
 """
 from __future__ import annotations
@@ -574,6 +575,49 @@ def run_notebook_latency(args):
             "xrt": samples / (ms * 1e-3) / sr, "xrt_sample_rate": sr, "output_finite": finite}
 
 
+def run_waveflow_trained_latency(args):
+    """WaveFlow in the layout of the reference author's trained checkpoints (SURVEY 8d config-5 note: squeeze height 20, 8 flows,
+    WN_2d 8 x 128 with depthwise-separable 7x7 in_layers; `scripts/WaveGlow from Ground Truth.ipynb` cell 2), batch 1, one
+    4.6-s utterance at 48 kHz (736 mel frames of hop 300): per-call latency of infer() in the fp32 CUDA-core mode - the
+    tensor-core WaveFlow kernels are specialised for the 3x3 / height-16 model of BASELINE config 5."""
+    import torch
+    from cookietts_b200 import WaveFlow
+    from cookietts_b200.synthetic import WaveFlowConfig, waveflow_state_dict, waveflow_reference_kwargs
+    world, rank, local_rank, dev = dist_setup()
+    cfg = WaveFlowConfig(n_group=20, kernel_size_h=7, kernel_size_w=7, seperable_conv=True, win_length=1200, hop_length=300)
+    model = WaveFlow(precision="ffma", **waveflow_reference_kwargs(cfg))
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in waveflow_state_dict(cfg, 3).items()})
+    model = model.to(dev).eval()
+    frames, sr = 736, 48000
+    g = torch.Generator().manual_seed(1)
+    mel = (torch.randn(1, 80, frames, generator=g) * 2.0 - 5.0).clamp_(-11.5129, 2.0).to(dev)
+    z = torch.randn(1, frames * cfg.hop_length, generator=g).to(dev)
+    for _ in range(3):                                # the third call of a shape replays its CUDA graph
+        out = model.infer(mel, sigma=0.666, return_CPU=False, z=z)
+    torch.cuda.synchronize()
+    n = 3
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(n):
+        out = model.infer(mel, sigma=0.666, return_CPU=False, z=z)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / n
+    samples, finite = int(out.shape[1]), bool(torch.isfinite(out).all())
+    # per call: mel interpolation, then per flow h row kernels and (h - 1) x L x (depthwise, GEMM1, gate, GEMM2) - cwg_wf_ffma.cu
+    launches = 1 + cfg.n_flows * (cfg.n_group + (cfg.n_group - 1) * cfg.n_layers * 4)
+    del model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": n, "ms_per_step": ms, "scaling": "replicas",
+            "dtype": "f32 (CUDA cores)", "gpu_launches": launches,
+            "config": {"workload": "WaveFlow in the trained-checkpoint layout (h = 20, 8 flows, WN_2d 8 x 128, depthwise-separable "
+                                   "7x7 in_layers kept separable), 1 x 736 mel frames (4.6 s at 48 kHz) per call, sigma 0.666, "
+                                   "injected z: per-call latency of infer(), CUDA-graph replay"},
+            "xrt": samples / (ms * 1e-3) / sr, "xrt_sample_rate": sr, "output_finite": finite}
+
+
 def with_extra_configs(args, line, rank):
     """Short (3-step) runs of BASELINE configs 3, 4 and 5 at this run's GPU count, attached to the headline line as
     `extra_configs` (still ONE JSON line), plus the headline workload in the 3-pass `bf16x3` mode.  A watchdog prints the headline without them if they overrun."""
@@ -594,7 +638,8 @@ def with_extra_configs(args, line, rank):
                          ("config2_bf16x3", run_waveglow, dict(config=2, precision="bf16x3")),
                          ("config3", run_waveglow, dict(config=3)), ("config4", run_longform, dict(config=4)),
                          ("config5", run_waveflow, dict(config=5, workload="waveflow")),
-                         ("notebook_ax_latency", run_notebook_latency, dict(config=6))):
+                         ("notebook_ax_latency", run_notebook_latency, dict(config=6)),
+                         ("waveflow_trained_layout_latency", run_waveflow_trained_latency, dict(config=6))):
         a = copy.copy(args)
         a.steps, a.warmup, a.no_cpu_baseline, a.precision = 3, 3, True, "bf16"
         for k, v in kw.items():
