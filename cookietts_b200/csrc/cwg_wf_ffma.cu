@@ -15,7 +15,7 @@
 namespace cwg {
 namespace {
 
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 128, GN = 64, GK = 16;
 constexpr int WFF_MAX_GROUP = 32;
 
 struct WffGemmP {
@@ -31,57 +31,90 @@ struct WffGemmP {
   const float* acts; const float* x_cur; float* x_next; float* eo; const float* eo_b; int first;
 };
 
-template <int MODE>     // 0: GEMM1, 1: GEMM2
-__device__ __forceinline__ float wff_a(const WffGemmP& p, long long m, int kk) {
-  if (m >= p.BT || kk >= p.K) return 0.f;
-  if (MODE == 1) return __ldg(p.acts + (size_t)m * p.C + kk);
+// Eight consecutive k (k1 .. k1+7) of row m of the implicit A matrix.  MODE 0 (GEMM1): k = ((a * KW + b) * C + c) over the
+// conv-queue rows a (causal in height, zero queue: glow_ax.py:597-602) and width taps b ('same' zero padding), then the M cond
+// columns; channels are contiguous in memory, so the (a, b) decomposition is redone only when a run crosses a tap.
+// MODE 1 (GEMM2): k = channel of acts.
+template <int MODE>
+__device__ __forceinline__ void wff_a8(const WffGemmP& p, long long m, int k1, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (m >= p.BT) return;
+  if (MODE == 1) {
+    const float* src = p.acts + (size_t)m * p.C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (k1 + i < p.K) v[i] = __ldg(src + k1 + i);
+    return;
+  }
   const int kx = p.KH * p.KW * p.C;
-  if (kk >= kx) return __ldg(p.mel + (size_t)m * p.M + (kk - kx));
-  const int a = kk / (p.KW * p.C), rem = kk - a * p.KW * p.C;
-  const int b = rem / p.C, c = rem - b * p.C;
-  const int src_row = p.row - (p.KH - 1 - a) * p.dil_h;           // causal in height: padding_h = (kernel_h - 1) * dilation_h on top
-  if (src_row < 0) return 0.f;                                    // the zero-initialised conv queue (glow_ax.py:597-602)
   const long long ub = m / p.Tp; const int t = (int)(m - ub * p.Tp);
-  const int tt = t + (b - p.KW / 2) * p.dil;                      // 'same' zero padding in width
-  if (tt < 0 || tt >= p.Tp) return 0.f;
-  return __ldg(p.ring + ((size_t)(src_row % p.ring_rows) * p.BT + (size_t)ub * p.Tp + tt) * p.C + c);
+  int seg = -1, c = 0; const float* src = nullptr;          // current (a, b) tap: base pointer of its channel run, or NULL = zeros
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kk = k1 + i;
+    if (kk >= p.K) break;
+    if (kk >= kx) { v[i] = __ldg(p.mel + (size_t)m * p.M + (kk - kx)); continue; }
+    if (seg < 0 || c >= p.C) {
+      seg = kk / p.C; c = kk - seg * p.C;
+      const int a = seg / p.KW, b = seg - a * p.KW;
+      const int src_row = p.row - (p.KH - 1 - a) * p.dil_h;
+      const int tt = t + (b - p.KW / 2) * p.dil;
+      src = (src_row < 0 || tt < 0 || tt >= p.Tp) ? nullptr
+            : p.ring + ((size_t)(src_row % p.ring_rows) * p.BT + (size_t)ub * p.Tp + tt) * p.C;
+    }
+    if (src) v[i] = __ldg(src + c);
+    ++c;
+  }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_wff_gemm(WffGemmP p) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Bs[GK][GN + 4];
+// 128 x 64 block tile, 256 threads, 8 rows (m = tx*4 + i and 64 + tx*4 + i) x 4 columns per thread, LDS.128 operand reads,
+// the next k-tile fetched into registers while the current one is multiplied.
+template <int MODE>     // 0: GEMM1, 1: GEMM2
+__global__ void __launch_bounds__(256, 2) k_wff_gemm(WffGemmP p) {
+  __shared__ __align__(16) float As[GK][GM + 4];
+  __shared__ __align__(16) float Bs[GK][GN + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const long long m0 = (long long)blockIdx.x * GM;
   const int n0 = blockIdx.y * GN;
-  float acc[4][4] = {};
+  float acc[8][4] = {};
+  const int a_row = tid >> 1, a_k = (tid & 1) * 8;           // A: row a_row, k a_k .. a_k+7 of the tile
+  const int b_n = tid >> 2, b_k = (tid & 3) * 4;             // B: row b_n, k b_k .. b_k+3
+  float ra[8], rb[4];
+  auto fetch = [&](int k0) {
+    wff_a8<MODE>(p, m0 + a_row, k0 + a_k, ra);
+    const float* wr = p.W + (size_t)(n0 + b_n) * p.K + k0 + b_k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rb[i] = (n0 + b_n < p.N && k0 + b_k + i < p.K) ? __ldg(wr + i) : 0.f;
+  };
+  fetch(0);
   for (int k0 = 0; k0 < p.K; k0 += GK) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int idx = tid + r * 256, row = idx / GK, kk = idx % GK;
-      As[kk][row] = wff_a<MODE>(p, m0 + row, k0 + kk);
-      Bs[kk][row] = (n0 + row < p.N && k0 + kk < p.K) ? __ldg(p.W + (size_t)(n0 + row) * p.K + k0 + kk) : 0.f;
-    }
+    for (int i = 0; i < 8; ++i) As[a_k + i][a_row] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[b_k + i][b_n] = rb[i];
     __syncthreads();
+    if (k0 + GK < p.K) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      float a[4], b[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + tx * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
     if (m >= p.BT) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + ty * 4 + j;
       if (n >= p.N) continue;
       if (MODE == 0) {
         const long long ub = m / p.Tp;
