@@ -177,6 +177,9 @@ def _bind(lib):
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
     lib.cwg_wf_infer_profiled.restype = C.c_int
     lib.cwg_wf_infer_profiled.argtypes = lib.cwg_wf_infer.argtypes + [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+    lib.cwg_ax_speaker_bias.restype = C.c_int
+    lib.cwg_ax_speaker_bias.argtypes = [C.POINTER(_cabi.CwgConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.cwg_wf_layer.restype = C.c_int
     lib.cwg_wf_layer.argtypes = [C.POINTER(CwgWfConfig), C.POINTER(CwgWfWeights), C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -493,9 +496,6 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                 if int(ids.min()) < 0 or int(ids.max()) >= 512:
                     raise IndexError("speaker id out of range [0, 512)")
                 pc = self.pack_config
-                lib.cwg_ax_speaker_bias.restype = C.c_int
-                lib.cwg_ax_speaker_bias.argtypes = [C.POINTER(_cabi.CwgConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
                 dims = _cabi.CwgConfig(n_mel=pc.n_mel, n_flows=pc.n_flows, n_group=pc.n_group, n_early_every=pc.n_flows, n_early_size=2,
                                        win_length=pc.hop_length, hop_length=pc.hop_length, n_layers=pc.n_layers,
                                        n_channels=pc.n_channels, kernel_size=pc.kernel_w, cond_hidden=pc.n_mel)
