@@ -145,6 +145,8 @@ AX_CASES = {
     # ... and with a scale product (3 x 2 = 6) != hop / n_group (4): the upsampled cond is interpolated to T'
     "waveglow_axv_tconv_interp": (dict(_V, n_group=4, hop_length=16, upsample_first=False, wn_tconv_scales=[3, 2],
                                        wn_tconv_hidden_dim=6, wn_tconv_kernel_size=[5, 4]), 1, 6, 0.9, 67, 17),
+    # n_group beyond the packed kernels' 32 (hop 80 / n_group 40), plain GTU WN: general mode by n_group alone
+    "waveglow_axv_group40": (dict(_V, n_group=40, hop_length=80, win_length=320, n_early_every=2, n_early_size=4), 2, 5, 0.9, 68, 18),
     # every remaining unit on one tiny model each (one flow pair, 2 layers)
     **{f"waveglow_axv_unit_{u.lower()}": (dict(_V, n_flows=2, n_early_every=4, n_layers=2, gated_unit=u), 1, 5, 0.9, 70 + i, 20 + i)
        for i, u in enumerate(["GTRU", "TTU", "STU", "GTSU", "GSIU", "GSIRU", "GTSRU", "GSIRLRU", "GSIRRLRU"])},

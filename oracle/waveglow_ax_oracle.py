@@ -72,7 +72,7 @@ class AxConfig:
     def is_variant(self) -> bool:
         return (self.gated_unit.upper() != "GTU" or self.dilations_w is not None or not self.res_skip or self.merge_res_skip
                 or self.wn_cond_layers != 1 or self.wn_cond_kernel_size != 1 or self.wn_cond_activation_func.lower() != "none"
-                or bool(self.wn_tconv_scales))
+                or bool(self.wn_tconv_scales) or self.n_group > 32)
 
     def flow_channels(self) -> List[int]:
         out, n_rem = [], self.n_group

@@ -70,7 +70,7 @@ def test_ax_1d_oracle_matches_reference(name):
 
 
 AXV_CASES = ["waveglow_axv_gsirru", "waveglow_axv_merge", "waveglow_axv_noskip", "waveglow_axv_cond", "waveglow_axv_256",
-             "waveglow_axv_tconv_crop", "waveglow_axv_tconv_interp"] + [
+             "waveglow_axv_tconv_crop", "waveglow_axv_tconv_interp", "waveglow_axv_group40"] + [
     "waveglow_axv_unit_" + u for u in ("gtru", "ttu", "stu", "gtsu", "gsiu", "gsiru", "gtsru", "gsirlru", "gsirrlru")]
 
 
