@@ -481,6 +481,11 @@ class WaveFlow(nn.Module, AxFrontEndMixin):
                     cond = self._wn_resample(lib, cond, Tp, stream)
                 pc = self.pack_config
                 need_ch = 2 * pc.n_channels * pc.n_layers
+                nb = 4 * pc.n_flows * B * need_ch * Tp          # all flows' cond tensors live at once (one C call runs every flow)
+                free, _ = torch.cuda.mem_get_info(dev)
+                if nb > free:
+                    raise RuntimeError(f"WaveFlow general cond path: {nb / 2**30:.1f} GiB of cond tensors for batch {B} x {Tp} "
+                                       f"group-steps do not fit the {free / 2**30:.1f} GiB free on the device; split the batch")
                 c_all = torch.empty(pc.n_flows, B, need_ch, Tp, device=dev, dtype=torch.float32)
                 for k in range(pc.n_flows):
                     x = self._wn_cond_apply(lib, cond, self._packed["flows"][k], ids, Tp, stream, k, crop_2d=True)
